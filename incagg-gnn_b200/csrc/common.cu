@@ -1,0 +1,51 @@
+// Library-level entry points and error plumbing.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace incagg {
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count() {
+  static thread_local int cached[16] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace incagg
+
+extern "C" int incagg_version(void) { return 100; }
+
+extern "C" const char* incagg_last_error(void) { return incagg::err_buf(); }
+
+extern "C" int incagg_device_info(int* sm_count_out, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  IA_CUDA(cudaGetDevice(&dev));
+  int n = 0, maj = 0, min_ = 0;
+  IA_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  IA_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  IA_CUDA(cudaDeviceGetAttribute(&min_, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count_out) *sm_count_out = n;
+  if (cc_major) *cc_major = maj;
+  if (cc_minor) *cc_minor = min_;
+  return INCAGG_OK;
+}

@@ -1,0 +1,106 @@
+// Shared helpers for the incagg_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/incagg_b200.h"
+
+namespace incagg {
+
+// ---- error plumbing (thread-local text, C-ABI status codes) ---------------
+char* err_buf();
+int set_err(int code, const char* fmt, ...);
+
+#define IA_CHECK_ARG(cond, ...)                                   \
+  do {                                                            \
+    if (!(cond)) return incagg::set_err(INCAGG_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define IA_CUDA(call)                                                               \
+  do {                                                                              \
+    cudaError_t _e = (call);                                                        \
+    if (_e != cudaSuccess)                                                          \
+      return incagg::set_err(INCAGG_ERR_CUDA, "%s failed: %s (%s:%d)", #call,        \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);           \
+  } while (0)
+
+#define IA_LAUNCH_CHECK()                                                           \
+  do {                                                                              \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess)                                                          \
+      return incagg::set_err(INCAGG_ERR_CUDA, "kernel launch failed: %s (%s:%d)",    \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);           \
+  } while (0)
+
+inline cudaStream_t as_stream(incagg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();  // cached SM count of the current device (148 on B200)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+
+// ---- device helpers --------------------------------------------------------
+// Streaming (read-once) loads that do not pollute L1: index/value arrays.
+__device__ __forceinline__ int ldg_stream(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Inclusive warp scan.
+template <typename T>
+__device__ __forceinline__ T warp_scan_incl(T v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+
+// Block-wide exclusive scan for blockDim.x == BLOCK (multiple of 32, <= 1024).
+// Returns the exclusive prefix of `v`; *total receives the block sum.
+template <typename T, int BLOCK>
+__device__ __forceinline__ T block_scan_excl(T v, T* total) {
+  __shared__ T warp_tot[BLOCK / 32];
+  __shared__ T block_tot;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T incl = warp_scan_incl(v);
+  if (lane == 31) warp_tot[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    T t = (lane < BLOCK / 32) ? warp_tot[lane] : T(0);
+    T ti = warp_scan_incl(t);
+    if (lane < BLOCK / 32) warp_tot[lane] = ti - t;  // exclusive warp offsets
+    if (lane == 31) block_tot = ti;
+  }
+  __syncthreads();
+  T out = incl - v + warp_tot[w];
+  *total = block_tot;
+  __syncthreads();  // shared arrays may be reused by the next call
+  return out;
+}
+
+// ---- device-wide exclusive scan over int64 counts (3-phase, deterministic) --
+// Used by relabel / transpose.  `scratch` needs scan_scratch_elems(n) int64 slots.
+constexpr int SCAN_BLOCK = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+inline int64_t scan_num_tiles(int64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+}  // namespace incagg

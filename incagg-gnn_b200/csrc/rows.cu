@@ -1,0 +1,254 @@
+// History gather / scatter / slice copies (sm_100a).
+//
+// Replaces History.pull/push (history.py:33-65) and the copy loops of read_async / write_async
+// (csrc/cuda/async_cuda.cu:61-111,139-163).  Pure data movement: every byte is read once and
+// written once, so the design is vector width + requests in flight:
+//   * rows are moved as 16/8/4-byte vectors (widest the alignment allows), consecutive lanes
+//     take consecutive vectors of a row -> full 128 B sectors per warp request;
+//   * each thread moves UNROLL vectors per trip, loads first and stores after, so UNROLL
+//     independent 128-bit requests per lane are in flight (what hides HBM, and PCIe for
+//     pinned-host sources, latency);
+//   * the gather source may be pinned host memory: the kernel then reads it through UVA, which
+//     replaces the reference's CPU index_select into a pinned bounce buffer + H2D copy;
+//   * contiguous slices between pinned host memory and the device go through cudaMemcpyAsync
+//     (DMA engines, overlappable with kernels); device<->device slices use one kernel launch
+//     for up to 64 slices instead of one memcpy per slice.
+#include "common.cuh"
+
+namespace incagg {
+
+template <int VB> struct Bytes;
+template <> struct Bytes<16> { using type = uint4; };
+template <> struct Bytes<8> { using type = uint2; };
+template <> struct Bytes<4> { using type = uint32_t; };
+
+constexpr int ROWS_THREADS = 256;
+constexpr int ROWS_UNROLL = 4;
+
+// mode 0: dst[i] = src[idx[i]]   mode 1: dst[idx[i]] = src[i]
+template <int VB, int MODE>
+__global__ void __launch_bounds__(ROWS_THREADS)
+index_rows_kernel(const char* __restrict__ src, int64_t src_ld, const int64_t* __restrict__ idx,
+                  int64_t n, char* __restrict__ dst, int64_t dst_ld, int nvec, int64_t limit_rows) {
+  using V = typename Bytes<VB>::type;
+  const int64_t total = n * nvec;
+  const int64_t stride = (int64_t)gridDim.x * ROWS_THREADS;
+  int64_t t = (int64_t)blockIdx.x * ROWS_THREADS + threadIdx.x;
+  for (; t < total; t += stride * ROWS_UNROLL) {
+    V v[ROWS_UNROLL];
+    int64_t doff[ROWS_UNROLL];
+#pragma unroll
+    for (int u = 0; u < ROWS_UNROLL; ++u) {
+      const int64_t g = t + u * stride;
+      doff[u] = -1;
+      if (g < total) {
+        const int64_t r = g / nvec;
+        const int c = (int)(g - r * nvec);
+        const int64_t j = idx[r];
+        if (j >= 0 && j < limit_rows) {
+          const int64_t srow = (MODE == 0) ? j : r;
+          const int64_t drow = (MODE == 0) ? r : j;
+          v[u] = *reinterpret_cast<const V*>(src + srow * src_ld + (int64_t)c * VB);
+          doff[u] = drow * dst_ld + (int64_t)c * VB;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS_UNROLL; ++u)
+      if (doff[u] >= 0) *reinterpret_cast<V*>(dst + doff[u]) = v[u];
+  }
+}
+
+constexpr int MAX_SLICES = 64;
+struct SliceTable {
+  int64_t off[MAX_SLICES];          // row offset in the strided (history) tensor
+  int64_t prefix[MAX_SLICES + 1];   // row offset in the packed tensor
+  int k;
+};
+
+// direction 0: packed dst <- strided src slices; direction 1: strided dst slices <- packed src
+template <int VB>
+__global__ void __launch_bounds__(ROWS_THREADS)
+slice_rows_kernel(const char* __restrict__ src, int64_t src_ld, char* __restrict__ dst,
+                  int64_t dst_ld, int nvec, int direction, const SliceTable tab) {
+  using V = typename Bytes<VB>::type;
+  const int64_t total = tab.prefix[tab.k] * nvec;
+  const int64_t stride = (int64_t)gridDim.x * ROWS_THREADS;
+  int64_t t = (int64_t)blockIdx.x * ROWS_THREADS + threadIdx.x;
+  for (; t < total; t += stride * ROWS_UNROLL) {
+    V v[ROWS_UNROLL];
+    int64_t doff[ROWS_UNROLL];
+#pragma unroll
+    for (int u = 0; u < ROWS_UNROLL; ++u) {
+      const int64_t g = t + u * stride;
+      doff[u] = -1;
+      if (g < total) {
+        const int64_t r = g / nvec;  // packed row
+        const int c = (int)(g - r * nvec);
+        int lo = 0, hi = tab.k;      // slice i with prefix[i] <= r < prefix[i+1]
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (tab.prefix[mid] <= r) lo = mid; else hi = mid;
+        }
+        const int64_t strided = tab.off[lo] + (r - tab.prefix[lo]);
+        const int64_t srow = direction == 0 ? strided : r;
+        const int64_t drow = direction == 0 ? r : strided;
+        v[u] = *reinterpret_cast<const V*>(src + srow * src_ld + (int64_t)c * VB);
+        doff[u] = drow * dst_ld + (int64_t)c * VB;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS_UNROLL; ++u)
+      if (doff[u] >= 0) *reinterpret_cast<V*>(dst + doff[u]) = v[u];
+  }
+}
+
+static int pick_vb(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t row_bytes) {
+  auto ok = [&](int vb) {
+    return row_bytes % vb == 0 && lda % vb == 0 && ldb % vb == 0 &&
+           reinterpret_cast<uintptr_t>(a) % vb == 0 && reinterpret_cast<uintptr_t>(b) % vb == 0;
+  };
+  return ok(16) ? 16 : (ok(8) ? 8 : 4);
+}
+
+static int grid_for(int64_t total_vec) {
+  const int64_t per_block = (int64_t)ROWS_THREADS * ROWS_UNROLL;
+  int64_t want = (total_vec + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)sm_count() * 16;  // 16 CTAs of 256 threads = 2 full waves / SM
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+template <int MODE>
+static int index_rows(const void* src, int64_t src_ld, const int64_t* idx, int64_t n, void* dst,
+                      int64_t dst_ld, int64_t row_bytes, int64_t limit_rows, cudaStream_t st) {
+  IA_CHECK_ARG(n >= 0 && row_bytes >= 0, "negative size");
+  if (n == 0 || row_bytes == 0) return INCAGG_OK;
+  IA_CHECK_ARG(src && dst && idx, "NULL argument");
+  IA_CHECK_ARG(row_bytes % 4 == 0, "row_bytes must be a multiple of 4 (got %lld)", (long long)row_bytes);
+  IA_CHECK_ARG(src_ld >= row_bytes && dst_ld >= row_bytes, "leading dimension smaller than a row");
+  IA_CHECK_ARG(src_ld % 4 == 0 && dst_ld % 4 == 0, "leading dimensions must be multiples of 4 bytes");
+  const int vb = pick_vb(src, src_ld, dst, dst_ld, row_bytes);
+  const int64_t nvec64 = row_bytes / vb;
+  IA_CHECK_ARG(nvec64 <= 0x7fffffff, "row too wide");
+  const int nvec = (int)nvec64;
+  const int grid = grid_for(n * nvec64);
+  const char* s = static_cast<const char*>(src);
+  char* d = static_cast<char*>(dst);
+  if (vb == 16)
+    index_rows_kernel<16, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+  else if (vb == 8)
+    index_rows_kernel<8, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+  else
+    index_rows_kernel<4, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}
+
+static bool is_host_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;  // unregistered pageable memory
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeUnregistered;
+}
+
+}  // namespace incagg
+
+using namespace incagg;
+
+extern "C" int incagg_gather_rows(const void* src, int64_t src_ld_bytes, int64_t src_rows,
+                                  const int64_t* idx, int64_t n, void* dst, int64_t dst_ld_bytes,
+                                  int64_t row_bytes, incagg_stream_t stream) {
+  return index_rows<0>(src, src_ld_bytes, idx, n, dst, dst_ld_bytes, row_bytes, src_rows,
+                       as_stream(stream));
+}
+
+extern "C" int incagg_scatter_rows(const void* src, int64_t src_ld_bytes, const int64_t* idx,
+                                   int64_t n, void* dst, int64_t dst_ld_bytes, int64_t dst_rows,
+                                   int64_t row_bytes, incagg_stream_t stream) {
+  return index_rows<1>(src, src_ld_bytes, idx, n, dst, dst_ld_bytes, row_bytes, dst_rows,
+                       as_stream(stream));
+}
+
+extern "C" int incagg_copy_slices(const void* src, int64_t src_ld_bytes, int64_t src_rows,
+                                  void* dst, int64_t dst_ld_bytes, int64_t dst_rows,
+                                  const int64_t* offset, const int64_t* count, int64_t k,
+                                  int64_t row_bytes, int direction, incagg_stream_t stream) {
+  IA_CHECK_ARG(k >= 0 && row_bytes >= 0, "negative size");
+  IA_CHECK_ARG(direction == 0 || direction == 1, "direction must be 0 (pull) or 1 (push)");
+  if (k == 0 || row_bytes == 0) return INCAGG_OK;
+  IA_CHECK_ARG(src && dst && offset && count, "NULL argument");
+  IA_CHECK_ARG(row_bytes % 4 == 0, "row_bytes must be a multiple of 4");
+  IA_CHECK_ARG(src_ld_bytes >= row_bytes && dst_ld_bytes >= row_bytes,
+               "leading dimension smaller than a row");
+  IA_CHECK_ARG(src_ld_bytes % 4 == 0 && dst_ld_bytes % 4 == 0,
+               "leading dimensions must be multiples of 4 bytes");
+  // Bounds, as the reference asserts per slice ("Invalid index", async_cuda.cu:78-79,148-149).
+  int64_t packed = 0;
+  for (int64_t i = 0; i < k; ++i) {
+    const int64_t o = offset[i], c = count[i];
+    IA_CHECK_ARG(o >= 0 && c >= 0, "Invalid index (negative offset/count)");
+    const int64_t strided_rows = direction == 0 ? src_rows : dst_rows;
+    const int64_t packed_rows = direction == 0 ? dst_rows : src_rows;
+    IA_CHECK_ARG(o + c <= strided_rows, "Invalid index (slice %lld: %lld+%lld > %lld rows)",
+                 (long long)i, (long long)o, (long long)c, (long long)strided_rows);
+    IA_CHECK_ARG(packed + c <= packed_rows, "Invalid index (packed side too small)");
+    packed += c;
+  }
+  if (packed == 0) return INCAGG_OK;
+  cudaStream_t st = as_stream(stream);
+  const char* s = static_cast<const char*>(src);
+  char* d = static_cast<char*>(dst);
+  if (is_host_ptr(src) || is_host_ptr(dst)) {
+    // Host <-> device: one DMA copy per slice on `stream` (2-D when a side is strided wider
+    // than the row).  cudaMemcpyDefault lets the driver infer the direction from UVA.
+    int64_t p = 0;
+    for (int64_t i = 0; i < k; ++i) {
+      const int64_t o = offset[i], c = count[i];
+      if (c == 0) continue;
+      const char* sp = direction == 0 ? s + o * src_ld_bytes : s + p * src_ld_bytes;
+      char* dp = direction == 0 ? d + p * dst_ld_bytes : d + o * dst_ld_bytes;
+      if (src_ld_bytes == row_bytes && dst_ld_bytes == row_bytes) {
+        IA_CUDA(cudaMemcpyAsync(dp, sp, (size_t)(c * row_bytes), cudaMemcpyDefault, st));
+      } else {
+        IA_CUDA(cudaMemcpy2DAsync(dp, (size_t)dst_ld_bytes, sp, (size_t)src_ld_bytes,
+                                  (size_t)row_bytes, (size_t)c, cudaMemcpyDefault, st));
+      }
+      p += c;
+    }
+    return INCAGG_OK;
+  }
+  // Device <-> device: up to MAX_SLICES slices per launch.
+  const int vb = pick_vb(src, src_ld_bytes, dst, dst_ld_bytes, row_bytes);
+  const int nvec = (int)(row_bytes / vb);
+  int64_t p = 0;
+  for (int64_t i0 = 0; i0 < k; i0 += MAX_SLICES) {
+    SliceTable tab;
+    const int kk = (int)((k - i0) < MAX_SLICES ? (k - i0) : MAX_SLICES);
+    tab.k = kk;
+    tab.prefix[0] = 0;
+    for (int i = 0; i < kk; ++i) {
+      tab.off[i] = offset[i0 + i];
+      tab.prefix[i + 1] = tab.prefix[i] + count[i0 + i];
+    }
+    const int64_t rows_here = tab.prefix[kk];
+    if (rows_here > 0) {
+      // the packed side starts at packed row p for this group of slices
+      const char* sp = direction == 0 ? s : s + p * src_ld_bytes;
+      char* dp = direction == 0 ? d + p * dst_ld_bytes : d;
+      const int grid = grid_for(rows_here * nvec);
+      if (vb == 16)
+        slice_rows_kernel<16><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
+      else if (vb == 8)
+        slice_rows_kernel<8><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
+      else
+        slice_rows_kernel<4><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
+      IA_LAUNCH_CHECK();
+    }
+    p += rows_here;
+  }
+  return INCAGG_OK;
+}

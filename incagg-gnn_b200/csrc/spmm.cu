@@ -1,0 +1,580 @@
+// CSR SpMM family for the IncAgg-GNN propagation hot path (sm_100a).
+//
+//   incagg_spmm_csr     out = reduce_e val[e] * X[col[e]]            (sum/mean/min/max)
+//   incagg_spmm_delta   out = reduce_e val[e] * (x[col[e]] - M_in[g(col[e])]) + M_ag[g(i)]
+//   incagg_spmm_multi   K slabs of X reduced with K different reducers in one launch (PNA)
+//   incagg_spmm_minmax_bwd
+//
+// These replace torch_sparse.matmul / spmm_{sum,mean,min,max} at the call sites listed in
+// include/incagg_b200.h.  The work is HBM/L2-bound gather traffic (<= 0.5 flop/B), so the
+// design is about bytes in flight, not tensor cores:
+//   * one G-lane group per output row (G = 8/16/32 chosen so that G*VEC*NCH covers F with few
+//     idle lanes; F=40 -> two rows per warp, F=128 -> one 512 B row segment per warp load);
+//   * 128-bit (VEC=4) feature loads when rows are 16 B aligned, 64-bit / 32-bit fallbacks;
+//   * col/val of G edges are fetched with one coalesced streaming load and broadcast with
+//     group-masked shuffles; the edge loop is unrolled so each lane keeps >= 4 independent
+//     128-bit loads in flight;
+//   * int32 indices (half the index traffic of the reference's int64 path);
+//   * rows longer than LONG_ROW edges are split across the warps of a CTA by a second
+//     kernel (degree-bucketed scheduling) and combined in a fixed order -> deterministic.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace incagg {
+
+enum { R_SUM = INCAGG_REDUCE_SUM, R_MEAN = INCAGG_REDUCE_MEAN, R_MIN = INCAGG_REDUCE_MIN,
+       R_MAX = INCAGG_REDUCE_MAX, R_RUNTIME = 4 };
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<1> { using type = float; };
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = __ldg(p);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  } else {
+    *p = v[0];
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void store_vec_i(int32_t* p, const int32_t (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<int4*>(p) = make_int4(v[0], v[1], v[2], v[3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<int2*>(p) = make_int2(v[0], v[1]);
+  } else {
+    *p = v[0];
+  }
+}
+
+struct SpmmParams {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* val;
+  const float* X;
+  int64_t ldx;
+  float* out;
+  int64_t ldo;
+  int32_t* arg;
+  int64_t lda;
+  int64_t rows;
+  int32_t F;
+  // delta extras
+  const float* m_in;
+  int64_t ld_in;
+  const float* m_ag;
+  int64_t ld_ag;
+  const int64_t* n_id;
+  // multi extras: slab k = blockIdx.y / tiles_per_slab uses reducers[k]
+  int32_t slab_F;
+  int32_t tiles_per_slab;
+  int32_t reducers[8];
+  // long-row handling
+  int32_t long_row;         // rows with more edges than this are skipped by the main kernel
+  int32_t* long_count;      // device counter of deferred (row, tile) entries
+  int2* long_rows;          // device list of deferred entries {row, blockIdx.y}
+  int32_t long_capacity;
+};
+
+template <int REDUCE>
+__device__ __forceinline__ float red_init(int op) {
+  const int r = (REDUCE == R_RUNTIME) ? op : REDUCE;
+  return r == R_MIN ? FLT_MAX : (r == R_MAX ? -FLT_MAX : 0.f);
+}
+
+// Accumulate one edge's feature vector into acc (and arg) under reducer `op`.
+template <int REDUCE, int VEC, bool ARG>
+__device__ __forceinline__ void red_update(int op, float (&acc)[VEC], int32_t (&arg)[VEC], float v,
+                                           const float (&x)[VEC], int e) {
+  const int r = (REDUCE == R_RUNTIME) ? op : REDUCE;
+  if (r == R_SUM || r == R_MEAN) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = fmaf(v, x[i], acc[i]);
+  } else if (r == R_MIN) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float t = v * x[i];
+      if (t < acc[i]) { acc[i] = t; if (ARG) arg[i] = e; }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float t = v * x[i];
+      if (t > acc[i]) { acc[i] = t; if (ARG) arg[i] = e; }
+    }
+  }
+}
+
+// One G-lane group walks edges [s, e) of one row and accumulates NCH vectors per lane.
+// lane_g: lane index inside the group; gmask: shuffle mask of the group.
+template <int REDUCE, int VEC, int G, int NCH, bool DELTA, bool ARG>
+__device__ __forceinline__ void walk_edges(const SpmmParams& p, int op, int s, int e, int fbase,
+                                           int F, int lane_g, unsigned gmask,
+                                           float (&acc)[NCH][VEC], int32_t (&arg)[NCH][VEC]) {
+  constexpr int UNROLL = (NCH >= 4) ? 2 : 4;
+  for (int base = s; base < e; base += G) {
+    const int my_e = base + lane_g;
+    int my_c = 0;
+    float my_v = 0.f;
+    if (my_e < e) {
+      my_c = ldg_stream(p.col + my_e);
+      my_v = p.val ? ldg_stream(p.val + my_e) : 1.f;
+    }
+    const int cnt = min(G, e - base);
+    int j = 0;
+    for (; j + UNROLL <= cnt; j += UNROLL) {
+      int c[UNROLL];
+      float v[UNROLL];
+      float x[UNROLL][NCH][VEC];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        c[u] = __shfl_sync(gmask, my_c, j + u, G);
+        v[u] = __shfl_sync(gmask, my_v, j + u, G);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const float* xr = p.X + (int64_t)c[u] * p.ldx;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const int f = fbase + (k * G + lane_g) * VEC;
+          if (f < F) {
+            load_vec<VEC>(xr + f, x[u][k]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) x[u][k][i] = 0.f;
+          }
+        }
+      }
+      if constexpr (DELTA) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const int64_t g = p.n_id ? p.n_id[c[u]] : (int64_t)c[u];
+          const float* mr = p.m_in + g * p.ld_in;
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            const int f = fbase + (k * G + lane_g) * VEC;
+            if (f < F) {
+              float m[VEC];
+              load_vec<VEC>(mr + f, m);
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) x[u][k][i] -= m[i];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+          red_update<REDUCE, VEC, ARG>(op, acc[k], arg[k], v[u], x[u][k], base + j + u);
+    }
+    for (; j < cnt; ++j) {
+      const int c = __shfl_sync(gmask, my_c, j, G);
+      const float v = __shfl_sync(gmask, my_v, j, G);
+      const float* xr = p.X + (int64_t)c * p.ldx;
+      const float* mr = nullptr;
+      if constexpr (DELTA) {
+        const int64_t g = p.n_id ? p.n_id[c] : (int64_t)c;
+        mr = p.m_in + g * p.ld_in;
+      }
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int f = fbase + (k * G + lane_g) * VEC;
+        if (f < F) {
+          float x[VEC];
+          load_vec<VEC>(xr + f, x);
+          if constexpr (DELTA) {
+            float m[VEC];
+            load_vec<VEC>(mr + f, m);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) x[i] -= m[i];
+          }
+          red_update<REDUCE, VEC, ARG>(op, acc[k], arg[k], v, x, base + j);
+        }
+      }
+    }
+  }
+}
+
+// Epilogue shared by the short-row and long-row kernels.
+template <int REDUCE, int VEC, int G, int NCH, bool DELTA, bool ARG>
+__device__ __forceinline__ void finish_row(const SpmmParams& p, int op, int64_t row, int deg,
+                                           int fbase, int F, int lane_g, float (&acc)[NCH][VEC],
+                                           int32_t (&arg)[NCH][VEC]) {
+  const int r = (REDUCE == R_RUNTIME) ? op : REDUCE;
+  const float inv = (r == R_MEAN) ? 1.f / (float)max(deg, 1) : 1.f;
+  const float* ag = nullptr;
+  if constexpr (DELTA) {
+    const int64_t g = p.n_id ? p.n_id[row] : row;
+    ag = p.m_ag + g * p.ld_ag;
+  }
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int f = fbase + (k * G + lane_g) * VEC;
+    if (f < F) {
+      float o[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float a = acc[k][i];
+        if (r == R_MEAN) a *= inv;
+        if ((r == R_MIN || r == R_MAX) && deg == 0) a = 0.f;
+        o[i] = a;
+      }
+      if constexpr (DELTA) {
+        float m[VEC];
+        load_vec<VEC>(ag + f, m);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] += m[i];
+      }
+      store_vec<VEC>(p.out + row * p.ldo + f, o);
+      if constexpr (ARG) {
+        if (p.arg) store_vec_i<VEC>(p.arg + row * p.lda + f, arg[k]);
+      }
+    }
+  }
+}
+
+constexpr int SPMM_THREADS = 256;
+
+// Feature tile -> (reducer, first feature, feature limit).  For the multi-aggregator launch
+// blockIdx.y enumerates (slab, tile-in-slab) and a tile never crosses its slab.
+template <int REDUCE, int COVER>
+__device__ __forceinline__ void tile_info(const SpmmParams& p, int y, int& op, int& fbase, int& flim) {
+  if constexpr (REDUCE == R_RUNTIME) {
+    const int slab = y / p.tiles_per_slab;
+    op = p.reducers[slab];
+    fbase = slab * p.slab_F + (y % p.tiles_per_slab) * COVER;
+    flim = min(p.F, (slab + 1) * p.slab_F);
+  } else {
+    op = REDUCE;
+    fbase = y * COVER;
+    flim = p.F;
+  }
+}
+
+// Main kernel: one G-lane group per row, blockIdx.y = feature tile.
+template <int REDUCE, int VEC, int G, int NCH, bool DELTA, bool ARG>
+__global__ void __launch_bounds__(SPMM_THREADS)
+spmm_rows_kernel(const SpmmParams p) {
+  constexpr int GROUPS = SPMM_THREADS / G;
+  const int lane = threadIdx.x & 31;
+  const int lane_g = threadIdx.x % G;
+  const int sub = lane / G;  // group index inside the warp
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
+  const int64_t row = (int64_t)blockIdx.x * GROUPS + threadIdx.x / G;
+  if (row >= p.rows) return;
+
+  int op, fbase, flim;
+  tile_info<REDUCE, G * VEC * NCH>(p, blockIdx.y, op, fbase, flim);
+  const int s = __ldg(p.rowptr + row), e = __ldg(p.rowptr + row + 1);
+  if (e - s > p.long_row) {
+    // Degree bucket "long": defer to spmm_long_rows_kernel (one CTA per entry).  If the list is
+    // full the row is simply processed here.
+    int slot = 0;
+    if (lane_g == 0) slot = atomicAdd(p.long_count, 1);
+    slot = __shfl_sync(gmask, slot, 0, G);
+    if (slot < p.long_capacity) {
+      if (lane_g == 0) p.long_rows[slot] = make_int2((int)row, (int)blockIdx.y);
+      return;
+    }
+  }
+  float acc[NCH][VEC];
+  int32_t arg[NCH][VEC];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { acc[k][i] = red_init<REDUCE>(op); arg[k][i] = -1; }
+  walk_edges<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, s, e, fbase, flim, lane_g, gmask, acc, arg);
+  finish_row<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, row, e - s, fbase, flim, lane_g, acc, arg);
+}
+
+// Long rows: one CTA per deferred (row, feature tile) entry, always 32 lanes per row segment.
+// Each of the 8 warps walks a contiguous slice of the row's edges; partials are combined through
+// shared memory in warp order (deterministic; min/max keep the first winner because warps own
+// increasing edge ranges).  COVER_MAIN is the tile width used by the kernel that deferred the row.
+template <int REDUCE, int VEC, int NCH, int COVER_MAIN, bool DELTA, bool ARG>
+__global__ void __launch_bounds__(SPMM_THREADS)
+spmm_long_rows_kernel(const SpmmParams p) {
+  constexpr int G = 32;
+  constexpr int WARPS = SPMM_THREADS / 32;
+  static_assert(COVER_MAIN <= G * VEC * NCH, "long-row tile must cover the deferring tile");
+  __shared__ float s_acc[WARPS][NCH][32 * VEC];
+  __shared__ int32_t s_arg[ARG ? WARPS : 1][NCH][32 * VEC];
+  const int n_long = min(*p.long_count, p.long_capacity);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
+    const int2 ent = p.long_rows[li];
+    const int64_t row = ent.x;
+    int op, fbase, flim;
+    tile_info<REDUCE, COVER_MAIN>(p, ent.y, op, fbase, flim);
+    flim = min(flim, fbase + COVER_MAIN);
+    const int s = __ldg(p.rowptr + row), e = __ldg(p.rowptr + row + 1);
+    const int deg = e - s;
+    // split on multiples of 32 edges so every warp issues full coalesced index loads
+    const int per = ((deg + WARPS - 1) / WARPS + 31) & ~31;
+    const int ws = min(e, s + w * per), we = min(e, ws + per);
+    float acc[NCH][VEC];
+    int32_t arg[NCH][VEC];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { acc[k][i] = red_init<REDUCE>(op); arg[k][i] = -1; }
+    walk_edges<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, ws, we, fbase, flim, lane, 0xffffffffu, acc,
+                                                arg);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        s_acc[w][k][lane * VEC + i] = acc[k][i];
+        if constexpr (ARG) s_arg[w][k][lane * VEC + i] = arg[k][i];
+      }
+    __syncthreads();
+    if (w == 0) {
+      const int r = (REDUCE == R_RUNTIME) ? op : REDUCE;
+      for (int ww = 1; ww < WARPS; ++ww) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            const float t = s_acc[ww][k][lane * VEC + i];
+            if (r == R_SUM || r == R_MEAN) {
+              acc[k][i] += t;
+            } else if ((r == R_MIN && t < acc[k][i]) || (r == R_MAX && t > acc[k][i])) {
+              acc[k][i] = t;
+              if constexpr (ARG) arg[k][i] = s_arg[ww][k][lane * VEC + i];
+            }
+          }
+      }
+      finish_row<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, row, deg, fbase, flim, lane, acc, arg);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void minmax_bwd_kernel(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                  const int32_t* __restrict__ arg, int64_t lda,
+                                  const float* __restrict__ grad_out, int64_t ldg,
+                                  float* __restrict__ grad_x, int64_t ldx, int64_t rows, int F) {
+  const int64_t total = rows * F;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / F;
+    const int f = (int)(t - i * F);
+    const int e = arg[i * lda + f];
+    if (e >= 0) {
+      const float v = val ? val[e] : 1.f;
+      atomicAdd(grad_x + (int64_t)col[e] * ldx + f, v * grad_out[i * ldg + f]);
+    }
+  }
+}
+
+// ---- host-side dispatch ------------------------------------------------------
+struct LongRowScratch {
+  int32_t* count = nullptr;  // [1] (+ padding)
+  int2* rows = nullptr;      // [capacity]
+  int capacity = 0;
+  int device = -1;
+};
+// A small per-device scratch for the long-row list (allocated once, reused by every call;
+// kernels on one stream serialise, and the count is re-zeroed on that stream before each use).
+static int get_long_scratch(LongRowScratch** out) {
+  static thread_local LongRowScratch scratch[16];
+  int dev = 0;
+  IA_CUDA(cudaGetDevice(&dev));
+  IA_CHECK_ARG(dev >= 0 && dev < 16, "device ordinal %d out of range", dev);
+  LongRowScratch& s = scratch[dev];
+  if (s.count == nullptr) {
+    s.capacity = 1 << 16;
+    IA_CUDA(cudaMalloc(&s.count, 16 + sizeof(int2) * (size_t)s.capacity));
+    s.rows = reinterpret_cast<int2*>(reinterpret_cast<char*>(s.count) + 16);
+    s.device = dev;
+  }
+  *out = &s;
+  return INCAGG_OK;
+}
+
+constexpr int LONG_ROW_EDGES = 2048;
+
+template <int REDUCE, int VEC, int G, int NCH, bool DELTA, bool ARG>
+static int launch_cfg(SpmmParams& p, int n_tiles, cudaStream_t st) {
+  constexpr int GROUPS = SPMM_THREADS / G;
+  const int64_t blocks = (p.rows + GROUPS - 1) / GROUPS;
+  IA_CHECK_ARG(blocks <= 0x7fffffff, "too many rows for one launch");
+  if (blocks == 0) return INCAGG_OK;
+  LongRowScratch* ls = nullptr;
+  int rc = get_long_scratch(&ls);
+  if (rc != INCAGG_OK) return rc;
+  p.long_row = LONG_ROW_EDGES;
+  p.long_count = ls->count;
+  p.long_rows = ls->rows;
+  p.long_capacity = ls->capacity;
+  IA_CUDA(cudaMemsetAsync(ls->count, 0, sizeof(int32_t), st));
+  dim3 grid((unsigned)blocks, (unsigned)n_tiles);
+  spmm_rows_kernel<REDUCE, VEC, G, NCH, DELTA, ARG><<<grid, SPMM_THREADS, 0, st>>>(p);
+  IA_LAUNCH_CHECK();
+  // Long-row bucket (reads the entry count on the device; an empty list costs one tiny launch).
+  constexpr int NCH_LONG = (G == 32) ? NCH : 1;
+  spmm_long_rows_kernel<REDUCE, VEC, NCH_LONG, G * VEC * NCH, DELTA, ARG>
+      <<<2 * sm_count(), SPMM_THREADS, 0, st>>>(p);
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}
+
+// Pick (VEC, G, NCH) for a feature width and alignment.
+template <int REDUCE, bool DELTA, bool ARG>
+static int dispatch_shape(SpmmParams& p, int width, int vec, int tiles_mult, cudaStream_t st) {
+  // `width` = number of features one tile row must cover (F, or slab_F for multi)
+  const int nvec = (width + vec - 1) / vec;
+  auto tiles = [&](int cover) { return tiles_mult * ((width + cover - 1) / cover); };
+#define IA_CFG(V, G_, N_)                                                    \
+  do {                                                                       \
+    if (REDUCE == R_RUNTIME) p.tiles_per_slab = (width + V * G_ * N_ - 1) / (V * G_ * N_); \
+    return launch_cfg<REDUCE, V, G_, N_, DELTA, ARG>(p, tiles(V * G_ * N_), st); \
+  } while (0)
+  if (vec == 4) {
+    if (nvec <= 8) IA_CFG(4, 8, 1);
+    if (nvec <= 16) IA_CFG(4, 16, 1);
+    if (nvec <= 32) IA_CFG(4, 32, 1);
+    if (nvec <= 64) IA_CFG(4, 32, 2);
+    IA_CFG(4, 32, 4);
+  } else if (vec == 2) {
+    if (nvec <= 32) IA_CFG(2, 32, 1);
+    IA_CFG(2, 32, 4);
+  } else {
+    if (nvec <= 8) IA_CFG(1, 8, 1);
+    if (nvec <= 32) IA_CFG(1, 32, 1);
+    IA_CFG(1, 32, 4);
+  }
+#undef IA_CFG
+}
+
+static int pick_vec(const SpmmParams& p, int width) {
+  bool a16 = aligned16(p.X) && aligned16(p.out) && p.ldx % 4 == 0 && p.ldo % 4 == 0 && width % 4 == 0;
+  bool a8 = aligned8(p.X) && aligned8(p.out) && p.ldx % 2 == 0 && p.ldo % 2 == 0 && width % 2 == 0;
+  if (p.arg) {
+    a16 = a16 && aligned16(p.arg) && p.lda % 4 == 0;
+    a8 = a8 && aligned8(p.arg) && p.lda % 2 == 0;
+  }
+  if (p.m_in) {
+    a16 = a16 && aligned16(p.m_in) && aligned16(p.m_ag) && p.ld_in % 4 == 0 && p.ld_ag % 4 == 0;
+    a8 = a8 && aligned8(p.m_in) && aligned8(p.m_ag) && p.ld_in % 2 == 0 && p.ld_ag % 2 == 0;
+  }
+  return a16 ? 4 : (a8 ? 2 : 1);
+}
+
+static int check_common(const int32_t* rowptr, const int32_t* col, const float* X, float* out,
+                        int64_t ldx, int64_t ldo, int64_t rows, int32_t F) {
+  IA_CHECK_ARG(rows >= 0 && F >= 0, "negative size (rows=%lld, F=%d)", (long long)rows, F);
+  if (rows == 0 || F == 0) return INCAGG_OK;
+  IA_CHECK_ARG(rowptr != nullptr, "rowptr is NULL");
+  IA_CHECK_ARG(out != nullptr, "out is NULL");
+  IA_CHECK_ARG(ldx >= F && ldo >= F, "leading dimension smaller than F");
+  (void)col; (void)X;
+  return INCAGG_OK;
+}
+
+}  // namespace incagg
+
+using namespace incagg;
+
+extern "C" int incagg_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col,
+                               const float* val, const float* X, int64_t ldx, float* out,
+                               int64_t ldo, int32_t* arg_out, int64_t lda, int64_t rows, int32_t F,
+                               incagg_stream_t stream) {
+  int rc = check_common(rowptr, col, X, out, ldx, ldo, rows, F);
+  if (rc != INCAGG_OK) return rc;
+  if (rows == 0 || F == 0) return INCAGG_OK;
+  IA_CHECK_ARG(reduce >= 0 && reduce <= 3, "unknown reducer %d", reduce);
+  IA_CHECK_ARG(arg_out == nullptr || lda >= F, "lda smaller than F");
+  SpmmParams p{};
+  p.rowptr = rowptr; p.col = col; p.val = val; p.X = X; p.ldx = ldx; p.out = out; p.ldo = ldo;
+  p.arg = (reduce == R_MIN || reduce == R_MAX) ? arg_out : nullptr;
+  p.lda = lda; p.rows = rows; p.F = F;
+  const int vec = pick_vec(p, F);
+  cudaStream_t st = as_stream(stream);
+  switch (reduce) {
+    case R_SUM: return dispatch_shape<R_SUM, false, false>(p, F, vec, 1, st);
+    case R_MEAN: return dispatch_shape<R_MEAN, false, false>(p, F, vec, 1, st);
+    case R_MIN:
+      return p.arg ? dispatch_shape<R_MIN, false, true>(p, F, vec, 1, st)
+                   : dispatch_shape<R_MIN, false, false>(p, F, vec, 1, st);
+    default:
+      return p.arg ? dispatch_shape<R_MAX, false, true>(p, F, vec, 1, st)
+                   : dispatch_shape<R_MAX, false, false>(p, F, vec, 1, st);
+  }
+}
+
+extern "C" int incagg_spmm_delta(int reduce, const int32_t* rowptr, const int32_t* col,
+                                 const float* val, const float* x, int64_t ldx, const float* m_in,
+                                 int64_t ld_in, const float* m_ag, int64_t ld_ag,
+                                 const int64_t* n_id, float* out, int64_t ldo, int64_t rows,
+                                 int32_t F, incagg_stream_t stream) {
+  int rc = check_common(rowptr, col, x, out, ldx, ldo, rows, F);
+  if (rc != INCAGG_OK) return rc;
+  if (rows == 0 || F == 0) return INCAGG_OK;
+  IA_CHECK_ARG(reduce == R_SUM || reduce == R_MEAN, "delta supports sum/mean only (got %d)", reduce);
+  IA_CHECK_ARG(m_in != nullptr && m_ag != nullptr, "M_in / M_ag is NULL");
+  IA_CHECK_ARG(ld_in >= F && ld_ag >= F, "history leading dimension smaller than F");
+  SpmmParams p{};
+  p.rowptr = rowptr; p.col = col; p.val = val; p.X = x; p.ldx = ldx; p.out = out; p.ldo = ldo;
+  p.rows = rows; p.F = F; p.m_in = m_in; p.ld_in = ld_in; p.m_ag = m_ag; p.ld_ag = ld_ag;
+  p.n_id = n_id;
+  const int vec = pick_vec(p, F);
+  cudaStream_t st = as_stream(stream);
+  if (reduce == R_SUM) return dispatch_shape<R_SUM, true, false>(p, F, vec, 1, st);
+  return dispatch_shape<R_MEAN, true, false>(p, F, vec, 1, st);
+}
+
+extern "C" int incagg_spmm_multi(const int32_t* rowptr, const int32_t* col, const float* val,
+                                 const float* X, int64_t ldx, float* out, int64_t ldo, int64_t rows,
+                                 int32_t F, int32_t K, const int32_t* reducers,
+                                 incagg_stream_t stream) {
+  IA_CHECK_ARG(K >= 1 && K <= 8, "K must be in [1, 8] (got %d)", K);
+  IA_CHECK_ARG(reducers != nullptr, "reducers is NULL");
+  int rc = check_common(rowptr, col, X, out, ldx, ldo, rows, F * K);
+  if (rc != INCAGG_OK) return rc;
+  if (rows == 0 || F == 0) return INCAGG_OK;
+  SpmmParams p{};
+  p.rowptr = rowptr; p.col = col; p.val = val; p.X = X; p.ldx = ldx; p.out = out; p.ldo = ldo;
+  p.rows = rows; p.F = F * K; p.slab_F = F;
+  for (int k = 0; k < K; ++k) {
+    IA_CHECK_ARG(reducers[k] >= 0 && reducers[k] <= 3, "unknown reducer %d", reducers[k]);
+    p.reducers[k] = reducers[k];
+  }
+  const int vec = pick_vec(p, F);  // slab starts k*F keep the alignment of F
+  return dispatch_shape<R_RUNTIME, false, false>(p, F, vec, K, as_stream(stream));
+}
+
+extern "C" int incagg_spmm_minmax_bwd(const int32_t* col, const float* val, const int32_t* arg,
+                                      int64_t lda, const float* grad_out, int64_t ldg,
+                                      float* grad_x, int64_t ldx, int64_t rows, int32_t F,
+                                      incagg_stream_t stream) {
+  IA_CHECK_ARG(rows >= 0 && F >= 0, "negative size");
+  if (rows == 0 || F == 0) return INCAGG_OK;
+  IA_CHECK_ARG(col && arg && grad_out && grad_x, "NULL argument");
+  const int64_t total = rows * F;
+  const int threads = 256;
+  const int64_t want = (total + threads - 1) / threads;
+  const int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
+  minmax_bwd_kernel<<<blocks, threads, 0, as_stream(stream)>>>(col, val, arg, lda, grad_out, ldg,
+                                                               grad_x, ldx, rows, F);
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}

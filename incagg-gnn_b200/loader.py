@@ -1,0 +1,172 @@
+"""``SubgraphLoader`` / ``EvalSubgraphLoader`` (reference: torch_geometric_autoscale/loader.py:95-285).
+
+Same constructor arguments, same ``SubData`` tuples ``(data, batch_size, n_id, offset, count)``, same
+batch order (the reference's DataLoader sampler classes are reused for the index stream, so a seeded
+shuffle yields the same partition order).  The collate itself runs on the GPU:
+
+  * relabel_one_hop / relabel_one_hop_within_batch are the bit-exact CUDA kernels (the reference has
+    no CUDA relabel, csrc/relabel.cpp:15-20, and runs a single-threaded unordered_map in DataLoader
+    worker processes),
+  * every node-level tensor is gathered with the indexed-row kernel; the source may sit in HBM or in
+    pinned host memory (read through UVA), so there is no CPU gather + pickling + H2D copy,
+  * batch CSR structures use int32 indices.
+
+``num_workers`` / ``persistent_workers`` are accepted and ignored (no worker processes are needed).
+"""
+import time
+from typing import List, NamedTuple, Tuple
+
+import torch
+from torch import Tensor
+from torch.utils.data import BatchSampler, RandomSampler, SequentialSampler
+
+from . import ops
+from .data import Data
+from .sparse import SparseTensor
+
+
+class SubData(NamedTuple):
+    data: Data
+    batch_size: int
+    n_id: Tensor  # The indices of mini-batched nodes
+    offset: Tensor  # The offset of contiguous mini-batched nodes
+    count: Tensor  # The number of contiguous mini-batched nodes
+
+    def to(self, *args, **kwargs):
+        return SubData(self.data.to(*args, **kwargs), self.batch_size,
+                       self.n_id, self.offset, self.count)
+
+
+class SubgraphLoader:
+    r"""A simple subgraph loader that, given a pre-partioned :obj:`data` object,
+    generates subgraphs from mini-batches in :obj:`ptr` (including their 1-hop
+    neighbors)."""
+
+    def __init__(self, data: Data, ptr: Tensor, batch_size: int = 1, bipartite: bool = True,
+                 log: bool = True, num_neighbors=-1, type='eval', IB=False, shuffle: bool = False,
+                 num_workers: int = 0, persistent_workers: bool = False, device=None, **kwargs):
+        self.data = data
+        self.ptr = ptr.cpu()
+        self.bipartite = bipartite
+        self.log = log
+        self.num_neighbors = num_neighbors
+        if num_neighbors is not None and num_neighbors >= 0:
+            raise NotImplementedError('neighbour sampling is out of scope (the reference call site is '
+                                      'broken, loader.py:235; num_neighbors=-1 is the identity)')
+        self.shuffle = shuffle
+        self.batch_size = batch_size
+        self.shuffled_batch_id = []
+        self.device = torch.device(device) if device is not None else data.adj_t.device
+        if self.device.type != 'cuda':
+            raise RuntimeError('SubgraphLoader collates on the GPU: data.adj_t must be a CUDA SparseTensor')
+
+        self.num_parts = self.ptr.numel() - 1
+        # global CSR for relabel: int64 rowptr, int32 col, fp32 values (device resident)
+        adj = data.adj_t
+        self._rowptr64 = adj.rowptr.to(torch.int64)
+        self._rowptr_host = self._rowptr64.cpu()
+        self._col = adj.col
+        self._val = adj.value
+        self._ws = ops.RelabelWorkspace(adj.size(0), self.device)
+
+        sampler = RandomSampler(range(self.num_parts)) if shuffle else SequentialSampler(range(self.num_parts))
+        self._batch_sampler = BatchSampler(sampler, batch_size, drop_last=False)
+
+        if type == 'train':
+            self._collate = self.compute_subgraph_IB if IB else self.compute_subgraph
+            self._cached = None
+        else:
+            self._collate = self.compute_subgraph
+            self._cached = None
+            if batch_size == 1:  # pre-process the subgraph generation (loader.py:153-170)
+                if log:
+                    t = time.perf_counter()
+                    print('Pre-processing subgraphs...', end=' ', flush=True)
+                self._cached = [self.compute_subgraph([b]) for b in range(self.num_parts)]
+                if log:
+                    torch.cuda.synchronize(self.device)
+                    print(f'Done! [{time.perf_counter() - t:.2f}s]')
+
+    # -- helpers -----------------------------------------------------------------------------
+    def _batch_nodes(self, batch_ids: List[int]):
+        ptr = self.ptr
+        ranges = [(int(ptr[b]), int(ptr[b + 1])) for b in batch_ids]
+        n_id = torch.cat([torch.arange(lo, hi, device=self.device) for lo, hi in ranges]) \
+            if len(ranges) > 1 else torch.arange(ranges[0][0], ranges[0][1], device=self.device)
+        batch_id = torch.tensor(batch_ids)
+        offset = ptr[batch_id]
+        count = ptr[batch_id + 1] - offset
+        rp = self._rowptr_host
+        nnz_b = sum(int(rp[hi]) - int(rp[lo]) for lo, hi in ranges)  # partitions are contiguous rows
+        return n_id, offset, count, nnz_b
+
+    def _finish(self, rowptr, col, value, n_id, batch_size, offset, count) -> SubData:
+        adj_t = SparseTensor(rowptr=rowptr, col=col, value=value,
+                             sparse_sizes=(rowptr.numel() - 1, n_id.numel()), is_sorted=True)
+        data = self.data.__class__(adj_t=adj_t)
+        for k, v in self.data:
+            if isinstance(v, Tensor) and v.size(0) == self.data.num_nodes:
+                if v.dtype == torch.bool:  # 1-byte rows: gather as uint8 through torch
+                    data[k] = v.to(self.device, non_blocking=True).index_select(0, n_id) if v.is_cuda \
+                        else v[n_id.cpu()].to(self.device, non_blocking=True)
+                elif (v[0].numel() * v.element_size()) % 4 == 0 and (v.is_cuda or v.is_pinned()):
+                    data[k] = ops.gather_rows(v, n_id)
+                else:
+                    data[k] = v.to(self.device).index_select(0, n_id)
+        return SubData(data, batch_size, n_id, offset, count)
+
+    # -- collates (same names as the reference) ---------------------------------------------
+    def compute_subgraph(self, batches) -> SubData:
+        batch_ids = [b[0] if isinstance(b, tuple) else int(b) for b in batches]
+        n_id, offset, count, nnz_b = self._batch_nodes(batch_ids)
+        batch_size = n_id.numel()
+        with torch.cuda.device(self.device):
+            rowptr, col, value, n_id = ops.relabel_one_hop(
+                self._rowptr64, self._col, self._val, n_id, self.bipartite, ws=self._ws,
+                out_int32=True, nnz_b=nnz_b)
+            return self._finish(rowptr, col, value, n_id, batch_size, offset, count)
+
+    def compute_subgraph_IB(self, batches) -> SubData:
+        batch_ids = [b[0] if isinstance(b, tuple) else int(b) for b in batches]
+        n_id, offset, count, nnz_b = self._batch_nodes(batch_ids)
+        batch_size = n_id.numel()
+        with torch.cuda.device(self.device):
+            rowptr, col, value, n_id = ops.relabel_one_hop_within_batch(
+                self._rowptr64, self._col, self._val, n_id, self.bipartite, ws=self._ws,
+                out_int32=True, nnz_b=nnz_b)
+            return self._finish(rowptr, col, value, n_id, batch_size, offset, count)
+
+    # the reference's train collate without IncAgg is compute_subgraph_NS, which equals
+    # compute_subgraph for num_neighbors=-1
+    compute_subgraph_NS = compute_subgraph
+
+    def __len__(self):
+        return len(self._batch_sampler)
+
+    def __iter__(self):
+        self.shuffled_batch_id = []
+        for batch_ids in self._batch_sampler:
+            if self.shuffle:
+                self.shuffled_batch_id.append(batch_ids)
+            if self._cached is not None:
+                yield self._cached[batch_ids[0]]
+            else:
+                yield self._collate(batch_ids)
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}()'
+
+
+class EvalSubgraphLoader(SubgraphLoader):
+    r"""Like :class:`SubgraphLoader`, but merges ``batch_size`` consecutive partitions into one
+    evaluation batch, never shuffles and pre-materialises every subgraph (loader.py:266-284)."""
+
+    def __init__(self, data: Data, ptr: Tensor, batch_size: int = 1, bipartite: bool = True,
+                 log: bool = True, **kwargs):
+        ptr = ptr.cpu()[::batch_size]
+        if int(ptr[-1]) != data.num_nodes:
+            ptr = torch.cat([ptr, torch.tensor([data.num_nodes])], dim=0)
+        kwargs.pop('shuffle', None)
+        kwargs.pop('num_workers', None)
+        super().__init__(data=data, ptr=ptr, batch_size=1, bipartite=bipartite, log=log,
+                         shuffle=False, num_workers=0, **kwargs)

@@ -1,0 +1,386 @@
+"""``ScalableGNN`` — the GAS / IncAgg runtime (reference: torch_geometric_autoscale/models/base.py).
+
+Same public surface: ``__call__`` (GAS step, base.py:126-240), ``VR_call`` (IncAgg step, :242-378),
+``push_and_pull`` (:380-456), ``push_only`` (:458-499), ``mini_inference`` (:509-603),
+``mini_inference_vr`` (per model in the reference, e.g. gcn2.py:432-507; shared here through two small
+per-model hooks), ``histories`` / ``histories_ag`` / ``pool`` / ``pool_ag`` / ``_out``.
+
+Two placements of the history tables:
+  * ``device='cuda'`` (HBM-resident, the B200-native default): no pools; push / pull are kernels on
+    the compute stream and the IncAgg step reads ``M_in`` / ``M_ag`` in place from the tables,
+  * ``device=None`` (pinned host memory, the reference's layout): ``AsyncIOPool`` pairs exactly as in
+    the reference, with event dependencies instead of device-wide synchronisation.
+
+History-slot map follows the fork as written: GCN pushes/pulls layer-l output at
+``histories[l+1]``, GCN2/APPNP/PNA at ``histories[l]``; the sweeps write layer-l output to
+``histories[l+1]``; IncAgg reads ``histories[l]`` / ``histories_ag[l]``.
+"""
+import time
+import warnings
+from typing import Optional, Callable, Dict, Any
+
+import torch
+from torch import Tensor
+
+from .. import ops
+from ..history import History
+from ..pool import AsyncIOPool
+from ..sparse import SparseTensor
+
+
+class _PushPull(torch.autograd.Function):
+    """cat([x[:B], pulled]) without the intermediate: the pulled rows are gathered straight into
+    the tail of the output buffer.  grad flows to x[:B] only (base.py:426,451)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, fill_tail, batch_size: int, n_tail: int):
+        out = torch.empty((batch_size + n_tail, x.size(1)), dtype=x.dtype, device=x.device)
+        out[:batch_size].copy_(x[:batch_size])
+        if n_tail > 0:
+            fill_tail(out[batch_size:])
+        ctx.batch_size, ctx.n_in = batch_size, x.size(0)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        B = ctx.batch_size
+        if ctx.n_in == B:
+            return grad_out[:B], None, None, None
+        g = grad_out.new_zeros((ctx.n_in, grad_out.size(1)))
+        g[:B] = grad_out[:B]
+        return g, None, None, None
+
+
+class ScalableGNN(torch.nn.Module):
+    r"""An abstract class for implementing scalable GNNs via historical embeddings."""
+
+    def __init__(self, num_nodes: int, hidden_channels: int, num_layers: int,
+                 pool_size: Optional[int] = None, buffer_size: Optional[int] = None, device=None,
+                 in_channels=None):
+        super().__init__()
+        self.num_nodes = num_nodes
+        self.hidden_channels = hidden_channels
+        self.num_layers = num_layers
+        self.pool_size = num_layers - 1 if pool_size is None else pool_size
+        self.buffer_size = buffer_size
+
+        # L histories (the fork; upstream PyGAS had L-1), all hidden-wide (base.py:67-72)
+        self.histories = torch.nn.ModuleList(
+            [History(num_nodes, hidden_channels, device) for _ in range(num_layers)])
+        self.pool: Optional[AsyncIOPool] = None
+        # M_ag tables (base.py:76-81)
+        self.histories_ag = torch.nn.ModuleList(
+            [History(num_nodes, hidden_channels, device) for _ in range(num_layers)])
+        self.pool_ag: Optional[AsyncIOPool] = None
+
+        self._async = False
+        self.__out: Optional[Tensor] = None
+
+    @property
+    def emb_device(self):
+        return self.histories[0].emb.device
+
+    @property
+    def device(self):
+        return self.histories[0]._device
+
+    def _apply(self, fn: Callable) -> None:
+        super()._apply(fn)
+        # We only initialize the AsyncIOPool in case histories are on CPU (base.py:96-120):
+        if (str(self.emb_device) == 'cpu' and str(self.device)[:4] == 'cuda'
+                and self.pool_size is not None and self.buffer_size is not None):
+            self.pool = AsyncIOPool(self.pool_size, self.buffer_size, self.histories[0].embedding_dim)
+            self.pool.to(self.device)
+            self.pool_ag = AsyncIOPool(self.pool_size, self.buffer_size,
+                                       self.histories_ag[0].embedding_dim)
+            self.pool_ag.to(self.device)
+        return self
+
+    def reset_parameters(self):
+        for history in self.histories:
+            history.reset_parameters()
+
+    # ------------------------------------------------------------------------------------------
+    # GAS step
+    # ------------------------------------------------------------------------------------------
+    def __call__(self, x: Optional[Tensor] = None, adj_t: Optional[SparseTensor] = None,
+                 batch_size: Optional[int] = None, n_id: Optional[Tensor] = None,
+                 offset: Optional[Tensor] = None, count: Optional[Tensor] = None, loader=None,
+                 drift_norm: int = 2, aggregate_combined: bool = True, use_aggregation: bool = True,
+                 **kwargs) -> Dict[str, Any]:
+        if loader is not None:
+            return self.mini_inference(loader, use_aggregation)
+
+        self._async = (self.pool is not None and batch_size is not None and n_id is not None
+                       and offset is not None and count is not None)
+        if (batch_size is not None and not self._async and str(self.emb_device) == 'cpu'
+                and str(self.device)[:4] == 'cuda'):
+            warnings.warn('Asynchronous I/O disabled, although history and model sit on different devices.')
+
+        if self._async:
+            # one pull per history consumed by forward(); the fork issues L and leaks the extra
+            # queue entries -- here exactly as many as push_and_pull will consume
+            for hist in self._gas_pull_histories():
+                self.pool.async_pull(hist.emb, None, None, n_id[batch_size:])
+
+        out, t_mov = self.forward(x, adj_t, drift_norm, aggregate_combined, use_aggregation,
+                                  batch_size, n_id, offset, count, **kwargs)
+
+        if self._async:
+            self.pool.synchronize_push()
+        self._async = False
+        return {'out': out, 'time_pool_pull': 0, 'time_pool_push': 0,
+                'time_forward_histories_movement': t_mov, 'time_forward_total': 0}
+
+    def _gas_pull_histories(self):
+        """Histories pulled by one GAS forward, in consumption order (model specific)."""
+        return list(self.histories)[:self.num_layers - 1]
+
+    # ------------------------------------------------------------------------------------------
+    # IncAgg step
+    # ------------------------------------------------------------------------------------------
+    def VR_call(self, x: Optional[Tensor] = None, adj_t: Optional[SparseTensor] = None,
+                batch_size: Optional[int] = None, n_id: Optional[Tensor] = None,
+                offset: Optional[Tensor] = None, count: Optional[Tensor] = None, loader=None,
+                debug_flag: bool = False, drift_norm: int = 2, epoch: int = 0, batch_idx: int = 0,
+                **kwargs) -> Dict[str, Any]:
+        if loader is not None:
+            return self.mini_inference(loader)
+        self._async = (self.pool is not None and batch_size is not None and n_id is not None
+                       and offset is not None and count is not None)
+        if self._async:
+            empty = torch.empty(0, dtype=torch.int64)
+            for i in range(len(self.histories)):  # M_in / M_ag slices of the batch (base.py:318-323)
+                self.pool.async_pull(self.histories[i].emb, offset, count, empty)
+                self.pool_ag.async_pull(self.histories_ag[i].emb, offset, count, empty)
+        out, t_mov, n_ib, n_ob = self.VR_forward(x, adj_t, drift_norm, epoch, batch_idx, batch_size,
+                                                 n_id, offset, count, **kwargs)
+        self._async = False
+        return {'out': out, 'time_pool_pull': 0, 'time_pool_push': 0,
+                'time_forward_histories_movement': t_mov, 'time_forward_total': 0,
+                'num_in_batch_neighbors': n_ib, 'num_out_batch_neighbors': n_ob}
+
+    def _incagg_tables(self, layer: int, batch_size: int, width: int, n_id: Tensor, offset, count):
+        """(M_in, M_ag, n_id_or_None) for ``spmm_delta`` at `layer`.
+
+        Pool mode (pinned-host tables): the pulled ``[:B, :F]`` slices as in gcn2.py:246-247 (no
+        clone: the slot is released only after the kernel that reads it has been enqueued).
+        HBM mode: the tables themselves; a single contiguous partition is a plain slice, several
+        partitions are addressed through n_id inside the kernel."""
+        if self._async:
+            m_in = self.pool.synchronize_pull()[:batch_size, :width]
+            m_ag = self.pool_ag.synchronize_pull()[:batch_size, :width]
+            return m_in, m_ag, None
+        hist, hist_ag = self.histories[layer].emb, self.histories_ag[layer].emb
+        if not hist.is_cuda:
+            raise RuntimeError('IncAgg step with host-resident histories needs the AsyncIOPool '
+                               '(pool_size and buffer_size must be set)')
+        if offset is not None and offset.numel() == 1:
+            o = int(offset[0])
+            return hist[o:o + batch_size, :width], hist_ag[o:o + batch_size, :width], None
+        return hist, hist_ag, n_id[:batch_size]
+
+    def _incagg_release(self):
+        if self._async:
+            self.pool.free_pull()
+            self.pool_ag.free_pull()
+
+    # ------------------------------------------------------------------------------------------
+    # push / pull
+    # ------------------------------------------------------------------------------------------
+    def push_and_pull(self, history, x: Tensor, batch_size: Optional[int] = None,
+                      n_id: Optional[Tensor] = None, offset: Optional[Tensor] = None,
+                      count: Optional[Tensor] = None):
+        r"""Pushes and pulls information from :obj:`x` to :obj:`history` and vice versa."""
+        if n_id is None and x.size(0) != self.num_nodes:
+            return x  # Do nothing...
+        if n_id is None and x.size(0) == self.num_nodes:
+            history.push(x)
+            return x, 0.
+        assert n_id is not None
+        if batch_size is None:
+            history.push(x, n_id)
+            return x
+        n_tail = n_id.numel() - batch_size
+        if not self._async:  # synchronous branch = the semantic definition (base.py:411-426)
+            history.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
+            idx = n_id[batch_size:]
+
+            def fill(dst):
+                ops.gather_rows(history.emb, idx.to(dst.device), out=dst)
+            return _PushPull.apply(x, fill, batch_size, n_tail), 0.
+        pulled = self.pool.synchronize_pull()
+
+        def fill(dst):
+            dst.copy_(pulled[:n_tail, :dst.size(1)])
+        self.pool.async_push(x[:batch_size].detach(), offset, count, history.emb)
+        out = _PushPull.apply(x, fill, batch_size, n_tail)
+        self.pool.free_pull()
+        return out, 0.
+
+    def push_only(self, history, x: Tensor, batch_size: Optional[int] = None,
+                  n_id: Optional[Tensor] = None, offset: Optional[Tensor] = None,
+                  count: Optional[Tensor] = None):
+        """Pushes updated embeddings to `history` without pulling (base.py:458-499)."""
+        if n_id is None and x.size(0) != self.num_nodes:
+            return x
+        if n_id is None and x.size(0) == self.num_nodes:
+            history.push(x)
+            return x, 0.
+        assert n_id is not None
+        if batch_size is None:
+            history.push(x, n_id)
+            return x, 0.
+        if not self._async:
+            history.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
+        else:
+            self.pool.async_push(x[:batch_size].detach(), offset, count, history.emb)
+        return x[:batch_size], 0.
+
+    @property
+    def _out(self):
+        if self.__out is None:
+            if self.emb_device.type == 'cuda':
+                self.__out = torch.empty(self.num_nodes, self.out_channels, device=self.emb_device)
+            else:
+                self.__out = torch.empty(self.num_nodes, self.out_channels,
+                                         pin_memory=torch.cuda.is_available())
+        return self.__out
+
+    # ------------------------------------------------------------------------------------------
+    # layer-wise sweeps
+    # ------------------------------------------------------------------------------------------
+    def _sweep_push(self, pool, x: Tensor, offset, count, table: Tensor):
+        """x rows -> table[offset_i : +count_i] (pool.async_push in the reference)."""
+        if table.size(1) > x.size(1):  # zero-pad to the table width (gcn.py:355-359)
+            xp = x.new_zeros((x.size(0), table.size(1)))
+            xp[:, :x.size(1)] = x
+            x = xp
+        if pool is not None:
+            pool.async_push(x, offset, count, table)
+        else:
+            ops.copy_slices(x.contiguous(), table, offset, count, 1)
+
+    def _sweep_pull_all(self, loader, table: Tensor):
+        """Pool mode: enqueue the pulls of every batch (base.py:555-557)."""
+        if self.pool is not None:
+            for _, batch_size, n_id, offset, count, _ in loader:
+                self.pool.async_pull(table, offset, count, n_id[batch_size:])
+
+    def _sweep_pull(self, table: Tensor, batch_size, n_id, offset, count) -> Tensor:
+        """[x_B ; x_halo] of one batch from `table` (pool.synchronize_pull()[:|n_id|])."""
+        if self.pool is not None:
+            return self.pool.synchronize_pull()[:n_id.numel()]
+        out = torch.empty((n_id.numel(), table.size(1)), dtype=table.dtype, device=self.device)
+        ops.copy_slices(table, out, offset, count, 0)
+        if n_id.numel() > batch_size:
+            ops.gather_rows(table, n_id[batch_size:].contiguous(), out=out[batch_size:])
+        return out
+
+    def _sweep_sync(self):
+        if self.pool is not None:
+            self.pool.synchronize_push()
+        if self.pool_ag is not None:
+            self.pool_ag.synchronize_push()
+
+    @torch.no_grad()
+    def mini_inference(self, loader, use_aggregation=True) -> Tensor:
+        """Layer-wise evaluation sweep (base.py:509-603): layer-l outputs -> histories[l+1], logits
+        -> ``_out``."""
+        loader = [sub_data + ({}, ) for sub_data in loader]
+        for data, batch_size, n_id, offset, count, state in loader:
+            x = data.x.to(self.device)
+            adj_t = data.adj_t.to(self.device)
+            out = self.forward_layer(0, x, adj_t, state, use_aggregation)[:batch_size]
+            self._sweep_push(self.pool, out, offset, count, self.histories[1].emb)
+        self._sweep_sync()
+        for i in range(1, len(self.histories) - 1):
+            self._sweep_pull_all(loader, self.histories[i].emb)
+            for batch, batch_size, n_id, offset, count, state in loader:
+                adj_t = batch.adj_t.to(self.device)
+                x = self._sweep_pull(self.histories[i].emb, batch_size, n_id, offset, count)
+                out = self.forward_layer(i, x, adj_t, state, use_aggregation)[:batch_size]
+                self._sweep_push(self.pool, out, offset, count, self.histories[i + 1].emb)
+                if self.pool is not None:
+                    self.pool.free_pull()
+            self._sweep_sync()
+        self._sweep_pull_all(loader, self.histories[-1].emb)
+        for batch, batch_size, n_id, offset, count, state in loader:
+            adj_t = batch.adj_t.to(self.device)
+            x = self._sweep_pull(self.histories[-1].emb, batch_size, n_id, offset, count)
+            out = self.forward_layer(self.num_layers - 1, x, adj_t, state, use_aggregation)[:batch_size]
+            self._sweep_push(self.pool, out, offset, count, self._out)
+            if self.pool is not None:
+                self.pool.free_pull()
+        self._sweep_sync()
+        return self._out
+
+    # per-model hooks of the IncAgg refresh --------------------------------------------------
+    def _refresh_layer0_input(self, x: Tensor) -> Tensor:
+        """M_in of layer 0 for all B+H rows (what the first propagation aggregates)."""
+        raise NotImplementedError
+
+    def _refresh_aggregate(self, adj_t: SparseTensor, x: Tensor) -> Tensor:
+        """M_ag = aggregate of stale layer inputs (sum; GraphSAGE overrides with mean)."""
+        return adj_t @ x
+
+    @torch.no_grad()
+    def mini_inference_vr(self, loader, use_aggregation=True) -> Tensor:
+        """Per-epoch refresh of M_in (``histories``) and M_ag (``histories_ag``) by a layer-wise sweep
+        (gcn.py:335-410, gcn2.py:432-507, appnp.py:228-314, graphsage.py:862-960).  Where the layer
+        aggregates its input directly (GCN2 / APPNP / GraphSAGE) the aggregate is computed once and
+        handed to ``forward_layer`` instead of being recomputed (the reference runs the SpMM twice)."""
+        loader = [sub_data + ({}, ) for sub_data in loader]
+        share = getattr(self, '_share_refresh_aggregate', False) and not self.training
+        for data, batch_size, n_id, offset, count, state in loader:
+            x = data.x.to(self.device)
+            adj_t = data.adj_t.to(self.device)
+            m_in0 = self._refresh_layer0_input(x)
+            m_ag0 = self._refresh_aggregate(adj_t, m_in0)
+            if share:
+                state['m_in0'] = m_in0
+                out = self.forward_layer(0, x, adj_t, state, use_aggregation, agg=m_ag0)[:batch_size]
+                state.pop('m_in0', None)
+            else:
+                out = self.forward_layer(0, x, adj_t, state, use_aggregation)[:batch_size]
+            self._sweep_push(self.pool_ag, m_ag0, offset, count, self.histories_ag[0].emb)
+            self._sweep_push(self.pool, m_in0[:batch_size], offset, count, self.histories[0].emb)
+            self._sweep_push(self.pool, out, offset, count, self.histories[1].emb)
+        self._sweep_sync()
+        for i in range(1, len(self.histories) - 1):
+            self._sweep_pull_all(loader, self.histories[i].emb)
+            for batch, batch_size, n_id, offset, count, state in loader:
+                adj_t = batch.adj_t.to(self.device)
+                x = self._sweep_pull(self.histories[i].emb, batch_size, n_id, offset, count)
+                m_ag = self._refresh_aggregate(adj_t, x)
+                self._sweep_push(self.pool_ag, m_ag, offset, count, self.histories_ag[i].emb)
+                if share:
+                    out = self.forward_layer(i, x, adj_t, state, use_aggregation, agg=m_ag)[:batch_size]
+                else:
+                    out = self.forward_layer(i, x, adj_t, state, use_aggregation)[:batch_size]
+                self._sweep_push(self.pool, out, offset, count, self.histories[i + 1].emb)
+                if self.pool is not None:
+                    self.pool.free_pull()
+            self._sweep_sync()
+        self._sweep_pull_all(loader, self.histories[-1].emb)
+        for batch, batch_size, n_id, offset, count, state in loader:
+            adj_t = batch.adj_t.to(self.device)
+            x = self._sweep_pull(self.histories[-1].emb, batch_size, n_id, offset, count)
+            m_ag = self._refresh_aggregate(adj_t, x)
+            if share:
+                out = self.forward_layer(self.num_layers - 1, x, adj_t, state, use_aggregation,
+                                         agg=m_ag)[:batch_size]
+            else:
+                out = self.forward_layer(self.num_layers - 1, x, adj_t, state, use_aggregation)[:batch_size]
+            self._sweep_push(self.pool_ag, m_ag, offset, count, self.histories_ag[-1].emb)
+            self._sweep_push(self.pool, out, offset, count, self._out)
+            if self.pool is not None:
+                self.pool.free_pull()
+        self._sweep_sync()
+        return self._out
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError
+
+    def forward_layer(self, *args, **kwargs):
+        raise NotImplementedError

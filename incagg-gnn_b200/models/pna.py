@@ -1,0 +1,158 @@
+"""PNA on the GAS runtime (reference: torch_geometric_autoscale/models/pna.py:24-158,281-295).
+
+PNA has no working IncAgg path in the reference; its GAS ``forward`` and
+``forward_layer`` are what is built here.  ``PNAConv.message_and_aggregate`` runs K =
+|aggregators| x |scalers| separate  pre_lin -> relu -> matmul(reduce) -> post_lin -> scaler  passes in
+the reference; here the K pre_lin outputs are written side by side into one ``[n, K*F]`` operand and
+the K reductions run in ONE launch of the multi-aggregator SpMM kernel when no gradient is needed
+(inference sweeps); the training path keeps per-aggregator autograd through the same SpMM kernels.
+"""
+from itertools import product
+from typing import Optional, List
+
+import torch
+from torch import Tensor
+import torch.nn.functional as F
+from torch.nn import ModuleList, Linear, BatchNorm1d
+
+from .. import ops
+from ..sparse import SparseTensor, spmm
+from .base import ScalableGNN
+
+EPS = 1e-5
+
+
+class PNAConv(torch.nn.Module):
+    def __init__(self, in_channels: int, out_channels: int, aggregators: List[str],
+                 scalers: List[str], deg: Tensor, **kwargs):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.aggregators = list(aggregators)
+        self.scalers = list(scalers)
+        deg = deg.to(torch.float)
+        self.avg_deg = {'lin': deg.mean().item(), 'log': (deg + 1).log().mean().item()}
+        K = len(self.aggregators) * len(self.scalers)
+        self.pre_lins = ModuleList([Linear(in_channels, out_channels) for _ in range(K)])
+        self.post_lins = ModuleList([Linear(out_channels, out_channels) for _ in range(K)])
+        self.lin = Linear(in_channels, out_channels)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for lin in self.pre_lins:
+            lin.reset_parameters()
+        for lin in self.post_lins:
+            lin.reset_parameters()
+        self.lin.reset_parameters()
+
+    def forward(self, x: Tensor, adj_t: SparseTensor) -> Tensor:
+        out = self.message_and_aggregate(adj_t, x)
+        out = out + self.lin(x)[:out.size(0)]
+        return out
+
+    def _scale(self, h: Tensor, scaler: str, deg: Tensor) -> Tensor:
+        if scaler == 'amplification':
+            h = h * ((deg + 1).log() / self.avg_deg['log'])
+        elif scaler == 'attenuation':
+            h = h * (self.avg_deg['log'] / ((deg + 1).log() + EPS))
+        return h
+
+    def message_and_aggregate(self, adj_t: SparseTensor, x: Tensor) -> Tensor:
+        deg = adj_t.storage.rowcount().to(x.dtype).view(-1, 1)
+        combos = list(product(self.aggregators, self.scalers))
+        fused = not torch.is_grad_enabled() and len(combos) <= 8 and self.out_channels % 4 == 0
+        out = 0
+        if fused:
+            Fo = self.out_channels
+            hs = torch.empty((x.size(0), len(combos) * Fo), dtype=x.dtype, device=x.device)
+            for k, pre_lin in enumerate(self.pre_lins):
+                torch.relu(pre_lin(x), out=hs[:, k * Fo:(k + 1) * Fo])
+            agg = ops.spmm_multi_raw(adj_t.rowptr, adj_t.col, adj_t.value, hs, Fo,
+                                     [a for a, _ in combos], rows=adj_t.size(0))
+            for k, ((aggr, scaler), post_lin) in enumerate(zip(combos, self.post_lins)):
+                h = post_lin(agg[:, k * Fo:(k + 1) * Fo])
+                out = out + self._scale(h, scaler, deg)
+            return out
+        for (aggr, scaler), pre_lin, post_lin in zip(combos, self.pre_lins, self.post_lins):
+            h = pre_lin(x).relu_()
+            h = spmm(adj_t, h, reduce=aggr)
+            h = post_lin(h)
+            out = out + self._scale(h, scaler, deg)
+        return out
+
+
+class PNA(ScalableGNN):
+    def __init__(self, num_nodes: int, in_channels: int, hidden_channels: int, out_channels: int,
+                 num_layers: int, aggregators: List[str], scalers: List[str], deg: Tensor,
+                 dropout: float = 0.0, drop_input: bool = True, batch_norm: bool = False,
+                 residual: bool = False, pool_size: Optional[int] = None,
+                 buffer_size: Optional[int] = None, device=None):
+        super().__init__(num_nodes, hidden_channels, num_layers, pool_size, buffer_size, device)
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.dropout = dropout
+        self.drop_input = drop_input
+        self.batch_norm = batch_norm
+        self.residual = residual
+        self.convs = ModuleList()
+        for i in range(num_layers):
+            in_dim = in_channels if i == 0 else hidden_channels
+            out_dim = out_channels if i == num_layers - 1 else hidden_channels
+            self.convs.append(PNAConv(in_dim, out_dim, aggregators=aggregators, scalers=scalers, deg=deg))
+        self.bns = ModuleList()
+        for i in range(num_layers - 1):
+            self.bns.append(BatchNorm1d(hidden_channels))
+
+    @property
+    def reg_modules(self):
+        return ModuleList(list(self.convs[:-1]) + list(self.bns))
+
+    @property
+    def nonreg_modules(self):
+        return self.convs[-1:]
+
+    def reset_parameters(self):
+        super().reset_parameters()
+        for conv in self.convs:
+            conv.reset_parameters()
+        for bn in self.bns:
+            bn.reset_parameters()
+
+    # GAS step (pna.py:138-158); the leading arguments follow ScalableGNN.__call__ of this repo
+    def forward(self, x: Tensor, adj_t: SparseTensor, drift_norm: int = 2,
+                aggregate_combined: bool = True, use_aggregation=True, *args):
+        batch_size, n_id, offset, count = (list(args) + [None] * 4)[:4]
+        t_all = 0
+        if self.drop_input:
+            x = F.dropout(x, p=self.dropout, training=self.training)
+        for conv, bn, hist in zip(self.convs[:-1], self.bns, self.histories):
+            h = conv(x, adj_t)
+            if self.batch_norm:
+                h = bn(h)
+            if self.residual and h.size(-1) == x.size(-1):
+                h = h + x[:h.size(0)]
+            x = h.relu_()
+            x, t = self.push_and_pull(hist, x, batch_size, n_id, offset, count)
+            t_all += t
+            x = F.dropout(x, p=self.dropout, training=self.training)
+        x = self.convs[-1](x, adj_t)
+        return x, t_all
+
+    def VR_forward(self, *args, **kwargs):
+        raise NotImplementedError('PNA has no working incremental-aggregation path in the reference '
+                                  '(pna.py:162-278 is a debugging mock, SURVEY F10)')
+
+    # layer-wise sweep (pna.py:281-295); `use_aggregation` accepted for mini_inference's call shape
+    @torch.no_grad()
+    def forward_layer(self, layer, x, adj_t, state, use_aggregation=True, agg=None):
+        if layer == 0 and self.drop_input:
+            x = F.dropout(x, p=self.dropout, training=self.training)
+        h = self.convs[layer](x, adj_t)
+        if layer < self.num_layers - 1:
+            if self.batch_norm:
+                h = self.bns[layer](h)
+            if self.residual and h.size(-1) == x.size(-1):
+                h = h + x[:h.size(0)]
+            h = h.relu_()
+            h = F.dropout(h, p=self.dropout, training=self.training)
+        return h

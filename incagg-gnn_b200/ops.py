@@ -1,0 +1,460 @@
+"""Tensor-level wrappers over the C ABI (include/incagg_b200.h) plus the autograd functions and
+the re-registration of the reference's operator names.
+
+Every function here launches the hand-written sm_100a kernels on the current CUDA stream.  Nothing
+falls back to PyTorch or to the CPU oracle: non-CUDA inputs raise.
+
+Reference op names re-registered (csrc/relabel.cpp:40-42, csrc/async.cpp:44-48):
+    torch.ops.torch_geometric_autoscale.{relabel_one_hop, relabel_one_hop_within_batch,
+                                         read_async, write_async, synchronize}
+"""
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import lib, check, ptr, REDUCE
+
+# Count of our kernel-launching C-ABI calls (bench.py reports it as `gpu_launches`).
+LAUNCHES = {"calls": 0}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("incagg_b200: expected a CUDA tensor (there is no CPU fallback)")
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"incagg_b200: expected float32, got {t.dtype}")
+    if t.dim() == 1:
+        t = t.unsqueeze(1)
+    if t.stride(-1) != 1 or (t.size(0) > 1 and t.stride(0) < t.size(1)):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: Tensor) -> int:
+    return t.stride(0) if t.size(0) > 1 else max(t.size(1), t.stride(0))
+
+
+# --------------------------------------------------------------------------------------------
+# SpMM
+# --------------------------------------------------------------------------------------------
+def spmm_raw(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, reduce: str = "sum",
+             rows: Optional[int] = None, out: Optional[Tensor] = None,
+             return_arg: bool = False):
+    """out[i] = reduce_e val[e] * x[col[e]] over a CSR with int32 rowptr/col (device)."""
+    _require_cuda(rowptr, col, val, x)
+    assert rowptr.dtype == torch.int32 and col.dtype == torch.int32
+    squeeze = x.dim() == 1
+    x = _f32c(x)
+    n_rows = rowptr.numel() - 1 if rows is None else rows
+    F = x.size(1)
+    if out is None:
+        out = torch.empty((n_rows, F), dtype=torch.float32, device=x.device)
+    arg = None
+    if return_arg and reduce in ("min", "max"):
+        arg = torch.empty((n_rows, F), dtype=torch.int32, device=x.device)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_spmm_csr(REDUCE[reduce], ptr(rowptr), ptr(col), ptr(val), ptr(x), _ld(x),
+                              ptr(out), _ld(out), ptr(arg), F if arg is not None else 0, n_rows, F,
+                              _stream()))
+    if squeeze:
+        out = out.squeeze(1)
+    return (out, arg) if return_arg else out
+
+
+def spmm_delta_raw(rowptr, col, val, x, m_in, m_ag, n_id=None, reduce="sum", rows=None, out=None):
+    """out = A (x - M_in[g]) + M_ag[g]; g = n_id if given (history tables read in place)."""
+    _require_cuda(rowptr, col, val, x, m_in, m_ag, n_id)
+    x = _f32c(x)
+    n_rows = rowptr.numel() - 1 if rows is None else rows
+    F = x.size(1)
+    assert m_in.dtype == torch.float32 and m_ag.dtype == torch.float32
+    assert m_in.stride(1) == 1 and m_ag.stride(1) == 1 and m_in.size(1) >= F and m_ag.size(1) >= F
+    if n_id is not None:
+        assert n_id.dtype == torch.int64 and n_id.is_contiguous()
+    if out is None:
+        out = torch.empty((n_rows, F), dtype=torch.float32, device=x.device)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_spmm_delta(REDUCE[reduce], ptr(rowptr), ptr(col), ptr(val), ptr(x), _ld(x),
+                                ptr(m_in), m_in.stride(0), ptr(m_ag), m_ag.stride(0), ptr(n_id),
+                                ptr(out), _ld(out), n_rows, F, _stream()))
+    return out
+
+
+def spmm_multi_raw(rowptr, col, val, x, F: int, reducers, rows=None, out=None):
+    """x is [n_src, K*F]; slab k reduced with reducers[k] ('sum'|'mean'|'min'|'max')."""
+    _require_cuda(rowptr, col, val, x)
+    x = _f32c(x)
+    K = len(reducers)
+    assert x.size(1) == K * F
+    n_rows = rowptr.numel() - 1 if rows is None else rows
+    if out is None:
+        out = torch.empty((n_rows, K * F), dtype=torch.float32, device=x.device)
+    import ctypes
+    red = (ctypes.c_int32 * K)(*[REDUCE[r] for r in reducers])
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_spmm_multi(ptr(rowptr), ptr(col), ptr(val), ptr(x), _ld(x), ptr(out), _ld(out),
+                                n_rows, F, K, ctypes.cast(red, ctypes.c_void_p), _stream()))
+    return out
+
+
+def spmm_minmax_bwd_raw(col, val, arg, grad_out, n_src: int):
+    grad_out = _f32c(grad_out)
+    F = grad_out.size(1)
+    grad_x = torch.zeros((n_src, F), dtype=torch.float32, device=grad_out.device)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_spmm_minmax_bwd(ptr(col), ptr(val), ptr(arg), arg.stride(0), ptr(grad_out),
+                                     _ld(grad_out), ptr(grad_x), _ld(grad_x), grad_out.size(0), F,
+                                     _stream()))
+    return grad_x
+
+
+def csr_transpose(rowptr: Tensor, col: Tensor, val: Optional[Tensor], rows: int, cols: int,
+                  want_perm: bool = False):
+    """CSR of A^T (deterministic entry order). Returns (t_rowptr, t_col, t_val, t_perm|None)."""
+    _require_cuda(rowptr, col, val)
+    assert rowptr.dtype == torch.int32 and col.dtype == torch.int32
+    nnz = col.numel()
+    dev = rowptr.device
+    t_rowptr = torch.empty(cols + 1, dtype=torch.int32, device=dev)
+    t_col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    t_val = torch.empty(nnz, dtype=torch.float32, device=dev) if val is not None else None
+    t_perm = torch.empty(nnz, dtype=torch.int32, device=dev) if want_perm else None
+    ws_bytes = lib.incagg_csr_transpose_workspace_bytes(rows, cols, nnz)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_csr_transpose(ptr(rowptr), ptr(col), ptr(val), rows, cols, nnz, ptr(t_rowptr),
+                                   ptr(t_col), ptr(t_val), ptr(t_perm), ptr(ws), ws_bytes, _stream()))
+    return t_rowptr, t_col, t_val, t_perm
+
+
+# --------------------------------------------------------------------------------------------
+# rows: gather / scatter / slices
+# --------------------------------------------------------------------------------------------
+def _row_view(t: Tensor):
+    """(pointer, leading dimension in bytes, row bytes, rows) of a 1-D/2-D row-major tensor."""
+    if t.dim() == 1:
+        t = t.unsqueeze(1)
+    if t.dim() > 2:
+        t = t.reshape(t.size(0), -1)
+    assert t.stride(1) == 1 or t.size(1) == 1, "rows must be contiguous"
+    es = t.element_size()
+    ld = (t.stride(0) if t.size(0) > 1 else t.size(1)) * es
+    return t, ld, t.size(1) * es, t.size(0)
+
+
+def _device_accessible(t: Tensor) -> bool:
+    return t.is_cuda or t.is_pinned()
+
+
+def gather_rows(src: Tensor, idx: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """out[i] = src[idx[i]].  src: CUDA or pinned-host tensor; idx: CUDA int64; out: CUDA."""
+    if not _device_accessible(src):
+        raise RuntimeError("gather_rows: src must be a CUDA or pinned host tensor")
+    _require_cuda(idx)
+    assert idx.dtype == torch.int64 and idx.is_contiguous()
+    n = idx.numel()
+    if out is None:
+        out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=idx.device)
+    _require_cuda(out)
+    s, s_ld, row_bytes, s_rows = _row_view(src)
+    d, d_ld, d_row_bytes, d_rows = _row_view(out)
+    assert d_row_bytes == row_bytes and d_rows >= n
+    if row_bytes % 4 != 0:
+        raise RuntimeError("gather_rows: rows must be a multiple of 4 bytes")
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_gather_rows(ptr(s), s_ld, s_rows, ptr(idx), n, ptr(d), d_ld, row_bytes, _stream()))
+    return out
+
+
+def scatter_rows(src: Tensor, idx: Tensor, dst: Tensor) -> None:
+    """dst[idx[i]] = src[i].  dst: CUDA or pinned-host tensor."""
+    if not _device_accessible(dst):
+        raise RuntimeError("scatter_rows: dst must be a CUDA or pinned host tensor")
+    _require_cuda(src, idx)
+    assert idx.dtype == torch.int64 and idx.is_contiguous()
+    n = idx.numel()
+    s, s_ld, row_bytes, s_rows = _row_view(src)
+    d, d_ld, d_row_bytes, d_rows = _row_view(dst)
+    assert d_row_bytes == row_bytes and s_rows >= n
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_scatter_rows(ptr(s), s_ld, ptr(idx), n, ptr(d), d_ld, d_rows, row_bytes, _stream()))
+
+
+def copy_slices(src: Tensor, dst: Tensor, offset, count, direction: int) -> int:
+    """direction 0 (pull): dst packed <- src[offset_i : offset_i + count_i];
+    direction 1 (push): dst[offset_i : +count_i] <- src packed.  offset / count: host int64
+    tensors or python lists.  Returns the number of packed rows."""
+    import ctypes
+    if not (_device_accessible(src) and _device_accessible(dst)):
+        raise RuntimeError("copy_slices: tensors must be CUDA or pinned host tensors")
+    off = offset.tolist() if isinstance(offset, Tensor) else list(offset)
+    cnt = count.tolist() if isinstance(count, Tensor) else list(count)
+    if len(off) != len(cnt):
+        raise RuntimeError("Size mismatch")
+    k = len(off)
+    s, s_ld, row_bytes, s_rows = _row_view(src)
+    d, d_ld, d_row_bytes, d_rows = _row_view(dst)
+    # the packed side may be wider than the strided side's crop: rows are min width
+    rb = min(row_bytes, d_row_bytes)
+    o_arr = (ctypes.c_int64 * k)(*off)
+    c_arr = (ctypes.c_int64 * k)(*cnt)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_copy_slices(ptr(s), s_ld, s_rows, ptr(d), d_ld, d_rows,
+                                 ctypes.cast(o_arr, ctypes.c_void_p),
+                                 ctypes.cast(c_arr, ctypes.c_void_p), k, rb, direction, _stream()))
+    return int(sum(cnt))
+
+
+# --------------------------------------------------------------------------------------------
+# relabel
+# --------------------------------------------------------------------------------------------
+class RelabelWorkspace:
+    """Direct-address table over global node ids used by the GPU relabel (one per graph/device).
+    Not shareable between concurrent relabel calls."""
+
+    def __init__(self, num_nodes: int, device):
+        self.num_nodes = int(num_nodes)
+        self.device = torch.device(device)
+        nbytes = lib.incagg_relabel_workspace_bytes(self.num_nodes)
+        self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
+        self.counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.counts_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+        with torch.cuda.device(self.device):
+            check(lib.incagg_relabel_workspace_init(ptr(self.buf), self.num_nodes, _stream()))
+
+
+_WS_CACHE = {}
+
+
+def _workspace_for(num_nodes: int, device) -> RelabelWorkspace:
+    key = (int(num_nodes), str(device))
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        ws = _WS_CACHE[key] = RelabelWorkspace(num_nodes, device)
+    return ws
+
+
+def _relabel(within: bool, rowptr: Tensor, col: Tensor, value: Optional[Tensor], idx: Tensor,
+             bipartite: bool, ws: Optional[RelabelWorkspace], out_int32: bool,
+             nnz_b: Optional[int]):
+    _require_cuda(rowptr, col, value, idx)
+    if rowptr.dtype != torch.int64:
+        raise RuntimeError("relabel: rowptr must be int64")
+    if col.dtype not in (torch.int32, torch.int64):
+        raise RuntimeError("relabel: col must be int32 or int64")
+    if value is not None:
+        if value.dim() != 1:
+            raise RuntimeError("Value tensor must be one-dimensional")
+        if value.dtype != torch.float32:
+            raise RuntimeError("relabel: only float32 edge values are supported on the GPU path")
+    idx = idx.contiguous()
+    dev = rowptr.device
+    N = rowptr.numel() - 1
+    B = idx.numel()
+    if ws is None:
+        ws = _workspace_for(N, dev)
+    st = _stream()
+    if nnz_b is None:
+        LAUNCHES["calls"] += 1
+        check(lib.incagg_relabel_degree_sum(ptr(rowptr), ptr(idx), B, N, ptr(ws.counts), ptr(ws.buf), st))
+        nnz_b = int(ws.counts[0].item())
+    odt = torch.int32 if out_int32 else torch.int64
+    ow = 4 if out_int32 else 8
+    out_rowptr = torch.empty(B + 1, dtype=odt, device=dev)
+    out_col = torch.empty(nnz_b, dtype=odt, device=dev)
+    out_val = torch.empty(nnz_b, dtype=torch.float32, device=dev) if value is not None else None
+    cw = 4 if col.dtype == torch.int32 else 8
+    LAUNCHES["calls"] += 1
+    if within:
+        check(lib.incagg_relabel_one_hop_within_batch(
+            ptr(rowptr), ptr(col), cw, ptr(value), ptr(idx), B, N, nnz_b, ptr(out_rowptr),
+            ptr(out_col), ow, ptr(out_val), ptr(ws.counts), ptr(ws.buf), st))
+        ws.counts_host.copy_(ws.counts, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        nnz_out = int(ws.counts_host[1])
+        out_col = out_col[:nnz_out]
+        if out_val is not None:
+            out_val = out_val[:nnz_out]
+        n_id = idx
+        if not bipartite:
+            # reference quirk (relabel_cpu.cpp:208-211): |n_id_map| = number of DISTINCT batch ids
+            pad = int(torch.unique(idx).numel())
+            out_rowptr = torch.cat([out_rowptr, out_rowptr.new_full((pad,), nnz_out)])
+        return out_rowptr, out_col, out_val, n_id
+    n_id_buf = torch.empty(B + min(nnz_b, N), dtype=torch.int64, device=dev)
+    check(lib.incagg_relabel_one_hop(
+        ptr(rowptr), ptr(col), cw, ptr(value), ptr(idx), B, N, nnz_b, ptr(out_rowptr), ptr(out_col),
+        ow, ptr(out_val), ptr(n_id_buf), ptr(ws.counts), ptr(ws.buf), st))
+    ws.counts_host.copy_(ws.counts, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    H = int(ws.counts_host[0])
+    n_id = n_id_buf[:B + H]
+    if not bipartite:
+        out_rowptr = torch.cat([out_rowptr, out_rowptr.new_full((H,), nnz_b)])
+    return out_rowptr, out_col, out_val, n_id
+
+
+def relabel_one_hop(rowptr, col, value, idx, bipartite: bool = True, ws=None,
+                    out_int32: bool = False, nnz_b: Optional[int] = None):
+    """GPU relabel_one_hop (csrc/cpu/relabel_cpu.cpp:3-108), bit-exact."""
+    return _relabel(False, rowptr, col, value, idx, bipartite, ws, out_int32, nnz_b)
+
+
+def relabel_one_hop_within_batch(rowptr, col, value, idx, bipartite: bool = True, ws=None,
+                                 out_int32: bool = False, nnz_b: Optional[int] = None):
+    """GPU relabel_one_hop_within_batch (csrc/cpu/relabel_cpu.cpp:111-214), bit-exact."""
+    return _relabel(True, rowptr, col, value, idx, bipartite, ws, out_int32, nnz_b)
+
+
+# --------------------------------------------------------------------------------------------
+# async host<->device history transfer (read_async / write_async / synchronize)
+# --------------------------------------------------------------------------------------------
+_PENDING_READS = []  # events of read_async calls not yet synchronised (FIFO, like Thread::results)
+
+
+def read_async(src: Tensor, offset: Optional[Tensor], count: Optional[Tensor], index: Tensor,
+               dst: Tensor, buffer: Optional[Tensor] = None) -> None:
+    """dst[0:sum(count)] <- src[offset_i : +count_i] slices, then dst[sum : sum+|index|] <- src[index].
+
+    Same contract and argument checks as csrc/cuda/async_cuda.cu:14-115, enqueued on the current
+    (non-default) stream.  Differences in mechanism, not in result: the slices are DMA copies, the
+    indexed rows are gathered by a kernel that reads the pinned source through UVA (no CPU
+    index_select, no bounce buffer: `buffer` is accepted for signature compatibility and only
+    validated), and nothing synchronises the stream.
+    """
+    if src.is_cuda:
+        raise RuntimeError("Source tensor must be a CPU tensor")
+    if not dst.is_cuda:
+        raise RuntimeError("Target tensor must be a CUDA tensor")
+    if buffer is not None:
+        if buffer.is_cuda:
+            raise RuntimeError("Buffer tensor must be a CPU tensor")
+        if not buffer.is_pinned():
+            raise RuntimeError("Buffer tensor must be pinned")
+        if not buffer.is_contiguous():
+            raise RuntimeError("Buffer tensor must be contiguous")
+    if not src.is_contiguous():
+        raise RuntimeError("Source tensor must be contiguous")
+    if not dst.is_contiguous():
+        raise RuntimeError("Target tensor must be contiguous")
+    if index.dim() != 1:
+        raise RuntimeError("Index tensor must be one-dimensional")
+    if not src.is_pinned():
+        raise RuntimeError("Source tensor must be pinned")
+    numel = 0
+    if offset is not None:
+        if count is None:
+            raise RuntimeError("Count tensor is undefined")
+        if offset.is_cuda or count.is_cuda:
+            raise RuntimeError("Offset/Count tensor must be a CPU tensor")
+        if offset.dim() != 1 or count.dim() != 1:
+            raise RuntimeError("Offset/Count tensor must be one-dimensional")
+        if offset.numel() != count.numel():
+            raise RuntimeError("Size mismatch")
+        numel = int(count.sum())
+    n_index = index.numel()
+    if buffer is not None and numel + n_index > buffer.size(0):
+        raise RuntimeError("Buffer tensor size too small")
+    if numel + n_index > dst.size(0):
+        raise RuntimeError("Target tensor size too small")
+    stream = torch.cuda.current_stream(dst.device)
+    if stream == torch.cuda.default_stream(dst.device):
+        raise RuntimeError("Asynchronous read requires a non-default CUDA stream")
+    with torch.cuda.device(dst.device):
+        if offset is not None and numel > 0:
+            copy_slices(src, dst, offset, count, 0)
+        if n_index > 0:
+            idx_dev = index if index.is_cuda else index.to(dst.device, dtype=torch.int64, non_blocking=True)
+            gather_rows(src, idx_dev.contiguous(), out=dst[numel:numel + n_index])
+        ev = torch.cuda.Event()
+        ev.record(stream)
+    _PENDING_READS.append(ev)
+
+
+def write_async(src: Tensor, offset: Tensor, count: Tensor, dst: Tensor) -> None:
+    """dst[offset_i : +count_i] <- src[s : s+count_i] (csrc/cuda/async_cuda.cu:117-165), D2H DMA
+    copies on the current non-default stream; no trailing stream synchronise."""
+    if not src.is_cuda:
+        raise RuntimeError("Source tensor must be a CUDA tensor")
+    if offset.is_cuda or count.is_cuda:
+        raise RuntimeError("Offset/Count tensor must be a CPU tensor")
+    if dst.is_cuda:
+        raise RuntimeError("Target tensor must be a CPU tensor")
+    if not dst.is_pinned():
+        raise RuntimeError("Target tensor must be pinned")
+    if not src.is_contiguous():
+        raise RuntimeError("Index tensor must be contiguous")
+    if not dst.is_contiguous():
+        raise RuntimeError("Target tensor must be contiguous")
+    if offset.dim() != 1 or count.dim() != 1:
+        raise RuntimeError("Offset/Count tensor must be one-dimensional")
+    if offset.numel() != count.numel():
+        raise RuntimeError("Size mismatch")
+    stream = torch.cuda.current_stream(src.device)
+    if stream == torch.cuda.default_stream(src.device):
+        raise RuntimeError("Asynchronous write requires a non-default CUDA stream")
+    with torch.cuda.device(src.device):
+        copy_slices(src, dst, offset, count, 1)
+
+
+def synchronize() -> None:
+    """Wait for the oldest outstanding read_async (Thread::synchronize, csrc/thread.h:64-69)."""
+    if _PENDING_READS:
+        _PENDING_READS.pop(0).synchronize()
+
+
+# --------------------------------------------------------------------------------------------
+# torch.ops.torch_geometric_autoscale.* registration (the reference's plugin surface)
+# --------------------------------------------------------------------------------------------
+_REGISTERED = False
+
+
+def register_reference_ops() -> None:
+    """Expose the five reference op names backed by the CUDA library.  Idempotent."""
+    global _REGISTERED
+    if _REGISTERED:
+        return
+    try:
+        lib_def = torch.library.Library("torch_geometric_autoscale", "DEF")
+    except RuntimeError:
+        _REGISTERED = True  # namespace already defined (e.g. the reference's own .so is loaded)
+        return
+    lib_def.define("relabel_one_hop(Tensor rowptr, Tensor col, Tensor? value, Tensor idx, bool bipartite)"
+                   " -> (Tensor, Tensor, Tensor?, Tensor)")
+    lib_def.define("relabel_one_hop_within_batch(Tensor rowptr, Tensor col, Tensor? value, Tensor idx, "
+                   "bool bipartite) -> (Tensor, Tensor, Tensor?, Tensor)")
+    lib_def.define("read_async(Tensor src, Tensor? offset, Tensor? count, Tensor index, Tensor(a!) dst, "
+                   "Tensor buffer) -> ()")
+    lib_def.define("write_async(Tensor src, Tensor offset, Tensor count, Tensor(a!) dst) -> ()")
+    lib_def.define("synchronize() -> ()")
+
+    def _rl(rowptr, col, value, idx, bipartite):
+        return relabel_one_hop(rowptr, col, value, idx, bipartite)
+
+    def _rlw(rowptr, col, value, idx, bipartite):
+        return relabel_one_hop_within_batch(rowptr, col, value, idx, bipartite)
+
+    def _cpu_reject(*args, **kwargs):
+        raise RuntimeError("incagg_b200: this operator runs on CUDA tensors only (no CPU fallback)")
+
+    lib_def.impl("relabel_one_hop", _rl, "CUDA")
+    lib_def.impl("relabel_one_hop_within_batch", _rlw, "CUDA")
+    lib_def.impl("relabel_one_hop", _cpu_reject, "CPU")
+    lib_def.impl("relabel_one_hop_within_batch", _cpu_reject, "CPU")
+    lib_def.impl("read_async", lambda src, offset, count, index, dst, buffer:
+                 read_async(src, offset, count, index, dst, buffer), "CompositeExplicitAutograd")
+    lib_def.impl("write_async", lambda src, offset, count, dst: write_async(src, offset, count, dst),
+                 "CompositeExplicitAutograd")
+    lib_def.impl("synchronize", lambda: synchronize(), "CompositeExplicitAutograd")
+    register_reference_ops._lib = lib_def  # keep alive
+    _REGISTERED = True

@@ -1,0 +1,235 @@
+"""A minimal ``SparseTensor`` with the surface the reference's models and loader use
+(SURVEY.md §8b "implicit third-party interface"): torch_sparse is not a dependency here.
+
+Storage is device-resident CSR with **int32** rowptr/col (half the index traffic of torch_sparse's
+int64) and optional fp32 values; the transposed CSR that the backward SpMM walks is built on
+first use by the counting-sort transpose kernel and cached on the object, so a batch structure
+that is reused (layers of one step, epochs of a fixed partition) pays for it once.
+
+    adj @ x, adj.matmul(x, reduce=)       -> hand-written SpMM kernels (ops.spmm_raw), with autograd
+    adj.csr(), adj.storage.row()/col()/value()/rowcount(), size(), sparse_sizes(), nnz(),
+    set_value(), to(), t()
+"""
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import ops
+
+
+class _Storage:
+    def __init__(self, owner: "SparseTensor"):
+        self._o = owner
+
+    def rowptr(self) -> Tensor:
+        return self._o.rowptr.to(torch.int64)
+
+    def row(self) -> Tensor:
+        o = self._o
+        counts = (o.rowptr[1:] - o.rowptr[:-1]).to(torch.int64)
+        return torch.repeat_interleave(torch.arange(o.size(0), device=o.device), counts)
+
+    def col(self) -> Tensor:
+        return self._o.col.to(torch.int64)
+
+    def value(self) -> Optional[Tensor]:
+        return self._o.value
+
+    def rowcount(self) -> Tensor:
+        o = self._o
+        return (o.rowptr[1:] - o.rowptr[:-1]).to(torch.int64)
+
+
+class SparseTensor:
+    def __init__(self, rowptr: Optional[Tensor] = None, row: Optional[Tensor] = None,
+                 col: Optional[Tensor] = None, value: Optional[Tensor] = None,
+                 sparse_sizes: Optional[Tuple[int, int]] = None, is_sorted: bool = False,
+                 trust_data: bool = False):
+        assert col is not None
+        if rowptr is None:
+            assert row is not None and sparse_sizes is not None
+            M = int(sparse_sizes[0])
+            row = row.to(torch.int64)
+            if not is_sorted:
+                # sort by (row, col) like torch_sparse's constructor
+                key = row * int(sparse_sizes[1]) + col.to(torch.int64)
+                perm = torch.argsort(key, stable=True)
+                row, col = row[perm], col[perm]
+                value = value[perm] if value is not None else None
+            counts = torch.bincount(row, minlength=M)
+            rowptr = torch.zeros(M + 1, dtype=torch.int64, device=col.device)
+            torch.cumsum(counts, 0, out=rowptr[1:])
+        M = rowptr.numel() - 1
+        if sparse_sizes is None:
+            N = int(col.max()) + 1 if col.numel() > 0 else 0
+            sparse_sizes = (M, max(M, N))
+        self._sizes = (int(sparse_sizes[0]), int(sparse_sizes[1]))
+        # rowptr may carry the non-bipartite padding (extra rows with no edges)
+        assert rowptr.numel() - 1 == self._sizes[0], "rowptr does not match sparse_sizes"
+        self.rowptr = rowptr.to(torch.int32).contiguous()
+        self.col = col.to(torch.int32).contiguous()
+        self.value = value.contiguous() if value is not None else None
+        self.storage = _Storage(self)
+        self._t = None  # cached (t_rowptr, t_col, t_val)
+
+    # ---- shape -------------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.col.device
+
+    def size(self, dim: int) -> int:
+        return self._sizes[dim]
+
+    def sizes(self):
+        return list(self._sizes)
+
+    def sparse_sizes(self) -> Tuple[int, int]:
+        return self._sizes
+
+    def nnz(self) -> int:
+        return self.col.numel()
+
+    def csr(self):
+        """(rowptr, col, value) with int64 indices, as torch_sparse returns them."""
+        return self.rowptr.to(torch.int64), self.col.to(torch.int64), self.value
+
+    def csr32(self):
+        return self.rowptr, self.col, self.value
+
+    def to(self, device, non_blocking: bool = False) -> "SparseTensor":
+        device = torch.device(device)
+        if device == self.device:
+            return self
+        out = SparseTensor.__new__(SparseTensor)
+        out._sizes = self._sizes
+        out.rowptr = self.rowptr.to(device, non_blocking=non_blocking)
+        out.col = self.col.to(device, non_blocking=non_blocking)
+        out.value = self.value.to(device, non_blocking=non_blocking) if self.value is not None else None
+        out.storage = _Storage(out)
+        out._t = None
+        return out
+
+    def cuda(self):
+        return self.to("cuda")
+
+    def set_value(self, value: Optional[Tensor], layout: Optional[str] = None) -> "SparseTensor":
+        out = SparseTensor.__new__(SparseTensor)
+        out._sizes = self._sizes
+        out.rowptr, out.col = self.rowptr, self.col
+        out.value = value.contiguous() if value is not None else None
+        out.storage = _Storage(out)
+        out._t = None
+        if self._t is not None and value is None:
+            out._t = (self._t[0], self._t[1], None)
+        return out
+
+    def masked_select_nnz(self, mask: Tensor, layout: Optional[str] = None) -> "SparseTensor":
+        row = self.storage.row()[mask]
+        col = self.col[mask]
+        val = self.value[mask] if self.value is not None else None
+        return SparseTensor(row=row, col=col, value=val, sparse_sizes=self._sizes, is_sorted=True)
+
+    # ---- transposed view for the backward pass ------------------------------------------
+    def t_csr(self):
+        """CSR of A^T: (t_rowptr [cols+1], t_col, t_val), built once by the transpose kernel."""
+        if self._t is None:
+            t_rowptr, t_col, t_val, _ = ops.csr_transpose(self.rowptr, self.col, self.value,
+                                                         self._sizes[0], self._sizes[1])
+            self._t = (t_rowptr, t_col, t_val)
+        return self._t
+
+    def t(self) -> "SparseTensor":
+        t_rowptr, t_col, t_val = self.t_csr()
+        out = SparseTensor.__new__(SparseTensor)
+        out._sizes = (self._sizes[1], self._sizes[0])
+        out.rowptr, out.col, out.value = t_rowptr, t_col, t_val
+        out.storage = _Storage(out)
+        out._t = (self.rowptr, self.col, self.value)
+        return out
+
+    # ---- products ------------------------------------------------------------------------
+    def matmul(self, x: Tensor, reduce: str = "sum", grad_rows: Optional[int] = None) -> Tensor:
+        return spmm(self, x, reduce=reduce, grad_rows=grad_rows)
+
+    def __matmul__(self, x: Tensor) -> Tensor:
+        return spmm(self, x, reduce="sum")
+
+    def __repr__(self):
+        return (f"SparseTensor(rows={self._sizes[0]}, cols={self._sizes[1]}, nnz={self.nnz()}, "
+                f"value={'fp32' if self.value is not None else None}, device={self.device})")
+
+
+class _SpMM(torch.autograd.Function):
+    """reduce(A, x) with grad only w.r.t. x (edge values carry no gradient in the reference's
+    pipelines: gcn_norm weights are constants)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, adj: SparseTensor, reduce: str, grad_rows: Optional[int]):
+        ctx.adj, ctx.reduce, ctx.n_src, ctx.grad_rows = adj, reduce, x.size(0), grad_rows
+        if reduce in ("min", "max"):
+            out, arg = ops.spmm_raw(adj.rowptr, adj.col, adj.value, x, reduce, rows=adj.size(0),
+                                    return_arg=True)
+            ctx.save_for_backward(arg)
+            return out
+        return ops.spmm_raw(adj.rowptr, adj.col, adj.value, x, reduce, rows=adj.size(0))
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        adj, reduce = ctx.adj, ctx.reduce
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        grad_out = grad_out.contiguous()
+        if reduce in ("min", "max"):
+            (arg,) = ctx.saved_tensors
+            return ops.spmm_minmax_bwd_raw(adj.col, adj.value, arg, grad_out, ctx.n_src), None, None, None
+        if reduce == "mean":
+            deg = (adj.rowptr[1:] - adj.rowptr[:-1]).clamp_(min=1).to(grad_out.dtype)
+            grad_out = grad_out / deg.unsqueeze(1)
+        return _transposed_product(adj, grad_out, ctx.n_src, ctx.grad_rows), None, None, None
+
+
+def _transposed_product(adj: SparseTensor, grad_out: Tensor, n_src: int, grad_rows: Optional[int]):
+    """grad_x = A^T grad_out.  With grad_rows = k only the first k source rows are computed (the
+    rest of x was a constant, e.g. pulled history rows) and the remainder is returned as zeros."""
+    t_rowptr, t_col, t_val = adj.t_csr()
+    if grad_rows is None or grad_rows >= n_src:
+        return ops.spmm_raw(t_rowptr, t_col, t_val, grad_out, "sum", rows=n_src)
+    gx = torch.zeros((n_src, grad_out.size(1)), dtype=grad_out.dtype, device=grad_out.device)
+    ops.spmm_raw(t_rowptr, t_col, t_val, grad_out, "sum", rows=grad_rows, out=gx[:grad_rows])
+    return gx
+
+
+def spmm(adj: SparseTensor, x: Tensor, reduce: str = "sum", grad_rows: Optional[int] = None) -> Tensor:
+    """torch_sparse.matmul / torch_geometric.utils.spmm replacement (graphsage.py:30,634)."""
+    if reduce == "add":
+        reduce = "sum"
+    if x.size(0) < adj.size(1):
+        raise RuntimeError(f"spmm: x has {x.size(0)} rows but the adjacency has {adj.size(1)} columns")
+    return _SpMM.apply(x, adj, reduce, grad_rows)
+
+
+class _SpMMDelta(torch.autograd.Function):
+    """h = reduce(A, x - M_in) + M_ag, fused (gcn2.py:255).  M_in / M_ag are constants."""
+
+    @staticmethod
+    def forward(ctx, x, adj, m_in, m_ag, n_id, reduce):
+        ctx.adj, ctx.reduce, ctx.n_src = adj, reduce, x.size(0)
+        return ops.spmm_delta_raw(adj.rowptr, adj.col, adj.value, x, m_in, m_ag, n_id, reduce,
+                                  rows=adj.size(0))
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        adj = ctx.adj
+        grad_out = grad_out.contiguous()
+        if ctx.reduce == "mean":
+            deg = (adj.rowptr[1:] - adj.rowptr[:-1]).clamp_(min=1).to(grad_out.dtype)
+            grad_out = grad_out / deg.unsqueeze(1)
+        return _transposed_product(adj, grad_out, ctx.n_src, None), None, None, None, None, None
+
+
+def spmm_delta(adj: SparseTensor, x: Tensor, m_in: Tensor, m_ag: Tensor,
+               n_id: Optional[Tensor] = None, reduce: str = "sum") -> Tensor:
+    """Fused incremental-aggregation update  A_BB (x - M_in) + M_ag  (one kernel instead of the
+    reference's sub + SpMM + add + two clones)."""
+    return _SpMMDelta.apply(x, adj, m_in, m_ag, n_id, reduce)

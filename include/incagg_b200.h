@@ -1,0 +1,191 @@
+/*
+ * incagg_b200.h — C ABI of the B200-native IncAgg-GNN propagation hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain
+ * pointers and sizes (no torch types), a cudaStream_t passed as `void*`, returns
+ * an `int` status (0 = ok, <0 = error, text via incagg_last_error()) and never
+ * throws.  All work is enqueued on `stream`; nothing here synchronises the
+ * device or the stream unless the comment says so.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   torch_sparse.matmul / SparseTensor.__matmul__ / torch_geometric.utils.spmm
+ *       call sites: torch_geometric_autoscale/models/gcn.py:143,164,241,262,296,361,386,403
+ *                   models/gcn2.py:130,142,255,305,336,454,477,499
+ *                   models/appnp.py:85,89,122,130,152,253,284,306
+ *                   models/graphsage.py:634,683,898,928,952   models/pna.py:75
+ *   History.pull / History.push            torch_geometric_autoscale/history.py:33-65
+ *   read_async / write_async / synchronize csrc/async.cpp:13-48, csrc/cuda/async_cuda.cu:12-165
+ *   relabel_one_hop                        csrc/relabel.cpp:10-24, csrc/cpu/relabel_cpu.cpp:3-108
+ *   relabel_one_hop_within_batch           csrc/relabel.cpp:27-38, csrc/cpu/relabel_cpu.cpp:111-214
+ *
+ * Index conventions: batch-local CSR structures (what the SpMM kernels read)
+ * use int32 rowptr/col; the global graph handed to relabel uses int64 rowptr and
+ * int32 or int64 col; node ids (`idx`, `n_id`) are int64 as in the reference.
+ * Feature matrices are fp32 row-major with an explicit leading dimension (in
+ * elements) so that history-table slices can be read in place.
+ */
+#ifndef INCAGG_B200_H
+#define INCAGG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* incagg_stream_t; /* a cudaStream_t */
+
+/* status codes */
+#define INCAGG_OK 0
+#define INCAGG_ERR_INVALID (-1)     /* bad argument (what the reference AT_ASSERTMs) */
+#define INCAGG_ERR_CUDA (-2)        /* CUDA runtime error, text in incagg_last_error() */
+#define INCAGG_ERR_UNSUPPORTED (-3) /* valid request this build does not implement */
+
+/* reducers: torch_sparse.matmul(reduce=...) */
+#define INCAGG_REDUCE_SUM 0
+#define INCAGG_REDUCE_MEAN 1
+#define INCAGG_REDUCE_MIN 2
+#define INCAGG_REDUCE_MAX 3
+
+/* ---- library --------------------------------------------------------- */
+int incagg_version(void);
+/* Thread-local text of the last error returned on this thread ("" if none). */
+const char* incagg_last_error(void);
+/* SM count and compute capability of the current device. */
+int incagg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- CSR SpMM -------------------------------------------------------- */
+/*
+ * out[i, 0:F] = reduce_{e in [rowptr[i], rowptr[i+1])} val[e] * X[col[e], 0:F]
+ * Replaces torch_sparse.matmul(adj_t, X, reduce) (SURVEY §8a "CSR SpMM").
+ *   val      nullable (treated as 1.0)
+ *   reduce   SUM / MEAN (sum / max(deg,1)) / MIN / MAX (empty row -> 0)
+ *   arg_out  nullable; for MIN/MAX receives, per output element, the edge
+ *            position e that won (first winner in CSR order), -1 for empty rows;
+ *            leading dimension lda (elements)
+ * The transposed call (backward, grad_X = A^T grad_out) is the same function on
+ * the CSR of A^T (incagg_csr_transpose).
+ */
+int incagg_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col, const float* val,
+                    const float* X, int64_t ldx, float* out, int64_t ldo, int32_t* arg_out,
+                    int64_t lda, int64_t rows, int32_t F, incagg_stream_t stream);
+
+/*
+ * Fused incremental-aggregation update (reference: gcn.py:241, gcn2.py:255,
+ * appnp.py:122, graphsage.py:634):
+ *     out[i] = reduce_e val[e] * (x[col[e]] - M_in[g(col[e])]) + M_ag[g(i)]
+ * where g(r) = n_id[r] when n_id != NULL (M_in / M_ag are whole history tables
+ * indexed by global node id; this fuses the History pull) and g(r) = r otherwise
+ * (M_in / M_ag are the already-pulled [B, >=F] slices).  reduce is SUM or MEAN
+ * (MEAN divides the delta term by max(in-batch degree, 1), graphsage.py:634).
+ */
+int incagg_spmm_delta(int reduce, const int32_t* rowptr, const int32_t* col, const float* val,
+                      const float* x, int64_t ldx, const float* m_in, int64_t ld_in,
+                      const float* m_ag, int64_t ld_ag, const int64_t* n_id, float* out,
+                      int64_t ldo, int64_t rows, int32_t F, incagg_stream_t stream);
+
+/*
+ * Backward of MIN/MAX: grad_X[col[arg[i,f]], f] += val[arg[i,f]] * grad_out[i,f]
+ * (atomic scatter; grad_X must be zero-filled by the caller).
+ */
+int incagg_spmm_minmax_bwd(const int32_t* col, const float* val, const int32_t* arg, int64_t lda,
+                           const float* grad_out, int64_t ldg, float* grad_x, int64_t ldx,
+                           int64_t rows, int32_t F, incagg_stream_t stream);
+
+/*
+ * Fused multi-aggregator propagate for PNA (reference pna.py:66-84 runs K separate
+ * matmul(reduce=aggr) passes).  X is [n_src, K*F]; slab k (columns k*F..(k+1)*F)
+ * is reduced with reducers[k] (host array of K INCAGG_REDUCE_* codes, K <= 8);
+ * the CSR structure is read once.  No arg output (forward / inference use).
+ */
+int incagg_spmm_multi(const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
+                      int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t F, int32_t K,
+                      const int32_t* reducers, incagg_stream_t stream);
+
+/* ---- CSR transpose (CSC view for the backward SpMM) ------------------- */
+/*
+ * Counting-sort transpose of a [rows x cols] CSR with nnz entries.
+ *   t_rowptr [cols+1], t_col [nnz] (source row of each entry), t_val [nnz] (nullable
+ *   iff val is NULL), t_perm [nnz] nullable (original edge position of each entry).
+ * Entries inside a transposed row are ordered by original edge position
+ * (deterministic), so repeated runs reduce in the same order.
+ * workspace: at least incagg_csr_transpose_workspace_bytes(rows, cols, nnz) bytes.
+ */
+size_t incagg_csr_transpose_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz);
+int incagg_csr_transpose(const int32_t* rowptr, const int32_t* col, const float* val, int64_t rows,
+                         int64_t cols, int64_t nnz, int32_t* t_rowptr, int32_t* t_col, float* t_val,
+                         int32_t* t_perm, void* workspace, size_t workspace_bytes,
+                         incagg_stream_t stream);
+
+/* ---- history gather / scatter / slice copies -------------------------- */
+/*
+ * dst[i, :] = src[idx[i], :] for i < n.  Replaces History.pull (history.py:38) and the
+ * CPU index_select + bounce-buffer H2D of read_async (async_cuda.cu:95-110): `src` may be
+ * device memory or pinned (page-locked, UVA-mapped) host memory, `dst` device memory.
+ * Rows are `row_bytes` bytes (multiple of 4); leading dimensions in bytes.  idx is a
+ * device-accessible int64 array.  Also the collate feature gather x[n_id] (loader.py:188-190).
+ */
+int incagg_gather_rows(const void* src, int64_t src_ld_bytes, int64_t src_rows, const int64_t* idx,
+                       int64_t n, void* dst, int64_t dst_ld_bytes, int64_t row_bytes,
+                       incagg_stream_t stream);
+/* dst[idx[i], :] = src[i, :]  (History.push index branch, history.py:58). Out-of-range
+ * indices are skipped and counted in *oob_count (device int32, nullable). */
+int incagg_scatter_rows(const void* src, int64_t src_ld_bytes, const int64_t* idx, int64_t n,
+                        void* dst, int64_t dst_ld_bytes, int64_t dst_rows, int64_t row_bytes,
+                        incagg_stream_t stream);
+/*
+ * Slice copies with HOST offset/count arrays of length k (they are host tensors in the
+ * reference too):
+ *   direction 0 (pull, read_async async_cuda.cu:68-92):  dst[d : d+c_i] = src[offset_i : offset_i+c_i], d += c_i
+ *   direction 1 (push, write_async async_cuda.cu:139-163, History.push history.py:60-65):
+ *                                                        dst[offset_i : +c_i] = src[s : s+c_i], s += c_i
+ * Either side may be pinned host memory (copies then run on the DMA engines).  Bounds are
+ * checked against src_rows / dst_rows as the reference does ("Invalid index").
+ */
+int incagg_copy_slices(const void* src, int64_t src_ld_bytes, int64_t src_rows, void* dst,
+                       int64_t dst_ld_bytes, int64_t dst_rows, const int64_t* offset,
+                       const int64_t* count, int64_t k, int64_t row_bytes, int direction,
+                       incagg_stream_t stream);
+
+/* ---- relabel ---------------------------------------------------------- */
+/*
+ * GPU relabel_one_hop / relabel_one_hop_within_batch, bit-exact with
+ * csrc/cpu/relabel_cpu.cpp (first-seen halo order, last duplicate of idx wins).
+ *
+ * The workspace is a direct-address table over global node ids (2 x int32 per node
+ * plus scan scratch) that is initialised once with incagg_relabel_workspace_init and
+ * left clean by every call.  It must not be shared by concurrent calls.
+ *
+ *   rowptr      [num_nodes+1] int64 (device)       col  [nnz] int32 or int64 (col_width 4/8)
+ *   val         [nnz] fp32, nullable               idx  [B] int64 (device)
+ *   nnz_b       sum of degrees of idx rows (host value; incagg_relabel_degree_sum computes it)
+ *   out_rowptr  [B+1]      out_col [nnz_b]   (index width out_width 4 or 8)
+ *   out_val     [nnz_b] nullable iff val NULL
+ *   n_id_out    capacity B + min(nnz_b, num_nodes); receives idx followed by the halo ids
+ *   counts_out  device int64[2]: {H (number of halo ids), nnz_out}
+ * The non-bipartite padding of out_rowptr (relabel_cpu.cpp:98-101,208-211) is a host-side
+ * concat done by the binding once H is known.
+ */
+size_t incagg_relabel_workspace_bytes(int64_t num_nodes);
+int incagg_relabel_workspace_init(void* workspace, int64_t num_nodes, incagg_stream_t stream);
+/* degsum_out: device int64[1] = sum_i (rowptr[idx[i]+1] - rowptr[idx[i]]) */
+int incagg_relabel_degree_sum(const int64_t* rowptr, const int64_t* idx, int64_t B,
+                              int64_t num_nodes, int64_t* degsum_out, void* workspace,
+                              incagg_stream_t stream);
+int incagg_relabel_one_hop(const int64_t* rowptr, const void* col, int col_width, const float* val,
+                           const int64_t* idx, int64_t B, int64_t num_nodes, int64_t nnz_b,
+                           void* out_rowptr, void* out_col, int out_width, float* out_val,
+                           int64_t* n_id_out, int64_t* counts_out, void* workspace,
+                           incagg_stream_t stream);
+int incagg_relabel_one_hop_within_batch(const int64_t* rowptr, const void* col, int col_width,
+                                        const float* val, const int64_t* idx, int64_t B,
+                                        int64_t num_nodes, int64_t nnz_b, void* out_rowptr,
+                                        void* out_col, int out_width, float* out_val,
+                                        int64_t* counts_out, void* workspace,
+                                        incagg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INCAGG_B200_H */
