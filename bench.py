@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""bench.py — edges/s of one GCNII training epoch on the synthetic ogbn-products shape (BASELINE.json
+metric, config C3) through this repo's hot path, plus the roofline of the dominant kernel, the
+end-to-end figure with host-resident inputs and the CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode gas|incagg]
+                    [--config C3] [--scale S]
+
+A "step" is one training step of the reference's ``mini_train`` loop (main.py:58-92) on one partition
+mini-batch: GPU collate (relabel_one_hop + feature gather) -> forward (SpMM + history push/pull per
+layer) -> loss -> backward (transposed SpMM) -> Adam.  edges/s = sum over the timed steps of
+nnz(batch adjacency) / time; over a whole epoch the batch adjacencies partition nnz(adj_t).
+
+N > 1 (launched by torch.distributed.run, one rank per GPU): partitions are sharded over ranks (rank
+r owns a contiguous block of partitions, their CSR rows, feature rows and history rows); each rank
+trains on its own batches (weak scaling: per-GPU work fixed = the full C3 graph per rank would not be
+"the products shape", so every rank holds its 1/N... see DESIGN.md §multi-GPU) and gradients are
+all-reduced with NCCL.
+
+One JSON line on stdout (rank 0).  Nothing here reads /root/reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=150)   # one full C3 epoch (150 partitions, batch 1)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="gas", choices=["gas", "incagg"])
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--scale", type=int, default=1, help="divide nodes and edges (debug only)")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    return ap.parse_args()
+
+
+# ---- clocks ----------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- CPU baseline (oracle) ----------------------------------------------------------------------------
+def cpu_baseline(run, mode: str, n_steps: int, threads: int):
+    """Times the CPU restatement of the same training step (oracle/gas.py: C relabel + torch CPU
+    sparse aggregation) on the first `n_steps` partitions of the same graph and weights."""
+    from oracle import gas
+    torch.set_num_threads(threads)
+    data, ptr, conf = run["data"], run["ptr"], run["conf"]
+    rp, col, val = [t.cpu() if t is not None else None for t in data.adj_t.csr()]
+    adj = gas.Adj(rp, col, val, data.num_nodes, data.num_nodes)
+    x, y, mask = data.x.cpu(), data.y.cpu(), data.train_mask.cpu()
+    model = gas.OracleGNN(conf["model"], run["model"].state_dict(), data.num_nodes, run["in_channels"],
+                          out_channels=run["out_channels"], dtype=torch.float32, **conf["architecture"])
+    if mode == "incagg":
+        for l in range(model.num_layers):  # any consistent-size tables: the arithmetic is the same
+            model.histories[l].emb.copy_(run["model"].histories[l].emb.cpu())
+            model.histories_ag[l].emb.copy_(run["model"].histories_ag[l].emb.cpu())
+    else:
+        for l in range(model.num_layers):
+            model.histories[l].emb.copy_(run["model"].histories[l].emb.cpu())
+    opt = torch.optim.Adam(model.parameters(), lr=conf["lr"])
+    bs = conf["batch_size"]
+    edges, t_total = 0, 0.0
+    for s in range(n_steps + 1):
+        group = list(range(s * bs, min((s + 1) * bs, ptr.numel() - 1)))
+        t0 = time.perf_counter()
+        b = gas.collate(adj, x, y, mask, ptr, group, within_batch=(mode == "incagg"))
+        gas.train_epoch(model, [b], opt, vr=(mode == "incagg"), grad_norm=conf["grad_norm"])
+        dt = time.perf_counter() - t0
+        if s > 0:  # first step is warm-up
+            t_total += dt
+            edges += int(adj.rowptr[int(ptr[group[-1] + 1])] - adj.rowptr[int(ptr[group[0]])])
+    return edges / t_total, edges, t_total
+
+
+# ---- one measured pass ------------------------------------------------------------------------------
+def batch_edges(run, batch_ids):
+    rp = run["train_loader"]._rowptr_host
+    ptr = run["ptr"]
+    return sum(int(rp[int(ptr[b + 1])]) - int(rp[int(ptr[b])]) for b in batch_ids)
+
+
+def timed_steps(run, mode, warmup, steps, dist, e2e=False):
+    """W warm-up + K timed training steps.  Returns (seconds, edges, h2d_bytes, d2h_bytes)."""
+    from incagg_gnn_b200.train import mini_train  # noqa: F401  (same loop body, unrolled for timing)
+    from incagg_gnn_b200.utils import dropout
+    model, opt, loader, conf = run["model"], run["optimizer"], run["train_loader"], run["conf"]
+    vr = mode == "incagg"
+    model.train()
+    order = []
+    sampler_iter = iter(loader._batch_sampler)
+
+    def next_ids():
+        nonlocal sampler_iter
+        try:
+            return next(sampler_iter)
+        except StopIteration:
+            sampler_iter = iter(loader._batch_sampler)
+            return next(sampler_iter)
+
+    params = [p for p in model.parameters() if p.requires_grad]
+    h2d = d2h = 0
+
+    def one_step(ids):
+        nonlocal h2d, d2h
+        batch, B, n_id, offset, count = loader._collate(ids)
+        x, adj_t = batch.x, batch.adj_t
+        y, m = batch.y[:B], batch.train_mask[:B]
+        if vr:
+            out = model.VR_call(x, adj_t, B, n_id, offset, count)["out"]
+        else:
+            out = model(x, adj_t, B, n_id, offset, count)["out"]
+        opt.zero_grad(set_to_none=True)
+        w = m.to(out.dtype)
+        loss = (torch.nn.functional.cross_entropy(out, y, reduction="none") * w).sum() / w.sum().clamp(min=1.)
+        loss.backward()
+        if dist is not None:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat /= dist.get_world_size()
+            o = 0
+            for p in params:
+                p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad)); o += p.numel()
+        if conf["grad_norm"] is not None:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), conf["grad_norm"])
+        opt.step()
+        if e2e:
+            lv = float(loss)  # device -> host read of the step's result
+            d2h += 4
+            # bytes that crossed the host<->device boundary this step (counted from the tensors)
+            h2d += x.numel() * 4 + y.numel() * 8 + m.numel() + adj_t.nnz() * 8 + (B + 1) * 8
+            D = model.histories[0].embedding_dim
+            H = n_id.numel() - B
+            L = model.num_layers
+            if vr:
+                h2d += 2 * L * B * D * 4
+            else:
+                n_pull = len(model._gas_pull_histories())
+                h2d += n_pull * H * D * 4
+                d2h += n_pull * B * D * 4
+            return lv
+        return None
+
+    for _ in range(warmup):
+        one_step(next_ids())
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    h2d = d2h = 0
+    ids_list = [next_ids() for _ in range(steps)]
+    edges = sum(batch_edges(run, ids) for ids in ids_list)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ev0.record()
+    for ids in ids_list:
+        one_step(ids)
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if dist is not None:
+        dist.barrier()
+    sec = ev0.elapsed_time(ev1) / 1e3
+    return sec, edges, h2d, d2h, wall
+
+
+def spmm_roofline(run, peaks):
+    """Dominant kernel = spmm_rows_kernel (forward aggregation of one batch).  Timed alone with CUDA
+    events on the launching stream, L2 flushed (256 MB write) before every launch, over 20 different
+    partition batches.  Algorithmic bytes per launch: SURVEY.md §8d (int32 indices)."""
+    from incagg_gnn_b200 import ops
+    loader, model = run["train_loader"], run["model"]
+    F = model.hidden_channels
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    tot_b = tot_t = 0.0
+    n = min(20, loader.num_parts)
+    for b in range(n):
+        sub = loader.compute_subgraph([b])
+        adj = sub.data.adj_t
+        x = torch.randn(adj.size(1), F, device="cuda")
+        out = torch.empty(adj.size(0), F, device="cuda")
+        ops.spmm_raw(adj.rowptr, adj.col, adj.value, x, "sum", out=out)  # warm the code path
+        flush.fill_(b & 0xff)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.spmm_raw(adj.rowptr, adj.col, adj.value, x, "sum", out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        rows, nnz, rsrc = adj.size(0), adj.nnz(), adj.size(1)
+        tot_b += nnz * 8 + (rows + 1) * 4 + rsrc * F * 4 + rows * F * 4
+        tot_t += e0.elapsed_time(e1) / 1e3
+    achieved = tot_b / tot_t / 1e9
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return {"bound": "hbm", "kernel": "spmm_rows_kernel<SUM,F=%d> fwd, one products batch, cold L2" % F,
+            "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback",
+            "bytes_per_launch": int(tot_b / n), "us_per_launch": round(tot_t / n * 1e6, 2),
+            "traffic": None}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+
+    import incagg_gnn_b200  # noqa: F401
+    from incagg_gnn_b200 import _lib
+    from incagg_gnn_b200.train import build, mini_test
+
+    vr = args.mode == "incagg"
+    # weak scaling: every rank holds and trains its own products-shaped shard (seed differs per rank)
+    run = build(args.config, device=dev, seed=args.seed + rank, scale=args.scale,
+                overrides=dict(VR_update=vr), shuffle=True)
+    model = run["model"]
+    mini_test(model, run["eval_loader"], VR_update=vr)  # fill the histories (main.py:211-215), untimed
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    sec, edges, _, _, wall = timed_steps(run, args.mode, args.warmup, args.steps, dist)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # max over ranks of the device time; edges summed over ranks
+    if dist is not None:
+        t = torch.tensor([sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e = torch.tensor([edges], device=dev, dtype=torch.float64)
+        dist.all_reduce(e)
+        sec, edges = float(t), float(e)
+    value = edges / sec
+
+    e2e = None
+    if not args.no_e2e:
+        data_pack = (run["data"], run["ptr"], run["in_channels"], run["out_channels"])
+        run_h = build(args.config, device=dev, seed=args.seed + rank, scale=args.scale,
+                      overrides=dict(VR_update=vr), shuffle=True, host_resident=True,
+                      history_device=None, data=data_pack)
+        run_h["model"].load_state_dict(model.state_dict(), strict=False)
+        mini_test(run_h["model"], run_h["eval_loader"], VR_update=vr)
+        torch.cuda.synchronize()
+        k = min(args.steps, 50)
+        s2, ed2, h2d, d2h, _ = timed_steps(run_h, args.mode, min(args.warmup, 5), k, dist, e2e=True)
+        if dist is not None:
+            t = torch.tensor([s2], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e = torch.tensor([ed2], device=dev, dtype=torch.float64)
+            dist.all_reduce(e)
+            s2, ed2 = float(t), float(e)
+        e2e = {"value": ed2 / s2, "unit": "edges/s", "h2d_bytes_per_step": int(h2d / k),
+               "d2h_bytes_per_step": int(d2h / k), "steps": k,
+               "layout": "graph, features, labels and all history tables in pinned host memory; "
+                         "AsyncIOPool staging; loss read back every step"}
+        del run_h
+        torch.cuda.empty_cache()
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    roof = spmm_roofline(run, peaks)
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, ed, tt = cpu_baseline(run, args.mode, args.cpu_steps, threads)
+        cpu = {"value": v, "unit": "edges/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_steps} training steps (partitions 1..{args.cpu_steps}) of the same "
+                         f"graph/weights, {ed} edges in {tt:.1f} s, oracle/gas.py fp32"}
+    conf = run["conf"]
+    line = {
+        "metric": "edges/s (train epoch, GCNII, products-shape)", "value": value, "unit": "edges/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {conf['model']} {args.mode.upper()} training steps on the "
+                               f"synthetic {conf['dataset']} shape ({run['data'].num_nodes} nodes, "
+                               f"nnz(adj_t)={run['data'].adj_t.nnz()} directed non-zeros incl. self loops; the "
+                               f"named 61.9M is used as directed nnz after symmetrisation), "
+                               f"{conf['num_parts']} parts, batch {conf['batch_size']}, per GPU",
+                   "mode": args.mode, "scale": args.scale,
+                   "l2": "inputs larger than L2: every step reads a different partition (graph + features "
+                         "+ 10 history tables = 14 GB per epoch)",
+                   "histories": "HBM-resident"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+        "cpu_baseline": cpu, "edges_timed": edges, "wall_s": wall,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def reference_arm(args, rank, world):
+    """The reference's CPU implementation of the path on the host cores: the reference package itself
+    cannot be imported (torch_sparse / torch_geometric absent) and has no CPU-only execution path
+    (SURVEY F6g), so this arm times the oracle port (oracle/gas.py + the C relabel restatement) with all
+    host threads on the same config, metric and unit.  Rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    from oracle import gas
+    # build the same graph on the CPU with the product's generator (inputs only), no GPU needed
+    from importlib import import_module
+    import incagg_gnn_b200  # noqa: F401  (generators / config table only; no kernels are launched)
+    train = import_module("incagg_gnn_b200.train")
+    tga = incagg_gnn_b200
+    conf = dict(train.CONFIGS[args.config])
+    gen_dev = "cuda" if torch.cuda.is_available() else "cpu"
+    data, fin, fout = tga.get_data("", conf["dataset"], seed=args.seed, device=gen_dev, scale=args.scale,
+                                   num_parts=conf["num_parts"])
+    data = data.to("cpu")
+    rp, col, _ = data.adj_t.csr()
+    adj = gas.Adj(rp, col, None, data.num_nodes, data.num_nodes)
+    if conf["loop"]:
+        adj = gas.set_diag(adj)
+    if conf["norm"]:
+        adj = gas.gcn_norm(adj)
+    ptr = tga.metis(data.adj_t, conf["num_parts"], log=False)[1] if False else None
+    from incagg_gnn_b200.metis import block_ptr
+    ptr = block_ptr(data.num_nodes, conf["num_parts"])
+    torch.manual_seed(args.seed)
+    a = conf["architecture"]
+    H, L = a["hidden_channels"], a["num_layers"]
+    g = torch.Generator().manual_seed(args.seed)
+
+    def glorot(o, i):
+        s = (6.0 / (o + i)) ** 0.5
+        return (torch.rand(o, i, generator=g) * 2 - 1) * s
+
+    st = {"lins.0.weight": glorot(H, fin), "lins.0.bias": torch.zeros(H),
+          "lins.1.weight": glorot(fout, H), "lins.1.bias": torch.zeros(fout)}
+    for l in range(L):
+        st[f"convs.{l}.weight1"] = glorot(H, H)
+        st[f"convs.{l}.weight2"] = glorot(H, H)
+    assert conf["model"] == "GCN2", "reference arm is wired for the headline config"
+    model = gas.OracleGNN("GCN2", st, data.num_nodes, fin, out_channels=fout, dtype=torch.float32, **a)
+    opt = torch.optim.Adam(model.parameters(), lr=conf["lr"])
+    vr = args.mode == "incagg"
+    bs = conf["batch_size"]
+    P = conf["num_parts"]
+
+    def step(s):
+        group = [(s * bs + j) % P for j in range(bs)]
+        b = gas.collate(adj, data.x, data.y, data.train_mask, ptr, group, within_batch=vr)
+        gas.train_epoch(model, [b], opt, vr=vr, grad_norm=conf["grad_norm"])
+        return sum(int(adj.rowptr[int(ptr[p + 1])] - adj.rowptr[int(ptr[p])]) for p in group)
+
+    steps = min(args.steps, 40)  # bounded sample: each CPU step is ~1 s
+    for s in range(min(args.warmup, 2)):
+        step(s)
+    edges, t0 = 0, time.perf_counter()
+    for s in range(steps):
+        edges += step(args.warmup + s)
+    sec = time.perf_counter() - t0
+    v = edges / sec
+    line = {
+        "impl": "reference", "metric": "edges/s (train epoch, GCNII, products-shape)", "value": v,
+        "unit": "edges/s", "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 2),
+        "ms_per_step": sec / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: GCN2 {args.mode.upper()} training steps, synthetic "
+                               f"{conf['dataset']} shape ({data.num_nodes} nodes, nnz={adj.col.numel()}), "
+                               f"{P} parts, batch {bs}; CPU port of the reference path (oracle/), "
+                               f"{steps} steps sampled", "mode": args.mode, "scale": args.scale},
+        "cpu_baseline": {"value": v, "unit": "edges/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} training steps, {edges} edges in {sec:.1f} s"},
+        "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,7 @@ P = c_void_p
 _PROTOS = {
     "incagg_version": (c_int, []),
     "incagg_last_error": (c_char_p, []),
+    "incagg_launch_count": (c_int64, []),
     "incagg_device_info": (c_int, [P, P, P]),
     "incagg_spmm_csr": (c_int, [c_int, P, P, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, P]),
     "incagg_spmm_delta": (c_int, [c_int, P, P, P, P, c_int64, P, c_int64, P, c_int64, P, P, c_int64,
@@ -86,6 +87,11 @@ def last_error() -> str:
 def check(rc: int):
     if rc != 0:
         raise IncAggError(rc, last_error())
+
+
+def launch_count() -> int:
+    """Kernels launched by libincagg_b200.so in this process (bench.py's gpu_launches)."""
+    return int(lib.incagg_launch_count())
 
 
 def ptr(t):

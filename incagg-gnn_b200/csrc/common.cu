@@ -18,6 +18,10 @@ int set_err(int code, const char* fmt, ...) {
   return code;
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int sm_count() {
   static thread_local int cached[16] = {0};
   int dev = 0;
@@ -33,7 +37,9 @@ int sm_count() {
 
 }  // namespace incagg
 
-extern "C" int incagg_version(void) { return 100; }
+extern "C" int incagg_version(void) { return 101; }
+
+extern "C" int64_t incagg_launch_count(void) { return (int64_t)incagg::launches(); }
 
 extern "C" const char* incagg_last_error(void) { return incagg::err_buf(); }
 

@@ -26,8 +26,10 @@ int set_err(int code, const char* fmt, ...);
                              cudaGetErrorString(_e), __FILE__, __LINE__);           \
   } while (0)
 
+// Every kernel launch is followed by IA_LAUNCH_CHECK(), which also counts it (incagg_launch_count).
 #define IA_LAUNCH_CHECK()                                                           \
   do {                                                                              \
+    incagg::count_launch();                                                         \
     cudaError_t _e = cudaGetLastError();                                            \
     if (_e != cudaSuccess)                                                          \
       return incagg::set_err(INCAGG_ERR_CUDA, "kernel launch failed: %s (%s:%d)",    \
@@ -37,6 +39,8 @@ int set_err(int code, const char* fmt, ...);
 inline cudaStream_t as_stream(incagg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();  // cached SM count of the current device (148 on B200)
+void count_launch();  // process-wide count of kernels launched by this library
+unsigned long long launches();
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }

@@ -21,6 +21,8 @@ template <int VB> struct Bytes;
 template <> struct Bytes<16> { using type = uint4; };
 template <> struct Bytes<8> { using type = uint2; };
 template <> struct Bytes<4> { using type = uint32_t; };
+template <> struct Bytes<2> { using type = uint16_t; };
+template <> struct Bytes<1> { using type = uint8_t; };  // label / mask columns (bool, int8)
 
 constexpr int ROWS_THREADS = 256;
 constexpr int ROWS_UNROLL = 4;
@@ -108,7 +110,7 @@ static int pick_vb(const void* a, int64_t lda, const void* b, int64_t ldb, int64
     return row_bytes % vb == 0 && lda % vb == 0 && ldb % vb == 0 &&
            reinterpret_cast<uintptr_t>(a) % vb == 0 && reinterpret_cast<uintptr_t>(b) % vb == 0;
   };
-  return ok(16) ? 16 : (ok(8) ? 8 : 4);
+  return ok(16) ? 16 : (ok(8) ? 8 : (ok(4) ? 4 : (ok(2) ? 2 : 1)));
 }
 
 static int grid_for(int64_t total_vec) {
@@ -126,9 +128,7 @@ static int index_rows(const void* src, int64_t src_ld, const int64_t* idx, int64
   IA_CHECK_ARG(n >= 0 && row_bytes >= 0, "negative size");
   if (n == 0 || row_bytes == 0) return INCAGG_OK;
   IA_CHECK_ARG(src && dst && idx, "NULL argument");
-  IA_CHECK_ARG(row_bytes % 4 == 0, "row_bytes must be a multiple of 4 (got %lld)", (long long)row_bytes);
   IA_CHECK_ARG(src_ld >= row_bytes && dst_ld >= row_bytes, "leading dimension smaller than a row");
-  IA_CHECK_ARG(src_ld % 4 == 0 && dst_ld % 4 == 0, "leading dimensions must be multiples of 4 bytes");
   const int vb = pick_vb(src, src_ld, dst, dst_ld, row_bytes);
   const int64_t nvec64 = row_bytes / vb;
   IA_CHECK_ARG(nvec64 <= 0x7fffffff, "row too wide");
@@ -140,8 +140,12 @@ static int index_rows(const void* src, int64_t src_ld, const int64_t* idx, int64
     index_rows_kernel<16, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
   else if (vb == 8)
     index_rows_kernel<8, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
-  else
+  else if (vb == 4)
     index_rows_kernel<4, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+  else if (vb == 2)
+    index_rows_kernel<2, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+  else
+    index_rows_kernel<1, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -181,11 +185,8 @@ extern "C" int incagg_copy_slices(const void* src, int64_t src_ld_bytes, int64_t
   IA_CHECK_ARG(direction == 0 || direction == 1, "direction must be 0 (pull) or 1 (push)");
   if (k == 0 || row_bytes == 0) return INCAGG_OK;
   IA_CHECK_ARG(src && dst && offset && count, "NULL argument");
-  IA_CHECK_ARG(row_bytes % 4 == 0, "row_bytes must be a multiple of 4");
   IA_CHECK_ARG(src_ld_bytes >= row_bytes && dst_ld_bytes >= row_bytes,
                "leading dimension smaller than a row");
-  IA_CHECK_ARG(src_ld_bytes % 4 == 0 && dst_ld_bytes % 4 == 0,
-               "leading dimensions must be multiples of 4 bytes");
   // Bounds, as the reference asserts per slice ("Invalid index", async_cuda.cu:78-79,148-149).
   int64_t packed = 0;
   for (int64_t i = 0; i < k; ++i) {
@@ -244,8 +245,12 @@ extern "C" int incagg_copy_slices(const void* src, int64_t src_ld_bytes, int64_t
         slice_rows_kernel<16><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
       else if (vb == 8)
         slice_rows_kernel<8><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
-      else
+      else if (vb == 4)
         slice_rows_kernel<4><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
+      else if (vb == 2)
+        slice_rows_kernel<2><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
+      else
+        slice_rows_kernel<1><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
       IA_LAUNCH_CHECK();
     }
     p += rows_here;

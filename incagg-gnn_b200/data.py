@@ -57,11 +57,28 @@ class Data:
     def num_edges(self) -> int:
         return self._store["adj_t"].nnz() if "adj_t" in self._store else 0
 
+    def __copy__(self) -> "Data":
+        out = self.__class__()
+        out._store = dict(self._store)
+        return out
+
     def to(self, device, non_blocking: bool = False) -> "Data":
         out = self.__class__()
         for k, v in self:
             if isinstance(v, (Tensor, SparseTensor)):
                 v = v.to(device, non_blocking=non_blocking)
+            out[k] = v
+        return out
+
+    def pin_memory(self) -> "Data":
+        """Host-resident copy in page-locked memory (the reference's layout; the GPU collate reads it
+        through UVA)."""
+        out = self.__class__()
+        for k, v in self:
+            if isinstance(v, Tensor):
+                v = v.cpu().pin_memory()
+            elif isinstance(v, SparseTensor):
+                v = v.pin_memory()
             out[k] = v
         return out
 

@@ -58,15 +58,22 @@ class SubgraphLoader:
         self.shuffled_batch_id = []
         self.device = torch.device(device) if device is not None else data.adj_t.device
         if self.device.type != 'cuda':
-            raise RuntimeError('SubgraphLoader collates on the GPU: data.adj_t must be a CUDA SparseTensor')
+            raise RuntimeError('SubgraphLoader collates on the GPU: pass device="cuda" (with data in '
+                               'pinned host memory) or a CUDA data.adj_t; there is no CPU collate')
 
         self.num_parts = self.ptr.numel() - 1
         # global CSR for relabel: int64 rowptr, int32 col, fp32 values (device resident)
+        # (device resident, or pinned host memory that the relabel kernels read through UVA)
         adj = data.adj_t
         self._rowptr64 = adj.rowptr.to(torch.int64)
         self._rowptr_host = self._rowptr64.cpu()
         self._col = adj.col
         self._val = adj.value
+        if not adj.col.is_cuda:
+            self._rowptr64 = self._rowptr64.pin_memory()
+            self._col = self._col if self._col.is_pinned() else self._col.pin_memory()
+            if self._val is not None and not self._val.is_pinned():
+                self._val = self._val.pin_memory()
         self._ws = ops.RelabelWorkspace(adj.size(0), self.device)
 
         sampler = RandomSampler(range(self.num_parts)) if shuffle else SequentialSampler(range(self.num_parts))
@@ -106,13 +113,12 @@ class SubgraphLoader:
         data = self.data.__class__(adj_t=adj_t)
         for k, v in self.data:
             if isinstance(v, Tensor) and v.size(0) == self.data.num_nodes:
-                if v.dtype == torch.bool:  # 1-byte rows: gather as uint8 through torch
-                    data[k] = v.to(self.device, non_blocking=True).index_select(0, n_id) if v.is_cuda \
-                        else v[n_id.cpu()].to(self.device, non_blocking=True)
-                elif (v[0].numel() * v.element_size()) % 4 == 0 and (v.is_cuda or v.is_pinned()):
-                    data[k] = ops.gather_rows(v, n_id)
+                if not (v.is_cuda or v.is_pinned()):
+                    raise RuntimeError(f'data.{k} must be a CUDA or pinned host tensor')
+                if v.dtype == torch.bool:
+                    data[k] = ops.gather_rows(v.view(torch.uint8), n_id).view(torch.bool)
                 else:
-                    data[k] = v.to(self.device).index_select(0, n_id)
+                    data[k] = ops.gather_rows(v, n_id)
         return SubData(data, batch_size, n_id, offset, count)
 
     # -- collates (same names as the reference) ---------------------------------------------

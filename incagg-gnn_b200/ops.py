@@ -169,8 +169,6 @@ def gather_rows(src: Tensor, idx: Tensor, out: Optional[Tensor] = None) -> Tenso
     s, s_ld, row_bytes, s_rows = _row_view(src)
     d, d_ld, d_row_bytes, d_rows = _row_view(out)
     assert d_row_bytes == row_bytes and d_rows >= n
-    if row_bytes % 4 != 0:
-        raise RuntimeError("gather_rows: rows must be a multiple of 4 bytes")
     LAUNCHES["calls"] += 1
     check(lib.incagg_gather_rows(ptr(s), s_ld, s_rows, ptr(idx), n, ptr(d), d_ld, row_bytes, _stream()))
     return out
@@ -247,7 +245,12 @@ def _workspace_for(num_nodes: int, device) -> RelabelWorkspace:
 def _relabel(within: bool, rowptr: Tensor, col: Tensor, value: Optional[Tensor], idx: Tensor,
              bipartite: bool, ws: Optional[RelabelWorkspace], out_int32: bool,
              nnz_b: Optional[int]):
-    _require_cuda(rowptr, col, value, idx)
+    # the global CSR may live in HBM or in pinned host memory (read through UVA); idx on the device
+    _require_cuda(idx)
+    for t in (rowptr, col, value):
+        if t is not None and not _device_accessible(t):
+            raise RuntimeError("relabel: the graph must be in CUDA or pinned host memory "
+                               "(there is no CPU fallback)")
     if rowptr.dtype != torch.int64:
         raise RuntimeError("relabel: rowptr must be int64")
     if col.dtype not in (torch.int32, torch.int64):
@@ -258,7 +261,7 @@ def _relabel(within: bool, rowptr: Tensor, col: Tensor, value: Optional[Tensor],
         if value.dtype != torch.float32:
             raise RuntimeError("relabel: only float32 edge values are supported on the GPU path")
     idx = idx.contiguous()
-    dev = rowptr.device
+    dev = idx.device
     N = rowptr.numel() - 1
     B = idx.numel()
     if ws is None:

@@ -113,6 +113,16 @@ class SparseTensor:
     def cuda(self):
         return self.to("cuda")
 
+    def pin_memory(self) -> "SparseTensor":
+        out = SparseTensor.__new__(SparseTensor)
+        out._sizes = self._sizes
+        out.rowptr = self.rowptr.cpu().pin_memory()
+        out.col = self.col.cpu().pin_memory()
+        out.value = self.value.cpu().pin_memory() if self.value is not None else None
+        out.storage = _Storage(out)
+        out._t = None
+        return out
+
     def set_value(self, value: Optional[Tensor], layout: Optional[str] = None) -> "SparseTensor":
         out = SparseTensor.__new__(SparseTensor)
         out._sizes = self._sizes

@@ -1,0 +1,158 @@
+"""The driver loop that calls the hot path (reference: main.py:47-110 ``mini_train`` / ``mini_test``,
+main.py:140-236 setup) and the hyper-parameters of the five BASELINE configs.
+
+Not a product by itself: it is the caller the benchmark and the parity tests need.
+Differences from the reference loop, none of which change results:
+  * ``total_loss`` / ``total_examples`` are initialised (the fork uses them unassigned),
+  * no ``torch.cuda.synchronize()`` after every forward (main.py:72,76) and no autograd anomaly mode
+    (main.py:41); the loss is accumulated on the device and read back once per epoch.
+"""
+from typing import Any, Dict, Optional
+
+import torch
+
+from . import models
+from .loader import EvalSubgraphLoader, SubgraphLoader
+from .metis import metis, permute
+from .preprocess import gcn_norm, set_diag
+from .synthetic import get_data
+from .utils import dropout
+
+# Hyper-parameters per BASELINE config (values from the reference YAML where the fork has them).
+CONFIGS: Dict[str, Dict[str, Any]] = {
+    # C1: no flickr entry in conf/model/gcn.yaml -> 2 layers, hidden 256
+    'C1': dict(model='GCN', dataset='flickr', loop=True, norm=True, VR_update=False,
+               architecture=dict(num_layers=2, hidden_channels=256, dropout=0.0, drop_input=False,
+                                 batch_norm=False, residual=False),
+               num_parts=24, batch_size=12, max_steps=-1, pool_size=2, lr=0.01,
+               reg_weight_decay=0., nonreg_weight_decay=0., grad_norm=None),
+    # C2: conf/model/appnp.yaml:7-22, IncAgg
+    'C2': dict(model='APPNP', dataset='arxiv', loop=False, norm=True, VR_update=True,
+               architecture=dict(num_layers=5, hidden_channels=256, alpha=0.1, dropout=0.3),
+               num_parts=80, batch_size=40, max_steps=-1, pool_size=2, lr=0.01,
+               reg_weight_decay=0., nonreg_weight_decay=0., grad_norm=1.0),
+    # C3: conf/model/gcn2.yaml:51-71 (headline metric)
+    'C3': dict(model='GCN2', dataset='products', loop=True, norm=True, VR_update=False,
+               architecture=dict(num_layers=5, hidden_channels=128, dropout=0.0, drop_input=False,
+                                 batch_norm=False, residual=False, shared_weights=False, alpha=0.1,
+                                 theta=0.5),
+               num_parts=150, batch_size=1, max_steps=-1, pool_size=1, lr=0.001,
+               reg_weight_decay=0., nonreg_weight_decay=0., grad_norm=None),
+    # C4: conf/model/graphsage.yaml:7-24
+    'C4': dict(model='GraphSAGE', dataset='reddit', loop=True, norm=True, VR_update=False,
+               architecture=dict(num_layers=2, hidden_channels=1024, dropout=0.5, drop_input=False,
+                                 batch_norm=False, residual=False),
+               num_parts=200, batch_size=100, max_steps=2, pool_size=2, lr=0.01,
+               reg_weight_decay=0., nonreg_weight_decay=0., grad_norm=None),
+    # C5: no PNA yaml in the fork; layer shape of conf/model/gcn.yaml:65-83
+    'C5': dict(model='PNA', dataset='amazonproducts', loop=True, norm=True, VR_update=False,
+               architecture=dict(num_layers=3, hidden_channels=256, dropout=0.3, drop_input=False,
+                                 batch_norm=False, residual=False,
+                                 aggregators=['sum', 'mean', 'min', 'max'], scalers=['identity']),
+               num_parts=200, batch_size=100, max_steps=-1, pool_size=1, lr=0.005,
+               reg_weight_decay=0., nonreg_weight_decay=0., grad_norm=None),
+}
+
+
+def mini_train(model, loader, criterion, optimizer, max_steps, grad_norm=None, edge_dropout=0.0,
+               epoch=0, VR_update=False, drift_norm=2, aggregate_combined=True,
+               use_aggregation=True) -> Dict[str, float]:
+    """One training epoch over the partition mini-batches (main.py:47-96)."""
+    model.train()
+    total_loss = torch.zeros((), dtype=torch.float64, device=model.device)
+    total_examples = torch.zeros((), dtype=torch.float64, device=model.device)
+    steps = 0
+    for i, (batch, batch_size, n_id, offset, count) in enumerate(loader):
+        x = batch.x.to(model.device)
+        adj_t = batch.adj_t.to(model.device)
+        y = batch.y[:batch_size].to(model.device)
+        train_mask = batch.train_mask[:batch_size].to(model.device)
+        adj_t = dropout(adj_t, p=edge_dropout)
+        if VR_update:
+            ret = model.VR_call(x, adj_t, batch_size, n_id, offset, count, drift_norm=drift_norm,
+                                epoch=epoch, batch_idx=i)
+        else:
+            ret = model(x, adj_t, batch_size, n_id, offset, count, drift_norm=drift_norm,
+                        aggregate_combined=aggregate_combined, use_aggregation=use_aggregation)
+        out = ret['out']
+        optimizer.zero_grad(set_to_none=True)
+        # mean CE over the training rows of the batch == criterion(out[mask], y[mask]) (main.py:80)
+        # written mask-weighted so that the row count never has to reach the host
+        w = train_mask.to(out.dtype)
+        n = w.sum()
+        if y.dim() == 1:
+            per_row = torch.nn.functional.cross_entropy(out, y, reduction='none')
+        else:
+            per_row = torch.nn.functional.binary_cross_entropy_with_logits(
+                out, y.to(out.dtype), reduction='none').mean(dim=-1)
+        loss = (per_row * w).sum() / n.clamp(min=1.)
+        loss.backward()
+        if grad_norm is not None:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), grad_norm)
+        optimizer.step()
+        total_loss += loss.detach().double() * n
+        total_examples += n
+        steps += 1
+        if (i + 1) >= max_steps and (i + 1) < len(loader):
+            break
+    tl, te = float(total_loss), float(total_examples)
+    return {'loss': tl / max(te, 1.), 'steps': steps}
+
+
+@torch.no_grad()
+def mini_test(model, loader, use_aggregation=True, VR_update=False):
+    model.eval()
+    if VR_update:
+        return model.mini_inference_vr(loader=loader, use_aggregation=use_aggregation)
+    return model(loader=loader, use_aggregation=use_aggregation)
+
+
+def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_device='cuda',
+          overrides: Optional[Dict[str, Any]] = None, log: bool = False, data_device=None,
+          shuffle: bool = True, host_resident: bool = False, data=None):
+    """Everything main.py:140-201 sets up for one named config on synthetic data: returns a dict
+    with data, ptr, loaders, model, optimizer, criterion and the config."""
+    conf = dict(CONFIGS[config])
+    if overrides:
+        conf.update(overrides)
+    torch.manual_seed(seed)
+    # data_device='cpu' generates with the CPU generator (identical inputs for the CPU oracle)
+    if data is None:
+        data, in_channels, out_channels = get_data('', conf['dataset'], seed=seed,
+                                                   device=data_device or device, scale=scale,
+                                                   num_parts=conf['num_parts'])
+        raw = data
+        data = data.to(device)
+        data.adj_t.clustered_parts = getattr(raw.adj_t, 'clustered_parts', None)
+        perm, ptr = metis(data.adj_t, num_parts=conf['num_parts'], log=log)
+        data = permute(data, perm, log=log)
+        if conf['loop']:
+            data.adj_t = set_diag(data.adj_t)
+        if conf['norm']:
+            data.adj_t = gcn_norm(data.adj_t, add_self_loops=False)
+    else:  # (data, ptr, in_channels, out_channels) of an earlier build(): reuse the preprocessed graph
+        data, ptr, in_channels, out_channels = data
+        raw = None
+    if host_resident:  # the reference's layout: graph + features in pinned host memory
+        data = data.pin_memory()
+    criterion = torch.nn.CrossEntropyLoss()
+    train_loader = SubgraphLoader(data, ptr, batch_size=conf['batch_size'], shuffle=shuffle,
+                                  num_neighbors=-1, type='train', IB=conf['VR_update'], log=log,
+                                  device=device)
+    eval_loader = EvalSubgraphLoader(data, ptr, batch_size=conf['batch_size'], log=log, device=device)
+    buffer_size = max(n_id.numel() for _, _, n_id, _, _ in eval_loader) * 2
+    kwargs = {}
+    if conf['model'][:3] == 'PNA':
+        kwargs['deg'] = data.adj_t.storage.rowcount()
+    GNN = getattr(models, conf['model'])
+    model = GNN(num_nodes=data.num_nodes, in_channels=in_channels, out_channels=out_channels,
+                pool_size=conf['pool_size'], buffer_size=buffer_size, device=history_device,
+                **conf['architecture'], **kwargs).to(device)
+    optimizer = torch.optim.Adam([
+        dict(params=model.reg_modules.parameters(), weight_decay=conf['reg_weight_decay']),
+        dict(params=model.nonreg_modules.parameters(), weight_decay=conf['nonreg_weight_decay']),
+    ], lr=conf['lr'])
+    max_steps = conf['max_steps'] if conf['max_steps'] != -1 else int(conf['num_parts'] / conf['batch_size'])
+    return dict(conf=conf, data=data, raw=raw, ptr=ptr, train_loader=train_loader, eval_loader=eval_loader,
+                model=model, optimizer=optimizer, criterion=criterion, max_steps=max_steps,
+                in_channels=in_channels, out_channels=out_channels, buffer_size=buffer_size)

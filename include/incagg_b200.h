@@ -52,6 +52,9 @@ typedef void* incagg_stream_t; /* a cudaStream_t */
 int incagg_version(void);
 /* Thread-local text of the last error returned on this thread ("" if none). */
 const char* incagg_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (every entry point counts
+ * its own launches; DMA copies issued through cudaMemcpyAsync are not kernels and not counted). */
+int64_t incagg_launch_count(void);
 /* SM count and compute capability of the current device. */
 int incagg_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -123,7 +126,7 @@ int incagg_csr_transpose(const int32_t* rowptr, const int32_t* col, const float*
  * dst[i, :] = src[idx[i], :] for i < n.  Replaces History.pull (history.py:38) and the
  * CPU index_select + bounce-buffer H2D of read_async (async_cuda.cu:95-110): `src` may be
  * device memory or pinned (page-locked, UVA-mapped) host memory, `dst` device memory.
- * Rows are `row_bytes` bytes (multiple of 4); leading dimensions in bytes.  idx is a
+ * Rows are `row_bytes` bytes (any size: 16/8/4/2/1-byte vectors by alignment); leading dimensions in bytes.  idx is a
  * device-accessible int64 array.  Also the collate feature gather x[n_id] (loader.py:188-190).
  */
 int incagg_gather_rows(const void* src, int64_t src_ld_bytes, int64_t src_rows, const int64_t* idx,

@@ -1,0 +1,367 @@
+"""Parity of every CUDA kernel family against the CPU oracle, called through the C ABI
+(incagg_gnn_b200.ops -> ctypes -> libincagg_b200.so).
+
+Bars: bit-exact for relabel / transpose structure / gather / scatter / slice copies / min-max
+argument indices; <= 1e-5 relative (fp32, vs an fp64 oracle) for aggregation outputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # the tolerance BASELINE.json's north_star states for fp32 aggregation outputs
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    import incagg_gnn_b200  # noqa: F401
+    from incagg_gnn_b200 import ops as _ops
+    return _ops
+
+
+def _rand_csr(rng, rows, cols, maxdeg, long_rows=0, long_len=0):
+    deg = rng.integers(0, maxdeg + 1, rows)
+    if rows > 10:
+        deg[rng.integers(0, rows, rows // 6)] = 0
+    for r in range(long_rows):
+        deg[rng.integers(0, rows)] = long_len
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    col = rng.integers(0, cols, rowptr[-1]).astype(np.int64)
+    val = rng.standard_normal(rowptr[-1]).astype(np.float32)
+    return rowptr, col, val
+
+
+def _dev(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(dev)
+
+
+def _rel_err(got, ref):
+    return float(np.abs(got.astype(np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+# ---- SpMM -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("reduce", ["sum", "mean", "min", "max"])
+@pytest.mark.parametrize("F", [1, 7, 32, 40, 64, 100, 128, 130, 256, 602])
+def test_spmm_matches_oracle(ops, cuda, reduce, F):
+    rng = np.random.default_rng(F * 7 + len(reduce))
+    rows, cols = 300, 500
+    rowptr, col, val = _rand_csr(rng, rows, cols, 20)
+    X = rng.standard_normal((cols, F)).astype(np.float32)
+    out, arg = ops.spmm_raw(_dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32), _dev(val, cuda),
+                            _dev(X, cuda), reduce, return_arg=True)
+    ref, ref_arg = oracle.spmm(rowptr, col, val, X, reduce, dtype=np.float64, return_arg=True)
+    assert _rel_err(out.cpu().numpy(), ref) <= RTOL
+    if reduce in ("min", "max"):
+        # exact values (one multiply, no accumulation) and exact argument indices
+        ref32 = oracle.spmm(rowptr, col, val, X, reduce, dtype=np.float32)
+        assert np.array_equal(out.cpu().numpy(), ref32)
+        assert np.array_equal(arg.cpu().numpy().astype(np.int64), ref_arg)
+
+
+@pytest.mark.parametrize("has_val", [True, False])
+def test_spmm_without_values_and_empty(ops, cuda, has_val):
+    rng = np.random.default_rng(11)
+    rowptr, col, val = _rand_csr(rng, 64, 64, 5)
+    X = rng.standard_normal((64, 24)).astype(np.float32)
+    v = val if has_val else None
+    out = ops.spmm_raw(_dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32),
+                       _dev(v, cuda) if has_val else None, _dev(X, cuda), "sum")
+    assert _rel_err(out.cpu().numpy(), oracle.spmm(rowptr, col, v, X, "sum", np.float64)) <= RTOL
+    # zero rows / zero edges
+    z = ops.spmm_raw(torch.zeros(1, dtype=torch.int32, device=cuda), torch.zeros(0, dtype=torch.int32, device=cuda),
+                     None, _dev(X, cuda), "sum")
+    assert z.shape == (0, 24)
+    rp0 = torch.zeros(9, dtype=torch.int32, device=cuda)
+    z = ops.spmm_raw(rp0, torch.zeros(0, dtype=torch.int32, device=cuda), None, _dev(X, cuda), "max")
+    assert z.shape == (8, 24) and float(z.abs().max()) == 0.
+
+
+@pytest.mark.parametrize("reduce", ["sum", "max"])
+@pytest.mark.parametrize("F", [40, 128, 602])
+def test_spmm_long_rows_bucket(ops, cuda, reduce, F):
+    """Rows above the long-row threshold go through the CTA-per-row kernel."""
+    rng = np.random.default_rng(F)
+    rowptr, col, val = _rand_csr(rng, 200, 4000, 30, long_rows=3, long_len=5000)
+    X = rng.standard_normal((4000, F)).astype(np.float32)
+    out, arg = ops.spmm_raw(_dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32), _dev(val, cuda),
+                            _dev(X, cuda), reduce, return_arg=True)
+    ref, ref_arg = oracle.spmm(rowptr, col, val, X, reduce, dtype=np.float64, return_arg=True)
+    assert _rel_err(out.cpu().numpy(), ref) <= RTOL
+    if reduce == "max":
+        assert np.array_equal(arg.cpu().numpy().astype(np.int64), ref_arg)
+
+
+def test_spmm_unaligned_views_and_leading_dimension(ops, cuda):
+    """Column-cropped history views (ld > F) and 4-byte-aligned-only bases use the narrower paths."""
+    rng = np.random.default_rng(2)
+    rowptr, col, val = _rand_csr(rng, 100, 100, 8)
+    big = torch.from_numpy(rng.standard_normal((100, 75)).astype(np.float32)).to(cuda)
+    for lo, hi in [(0, 64), (1, 65), (2, 42), (3, 10)]:
+        X = big[:, lo:hi]
+        out = ops.spmm_raw(_dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32), _dev(val, cuda), X, "sum")
+        ref = oracle.spmm(rowptr, col, val, X.cpu().numpy(), "sum", np.float64)
+        assert _rel_err(out.cpu().numpy(), ref) <= RTOL
+
+
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+@pytest.mark.parametrize("F", [40, 128, 100])
+@pytest.mark.parametrize("use_nid", [False, True])
+def test_spmm_delta_matches_oracle(ops, cuda, reduce, F, use_nid):
+    rng = np.random.default_rng(F + use_nid)
+    B, N = 150, 400
+    rowptr, col, val = _rand_csr(rng, B, B, 12)
+    x = rng.standard_normal((B, F)).astype(np.float32)
+    hist_in = rng.standard_normal((N, F + 8)).astype(np.float32)
+    hist_ag = rng.standard_normal((N, F + 8)).astype(np.float32)
+    v = val if reduce == "sum" else None
+    if use_nid:
+        n_id = rng.permutation(N)[:B].astype(np.int64)
+        m_in, m_ag = hist_in[n_id], hist_ag[n_id]
+        out = ops.spmm_delta_raw(_dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32),
+                                 _dev(v, cuda) if v is not None else None, _dev(x, cuda), _dev(hist_in, cuda),
+                                 _dev(hist_ag, cuda), _dev(n_id, cuda), reduce)
+    else:
+        m_in, m_ag = hist_in[40:40 + B], hist_ag[40:40 + B]
+        out = ops.spmm_delta_raw(_dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32),
+                                 _dev(v, cuda) if v is not None else None, _dev(x, cuda),
+                                 _dev(hist_in, cuda)[40:40 + B, :F], _dev(hist_ag, cuda)[40:40 + B, :F], None, reduce)
+    ref = oracle.spmm_delta(rowptr, col, v, x, m_in, m_ag, reduce, np.float64)
+    assert _rel_err(out.cpu().numpy(), ref) <= RTOL
+
+
+@pytest.mark.parametrize("F", [16, 64, 100])
+def test_spmm_multi_matches_separate_passes(ops, cuda, F):
+    rng = np.random.default_rng(F)
+    rowptr, col, val = _rand_csr(rng, 120, 200, 10, long_rows=1, long_len=3000)
+    reducers = ["sum", "mean", "min", "max"]
+    X = rng.standard_normal((200, 4 * F)).astype(np.float32)
+    out = ops.spmm_multi_raw(_dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32), _dev(val, cuda),
+                             _dev(X, cuda), F, reducers)
+    ref = oracle.spmm_multi(rowptr, col, val, X, F, reducers, np.float64)
+    assert _rel_err(out.cpu().numpy(), ref) <= RTOL
+
+
+def test_minmax_backward_routes_to_arg(ops, cuda):
+    rng = np.random.default_rng(9)
+    rowptr, col, val = _rand_csr(rng, 80, 60, 6)
+    X = rng.standard_normal((60, 20)).astype(np.float32)
+    rp, c, v = _dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32), _dev(val, cuda)
+    out, arg = ops.spmm_raw(rp, c, v, _dev(X, cuda), "max", return_arg=True)
+    g = rng.standard_normal((80, 20)).astype(np.float32)
+    gx = ops.spmm_minmax_bwd_raw(c, v, arg, _dev(g, cuda), 60).cpu().numpy()
+    _, ref_arg = oracle.spmm(rowptr, col, val, X, "max", return_arg=True)
+    ref = np.zeros((60, 20))
+    for i in range(80):
+        for f in range(20):
+            e = ref_arg[i, f]
+            if e >= 0:
+                ref[col[e], f] += float(val[e]) * float(g[i, f])
+    assert _rel_err(gx, ref) <= RTOL
+
+
+# ---- transpose --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(50, 70, 6, 0, 0), (300, 40, 40, 0, 0), (64, 20, 4, 2, 40000)])
+def test_csr_transpose_is_bit_exact_and_ordered(ops, cuda, shape):
+    rows, cols, maxdeg, nlong, llen = shape
+    rng = np.random.default_rng(rows)
+    rowptr, col, val = _rand_csr(rng, rows, cols, maxdeg, nlong, llen)
+    t_rowptr, t_col, t_val, t_perm = ops.csr_transpose(_dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32),
+                                                       _dev(val, cuda), rows, cols, want_perm=True)
+    e_rowptr, e_col, e_val, e_perm = oracle.csr_transpose(rowptr, col, val, cols)
+    assert np.array_equal(t_rowptr.cpu().numpy(), e_rowptr)
+    assert np.array_equal(t_perm.cpu().numpy(), e_perm)
+    assert np.array_equal(t_col.cpu().numpy(), e_col)
+    assert np.array_equal(t_val.cpu().numpy(), e_val)
+
+
+def test_backward_spmm_through_transpose(ops, cuda):
+    """grad_X = A^T grad_out via the transposed CSR equals the dense formula."""
+    from incagg_gnn_b200.sparse import SparseTensor
+    rng = np.random.default_rng(4)
+    rowptr, col, val = _rand_csr(rng, 90, 140, 9)
+    adj = SparseTensor(rowptr=_dev(rowptr, cuda), col=_dev(col, cuda), value=_dev(val, cuda), sparse_sizes=(90, 140))
+    x = torch.from_numpy(rng.standard_normal((140, 36)).astype(np.float32)).to(cuda).requires_grad_(True)
+    g = torch.from_numpy(rng.standard_normal((90, 36)).astype(np.float32)).to(cuda)
+    for reduce in ("sum", "mean"):
+        x.grad = None
+        (adj.matmul(x, reduce=reduce) * g).sum().backward()
+        from scipy.sparse import csr_matrix
+        a = csr_matrix((val.astype(np.float64), col, rowptr), shape=(90, 140)).toarray()
+        gg = g.cpu().numpy().astype(np.float64)
+        if reduce == "mean":
+            gg = gg / np.maximum(np.diff(rowptr), 1)[:, None]
+        assert _rel_err(x.grad.cpu().numpy(), a.T @ gg) <= RTOL
+
+
+# ---- rows: gather / scatter / slices -----------------------------------------------------------------
+@pytest.mark.parametrize("D,dtype", [(128, torch.float32), (40, torch.float32), (100, torch.float32),
+                                     (7, torch.float32), (1, torch.int64), (3, torch.int32)])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_gather_scatter_rows_bit_exact(ops, cuda, D, dtype, pinned):
+    g = torch.Generator().manual_seed(D)
+    N, n = 1000, 333
+    src = (torch.randn(N, D, generator=g) * 100).to(dtype)
+    idx = torch.randperm(N, generator=g)[:n]
+    s = src.pin_memory() if pinned else src.to(cuda)
+    out = ops.gather_rows(s, idx.to(cuda))
+    assert torch.equal(out.cpu(), src[idx])
+    dst = torch.zeros(N, D, dtype=dtype)
+    d = dst.pin_memory() if pinned else dst.to(cuda)
+    ops.scatter_rows(out, idx.to(cuda), d)
+    torch.cuda.synchronize()
+    exp = torch.zeros(N, D, dtype=dtype)
+    exp[idx] = src[idx]
+    assert torch.equal(d.cpu(), exp)
+    # empty index
+    assert ops.gather_rows(s, torch.empty(0, dtype=torch.int64, device=cuda)).shape[0] == 0
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_copy_slices_both_directions(ops, cuda, pinned):
+    g = torch.Generator().manual_seed(1)
+    N, D = 500, 48
+    table = torch.randn(N, D, generator=g)
+    t = table.clone().pin_memory() if pinned else table.to(cuda)
+    offset = torch.tensor([10, 300, 120, 499, 0])
+    count = torch.tensor([50, 7, 0, 1, 3])
+    total = int(count.sum())
+    packed = torch.zeros(total + 5, D, device=cuda)
+    assert ops.copy_slices(t, packed, offset, count, 0) == total
+    exp = torch.cat([table[o:o + c] for o, c in zip(offset.tolist(), count.tolist())])
+    torch.cuda.synchronize()
+    assert torch.equal(packed[:total].cpu(), exp)
+    new = torch.randn(total, D, generator=g)
+    ops.copy_slices(new.to(cuda), t, offset, count, 1)
+    torch.cuda.synchronize()
+    exp_t = table.clone()
+    s = 0
+    for o, c in zip(offset.tolist(), count.tolist()):
+        exp_t[o:o + c] = new[s:s + c]
+        s += c
+    assert torch.equal(t.cpu(), exp_t)
+    # many slices (> one launch table) on the device path
+    if not pinned:
+        k = 150
+        off = torch.arange(k) * 3
+        cnt = torch.ones(k, dtype=torch.int64) * 2
+        pk = torch.zeros(2 * k, D, device=cuda)
+        ops.copy_slices(t, pk, off, cnt, 0)
+        exp = torch.cat([exp_t[o:o + 2] for o in off.tolist()])
+        assert torch.equal(pk.cpu(), exp)
+    # bounds are checked like the reference's "Invalid index"
+    from incagg_gnn_b200._lib import IncAggError
+    with pytest.raises(IncAggError):
+        ops.copy_slices(t, packed, torch.tensor([490]), torch.tensor([20]), 0)
+
+
+# ---- relabel ----------------------------------------------------------------------------------------
+def _golden_cases():
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "relabel_golden.npz"))
+    for k in range(int(d["num_cases"])):
+        p = f"c{k}_"
+        val = d[p + "in_value"] if p + "in_value" in d.files else None
+        yield (str(d[p + "fn"]), bool(d[p + "bipartite"]), d[p + "in_rowptr"], d[p + "in_col"], val,
+               d[p + "in_idx"], d[p + "out_rowptr"], d[p + "out_col"],
+               d[p + "out_value"] if val is not None else None, d[p + "out_n_id"])
+
+
+def test_relabel_matches_reference_golden_vectors(ops, cuda):
+    """GPU relabel vs the outputs of the reference's own compiled op, through the re-registered
+    torch.ops.torch_geometric_autoscale.* names (int64 in / int64 out like the reference)."""
+    ns = torch.ops.torch_geometric_autoscale
+    n = 0
+    for fn, bip, rowptr, col, val, idx, e_rowptr, e_col, e_val, e_nid in _golden_cases():
+        r, c, v, nid = getattr(ns, fn)(_dev(rowptr, cuda), _dev(col, cuda), _dev(val, cuda) if val is not None else None,
+                                       _dev(idx, cuda), bip)
+        assert r.dtype == torch.int64 and c.dtype == torch.int64
+        assert np.array_equal(r.cpu().numpy(), e_rowptr), (fn, bip, n)
+        assert np.array_equal(c.cpu().numpy(), e_col), (fn, bip, n)
+        assert np.array_equal(nid.cpu().numpy(), e_nid), (fn, bip, n)
+        if val is not None:
+            assert np.array_equal(v.cpu().numpy(), e_val)
+        else:
+            assert v is None
+        n += 1
+    assert n == 56
+
+
+@pytest.mark.parametrize("within", [False, True])
+@pytest.mark.parametrize("col32", [False, True])
+def test_relabel_random_graphs_vs_oracle(ops, cuda, within, col32):
+    rng = np.random.default_rng(17 + within)
+    N = 20000
+    rowptr, col, val = _rand_csr(rng, N, N, 40, long_rows=4, long_len=3000)
+    fn_gpu = ops.relabel_one_hop_within_batch if within else ops.relabel_one_hop
+    fn_cpu = oracle.relabel_one_hop_within_batch if within else oracle.relabel_one_hop
+    d_rowptr, d_val = _dev(rowptr, cuda), _dev(val, cuda)
+    d_col = _dev(col, cuda, torch.int32 if col32 else torch.int64)
+    for trial in range(3):  # the workspace table must be left clean by every call
+        idx = (rng.integers(0, N, 3000) if trial == 1 else
+               np.concatenate([np.arange(5000, 7000), rng.permutation(5000)[:500]])).astype(np.int64)
+        got = fn_gpu(d_rowptr, d_col, d_val, _dev(idx, cuda), trial != 2, out_int32=(trial == 0))
+        exp = fn_cpu(rowptr, col, val, idx, trial != 2)
+        for g, e in zip(got, exp):
+            assert np.array_equal(g.cpu().numpy().astype(e.dtype), e)
+
+
+def test_relabel_cpu_tensors_raise(ops, cuda):
+    with pytest.raises(RuntimeError):
+        ops.relabel_one_hop(torch.tensor([0, 1]), torch.tensor([0]), None, torch.tensor([0]))
+
+
+# ---- async staging ------------------------------------------------------------------------------------
+def test_read_write_async_semantics(ops, cuda):
+    """read_async / write_async (csrc/cuda/async_cuda.cu:14-165): slices then indexed rows; the same
+    argument checks raise."""
+    g = torch.Generator().manual_seed(3)
+    N, D = 800, 64
+    table = torch.randn(N, D, generator=g).pin_memory()
+    offset, count = torch.tensor([100, 400]), torch.tensor([30, 20])
+    index = torch.randperm(N, generator=g)[:77]
+    dst = torch.zeros(200, D, device=cuda)
+    buf = torch.empty(200, D).pin_memory()
+    side = torch.cuda.Stream(cuda)
+    with torch.cuda.stream(side):
+        torch.ops.torch_geometric_autoscale.read_async(table, offset, count, index, dst, buf)
+    torch.ops.torch_geometric_autoscale.synchronize()
+    exp = torch.cat([table[100:130], table[400:420], table[index]])
+    assert torch.equal(dst[:127].cpu(), exp)
+    with pytest.raises(RuntimeError, match="non-default"):
+        ops.read_async(table, offset, count, index, dst, buf)
+    with pytest.raises(RuntimeError, match="too small"):
+        with torch.cuda.stream(side):
+            ops.read_async(table, offset, count, torch.arange(500), dst, buf)
+    src = torch.randn(50, D, generator=g).to(cuda)
+    with torch.cuda.stream(side):
+        side.wait_stream(torch.cuda.current_stream())
+        torch.ops.torch_geometric_autoscale.write_async(src, offset, count, table)
+    side.synchronize()
+    assert torch.equal(table[100:130], src[:30].cpu()) and torch.equal(table[400:420], src[30:].cpu())
+
+
+def test_async_io_pool_fifo(ops, cuda):
+    """AsyncIOPool state machine (pool.py:64-123): more pulls than slots, FIFO order preserved."""
+    from incagg_gnn_b200 import AsyncIOPool
+    g = torch.Generator().manual_seed(5)
+    table = torch.randn(300, 32, generator=g).pin_memory()
+    pool = AsyncIOPool(pool_size=2, buffer_size=64, embedding_dim=32).to(cuda)
+    idxs = [torch.randperm(300, generator=g)[:40] for _ in range(5)]
+    empty_o = torch.tensor([5]), torch.tensor([10])
+    for ix in idxs:
+        pool.async_pull(table, empty_o[0], empty_o[1], ix)
+    for ix in idxs:
+        out = pool.synchronize_pull()[:50].clone()
+        pool.free_pull()
+        torch.cuda.synchronize()
+        assert torch.equal(out.cpu(), torch.cat([table[5:15], table[ix]]))
+    x = torch.randn(20, 32, generator=g).to(cuda)
+    pool.async_push(x, torch.tensor([100]), torch.tensor([20]), table)
+    pool.synchronize_push()
+    assert torch.equal(table[100:120], x.cpu())

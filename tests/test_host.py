@@ -1,0 +1,112 @@
+"""Host-side logic that runs without a GPU: containers, preprocessing, synthetic inputs, partition
+helpers and the loud failures of the product path when there is no CUDA device."""
+import numpy as np
+import pytest
+import torch
+
+import incagg_gnn_b200 as tga
+from oracle import gas
+
+
+def test_sparse_tensor_container():
+    row = torch.tensor([2, 0, 1, 0, 2])
+    col = torch.tensor([1, 2, 0, 0, 2])
+    val = torch.arange(5, dtype=torch.float32)
+    a = tga.SparseTensor(row=row, col=col, value=val, sparse_sizes=(3, 3))
+    rp, c, v = a.csr()
+    assert rp.tolist() == [0, 2, 3, 5] and c.tolist() == [0, 2, 0, 1, 2] and v.tolist() == [3, 1, 2, 0, 4]
+    assert a.rowptr.dtype == torch.int32 and a.col.dtype == torch.int32
+    assert a.nnz() == 5 and a.size(0) == 3 and a.sparse_sizes() == (3, 3)
+    assert a.storage.row().tolist() == [0, 0, 1, 2, 2] and a.storage.rowcount().tolist() == [2, 1, 2]
+    b = a.set_value(None)
+    assert b.value is None and b.col is a.col
+    m = a.masked_select_nnz(torch.tensor([True, False, True, True, False]))
+    assert m.nnz() == 3 and m.csr()[0].tolist() == [0, 1, 2, 3]
+    with pytest.raises(RuntimeError):
+        a @ torch.randn(3, 4)  # CPU tensors: no fallback
+
+
+def test_preprocess_matches_oracle():
+    data, ptr = tga.synthetic_graph(3000, 30000, 8, 4, 6, seed=3)
+    rp, col, _ = data.adj_t.csr()
+    o = gas.gcn_norm(gas.set_diag(gas.Adj(rp, col, None, 3000, 3000)))
+    p = tga.gcn_norm(tga.set_diag(data.adj_t))
+    prp, pcol, pval = p.csr()
+    assert torch.equal(prp, o.rowptr) and torch.equal(pcol, o.col)
+    torch.testing.assert_close(pval, o.val, rtol=1e-6, atol=1e-7)
+    # rows of a normalised symmetric graph with self loops: sum_j a_ij * sqrt(d_j / d_i) == 1
+    deg = torch.zeros(3000).index_add_(0, p.storage.row(), torch.ones(p.nnz()))
+    s = torch.zeros(3000).index_add_(0, p.storage.row(), pval * deg[pcol].sqrt()) / deg.sqrt()
+    torch.testing.assert_close(s, torch.ones(3000), rtol=1e-4, atol=1e-4)
+
+
+def test_to_symmetric_and_set_diag():
+    a = tga.SparseTensor(row=torch.tensor([0, 0, 1]), col=torch.tensor([1, 2, 0]), sparse_sizes=(3, 3))
+    s = tga.to_symmetric(a)
+    assert s.csr()[0].tolist() == [0, 2, 3, 4] and s.csr()[1].tolist() == [1, 2, 0, 0]
+    d = tga.set_diag(s)
+    assert d.csr()[1].tolist() == [0, 1, 2, 0, 1, 0, 2]
+
+
+def test_synthetic_graph_shape_and_determinism():
+    d1, ptr = tga.synthetic_graph(5000, 60000, 16, 7, 10, seed=1)
+    d2, _ = tga.synthetic_graph(5000, 60000, 16, 7, 10, seed=1)
+    assert torch.equal(d1.adj_t.col, d2.adj_t.col) and torch.equal(d1.x, d2.x)
+    assert d1.adj_t.nnz() == 60000 and ptr.tolist()[-1] == 5000 and ptr.numel() == 11
+    rp, col, _ = d1.adj_t.csr()
+    row = d1.adj_t.storage.row()
+    assert bool((row != col).all())                       # no self loops
+    key = row * 5000 + col
+    assert torch.unique(key).numel() == key.numel()       # no duplicates
+    assert set((col * 5000 + row).tolist()) == set(key.tolist())  # symmetric
+    assert int(d1.y.max()) < 7 and d1.train_mask.dtype == torch.bool
+    # a partition's halo is a few times the partition, not the whole graph
+    b = gas.collate(gas.Adj(rp, col, None, 5000, 5000), d1.x, d1.y, d1.train_mask, ptr, [3])
+    assert b.batch_size == 500 and 0 < b.n_id.numel() - 500 < 4500
+
+
+def test_metis_standin_and_permute():
+    data, ptr = tga.synthetic_graph(1200, 9000, 4, 3, 6, seed=2)
+    perm, p2 = tga.metis(data.adj_t, 6, log=False)
+    assert torch.equal(perm, torch.arange(1200)) and torch.equal(p2, ptr)
+    # a graph that is not pre-clustered gets a locality order and equal cuts
+    perm3, p3 = tga.metis(data.adj_t, 4, log=False)
+    assert sorted(perm3.tolist()) == list(range(1200)) and p3.tolist() == [0, 300, 600, 900, 1200]
+    d3 = tga.permute(data, perm3, log=False)
+    assert torch.equal(d3.x, data.x[perm3]) and d3.adj_t.nnz() == data.adj_t.nnz()
+    # permuted adjacency: edge (i, j) of the new graph is edge (perm[i], perm[j]) of the old one
+    r, c = d3.adj_t.storage.row(), d3.adj_t.storage.col()
+    old = set((data.adj_t.storage.row() * 1200 + data.adj_t.storage.col()).tolist())
+    assert set((perm3[r] * 1200 + perm3[c]).tolist()) == old
+    assert data.x is not d3.x and torch.equal(data.x, tga.synthetic_graph(1200, 9000, 4, 3, 6, seed=2)[0].x)
+
+
+def test_no_cpu_fallback_on_the_product_path():
+    data, ptr = tga.synthetic_graph(600, 4000, 4, 3, 3, seed=0)
+    with pytest.raises(RuntimeError):
+        tga.SubgraphLoader(data, ptr)  # CPU graph, no device: refuses
+    h = tga.History(10, 4, device='cpu')
+    with pytest.raises(RuntimeError):
+        h.pull(torch.tensor([1, 2]))
+    from incagg_gnn_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.gather_rows(torch.randn(4, 4), torch.tensor([0]))
+    with pytest.raises(RuntimeError):
+        ops.spmm_raw(torch.zeros(2, dtype=torch.int32), torch.zeros(0, dtype=torch.int32), None, torch.randn(2, 4))
+
+
+def test_config_table_matches_reference_yaml_values():
+    from incagg_gnn_b200.train import CONFIGS
+    c3 = CONFIGS['C3']
+    assert c3['model'] == 'GCN2' and c3['num_parts'] == 150 and c3['batch_size'] == 1
+    assert c3['architecture']['num_layers'] == 5 and c3['architecture']['hidden_channels'] == 128
+    assert c3['architecture']['shared_weights'] is False and c3['lr'] == 0.001
+    assert CONFIGS['C2']['architecture']['alpha'] == 0.1 and CONFIGS['C2']['grad_norm'] == 1.0
+    assert tga.SHAPES['products'][0] == 2_449_029 and tga.SHAPES['reddit'][2] == 602
+
+
+def test_utils():
+    logits = torch.tensor([[2., 1.], [0., 3.], [1., 0.]])
+    y = torch.tensor([0, 1, 1])
+    assert abs(tga.compute_micro_f1(logits, y) - 2 / 3) < 1e-9
+    assert tga.index2mask(torch.tensor([1, 3]), 5).tolist() == [False, True, False, True, False]
