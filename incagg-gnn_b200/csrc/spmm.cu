@@ -18,6 +18,8 @@
 //   * rows longer than LONG_ROW edges are split across the warps of a CTA by a second
 //     kernel (degree-bucketed scheduling) and combined in a fixed order -> deterministic.
 #include <float.h>
+#include <stdlib.h>
+#include <limits.h>
 
 #include "common.cuh"
 
@@ -64,6 +66,24 @@ __device__ __forceinline__ void store_vec_i(int32_t* p, const int32_t (&v)[VEC])
   }
 }
 
+// Degree-bucket plan of one CSR structure.  Rows with more than `long_row` edges are not handled by
+// a lane group but by whole CTAs: a row of up to `chunk` edges is one work item, a longer ("giant")
+// row is split into ceil(deg / chunk) items whose partial results meet in a scratch area.  The plan
+// depends only on rowptr, so it is built once per structure and reused by every SpMM over it
+// (all layers of a step, forward and - for the transposed structure - backward).
+struct SpmmPlan {
+  int32_t n_items;    // number of work items
+  int32_t n_scratch;  // scratch slots handed out to split rows (may exceed the usable capacity)
+  int32_t long_row;
+  int32_t chunk;
+  int32_t capacity;   // size of the item array
+  int32_t pad[3];
+  // followed by int4 items[capacity]: {row, chunk index, scratch base or -1, number of chunks}
+};
+constexpr int PART_STRIDE = 512;        // floats per scratch slot (= widest tile, 32 lanes * 4 * 4)
+constexpr int PART_SLOTS = 16384;       // scratch slots per device (32 MB values + 32 MB args)
+constexpr int PLAN_SCRATCH_CAP = 8192;  // slots one plan may hand out (times the feature tiles)
+
 struct SpmmParams {
   const int32_t* rowptr;
   const int32_t* col;
@@ -86,12 +106,17 @@ struct SpmmParams {
   int32_t slab_F;
   int32_t tiles_per_slab;
   int32_t reducers[8];
-  // long-row handling
-  int32_t long_row;         // rows with more edges than this are skipped by the main kernel
-  int32_t* long_count;      // device counter of deferred (row, tile) entries
-  int2* long_rows;          // device list of deferred entries {row, blockIdx.y}
-  int32_t long_capacity;
+  // degree-bucket plan (see SpmmPlan) and the scratch area of split rows
+  const SpmmPlan* plan;
+  const int4* items;        // work items of the plan
+  int32_t long_grid;        // CTAs [0, long_grid) walk the plan's items, the rest own short rows
+  int32_t n_tiles;          // gridDim.y
+  float* part_val;          // [part_slots][PART_STRIDE] partial results of split rows
+  int32_t* part_arg;        // same shape, winning edge of min/max partials
+  int32_t* part_done;       // [part_slots] arrival counters (left at zero by every call)
+  int32_t part_slots;
 };
+
 
 template <int REDUCE>
 __device__ __forceinline__ float red_init(int op) {
@@ -269,77 +294,81 @@ __device__ __forceinline__ void tile_info(const SpmmParams& p, int y, int& op, i
   }
 }
 
-// Main kernel: one G-lane group per row, blockIdx.y = feature tile.
+// One launch per SpMM.  blockIdx.y = feature tile.
+//   CTAs [0, long_grid): walk the plan's work items (long / giant rows), one item per CTA trip:
+//     the 8 warps take contiguous 32-aligned slices of the item's edges and are combined through
+//     shared memory in warp order (deterministic; min/max keep the first winner because warps own
+//     increasing edge ranges).  Items of a split row store their partial in the scratch area; the
+//     last one to arrive combines them in chunk order and writes the row, so the result does not
+//     depend on scheduling.  Low block indices are scheduled first, so the heavy rows start early.
+//   remaining CTAs: one G-lane group per short row.
 template <int REDUCE, int VEC, int G, int NCH, bool DELTA, bool ARG>
 __global__ void __launch_bounds__(SPMM_THREADS)
-spmm_rows_kernel(const SpmmParams p) {
-  constexpr int GROUPS = SPMM_THREADS / G;
+spmm_kernel(const SpmmParams p) {
+  constexpr int COVER = G * VEC * NCH;
   const int lane = threadIdx.x & 31;
-  const int lane_g = threadIdx.x % G;
-  const int sub = lane / G;  // group index inside the warp
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
-  const int64_t row = (int64_t)blockIdx.x * GROUPS + threadIdx.x / G;
-  if (row >= p.rows) return;
-
+  const int long_row = p.plan->long_row;
   int op, fbase, flim;
-  tile_info<REDUCE, G * VEC * NCH>(p, blockIdx.y, op, fbase, flim);
-  const int s = __ldg(p.rowptr + row), e = __ldg(p.rowptr + row + 1);
-  if (e - s > p.long_row) {
-    // Degree bucket "long": defer to spmm_long_rows_kernel (one CTA per entry).  If the list is
-    // full the row is simply processed here.
-    int slot = 0;
-    if (lane_g == 0) slot = atomicAdd(p.long_count, 1);
-    slot = __shfl_sync(gmask, slot, 0, G);
-    if (slot < p.long_capacity) {
-      if (lane_g == 0) p.long_rows[slot] = make_int2((int)row, (int)blockIdx.y);
-      return;
-    }
-  }
-  float acc[NCH][VEC];
-  int32_t arg[NCH][VEC];
-#pragma unroll
-  for (int k = 0; k < NCH; ++k)
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { acc[k][i] = red_init<REDUCE>(op); arg[k][i] = -1; }
-  walk_edges<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, s, e, fbase, flim, lane_g, gmask, acc, arg);
-  finish_row<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, row, e - s, fbase, flim, lane_g, acc, arg);
-}
+  tile_info<REDUCE, COVER>(p, blockIdx.y, op, fbase, flim);
 
-// Long rows: one CTA per deferred (row, feature tile) entry, always 32 lanes per row segment.
-// Each of the 8 warps walks a contiguous slice of the row's edges; partials are combined through
-// shared memory in warp order (deterministic; min/max keep the first winner because warps own
-// increasing edge ranges).  COVER_MAIN is the tile width used by the kernel that deferred the row.
-template <int REDUCE, int VEC, int NCH, int COVER_MAIN, bool DELTA, bool ARG>
-__global__ void __launch_bounds__(SPMM_THREADS)
-spmm_long_rows_kernel(const SpmmParams p) {
-  constexpr int G = 32;
-  constexpr int WARPS = SPMM_THREADS / 32;
-  static_assert(COVER_MAIN <= G * VEC * NCH, "long-row tile must cover the deferring tile");
-  __shared__ float s_acc[WARPS][NCH][32 * VEC];
-  __shared__ int32_t s_arg[ARG ? WARPS : 1][NCH][32 * VEC];
-  const int n_long = min(*p.long_count, p.long_capacity);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
-    const int2 ent = p.long_rows[li];
-    const int64_t row = ent.x;
-    int op, fbase, flim;
-    tile_info<REDUCE, COVER_MAIN>(p, ent.y, op, fbase, flim);
-    flim = min(flim, fbase + COVER_MAIN);
+  if ((int)blockIdx.x >= p.long_grid) {
+    // ---- short rows ----
+    constexpr int GROUPS = SPMM_THREADS / G;
+    const int lane_g = threadIdx.x % G;
+    const int sub = lane / G;  // group index inside the warp
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
+    const int64_t row = (int64_t)(blockIdx.x - p.long_grid) * GROUPS + threadIdx.x / G;
+    if (row >= p.rows) return;
     const int s = __ldg(p.rowptr + row), e = __ldg(p.rowptr + row + 1);
-    const int deg = e - s;
-    // split on multiples of 32 edges so every warp issues full coalesced index loads
-    const int per = ((deg + WARPS - 1) / WARPS + 31) & ~31;
-    const int ws = min(e, s + w * per), we = min(e, ws + per);
+    if (e - s > long_row) return;  // owned by the plan's items
     float acc[NCH][VEC];
     int32_t arg[NCH][VEC];
 #pragma unroll
     for (int k = 0; k < NCH; ++k)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) { acc[k][i] = red_init<REDUCE>(op); arg[k][i] = -1; }
-    walk_edges<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, ws, we, fbase, flim, lane, 0xffffffffu, acc,
-                                                arg);
+    walk_edges<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, s, e, fbase, flim, lane_g, gmask, acc, arg);
+    finish_row<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, row, e - s, fbase, flim, lane_g, acc, arg);
+    return;
+  }
+
+  // ---- long / giant rows ----
+  constexpr int LN = (G == 32) ? NCH : 1;  // vectors per lane with 32 lanes per row segment
+  static_assert(COVER <= 32 * VEC * LN, "long-row lanes must cover the tile");
+  static_assert(32 * VEC * LN <= PART_STRIDE, "partial slot too small");
+  constexpr int WARPS = SPMM_THREADS / 32;
+  __shared__ float s_acc[WARPS][LN][32 * VEC];
+  __shared__ int32_t s_arg[ARG ? WARPS : 1][LN][32 * VEC];
+  const int n_items = min(p.plan->n_items, p.plan->capacity);
+  const int chunk = p.plan->chunk;
+  const int w = threadIdx.x >> 5;
+  const int r = (REDUCE == R_RUNTIME) ? op : REDUCE;
+  flim = min(flim, fbase + COVER);
+  for (int li = blockIdx.x; li < n_items; li += p.long_grid) {
+    const int4 ent = p.items[li];  // {row, chunk index, scratch base, number of chunks}
+    const int64_t row = ent.x;
+    const int rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
+    const int deg = re - rs;
+    // a split row whose scratch slots do not fit is walked whole by its first item
+    bool split = ent.z >= 0;
+    if (split && (int64_t)(ent.z + ent.w) * p.n_tiles > p.part_slots) {
+      if (ent.y != 0) continue;  // (uniform over the CTA)
+      split = false;
+    }
+    const int s = split ? rs + ent.y * chunk : rs;
+    const int e = split ? min(re, s + chunk) : re;
+    // split on multiples of 32 edges so every warp issues full coalesced index loads
+    const int per = (((e - s) + WARPS - 1) / WARPS + 31) & ~31;
+    const int ws = min(e, s + w * per), we = min(e, ws + per);
+    float acc[LN][VEC];
+    int32_t arg[LN][VEC];
 #pragma unroll
-    for (int k = 0; k < NCH; ++k)
+    for (int k = 0; k < LN; ++k)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { acc[k][i] = red_init<REDUCE>(op); arg[k][i] = -1; }
+    walk_edges<REDUCE, VEC, 32, LN, DELTA, ARG>(p, op, ws, we, fbase, flim, lane, 0xffffffffu, acc, arg);
+#pragma unroll
+    for (int k = 0; k < LN; ++k)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         s_acc[w][k][lane * VEC + i] = acc[k][i];
@@ -347,10 +376,9 @@ spmm_long_rows_kernel(const SpmmParams p) {
       }
     __syncthreads();
     if (w == 0) {
-      const int r = (REDUCE == R_RUNTIME) ? op : REDUCE;
       for (int ww = 1; ww < WARPS; ++ww) {
 #pragma unroll
-        for (int k = 0; k < NCH; ++k)
+        for (int k = 0; k < LN; ++k)
 #pragma unroll
           for (int i = 0; i < VEC; ++i) {
             const float t = s_acc[ww][k][lane * VEC + i];
@@ -362,10 +390,75 @@ spmm_long_rows_kernel(const SpmmParams p) {
             }
           }
       }
-      finish_row<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, row, deg, fbase, flim, lane, acc, arg);
+      bool write_row = true;
+      if (split) {
+        const int64_t slot0 = (int64_t)ent.z * p.n_tiles + (int64_t)blockIdx.y * ent.w;
+        float* pv = p.part_val + (slot0 + ent.y) * PART_STRIDE;
+        int32_t* pa = p.part_arg + (slot0 + ent.y) * PART_STRIDE;
+#pragma unroll
+        for (int k = 0; k < LN; ++k)
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            pv[(k * 32 + lane) * VEC + i] = acc[k][i];
+            if constexpr (ARG) pa[(k * 32 + lane) * VEC + i] = arg[k][i];
+          }
+        __threadfence();
+        int prev = 0;
+        if (lane == 0) prev = atomicAdd(p.part_done + slot0, 1);
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        write_row = (prev == ent.w - 1);
+        if (write_row) {  // last arriver: combine all partials in chunk order
+          __threadfence();
+#pragma unroll
+          for (int k = 0; k < LN; ++k)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) { acc[k][i] = red_init<REDUCE>(op); arg[k][i] = -1; }
+          for (int c = 0; c < ent.w; ++c) {
+            const float* qv = p.part_val + (slot0 + c) * PART_STRIDE;
+            const int32_t* qa = p.part_arg + (slot0 + c) * PART_STRIDE;
+#pragma unroll
+            for (int k = 0; k < LN; ++k)
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) {
+                const float t = __ldcg(qv + (k * 32 + lane) * VEC + i);
+                if (r == R_SUM || r == R_MEAN) {
+                  acc[k][i] += t;
+                } else if ((r == R_MIN && t < acc[k][i]) || (r == R_MAX && t > acc[k][i])) {
+                  acc[k][i] = t;
+                  if constexpr (ARG) arg[k][i] = __ldcg(qa + (k * 32 + lane) * VEC + i);
+                }
+              }
+          }
+          if (lane == 0) p.part_done[slot0] = 0;  // leave the counters clean for the next call
+        }
+      }
+      if (write_row)
+        finish_row<REDUCE, VEC, 32, LN, DELTA, ARG>(p, op, row, deg, fbase, flim, lane, acc, arg);
     }
     __syncthreads();
   }
+}
+
+// Plan construction: one thread per row appends the row's work items.
+__global__ void spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t rows, SpmmPlan* plan,
+                                 int4* __restrict__ items, int long_row, int chunk, int capacity) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row == 0) {
+    plan->long_row = long_row;
+    plan->chunk = chunk;
+    plan->capacity = capacity;
+  }
+  if (row >= rows) return;
+  const int deg = rowptr[row + 1] - rowptr[row];
+  if (deg <= long_row) return;
+  int n = (deg + chunk - 1) / chunk, sbase = -1;
+  if (n > 1) {
+    sbase = atomicAdd(&plan->n_scratch, n);
+    if (sbase + n > PLAN_SCRATCH_CAP) { sbase = -1; n = 1; }
+  }
+  const int slot = atomicAdd(&plan->n_items, n);
+  if (slot + n <= capacity)
+    for (int c = 0; c < n; ++c) items[slot + c] = make_int4((int)row, c, sbase, n);
 }
 
 __global__ void minmax_bwd_kernel(const int32_t* __restrict__ col, const float* __restrict__ val,
@@ -386,67 +479,118 @@ __global__ void minmax_bwd_kernel(const int32_t* __restrict__ col, const float* 
 }
 
 // ---- host-side dispatch ------------------------------------------------------
-struct LongRowScratch {
-  int32_t* count = nullptr;  // [1] (+ padding)
-  int2* rows = nullptr;      // [capacity]
-  int capacity = 0;
-  int device = -1;
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+// Degree buckets: rows up to LONG_ROW edges -> one lane group; up to CHUNK edges -> one CTA; longer
+// rows -> ceil(deg / CHUNK) CTAs.  (Tunable for experiments through the environment.)
+static int long_row_edges() { static int v = env_int("INCAGG_SPMM_LONG_ROW", 64); return v; }
+static int chunk_edges() { static int v = env_int("INCAGG_SPMM_CHUNK", 2048); return v; }
+
+// Upper bound of the work items of a structure: one per row longer than LONG_ROW plus the extra
+// chunks of split rows.  nnz < 0 = unknown.
+static int64_t plan_capacity(int64_t rows, int64_t nnz) {
+  int64_t long_rows = rows;
+  if (nnz >= 0) {
+    const int64_t by_edges = nnz / (long_row_edges() + 1) + 1;
+    if (by_edges < long_rows) long_rows = by_edges;
+  }
+  return long_rows + PLAN_SCRATCH_CAP + 8;
+}
+
+static int build_plan(const int32_t* rowptr, int64_t rows, void* plan, int64_t capacity,
+                      cudaStream_t st) {
+  IA_CHECK_ARG(capacity < 0x7fffffff, "plan too large");
+  IA_CUDA(cudaMemsetAsync(plan, 0, sizeof(SpmmPlan), st));
+  if (rows == 0) return INCAGG_OK;
+  SpmmPlan* hdr = static_cast<SpmmPlan*>(plan);
+  int4* items = reinterpret_cast<int4*>(hdr + 1);
+  spmm_plan_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(rowptr, rows, hdr, items,
+                                                                  long_row_edges(), chunk_edges(),
+                                                                  (int)capacity);
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}
+
+struct SpmmScratch {
+  float* part_val = nullptr;
+  int32_t* part_arg = nullptr;
+  int32_t* part_done = nullptr;
+  void* plan = nullptr;  // temporary plan of calls that pass none
+  int64_t plan_capacity = 0;
 };
-// A small per-device scratch for the long-row list (allocated once, reused by every call;
-// kernels on one stream serialise, and the count is re-zeroed on that stream before each use).
-static int get_long_scratch(LongRowScratch** out) {
-  static thread_local LongRowScratch scratch[16];
+// Per-device scratch (allocated once / grown on demand, reused by every call: kernels of one stream
+// serialise).  Concurrent SpMM calls on different streams of one device must not share a thread.
+static int get_scratch(SpmmScratch** out, int64_t want_plan_capacity) {
+  static thread_local SpmmScratch scratch[16];
   int dev = 0;
   IA_CUDA(cudaGetDevice(&dev));
   IA_CHECK_ARG(dev >= 0 && dev < 16, "device ordinal %d out of range", dev);
-  LongRowScratch& s = scratch[dev];
-  if (s.count == nullptr) {
-    s.capacity = 1 << 16;
-    IA_CUDA(cudaMalloc(&s.count, 16 + sizeof(int2) * (size_t)s.capacity));
-    s.rows = reinterpret_cast<int2*>(reinterpret_cast<char*>(s.count) + 16);
-    s.device = dev;
+  SpmmScratch& s = scratch[dev];
+  if (s.part_val == nullptr) {
+    IA_CUDA(cudaMalloc(&s.part_val, sizeof(float) * (size_t)PART_SLOTS * PART_STRIDE));
+    IA_CUDA(cudaMalloc(&s.part_arg, sizeof(int32_t) * (size_t)PART_SLOTS * PART_STRIDE));
+    IA_CUDA(cudaMalloc(&s.part_done, sizeof(int32_t) * (size_t)PART_SLOTS));
+    IA_CUDA(cudaMemset(s.part_done, 0, sizeof(int32_t) * (size_t)PART_SLOTS));
+  }
+  if (want_plan_capacity > s.plan_capacity) {
+    int64_t cap = s.plan_capacity ? s.plan_capacity : (1 << 16);
+    while (cap < want_plan_capacity) cap <<= 1;
+    if (s.plan) IA_CUDA(cudaFree(s.plan));  // synchronises the device: earlier users are done
+    s.plan = nullptr;
+    s.plan_capacity = 0;
+    IA_CUDA(cudaMalloc(&s.plan, sizeof(SpmmPlan) + sizeof(int4) * (size_t)cap));
+    s.plan_capacity = cap;
   }
   *out = &s;
   return INCAGG_OK;
 }
 
-constexpr int LONG_ROW_EDGES = 2048;
-
 template <int REDUCE, int VEC, int G, int NCH, bool DELTA, bool ARG>
-static int launch_cfg(SpmmParams& p, int n_tiles, cudaStream_t st) {
+static int launch_cfg(SpmmParams& p, int n_tiles, int64_t items_bound, cudaStream_t st) {
   constexpr int GROUPS = SPMM_THREADS / G;
   const int64_t blocks = (p.rows + GROUPS - 1) / GROUPS;
-  IA_CHECK_ARG(blocks <= 0x7fffffff, "too many rows for one launch");
   if (blocks == 0) return INCAGG_OK;
-  LongRowScratch* ls = nullptr;
-  int rc = get_long_scratch(&ls);
+  SpmmScratch* sc = nullptr;
+  const bool own_plan = (p.plan == nullptr);
+  int rc = get_scratch(&sc, own_plan ? plan_capacity(p.rows, -1) : 0);
   if (rc != INCAGG_OK) return rc;
-  p.long_row = LONG_ROW_EDGES;
-  p.long_count = ls->count;
-  p.long_rows = ls->rows;
-  p.long_capacity = ls->capacity;
-  IA_CUDA(cudaMemsetAsync(ls->count, 0, sizeof(int32_t), st));
-  dim3 grid((unsigned)blocks, (unsigned)n_tiles);
-  spmm_rows_kernel<REDUCE, VEC, G, NCH, DELTA, ARG><<<grid, SPMM_THREADS, 0, st>>>(p);
-  IA_LAUNCH_CHECK();
-  // Long-row bucket (reads the entry count on the device; an empty list costs one tiny launch).
-  constexpr int NCH_LONG = (G == 32) ? NCH : 1;
-  spmm_long_rows_kernel<REDUCE, VEC, NCH_LONG, G * VEC * NCH, DELTA, ARG>
-      <<<2 * sm_count(), SPMM_THREADS, 0, st>>>(p);
+  if (own_plan) {  // no plan given: build a temporary one (one memset + one small launch)
+    rc = build_plan(p.rowptr, p.rows, sc->plan, sc->plan_capacity, st);
+    if (rc != INCAGG_OK) return rc;
+    p.plan = static_cast<const SpmmPlan*>(sc->plan);
+    items_bound = p.rows + PLAN_SCRATCH_CAP;
+  }
+  p.items = reinterpret_cast<const int4*>(p.plan + 1);
+  p.part_val = sc->part_val;
+  p.part_arg = sc->part_arg;
+  p.part_done = sc->part_done;
+  p.part_slots = PART_SLOTS;
+  p.n_tiles = n_tiles;
+  // CTAs that walk the plan's items: never more than the items can be, at most 4 per SM
+  int64_t lg = 4 * (int64_t)sm_count();
+  if (items_bound < lg) lg = items_bound;
+  if (lg < 1) lg = 1;
+  p.long_grid = (int)lg;
+  IA_CHECK_ARG(blocks + lg <= 0x7fffffff, "too many rows for one launch");
+  dim3 grid((unsigned)(blocks + lg), (unsigned)n_tiles);
+  spmm_kernel<REDUCE, VEC, G, NCH, DELTA, ARG><<<grid, SPMM_THREADS, 0, st>>>(p);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
 
 // Pick (VEC, G, NCH) for a feature width and alignment.
 template <int REDUCE, bool DELTA, bool ARG>
-static int dispatch_shape(SpmmParams& p, int width, int vec, int tiles_mult, cudaStream_t st) {
+static int dispatch_shape(SpmmParams& p, int width, int vec, int tiles_mult, int64_t items_bound,
+                          cudaStream_t st) {
   // `width` = number of features one tile row must cover (F, or slab_F for multi)
   const int nvec = (width + vec - 1) / vec;
   auto tiles = [&](int cover) { return tiles_mult * ((width + cover - 1) / cover); };
 #define IA_CFG(V, G_, N_)                                                    \
   do {                                                                       \
     if (REDUCE == R_RUNTIME) p.tiles_per_slab = (width + V * G_ * N_ - 1) / (V * G_ * N_); \
-    return launch_cfg<REDUCE, V, G_, N_, DELTA, ARG>(p, tiles(V * G_ * N_), st); \
+    return launch_cfg<REDUCE, V, G_, N_, DELTA, ARG>(p, tiles(V * G_ * N_), items_bound, st); \
   } while (0)
   if (vec == 4) {
     if (nvec <= 8) IA_CFG(4, 8, 1);
@@ -494,10 +638,25 @@ static int check_common(const int32_t* rowptr, const int32_t* col, const float* 
 
 using namespace incagg;
 
+extern "C" size_t incagg_spmm_plan_bytes(int64_t rows, int64_t nnz) {
+  if (rows < 0) return 0;
+  return sizeof(SpmmPlan) + sizeof(int4) * (size_t)plan_capacity(rows, nnz);
+}
+
+extern "C" int incagg_spmm_plan(const int32_t* rowptr, int64_t rows, int64_t nnz, void* plan,
+                                size_t plan_bytes, incagg_stream_t stream) {
+  IA_CHECK_ARG(rows >= 0, "negative size");
+  IA_CHECK_ARG(plan != nullptr && plan_bytes >= incagg_spmm_plan_bytes(rows, nnz), "plan buffer too small");
+  IA_CHECK_ARG(rows == 0 || rowptr != nullptr, "rowptr is NULL");
+  IA_CHECK_ARG((reinterpret_cast<uintptr_t>(plan) & 15) == 0, "plan buffer must be 16-byte aligned");
+  return build_plan(rowptr, rows, plan, (int64_t)((plan_bytes - sizeof(SpmmPlan)) / sizeof(int4)),
+                    as_stream(stream));
+}
+
 extern "C" int incagg_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col,
                                const float* val, const float* X, int64_t ldx, float* out,
                                int64_t ldo, int32_t* arg_out, int64_t lda, int64_t rows, int32_t F,
-                               incagg_stream_t stream) {
+                               const void* plan, incagg_stream_t stream) {
   int rc = check_common(rowptr, col, X, out, ldx, ldo, rows, F);
   if (rc != INCAGG_OK) return rc;
   if (rows == 0 || F == 0) return INCAGG_OK;
@@ -507,17 +666,19 @@ extern "C" int incagg_spmm_csr(int reduce, const int32_t* rowptr, const int32_t*
   p.rowptr = rowptr; p.col = col; p.val = val; p.X = X; p.ldx = ldx; p.out = out; p.ldo = ldo;
   p.arg = (reduce == R_MIN || reduce == R_MAX) ? arg_out : nullptr;
   p.lda = lda; p.rows = rows; p.F = F;
+  p.plan = static_cast<const SpmmPlan*>(plan);
   const int vec = pick_vec(p, F);
   cudaStream_t st = as_stream(stream);
+  const int64_t ib = INT64_MAX;
   switch (reduce) {
-    case R_SUM: return dispatch_shape<R_SUM, false, false>(p, F, vec, 1, st);
-    case R_MEAN: return dispatch_shape<R_MEAN, false, false>(p, F, vec, 1, st);
+    case R_SUM: return dispatch_shape<R_SUM, false, false>(p, F, vec, 1, ib, st);
+    case R_MEAN: return dispatch_shape<R_MEAN, false, false>(p, F, vec, 1, ib, st);
     case R_MIN:
-      return p.arg ? dispatch_shape<R_MIN, false, true>(p, F, vec, 1, st)
-                   : dispatch_shape<R_MIN, false, false>(p, F, vec, 1, st);
+      return p.arg ? dispatch_shape<R_MIN, false, true>(p, F, vec, 1, ib, st)
+                   : dispatch_shape<R_MIN, false, false>(p, F, vec, 1, ib, st);
     default:
-      return p.arg ? dispatch_shape<R_MAX, false, true>(p, F, vec, 1, st)
-                   : dispatch_shape<R_MAX, false, false>(p, F, vec, 1, st);
+      return p.arg ? dispatch_shape<R_MAX, false, true>(p, F, vec, 1, ib, st)
+                   : dispatch_shape<R_MAX, false, false>(p, F, vec, 1, ib, st);
   }
 }
 
@@ -525,7 +686,7 @@ extern "C" int incagg_spmm_delta(int reduce, const int32_t* rowptr, const int32_
                                  const float* val, const float* x, int64_t ldx, const float* m_in,
                                  int64_t ld_in, const float* m_ag, int64_t ld_ag,
                                  const int64_t* n_id, float* out, int64_t ldo, int64_t rows,
-                                 int32_t F, incagg_stream_t stream) {
+                                 int32_t F, const void* plan, incagg_stream_t stream) {
   int rc = check_common(rowptr, col, x, out, ldx, ldo, rows, F);
   if (rc != INCAGG_OK) return rc;
   if (rows == 0 || F == 0) return INCAGG_OK;
@@ -536,15 +697,16 @@ extern "C" int incagg_spmm_delta(int reduce, const int32_t* rowptr, const int32_
   p.rowptr = rowptr; p.col = col; p.val = val; p.X = x; p.ldx = ldx; p.out = out; p.ldo = ldo;
   p.rows = rows; p.F = F; p.m_in = m_in; p.ld_in = ld_in; p.m_ag = m_ag; p.ld_ag = ld_ag;
   p.n_id = n_id;
+  p.plan = static_cast<const SpmmPlan*>(plan);
   const int vec = pick_vec(p, F);
   cudaStream_t st = as_stream(stream);
-  if (reduce == R_SUM) return dispatch_shape<R_SUM, true, false>(p, F, vec, 1, st);
-  return dispatch_shape<R_MEAN, true, false>(p, F, vec, 1, st);
+  if (reduce == R_SUM) return dispatch_shape<R_SUM, true, false>(p, F, vec, 1, INT64_MAX, st);
+  return dispatch_shape<R_MEAN, true, false>(p, F, vec, 1, INT64_MAX, st);
 }
 
 extern "C" int incagg_spmm_multi(const int32_t* rowptr, const int32_t* col, const float* val,
                                  const float* X, int64_t ldx, float* out, int64_t ldo, int64_t rows,
-                                 int32_t F, int32_t K, const int32_t* reducers,
+                                 int32_t F, int32_t K, const int32_t* reducers, const void* plan,
                                  incagg_stream_t stream) {
   IA_CHECK_ARG(K >= 1 && K <= 8, "K must be in [1, 8] (got %d)", K);
   IA_CHECK_ARG(reducers != nullptr, "reducers is NULL");
@@ -558,8 +720,9 @@ extern "C" int incagg_spmm_multi(const int32_t* rowptr, const int32_t* col, cons
     IA_CHECK_ARG(reducers[k] >= 0 && reducers[k] <= 3, "unknown reducer %d", reducers[k]);
     p.reducers[k] = reducers[k];
   }
+  p.plan = static_cast<const SpmmPlan*>(plan);
   const int vec = pick_vec(p, F);  // slab starts k*F keep the alignment of F
-  return dispatch_shape<R_RUNTIME, false, false>(p, F, vec, K, as_stream(stream));
+  return dispatch_shape<R_RUNTIME, false, false>(p, F, vec, K, INT64_MAX, as_stream(stream));
 }
 
 extern "C" int incagg_spmm_minmax_bwd(const int32_t* col, const float* val, const int32_t* arg,

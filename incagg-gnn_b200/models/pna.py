@@ -66,9 +66,9 @@ class PNAConv(torch.nn.Module):
             Fo = self.out_channels
             hs = torch.empty((x.size(0), len(combos) * Fo), dtype=x.dtype, device=x.device)
             for k, pre_lin in enumerate(self.pre_lins):
-                torch.relu(pre_lin(x), out=hs[:, k * Fo:(k + 1) * Fo])
+                hs[:, k * Fo:(k + 1) * Fo] = pre_lin(x).relu_()
             agg = ops.spmm_multi_raw(adj_t.rowptr, adj_t.col, adj_t.value, hs, Fo,
-                                     [a for a, _ in combos], rows=adj_t.size(0))
+                                     [a for a, _ in combos], rows=adj_t.size(0), plan=adj_t.plan())
             for k, ((aggr, scaler), post_lin) in enumerate(zip(combos, self.post_lins)):
                 h = post_lin(agg[:, k * Fo:(k + 1) * Fo])
                 out = out + self._scale(h, scaler, deg)

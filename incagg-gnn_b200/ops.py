@@ -47,9 +47,21 @@ def _ld(t: Tensor) -> int:
 # --------------------------------------------------------------------------------------------
 # SpMM
 # --------------------------------------------------------------------------------------------
+def spmm_plan(rowptr: Tensor, rows: Optional[int] = None, nnz: int = -1) -> Tensor:
+    """Degree-bucket plan of a CSR structure (built once, reused by every SpMM over it)."""
+    _require_cuda(rowptr)
+    assert rowptr.dtype == torch.int32
+    n_rows = rowptr.numel() - 1 if rows is None else rows
+    nbytes = lib.incagg_spmm_plan_bytes(n_rows, nnz)
+    plan = torch.empty(nbytes, dtype=torch.uint8, device=rowptr.device)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_spmm_plan(ptr(rowptr), n_rows, nnz, ptr(plan), nbytes, _stream()))
+    return plan
+
+
 def spmm_raw(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, reduce: str = "sum",
              rows: Optional[int] = None, out: Optional[Tensor] = None,
-             return_arg: bool = False):
+             return_arg: bool = False, plan: Optional[Tensor] = None):
     """out[i] = reduce_e val[e] * x[col[e]] over a CSR with int32 rowptr/col (device)."""
     _require_cuda(rowptr, col, val, x)
     assert rowptr.dtype == torch.int32 and col.dtype == torch.int32
@@ -65,13 +77,14 @@ def spmm_raw(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, redu
     LAUNCHES["calls"] += 1
     check(lib.incagg_spmm_csr(REDUCE[reduce], ptr(rowptr), ptr(col), ptr(val), ptr(x), _ld(x),
                               ptr(out), _ld(out), ptr(arg), F if arg is not None else 0, n_rows, F,
-                              _stream()))
+                              ptr(plan), _stream()))
     if squeeze:
         out = out.squeeze(1)
     return (out, arg) if return_arg else out
 
 
-def spmm_delta_raw(rowptr, col, val, x, m_in, m_ag, n_id=None, reduce="sum", rows=None, out=None):
+def spmm_delta_raw(rowptr, col, val, x, m_in, m_ag, n_id=None, reduce="sum", rows=None, out=None,
+                   plan=None):
     """out = A (x - M_in[g]) + M_ag[g]; g = n_id if given (history tables read in place)."""
     _require_cuda(rowptr, col, val, x, m_in, m_ag, n_id)
     x = _f32c(x)
@@ -86,11 +99,11 @@ def spmm_delta_raw(rowptr, col, val, x, m_in, m_ag, n_id=None, reduce="sum", row
     LAUNCHES["calls"] += 1
     check(lib.incagg_spmm_delta(REDUCE[reduce], ptr(rowptr), ptr(col), ptr(val), ptr(x), _ld(x),
                                 ptr(m_in), m_in.stride(0), ptr(m_ag), m_ag.stride(0), ptr(n_id),
-                                ptr(out), _ld(out), n_rows, F, _stream()))
+                                ptr(out), _ld(out), n_rows, F, ptr(plan), _stream()))
     return out
 
 
-def spmm_multi_raw(rowptr, col, val, x, F: int, reducers, rows=None, out=None):
+def spmm_multi_raw(rowptr, col, val, x, F: int, reducers, rows=None, out=None, plan=None):
     """x is [n_src, K*F]; slab k reduced with reducers[k] ('sum'|'mean'|'min'|'max')."""
     _require_cuda(rowptr, col, val, x)
     x = _f32c(x)
@@ -103,7 +116,7 @@ def spmm_multi_raw(rowptr, col, val, x, F: int, reducers, rows=None, out=None):
     red = (ctypes.c_int32 * K)(*[REDUCE[r] for r in reducers])
     LAUNCHES["calls"] += 1
     check(lib.incagg_spmm_multi(ptr(rowptr), ptr(col), ptr(val), ptr(x), _ld(x), ptr(out), _ld(out),
-                                n_rows, F, K, ctypes.cast(red, ctypes.c_void_p), _stream()))
+                                n_rows, F, K, ctypes.cast(red, ctypes.c_void_p), ptr(plan), _stream()))
     return out
 
 

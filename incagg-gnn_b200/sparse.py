@@ -72,6 +72,8 @@ class SparseTensor:
         self.value = value.contiguous() if value is not None else None
         self.storage = _Storage(self)
         self._t = None  # cached (t_rowptr, t_col, t_val)
+        self._plan = None    # cached SpMM degree-bucket plan of this structure
+        self._t_plan = None  # ... and of the transposed structure
 
     # ---- shape -------------------------------------------------------------------------
     @property
@@ -108,6 +110,7 @@ class SparseTensor:
         out.value = self.value.to(device, non_blocking=non_blocking) if self.value is not None else None
         out.storage = _Storage(out)
         out._t = None
+        out._plan = out._t_plan = None
         return out
 
     def cuda(self):
@@ -121,17 +124,28 @@ class SparseTensor:
         out.value = self.value.cpu().pin_memory() if self.value is not None else None
         out.storage = _Storage(out)
         out._t = None
+        out._plan = out._t_plan = None
         return out
 
     def set_value(self, value: Optional[Tensor], layout: Optional[str] = None) -> "SparseTensor":
+        if value is None:
+            # the value-less view is cached so that its transposed CSR / plans are built once
+            if self.value is None:
+                return self
+            cached = self.__dict__.get('_stripped')
+            if cached is not None:
+                return cached
         out = SparseTensor.__new__(SparseTensor)
         out._sizes = self._sizes
         out.rowptr, out.col = self.rowptr, self.col
         out.value = value.contiguous() if value is not None else None
         out.storage = _Storage(out)
         out._t = None
+        out._plan, out._t_plan = self._plan, self._t_plan  # plans depend on the structure only
         if self._t is not None and value is None:
             out._t = (self._t[0], self._t[1], None)
+        if value is None:
+            self.__dict__['_stripped'] = out
         return out
 
     def masked_select_nnz(self, mask: Tensor, layout: Optional[str] = None) -> "SparseTensor":
@@ -149,6 +163,26 @@ class SparseTensor:
             self._t = (t_rowptr, t_col, t_val)
         return self._t
 
+    def plan(self) -> Tensor:
+        """SpMM plan of this structure (one small launch, cached)."""
+        if getattr(self, '_plan', None) is None:
+            self._plan = ops.spmm_plan(self.rowptr, self._sizes[0], self.col.numel())
+        return self._plan
+
+    def t_plan(self) -> Tensor:
+        if getattr(self, '_t_plan', None) is None:
+            t_rowptr = self.t_csr()[0]
+            self._t_plan = ops.spmm_plan(t_rowptr, self._sizes[1], self.col.numel())
+        return self._t_plan
+
+    def t_plan_prefix(self, rows: int) -> Tensor:
+        """Plan of the first `rows` rows of the transposed structure (backward over the in-batch
+        source rows only)."""
+        cache = self.__dict__.setdefault('_t_prefix_plans', {})
+        if rows not in cache:
+            cache[rows] = ops.spmm_plan(self.t_csr()[0], rows, -1)
+        return cache[rows]
+
     def t(self) -> "SparseTensor":
         t_rowptr, t_col, t_val = self.t_csr()
         out = SparseTensor.__new__(SparseTensor)
@@ -156,6 +190,7 @@ class SparseTensor:
         out.rowptr, out.col, out.value = t_rowptr, t_col, t_val
         out.storage = _Storage(out)
         out._t = (self.rowptr, self.col, self.value)
+        out._plan, out._t_plan = self._t_plan, self._plan
         return out
 
     # ---- products ------------------------------------------------------------------------
@@ -179,10 +214,11 @@ class _SpMM(torch.autograd.Function):
         ctx.adj, ctx.reduce, ctx.n_src, ctx.grad_rows = adj, reduce, x.size(0), grad_rows
         if reduce in ("min", "max"):
             out, arg = ops.spmm_raw(adj.rowptr, adj.col, adj.value, x, reduce, rows=adj.size(0),
-                                    return_arg=True)
+                                    return_arg=True, plan=adj.plan())
             ctx.save_for_backward(arg)
             return out
-        return ops.spmm_raw(adj.rowptr, adj.col, adj.value, x, reduce, rows=adj.size(0))
+        return ops.spmm_raw(adj.rowptr, adj.col, adj.value, x, reduce, rows=adj.size(0),
+                            plan=adj.plan())
 
     @staticmethod
     def backward(ctx, grad_out: Tensor):
@@ -203,10 +239,12 @@ def _transposed_product(adj: SparseTensor, grad_out: Tensor, n_src: int, grad_ro
     """grad_x = A^T grad_out.  With grad_rows = k only the first k source rows are computed (the
     rest of x was a constant, e.g. pulled history rows) and the remainder is returned as zeros."""
     t_rowptr, t_col, t_val = adj.t_csr()
+    t_plan = adj.t_plan()
     if grad_rows is None or grad_rows >= n_src:
-        return ops.spmm_raw(t_rowptr, t_col, t_val, grad_out, "sum", rows=n_src)
+        return ops.spmm_raw(t_rowptr, t_col, t_val, grad_out, "sum", rows=n_src, plan=t_plan)
     gx = torch.zeros((n_src, grad_out.size(1)), dtype=grad_out.dtype, device=grad_out.device)
-    ops.spmm_raw(t_rowptr, t_col, t_val, grad_out, "sum", rows=grad_rows, out=gx[:grad_rows])
+    ops.spmm_raw(t_rowptr, t_col, t_val, grad_out, "sum", rows=grad_rows, out=gx[:grad_rows],
+                 plan=adj.t_plan_prefix(grad_rows))
     return gx
 
 
@@ -226,7 +264,7 @@ class _SpMMDelta(torch.autograd.Function):
     def forward(ctx, x, adj, m_in, m_ag, n_id, reduce):
         ctx.adj, ctx.reduce, ctx.n_src = adj, reduce, x.size(0)
         return ops.spmm_delta_raw(adj.rowptr, adj.col, adj.value, x, m_in, m_ag, n_id, reduce,
-                                  rows=adj.size(0))
+                                  rows=adj.size(0), plan=adj.plan())
 
     @staticmethod
     def backward(ctx, grad_out):

@@ -69,10 +69,19 @@ int incagg_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *            leading dimension lda (elements)
  * The transposed call (backward, grad_X = A^T grad_out) is the same function on
  * the CSR of A^T (incagg_csr_transpose).
+ *
+ * `plan` (nullable) is the degree-bucket plan of this CSR structure built by incagg_spmm_plan: rows
+ * longer than 64 edges are walked by whole CTAs, rows longer than 2048 edges by several CTAs whose
+ * partials are combined in a fixed order (deterministic).  With plan == NULL a temporary plan is
+ * built inside the call (one extra small launch); structures that are reused (all layers of a step,
+ * forward and transposed backward) should build it once.  One kernel launch per call.
  */
+size_t incagg_spmm_plan_bytes(int64_t rows, int64_t nnz /* -1 if unknown */);
+int incagg_spmm_plan(const int32_t* rowptr, int64_t rows, int64_t nnz, void* plan /* 16-B aligned */,
+                     size_t plan_bytes, incagg_stream_t stream);
 int incagg_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col, const float* val,
                     const float* X, int64_t ldx, float* out, int64_t ldo, int32_t* arg_out,
-                    int64_t lda, int64_t rows, int32_t F, incagg_stream_t stream);
+                    int64_t lda, int64_t rows, int32_t F, const void* plan, incagg_stream_t stream);
 
 /*
  * Fused incremental-aggregation update (reference: gcn.py:241, gcn2.py:255,
@@ -86,7 +95,7 @@ int incagg_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col, const
 int incagg_spmm_delta(int reduce, const int32_t* rowptr, const int32_t* col, const float* val,
                       const float* x, int64_t ldx, const float* m_in, int64_t ld_in,
                       const float* m_ag, int64_t ld_ag, const int64_t* n_id, float* out,
-                      int64_t ldo, int64_t rows, int32_t F, incagg_stream_t stream);
+                      int64_t ldo, int64_t rows, int32_t F, const void* plan, incagg_stream_t stream);
 
 /*
  * Backward of MIN/MAX: grad_X[col[arg[i,f]], f] += val[arg[i,f]] * grad_out[i,f]
@@ -104,7 +113,7 @@ int incagg_spmm_minmax_bwd(const int32_t* col, const float* val, const int32_t* 
  */
 int incagg_spmm_multi(const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
                       int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t F, int32_t K,
-                      const int32_t* reducers, incagg_stream_t stream);
+                      const int32_t* reducers, const void* plan, incagg_stream_t stream);
 
 /* ---- CSR transpose (CSC view for the backward SpMM) ------------------- */
 /*

@@ -23,7 +23,7 @@ def test_argument_errors_do_not_need_a_gpu():
     from importlib import import_module
     _lib = import_module("incagg_gnn_b200._lib")
     # negative sizes are rejected before any CUDA call
-    rc = _lib.lib.incagg_spmm_csr(0, None, None, None, None, 0, None, 0, None, 0, -1, 4, None)
+    rc = _lib.lib.incagg_spmm_csr(0, None, None, None, None, 0, None, 0, None, 0, -1, 4, None, None)
     assert rc == _lib.ERR_INVALID and "negative" in _lib.last_error()
     rc = _lib.lib.incagg_gather_rows(None, 0, 0, None, 5, None, 0, 6, None)
     assert rc == _lib.ERR_INVALID

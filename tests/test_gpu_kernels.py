@@ -97,6 +97,23 @@ def test_spmm_long_rows_bucket(ops, cuda, reduce, F):
         assert np.array_equal(arg.cpu().numpy().astype(np.int64), ref_arg)
 
 
+@pytest.mark.parametrize("reduce", ["sum", "min"])
+def test_spmm_with_prebuilt_plan_is_identical(ops, cuda, reduce):
+    """A cached degree-bucket plan (incagg_spmm_plan) gives bit-identical results to the temporary
+    plan of a plain call, run to run (giant rows are combined in a fixed order)."""
+    rng = np.random.default_rng(21)
+    rowptr, col, val = _rand_csr(rng, 500, 3000, 50, long_rows=3, long_len=7000)
+    X = _dev(rng.standard_normal((3000, 96)).astype(np.float32), cuda)
+    rp, c, v = _dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32), _dev(val, cuda)
+    plan = ops.spmm_plan(rp, 500, col.size)
+    a = ops.spmm_raw(rp, c, v, X, reduce, plan=plan)
+    for _ in range(3):
+        assert torch.equal(a, ops.spmm_raw(rp, c, v, X, reduce, plan=plan))
+        assert torch.equal(a, ops.spmm_raw(rp, c, v, X, reduce))
+    ref = oracle.spmm(rowptr, col, val, X.cpu().numpy(), reduce, np.float64)
+    assert _rel_err(a.cpu().numpy(), ref) <= RTOL
+
+
 def test_spmm_unaligned_views_and_leading_dimension(ops, cuda):
     """Column-cropped history views (ld > F) and 4-byte-aligned-only bases use the narrower paths."""
     rng = np.random.default_rng(2)
