@@ -144,23 +144,24 @@ def timed_steps(run, mode, warmup, steps, dist, e2e=False):
     model, opt, loader, conf = run["model"], run["optimizer"], run["train_loader"], run["conf"]
     vr = mode == "incagg"
     model.train()
-    order = []
-    sampler_iter = iter(loader._batch_sampler)
+    rp_host = loader._rowptr_host
 
-    def next_ids():
-        nonlocal sampler_iter
-        try:
-            return next(sampler_iter)
-        except StopIteration:
-            sampler_iter = iter(loader._batch_sampler)
-            return next(sampler_iter)
+    def stream_of_batches():  # epochs back to back, collate prefetched on the loader's side stream
+        while True:
+            for sub in loader:
+                yield sub
+
+    batches = stream_of_batches()
+
+    def sub_edges(sub):
+        return sum(int(rp_host[o + c]) - int(rp_host[o]) for o, c in zip(sub.offset.tolist(), sub.count.tolist()))
 
     params = [p for p in model.parameters() if p.requires_grad]
     h2d = d2h = 0
 
-    def one_step(ids):
+    def one_step(sub):
         nonlocal h2d, d2h
-        batch, B, n_id, offset, count = loader._collate(ids)
+        batch, B, n_id, offset, count = sub
         x, adj_t = batch.x, batch.adj_t
         y, m = batch.y[:B], batch.train_mask[:B]
         if vr:
@@ -199,19 +200,20 @@ def timed_steps(run, mode, warmup, steps, dist, e2e=False):
         return None
 
     for _ in range(warmup):
-        one_step(next_ids())
+        one_step(next(batches))
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     h2d = d2h = 0
-    ids_list = [next_ids() for _ in range(steps)]
-    edges = sum(batch_edges(run, ids) for ids in ids_list)
+    edges = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ev0.record()
-    for ids in ids_list:
-        one_step(ids)
+    for _ in range(steps):
+        sub = next(batches)   # the collate of this batch is part of the timed step
+        edges += sub_edges(sub)
+        one_step(sub)
     ev1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0

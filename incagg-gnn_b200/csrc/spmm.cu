@@ -276,7 +276,13 @@ __device__ __forceinline__ void finish_row(const SpmmParams& p, int op, int64_t 
   }
 }
 
-constexpr int SPMM_THREADS = 256;
+#ifndef SPMM_THREADS_N
+#define SPMM_THREADS_N 256
+#endif
+constexpr int SPMM_THREADS = SPMM_THREADS_N;
+#ifndef SPMM_MIN_CTAS
+#define SPMM_MIN_CTAS (1536 / SPMM_THREADS_N)
+#endif
 
 // Feature tile -> (reducer, first feature, feature limit).  For the multi-aggregator launch
 // blockIdx.y enumerates (slab, tile-in-slab) and a tile never crosses its slab.
@@ -303,7 +309,7 @@ __device__ __forceinline__ void tile_info(const SpmmParams& p, int y, int& op, i
 //     depend on scheduling.  Low block indices are scheduled first, so the heavy rows start early.
 //   remaining CTAs: one G-lane group per short row.
 template <int REDUCE, int VEC, int G, int NCH, bool DELTA, bool ARG>
-__global__ void __launch_bounds__(SPMM_THREADS)
+__global__ void __launch_bounds__(SPMM_THREADS, (NCH == 1 && !ARG) ? SPMM_MIN_CTAS : 1)
 spmm_kernel(const SpmmParams p) {
   constexpr int COVER = G * VEC * NCH;
   const int lane = threadIdx.x & 31;
@@ -443,6 +449,13 @@ spmm_kernel(const SpmmParams p) {
 __global__ void spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t rows, SpmmPlan* plan,
                                  int4* __restrict__ items, int long_row, int chunk, int capacity) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (chunk <= 0) {
+    // adaptive chunk: small enough that one CTA trip is a few microseconds on batch-sized
+    // structures, large enough that the split rows of a whole graph fit the scratch area
+    const int64_t nnz = (int64_t)rowptr[rows] - rowptr[0];
+    chunk = 256;
+    while (chunk < 4096 && (int64_t)chunk * (PLAN_SCRATCH_CAP / 2) < nnz) chunk <<= 1;
+  }
   if (row == 0) {
     plan->long_row = long_row;
     plan->chunk = chunk;
@@ -484,9 +497,10 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 // Degree buckets: rows up to LONG_ROW edges -> one lane group; up to CHUNK edges -> one CTA; longer
-// rows -> ceil(deg / CHUNK) CTAs.  (Tunable for experiments through the environment.)
+// rows -> ceil(deg / CHUNK) CTAs, CHUNK = 256 .. 4096 by structure size.  (Tunable for experiments
+// through the environment.)
 static int long_row_edges() { static int v = env_int("INCAGG_SPMM_LONG_ROW", 64); return v; }
-static int chunk_edges() { static int v = env_int("INCAGG_SPMM_CHUNK", 2048); return v; }
+static int chunk_edges() { static int v = env_int("INCAGG_SPMM_CHUNK", 0); return v; }  // 0 = adaptive
 
 // Upper bound of the work items of a structure: one per row longer than LONG_ROW plus the extra
 // chunks of split rows.  nnz < 0 = unknown.
@@ -568,8 +582,8 @@ static int launch_cfg(SpmmParams& p, int n_tiles, int64_t items_bound, cudaStrea
   p.part_done = sc->part_done;
   p.part_slots = PART_SLOTS;
   p.n_tiles = n_tiles;
-  // CTAs that walk the plan's items: never more than the items can be, at most 4 per SM
-  int64_t lg = 4 * (int64_t)sm_count();
+  // CTAs that walk the plan's items: never more than the items can be, at most 8 per SM
+  int64_t lg = (int64_t)env_int("INCAGG_SPMM_LONG_CTAS", 8) * sm_count();
   if (items_bound < lg) lg = items_bound;
   if (lg < 1) lg = 1;
   p.long_grid = (int)lg;

@@ -44,7 +44,8 @@ class SubgraphLoader:
 
     def __init__(self, data: Data, ptr: Tensor, batch_size: int = 1, bipartite: bool = True,
                  log: bool = True, num_neighbors=-1, type='eval', IB=False, shuffle: bool = False,
-                 num_workers: int = 0, persistent_workers: bool = False, device=None, **kwargs):
+                 num_workers: int = 0, persistent_workers: bool = False, device=None,
+                 prefetch: bool = True, **kwargs):
         self.data = data
         self.ptr = ptr.cpu()
         self.bipartite = bipartite
@@ -54,6 +55,8 @@ class SubgraphLoader:
             raise NotImplementedError('neighbour sampling is out of scope (the reference call site is '
                                       'broken, loader.py:235; num_neighbors=-1 is the identity)')
         self.shuffle = shuffle
+        self.prefetch = prefetch
+        self._collate_stream = None
         self.batch_size = batch_size
         self.shuffled_batch_id = []
         self.device = torch.device(device) if device is not None else data.adj_t.device
@@ -149,15 +152,60 @@ class SubgraphLoader:
     def __len__(self):
         return len(self._batch_sampler)
 
+    # -- prefetching iterator ------------------------------------------------------------------
+    # The collate of batch i+1 is issued on a side stream while batch i trains on the caller's
+    # stream (the role the reference gives to DataLoader worker processes, main.py:158-160).  The one
+    # host synchronisation of a collate (reading the halo count) then waits for the side stream only,
+    # so the host keeps running ahead of the training kernels.
+    def _collate_async(self, batch_ids):
+        if self._collate_stream is None:
+            self._collate_stream = torch.cuda.Stream(self.device)
+        st = self._collate_stream
+        with torch.cuda.stream(st):
+            sub = self._collate(batch_ids)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        return sub, ev
+
+    def _hand_over(self, sub: SubData, ev) -> SubData:
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        # tensors were allocated on the side stream: tell the caching allocator about their consumer
+        for _, v in sub.data:
+            if isinstance(v, Tensor) and v.is_cuda:
+                v.record_stream(cur)
+            elif isinstance(v, SparseTensor):
+                for t in (v.rowptr, v.col, v.value):
+                    if t is not None and t.is_cuda:
+                        t.record_stream(cur)
+        if sub.n_id.is_cuda:
+            sub.n_id.record_stream(cur)
+        return sub
+
     def __iter__(self):
         self.shuffled_batch_id = []
+        if self._cached is not None:
+            for batch_ids in self._batch_sampler:
+                if self.shuffle:
+                    self.shuffled_batch_id.append(batch_ids)
+                yield self._cached[batch_ids[0]]
+            return
+        if not self.prefetch:
+            for batch_ids in self._batch_sampler:
+                if self.shuffle:
+                    self.shuffled_batch_id.append(batch_ids)
+                yield self._collate(batch_ids)
+            return
+        pending = None
         for batch_ids in self._batch_sampler:
             if self.shuffle:
                 self.shuffled_batch_id.append(batch_ids)
-            if self._cached is not None:
-                yield self._cached[batch_ids[0]]
-            else:
-                yield self._collate(batch_ids)
+            nxt = self._collate_async(batch_ids)
+            if pending is not None:
+                yield self._hand_over(*pending)
+            pending = nxt
+        if pending is not None:
+            yield self._hand_over(*pending)
 
     def __repr__(self):
         return f'{self.__class__.__name__}()'

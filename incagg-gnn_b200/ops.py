@@ -20,8 +20,14 @@ from ._lib import lib, check, ptr, REDUCE
 LAUNCHES = {"calls": 0}
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream
+_cur_dev = torch._C._cuda_getDevice
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # raw handle of the current stream of the current device (the Python Stream object of
+    # torch.cuda.current_stream() costs ~15 us per call, which matters at ~60 launches per step)
+    return _raw_stream(_cur_dev())
 
 
 def _require_cuda(*ts):

@@ -82,7 +82,8 @@ def main():
         agg.setdefault("relabel_one_hop", []).append((by, t_c, t_w))
         x = torch.randn(B + H, F, device=dev)
         out = torch.empty(B, F, device=dev)
-        fn = lambda: ops.spmm_raw(rp, col, val, x, "sum", out=out)
+        plan = ops.spmm_plan(rp, B, nnz_b)
+        fn = lambda: ops.spmm_raw(rp, col, val, x, "sum", out=out, plan=plan)
         by = nnz_b * 8 + (B + 1) * 4 + (B + H) * F * 4 + B * F * 4
         agg.setdefault("spmm_sum_fwd", []).append((by, timeit(fn, flush), timeit(fn, flush, cold=False)))
         fn = lambda: ops.csr_transpose(rp, col, val, B, B + H)
@@ -90,7 +91,8 @@ def main():
         agg.setdefault("csr_transpose", []).append((nnz_b * 16 + (2 * B + H) * 4, timeit(fn, flush), timeit(fn, flush, cold=False)))
         g = torch.randn(B, F, device=dev)
         gx = torch.empty(B + H, F, device=dev)
-        fn = lambda: ops.spmm_raw(t_rp, t_col, t_val, g, "sum", out=gx)
+        t_plan = ops.spmm_plan(t_rp, B + H, nnz_b)
+        fn = lambda: ops.spmm_raw(t_rp, t_col, t_val, g, "sum", out=gx, plan=t_plan)
         by = nnz_b * 8 + (B + H + 1) * 4 + B * F * 4 + (B + H) * F * 4
         agg.setdefault("spmm_sum_bwd", []).append((by, timeit(fn, flush), timeit(fn, flush, cold=False)))
         table = torch.randn(n, F, device=dev)
@@ -106,7 +108,8 @@ def main():
         rpb, colb, valb, _ = ops.relabel_one_hop_within_batch(rowptr64, adj.col, adj.value, idx, True, ws=ws, out_int32=True, nnz_b=nnz_b)
         m_in, m_ag = torch.randn(n, F, device=dev), torch.randn(n, F, device=dev)
         o0 = int(off[0])
-        fn = lambda: ops.spmm_delta_raw(rpb, colb, valb, xs, m_in[o0:o0 + B], m_ag[o0:o0 + B], None, "sum", out=out)
+        planb = ops.spmm_plan(rpb, B, colb.numel())
+        fn = lambda: ops.spmm_delta_raw(rpb, colb, valb, xs, m_in[o0:o0 + B], m_ag[o0:o0 + B], None, "sum", out=out, plan=planb)
         by = colb.numel() * 8 + (B + 1) * 4 + 4 * B * F * 4
         agg.setdefault("incagg_delta", []).append((by, timeit(fn, flush), timeit(fn, flush, cold=False)))
         feat = data.x
@@ -119,7 +122,8 @@ def main():
     if args.full:
         x = torch.randn(n, F, device=dev)
         out = torch.empty(n, F, device=dev)
-        fn = lambda: ops.spmm_raw(adj.rowptr, adj.col, adj.value, x, "sum", out=out)
+        fplan = ops.spmm_plan(adj.rowptr, n, adj.nnz())
+        fn = lambda: ops.spmm_raw(adj.rowptr, adj.col, adj.value, x, "sum", out=out, plan=fplan)
         by = adj.nnz() * 8 + (n + 1) * 4 + 2 * n * F * 4
         emit("spmm_sum_full_graph", by, timeit(fn, flush, reps=3), timeit(fn, flush, reps=3, cold=False), nnz=adj.nnz())
 
