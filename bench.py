@@ -11,11 +11,11 @@ mini-batch: GPU collate (relabel_one_hop + feature gather) -> forward (SpMM + hi
 layer) -> loss -> backward (transposed SpMM) -> Adam.  edges/s = sum over the timed steps of
 nnz(batch adjacency) / time; over a whole epoch the batch adjacencies partition nnz(adj_t).
 
-N > 1 (launched by torch.distributed.run, one rank per GPU): partitions are sharded over ranks (rank
-r owns a contiguous block of partitions, their CSR rows, feature rows and history rows); each rank
-trains on its own batches (weak scaling: per-GPU work fixed = the full C3 graph per rank would not be
-"the products shape", so every rank holds its 1/N... see DESIGN.md §multi-GPU) and gradients are
-all-reduced with NCCL.
+N > 1 (launched by torch.distributed.run, one rank per GPU): the partitions of the one graph are
+sharded over the ranks (rank r owns a contiguous block of partitions and those rows of every history
+table); each rank trains on batches of its own partitions, halo rows owned by other ranks are fetched
+by an all-to-all-v over NCCL (GAS mode) and gradients are all-reduced every step.  A
+step at N GPUs is N batches in flight, so per-GPU work per step is fixed ("weak").
 
 One JSON line on stdout (rank 0).  Nothing here reads /root/reference.
 """
@@ -156,7 +156,10 @@ def timed_steps(run, mode, warmup, steps, dist, e2e=False):
     def sub_edges(sub):
         return sum(int(rp_host[o + c]) - int(rp_host[o]) for o, c in zip(sub.offset.tolist(), sub.count.tolist()))
 
-    params = [p for p in model.parameters() if p.requires_grad]
+    averager = None
+    if dist is not None:
+        from incagg_gnn_b200.parallel import GradAverager
+        averager = GradAverager(model.parameters(), run["shard"])
     h2d = d2h = 0
 
     def one_step(sub):
@@ -172,13 +175,8 @@ def timed_steps(run, mode, warmup, steps, dist, e2e=False):
         w = m.to(out.dtype)
         loss = (torch.nn.functional.cross_entropy(out, y, reduction="none") * w).sum() / w.sum().clamp(min=1.)
         loss.backward()
-        if dist is not None:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            flat /= dist.get_world_size()
-            o = 0
-            for p in params:
-                p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad)); o += p.numel()
+        if averager is not None:
+            averager()  # NCCL all-reduce of the flat gradient buffer
         if conf["grad_norm"] is not None:
             torch.nn.utils.clip_grad_norm_(model.parameters(), conf["grad_norm"])
         opt.step()
@@ -288,9 +286,11 @@ def main():
     from incagg_gnn_b200.train import build, mini_test
 
     vr = args.mode == "incagg"
-    # weak scaling: every rank holds and trains its own products-shaped shard (seed differs per rank)
-    run = build(args.config, device=dev, seed=args.seed + rank, scale=args.scale,
-                overrides=dict(VR_update=vr), shuffle=True)
+    # one products-shaped graph (same seed on every rank); partitions, history rows and batches are
+    # sharded over the ranks.  A step at N GPUs = N batches in flight (one per rank) + gradient
+    # all-reduce, so per-GPU work per step is fixed ("weak") and `value` is the whole-job edges/s.
+    run = build(args.config, device=dev, seed=args.seed, scale=args.scale,
+                overrides=dict(VR_update=vr), shuffle=True, rank=rank, world_size=world)
     model = run["model"]
     mini_test(model, run["eval_loader"], VR_update=vr)  # fill the histories (main.py:211-215), untimed
     torch.cuda.synchronize()
@@ -313,9 +313,9 @@ def main():
     value = edges / sec
 
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and world == 1:  # the pinned-host layout is the reference's single-GPU layout
         data_pack = (run["data"], run["ptr"], run["in_channels"], run["out_channels"])
-        run_h = build(args.config, device=dev, seed=args.seed + rank, scale=args.scale,
+        run_h = build(args.config, device=dev, seed=args.seed, scale=args.scale,
                       overrides=dict(VR_update=vr), shuffle=True, host_resident=True,
                       history_device=None, data=data_pack)
         run_h["model"].load_state_dict(model.state_dict(), strict=False)

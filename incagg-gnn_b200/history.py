@@ -28,6 +28,8 @@ class History(torch.nn.Module):
             pin_memory = False  # host-logic tests without a GPU; pull/push will refuse to run
         self.emb = torch.empty(num_embeddings, embedding_dim, device=device, pin_memory=pin_memory)
         self._device = torch.device('cpu')
+        # first global row held by this table (> 0 for a rank's shard of a partitioned table)
+        self.row_offset = 0
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -51,6 +53,8 @@ class History(torch.nn.Module):
             return self.emb.to(device=self._device)
         dev = self._compute_device()
         idx = n_id.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        if self.row_offset:
+            idx = idx - self.row_offset
         with torch.cuda.device(dev):
             out = ops.gather_rows(self.emb, idx)
         return out.to(device=self._device)
@@ -65,10 +69,14 @@ class History(torch.nn.Module):
         elif offset is None or count is None:
             dev = self._compute_device()
             idx = n_id.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+            if self.row_offset:
+                idx = idx - self.row_offset
             with torch.cuda.device(dev):
                 ops.scatter_rows(x.to(dev).contiguous(), idx, self.emb)
         else:  # push in chunks (history.py:60-65); n_id is ignored here as in the reference
             dev = self._compute_device()
+            if self.row_offset:
+                offset = offset - self.row_offset
             with torch.cuda.device(dev):
                 ops.copy_slices(x.to(dev).contiguous(), self.emb, offset, count, 1)
 

@@ -45,7 +45,7 @@ class SubgraphLoader:
     def __init__(self, data: Data, ptr: Tensor, batch_size: int = 1, bipartite: bool = True,
                  log: bool = True, num_neighbors=-1, type='eval', IB=False, shuffle: bool = False,
                  num_workers: int = 0, persistent_workers: bool = False, device=None,
-                 prefetch: bool = True, **kwargs):
+                 prefetch: bool = True, shard=None, **kwargs):
         self.data = data
         self.ptr = ptr.cpu()
         self.bipartite = bipartite
@@ -65,6 +65,15 @@ class SubgraphLoader:
                                'pinned host memory) or a CUDA data.adj_t; there is no CPU collate')
 
         self.num_parts = self.ptr.numel() - 1
+        # multi-GPU: this rank iterates over the partitions it owns only (parallel.Shard); every rank
+        # yields the same number of batches per epoch (wrapping around) so collectives stay matched
+        self.shard = shard
+        if shard is not None:
+            self._parts = [p for p in range(self.num_parts) if shard.lo <= int(self.ptr[p]) < shard.hi]
+            assert all(int(self.ptr[p + 1]) <= shard.hi for p in self._parts), \
+                'partition blocks of the loader must nest in the rank shards'
+        else:
+            self._parts = list(range(self.num_parts))
         # global CSR for relabel: int64 rowptr, int32 col, fp32 values (device resident)
         # (device resident, or pinned host memory that the relabel kernels read through UVA)
         adj = data.adj_t
@@ -79,8 +88,15 @@ class SubgraphLoader:
                 self._val = self._val.pin_memory()
         self._ws = ops.RelabelWorkspace(adj.size(0), self.device)
 
-        sampler = RandomSampler(range(self.num_parts)) if shuffle else SequentialSampler(range(self.num_parts))
+        n_local = len(self._parts)
+        sampler = RandomSampler(range(n_local)) if shuffle else SequentialSampler(range(n_local))
         self._batch_sampler = BatchSampler(sampler, batch_size, drop_last=False)
+        self._steps = len(self._batch_sampler)
+        if shard is not None and shard.world_size > 1:
+            import torch.distributed as dist
+            t = torch.tensor([self._steps], device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=shard.group)
+            self._steps = int(t)
 
         if type == 'train':
             self._collate = self.compute_subgraph_IB if IB else self.compute_subgraph
@@ -92,7 +108,10 @@ class SubgraphLoader:
                 if log:
                     t = time.perf_counter()
                     print('Pre-processing subgraphs...', end=' ', flush=True)
-                self._cached = [self.compute_subgraph([b]) for b in range(self.num_parts)]
+                # one entry per step; every rank runs the same number of steps (halo plans are
+                # exchanged pairwise per step), a rank with fewer partitions wraps around
+                self._cached = [self.compute_subgraph([self._parts[j % len(self._parts)]])
+                                for j in range(self._steps)]
                 if log:
                     torch.cuda.synchronize(self.device)
                     print(f'Done! [{time.perf_counter() - t:.2f}s]')
@@ -113,6 +132,9 @@ class SubgraphLoader:
     def _finish(self, rowptr, col, value, n_id, batch_size, offset, count) -> SubData:
         adj_t = SparseTensor(rowptr=rowptr, col=col, value=value,
                              sparse_sizes=(rowptr.numel() - 1, n_id.numel()), is_sorted=True)
+        if self.shard is not None and self.shard.world_size > 1:
+            from .parallel import HaloPlan
+            n_id.halo_plan = HaloPlan(n_id[batch_size:], self.shard)
         data = self.data.__class__(adj_t=adj_t)
         for k, v in self.data:
             if isinstance(v, Tensor) and v.size(0) == self.data.num_nodes:
@@ -150,7 +172,17 @@ class SubgraphLoader:
     compute_subgraph_NS = compute_subgraph
 
     def __len__(self):
-        return len(self._batch_sampler)
+        return self._steps
+
+    def _batches_of_epoch(self):
+        """Lists of partition ids, one per step; a rank with fewer batches than the slowest rank
+        wraps around."""
+        groups = [[self._parts[i] for i in ids] for ids in self._batch_sampler]
+        j = 0
+        while len(groups) < self._steps:
+            groups.append(groups[j])
+            j += 1
+        return groups
 
     # -- prefetching iterator ------------------------------------------------------------------
     # The collate of batch i+1 is issued on a side stream while batch i trains on the caller's
@@ -180,24 +212,27 @@ class SubgraphLoader:
                         t.record_stream(cur)
         if sub.n_id.is_cuda:
             sub.n_id.record_stream(cur)
+        plan = getattr(sub.n_id, 'halo_plan', None)
+        if plan is not None:
+            for t in plan.tensors():
+                if t.is_cuda:
+                    t.record_stream(cur)
         return sub
 
     def __iter__(self):
         self.shuffled_batch_id = []
-        if self._cached is not None:
-            for batch_ids in self._batch_sampler:
-                if self.shuffle:
-                    self.shuffled_batch_id.append(batch_ids)
-                yield self._cached[batch_ids[0]]
+        if self._cached is not None:  # pre-materialised (evaluation): fixed step order
+            for sub in self._cached:
+                yield sub
             return
         if not self.prefetch:
-            for batch_ids in self._batch_sampler:
+            for batch_ids in self._batches_of_epoch():
                 if self.shuffle:
                     self.shuffled_batch_id.append(batch_ids)
                 yield self._collate(batch_ids)
             return
         pending = None
-        for batch_ids in self._batch_sampler:
+        for batch_ids in self._batches_of_epoch():
             if self.shuffle:
                 self.shuffled_batch_id.append(batch_ids)
             nxt = self._collate_async(batch_ids)

@@ -75,6 +75,23 @@ class ScalableGNN(torch.nn.Module):
 
         self._async = False
         self.__out: Optional[Tensor] = None
+        self.shard = None      # parallel.Shard when the history tables are sharded over ranks
+        self._row_lo = 0       # first global row of this rank's shard
+
+    def shard_histories(self, shard) -> 'ScalableGNN':
+        """Keep only this rank's rows ``[shard.lo, shard.hi)`` of every history table (HBM-resident
+        shards; multi-GPU design of DESIGN.md §6).  Halo rows owned by other ranks are then fetched
+        through ``parallel.pull_halo_rows``."""
+        if self.pool is not None or self.histories[0].emb.device.type != 'cuda':
+            raise RuntimeError('sharded histories are HBM-resident (device="cuda"); the pinned-host '
+                               'AsyncIOPool layout is single-GPU')
+        self.shard, self._row_lo = shard, shard.lo
+        for h in list(self.histories) + list(self.histories_ag):
+            h.emb = torch.zeros(shard.num_local, h.embedding_dim, device=h.emb.device)
+            h.num_embeddings = shard.num_local
+            h.row_offset = shard.lo
+        self.__out = None
+        return self
 
     @property
     def emb_device(self):
@@ -176,9 +193,10 @@ class ScalableGNN(torch.nn.Module):
             raise RuntimeError('IncAgg step with host-resident histories needs the AsyncIOPool '
                                '(pool_size and buffer_size must be set)')
         if offset is not None and offset.numel() == 1:
-            o = int(offset[0])
+            o = int(offset[0]) - self._row_lo
             return hist[o:o + batch_size, :width], hist_ag[o:o + batch_size, :width], None
-        return hist, hist_ag, n_id[:batch_size]
+        gid = n_id[:batch_size]
+        return hist, hist_ag, (gid - self._row_lo if self._row_lo else gid)
 
     def _incagg_release(self):
         if self._async:
@@ -205,9 +223,14 @@ class ScalableGNN(torch.nn.Module):
         if not self._async:  # synchronous branch = the semantic definition (base.py:411-426)
             history.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
             idx = n_id[batch_size:]
+            plan = getattr(n_id, 'halo_plan', None)
 
             def fill(dst):
-                ops.gather_rows(history.emb, idx.to(dst.device), out=dst)
+                if plan is not None:  # sharded tables: all-to-all-v of halo rows
+                    from ..parallel import pull_halo_rows
+                    pull_halo_rows(history.emb, plan, dst)
+                else:
+                    ops.gather_rows(history.emb, idx.to(dst.device), out=dst)
             return _PushPull.apply(x, fill, batch_size, n_tail), 0.
         pulled = self.pool.synchronize_pull()
 
@@ -240,7 +263,9 @@ class ScalableGNN(torch.nn.Module):
     @property
     def _out(self):
         if self.__out is None:
-            if self.emb_device.type == 'cuda':
+            if self.shard is not None:  # logits of this rank's rows only
+                self.__out = torch.empty(self.shard.num_local, self.out_channels, device=self.emb_device)
+            elif self.emb_device.type == 'cuda':
                 self.__out = torch.empty(self.num_nodes, self.out_channels, device=self.emb_device)
             else:
                 self.__out = torch.empty(self.num_nodes, self.out_channels,
@@ -259,6 +284,8 @@ class ScalableGNN(torch.nn.Module):
         if pool is not None:
             pool.async_push(x, offset, count, table)
         else:
+            if self._row_lo:
+                offset = offset - self._row_lo
             ops.copy_slices(x.contiguous(), table, offset, count, 1)
 
     def _sweep_pull_all(self, loader, table: Tensor):
@@ -272,8 +299,12 @@ class ScalableGNN(torch.nn.Module):
         if self.pool is not None:
             return self.pool.synchronize_pull()[:n_id.numel()]
         out = torch.empty((n_id.numel(), table.size(1)), dtype=table.dtype, device=self.device)
-        ops.copy_slices(table, out, offset, count, 0)
-        if n_id.numel() > batch_size:
+        ops.copy_slices(table, out, offset - self._row_lo if self._row_lo else offset, count, 0)
+        plan = getattr(n_id, 'halo_plan', None)
+        if plan is not None:
+            from ..parallel import pull_halo_rows
+            pull_halo_rows(table, plan, out[batch_size:])
+        elif n_id.numel() > batch_size:
             ops.gather_rows(table, n_id[batch_size:].contiguous(), out=out[batch_size:])
         return out
 

@@ -1,0 +1,206 @@
+"""Multi-GPU sharding of the hot path: one process per GPU (``torch.distributed``, NCCL over NVLink /
+NVSwitch), METIS partitions sharded over ranks (the reference itself is single-GPU).
+
+* rank ``r`` owns a contiguous block of partitions = a contiguous node range ``[lo, hi)``, and with it
+  those rows of every history table (``histories[l]``, ``histories_ag[l]``) as an HBM-resident shard;
+* a rank trains only on batches of its own partitions, so every push is local;
+* halo rows owned by other ranks are fetched by an all-to-all-v: the row ids a batch needs from each
+  owner are exchanged once per batch (``HaloPlan``, known at collate time), then each layer's pull is
+  one exchange of ``[H_peer, D]`` fp32 rows — the owner gathers them out of its shard with the
+  indexed-row kernel, ``ncclSend/ncclRecv`` (``batch_isend_irecv``: one NCCL group = an all-to-all-v),
+  and the requester scatters them into the tail of its layer input;
+* gradients are averaged with one ``all_reduce`` per step over a flat buffer.
+
+The IncAgg training step needs no halo traffic (``A_BB`` and the rank's own ``M_in``/``M_ag`` slices);
+only the per-epoch refresh sweep exchanges halos.
+
+The row gather / scatter used on each side are injectable so that the protocol itself is testable
+with the ``gloo`` backend on CPU tensors (tests/test_parallel.py); the product path uses the CUDA
+kernels and refuses CPU tensors.
+"""
+from typing import Callable, List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+class Shard:
+    """Ownership map: partitions -> ranks -> node ranges."""
+
+    def __init__(self, ptr: Tensor, rank: int, world_size: int, group=None):
+        self.rank, self.world_size, self.group = int(rank), int(world_size), group
+        ptr = ptr.cpu().to(torch.int64)
+        P = ptr.numel() - 1
+        if world_size > P:
+            raise ValueError(f'{world_size} ranks for {P} partitions')
+        # contiguous blocks of partitions, sizes differing by at most one
+        self.part_bounds = [(r * P) // world_size for r in range(world_size + 1)]
+        self.node_bounds = ptr[torch.tensor(self.part_bounds)].contiguous()  # [W+1] on the host
+        self.part_lo, self.part_hi = self.part_bounds[rank], self.part_bounds[rank + 1]
+        self.lo, self.hi = int(self.node_bounds[rank]), int(self.node_bounds[rank + 1])
+        self.num_local = self.hi - self.lo
+        self._bounds_dev = {}
+
+    @property
+    def parts(self) -> range:
+        return range(self.part_lo, self.part_hi)
+
+    def bounds_on(self, device) -> Tensor:
+        key = str(device)
+        if key not in self._bounds_dev:
+            self._bounds_dev[key] = self.node_bounds.to(device)
+        return self._bounds_dev[key]
+
+    def owner_of(self, ids: Tensor) -> Tensor:
+        """Rank that owns each global node id."""
+        b = self.bounds_on(ids.device)
+        return torch.bucketize(ids, b[1:], right=True)
+
+    def steps_per_epoch(self, batch_size: int) -> int:
+        """Steps every rank runs per epoch (ranks with fewer batches wrap around): collectives must
+        be entered the same number of times on all ranks."""
+        most = max(self.part_bounds[r + 1] - self.part_bounds[r] for r in range(self.world_size))
+        return -(-most // batch_size)
+
+
+class HaloPlan:
+    """Who serves which halo rows of one batch.  Built once per batch (one small id exchange),
+    reused by every layer's pull."""
+
+    def __init__(self, halo_ids: Tensor, shard: Shard):
+        self.shard = shard
+        W, dev = shard.world_size, halo_ids.device
+        self.n_halo = halo_ids.numel()
+        owner = shard.owner_of(halo_ids)
+        order = torch.argsort(owner, stable=True)              # halo positions grouped by owner
+        self.order = order
+        counts = torch.bincount(owner, minlength=W)
+        self.req_counts = counts.tolist()                      # rows I request from each rank
+        ids_sorted = halo_ids[order].contiguous()
+        # counts of the requests the others make to me
+        if W > 1:
+            theirs = _exchange_counts(counts, shard)
+        else:
+            theirs = counts.clone()
+        self.serve_counts = theirs.tolist()
+        # ids the others request from me (global ids; I own all of them)
+        req_splits = list(torch.split(ids_sorted, self.req_counts))
+        self.local_ids = req_splits[shard.rank]                # my own halo rows: no exchange
+        self.local_pos = torch.split(order, self.req_counts)[shard.rank]
+        self.serve_ids: List[Tensor] = [torch.empty(0, dtype=torch.int64, device=dev) for _ in range(W)]
+        ops_list, keep = [], []
+        for r in range(W):
+            if r == shard.rank:
+                continue
+            if self.serve_counts[r] > 0:
+                buf = torch.empty(self.serve_counts[r], dtype=torch.int64, device=dev)
+                self.serve_ids[r] = buf
+                ops_list.append(dist.P2POp(dist.irecv, buf, _global_rank(r, shard), group=shard.group))
+            if self.req_counts[r] > 0:
+                keep.append(req_splits[r].contiguous())
+                ops_list.append(dist.P2POp(dist.isend, keep[-1], _global_rank(r, shard), group=shard.group))
+        if ops_list:
+            for w in dist.batch_isend_irecv(ops_list):
+                w.wait()
+        self.recv_pos = torch.split(order, self.req_counts)    # where each rank's rows go in the halo block
+
+    def tensors(self):
+        """Device tensors of the plan (for allocator stream bookkeeping when it was built on a side
+        stream)."""
+        return [self.order, self.local_ids] + [t for t in self.serve_ids]
+
+
+def _global_rank(r: int, shard: Shard) -> int:
+    return r if shard.group is None else dist.get_global_rank(shard.group, r)
+
+
+def _exchange_counts(counts: Tensor, shard: Shard) -> Tensor:
+    """all-to-all of one int64 per peer (all_gather of the count vectors: W*W integers)."""
+    W = shard.world_size
+    gathered = [torch.empty_like(counts) for _ in range(W)]
+    dist.all_gather(gathered, counts.contiguous(), group=shard.group)
+    return torch.stack([g[shard.rank] for g in gathered])
+
+
+def _default_gather(table: Tensor, idx: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    from . import ops
+    return ops.gather_rows(table, idx, out=out)
+
+
+def _default_scatter(src: Tensor, idx: Tensor, dst: Tensor) -> None:
+    from . import ops
+    ops.scatter_rows(src, idx, dst)
+
+
+def pull_halo_rows(table_local: Tensor, plan: HaloPlan, out: Tensor, width: Optional[int] = None,
+                   gather: Callable = _default_gather, scatter: Callable = _default_scatter) -> Tensor:
+    """out[j] = table[halo_ids[j]] for the halo block of one batch, where `table_local` holds only the
+    rows ``[shard.lo, shard.hi)`` of the global table.  One all-to-all-v of rows."""
+    shard = plan.shard
+    W, lo = shard.world_size, shard.lo
+    D = table_local.size(1)
+    # 1. the rows I own myself
+    if plan.local_ids.numel() > 0:
+        mine = gather(table_local, plan.local_ids - lo)
+        scatter(mine, plan.local_pos, out)
+    if W == 1:
+        return out
+    # 2. serve the others, receive mine
+    ops_list, keep, recv = [], [], {}
+    for r in range(W):
+        if r == shard.rank:
+            continue
+        if plan.req_counts[r] > 0:
+            recv[r] = torch.empty((plan.req_counts[r], D), dtype=table_local.dtype, device=out.device)
+            ops_list.append(dist.P2POp(dist.irecv, recv[r], _global_rank(r, shard), group=shard.group))
+        if plan.serve_counts[r] > 0:
+            keep.append(gather(table_local, plan.serve_ids[r] - lo))
+            ops_list.append(dist.P2POp(dist.isend, keep[-1], _global_rank(r, shard), group=shard.group))
+    if ops_list:
+        for w in dist.batch_isend_irecv(ops_list):
+            w.wait()
+    for r, buf in recv.items():
+        scatter(buf, plan.recv_pos[r], out)
+    return out
+
+
+def idle_exchange(shard: Shard) -> None:
+    """Take part in one halo exchange without needing rows (a rank that has run out of batches while
+    others still pull).  Serves whatever the others request from an empty request of its own."""
+    raise NotImplementedError('ranks run the same number of steps (Shard.steps_per_epoch)')
+
+
+class GradAverager:
+    """One all_reduce per step over a flat view of the gradients."""
+
+    def __init__(self, params, shard: Shard):
+        self.params = [p for p in params if p.requires_grad]
+        self.shard = shard
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = None
+
+    def __call__(self):
+        if self.shard.world_size == 1:
+            return
+        if self.flat is None:
+            p0 = self.params[0]
+            self.flat = torch.empty(self.numel, dtype=p0.dtype, device=p0.device)
+        o = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                self.flat[o:o + n].zero_()
+            else:
+                self.flat[o:o + n].copy_(p.grad.reshape(-1))
+            o += n
+        dist.all_reduce(self.flat, group=self.shard.group)
+        self.flat.div_(self.shard.world_size)
+        o = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                p.grad = self.flat[o:o + n].view_as(p).clone()
+            else:
+                p.grad.copy_(self.flat[o:o + n].view_as(p))
+            o += n

@@ -109,7 +109,8 @@ def mini_test(model, loader, use_aggregation=True, VR_update=False):
 
 def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_device='cuda',
           overrides: Optional[Dict[str, Any]] = None, log: bool = False, data_device=None,
-          shuffle: bool = True, host_resident: bool = False, data=None):
+          shuffle: bool = True, host_resident: bool = False, data=None, rank: int = 0,
+          world_size: int = 1):
     """Everything main.py:140-201 sets up for one named config on synthetic data: returns a dict
     with data, ptr, loaders, model, optimizer, criterion and the config."""
     conf = dict(CONFIGS[config])
@@ -136,10 +137,15 @@ def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_dev
     if host_resident:  # the reference's layout: graph + features in pinned host memory
         data = data.pin_memory()
     criterion = torch.nn.CrossEntropyLoss()
+    shard = None
+    if world_size > 1:  # partitions, CSR rows and history rows are sharded over the ranks
+        from .parallel import Shard
+        shard = Shard(ptr, rank, world_size)
     train_loader = SubgraphLoader(data, ptr, batch_size=conf['batch_size'], shuffle=shuffle,
                                   num_neighbors=-1, type='train', IB=conf['VR_update'], log=log,
-                                  device=device)
-    eval_loader = EvalSubgraphLoader(data, ptr, batch_size=conf['batch_size'], log=log, device=device)
+                                  device=device, shard=shard)
+    eval_loader = EvalSubgraphLoader(data, ptr, batch_size=conf['batch_size'], log=log, device=device,
+                                     shard=shard)
     buffer_size = max(n_id.numel() for _, _, n_id, _, _ in eval_loader) * 2
     kwargs = {}
     if conf['model'][:3] == 'PNA':
@@ -148,11 +154,13 @@ def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_dev
     model = GNN(num_nodes=data.num_nodes, in_channels=in_channels, out_channels=out_channels,
                 pool_size=conf['pool_size'], buffer_size=buffer_size, device=history_device,
                 **conf['architecture'], **kwargs).to(device)
+    if shard is not None:
+        model.shard_histories(shard)
     optimizer = torch.optim.Adam([
         dict(params=model.reg_modules.parameters(), weight_decay=conf['reg_weight_decay']),
         dict(params=model.nonreg_modules.parameters(), weight_decay=conf['nonreg_weight_decay']),
     ], lr=conf['lr'])
     max_steps = conf['max_steps'] if conf['max_steps'] != -1 else int(conf['num_parts'] / conf['batch_size'])
-    return dict(conf=conf, data=data, raw=raw, ptr=ptr, train_loader=train_loader, eval_loader=eval_loader,
+    return dict(conf=conf, data=data, raw=raw, ptr=ptr, shard=shard, train_loader=train_loader, eval_loader=eval_loader,
                 model=model, optimizer=optimizer, criterion=criterion, max_steps=max_steps,
                 in_channels=in_channels, out_channels=out_channels, buffer_size=buffer_size)
