@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--scale", type=int, default=1, help="divide nodes and edges (debug only)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="issue every step eagerly from Python")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=6)
     return ap.parse_args()
@@ -135,6 +136,53 @@ def batch_edges(run, batch_ids):
     rp = run["train_loader"]._rowptr_host
     ptr = run["ptr"]
     return sum(int(rp[int(ptr[b + 1])]) - int(rp[int(ptr[b])]) for b in batch_ids)
+
+
+def timed_steps_graphed(run, mode, warmup, steps, dist):
+    """W warm-up + K timed training steps, each step one replay of the CUDA graph of its batch
+    (train.GraphedTrainer; graphs are captured before the timed region, one per partition)."""
+    from incagg_gnn_b200.train import GraphedTrainer
+    model, opt, loader, conf = run["model"], run["optimizer"], run["train_loader"], run["conf"]
+    averager = None
+    if dist is not None:
+        from incagg_gnn_b200.parallel import GradAverager
+        averager = GradAverager(model.parameters(), run["shard"])
+    tr = GraphedTrainer(model, loader, opt, VR_update=(mode == "incagg"), grad_norm=conf["grad_norm"],
+                        averager=averager)
+    rp_host, ptr = loader._rowptr_host, loader.ptr
+    groups = loader._batches_of_epoch()
+    tr.warmup(groups[0])
+    t0 = time.perf_counter()
+    for ids in groups:
+        tr.capture(ids)
+    torch.cuda.synchronize()
+    t_capture = time.perf_counter() - t0
+
+    def stream_of_ids():
+        while True:
+            for ids in loader._batches_of_epoch():
+                yield ids
+
+    it = stream_of_ids()
+    for _ in range(warmup):
+        tr.step(next(it))
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    seq = [next(it) for _ in range(steps)]
+    edges = sum(int(rp_host[int(ptr[b + 1])]) - int(rp_host[int(ptr[b])]) for ids in seq for b in ids)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ev0.record()
+    for ids in seq:
+        tr.step(ids)
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if dist is not None:
+        dist.barrier()
+    return ev0.elapsed_time(ev1) / 1e3, edges, 0, 0, wall, len(tr.graphs), t_capture
 
 
 def timed_steps(run, mode, warmup, steps, dist, e2e=False):
@@ -305,9 +353,20 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = _lib.launch_count()
-    sec, edges, _, _, wall = timed_steps(run, args.mode, args.warmup, args.steps, dist)
-    launches = _lib.launch_count() - l0
+    graphs = None
+    if args.no_graphs:
+        l0 = _lib.launch_count()
+        sec, edges, _, _, wall = timed_steps(run, args.mode, args.warmup, args.steps, dist)
+        launches = _lib.launch_count() - l0
+    else:
+        # kernels of this library per step, counted on one eager step (a graph replay re-launches
+        # exactly the captured kernels, which the host-side counter cannot see)
+        l0 = _lib.launch_count()
+        timed_steps(run, args.mode, 0, 1, dist)
+        per_step = _lib.launch_count() - l0
+        sec, edges, _, _, wall, n_graphs, t_cap = timed_steps_graphed(run, args.mode, args.warmup, args.steps, dist)
+        launches = per_step * args.steps
+        graphs = {"captured": n_graphs, "capture_s": round(t_cap, 2)}
     clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks of the device time; edges summed over ranks
@@ -372,7 +431,11 @@ def main():
                    "mode": args.mode, "scale": args.scale,
                    "l2": "inputs larger than L2: every step reads a different partition (graph + features "
                          "+ 10 history tables = 14 GB per epoch)",
-                   "histories": "HBM-resident"},
+                   "histories": "HBM-resident",
+                   "step_issue": ("eager (Python launches)" if graphs is None else
+                                  f"CUDA graph per partition batch ({graphs['captured']} graphs captured before the "
+                                  f"timed region in {graphs['capture_s']} s; every replay re-runs collate, forward, "
+                                  f"history push/pull, backward and Adam)")},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
         "cpu_baseline": cpu, "edges_timed": edges, "wall_s": wall,
     }

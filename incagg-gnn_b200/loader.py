@@ -87,6 +87,7 @@ class SubgraphLoader:
             if self._val is not None and not self._val.is_pinned():
                 self._val = self._val.pin_memory()
         self._ws = ops.RelabelWorkspace(adj.size(0), self.device)
+        self._known_sizes = {}
 
         n_local = len(self._parts)
         sampler = RandomSampler(range(n_local)) if shuffle else SequentialSampler(range(n_local))
@@ -147,25 +148,36 @@ class SubgraphLoader:
         return SubData(data, batch_size, n_id, offset, count)
 
     # -- collates (same names as the reference) ---------------------------------------------
+    # The output sizes of a relabel are data dependent (halo count / kept edges) and are read back
+    # once per distinct batch; the loader remembers them, so a batch that comes round again (every
+    # epoch with batch_size = 1, every evaluation sweep) is collated without any host synchronisation.
     def compute_subgraph(self, batches) -> SubData:
         batch_ids = [b[0] if isinstance(b, tuple) else int(b) for b in batches]
         n_id, offset, count, nnz_b = self._batch_nodes(batch_ids)
         batch_size = n_id.numel()
+        key = ('gas',) + tuple(batch_ids)
         with torch.cuda.device(self.device):
             rowptr, col, value, n_id = ops.relabel_one_hop(
                 self._rowptr64, self._col, self._val, n_id, self.bipartite, ws=self._ws,
-                out_int32=True, nnz_b=nnz_b)
+                out_int32=True, nnz_b=nnz_b, known=self._known_sizes.get(key))
+            self._remember(key, self._ws.last_count)
             return self._finish(rowptr, col, value, n_id, batch_size, offset, count)
 
     def compute_subgraph_IB(self, batches) -> SubData:
         batch_ids = [b[0] if isinstance(b, tuple) else int(b) for b in batches]
         n_id, offset, count, nnz_b = self._batch_nodes(batch_ids)
         batch_size = n_id.numel()
+        key = ('ib',) + tuple(batch_ids)
         with torch.cuda.device(self.device):
             rowptr, col, value, n_id = ops.relabel_one_hop_within_batch(
                 self._rowptr64, self._col, self._val, n_id, self.bipartite, ws=self._ws,
-                out_int32=True, nnz_b=nnz_b)
+                out_int32=True, nnz_b=nnz_b, known=self._known_sizes.get(key))
+            self._remember(key, self._ws.last_count)
             return self._finish(rowptr, col, value, n_id, batch_size, offset, count)
+
+    def _remember(self, key, size):
+        if len(self._known_sizes) < 65536:
+            self._known_sizes[key] = size
 
     # the reference's train collate without IncAgg is compute_subgraph_NS, which equals
     # compute_subgraph for num_neighbors=-1

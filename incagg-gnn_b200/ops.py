@@ -246,6 +246,7 @@ class RelabelWorkspace:
         self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
         self.counts = torch.zeros(2, dtype=torch.int64, device=self.device)
         self.counts_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self.last_count = None  # data-dependent output size of the last relabel call
         with torch.cuda.device(self.device):
             check(lib.incagg_relabel_workspace_init(ptr(self.buf), self.num_nodes, _stream()))
 
@@ -263,7 +264,10 @@ def _workspace_for(num_nodes: int, device) -> RelabelWorkspace:
 
 def _relabel(within: bool, rowptr: Tensor, col: Tensor, value: Optional[Tensor], idx: Tensor,
              bipartite: bool, ws: Optional[RelabelWorkspace], out_int32: bool,
-             nnz_b: Optional[int]):
+             nnz_b: Optional[int], known: Optional[int] = None):
+    """`known`: the data-dependent output size of this very batch from an earlier call (number of
+    halo ids for relabel_one_hop, number of kept edges for the within-batch variant).  With it the call
+    needs no device->host readback, i.e. no synchronisation (and can be captured in a CUDA graph)."""
     # the global CSR may live in HBM or in pinned host memory (read through UVA); idx on the device
     _require_cuda(idx)
     for t in (rowptr, col, value):
@@ -301,9 +305,13 @@ def _relabel(within: bool, rowptr: Tensor, col: Tensor, value: Optional[Tensor],
         check(lib.incagg_relabel_one_hop_within_batch(
             ptr(rowptr), ptr(col), cw, ptr(value), ptr(idx), B, N, nnz_b, ptr(out_rowptr),
             ptr(out_col), ow, ptr(out_val), ptr(ws.counts), ptr(ws.buf), st))
-        ws.counts_host.copy_(ws.counts, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        nnz_out = int(ws.counts_host[1])
+        if known is None:
+            ws.counts_host.copy_(ws.counts, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            nnz_out = int(ws.counts_host[1])
+        else:
+            nnz_out = int(known)
+        ws.last_count = nnz_out
         out_col = out_col[:nnz_out]
         if out_val is not None:
             out_val = out_val[:nnz_out]
@@ -313,13 +321,18 @@ def _relabel(within: bool, rowptr: Tensor, col: Tensor, value: Optional[Tensor],
             pad = int(torch.unique(idx).numel())
             out_rowptr = torch.cat([out_rowptr, out_rowptr.new_full((pad,), nnz_out)])
         return out_rowptr, out_col, out_val, n_id
-    n_id_buf = torch.empty(B + min(nnz_b, N), dtype=torch.int64, device=dev)
+    n_id_buf = torch.empty(B + (min(nnz_b, N) if known is None else int(known)), dtype=torch.int64,
+                           device=dev)
     check(lib.incagg_relabel_one_hop(
         ptr(rowptr), ptr(col), cw, ptr(value), ptr(idx), B, N, nnz_b, ptr(out_rowptr), ptr(out_col),
         ow, ptr(out_val), ptr(n_id_buf), ptr(ws.counts), ptr(ws.buf), st))
-    ws.counts_host.copy_(ws.counts, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    H = int(ws.counts_host[0])
+    if known is None:
+        ws.counts_host.copy_(ws.counts, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        H = int(ws.counts_host[0])
+    else:
+        H = int(known)
+    ws.last_count = H
     n_id = n_id_buf[:B + H]
     if not bipartite:
         out_rowptr = torch.cat([out_rowptr, out_rowptr.new_full((H,), nnz_b)])
@@ -327,15 +340,16 @@ def _relabel(within: bool, rowptr: Tensor, col: Tensor, value: Optional[Tensor],
 
 
 def relabel_one_hop(rowptr, col, value, idx, bipartite: bool = True, ws=None,
-                    out_int32: bool = False, nnz_b: Optional[int] = None):
+                    out_int32: bool = False, nnz_b: Optional[int] = None, known: Optional[int] = None):
     """GPU relabel_one_hop (csrc/cpu/relabel_cpu.cpp:3-108), bit-exact."""
-    return _relabel(False, rowptr, col, value, idx, bipartite, ws, out_int32, nnz_b)
+    return _relabel(False, rowptr, col, value, idx, bipartite, ws, out_int32, nnz_b, known)
 
 
 def relabel_one_hop_within_batch(rowptr, col, value, idx, bipartite: bool = True, ws=None,
-                                 out_int32: bool = False, nnz_b: Optional[int] = None):
+                                 out_int32: bool = False, nnz_b: Optional[int] = None,
+                                 known: Optional[int] = None):
     """GPU relabel_one_hop_within_batch (csrc/cpu/relabel_cpu.cpp:111-214), bit-exact."""
-    return _relabel(True, rowptr, col, value, idx, bipartite, ws, out_int32, nnz_b)
+    return _relabel(True, rowptr, col, value, idx, bipartite, ws, out_int32, nnz_b, known)
 
 
 # --------------------------------------------------------------------------------------------

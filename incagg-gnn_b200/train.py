@@ -99,6 +99,119 @@ def mini_train(model, loader, criterion, optimizer, max_steps, grad_norm=None, e
     return {'loss': tl / max(te, 1.), 'steps': steps}
 
 
+def train_step(model, sub, optimizer, VR_update=False, grad_norm=None, averager=None, epoch=0,
+               batch_idx=0):
+    """One iteration of the mini_train loop body on an already collated batch.  Returns
+    (loss * n_train, n_train) as device scalars (no host synchronisation)."""
+    batch, batch_size, n_id, offset, count = sub
+    x, adj_t = batch.x, batch.adj_t
+    y, train_mask = batch.y[:batch_size], batch.train_mask[:batch_size]
+    if VR_update:
+        out = model.VR_call(x, adj_t, batch_size, n_id, offset, count, epoch=epoch, batch_idx=batch_idx)['out']
+    else:
+        out = model(x, adj_t, batch_size, n_id, offset, count)['out']
+    optimizer.zero_grad(set_to_none=True)
+    w = train_mask.to(out.dtype)
+    n = w.sum()
+    if y.dim() == 1:
+        per_row = torch.nn.functional.cross_entropy(out, y, reduction='none')
+    else:
+        per_row = torch.nn.functional.binary_cross_entropy_with_logits(
+            out, y.to(out.dtype), reduction='none').mean(dim=-1)
+    loss = (per_row * w).sum() / n.clamp(min=1.)
+    loss.backward()
+    if averager is not None:
+        averager()
+    if grad_norm is not None:
+        torch.nn.utils.clip_grad_norm_(model.parameters(), grad_norm)
+    optimizer.step()
+    return loss.detach() * n, n
+
+
+class GraphedTrainer:
+    """Replays one CUDA graph per distinct batch (group of partitions).
+
+    A training step is ~230 kernel launches of a few microseconds each, so issuing it from Python is
+    launch-bound.  With a fixed partition -> batch assignment (``batch_size`` partitions per step drawn
+    from a fixed set of groups; C3 uses batch_size = 1, i.e. 150 distinct batches) every step of a given
+    batch has the same kernel sequence and the same sizes: the whole step - GPU collate (relabel +
+    gathers), forward, history push / pull, loss, backward, Adam - is captured once per batch and
+    replayed every epoch.  Nothing is cached between replays: each replay runs every kernel again on
+    the current weights and history tables.  All graphs share one memory pool (they are replayed one at
+    a time).  Data-dependent sizes (halo counts) are read back once, before the capture.
+    """
+
+    def __init__(self, model, loader, optimizer, VR_update=False, grad_norm=None, averager=None):
+        self.model, self.loader, self.optimizer = model, loader, optimizer
+        self.vr, self.grad_norm, self.averager = VR_update, grad_norm, averager
+        self.graphs = {}
+        self.pool = None
+        self.acc = torch.zeros(2, dtype=torch.float64, device=model.device)  # sum(loss * n), sum(n)
+        for g in optimizer.param_groups:
+            if not g.get('capturable', False):
+                raise RuntimeError('GraphedTrainer needs an optimizer built with capturable=True')
+
+    def _body(self, ids):
+        sub = self.loader._collate(list(ids))
+        ln, n = train_step(self.model, sub, self.optimizer, self.vr, self.grad_norm, self.averager)
+        self.acc += torch.stack([ln.double(), n.double()])
+
+    def warmup(self, ids, steps: int = 3):
+        """Eager steps before the first capture (lazy optimizer state, cuBLAS workspaces, scratch)."""
+        self.model.train()
+        s = torch.cuda.Stream(self.model.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(steps):
+                self._body(ids)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+
+    def capture(self, ids):
+        key = tuple(ids)
+        if key in self.graphs:
+            return
+        self.model.train()
+        if len(self.optimizer.state) == 0:
+            raise RuntimeError('run GraphedTrainer.warmup() first: the optimizer state must exist before '
+                               'a step is captured (its lazy initialisation cannot be part of a graph)')
+        # make sure the loader knows the data-dependent sizes of this batch (one eager collate)
+        lk = (('ib',) if self.vr else ('gas',)) + key
+        if lk not in self.loader._known_sizes:
+            self.loader._collate(list(ids))
+        if self.pool is None:
+            self.pool = torch.cuda.graph_pool_handle()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self.pool):
+            self._body(ids)
+        self.graphs[key] = g
+
+    MAX_GRAPHS = 4096
+
+    def step(self, ids):
+        key = tuple(ids)
+        g = self.graphs.get(key)
+        if g is None:
+            if len(self.graphs) >= self.MAX_GRAPHS:  # ever-changing groups (shuffled batch_size > 1)
+                self.model.train()
+                return self._body(ids)
+            self.capture(ids)
+            g = self.graphs[key]
+        g.replay()
+
+    def epoch(self, max_steps=None):
+        """One epoch in the loader's (shuffled) batch order.  Returns the mean training loss."""
+        self.acc.zero_()
+        steps = 0
+        for ids in self.loader._batches_of_epoch():
+            self.step(ids)
+            steps += 1
+            if max_steps is not None and steps >= max_steps:
+                break
+        a = self.acc.tolist()
+        return {'loss': a[0] / max(a[1], 1.), 'steps': steps}
+
+
 @torch.no_grad()
 def mini_test(model, loader, use_aggregation=True, VR_update=False):
     model.eval()
@@ -159,7 +272,7 @@ def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_dev
     optimizer = torch.optim.Adam([
         dict(params=model.reg_modules.parameters(), weight_decay=conf['reg_weight_decay']),
         dict(params=model.nonreg_modules.parameters(), weight_decay=conf['nonreg_weight_decay']),
-    ], lr=conf['lr'])
+    ], lr=conf['lr'], capturable=torch.device(device).type == 'cuda')  # step counter on the device
     max_steps = conf['max_steps'] if conf['max_steps'] != -1 else int(conf['num_parts'] / conf['batch_size'])
     return dict(conf=conf, data=data, raw=raw, ptr=ptr, shard=shard, train_loader=train_loader, eval_loader=eval_loader,
                 model=model, optimizer=optimizer, criterion=criterion, max_steps=max_steps,

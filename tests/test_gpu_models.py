@@ -187,3 +187,37 @@ def test_full_size_products_batch_properties(cuda):
     lhs = ops.spmm_raw(rp, col, val, 2.0 * x - 3.0 * y)
     rhs = 2.0 * ops.spmm_raw(rp, col, val, x) - 3.0 * ops.spmm_raw(rp, col, val, y)
     assert _rel(lhs, rhs) <= RTOL
+
+
+@pytest.mark.parametrize("vr", [False, True])
+def test_graphed_trainer_matches_eager(cuda, vr):
+    """Replaying the per-batch CUDA graphs gives the same losses, weights and history tables as issuing
+    the steps eagerly (two epochs, fixed batch order)."""
+    from incagg_gnn_b200.train import GraphedTrainer, mini_train, mini_test
+    res = {}
+    for graphed in (False, True):
+        run, *_ = _setup(cuda, 'C3', 64, dict(VR_update=vr), num_parts=6)
+        model = run['model']
+        mini_test(model, run['eval_loader'], VR_update=vr)
+        losses = []
+        # one eager step on batch 0 first in both variants (creates the optimizer state, which must
+        # exist before a step can be captured)
+        tr = GraphedTrainer(model, run['train_loader'], run['optimizer'], VR_update=vr)
+        tr.warmup(run['train_loader']._batches_of_epoch()[0], steps=1)
+        if graphed:
+            for _ in range(2):
+                losses.append(tr.epoch()['loss'])
+            assert len(tr.graphs) == 6
+        else:
+            for _ in range(2):
+                losses.append(mini_train(model, run['train_loader'], run['criterion'], run['optimizer'],
+                                         run['max_steps'], VR_update=vr)['loss'])
+        torch.cuda.synchronize()
+        res[graphed] = (losses, [p.detach().clone() for p in model.parameters()],
+                        [h.emb.clone() for h in model.histories])
+    for a, b in zip(res[False][0], res[True][0]):
+        assert abs(a - b) <= 1e-6 * abs(a), (a, b)
+    for a, b in zip(res[False][1], res[True][1]):
+        assert _rel(a, b) <= 1e-5
+    for a, b in zip(res[False][2], res[True][2]):
+        assert _rel(a, b) <= 1e-5
