@@ -6,7 +6,7 @@ if the library is missing the import fails, and every compute entry point requir
 import ctypes
 import os
 import re
-from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_char_p
+from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_char_p, c_float
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libincagg_b200.so")
@@ -50,6 +50,9 @@ _PROTOS = {
                                   c_int64, c_int32, P, P]),
     "incagg_spmm_minmax_bwd": (c_int, [P, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, P]),
     "incagg_spmm_multi": (c_int, [P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, c_int32, P, P, P]),
+    "incagg_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "incagg_gemm_tf32x3": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, P, c_int64, P, c_int64, c_float, P,
+                                   c_int64, c_float, P, c_int, P, c_int64, P, c_size_t, P]),
     "incagg_csr_transpose_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "incagg_csr_transpose": (c_int, [P, P, P, c_int64, c_int64, c_int64, P, P, P, P, P, c_size_t, P]),
     "incagg_gather_rows": (c_int, [P, c_int64, c_int64, P, c_int64, P, c_int64, c_int64, P]),

@@ -42,8 +42,8 @@ int sm_count();  // cached SM count of the current device (148 on B200)
 void count_launch();  // process-wide count of kernels launched by this library
 unsigned long long launches();
 
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+__host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__host__ __device__ inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
 
 // ---- device helpers --------------------------------------------------------
 // Streaming (read-once) loads that do not pollute L1: index/value arrays.

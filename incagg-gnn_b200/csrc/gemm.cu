@@ -1,0 +1,433 @@
+// Dense feature transforms X·W on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   D[M,N] = alpha * op(A)[M,K] · op(B)[K,N] + beta * Cin + bias[n]      (optional ReLU)
+//
+// Replaces the cuBLAS SGEMMs behind torch.nn.Linear / torch.addmm on the propagation path
+// (reference call sites: gcn2.py:87,149 lins, GCN2Conv addmm, gcn.py:63 GCNConv.lin, graphsage.py
+// lin_l / lin_r, appnp.py:79-83).  The reference computes them in fp32 (allow_tf32 = False), and
+// parity is 1e-5 relative, which plain TF32 (10-bit mantissa, ~1e-3) cannot hold.  The kernel
+// therefore runs the error-compensated 3xTF32 scheme: every fp32 operand is split on the way into
+// shared memory into  hi = rna_tf32(x)  and  lo = rna_tf32(x - hi)  and three tcgen05.mma
+// (kind::tf32, fp32 accumulation in TMEM) are issued per k-step:
+//        acc += A_lo·B_hi ;  acc += A_hi·B_lo ;  acc += A_hi·B_hi
+// (the dropped lo·lo term is ~2^-22 relative).
+//
+// Structure of one CTA (128 threads, one 128 x BN output tile, BN = 64 / 128):
+//   * operand tiles are 128 (or BN) rows x 32 k-elements = one 128-byte swizzle row per operand row,
+//     stored K-major in the canonical SWIZZLE_128B layout that the UMMA shared-memory descriptor
+//     expects (16-byte chunk index XOR row-in-atom).  All four source layouts (A as [M,K] or [K,M],
+//     B as [N,K] or [K,N], row-major) are handled by the loader, which transposes on the way in, so
+//     forward (x·W^T), input-gradient (g·W) and weight-gradient (x^T·g) GEMMs are the same kernel;
+//   * global loads of tile k+1 are issued into registers before tile k is stored / multiplied;
+//   * a 3-stage ring of smem tiles: thread 0 issues the 12 MMAs of a stage and commits them to the
+//     stage's mbarrier (tcgen05.commit), which frees the stage for the loader;
+//   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp), alpha / beta / bias / ReLU fused,
+//     vectorised stores.
+//   * split-K (weight gradients: K = number of batch rows) writes fp32 partials that a second small
+//     kernel sums in a fixed order (deterministic) and finishes with the same epilogue.
+#include "common.cuh"
+
+namespace incagg {
+
+constexpr int G_BM = 128;
+constexpr int G_BK = 32;     // 32 tf32 = 128 bytes = one swizzle row
+constexpr int G_STAGES = 3;
+constexpr int G_THREADS = 128;
+
+struct GemmParams {
+  const float* A; int64_t lda; int transA;   // transA = 0: A is [M,K] row-major; 1: stored [K,M]
+  const float* B; int64_t ldb; int transB;   // transB = 0: B is [K,N] row-major; 1: stored [N,K]
+  const float* Cin; int64_t ldcin;
+  const float* bias;
+  float* D; int64_t ldd;
+  float* partial;                            // split-K partial sums [splits][M][N] (NULL if 1 split)
+  int64_t M, N, K;
+  float alpha, beta;
+  int relu;
+  int kb_per_split;                          // k-blocks handled by one blockIdx.z
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] · B[smem], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor of a K-major SWIZZLE_128B tile (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (= 1, unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups)
+//   [46,48) version = 1 (Blackwell)   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b_format TF32 = 2
+// @7 / @10, a/b K-major = 0 @15 / @16, N >> 3 @17, M >> 4 @24.
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---- tile loader ----------------------------------------------------------------------------------
+// A tile is ROWS "output" rows (m or n) x 32 k.  `trans` = the source is contiguous along the output
+// dimension ([K, rows] row-major) instead of along k ([rows, K]).  Each thread owns ROWS/16 float4.
+template <int ROWS>
+struct TileRegs {
+  float4 v[ROWS / 16];
+};
+
+__device__ __forceinline__ float4 ldg4_guarded(const float* p, int valid, bool vec_ok) {
+  // valid = number of in-range elements starting at p (<= 0: none)
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid >= 4 && vec_ok) return __ldg(reinterpret_cast<const float4*>(p));
+  if (valid > 0) r.x = __ldg(p);
+  if (valid > 1) r.y = __ldg(p + 1);
+  if (valid > 2) r.z = __ldg(p + 2);
+  if (valid > 3) r.w = __ldg(p + 3);
+  return r;
+}
+
+template <int ROWS>
+__device__ __forceinline__ void load_tile(const float* __restrict__ src, int64_t ld, int trans, int64_t row0,
+                                          int64_t rows_total, int64_t k0, int64_t k_end, bool vec_ok,
+                                          TileRegs<ROWS>& t) {
+  const int tid = threadIdx.x;
+  if (!trans) {  // [rows, K]: 8 float4 per row along k
+    const int c = tid & 7;
+    const int64_t k = k0 + c * 4;
+#pragma unroll
+    for (int i = 0; i < ROWS / 16; ++i) {
+      const int64_t r = row0 + (tid >> 3) + 16 * i;
+      const int valid = (r < rows_total) ? (int)min((int64_t)4, k_end - k) : 0;
+      t.v[i] = ldg4_guarded(src + r * ld + k, valid, vec_ok);
+    }
+  } else {  // [K, rows]: ROWS/4 float4 per k-row along the output dimension
+    constexpr int F4_PER_K = ROWS / 4;            // 32 (ROWS=128) or 16 (ROWS=64)
+    constexpr int K_PER_PASS = G_THREADS / F4_PER_K;  // 4 or 8
+    const int m4 = tid % F4_PER_K;
+    const int64_t r = row0 + m4 * 4;
+#pragma unroll
+    for (int i = 0; i < ROWS / 16; ++i) {
+      const int64_t k = k0 + tid / F4_PER_K + K_PER_PASS * i;
+      const int valid = (k < k_end) ? (int)min((int64_t)4, rows_total - r) : 0;
+      t.v[i] = ldg4_guarded(src + k * ld + r, valid, vec_ok);
+    }
+  }
+}
+
+// Split into hi / lo TF32 parts and store into the two swizzled K-major tiles.
+template <int ROWS>
+__device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, int trans, char* hi, char* lo) {
+  const int tid = threadIdx.x;
+  if (!trans) {
+    const int c = tid & 7;
+#pragma unroll
+    for (int i = 0; i < ROWS / 16; ++i) {
+      const int r = (tid >> 3) + 16 * i;
+      const float4 x = t.v[i];
+      float4 h, l;
+      h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+      l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+      const int off = r * 128 + ((c ^ (r & 7)) << 4);
+      *reinterpret_cast<float4*>(hi + off) = h;
+      *reinterpret_cast<float4*>(lo + off) = l;
+    }
+  } else {
+    constexpr int F4_PER_K = ROWS / 4;
+    constexpr int K_PER_PASS = G_THREADS / F4_PER_K;
+    const int m4 = tid % F4_PER_K;
+#pragma unroll
+    for (int i = 0; i < ROWS / 16; ++i) {
+      const int k = tid / F4_PER_K + K_PER_PASS * i;
+      const float xs[4] = {t.v[i].x, t.v[i].y, t.v[i].z, t.v[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = m4 * 4 + j;
+        const float h = to_tf32(xs[j]);
+        const float l = to_tf32(xs[j] - h);
+        const int off = r * 128 + (((k >> 2) ^ (r & 7)) << 4) + (k & 3) * 4;
+        *reinterpret_cast<float*>(hi + off) = h;
+        *reinterpret_cast<float*>(lo + off) = l;
+      }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_tf32x3_kernel(const GemmParams p) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  // 1024-byte alignment of every tile (the swizzle is a function of the absolute smem address)
+  char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = G_BM * 128, B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  __shared__ uint64_t mma_done[G_STAGES];
+  __shared__ uint64_t acc_ready;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * G_BM, n0 = (int64_t)blockIdx.y * BN;
+  const int64_t num_kb_total = (p.K + G_BK - 1) / G_BK;
+  const int64_t kb_lo = (int64_t)blockIdx.z * p.kb_per_split;
+  const int64_t kb_hi = min(num_kb_total, kb_lo + p.kb_per_split);
+  const int64_t num_kb = kb_hi - kb_lo;
+
+  if (tid == 0) {
+    for (int s = 0; s < G_STAGES; ++s) mbar_init(&mma_done[s], 1);
+    mbar_init(&acc_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_slot, BN);  // BN fp32 accumulator columns x 128 lanes
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_slot;
+
+  const bool vecA = (p.lda % 4 == 0) && aligned16(p.A);
+  const bool vecB = (p.ldb % 4 == 0) && aligned16(p.B);
+  constexpr uint32_t IDESC = umma_idesc(G_BM, BN);
+
+  TileRegs<G_BM> ra;
+  TileRegs<BN> rb;
+  if (num_kb > 0) {
+    load_tile<G_BM>(p.A, p.lda, p.transA, m0, p.M, kb_lo * G_BK, p.K, vecA, ra);
+    load_tile<BN>(p.B, p.ldb, !p.transB, n0, p.N, kb_lo * G_BK, p.K, vecB, rb);
+  }
+  for (int64_t kb = 0; kb < num_kb; ++kb) {
+    const int s = (int)(kb % G_STAGES);
+    char* st = smem + (size_t)s * STAGE_BYTES;
+    if (kb >= G_STAGES) mbar_wait(&mma_done[s], (uint32_t)(((kb / G_STAGES) - 1) & 1));  // stage free?
+    store_tile<G_BM>(ra, p.transA, st, st + A_BYTES);
+    store_tile<BN>(rb, !p.transB, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES);
+    if (kb + 1 < num_kb) {  // next tile's global loads fly while this one is multiplied
+      load_tile<G_BM>(p.A, p.lda, p.transA, m0, p.M, (kb_lo + kb + 1) * G_BK, p.K, vecA, ra);
+      load_tile<BN>(p.B, p.ldb, !p.transB, n0, p.N, (kb_lo + kb + 1) * G_BK, p.K, vecB, rb);
+    }
+    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_BYTES;
+      const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+      for (int k = 0; k < G_BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte row
+        const uint32_t ko = k * 32;
+        umma_tf32(tmem_acc, umma_desc(a_lo + ko), umma_desc(b_hi + ko), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+        umma_tf32(tmem_acc, umma_desc(a_hi + ko), umma_desc(b_lo + ko), IDESC, 1u);
+        umma_tf32(tmem_acc, umma_desc(a_hi + ko), umma_desc(b_hi + ko), IDESC, 1u);
+      }
+      umma_commit(&mma_done[s]);  // arrives when the MMAs that read this stage have finished
+      if (kb == num_kb - 1) umma_commit(&acc_ready);
+    }
+  }
+  // ---- epilogue ----
+  if (num_kb > 0) mbar_wait(&acc_ready, 0);
+  tc_fence_after();
+  const int64_t m = m0 + warp * 32 + lane;  // TMEM lane = output row of the tile
+  const bool splitk = p.partial != nullptr;
+  float* drow = splitk ? p.partial + ((int64_t)blockIdx.z * p.M + m) * p.N : p.D + m * p.ldd;
+  const int64_t ldd_eff = splitk ? p.N : p.ldd;
+  const bool vecD = (ldd_eff % 4 == 0) && aligned16(splitk ? (const void*)p.partial : (const void*)p.D);
+  const bool vecC = p.Cin && (p.ldcin % 4 == 0) && aligned16(p.Cin);
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    float v[32];
+    if (num_kb > 0) {
+      tmem_ld32(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    }
+    if (m < p.M) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const int64_t n = n0 + c0 + i;
+        if (n >= p.N) break;
+        float o[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
+        const int valid = (int)min((int64_t)4, p.N - n);
+        if (!splitk) {
+          float cin[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.Cin && p.beta != 0.f) {
+            const float4 t = ldg4_guarded(p.Cin + m * p.ldcin + n, valid, vecC);
+            cin[0] = t.x; cin[1] = t.y; cin[2] = t.z; cin[3] = t.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float x = p.alpha * o[j] + p.beta * cin[j];
+            if (p.bias && j < valid) x += __ldg(p.bias + n + j);
+            if (p.relu) x = fmaxf(x, 0.f);
+            o[j] = x;
+          }
+        }
+        if (valid == 4 && vecD) {
+          *reinterpret_cast<float4*>(drow + n) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+          for (int j = 0; j < valid; ++j) drow[n + j] = o[j];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_acc, BN);
+}
+
+// D = alpha * sum_z partial[z] + beta * Cin + bias (+ReLU): fixed summation order -> deterministic.
+__global__ void gemm_splitk_reduce_kernel(const GemmParams p, int splits) {
+  const int64_t total = p.M * p.N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / p.N, n = i - m * p.N;
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += p.partial[(int64_t)z * total + i];
+    float x = p.alpha * acc;
+    if (p.Cin && p.beta != 0.f) x += p.beta * p.Cin[m * p.ldcin + n];
+    if (p.bias) x += p.bias[n];
+    if (p.relu) x = fmaxf(x, 0.f);
+    p.D[m * p.ldd + n] = x;
+  }
+}
+
+template <int BN>
+static int launch_gemm(const GemmParams& p, int splits, cudaStream_t st) {
+  constexpr int STAGE_BYTES = 2 * G_BM * 128 + 2 * BN * 128;
+  constexpr int SMEM = G_STAGES * STAGE_BYTES + 1024;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    IA_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((p.M + G_BM - 1) / G_BM), (unsigned)((p.N + BN - 1) / BN), (unsigned)splits);
+  gemm_tf32x3_kernel<BN><<<grid, G_THREADS, SMEM, st>>>(p);
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}
+
+}  // namespace incagg
+
+using namespace incagg;
+
+extern "C" size_t incagg_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  // split-K partials; the split count never exceeds 128
+  return sizeof(float) * (size_t)M * (size_t)N * 128;
+}
+
+extern "C" int incagg_gemm_tf32x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A,
+                                  int64_t lda, const float* B, int64_t ldb, float alpha, const float* Cin,
+                                  int64_t ldcin, float beta, const float* bias, int relu, float* D,
+                                  int64_t ldd, void* workspace, size_t workspace_bytes,
+                                  incagg_stream_t stream) {
+  IA_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "negative size");
+  if (M == 0 || N == 0) return INCAGG_OK;
+  IA_CHECK_ARG(D != nullptr, "D is NULL");
+  IA_CHECK_ARG(K == 0 || (A != nullptr && B != nullptr), "NULL operand");
+  IA_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldd >= N, "leading dimension too small");
+  IA_CHECK_ARG(Cin == nullptr || ldcin >= N, "ldcin too small");
+  IA_CHECK_ARG((M + G_BM - 1) / G_BM <= 0x7fffffff, "M too large");
+  GemmParams p{};
+  p.A = A; p.lda = lda; p.transA = transA; p.B = B; p.ldb = ldb; p.transB = transB;
+  p.Cin = Cin; p.ldcin = ldcin; p.bias = bias; p.D = D; p.ldd = ldd; p.M = M; p.N = N; p.K = K;
+  p.alpha = alpha; p.beta = beta; p.relu = relu;
+  const int64_t num_kb = (K + G_BK - 1) / G_BK;
+  // split-K when the output has few tiles and the reduction is long (weight gradients)
+  const int64_t tiles = ((M + G_BM - 1) / G_BM) * ((N + (N <= 64 ? 63 : 127)) / (N <= 64 ? 64 : 128));
+  int splits = 1;
+  if (num_kb >= 16 && tiles < sm_count()) {
+    int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+    if (want > num_kb / 4) want = num_kb / 4;
+    if (want > 128) want = 128;
+    if (want > 1 && workspace != nullptr &&
+        workspace_bytes >= sizeof(float) * (size_t)M * (size_t)N * (size_t)want)
+      splits = (int)want;
+  }
+  p.kb_per_split = (int)((num_kb + splits - 1) / splits);
+  if (p.kb_per_split < 1) p.kb_per_split = 1;
+  splits = (int)((num_kb + p.kb_per_split - 1) / p.kb_per_split);
+  if (splits < 1) splits = 1;
+  p.partial = splits > 1 ? static_cast<float*>(workspace) : nullptr;
+  cudaStream_t st = as_stream(stream);
+  int rc = (N <= 64) ? launch_gemm<64>(p, splits, st) : launch_gemm<128>(p, splits, st);
+  if (rc != INCAGG_OK) return rc;
+  if (splits > 1) {
+    const int64_t total = M * N;
+    const int blocks = (int)((total + 255) / 256 < (int64_t)sm_count() * 8 ? (total + 255) / 256 : (int64_t)sm_count() * 8);
+    gemm_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p, splits);
+    IA_LAUNCH_CHECK();
+  }
+  return INCAGG_OK;
+}

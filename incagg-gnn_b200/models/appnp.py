@@ -4,8 +4,9 @@ from typing import Optional
 import torch
 from torch import Tensor
 import torch.nn.functional as F
-from torch.nn import ModuleList, Linear
+from torch.nn import ModuleList
 
+from ..nn import Linear
 from ..sparse import SparseTensor, spmm, spmm_delta
 from .base import ScalableGNN
 from ._masking import select_edges
@@ -40,7 +41,7 @@ class APPNP(ScalableGNN):
 
     def _mlp(self, x):
         x = F.dropout(x, p=self.dropout, training=self.training)
-        x = self.lins[0](x).relu()
+        x = self.lins[0](x, relu=True)
         x = F.dropout(x, p=self.dropout, training=self.training)
         return self.lins[1](x)
 
@@ -96,4 +97,4 @@ class APPNP(ScalableGNN):
         return (1 - self.alpha) * ax + self.alpha * state['x_0']
 
     def _refresh_layer0_input(self, x: Tensor) -> Tensor:
-        return self.lins[1](self.lins[0](x).relu())  # appnp.py:249-251
+        return self.lins[1](self.lins[0](x, relu=True))  # appnp.py:249-251

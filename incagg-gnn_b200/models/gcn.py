@@ -4,9 +4,9 @@ from typing import Optional
 import torch
 from torch import Tensor
 import torch.nn.functional as F
-from torch.nn import ModuleList, Linear, BatchNorm1d
+from torch.nn import ModuleList, BatchNorm1d
 
-from ..nn import GCNConv
+from ..nn import GCNConv, Linear
 from ..sparse import SparseTensor, spmm_delta
 from .base import ScalableGNN
 from ._masking import select_edges

@@ -4,9 +4,9 @@ from typing import Optional
 import torch
 from torch import Tensor
 import torch.nn.functional as F
-from torch.nn import ModuleList, Linear, BatchNorm1d
+from torch.nn import ModuleList, BatchNorm1d
 
-from ..nn import GCN2Conv
+from ..nn import GCN2Conv, Linear
 from ..sparse import SparseTensor, spmm_delta
 from .base import ScalableGNN
 from ._masking import select_edges
@@ -57,6 +57,10 @@ class GCN2(ScalableGNN):
         for bn in self.bns:
             bn.reset_parameters()
 
+    @property
+    def _fuse_relu(self) -> bool:
+        return not self.batch_norm and not self.residual
+
     def _post(self, i: int, h: Tensor, x: Tensor) -> Tensor:
         if self.batch_norm:
             h = self.bns[i](h)
@@ -70,28 +74,30 @@ class GCN2(ScalableGNN):
         batch_size, n_id, offset, count = (list(args) + [None] * 4)[:4]
         if self.drop_input:
             x = F.dropout(x, p=self.dropout, training=self.training)
-        x = x_0 = self.lins[0](x).relu_()
+        x = x_0 = self.lins[0](x, relu=True)
         x = F.dropout(x, p=self.dropout, training=self.training)
         t_all = 0
+        fuse = self._fuse_relu  # no batch norm / residual: ReLU rides in the GEMM epilogue
+        x0b = x_0[:adj_t.size(0)]
         if use_aggregation:
             adj_t = select_edges(adj_t, batch_size, aggregate_combined)
             for i, (conv, hist) in enumerate(zip(self.convs[:-1], self.histories)):
                 # rows >= B of x are constants (pulled history) after the first push_and_pull
-                h = conv(x, x_0, adj_t, grad_rows=batch_size if i > 0 else None)
-                x = self._post(i, h, x)
+                h = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=fuse)
+                x = h if fuse else self._post(i, h, x)
                 x, t = self.push_and_pull(hist, x, batch_size, n_id, offset, count)
                 t_all += t
                 x = F.dropout(x, p=self.dropout, training=self.training)
-            h = self.convs[-1](x, x_0, adj_t,
-                               grad_rows=batch_size if self.num_layers > 1 else None)
+            h = self.convs[-1](x, x0b, adj_t,
+                               grad_rows=batch_size if self.num_layers > 1 else None, relu=fuse)
         else:  # no neighbour information (gcn2.py:151-181)
             x, x_0 = x[:batch_size], x_0[:batch_size]
             for i, conv in enumerate(self.convs[:-1]):
-                h = conv.forward_no_neighbor(x, x_0)
-                x = self._post(i, h, x)
+                h = conv.forward_no_neighbor(x, x_0, relu=fuse)
+                x = h if fuse else self._post(i, h, x)
                 x = F.dropout(x, p=self.dropout, training=self.training)
-            h = self.convs[-1].forward_no_neighbor(x, x_0)
-        x = self._post(self.num_layers - 1, h, x)
+            h = self.convs[-1].forward_no_neighbor(x, x_0, relu=fuse)
+        x = h if fuse else self._post(self.num_layers - 1, h, x)
         x = F.dropout(x, p=self.dropout, training=self.training)
         return self.lins[1](x), t_all
 
@@ -101,16 +107,18 @@ class GCN2(ScalableGNN):
         batch_size, n_id, offset, count = (list(args) + [None] * 4)[:4]
         if self.drop_input:
             x = F.dropout(x, p=self.dropout, training=self.training)
-        x = x_0 = self.lins[0](x).relu_()
+        x = x_0 = self.lins[0](x, relu=True)
         x = F.dropout(x, p=self.dropout, training=self.training)
+        fuse = self._fuse_relu
+        x0b = x_0[:adj_t.size(0)]
         for i, conv in enumerate(self.convs):
             if i == self.num_layers - 1:
                 x = x[:batch_size]
             m_in, m_ag, gid = self._incagg_tables(i, batch_size, x.shape[1], n_id, offset, count)
             h = spmm_delta(adj_t, x, m_in, m_ag, gid)  # A_BB (x - M_in) + M_ag, one kernel
-            h = conv.forward_after_propagate(h, x_0)
+            h = conv.forward_after_propagate(h, x0b, relu=fuse)
             self._incagg_release()
-            x = self._post(i, h, x)
+            x = h if fuse else self._post(i, h, x)
             x = F.dropout(x, p=self.dropout, training=self.training)
         return self.lins[1](x), 0, 0, 0
 
@@ -125,7 +133,7 @@ class GCN2(ScalableGNN):
             else:
                 if self.drop_input:
                     x = F.dropout(x, p=self.dropout, training=self.training)
-                x = x_0 = self.lins[0](x).relu_()
+                x = x_0 = self.lins[0](x, relu=True)
             state['x_0'] = x_0[:adj_t.size(0)]
         x = F.dropout(x, p=self.dropout, training=self.training)
         conv = self.convs[layer]
@@ -146,4 +154,4 @@ class GCN2(ScalableGNN):
         return x
 
     def _refresh_layer0_input(self, x: Tensor) -> Tensor:
-        return self.lins[0](x).relu_()  # gcn2.py:452
+        return self.lins[0](x, relu=True)  # gcn2.py:452

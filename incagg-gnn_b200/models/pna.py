@@ -13,9 +13,10 @@ from typing import Optional, List
 import torch
 from torch import Tensor
 import torch.nn.functional as F
-from torch.nn import ModuleList, Linear, BatchNorm1d
+from torch.nn import ModuleList, BatchNorm1d
 
 from .. import ops
+from ..nn import Linear
 from ..sparse import SparseTensor, spmm
 from .base import ScalableGNN
 

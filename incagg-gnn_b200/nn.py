@@ -12,9 +12,95 @@ from typing import Optional
 
 import torch
 from torch import Tensor
-from torch.nn import Linear, Parameter
+from torch.nn import Parameter
 
+from . import ops
 from .sparse import SparseTensor, spmm
+
+
+# ---- dense transforms on the tensor cores ---------------------------------------------------------
+class _LinearTC(torch.autograd.Function):
+    """y = x W^T + b (optionally ReLU) on the tcgen05 3xTF32 GEMM; backward = two more GEMMs of the
+    same kernel (input gradient g W, weight gradient g^T x with deterministic split-K)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        y = ops.gemm(x, weight, trans_b=True, bias=bias, relu=relu)
+        ctx.relu = relu
+        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, y = ctx.saved_tensors
+        g = g.contiguous()
+        if ctx.relu:
+            g = g * (y > 0)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ops.gemm(g, weight)                      # [M,N] x [N,K]
+        if ctx.needs_input_grad[1]:
+            gw = ops.gemm(g, x, trans_a=True)             # g^T x : [N,M] x [M,K]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        return gx, gw, gb, None
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu: bool = False) -> Tensor:
+    if x.dim() != 2:
+        return linear(x.reshape(-1, x.size(-1)), weight, bias, relu).reshape(*x.shape[:-1], weight.size(0))
+    return _LinearTC.apply(x, weight, bias, relu)
+
+
+class Linear(torch.nn.Linear):
+    """torch.nn.Linear whose product runs on the hand-written tcgen05 GEMM (same parameters, same
+    initialisation).  ``forward(x, relu=True)`` fuses the activation into the GEMM epilogue."""
+
+    def forward(self, x: Tensor, relu: bool = False) -> Tensor:
+        return linear(x, self.weight, self.bias, relu)
+
+
+class _GCN2Dense(torch.autograd.Function):
+    """The dense half of GCN2Conv after the propagation, fused around the tensor-core GEMM:
+        s   = (1-a) h + a x0
+        out = (1-b) s + b ((1-a) h W1 + a x0 W2)          (W2 = W1 when weights are shared)
+    forward: one lerp + two GEMMs with alpha / beta / Cin (/ ReLU) epilogues instead of ~10 elementwise
+    and addmm launches; backward: four GEMMs whose epilogues produce the input gradients directly."""
+
+    @staticmethod
+    def forward(ctx, h, x0, w1, w2, a, b, relu):
+        s = torch.lerp(h, x0, a)
+        if w2 is None:
+            out = ops.gemm(s, w1, alpha=b, cin=s, beta=1. - b, relu=relu)
+        else:
+            out = ops.gemm(h, w1, alpha=b * (1. - a), cin=s, beta=1. - b)
+            out = ops.gemm(x0, w2, alpha=b * a, cin=out, beta=1., relu=relu, out=out)
+        ctx.a, ctx.b, ctx.relu, ctx.shared = a, b, relu, w2 is None
+        ctx.save_for_backward(h, x0, w1, w2, out if relu else None, s if w2 is None else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, x0, w1, w2, out, s = ctx.saved_tensors
+        a, b = ctx.a, ctx.b
+        g = g.contiguous()
+        if ctx.relu:
+            g = g * (out > 0)
+        gh = gx0 = gw1 = gw2 = None
+        if ctx.shared:
+            # out = (1-b) s + b s W1 ;  ds = (1-b) g + b g W1^T ; dh = (1-a) ds ; dx0 = a ds
+            ds = ops.gemm(g, w1, trans_b=True, alpha=b, cin=g, beta=1. - b)
+            gh, gx0 = (1. - a) * ds, a * ds
+            gw1 = ops.gemm(s, g, trans_a=True, alpha=b)
+        else:
+            if ctx.needs_input_grad[0]:
+                gh = ops.gemm(g, w1, trans_b=True, alpha=b * (1. - a), cin=g, beta=(1. - b) * (1. - a))
+            if ctx.needs_input_grad[1]:
+                gx0 = ops.gemm(g, w2, trans_b=True, alpha=b * a, cin=g, beta=(1. - b) * a)
+            gw1 = ops.gemm(h, g, trans_a=True, alpha=b * (1. - a))
+            gw2 = ops.gemm(x0, g, trans_a=True, alpha=b * a)
+        return gh, gx0, gw1, gw2, None, None, None
 
 
 def glorot_(w: Tensor) -> Tensor:
@@ -74,24 +160,24 @@ class GCN2Conv(torch.nn.Module):
         if self.weight2 is not None:
             glorot_(self.weight2)
 
-    def forward_after_propagate(self, h: Tensor, x_0: Tensor) -> Tensor:
-        x = h * (1 - self.alpha)
-        x_0 = self.alpha * x_0[:x.size(0)]
-        if self.weight2 is None:
-            out = x + x_0
-            out = torch.addmm(out, out, self.weight1, beta=1. - self.beta, alpha=self.beta)
-        else:
-            out = torch.addmm(x, x, self.weight1, beta=1. - self.beta, alpha=self.beta)
-            out = out + torch.addmm(x_0, x_0, self.weight2, beta=1. - self.beta, alpha=self.beta)
-        return out
+    def forward_after_propagate(self, h: Tensor, x_0: Tensor, relu: bool = False) -> Tensor:
+        """Everything of PyG's GCN2Conv.forward after ``propagate``:
+            x = (1-alpha) h ; x_0 = alpha x_0[:B]
+            shared:   out = x + x_0 ; out = (1-beta) out + beta out W1
+            unshared: out = (1-beta) x + beta x W1 + (1-beta) x_0 + beta x_0 W2
+        evaluated by the fused tensor-core block (``relu=True`` also applies the activation that
+        follows in the models when there is no batch norm / residual in between)."""
+        x_0 = x_0[:h.size(0)]
+        return _GCN2Dense.apply(h.contiguous(), x_0.contiguous(), self.weight1, self.weight2,
+                                float(self.alpha), float(self.beta), relu)
 
-    def forward_no_neighbor(self, x: Tensor, x_0: Tensor) -> Tensor:
-        return self.forward_after_propagate(x, x_0)
+    def forward_no_neighbor(self, x: Tensor, x_0: Tensor, relu: bool = False) -> Tensor:
+        return self.forward_after_propagate(x, x_0, relu)
 
     def forward(self, x: Tensor, x_0: Tensor, adj_t: SparseTensor,
-                grad_rows: Optional[int] = None) -> Tensor:
+                grad_rows: Optional[int] = None, relu: bool = False) -> Tensor:
         h = spmm(adj_t, x, reduce='sum', grad_rows=grad_rows)
-        return self.forward_after_propagate(h, x_0)
+        return self.forward_after_propagate(h, x_0, relu)
 
 
 class SAGEConv(torch.nn.Module):

@@ -157,6 +157,55 @@ def csr_transpose(rowptr: Tensor, col: Tensor, val: Optional[Tensor], rows: int,
 
 
 # --------------------------------------------------------------------------------------------
+# dense X·W on the tensor cores (tcgen05, 3xTF32)
+# --------------------------------------------------------------------------------------------
+_GEMM_WS = {}
+
+
+def _gemm_workspace(device, nbytes: int) -> Tensor:
+    ws = _GEMM_WS.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = _GEMM_WS[device] = torch.empty(max(nbytes, 1 << 24), dtype=torch.uint8, device=device)
+    return ws
+
+
+def _rowmajor(t: Tensor) -> Tensor:
+    if t.dim() != 2 or t.dtype != torch.float32:
+        raise RuntimeError("gemm: expected 2-D float32 tensors")
+    if t.stride(1) != 1 or (t.size(0) > 1 and t.stride(0) < t.size(1)):
+        t = t.contiguous()
+    return t
+
+
+def gemm(a: Tensor, b: Tensor, trans_a: bool = False, trans_b: bool = False, alpha: float = 1.0,
+         cin: Optional[Tensor] = None, beta: float = 0.0, bias: Optional[Tensor] = None,
+         relu: bool = False, out: Optional[Tensor] = None) -> Tensor:
+    """out[M,N] = alpha * op(a) @ op(b) + beta * cin + bias (+ReLU) with the tcgen05 3xTF32 kernel.
+    trans_a: `a` is stored [K, M]; trans_b: `b` is stored [N, K] (a Linear weight)."""
+    _require_cuda(a, b, cin, bias, out)
+    a, b = _rowmajor(a), _rowmajor(b)
+    M, K = (a.size(1), a.size(0)) if trans_a else (a.size(0), a.size(1))
+    N, Kb = (b.size(0), b.size(1)) if trans_b else (b.size(1), b.size(0))
+    if K != Kb:
+        raise RuntimeError(f"gemm: inner dimensions differ ({K} vs {Kb})")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if cin is not None:
+        cin = _rowmajor(cin)
+    ws_bytes = 0
+    ws = None
+    if K >= 512 and M * N <= (1 << 20):  # long reduction, few output tiles: split-K partials
+        ws_bytes = min(lib.incagg_gemm_workspace_bytes(M, N, K), 1 << 28)
+        ws = _gemm_workspace(a.device, ws_bytes)
+        ws_bytes = ws.numel()
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_gemm_tf32x3(int(trans_a), int(trans_b), M, N, K, ptr(a), _ld(a), ptr(b), _ld(b),
+                                 float(alpha), ptr(cin), _ld(cin) if cin is not None else 0, float(beta),
+                                 ptr(bias), int(relu), ptr(out), _ld(out), ptr(ws), ws_bytes, _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # rows: gather / scatter / slices
 # --------------------------------------------------------------------------------------------
 def _row_view(t: Tensor):

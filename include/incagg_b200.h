@@ -115,6 +115,24 @@ int incagg_spmm_multi(const int32_t* rowptr, const int32_t* col, const float* va
                       int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t F, int32_t K,
                       const int32_t* reducers, const void* plan, incagg_stream_t stream);
 
+/* ---- dense feature transform on the tensor cores ----------------------- */
+/*
+ * D[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * Cin + bias[n]   (+ ReLU if relu != 0), fp32 in/out.
+ * Replaces the cuBLAS SGEMMs behind torch.nn.Linear / torch.addmm on the path (gcn2.py:87,149;
+ * GCN2Conv addmm; GCNConv.lin gcn.py:63; SAGEConv.lin_l/lin_r; appnp.py:79-83).  tcgen05.mma kind::tf32
+ * with fp32 accumulation in TMEM and the error-compensated 3xTF32 operand split, so results stay
+ * within ~1e-6 relative of an fp32 GEMM.
+ *   transA = 0: A is [M,K] row-major (lda); 1: A is stored [K,M] row-major
+ *   transB = 0: B is [K,N] row-major (ldb); 1: B is stored [N,K] row-major (a Linear weight)
+ *   Cin / bias nullable.  workspace (nullable) enables deterministic split-K for long reductions
+ *   (weight gradients); incagg_gemm_workspace_bytes gives a sufficient size.
+ */
+size_t incagg_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int incagg_gemm_tf32x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A,
+                       int64_t lda, const float* B, int64_t ldb, float alpha, const float* Cin,
+                       int64_t ldcin, float beta, const float* bias, int relu, float* D, int64_t ldd,
+                       void* workspace, size_t workspace_bytes, incagg_stream_t stream);
+
 /* ---- CSR transpose (CSC view for the backward SpMM) ------------------- */
 /*
  * Counting-sort transpose of a [rows x cols] CSR with nnz entries.

@@ -182,6 +182,49 @@ def test_minmax_backward_routes_to_arg(ops, cuda):
     assert _rel_err(gx, ref) <= RTOL
 
 
+# ---- dense GEMM (tcgen05 3xTF32) -------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (300, 128, 100), (1000, 47, 128), (77, 64, 32),
+                                   (130, 200, 260), (5, 3, 7), (256, 128, 4096), (100, 128, 20000)])
+@pytest.mark.parametrize("trans_a,trans_b", [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_tf32x3_matches_fp64(ops, cuda, M, N, K, trans_a, trans_b):
+    """All four operand layouts, ragged sizes, split-K; fp32-level accuracy (<= 1e-5 of max |out|, the
+    north_star tolerance; typically ~1e-6) although the products run on TF32 tensor cores."""
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(K, N, generator=g)
+    a = (A.t().contiguous() if trans_a else A).to(cuda)
+    b = (B.t().contiguous() if trans_b else B).to(cuda)
+    out = ops.gemm(a, b, trans_a=trans_a, trans_b=trans_b)
+    ref = A.double() @ B.double()
+    err = float((out.cpu().double() - ref).abs().max() / ref.abs().max())
+    assert err <= RTOL, err
+    assert err <= 3e-6, err   # what 3xTF32 actually delivers
+
+
+def test_gemm_epilogue_and_views(ops, cuda):
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 333, 128, 128
+    x = torch.randn(M, K, generator=g).to(cuda)
+    w = torch.randn(N, K, generator=g).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    cin = torch.randn(M, N, generator=g).to(cuda)
+    out = ops.gemm(x, w, trans_b=True, alpha=0.3, cin=cin, beta=0.7, bias=bias, relu=True)
+    ref = torch.relu(0.3 * (x.double() @ w.double().t()) + 0.7 * cin.double() + bias.double())
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) <= RTOL
+    # strided views: column-cropped A (ld > K, 16-byte aligned and not), output into a slice
+    big = torch.randn(M, 200, generator=g).to(cuda)
+    for lo in (0, 4, 1):
+        xa = big[:, lo:lo + K]
+        o = ops.gemm(xa, w, trans_b=True)
+        r = xa.double() @ w.double().t()
+        assert float((o.double() - r).abs().max() / r.abs().max()) <= RTOL
+    dst = torch.zeros(M, 256, device=cuda)
+    ops.gemm(x, w, trans_b=True, out=dst[:, 128:])
+    r = x.double() @ w.double().t()
+    assert float((dst[:, 128:].double() - r).abs().max() / r.abs().max()) <= RTOL
+    assert float(dst[:, :128].abs().max()) == 0.
+
+
 # ---- transpose --------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(50, 70, 6, 0, 0), (300, 40, 40, 0, 0), (64, 20, 4, 2, 40000)])
 def test_csr_transpose_is_bit_exact_and_ordered(ops, cuda, shape):
