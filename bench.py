@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="issue every step eagerly from Python")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU halo rows: NVLink peer loads in the gather kernel, or NCCL all-to-all-v")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=6)
     return ap.parse_args()
@@ -224,12 +226,15 @@ def timed_steps(run, mode, warmup, steps, dist, e2e=False):
             out = model.VR_call(x, adj_t, B, n_id, offset, count)["out"]
         else:
             out = model(x, adj_t, B, n_id, offset, count)["out"]
-        opt.zero_grad(set_to_none=True)
+        if averager is not None:
+            averager.zero()
+        else:
+            opt.zero_grad(set_to_none=True)
         w = m.to(out.dtype)
         loss = (torch.nn.functional.cross_entropy(out, y, reduction="none") * w).sum() / w.sum().clamp(min=1.)
         loss.backward()
         if averager is not None:
-            averager()  # NCCL all-reduce of the flat gradient buffer
+            averager()  # NCCL all-reduce of the flat gradient buffer (p.grad are views into it)
         if conf["grad_norm"] is not None:
             torch.nn.utils.clip_grad_norm_(model.parameters(), conf["grad_norm"])
         opt.step()
@@ -350,7 +355,8 @@ def main():
     # sharded over the ranks.  A step at N GPUs = N batches in flight (one per rank) + gradient
     # all-reduce, so per-GPU work per step is fixed ("weak") and `value` is the whole-job edges/s.
     run = build(args.config, device=dev, seed=args.seed, scale=args.scale,
-                overrides=dict(VR_update=vr), shuffle=True, rank=rank, world_size=world)
+                overrides=dict(VR_update=vr), shuffle=True, rank=rank, world_size=world,
+                transport=args.transport)
     model = run["model"]
     mini_test(model, run["eval_loader"], VR_update=vr)  # fill the histories (main.py:211-215), untimed
     torch.cuda.synchronize()
@@ -359,7 +365,7 @@ def main():
     if rank == 0:
         sampler.start()
     graphs = None
-    if args.no_graphs:
+    if args.no_graphs or (world > 1 and args.transport == "nccl"):
         l0 = _lib.launch_count()
         sec, edges, _, _, wall = timed_steps(run, args.mode, args.warmup, args.steps, dist)
         launches = _lib.launch_count() - l0
@@ -436,7 +442,11 @@ def main():
                    "mode": args.mode, "scale": args.scale,
                    "l2": "inputs larger than L2: every step reads a different partition (graph + features "
                          "+ 10 history tables = 14 GB per epoch)",
-                   "histories": "HBM-resident",
+                   "histories": "HBM-resident" + ("" if world == 1 else
+                                                  f", sharded by partition over {world} ranks; halo rows via "
+                                                  + ("NVLink peer loads inside the gather kernel (CUDA IPC)"
+                                                     if args.transport == "p2p" else "NCCL all-to-all-v")
+                                                  + ", gradients NCCL all-reduce"),
                    "step_issue": ("eager (Python launches)" if graphs is None else
                                   f"CUDA graph per partition batch ({graphs['captured']} graphs captured before the "
                                   f"timed region in {graphs['capture_s']} s; every replay re-runs collate, forward, "

@@ -43,6 +43,7 @@ _PROTOS = {
     "incagg_last_error": (c_char_p, []),
     "incagg_launch_count": (c_int64, []),
     "incagg_device_info": (c_int, [P, P, P]),
+    "incagg_enable_peer_access": (c_int, [c_int]),
     "incagg_spmm_plan_bytes": (c_size_t, [c_int64, c_int64]),
     "incagg_spmm_plan": (c_int, [P, c_int64, c_int64, P, c_size_t, P]),
     "incagg_spmm_csr": (c_int, [c_int, P, P, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, P, P]),
@@ -56,6 +57,7 @@ _PROTOS = {
     "incagg_csr_transpose_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "incagg_csr_transpose": (c_int, [P, P, P, c_int64, c_int64, c_int64, P, P, P, P, P, c_size_t, P]),
     "incagg_gather_rows": (c_int, [P, c_int64, c_int64, P, c_int64, P, c_int64, c_int64, P]),
+    "incagg_gather_rows_sharded": (c_int, [P, P, c_int, c_int64, P, c_int64, P, c_int64, c_int64, P]),
     "incagg_scatter_rows": (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int64, P]),
     "incagg_copy_slices": (c_int, [P, c_int64, c_int64, P, c_int64, c_int64, P, P, c_int64, c_int64,
                                    c_int, P]),

@@ -55,3 +55,21 @@ extern "C" int incagg_device_info(int* sm_count_out, int* cc_major, int* cc_mino
   if (cc_minor) *cc_minor = min_;
   return INCAGG_OK;
 }
+
+// Let kernels of the current device load / store memory of `peer_device` over NVLink (the history
+// shards of other ranks, mapped into this process through CUDA IPC).  Idempotent.
+extern "C" int incagg_enable_peer_access(int peer_device) {
+  int dev = 0;
+  IA_CUDA(cudaGetDevice(&dev));
+  if (dev == peer_device) return INCAGG_OK;
+  int can = 0;
+  IA_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  IA_CHECK_ARG(can != 0, "device %d cannot access peer device %d", dev, peer_device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return INCAGG_OK;
+  }
+  IA_CUDA(e);
+  return INCAGG_OK;
+}

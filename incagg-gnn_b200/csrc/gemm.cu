@@ -12,17 +12,18 @@
 //        acc += A_lo·B_hi ;  acc += A_hi·B_lo ;  acc += A_hi·B_hi
 // (the dropped lo·lo term is ~2^-22 relative).
 //
-// Structure of one CTA (128 threads, one 128 x BN output tile, BN = 64 / 128):
+// Structure of one CTA (256 threads, one 128 x BN output tile, BN = 64 / 128):
 //   * operand tiles are 128 (or BN) rows x 32 k-elements = one 128-byte swizzle row per operand row,
 //     stored K-major in the canonical SWIZZLE_128B layout that the UMMA shared-memory descriptor
 //     expects (16-byte chunk index XOR row-in-atom).  All four source layouts (A as [M,K] or [K,M],
 //     B as [N,K] or [K,N], row-major) are handled by the loader, which transposes on the way in, so
 //     forward (x·W^T), input-gradient (g·W) and weight-gradient (x^T·g) GEMMs are the same kernel;
-//   * global loads of tile k+1 are issued into registers before tile k is stored / multiplied;
+//   * the global loads of tiles k+1 and k+2 are in flight (two register sets) while tile k is split,
+//     stored and multiplied;
 //   * a 3-stage ring of smem tiles: thread 0 issues the 12 MMAs of a stage and commits them to the
 //     stage's mbarrier (tcgen05.commit), which frees the stage for the loader;
-//   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp), alpha / beta / bias / ReLU fused,
-//     vectorised stores.
+//   * epilogue: 8 warps, each tcgen05.ld's 32 lanes x BN/2 columns; Cin is fetched before the
+//     accumulator is waited for; alpha / beta / bias / ReLU fused, vectorised stores.
 //   * split-K (weight gradients: K = number of batch rows) writes fp32 partials that a second small
 //     kernel sums in a fixed order (deterministic) and finishes with the same epilogue.
 #include "common.cuh"
@@ -32,7 +33,7 @@ namespace incagg {
 constexpr int G_BM = 128;
 constexpr int G_BK = 32;     // 32 tf32 = 128 bytes = one swizzle row
 constexpr int G_STAGES = 3;
-constexpr int G_THREADS = 128;
+constexpr int G_THREADS = 256;
 
 struct GemmParams {
   const float* A; int64_t lda; int transA;   // transA = 0: A is [M,K] row-major; 1: stored [K,M]
@@ -143,10 +144,11 @@ __device__ __forceinline__ float to_tf32(float x) {
 
 // ---- tile loader ----------------------------------------------------------------------------------
 // A tile is ROWS "output" rows (m or n) x 32 k.  `trans` = the source is contiguous along the output
-// dimension ([K, rows] row-major) instead of along k ([rows, K]).  Each thread owns ROWS/16 float4.
+// dimension ([K, rows] row-major) instead of along k ([rows, K]).  Each of the 256 threads owns
+// ROWS/32 float4 of a tile.
 template <int ROWS>
 struct TileRegs {
-  float4 v[ROWS / 16];
+  float4 v[ROWS / 32];
 };
 
 __device__ __forceinline__ float4 ldg4_guarded(const float* p, int valid, bool vec_ok) {
@@ -160,28 +162,34 @@ __device__ __forceinline__ float4 ldg4_guarded(const float* p, int valid, bool v
   return r;
 }
 
+// Thread -> element mapping.
+//   !trans: chunk c = tid & 7 (16 bytes of the 128-byte k-row), row r = (tid >> 3) + 32 i.  A quarter
+//           warp writes the 8 chunks of one row: the XOR swizzle keeps them on distinct banks.
+//   trans : a warp owns a 4 (k) x 32 (rows) patch: kq = lane >> 3, m4 = lane & 7 -> one float4 along
+//           the rows; patch index wt = warp + 8 i, k-group = wt & 7, row-group = wt >> 3.  The four
+//           elements of a float4 go to four different tile rows; element j = (t + (m4 >> 1)) & 3 is
+//           written in store instruction t, which spreads the 32 lanes over all 32 banks.
 template <int ROWS>
 __device__ __forceinline__ void load_tile(const float* __restrict__ src, int64_t ld, int trans, int64_t row0,
                                           int64_t rows_total, int64_t k0, int64_t k_end, bool vec_ok,
                                           TileRegs<ROWS>& t) {
   const int tid = threadIdx.x;
-  if (!trans) {  // [rows, K]: 8 float4 per row along k
-    const int c = tid & 7;
-    const int64_t k = k0 + c * 4;
+  if (!trans) {
+    const int64_t k = k0 + (tid & 7) * 4;
 #pragma unroll
-    for (int i = 0; i < ROWS / 16; ++i) {
-      const int64_t r = row0 + (tid >> 3) + 16 * i;
+    for (int i = 0; i < ROWS / 32; ++i) {
+      const int64_t r = row0 + (tid >> 3) + 32 * i;
       const int valid = (r < rows_total) ? (int)min((int64_t)4, k_end - k) : 0;
       t.v[i] = ldg4_guarded(src + r * ld + k, valid, vec_ok);
     }
-  } else {  // [K, rows]: ROWS/4 float4 per k-row along the output dimension
-    constexpr int F4_PER_K = ROWS / 4;            // 32 (ROWS=128) or 16 (ROWS=64)
-    constexpr int K_PER_PASS = G_THREADS / F4_PER_K;  // 4 or 8
-    const int m4 = tid % F4_PER_K;
-    const int64_t r = row0 + m4 * 4;
+  } else {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int kq = lane >> 3, m4 = lane & 7;
 #pragma unroll
-    for (int i = 0; i < ROWS / 16; ++i) {
-      const int64_t k = k0 + tid / F4_PER_K + K_PER_PASS * i;
+    for (int i = 0; i < ROWS / 32; ++i) {
+      const int wt = warp + 8 * i;
+      const int64_t k = k0 + (wt & 7) * 4 + kq;
+      const int64_t r = row0 + (wt >> 3) * 32 + m4 * 4;
       const int valid = (k < k_end) ? (int)min((int64_t)4, rows_total - r) : 0;
       t.v[i] = ldg4_guarded(src + k * ld + r, valid, vec_ok);
     }
@@ -195,8 +203,8 @@ __device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, int trans, c
   if (!trans) {
     const int c = tid & 7;
 #pragma unroll
-    for (int i = 0; i < ROWS / 16; ++i) {
-      const int r = (tid >> 3) + 16 * i;
+    for (int i = 0; i < ROWS / 32; ++i) {
+      const int r = (tid >> 3) + 32 * i;
       const float4 x = t.v[i];
       float4 h, l;
       h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
@@ -206,18 +214,21 @@ __device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, int trans, c
       *reinterpret_cast<float4*>(lo + off) = l;
     }
   } else {
-    constexpr int F4_PER_K = ROWS / 4;
-    constexpr int K_PER_PASS = G_THREADS / F4_PER_K;
-    const int m4 = tid % F4_PER_K;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int kq = lane >> 3, m4 = lane & 7;
 #pragma unroll
-    for (int i = 0; i < ROWS / 16; ++i) {
-      const int k = tid / F4_PER_K + K_PER_PASS * i;
-      const float xs[4] = {t.v[i].x, t.v[i].y, t.v[i].z, t.v[i].w};
+    for (int i = 0; i < ROWS / 32; ++i) {
+      const int wt = warp + 8 * i;
+      const int k = (wt & 7) * 4 + kq;
+      const int rbase = (wt >> 3) * 32 + m4 * 4;
+      const float4 x = t.v[i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = m4 * 4 + j;
-        const float h = to_tf32(xs[j]);
-        const float l = to_tf32(xs[j] - h);
+      for (int s = 0; s < 4; ++s) {
+        const int j = (s + (m4 >> 1)) & 3;
+        const float xv = j == 0 ? x.x : (j == 1 ? x.y : (j == 2 ? x.z : x.w));
+        const int r = rbase + j;
+        const float h = to_tf32(xv);
+        const float l = to_tf32(xv - h);
         const int off = r * 128 + (((k >> 2) ^ (r & 7)) << 4) + (k & 3) * 4;
         *reinterpret_cast<float*>(hi + off) = h;
         *reinterpret_cast<float*>(lo + off) = l;
@@ -251,30 +262,35 @@ gemm_tf32x3_kernel(const GemmParams p) {
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_slot, BN);  // BN fp32 accumulator columns x 128 lanes
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_acc = tmem_base_slot;
 
   const bool vecA = (p.lda % 4 == 0) && aligned16(p.A);
   const bool vecB = (p.ldb % 4 == 0) && aligned16(p.B);
   constexpr uint32_t IDESC = umma_idesc(G_BM, BN);
 
-  TileRegs<G_BM> ra;
-  TileRegs<BN> rb;
-  if (num_kb > 0) {
-    load_tile<G_BM>(p.A, p.lda, p.transA, m0, p.M, kb_lo * G_BK, p.K, vecA, ra);
-    load_tile<BN>(p.B, p.ldb, !p.transB, n0, p.N, kb_lo * G_BK, p.K, vecB, rb);
-  }
-  for (int64_t kb = 0; kb < num_kb; ++kb) {
+  // two register sets: the global loads of k-blocks kb+1 and kb+2 are in flight while kb is
+  // split, stored and multiplied
+  TileRegs<G_BM> ra[2];
+  TileRegs<BN> rb[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    if (q < num_kb) {
+      load_tile<G_BM>(p.A, p.lda, p.transA, m0, p.M, (kb_lo + q) * G_BK, p.K, vecA, ra[q]);
+      load_tile<BN>(p.B, p.ldb, !p.transB, n0, p.N, (kb_lo + q) * G_BK, p.K, vecB, rb[q]);
+    }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_slot;
+
+  auto k_step = [&](int64_t kb, TileRegs<G_BM>& a, TileRegs<BN>& b) {
     const int s = (int)(kb % G_STAGES);
     char* st = smem + (size_t)s * STAGE_BYTES;
     if (kb >= G_STAGES) mbar_wait(&mma_done[s], (uint32_t)(((kb / G_STAGES) - 1) & 1));  // stage free?
-    store_tile<G_BM>(ra, p.transA, st, st + A_BYTES);
-    store_tile<BN>(rb, !p.transB, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES);
-    if (kb + 1 < num_kb) {  // next tile's global loads fly while this one is multiplied
-      load_tile<G_BM>(p.A, p.lda, p.transA, m0, p.M, (kb_lo + kb + 1) * G_BK, p.K, vecA, ra);
-      load_tile<BN>(p.B, p.ldb, !p.transB, n0, p.N, (kb_lo + kb + 1) * G_BK, p.K, vecB, rb);
+    store_tile<G_BM>(a, p.transA, st, st + A_BYTES);
+    store_tile<BN>(b, !p.transB, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES);
+    if (kb + 2 < num_kb) {
+      load_tile<G_BM>(p.A, p.lda, p.transA, m0, p.M, (kb_lo + kb + 2) * G_BK, p.K, vecA, a);
+      load_tile<BN>(p.B, p.ldb, !p.transB, n0, p.N, (kb_lo + kb + 2) * G_BK, p.K, vecB, b);
     }
     fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     tc_fence_before();
@@ -293,21 +309,38 @@ gemm_tf32x3_kernel(const GemmParams p) {
       umma_commit(&mma_done[s]);  // arrives when the MMAs that read this stage have finished
       if (kb == num_kb - 1) umma_commit(&acc_ready);
     }
+  };
+#pragma unroll 1
+  for (int64_t kb = 0; kb < num_kb; kb += 2) {
+    k_step(kb, ra[0], rb[0]);
+    if (kb + 1 < num_kb) k_step(kb + 1, ra[1], rb[1]);
   }
-  // ---- epilogue ----
-  if (num_kb > 0) mbar_wait(&acc_ready, 0);
-  tc_fence_after();
-  const int64_t m = m0 + warp * 32 + lane;  // TMEM lane = output row of the tile
+
+  // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (its rows), columns half (w >> 2) ----
+  constexpr int CW = BN / 2;             // columns per warp
+  const int64_t m = m0 + (warp & 3) * 32 + lane;
+  const int cbase = (warp >> 2) * CW;
   const bool splitk = p.partial != nullptr;
   float* drow = splitk ? p.partial + ((int64_t)blockIdx.z * p.M + m) * p.N : p.D + m * p.ldd;
   const int64_t ldd_eff = splitk ? p.N : p.ldd;
   const bool vecD = (ldd_eff % 4 == 0) && aligned16(splitk ? (const void*)p.partial : (const void*)p.D);
-  const bool vecC = p.Cin && (p.ldcin % 4 == 0) && aligned16(p.Cin);
-#pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  const bool use_cin = !splitk && p.Cin && p.beta != 0.f;
+  const bool vecC = use_cin && (p.ldcin % 4 == 0) && aligned16(p.Cin);
+  // Cin of this thread's row segment is fetched before waiting for the accumulator
+  float4 cin[CW / 4];
+#pragma unroll
+  for (int i = 0; i < CW / 4; ++i) {
+    const int64_t n = n0 + cbase + i * 4;
+    const int valid = (use_cin && m < p.M) ? (int)min((int64_t)4, p.N - n) : 0;
+    cin[i] = ldg4_guarded(p.Cin + m * p.ldcin + n, valid, vecC);
+  }
+  if (num_kb > 0) mbar_wait(&acc_ready, 0);
+  tc_fence_after();
+#pragma unroll
+  for (int c0 = 0; c0 < CW; c0 += 32) {
     float v[32];
     if (num_kb > 0) {
-      tmem_ld32(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld32(tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cbase + c0), v);
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -315,28 +348,26 @@ gemm_tf32x3_kernel(const GemmParams p) {
     if (m < p.M) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        const int64_t n = n0 + c0 + i;
-        if (n >= p.N) break;
-        float o[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
-        const int valid = (int)min((int64_t)4, p.N - n);
-        if (!splitk) {
-          float cin[4] = {0.f, 0.f, 0.f, 0.f};
-          if (p.Cin && p.beta != 0.f) {
-            const float4 t = ldg4_guarded(p.Cin + m * p.ldcin + n, valid, vecC);
-            cin[0] = t.x; cin[1] = t.y; cin[2] = t.z; cin[3] = t.w;
-          }
+        const int64_t n = n0 + cbase + c0 + i;
+        if (n < p.N) {
+          float o[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
+          const int valid = (int)min((int64_t)4, p.N - n);
+          if (!splitk) {
+            const float4 ci = cin[(c0 + i) / 4];
+            const float cv[4] = {ci.x, ci.y, ci.z, ci.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float x = p.alpha * o[j] + p.beta * cin[j];
-            if (p.bias && j < valid) x += __ldg(p.bias + n + j);
-            if (p.relu) x = fmaxf(x, 0.f);
-            o[j] = x;
+            for (int j = 0; j < 4; ++j) {
+              float x = p.alpha * o[j] + p.beta * cv[j];
+              if (p.bias && j < valid) x += __ldg(p.bias + n + j);
+              if (p.relu) x = fmaxf(x, 0.f);
+              o[j] = x;
+            }
           }
-        }
-        if (valid == 4 && vecD) {
-          *reinterpret_cast<float4*>(drow + n) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-          for (int j = 0; j < valid; ++j) drow[n + j] = o[j];
+          if (valid == 4 && vecD) {
+            *reinterpret_cast<float4*>(drow + n) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+            for (int j = 0; j < valid; ++j) drow[n + j] = o[j];
+          }
         }
       }
     }

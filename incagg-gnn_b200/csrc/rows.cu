@@ -61,6 +61,50 @@ index_rows_kernel(const char* __restrict__ src, int64_t src_ld, const int64_t* _
   }
 }
 
+// Row gather out of a table that is sharded by contiguous row ranges over up to 16 memories (the
+// history shards of all ranks: the local one and the peers' HBM mapped over NVLink through CUDA IPC).
+// dst[i] = shard[s][idx[i] - bounds[s]] with bounds[s] <= idx[i] < bounds[s+1]: the remote rows are
+// fetched by plain loads over NVLink inside the same kernel that packs them.
+constexpr int MAX_SHARDS = 16;
+struct ShardTable {
+  const char* base[MAX_SHARDS];
+  int64_t bounds[MAX_SHARDS + 1];
+  int n;
+};
+
+template <int VB>
+__global__ void __launch_bounds__(ROWS_THREADS)
+sharded_gather_kernel(const ShardTable tab, int64_t src_ld, const int64_t* __restrict__ idx, int64_t n,
+                      char* __restrict__ dst, int64_t dst_ld, int nvec) {
+  using V = typename Bytes<VB>::type;
+  const int64_t total = n * nvec;
+  const int64_t stride = (int64_t)gridDim.x * ROWS_THREADS;
+  int64_t t = (int64_t)blockIdx.x * ROWS_THREADS + threadIdx.x;
+  for (; t < total; t += stride * ROWS_UNROLL) {
+    V v[ROWS_UNROLL];
+    int64_t doff[ROWS_UNROLL];
+#pragma unroll
+    for (int u = 0; u < ROWS_UNROLL; ++u) {
+      const int64_t g = t + u * stride;
+      doff[u] = -1;
+      if (g < total) {
+        const int64_t r = g / nvec;
+        const int c = (int)(g - r * nvec);
+        const int64_t j = idx[r];
+        if (j >= tab.bounds[0] && j < tab.bounds[tab.n]) {
+          int s = 0;
+          while (j >= tab.bounds[s + 1]) ++s;
+          v[u] = *reinterpret_cast<const V*>(tab.base[s] + (j - tab.bounds[s]) * src_ld + (int64_t)c * VB);
+          doff[u] = r * dst_ld + (int64_t)c * VB;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS_UNROLL; ++u)
+      if (doff[u] >= 0) *reinterpret_cast<V*>(dst + doff[u]) = v[u];
+  }
+}
+
 constexpr int MAX_SLICES = 64;
 struct SliceTable {
   int64_t off[MAX_SLICES];          // row offset in the strided (history) tensor
@@ -168,6 +212,41 @@ extern "C" int incagg_gather_rows(const void* src, int64_t src_ld_bytes, int64_t
                                   int64_t row_bytes, incagg_stream_t stream) {
   return index_rows<0>(src, src_ld_bytes, idx, n, dst, dst_ld_bytes, row_bytes, src_rows,
                        as_stream(stream));
+}
+
+extern "C" int incagg_gather_rows_sharded(const void* const* shard_ptrs, const int64_t* bounds, int num_shards,
+                                          int64_t src_ld_bytes, const int64_t* idx, int64_t n, void* dst,
+                                          int64_t dst_ld_bytes, int64_t row_bytes, incagg_stream_t stream) {
+  IA_CHECK_ARG(num_shards >= 1 && num_shards <= MAX_SHARDS, "num_shards must be in [1, %d]", MAX_SHARDS);
+  IA_CHECK_ARG(n >= 0 && row_bytes >= 0, "negative size");
+  if (n == 0 || row_bytes == 0) return INCAGG_OK;
+  IA_CHECK_ARG(shard_ptrs && bounds && idx && dst, "NULL argument");
+  IA_CHECK_ARG(src_ld_bytes >= row_bytes && dst_ld_bytes >= row_bytes, "leading dimension smaller than a row");
+  ShardTable tab;
+  tab.n = num_shards;
+  int vb = 16;
+  for (int s = 0; s < num_shards; ++s) {
+    IA_CHECK_ARG(bounds[s] <= bounds[s + 1], "bounds must be non-decreasing");
+    IA_CHECK_ARG(shard_ptrs[s] != nullptr || bounds[s] == bounds[s + 1], "shard %d is NULL", s);
+    tab.base[s] = static_cast<const char*>(shard_ptrs[s]);
+    tab.bounds[s] = bounds[s];
+    if (shard_ptrs[s]) {
+      const int v = pick_vb(shard_ptrs[s], src_ld_bytes, dst, dst_ld_bytes, row_bytes);
+      if (v < vb) vb = v;
+    }
+  }
+  tab.bounds[num_shards] = bounds[num_shards];
+  const int64_t nvec64 = row_bytes / vb;
+  IA_CHECK_ARG(nvec64 <= 0x7fffffff, "row too wide");
+  const int nvec = (int)nvec64;
+  const int grid = grid_for(n * nvec64);
+  cudaStream_t st = as_stream(stream);
+  char* d = static_cast<char*>(dst);
+#define IA_SG(VB_) sharded_gather_kernel<VB_><<<grid, ROWS_THREADS, 0, st>>>(tab, src_ld_bytes, idx, n, d, dst_ld_bytes, nvec)
+  if (vb == 16) IA_SG(16); else if (vb == 8) IA_SG(8); else if (vb == 4) IA_SG(4); else if (vb == 2) IA_SG(2); else IA_SG(1);
+#undef IA_SG
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
 }
 
 extern "C" int incagg_scatter_rows(const void* src, int64_t src_ld_bytes, const int64_t* idx,

@@ -45,7 +45,7 @@ class SubgraphLoader:
     def __init__(self, data: Data, ptr: Tensor, batch_size: int = 1, bipartite: bool = True,
                  log: bool = True, num_neighbors=-1, type='eval', IB=False, shuffle: bool = False,
                  num_workers: int = 0, persistent_workers: bool = False, device=None,
-                 prefetch: bool = True, shard=None, **kwargs):
+                 prefetch: bool = True, shard=None, halo_plans: bool = False, **kwargs):
         self.data = data
         self.ptr = ptr.cpu()
         self.bipartite = bipartite
@@ -68,6 +68,7 @@ class SubgraphLoader:
         # multi-GPU: this rank iterates over the partitions it owns only (parallel.Shard); every rank
         # yields the same number of batches per epoch (wrapping around) so collectives stay matched
         self.shard = shard
+        self.halo_plans = halo_plans  # NCCL transport: exchange the halo-row plan of every batch
         if shard is not None:
             self._parts = [p for p in range(self.num_parts) if shard.lo <= int(self.ptr[p]) < shard.hi]
             assert all(int(self.ptr[p + 1]) <= shard.hi for p in self._parts), \
@@ -133,7 +134,7 @@ class SubgraphLoader:
     def _finish(self, rowptr, col, value, n_id, batch_size, offset, count) -> SubData:
         adj_t = SparseTensor(rowptr=rowptr, col=col, value=value,
                              sparse_sizes=(rowptr.numel() - 1, n_id.numel()), is_sorted=True)
-        if self.shard is not None and self.shard.world_size > 1:
+        if self.shard is not None and self.shard.world_size > 1 and self.halo_plans:
             from .parallel import HaloPlan
             n_id.halo_plan = HaloPlan(n_id[batch_size:], self.shard)
         data = self.data.__class__(adj_t=adj_t)

@@ -78,20 +78,47 @@ class ScalableGNN(torch.nn.Module):
         self.shard = None      # parallel.Shard when the history tables are sharded over ranks
         self._row_lo = 0       # first global row of this rank's shard
 
-    def shard_histories(self, shard) -> 'ScalableGNN':
+    def shard_histories(self, shard, transport: str = 'p2p') -> 'ScalableGNN':
         """Keep only this rank's rows ``[shard.lo, shard.hi)`` of every history table (HBM-resident
-        shards; multi-GPU design of DESIGN.md §6).  Halo rows owned by other ranks are then fetched
-        through ``parallel.pull_halo_rows``."""
+        shards; multi-GPU design of DESIGN.md §6).  Halo rows owned by other ranks are fetched
+          * ``transport='p2p'``  by the gather kernel itself, loading the peers' shards over NVLink
+            (tables mapped through CUDA IPC; no collective, no lockstep, capturable in CUDA graphs),
+          * ``transport='nccl'`` by an all-to-all-v of row ids and rows (``parallel.pull_halo_rows``).
+        Collective: every rank must call it."""
         if self.pool is not None or self.histories[0].emb.device.type != 'cuda':
             raise RuntimeError('sharded histories are HBM-resident (device="cuda"); the pinned-host '
                                'AsyncIOPool layout is single-GPU')
-        self.shard, self._row_lo = shard, shard.lo
+        assert transport in ('p2p', 'nccl')
+        self.shard, self._row_lo, self.transport = shard, shard.lo, transport
+        self._peer_views = {}
         for h in list(self.histories) + list(self.histories_ag):
             h.emb = torch.zeros(shard.num_local, h.embedding_dim, device=h.emb.device)
             h.num_embeddings = shard.num_local
             h.row_offset = shard.lo
+            if transport == 'p2p' and shard.world_size > 1:
+                from ..parallel import open_peer_views
+                self._peer_views[h.emb.data_ptr()] = open_peer_views(h.emb, shard)
+        self._shard_bounds = shard.node_bounds.tolist()
         self.__out = None
         return self
+
+    def _pull_rows(self, table: Tensor, idx: Tensor, n_id: Tensor, dst: Tensor) -> None:
+        """dst[j] = table_global[idx[j]] for halo ids `idx` (= n_id[B:]); `table` is this rank's
+        shard (or the whole table on one GPU)."""
+        if dst.size(0) == 0:
+            return
+        views = getattr(self, '_peer_views', {}).get(table.data_ptr()) if self.shard is not None else None
+        if views is not None:      # NVLink peer loads inside the gather kernel
+            ops.gather_rows_sharded(views, self._shard_bounds, idx.contiguous(), dst)
+            return
+        plan = getattr(n_id, 'halo_plan', None)
+        if plan is not None:       # NCCL all-to-all-v
+            from ..parallel import pull_halo_rows
+            pull_halo_rows(table, plan, dst)
+            return
+        if self._row_lo:
+            idx = idx - self._row_lo
+        ops.gather_rows(table, idx.contiguous(), out=dst)
 
     @property
     def emb_device(self):
@@ -223,14 +250,9 @@ class ScalableGNN(torch.nn.Module):
         if not self._async:  # synchronous branch = the semantic definition (base.py:411-426)
             history.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
             idx = n_id[batch_size:]
-            plan = getattr(n_id, 'halo_plan', None)
 
             def fill(dst):
-                if plan is not None:  # sharded tables: all-to-all-v of halo rows
-                    from ..parallel import pull_halo_rows
-                    pull_halo_rows(history.emb, plan, dst)
-                else:
-                    ops.gather_rows(history.emb, idx.to(dst.device), out=dst)
+                self._pull_rows(history.emb, idx, n_id, dst)
             return _PushPull.apply(x, fill, batch_size, n_tail), 0.
         pulled = self.pool.synchronize_pull()
 
@@ -300,12 +322,7 @@ class ScalableGNN(torch.nn.Module):
             return self.pool.synchronize_pull()[:n_id.numel()]
         out = torch.empty((n_id.numel(), table.size(1)), dtype=table.dtype, device=self.device)
         ops.copy_slices(table, out, offset - self._row_lo if self._row_lo else offset, count, 0)
-        plan = getattr(n_id, 'halo_plan', None)
-        if plan is not None:
-            from ..parallel import pull_halo_rows
-            pull_halo_rows(table, plan, out[batch_size:])
-        elif n_id.numel() > batch_size:
-            ops.gather_rows(table, n_id[batch_size:].contiguous(), out=out[batch_size:])
+        self._pull_rows(table, n_id[batch_size:], n_id, out[batch_size:])
         return out
 
     def _sweep_sync(self):
@@ -313,6 +330,12 @@ class ScalableGNN(torch.nn.Module):
             self.pool.synchronize_push()
         if self.pool_ag is not None:
             self.pool_ag.synchronize_push()
+        if self.shard is not None and self.shard.world_size > 1 and getattr(self, 'transport', '') == 'p2p':
+            # peers read this rank's rows directly: a layer phase must be complete on every rank before
+            # the next one starts (the NCCL transport gets this ordering from its collectives)
+            import torch.distributed as dist
+            torch.cuda.current_stream(self.device).synchronize()
+            dist.barrier(group=self.shard.group)
 
     @torch.no_grad()
     def mini_inference(self, loader, use_aggregation=True) -> Tensor:

@@ -242,6 +242,27 @@ def gather_rows(src: Tensor, idx: Tensor, out: Optional[Tensor] = None) -> Tenso
     return out
 
 
+def gather_rows_sharded(shards, bounds, idx: Tensor, out: Tensor) -> Tensor:
+    """out[i] = table[idx[i]] where the table is split by rows over `shards` (shard s holds global rows
+    [bounds[s], bounds[s+1])); shards may be peer-GPU memory mapped through CUDA IPC."""
+    import ctypes
+    _require_cuda(idx, out)
+    assert idx.dtype == torch.int64 and idx.is_contiguous()
+    W = len(shards)
+    ref = next(t for t in shards if t is not None and t.numel() > 0)
+    es = ref.element_size()
+    ld = ref.stride(0) * es if ref.dim() > 1 else es
+    row_bytes = (ref.size(1) if ref.dim() > 1 else 1) * es
+    d, d_ld, d_row_bytes, d_rows = _row_view(out)
+    assert d_row_bytes == row_bytes and d_rows >= idx.numel()
+    ptrs = (ctypes.c_void_p * W)(*[(t.data_ptr() if t is not None and t.numel() > 0 else None) for t in shards])
+    bnd = (ctypes.c_int64 * (W + 1))(*[int(b) for b in bounds])
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_gather_rows_sharded(ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(bnd, ctypes.c_void_p),
+                                         W, ld, ptr(idx), idx.numel(), ptr(d), d_ld, row_bytes, _stream()))
+    return out
+
+
 def scatter_rows(src: Tensor, idx: Tensor, dst: Tensor) -> None:
     """dst[idx[i]] = src[i].  dst: CUDA or pinned-host tensor."""
     if not _device_accessible(dst):

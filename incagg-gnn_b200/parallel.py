@@ -171,36 +171,60 @@ def idle_exchange(shard: Shard) -> None:
     raise NotImplementedError('ranks run the same number of steps (Shard.steps_per_epoch)')
 
 
+def open_peer_views(t: Tensor, shard: Shard):
+    """Map every rank's copy of a (differently sized) table into this process: returns one tensor per
+    rank (this rank's own tensor at its index).  The peers' storages are opened through CUDA IPC *in
+    this rank's device context*, so kernels running on this GPU can load the peers' HBM directly over
+    NVLink / NVSwitch.  Collective: every rank of the group must call it with its own table."""
+    W = shard.world_size
+    if W == 1:
+        return [t]
+    info = t.untyped_storage()._share_cuda_()
+    meta = (tuple(info), tuple(t.shape), tuple(t.stride()), t.storage_offset(), t.dtype)
+    gathered = [None] * W
+    dist.all_gather_object(gathered, meta, group=shard.group)
+    dev = t.device.index
+    views = []
+    for r in range(W):
+        if r == shard.rank:
+            views.append(t)
+            continue
+        inf, shape, stride, off, dtype = gathered[r]
+        st = torch.UntypedStorage._new_shared_cuda(dev, *inf[1:])
+        views.append(torch.empty(0, dtype=dtype, device=t.device).set_(st, off, shape, stride))
+    return views
+
+
 class GradAverager:
-    """One all_reduce per step over a flat view of the gradients."""
+    """Gradient averaging over the ranks with one all_reduce per step.  All gradients live in ONE flat
+    buffer (every ``p.grad`` is a view into it, the DDP bucket idea), so the step is
+    ``zero() -> backward (accumulates in place) -> all_reduce(flat) -> flat /= W`` without any packing
+    copies, and the buffer addresses are static (CUDA-graph friendly)."""
 
     def __init__(self, params, shard: Shard):
         self.params = [p for p in params if p.requires_grad]
         self.shard = shard
+        p0 = self.params[0]
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = None
+        self.flat = torch.zeros(self.numel, dtype=p0.dtype, device=p0.device)
+        o = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[o:o + n].view_as(p)
+            o += n
+
+    def zero(self):
+        """Instead of optimizer.zero_grad(): keeps the views in place."""
+        self.flat.zero_()
+
+    def all_reduce(self):
+        if self.shard.world_size > 1:
+            dist.all_reduce(self.flat, group=self.shard.group)
+
+    def scale(self):
+        if self.shard.world_size > 1:
+            self.flat.div_(self.shard.world_size)
 
     def __call__(self):
-        if self.shard.world_size == 1:
-            return
-        if self.flat is None:
-            p0 = self.params[0]
-            self.flat = torch.empty(self.numel, dtype=p0.dtype, device=p0.device)
-        o = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                self.flat[o:o + n].zero_()
-            else:
-                self.flat[o:o + n].copy_(p.grad.reshape(-1))
-            o += n
-        dist.all_reduce(self.flat, group=self.shard.group)
-        self.flat.div_(self.shard.world_size)
-        o = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                p.grad = self.flat[o:o + n].view_as(p).clone()
-            else:
-                p.grad.copy_(self.flat[o:o + n].view_as(p))
-            o += n
+        self.all_reduce()
+        self.scale()

@@ -99,9 +99,8 @@ def mini_train(model, loader, criterion, optimizer, max_steps, grad_norm=None, e
     return {'loss': tl / max(te, 1.), 'steps': steps}
 
 
-def train_step(model, sub, optimizer, VR_update=False, grad_norm=None, averager=None, epoch=0,
-               batch_idx=0):
-    """One iteration of the mini_train loop body on an already collated batch.  Returns
+def forward_backward(model, sub, optimizer, VR_update=False, averager=None, epoch=0, batch_idx=0):
+    """Forward + loss + backward of one mini_train iteration on an already collated batch.  Returns
     (loss * n_train, n_train) as device scalars (no host synchronisation)."""
     batch, batch_size, n_id, offset, count = sub
     x, adj_t = batch.x, batch.adj_t
@@ -110,7 +109,10 @@ def train_step(model, sub, optimizer, VR_update=False, grad_norm=None, averager=
         out = model.VR_call(x, adj_t, batch_size, n_id, offset, count, epoch=epoch, batch_idx=batch_idx)['out']
     else:
         out = model(x, adj_t, batch_size, n_id, offset, count)['out']
-    optimizer.zero_grad(set_to_none=True)
+    if averager is not None:
+        averager.zero()  # gradients are views into the averager's flat buffer
+    else:
+        optimizer.zero_grad(set_to_none=True)
     w = train_mask.to(out.dtype)
     n = w.sum()
     if y.dim() == 1:
@@ -120,18 +122,32 @@ def train_step(model, sub, optimizer, VR_update=False, grad_norm=None, averager=
             out, y.to(out.dtype), reduction='none').mean(dim=-1)
     loss = (per_row * w).sum() / n.clamp(min=1.)
     loss.backward()
-    if averager is not None:
-        averager()
-    if grad_norm is not None:
-        torch.nn.utils.clip_grad_norm_(model.parameters(), grad_norm)
-    optimizer.step()
     return loss.detach() * n, n
 
 
-class GraphedTrainer:
-    """Replays one CUDA graph per distinct batch (group of partitions).
+def apply_update(model, optimizer, grad_norm=None, averager=None):
+    """Second half of the iteration: (averaged) gradients -> clip -> optimizer step."""
+    if averager is not None:
+        averager.scale()
+    if grad_norm is not None:
+        torch.nn.utils.clip_grad_norm_(model.parameters(), grad_norm)
+    optimizer.step()
 
-    A training step is ~230 kernel launches of a few microseconds each, so issuing it from Python is
+
+def train_step(model, sub, optimizer, VR_update=False, grad_norm=None, averager=None, epoch=0,
+               batch_idx=0):
+    """One iteration of the mini_train loop body on an already collated batch."""
+    ln, n = forward_backward(model, sub, optimizer, VR_update, averager, epoch, batch_idx)
+    if averager is not None:
+        averager.all_reduce()
+    apply_update(model, optimizer, grad_norm, averager)
+    return ln, n
+
+
+class GraphedTrainer:
+    """Replays CUDA graphs of the training step, one per distinct batch (group of partitions).
+
+    A training step is ~200 kernel launches of a few microseconds each, so issuing it from Python is
     launch-bound.  With a fixed partition -> batch assignment (``batch_size`` partitions per step drawn
     from a fixed set of groups; C3 uses batch_size = 1, i.e. 150 distinct batches) every step of a given
     batch has the same kernel sequence and the same sizes: the whole step - GPU collate (relabel +
@@ -139,6 +155,11 @@ class GraphedTrainer:
     replayed every epoch.  Nothing is cached between replays: each replay runs every kernel again on
     the current weights and history tables.  All graphs share one memory pool (they are replayed one at
     a time).  Data-dependent sizes (halo counts) are read back once, before the capture.
+
+    Multi-GPU: the step is captured as two graphs around the NCCL gradient all-reduce, which is issued
+    eagerly between them (collate + forward + backward | all_reduce | scale + clip + Adam).  Halo rows
+    of other ranks are read by the captured gather kernels straight out of the peers' HBM (p2p
+    transport), so the graphs contain no collective.
     """
 
     def __init__(self, model, loader, optimizer, VR_update=False, grad_norm=None, averager=None):
@@ -151,10 +172,19 @@ class GraphedTrainer:
             if not g.get('capturable', False):
                 raise RuntimeError('GraphedTrainer needs an optimizer built with capturable=True')
 
-    def _body(self, ids):
+    def _body_a(self, ids):
         sub = self.loader._collate(list(ids))
-        ln, n = train_step(self.model, sub, self.optimizer, self.vr, self.grad_norm, self.averager)
+        ln, n = forward_backward(self.model, sub, self.optimizer, self.vr, self.averager)
         self.acc += torch.stack([ln.double(), n.double()])
+
+    def _body_b(self):
+        apply_update(self.model, self.optimizer, self.grad_norm, self.averager)
+
+    def _body(self, ids):
+        self._body_a(ids)
+        if self.averager is not None:
+            self.averager.all_reduce()
+        self._body_b()
 
     def warmup(self, ids, steps: int = 3):
         """Eager steps before the first capture (lazy optimizer state, cuBLAS workspaces, scratch)."""
@@ -181,10 +211,18 @@ class GraphedTrainer:
             self.loader._collate(list(ids))
         if self.pool is None:
             self.pool = torch.cuda.graph_pool_handle()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, pool=self.pool):
-            self._body(ids)
-        self.graphs[key] = g
+        if self.averager is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.pool):
+                self._body(ids)
+            self.graphs[key] = (g, None)
+        else:
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga, pool=self.pool):
+                self._body_a(ids)
+            with torch.cuda.graph(gb, pool=self.pool):
+                self._body_b()
+            self.graphs[key] = (ga, gb)
 
     MAX_GRAPHS = 4096
 
@@ -197,7 +235,10 @@ class GraphedTrainer:
                 return self._body(ids)
             self.capture(ids)
             g = self.graphs[key]
-        g.replay()
+        g[0].replay()
+        if g[1] is not None:
+            self.averager.all_reduce()  # NCCL, eager, between the two graphs
+            g[1].replay()
 
     def epoch(self, max_steps=None):
         """One epoch in the loader's (shuffled) batch order.  Returns the mean training loss."""
@@ -223,7 +264,7 @@ def mini_test(model, loader, use_aggregation=True, VR_update=False):
 def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_device='cuda',
           overrides: Optional[Dict[str, Any]] = None, log: bool = False, data_device=None,
           shuffle: bool = True, host_resident: bool = False, data=None, rank: int = 0,
-          world_size: int = 1):
+          world_size: int = 1, transport: str = 'p2p'):
     """Everything main.py:140-201 sets up for one named config on synthetic data: returns a dict
     with data, ptr, loaders, model, optimizer, criterion and the config."""
     conf = dict(CONFIGS[config])
@@ -256,9 +297,9 @@ def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_dev
         shard = Shard(ptr, rank, world_size)
     train_loader = SubgraphLoader(data, ptr, batch_size=conf['batch_size'], shuffle=shuffle,
                                   num_neighbors=-1, type='train', IB=conf['VR_update'], log=log,
-                                  device=device, shard=shard)
+                                  device=device, shard=shard, halo_plans=(transport == 'nccl'))
     eval_loader = EvalSubgraphLoader(data, ptr, batch_size=conf['batch_size'], log=log, device=device,
-                                     shard=shard)
+                                     shard=shard, halo_plans=(transport == 'nccl'))
     buffer_size = max(n_id.numel() for _, _, n_id, _, _ in eval_loader) * 2
     kwargs = {}
     if conf['model'][:3] == 'PNA':
@@ -268,7 +309,7 @@ def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_dev
                 pool_size=conf['pool_size'], buffer_size=buffer_size, device=history_device,
                 **conf['architecture'], **kwargs).to(device)
     if shard is not None:
-        model.shard_histories(shard)
+        model.shard_histories(shard, transport=transport)
     optimizer = torch.optim.Adam([
         dict(params=model.reg_modules.parameters(), weight_decay=conf['reg_weight_decay']),
         dict(params=model.nonreg_modules.parameters(), weight_decay=conf['nonreg_weight_decay']),

@@ -58,6 +58,10 @@ int64_t incagg_launch_count(void);
 /* SM count and compute capability of the current device. */
 int incagg_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Enable loads / stores from kernels of the current device to memory of `peer_device` (NVLink P2P;
+ * the history shards of other ranks are mapped through CUDA IPC by the host side).  Idempotent. */
+int incagg_enable_peer_access(int peer_device);
+
 /* ---- CSR SpMM -------------------------------------------------------- */
 /*
  * out[i, 0:F] = reduce_{e in [rowptr[i], rowptr[i+1])} val[e] * X[col[e], 0:F]
@@ -159,6 +163,16 @@ int incagg_csr_transpose(const int32_t* rowptr, const int32_t* col, const float*
 int incagg_gather_rows(const void* src, int64_t src_ld_bytes, int64_t src_rows, const int64_t* idx,
                        int64_t n, void* dst, int64_t dst_ld_bytes, int64_t row_bytes,
                        incagg_stream_t stream);
+/*
+ * The same gather out of a table that is sharded by contiguous row ranges over `num_shards` <= 16
+ * memories: shard s holds global rows [bounds[s], bounds[s+1]) at shard_ptrs[s] (host arrays).  Used
+ * for multi-GPU history pulls: the local shard plus the peers' HBM shards mapped into this process
+ * (CUDA IPC); remote rows are fetched by loads over NVLink inside the packing kernel.  Indices outside
+ * [bounds[0], bounds[num_shards]) are skipped.
+ */
+int incagg_gather_rows_sharded(const void* const* shard_ptrs, const int64_t* bounds, int num_shards,
+                               int64_t src_ld_bytes, const int64_t* idx, int64_t n, void* dst,
+                               int64_t dst_ld_bytes, int64_t row_bytes, incagg_stream_t stream);
 /* dst[idx[i], :] = src[i, :]  (History.push index branch, history.py:58). Out-of-range
  * indices are skipped and counted in *oob_count (device int32, nullable). */
 int incagg_scatter_rows(const void* src, int64_t src_ld_bytes, const int64_t* idx, int64_t n,

@@ -50,10 +50,14 @@ def _worker(rank, world, port, ret):
         # gradient averaging
         w = torch.nn.Parameter(torch.zeros(3, 2))
         b = torch.nn.Parameter(torch.zeros(5))
-        w.grad = torch.full((3, 2), float(rank + 1))
-        avg = GradAverager([w, b], shard)
+        avg = GradAverager([w, b], shard)          # p.grad become views into one flat buffer
+        assert w.grad.data_ptr() == avg.flat.data_ptr() and b.grad.numel() == 5
+        (w.sum() * float(rank + 1)).backward()     # autograd accumulates in place into the views
         avg()
         assert torch.allclose(w.grad, torch.full((3, 2), 1.5)) and torch.equal(b.grad, torch.zeros(5))
+        assert w.grad.data_ptr() == avg.flat.data_ptr()
+        avg.zero()
+        assert float(avg.flat.abs().sum()) == 0.
         assert shard.steps_per_epoch(1) == 5 and Shard(torch.arange(0, 8), 0, 2).steps_per_epoch(1) == 4
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover

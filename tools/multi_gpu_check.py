@@ -20,9 +20,11 @@ from incagg_gnn_b200.train import build, mini_test
 from incagg_gnn_b200.parallel import GradAverager
 
 ok = True
-for vr in (False, True):
+import itertools
+for transport, vr in itertools.product(("nccl", "p2p"), (False, True)):
     ov = dict(VR_update=vr, num_parts=12)
-    sharded = build("C3", device=dev, seed=0, scale=32, overrides=ov, rank=rank, world_size=world, shuffle=False)
+    sharded = build("C3", device=dev, seed=0, scale=32, overrides=ov, rank=rank, world_size=world, shuffle=False,
+                    transport=transport)
     single = build("C3", device=dev, seed=0, scale=32, overrides=ov, shuffle=False)
     single["model"].load_state_dict(sharded["model"].state_dict(), strict=False)
     # identical weights on all ranks
@@ -37,7 +39,7 @@ for vr in (False, True):
         same &= torch.equal(sharded["model"].histories[l].emb, single["model"].histories[l].emb[sh.lo:sh.hi])
         if vr:
             same &= torch.equal(sharded["model"].histories_ag[l].emb, single["model"].histories_ag[l].emb[sh.lo:sh.hi])
-    print(f"[rank {rank}] {'IncAgg' if vr else 'GAS'} sharded sweep == single-GPU sweep: {same}", flush=True)
+    print(f"[rank {rank}] {transport} {'IncAgg' if vr else 'GAS'} sharded sweep == single-GPU sweep: {same}", flush=True)
     ok &= same
     # one training epoch in lockstep
     model, opt = sharded["model"], sharded["optimizer"]
@@ -46,20 +48,38 @@ for vr in (False, True):
     tot = 0.0
     for batch, B, n_id, offset, count in sharded["train_loader"]:
         out = (model.VR_call if vr else model)(batch.x, batch.adj_t, B, n_id, offset, count)["out"]
-        opt.zero_grad(set_to_none=True)
         m = batch.train_mask[:B]
         loss = torch.nn.functional.cross_entropy(out[m], batch.y[:B][m])
+        avg.zero()
         loss.backward()
         avg()
         opt.step()
         tot += float(loss)
+    del loss, out  # a live autograd graph keeps grad accumulators bound to this (legacy) stream
     flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     ref = flat.clone()
     dist.broadcast(ref, 0)
     same_p = torch.equal(flat, ref)
     fin = bool(torch.isfinite(torch.tensor(tot)))
-    print(f"[rank {rank}] {'IncAgg' if vr else 'GAS'} epoch: loss sum {tot:.4f}, params identical across ranks: {same_p}", flush=True)
+    print(f"[rank {rank}] {transport} {'IncAgg' if vr else 'GAS'} epoch: loss sum {tot:.4f}, params identical across ranks: {same_p}", flush=True)
     ok &= same_p and fin
+    if transport == "p2p":
+        # CUDA-graph replays with the peer gathers and the NCCL gradient all-reduce captured
+        from incagg_gnn_b200.train import GraphedTrainer
+        tr = GraphedTrainer(model, sharded["train_loader"], opt, VR_update=vr, averager=avg)
+        tr.warmup(sharded["train_loader"]._batches_of_epoch()[0], steps=1)
+        r1 = tr.epoch()
+        r2 = tr.epoch()
+        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        same_g = torch.equal(flat, ref)
+        print(f"[rank {rank}] p2p {'IncAgg' if vr else 'GAS'} graphed epochs: losses {r1['loss']:.4f} {r2['loss']:.4f}, "
+              f"{len(tr.graphs)} graphs, params identical: {same_g}", flush=True)
+        ok &= same_g and r2['loss'] == r2['loss']
+    del sharded, single, model, opt
+    torch.cuda.synchronize()
+    dist.barrier()
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 dist.barrier()
