@@ -425,3 +425,22 @@ def test_async_io_pool_fifo(ops, cuda):
     pool.async_push(x, torch.tensor([100]), torch.tensor([20]), table)
     pool.synchronize_push()
     assert torch.equal(table[100:120], x.cpu())
+
+
+def test_gather_rows_sharded_matches_unsharded(ops, cuda):
+    """Row gather out of a table split by row ranges over several memories (the multi-GPU history
+    pull; here all shards live on one GPU): bit-exact with the gather out of the whole table."""
+    g = torch.Generator().manual_seed(8)
+    N, D = 1000, 96
+    table = torch.randn(N, D, generator=g).to(cuda)
+    bounds = [0, 130, 130, 700, 1000]                      # one empty shard
+    shards = [table[bounds[i]:bounds[i + 1]].clone() for i in range(4)]
+    idx = torch.randperm(N, generator=g)[:400].to(cuda)
+    out = torch.full((400, D), float("nan"), device=cuda)
+    ops.gather_rows_sharded(shards, bounds, idx, out)
+    assert torch.equal(out, table[idx])
+    # a window of the id space: ids outside [bounds[0], bounds[-1]) are skipped
+    out2 = torch.zeros(400, D, device=cuda)
+    ops.gather_rows_sharded(shards[2:], bounds[2:], idx, out2)
+    inside = (idx >= 130)
+    assert torch.equal(out2[inside], table[idx[inside]]) and float(out2[~inside].abs().max()) == 0.
