@@ -18,8 +18,10 @@
 //     expects (16-byte chunk index XOR row-in-atom).  All four source layouts (A as [M,K] or [K,M],
 //     B as [N,K] or [K,N], row-major) are handled by the loader, which transposes on the way in, so
 //     forward (x·W^T), input-gradient (g·W) and weight-gradient (x^T·g) GEMMs are the same kernel;
-//   * the global loads of tiles k+1 and k+2 are in flight (two register sets) while tile k is split,
-//     stored and multiplied;
+//   * the global loads of tile k+1 are in flight (registers) while tile k is split, stored and
+//     multiplied; the four layout combinations are separate template instances and the ragged-edge
+//     loader is out of line, because the kernel body runs once per CTA and instruction fetch of a
+//     large straight-line body was the first bottleneck found (ncu: 55 % of stalls "no instruction");
 //   * a 3-stage ring of smem tiles: thread 0 issues the 12 MMAs of a stage and commits them to the
 //     stage's mbarrier (tcgen05.commit), which frees the stage for the loader;
 //   * epilogue: 8 warps, each tcgen05.ld's 32 lanes x BN/2 columns; Cin is fetched before the
@@ -143,18 +145,18 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 
 // ---- tile loader ----------------------------------------------------------------------------------
-// A tile is ROWS "output" rows (m or n) x 32 k.  `trans` = the source is contiguous along the output
+// A tile is ROWS "output" rows (m or n) x 32 k.  TRANS = the source is contiguous along the output
 // dimension ([K, rows] row-major) instead of along k ([rows, K]).  Each of the 256 threads owns
-// ROWS/32 float4 of a tile.
+// ROWS/32 float4 of a tile.  (The source layouts are template parameters and the ragged-edge loader is
+// kept out of line: the kernel body is executed once per CTA, so its size in instructions matters.)
 template <int ROWS>
 struct TileRegs {
   float4 v[ROWS / 32];
 };
 
-__device__ __forceinline__ float4 ldg4_guarded(const float* p, int valid, bool vec_ok) {
-  // valid = number of in-range elements starting at p (<= 0: none)
+__device__ __noinline__ float4 ldg4_guarded(const float* p, int valid) {
+  // valid = number of in-range elements starting at p (<= 0: none); no alignment assumed
   float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (valid >= 4 && vec_ok) return __ldg(reinterpret_cast<const float4*>(p));
   if (valid > 0) r.x = __ldg(p);
   if (valid > 1) r.y = __ldg(p + 1);
   if (valid > 2) r.z = __ldg(p + 2);
@@ -163,44 +165,60 @@ __device__ __forceinline__ float4 ldg4_guarded(const float* p, int valid, bool v
 }
 
 // Thread -> element mapping.
-//   !trans: chunk c = tid & 7 (16 bytes of the 128-byte k-row), row r = (tid >> 3) + 32 i.  A quarter
+//   !TRANS: chunk c = tid & 7 (16 bytes of the 128-byte k-row), row r = (tid >> 3) + 32 i.  A quarter
 //           warp writes the 8 chunks of one row: the XOR swizzle keeps them on distinct banks.
-//   trans : a warp owns a 4 (k) x 32 (rows) patch: kq = lane >> 3, m4 = lane & 7 -> one float4 along
+//   TRANS : a warp owns a 4 (k) x 32 (rows) patch: kq = lane >> 3, m4 = lane & 7 -> one float4 along
 //           the rows; patch index wt = warp + 8 i, k-group = wt & 7, row-group = wt >> 3.  The four
 //           elements of a float4 go to four different tile rows; element j = (t + (m4 >> 1)) & 3 is
 //           written in store instruction t, which spreads the 32 lanes over all 32 banks.
-template <int ROWS>
-__device__ __forceinline__ void load_tile(const float* __restrict__ src, int64_t ld, int trans, int64_t row0,
+template <int ROWS, bool TRANS>
+__device__ __forceinline__ void load_tile(const float* __restrict__ src, int64_t ld, int64_t row0,
                                           int64_t rows_total, int64_t k0, int64_t k_end, bool vec_ok,
                                           TileRegs<ROWS>& t) {
   const int tid = threadIdx.x;
-  if (!trans) {
+  // whole tile in range and 16-byte aligned: plain vector loads (uniform branch)
+  const bool fast = vec_ok && (row0 + ROWS <= rows_total) && (k0 + G_BK <= k_end);
+  if constexpr (!TRANS) {
     const int64_t k = k0 + (tid & 7) * 4;
+    const float* base = src + (row0 + (tid >> 3)) * ld + k;
+    if (fast) {
 #pragma unroll
-    for (int i = 0; i < ROWS / 32; ++i) {
-      const int64_t r = row0 + (tid >> 3) + 32 * i;
-      const int valid = (r < rows_total) ? (int)min((int64_t)4, k_end - k) : 0;
-      t.v[i] = ldg4_guarded(src + r * ld + k, valid, vec_ok);
+      for (int i = 0; i < ROWS / 32; ++i) t.v[i] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(32 * i) * ld));
+    } else {
+#pragma unroll
+      for (int i = 0; i < ROWS / 32; ++i) {
+        const int64_t r = row0 + (tid >> 3) + 32 * i;
+        const int valid = (r < rows_total) ? (int)min((int64_t)4, k_end - k) : 0;
+        t.v[i] = ldg4_guarded(base + (int64_t)(32 * i) * ld, valid);
+      }
     }
   } else {
     const int lane = tid & 31, warp = tid >> 5;
     const int kq = lane >> 3, m4 = lane & 7;
+    if (fast) {
 #pragma unroll
-    for (int i = 0; i < ROWS / 32; ++i) {
-      const int wt = warp + 8 * i;
-      const int64_t k = k0 + (wt & 7) * 4 + kq;
-      const int64_t r = row0 + (wt >> 3) * 32 + m4 * 4;
-      const int valid = (k < k_end) ? (int)min((int64_t)4, rows_total - r) : 0;
-      t.v[i] = ldg4_guarded(src + k * ld + r, valid, vec_ok);
+      for (int i = 0; i < ROWS / 32; ++i) {
+        const int wt = warp + 8 * i;
+        t.v[i] = __ldg(reinterpret_cast<const float4*>(src + (k0 + (wt & 7) * 4 + kq) * ld + row0 + (wt >> 3) * 32 + m4 * 4));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < ROWS / 32; ++i) {
+        const int wt = warp + 8 * i;
+        const int64_t k = k0 + (wt & 7) * 4 + kq;
+        const int64_t r = row0 + (wt >> 3) * 32 + m4 * 4;
+        const int valid = (k < k_end) ? (int)min((int64_t)4, rows_total - r) : 0;
+        t.v[i] = ldg4_guarded(src + k * ld + r, valid);
+      }
     }
   }
 }
 
 // Split into hi / lo TF32 parts and store into the two swizzled K-major tiles.
-template <int ROWS>
-__device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, int trans, char* hi, char* lo) {
+template <int ROWS, bool TRANS>
+__device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, char* hi, char* lo) {
   const int tid = threadIdx.x;
-  if (!trans) {
+  if constexpr (!TRANS) {
     const int c = tid & 7;
 #pragma unroll
     for (int i = 0; i < ROWS / 32; ++i) {
@@ -237,7 +255,9 @@ __device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, int trans, c
   }
 }
 
-template <int BN>
+// TA: A is stored [K, M] (contiguous along m).  TBK: B is stored [K, N] (contiguous along n), i.e.
+// transB == 0 of the C ABI; both make the loader transpose on the way into shared memory.
+template <int BN, bool TA, bool TBK>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tf32x3_kernel(const GemmParams p) {
   extern __shared__ __align__(1024) char smem_raw[];
@@ -249,12 +269,13 @@ gemm_tf32x3_kernel(const GemmParams p) {
   __shared__ uint64_t acc_ready;
   __shared__ uint32_t tmem_base_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const int64_t m0 = (int64_t)blockIdx.x * G_BM, n0 = (int64_t)blockIdx.y * BN;
   const int64_t num_kb_total = (p.K + G_BK - 1) / G_BK;
   const int64_t kb_lo = (int64_t)blockIdx.z * p.kb_per_split;
   const int64_t kb_hi = min(num_kb_total, kb_lo + p.kb_per_split);
-  const int64_t num_kb = kb_hi - kb_lo;
+  const int num_kb = (int)(kb_hi - kb_lo);
 
   if (tid == 0) {
     for (int s = 0; s < G_STAGES; ++s) mbar_init(&mma_done[s], 1);
@@ -267,53 +288,51 @@ gemm_tf32x3_kernel(const GemmParams p) {
   const bool vecB = (p.ldb % 4 == 0) && aligned16(p.B);
   constexpr uint32_t IDESC = umma_idesc(G_BM, BN);
 
-  // two register sets: the global loads of k-blocks kb+1 and kb+2 are in flight while kb is
-  // split, stored and multiplied
-  TileRegs<G_BM> ra[2];
-  TileRegs<BN> rb[2];
-#pragma unroll
-  for (int q = 0; q < 2; ++q)
-    if (q < num_kb) {
-      load_tile<G_BM>(p.A, p.lda, p.transA, m0, p.M, (kb_lo + q) * G_BK, p.K, vecA, ra[q]);
-      load_tile<BN>(p.B, p.ldb, !p.transB, n0, p.N, (kb_lo + q) * G_BK, p.K, vecB, rb[q]);
-    }
+  // the global loads of k-block kb+1 are in flight while kb is split, stored and multiplied
+  TileRegs<G_BM> ra;
+  TileRegs<BN> rb;
+  if (num_kb > 0) {
+    load_tile<G_BM, TA>(p.A, p.lda, m0, p.M, kb_lo * G_BK, p.K, vecA, ra);
+    load_tile<BN, TBK>(p.B, p.ldb, n0, p.N, kb_lo * G_BK, p.K, vecB, rb);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_slot;
 
-  auto k_step = [&](int64_t kb, TileRegs<G_BM>& a, TileRegs<BN>& b) {
-    const int s = (int)(kb % G_STAGES);
+#pragma unroll 1
+  for (int kb = 0; kb < num_kb; ++kb) {
+    const int s = kb % G_STAGES;
     char* st = smem + (size_t)s * STAGE_BYTES;
     if (kb >= G_STAGES) mbar_wait(&mma_done[s], (uint32_t)(((kb / G_STAGES) - 1) & 1));  // stage free?
-    store_tile<G_BM>(a, p.transA, st, st + A_BYTES);
-    store_tile<BN>(b, !p.transB, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES);
-    if (kb + 2 < num_kb) {
-      load_tile<G_BM>(p.A, p.lda, p.transA, m0, p.M, (kb_lo + kb + 2) * G_BK, p.K, vecA, a);
-      load_tile<BN>(p.B, p.ldb, !p.transB, n0, p.N, (kb_lo + kb + 2) * G_BK, p.K, vecB, b);
+    store_tile<G_BM, TA>(ra, st, st + A_BYTES);
+    store_tile<BN, TBK>(rb, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES);
+    if (kb + 1 < num_kb) {
+      load_tile<G_BM, TA>(p.A, p.lda, m0, p.M, (kb_lo + kb + 1) * G_BK, p.K, vecA, ra);
+      load_tile<BN, TBK>(p.B, p.ldb, n0, p.N, (kb_lo + kb + 1) * G_BK, p.K, vecB, rb);
     }
     fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_BYTES;
-      const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+    if (warp == 0) {
+      if (lane == 0) {
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+        const uint64_t d_ahi = umma_desc(a_hi), d_alo = umma_desc(a_lo);
+        const uint64_t d_bhi = umma_desc(b_hi), d_blo = umma_desc(b_lo);
 #pragma unroll
-      for (int k = 0; k < G_BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte row
-        const uint32_t ko = k * 32;
-        umma_tf32(tmem_acc, umma_desc(a_lo + ko), umma_desc(b_hi + ko), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
-        umma_tf32(tmem_acc, umma_desc(a_hi + ko), umma_desc(b_lo + ko), IDESC, 1u);
-        umma_tf32(tmem_acc, umma_desc(a_hi + ko), umma_desc(b_hi + ko), IDESC, 1u);
+        for (int k = 0; k < G_BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes: start address += 32 >> 4
+          const uint64_t ko = (uint64_t)(k * 2);
+          umma_tf32(tmem_acc, d_alo + ko, d_bhi + ko, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_tf32(tmem_acc, d_ahi + ko, d_blo + ko, IDESC, 1u);
+          umma_tf32(tmem_acc, d_ahi + ko, d_bhi + ko, IDESC, 1u);
+        }
+        umma_commit(&mma_done[s]);  // arrives when the MMAs that read this stage have finished
+        if (kb == num_kb - 1) umma_commit(&acc_ready);
       }
-      umma_commit(&mma_done[s]);  // arrives when the MMAs that read this stage have finished
-      if (kb == num_kb - 1) umma_commit(&acc_ready);
+      __syncwarp();
     }
-  };
-#pragma unroll 1
-  for (int64_t kb = 0; kb < num_kb; kb += 2) {
-    k_step(kb, ra[0], rb[0]);
-    if (kb + 1 < num_kb) k_step(kb + 1, ra[1], rb[1]);
   }
 
   // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (its rows), columns half (w >> 2) ----
@@ -326,16 +345,28 @@ gemm_tf32x3_kernel(const GemmParams p) {
   const bool vecD = (ldd_eff % 4 == 0) && aligned16(splitk ? (const void*)p.partial : (const void*)p.D);
   const bool use_cin = !splitk && p.Cin && p.beta != 0.f;
   const bool vecC = use_cin && (p.ldcin % 4 == 0) && aligned16(p.Cin);
+  const bool full_n = (n0 + BN <= p.N);
   // Cin of this thread's row segment is fetched before waiting for the accumulator
   float4 cin[CW / 4];
+  if (use_cin && m < p.M) {
+    const float* cp = p.Cin + m * p.ldcin + n0 + cbase;
+    if (vecC && full_n) {
 #pragma unroll
-  for (int i = 0; i < CW / 4; ++i) {
-    const int64_t n = n0 + cbase + i * 4;
-    const int valid = (use_cin && m < p.M) ? (int)min((int64_t)4, p.N - n) : 0;
-    cin[i] = ldg4_guarded(p.Cin + m * p.ldcin + n, valid, vecC);
+      for (int i = 0; i < CW / 4; ++i) cin[i] = __ldg(reinterpret_cast<const float4*>(cp + i * 4));
+    } else {
+#pragma unroll
+      for (int i = 0; i < CW / 4; ++i)
+        cin[i] = ldg4_guarded(cp + i * 4, (int)min((int64_t)4, p.N - (n0 + cbase + i * 4)));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) cin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (num_kb > 0) mbar_wait(&acc_ready, 0);
   tc_fence_after();
+  const float alpha = p.alpha, beta = splitk ? 0.f : p.beta;
+  const bool do_relu = !splitk && p.relu;
+  const float* bias = splitk ? nullptr : p.bias;
 #pragma unroll
   for (int c0 = 0; c0 < CW; c0 += 32) {
     float v[32];
@@ -349,25 +380,33 @@ gemm_tf32x3_kernel(const GemmParams p) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         const int64_t n = n0 + cbase + c0 + i;
-        if (n < p.N) {
-          float o[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
-          const int valid = (int)min((int64_t)4, p.N - n);
-          if (!splitk) {
-            const float4 ci = cin[(c0 + i) / 4];
-            const float cv[4] = {ci.x, ci.y, ci.z, ci.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float x = p.alpha * o[j] + p.beta * cv[j];
-              if (p.bias && j < valid) x += __ldg(p.bias + n + j);
-              if (p.relu) x = fmaxf(x, 0.f);
-              o[j] = x;
+        const float4 ci = cin[(c0 + i) / 4];
+        float o[4];
+        if (splitk) {
+          o[0] = v[i]; o[1] = v[i + 1]; o[2] = v[i + 2]; o[3] = v[i + 3];
+        } else {
+          o[0] = alpha * v[i] + beta * ci.x;
+          o[1] = alpha * v[i + 1] + beta * ci.y;
+          o[2] = alpha * v[i + 2] + beta * ci.z;
+          o[3] = alpha * v[i + 3] + beta * ci.w;
+        }
+        if (full_n && vecD) {
+          if (bias) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+            o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
+          }
+          if (do_relu) {
+            o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f);
+          }
+          *reinterpret_cast<float4*>(drow + n) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+          for (int j = 0; j < 4; ++j)
+            if (n + j < p.N) {
+              float x = o[j];
+              if (bias) x += __ldg(bias + n + j);
+              if (do_relu) x = fmaxf(x, 0.f);
+              drow[n + j] = x;
             }
-          }
-          if (valid == 4 && vecD) {
-            *reinterpret_cast<float4*>(drow + n) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-            for (int j = 0; j < valid; ++j) drow[n + j] = o[j];
-          }
         }
       }
     }
@@ -393,19 +432,26 @@ __global__ void gemm_splitk_reduce_kernel(const GemmParams p, int splits) {
   }
 }
 
-template <int BN>
-static int launch_gemm(const GemmParams& p, int splits, cudaStream_t st) {
+template <int BN, bool TA, bool TBK>
+static int launch_gemm_t(const GemmParams& p, int splits, cudaStream_t st) {
   constexpr int STAGE_BYTES = 2 * G_BM * 128 + 2 * BN * 128;
   constexpr int SMEM = G_STAGES * STAGE_BYTES + 1024;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    IA_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    IA_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, TA, TBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
   dim3 grid((unsigned)((p.M + G_BM - 1) / G_BM), (unsigned)((p.N + BN - 1) / BN), (unsigned)splits);
-  gemm_tf32x3_kernel<BN><<<grid, G_THREADS, SMEM, st>>>(p);
+  gemm_tf32x3_kernel<BN, TA, TBK><<<grid, G_THREADS, SMEM, st>>>(p);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
+}
+
+template <int BN>
+static int launch_gemm(const GemmParams& p, int splits, cudaStream_t st) {
+  const bool ta = p.transA != 0, tbk = p.transB == 0;
+  if (ta) return tbk ? launch_gemm_t<BN, true, true>(p, splits, st) : launch_gemm_t<BN, true, false>(p, splits, st);
+  return tbk ? launch_gemm_t<BN, false, true>(p, splits, st) : launch_gemm_t<BN, false, false>(p, splits, st);
 }
 
 }  // namespace incagg
