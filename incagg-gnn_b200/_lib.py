@@ -54,6 +54,10 @@ _PROTOS = {
     "incagg_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "incagg_gemm_tf32x3": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, P, c_int64, P, c_int64, c_float, P,
                                    c_int64, c_float, P, c_int, P, c_int64, P, c_size_t, P]),
+    "incagg_gemm_tf32x3_dual": (c_int, [c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, P, c_int64, P,
+                                        c_int64, P, c_int64, P, c_int64, c_float, c_float, c_float, c_float,
+                                        P, c_int64, c_float, P, c_int64, c_float, c_int, P, c_int64, P, c_int64,
+                                        P, c_size_t, P]),
     "incagg_csr_transpose_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "incagg_csr_transpose": (c_int, [P, P, P, c_int64, c_int64, c_int64, P, P, P, P, P, c_size_t, P]),
     "incagg_gather_rows": (c_int, [P, c_int64, c_int64, P, c_int64, P, c_int64, c_int64, P]),

@@ -37,17 +37,30 @@ constexpr int G_BK = 32;     // 32 tf32 = 128 bytes = one swizzle row
 constexpr int G_STAGES = 3;
 constexpr int G_THREADS = 256;
 
+enum { DUAL_NONE = 0, DUAL_K = 1, DUAL_N = 2, DUAL_M = 3 };
+
 struct GemmParams {
   const float* A; int64_t lda; int transA;   // transA = 0: A is [M,K] row-major; 1: stored [K,M]
   const float* B; int64_t ldb; int transB;   // transB = 0: B is [K,N] row-major; 1: stored [N,K]
   const float* Cin; int64_t ldcin;
   const float* bias;
   float* D; int64_t ldd;
-  float* partial;                            // split-K partial sums [splits][M][N] (NULL if 1 split)
+  float* partial;                            // split-K partial sums [splits][Mpad][N] (NULL if 1 split)
   int64_t M, N, K;
   float alpha, beta;
   int relu;
   int kb_per_split;                          // k-blocks handled by one blockIdx.z
+  // second operand set (fused GCNII layer GEMMs, see incagg_gemm_tf32x3_dual)
+  int dual;
+  const float* A2; int64_t lda2;             // DUAL_K / DUAL_M
+  const float* B2; int64_t ldb2;             // DUAL_K / DUAL_N
+  const float* Cin2; int64_t ldcin2; float beta2;   // DUAL_K: D += beta2 * Cin2; DUAL_N: Cin/beta of set 2
+  float* D2; int64_t ldd2; float alpha2;     // DUAL_N / DUAL_M
+  float scaleB, scaleB2;                     // B (B2) is multiplied by this before the hi/lo split
+  int kb1;                                   // DUAL_K: k-blocks of the first segment (K = K1 + K2)
+  int64_t K2;
+  int tiles1;                                // DUAL_N / DUAL_M: tiles (y resp. x) of the first set
+  int64_t Mpad;                              // rows of one split-K partial slab
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -216,14 +229,15 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ src, int64_t
 
 // Split into hi / lo TF32 parts and store into the two swizzled K-major tiles.
 template <int ROWS, bool TRANS>
-__device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, char* hi, char* lo) {
+__device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, char* hi, char* lo, float scale = 1.f) {
   const int tid = threadIdx.x;
   if constexpr (!TRANS) {
     const int c = tid & 7;
 #pragma unroll
     for (int i = 0; i < ROWS / 32; ++i) {
       const int r = (tid >> 3) + 32 * i;
-      const float4 x = t.v[i];
+      float4 x = t.v[i];
+      x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
       float4 h, l;
       h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
       l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
@@ -243,7 +257,7 @@ __device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, char* hi, ch
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         const int j = (s + (m4 >> 1)) & 3;
-        const float xv = j == 0 ? x.x : (j == 1 ? x.y : (j == 2 ? x.z : x.w));
+        const float xv = (j == 0 ? x.x : (j == 1 ? x.y : (j == 2 ? x.z : x.w))) * scale;
         const int r = rbase + j;
         const float h = to_tf32(xv);
         const float l = to_tf32(xv - h);
@@ -271,8 +285,22 @@ gemm_tf32x3_kernel(const GemmParams p) {
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
-  const int64_t m0 = (int64_t)blockIdx.x * G_BM, n0 = (int64_t)blockIdx.y * BN;
-  const int64_t num_kb_total = (p.K + G_BK - 1) / G_BK;
+  // operand set of this CTA (uniform): DUAL_N switches B / D / Cin by n-tile, DUAL_M switches A / D by m-tile
+  const float* Aptr = p.A; int64_t lda = p.lda; int64_t Mrows = p.M;
+  const float* Bptr = p.B; int64_t ldb = p.ldb;
+  const float* Cin = p.Cin; int64_t ldcin = p.ldcin;
+  float* Dptr = p.D; int64_t ldd = p.ldd;
+  float alpha_e = p.alpha, beta_e = p.beta, scaleB = p.scaleB;
+  int bx = blockIdx.x, by = blockIdx.y;
+  if (p.dual == DUAL_N && by >= p.tiles1) {
+    by -= p.tiles1; Bptr = p.B2; ldb = p.ldb2; Dptr = p.D2; ldd = p.ldd2; alpha_e = p.alpha2; beta_e = p.beta2;
+    Cin = p.Cin2; ldcin = p.ldcin2; scaleB = p.scaleB2;
+  }
+  if (p.dual == DUAL_M && bx >= p.tiles1) {
+    bx -= p.tiles1; Aptr = p.A2; lda = p.lda2; Dptr = p.D2; ldd = p.ldd2; alpha_e = p.alpha2;
+  }
+  const int64_t m0 = (int64_t)bx * G_BM, n0 = (int64_t)by * BN;
+  const int64_t num_kb_total = (p.dual == DUAL_K) ? (p.kb1 + (p.K2 + G_BK - 1) / G_BK) : (p.K + G_BK - 1) / G_BK;
   const int64_t kb_lo = (int64_t)blockIdx.z * p.kb_per_split;
   const int64_t kb_hi = min(num_kb_total, kb_lo + p.kb_per_split);
   const int num_kb = (int)(kb_hi - kb_lo);
@@ -284,17 +312,26 @@ gemm_tf32x3_kernel(const GemmParams p) {
   }
   if (warp == 0) tmem_alloc(&tmem_base_slot, BN);  // BN fp32 accumulator columns x 128 lanes
 
-  const bool vecA = (p.lda % 4 == 0) && aligned16(p.A);
-  const bool vecB = (p.ldb % 4 == 0) && aligned16(p.B);
+  const bool vecA = (lda % 4 == 0) && aligned16(Aptr) &&
+                    (p.dual != DUAL_K || ((p.lda2 % 4 == 0) && aligned16(p.A2)));
+  const bool vecB = (ldb % 4 == 0) && aligned16(Bptr) &&
+                    (p.dual != DUAL_K || ((p.ldb2 % 4 == 0) && aligned16(p.B2)));
   constexpr uint32_t IDESC = umma_idesc(G_BM, BN);
 
+  // k-block -> operand segment (DUAL_K: the first kb1 blocks read (A, B), the rest (A2, B2))
+  auto load_kb = [&](int64_t kbg, TileRegs<G_BM>& a, TileRegs<BN>& b) {
+    if (p.dual == DUAL_K && kbg >= p.kb1) {
+      load_tile<G_BM, TA>(p.A2, p.lda2, m0, Mrows, (kbg - p.kb1) * G_BK, p.K2, vecA, a);
+      load_tile<BN, TBK>(p.B2, p.ldb2, n0, p.N, (kbg - p.kb1) * G_BK, p.K2, vecB, b);
+    } else {
+      load_tile<G_BM, TA>(Aptr, lda, m0, Mrows, kbg * G_BK, p.K, vecA, a);
+      load_tile<BN, TBK>(Bptr, ldb, n0, p.N, kbg * G_BK, p.K, vecB, b);
+    }
+  };
   // the global loads of k-block kb+1 are in flight while kb is split, stored and multiplied
   TileRegs<G_BM> ra;
   TileRegs<BN> rb;
-  if (num_kb > 0) {
-    load_tile<G_BM, TA>(p.A, p.lda, m0, p.M, kb_lo * G_BK, p.K, vecA, ra);
-    load_tile<BN, TBK>(p.B, p.ldb, n0, p.N, kb_lo * G_BK, p.K, vecB, rb);
-  }
+  if (num_kb > 0) load_kb(kb_lo, ra, rb);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -306,11 +343,9 @@ gemm_tf32x3_kernel(const GemmParams p) {
     char* st = smem + (size_t)s * STAGE_BYTES;
     if (kb >= G_STAGES) mbar_wait(&mma_done[s], (uint32_t)(((kb / G_STAGES) - 1) & 1));  // stage free?
     store_tile<G_BM, TA>(ra, st, st + A_BYTES);
-    store_tile<BN, TBK>(rb, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES);
-    if (kb + 1 < num_kb) {
-      load_tile<G_BM, TA>(p.A, p.lda, m0, p.M, (kb_lo + kb + 1) * G_BK, p.K, vecA, ra);
-      load_tile<BN, TBK>(p.B, p.ldb, n0, p.N, (kb_lo + kb + 1) * G_BK, p.K, vecB, rb);
-    }
+    store_tile<BN, TBK>(rb, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES,
+                        (p.dual == DUAL_K && kb_lo + kb >= p.kb1) ? p.scaleB2 : scaleB);
+    if (kb + 1 < num_kb) load_kb(kb_lo + kb + 1, ra, rb);
     fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     tc_fence_before();
     __syncthreads();
@@ -340,31 +375,41 @@ gemm_tf32x3_kernel(const GemmParams p) {
   const int64_t m = m0 + (warp & 3) * 32 + lane;
   const int cbase = (warp >> 2) * CW;
   const bool splitk = p.partial != nullptr;
-  float* drow = splitk ? p.partial + ((int64_t)blockIdx.z * p.M + m) * p.N : p.D + m * p.ldd;
-  const int64_t ldd_eff = splitk ? p.N : p.ldd;
-  const bool vecD = (ldd_eff % 4 == 0) && aligned16(splitk ? (const void*)p.partial : (const void*)p.D);
-  const bool use_cin = !splitk && p.Cin && p.beta != 0.f;
-  const bool vecC = use_cin && (p.ldcin % 4 == 0) && aligned16(p.Cin);
+  // split-K partial slab row: the global m-tile index (blockIdx.x), so DUAL_M sets do not collide
+  float* drow = splitk ? p.partial + ((int64_t)blockIdx.z * p.Mpad + (int64_t)blockIdx.x * G_BM + (warp & 3) * 32 + lane) * p.N
+                       : Dptr + m * ldd;
+  const int64_t ldd_eff = splitk ? p.N : ldd;
+  const bool vecD = (ldd_eff % 4 == 0) && aligned16(splitk ? (const void*)p.partial : (const void*)Dptr);
+  const bool use_cin = !splitk && Cin && beta_e != 0.f;
+  const bool vecC = use_cin && (ldcin % 4 == 0) && aligned16(Cin);
   const bool full_n = (n0 + BN <= p.N);
   // Cin of this thread's row segment is fetched before waiting for the accumulator
+  // (pre-scaled by beta; DUAL_K adds beta2 * Cin2)
   float4 cin[CW / 4];
-  if (use_cin && m < p.M) {
-    const float* cp = p.Cin + m * p.ldcin + n0 + cbase;
-    if (vecC && full_n) {
 #pragma unroll
-      for (int i = 0; i < CW / 4; ++i) cin[i] = __ldg(reinterpret_cast<const float4*>(cp + i * 4));
-    } else {
+  for (int i = 0; i < CW / 4; ++i) cin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (use_cin && m < Mrows) {
+    const float* cp = Cin + m * ldcin + n0 + cbase;
 #pragma unroll
-      for (int i = 0; i < CW / 4; ++i)
-        cin[i] = ldg4_guarded(cp + i * 4, (int)min((int64_t)4, p.N - (n0 + cbase + i * 4)));
+    for (int i = 0; i < CW / 4; ++i) {
+      const float4 t = (vecC && full_n) ? __ldg(reinterpret_cast<const float4*>(cp + i * 4))
+                                        : ldg4_guarded(cp + i * 4, (int)min((int64_t)4, p.N - (n0 + cbase + i * 4)));
+      cin[i] = make_float4(beta_e * t.x, beta_e * t.y, beta_e * t.z, beta_e * t.w);
     }
-  } else {
+  }
+  if (!splitk && p.dual == DUAL_K && p.Cin2 && p.beta2 != 0.f && m < Mrows) {
+    const float* cp = p.Cin2 + m * p.ldcin2 + n0 + cbase;
+    const bool v2 = (p.ldcin2 % 4 == 0) && aligned16(p.Cin2) && full_n;
 #pragma unroll
-    for (int i = 0; i < CW / 4; ++i) cin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < CW / 4; ++i) {
+      const float4 t = v2 ? __ldg(reinterpret_cast<const float4*>(cp + i * 4))
+                          : ldg4_guarded(cp + i * 4, (int)min((int64_t)4, p.N - (n0 + cbase + i * 4)));
+      cin[i].x += p.beta2 * t.x; cin[i].y += p.beta2 * t.y; cin[i].z += p.beta2 * t.z; cin[i].w += p.beta2 * t.w;
+    }
   }
   if (num_kb > 0) mbar_wait(&acc_ready, 0);
   tc_fence_after();
-  const float alpha = p.alpha, beta = splitk ? 0.f : p.beta;
+  const float alpha = alpha_e;
   const bool do_relu = !splitk && p.relu;
   const float* bias = splitk ? nullptr : p.bias;
 #pragma unroll
@@ -376,7 +421,7 @@ gemm_tf32x3_kernel(const GemmParams p) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = 0.f;
     }
-    if (m < p.M) {
+    if (m < Mrows) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         const int64_t n = n0 + cbase + c0 + i;
@@ -385,10 +430,10 @@ gemm_tf32x3_kernel(const GemmParams p) {
         if (splitk) {
           o[0] = v[i]; o[1] = v[i + 1]; o[2] = v[i + 2]; o[3] = v[i + 3];
         } else {
-          o[0] = alpha * v[i] + beta * ci.x;
-          o[1] = alpha * v[i + 1] + beta * ci.y;
-          o[2] = alpha * v[i + 2] + beta * ci.z;
-          o[3] = alpha * v[i + 3] + beta * ci.w;
+          o[0] = alpha * v[i] + ci.x;
+          o[1] = alpha * v[i + 1] + ci.y;
+          o[2] = alpha * v[i + 2] + ci.z;
+          o[3] = alpha * v[i + 3] + ci.w;
         }
         if (full_n && vecD) {
           if (bias) {
@@ -417,18 +462,29 @@ gemm_tf32x3_kernel(const GemmParams p) {
 }
 
 // D = alpha * sum_z partial[z] + beta * Cin + bias (+ReLU): fixed summation order -> deterministic.
+// Partial slabs are [Mpad][N] with Mpad = gridDim.x * 128 rows; for DUAL_M the rows of the second
+// output start at tiles1 * 128.
 __global__ void gemm_splitk_reduce_kernel(const GemmParams p, int splits) {
-  const int64_t total = p.M * p.N;
+  const int64_t sets = (p.dual == DUAL_M) ? 2 : 1;
+  const int64_t total = sets * p.M * p.N;
+  const int64_t slab = p.Mpad * p.N;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = i / p.N, n = i - m * p.N;
+    const int64_t set = i / (p.M * p.N);
+    const int64_t j = i - set * p.M * p.N;
+    const int64_t m = j / p.N, n = j - m * p.N;
+    const int64_t prow = m + (set ? (int64_t)p.tiles1 * G_BM : 0);
     float acc = 0.f;
-    for (int z = 0; z < splits; ++z) acc += p.partial[(int64_t)z * total + i];
-    float x = p.alpha * acc;
-    if (p.Cin && p.beta != 0.f) x += p.beta * p.Cin[m * p.ldcin + n];
-    if (p.bias) x += p.bias[n];
-    if (p.relu) x = fmaxf(x, 0.f);
-    p.D[m * p.ldd + n] = x;
+    for (int z = 0; z < splits; ++z) acc += p.partial[(int64_t)z * slab + prow * p.N + n];
+    if (set == 0) {
+      float x = p.alpha * acc;
+      if (p.Cin && p.beta != 0.f) x += p.beta * p.Cin[m * p.ldcin + n];
+      if (p.bias) x += p.bias[n];
+      if (p.relu) x = fmaxf(x, 0.f);
+      p.D[m * p.ldd + n] = x;
+    } else {
+      p.D2[m * p.ldd2 + n] = p.alpha2 * acc;
+    }
   }
 }
 
@@ -441,7 +497,10 @@ static int launch_gemm_t(const GemmParams& p, int splits, cudaStream_t st) {
     IA_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, TA, TBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  dim3 grid((unsigned)((p.M + G_BM - 1) / G_BM), (unsigned)((p.N + BN - 1) / BN), (unsigned)splits);
+  unsigned gx = (unsigned)((p.M + G_BM - 1) / G_BM), gy = (unsigned)((p.N + BN - 1) / BN);
+  if (p.dual == DUAL_M) gx *= 2;
+  if (p.dual == DUAL_N) gy *= 2;
+  dim3 grid(gx, gy, (unsigned)splits);
   gemm_tf32x3_kernel<BN, TA, TBK><<<grid, G_THREADS, SMEM, st>>>(p);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
@@ -454,14 +513,50 @@ static int launch_gemm(const GemmParams& p, int splits, cudaStream_t st) {
   return tbk ? launch_gemm_t<BN, false, true>(p, splits, st) : launch_gemm_t<BN, false, false>(p, splits, st);
 }
 
+static int run_gemm(GemmParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int bn = (p.N <= 64) ? 64 : 128;
+  const int64_t mt = (p.M + G_BM - 1) / G_BM, nt = (p.N + bn - 1) / bn;
+  p.tiles1 = (int)(p.dual == DUAL_N ? nt : mt);
+  const int64_t gx = mt * (p.dual == DUAL_M ? 2 : 1), gy = nt * (p.dual == DUAL_N ? 2 : 1);
+  p.Mpad = gx * G_BM;
+  if (p.dual == DUAL_K) p.kb1 = (int)((p.K + G_BK - 1) / G_BK);
+  const int64_t num_kb = (p.K + G_BK - 1) / G_BK + (p.dual == DUAL_K ? (p.K2 + G_BK - 1) / G_BK : 0);
+  // split-K when the output has few tiles and the reduction is long (weight gradients)
+  const int64_t tiles = gx * gy;
+  int splits = 1;
+  if (num_kb >= 16 && tiles < sm_count() && p.dual != DUAL_K && p.dual != DUAL_N) {
+    int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+    if (want > num_kb / 4) want = num_kb / 4;
+    if (want > 128) want = 128;
+    if (want > 1 && workspace != nullptr &&
+        workspace_bytes >= sizeof(float) * (size_t)p.Mpad * (size_t)p.N * (size_t)want)
+      splits = (int)want;
+  }
+  p.kb_per_split = (int)((num_kb + splits - 1) / splits);
+  if (p.kb_per_split < 1) p.kb_per_split = 1;
+  splits = (int)((num_kb + p.kb_per_split - 1) / p.kb_per_split);
+  if (splits < 1) splits = 1;
+  p.partial = splits > 1 ? static_cast<float*>(workspace) : nullptr;
+  int rc = (bn == 64) ? launch_gemm<64>(p, splits, st) : launch_gemm<128>(p, splits, st);
+  if (rc != INCAGG_OK) return rc;
+  if (splits > 1) {
+    const int64_t total = p.M * p.N * (p.dual == DUAL_M ? 2 : 1);
+    const int blocks = (int)((total + 255) / 256 < (int64_t)sm_count() * 8 ? (total + 255) / 256 : (int64_t)sm_count() * 8);
+    gemm_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p, splits);
+    IA_LAUNCH_CHECK();
+  }
+  return INCAGG_OK;
+}
+
 }  // namespace incagg
 
 using namespace incagg;
 
 extern "C" size_t incagg_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  // split-K partials; the split count never exceeds 128
-  return sizeof(float) * (size_t)M * (size_t)N * 128;
+  // split-K partials (rows padded to the 128-row tile, two output sets at most, <= 128 splits)
+  const size_t mpad = (size_t)((M + G_BM - 1) / G_BM) * G_BM * 2;
+  return sizeof(float) * mpad * (size_t)N * 128;
 }
 
 extern "C" int incagg_gemm_tf32x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A,
@@ -475,36 +570,33 @@ extern "C" int incagg_gemm_tf32x3(int transA, int transB, int64_t M, int64_t N, 
   IA_CHECK_ARG(K == 0 || (A != nullptr && B != nullptr), "NULL operand");
   IA_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldd >= N, "leading dimension too small");
   IA_CHECK_ARG(Cin == nullptr || ldcin >= N, "ldcin too small");
-  IA_CHECK_ARG((M + G_BM - 1) / G_BM <= 0x7fffffff, "M too large");
+  IA_CHECK_ARG((M + G_BM - 1) / G_BM <= 0x3fffffff, "M too large");
   GemmParams p{};
   p.A = A; p.lda = lda; p.transA = transA; p.B = B; p.ldb = ldb; p.transB = transB;
   p.Cin = Cin; p.ldcin = ldcin; p.bias = bias; p.D = D; p.ldd = ldd; p.M = M; p.N = N; p.K = K;
-  p.alpha = alpha; p.beta = beta; p.relu = relu;
-  const int64_t num_kb = (K + G_BK - 1) / G_BK;
-  // split-K when the output has few tiles and the reduction is long (weight gradients)
-  const int64_t tiles = ((M + G_BM - 1) / G_BM) * ((N + (N <= 64 ? 63 : 127)) / (N <= 64 ? 64 : 128));
-  int splits = 1;
-  if (num_kb >= 16 && tiles < sm_count()) {
-    int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
-    if (want > num_kb / 4) want = num_kb / 4;
-    if (want > 128) want = 128;
-    if (want > 1 && workspace != nullptr &&
-        workspace_bytes >= sizeof(float) * (size_t)M * (size_t)N * (size_t)want)
-      splits = (int)want;
-  }
-  p.kb_per_split = (int)((num_kb + splits - 1) / splits);
-  if (p.kb_per_split < 1) p.kb_per_split = 1;
-  splits = (int)((num_kb + p.kb_per_split - 1) / p.kb_per_split);
-  if (splits < 1) splits = 1;
-  p.partial = splits > 1 ? static_cast<float*>(workspace) : nullptr;
-  cudaStream_t st = as_stream(stream);
-  int rc = (N <= 64) ? launch_gemm<64>(p, splits, st) : launch_gemm<128>(p, splits, st);
-  if (rc != INCAGG_OK) return rc;
-  if (splits > 1) {
-    const int64_t total = M * N;
-    const int blocks = (int)((total + 255) / 256 < (int64_t)sm_count() * 8 ? (total + 255) / 256 : (int64_t)sm_count() * 8);
-    gemm_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p, splits);
-    IA_LAUNCH_CHECK();
-  }
-  return INCAGG_OK;
+  p.alpha = alpha; p.beta = beta; p.relu = relu; p.scaleB = 1.f; p.scaleB2 = 1.f; p.dual = DUAL_NONE;
+  return run_gemm(p, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int incagg_gemm_tf32x3_dual(int mode, int transA, int transB, int64_t M, int64_t N, int64_t K,
+                                       int64_t K2, const float* A, int64_t lda, const float* A2, int64_t lda2,
+                                       const float* B, int64_t ldb, const float* B2, int64_t ldb2,
+                                       float alpha, float alpha2, float scaleB, float scaleB2,
+                                       const float* Cin, int64_t ldcin, float beta, const float* Cin2,
+                                       int64_t ldcin2, float beta2, int relu, float* D, int64_t ldd,
+                                       float* D2, int64_t ldd2, void* workspace, size_t workspace_bytes,
+                                       incagg_stream_t stream) {
+  IA_CHECK_ARG(mode >= DUAL_K && mode <= DUAL_M, "mode must be 1 (K), 2 (N) or 3 (M)");
+  IA_CHECK_ARG(M > 0 && N > 0 && K > 0, "empty problem");
+  IA_CHECK_ARG(A && B && D, "NULL operand");
+  IA_CHECK_ARG(mode != DUAL_K || (A2 && B2 && K2 > 0), "K-concatenation needs A2, B2, K2");
+  IA_CHECK_ARG(mode != DUAL_N || (B2 && D2), "N-concatenation needs B2, D2");
+  IA_CHECK_ARG(mode != DUAL_M || (A2 && D2), "M-concatenation needs A2, D2");
+  GemmParams p{};
+  p.A = A; p.lda = lda; p.transA = transA; p.B = B; p.ldb = ldb; p.transB = transB;
+  p.A2 = A2; p.lda2 = lda2; p.B2 = B2; p.ldb2 = ldb2;
+  p.Cin = Cin; p.ldcin = ldcin; p.beta = beta; p.Cin2 = Cin2; p.ldcin2 = ldcin2; p.beta2 = beta2;
+  p.D = D; p.ldd = ldd; p.D2 = D2; p.ldd2 = ldd2; p.M = M; p.N = N; p.K = K; p.K2 = K2;
+  p.alpha = alpha; p.alpha2 = alpha2; p.scaleB = scaleB; p.scaleB2 = scaleB2; p.relu = relu; p.dual = mode;
+  return run_gemm(p, workspace, workspace_bytes, as_stream(stream));
 }

@@ -36,7 +36,7 @@ class _LinearTC(torch.autograd.Function):
         x, weight, y = ctx.saved_tensors
         g = g.contiguous()
         if ctx.relu:
-            g = g * (y > 0)
+            g = torch.ops.aten.threshold_backward(g, y, 0.)  # ReLU backward, one kernel
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = ops.gemm(g, weight)                      # [M,N] x [N,K]
@@ -65,19 +65,25 @@ class _GCN2Dense(torch.autograd.Function):
     """The dense half of GCN2Conv after the propagation, fused around the tensor-core GEMM:
         s   = (1-a) h + a x0
         out = (1-b) s + b ((1-a) h W1 + a x0 W2)          (W2 = W1 when weights are shared)
-    forward: one lerp + two GEMMs with alpha / beta / Cin (/ ReLU) epilogues instead of ~10 elementwise
-    and addmm launches; backward: four GEMMs whose epilogues produce the input gradients directly."""
+    Unshared weights (the reference's products config):
+      forward  ONE launch: K-concatenated GEMM  [h | x0] · [c1 W1 ; c2 W2]  with the  (1-b)s  term and the
+               ReLU in the epilogue (h and x0 are the Cin operands);
+      backward TWO launches (+ one split-K reduce): N-concatenated  g · [c1 W1^T | c2 W2^T]  whose
+               epilogues add the  (1-b)(1-a) g  /  (1-b) a g  terms -> dh, dx0;  M-concatenated
+               [h | x0]^T · g -> dW1, dW2.
+    (The reference path issues ~10 elementwise / addmm launches forward and ~20 backward here.)"""
 
     @staticmethod
     def forward(ctx, h, x0, w1, w2, a, b, relu):
-        s = torch.lerp(h, x0, a)
         if w2 is None:
+            s = torch.lerp(h, x0, a)
             out = ops.gemm(s, w1, alpha=b, cin=s, beta=1. - b, relu=relu)
+            ctx.save_for_backward(h, x0, w1, w2, out if relu else None, s)
         else:
-            out = ops.gemm(h, w1, alpha=b * (1. - a), cin=s, beta=1. - b)
-            out = ops.gemm(x0, w2, alpha=b * a, cin=out, beta=1., relu=relu, out=out)
+            out = ops.gemm_dual("k", h, w1, x0, w2, scale_b=b * (1. - a), scale_b2=b * a,
+                                cin=h, beta=(1. - b) * (1. - a), cin2=x0, beta2=(1. - b) * a, relu=relu)
+            ctx.save_for_backward(h, x0, w1, w2, out if relu else None, None)
         ctx.a, ctx.b, ctx.relu, ctx.shared = a, b, relu, w2 is None
-        ctx.save_for_backward(h, x0, w1, w2, out if relu else None, s if w2 is None else None)
         return out
 
     @staticmethod
@@ -86,7 +92,7 @@ class _GCN2Dense(torch.autograd.Function):
         a, b = ctx.a, ctx.b
         g = g.contiguous()
         if ctx.relu:
-            g = g * (out > 0)
+            g = torch.ops.aten.threshold_backward(g, out, 0.)  # ReLU backward, one kernel
         gh = gx0 = gw1 = gw2 = None
         if ctx.shared:
             # out = (1-b) s + b s W1 ;  ds = (1-b) g + b g W1^T ; dh = (1-a) ds ; dx0 = a ds
@@ -94,12 +100,9 @@ class _GCN2Dense(torch.autograd.Function):
             gh, gx0 = (1. - a) * ds, a * ds
             gw1 = ops.gemm(s, g, trans_a=True, alpha=b)
         else:
-            if ctx.needs_input_grad[0]:
-                gh = ops.gemm(g, w1, trans_b=True, alpha=b * (1. - a), cin=g, beta=(1. - b) * (1. - a))
-            if ctx.needs_input_grad[1]:
-                gx0 = ops.gemm(g, w2, trans_b=True, alpha=b * a, cin=g, beta=(1. - b) * a)
-            gw1 = ops.gemm(h, g, trans_a=True, alpha=b * (1. - a))
-            gw2 = ops.gemm(x0, g, trans_a=True, alpha=b * a)
+            gh, gx0 = ops.gemm_dual("n", g, w1, b2=w2, trans_b=True, scale_b=b * (1. - a), scale_b2=b * a,
+                                    cin=g, beta=(1. - b) * (1. - a), cin2=g, beta2=(1. - b) * a)
+            gw1, gw2 = ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a)
         return gh, gx0, gw1, gw2, None, None, None
 
 

@@ -205,6 +205,46 @@ def gemm(a: Tensor, b: Tensor, trans_a: bool = False, trans_b: bool = False, alp
     return out
 
 
+def gemm_dual(mode: str, a: Tensor, b: Tensor, a2: Optional[Tensor] = None, b2: Optional[Tensor] = None,
+              trans_a: bool = False, trans_b: bool = False, alpha: float = 1.0, alpha2: float = 1.0,
+              scale_b: float = 1.0, scale_b2: float = 1.0, cin: Optional[Tensor] = None, beta: float = 0.0,
+              cin2: Optional[Tensor] = None, beta2: float = 0.0, relu: bool = False,
+              out: Optional[Tensor] = None, out2: Optional[Tensor] = None):
+    """Two GEMMs sharing an operand in one launch (include/incagg_b200.h, incagg_gemm_tf32x3_dual):
+    mode 'k': out = alpha (a @ (scale_b b) + a2 @ (scale_b2 b2)) + beta cin + beta2 cin2
+    mode 'n': out = alpha a @ (scale_b b) + beta cin ; out2 = alpha2 a @ (scale_b2 b2) + beta2 cin2
+    mode 'm': out = alpha op(a) @ b ; out2 = alpha2 op(a2) @ b      (split-K)."""
+    code = {"k": 1, "n": 2, "m": 3}[mode]
+    a, b = _rowmajor(a), _rowmajor(b)
+    a2 = _rowmajor(a2) if a2 is not None else None
+    b2 = _rowmajor(b2) if b2 is not None else None
+    M, K = (a.size(1), a.size(0)) if trans_a else (a.size(0), a.size(1))
+    N = b.size(0) if trans_b else b.size(1)
+    K2 = 0
+    if mode == "k":
+        K2 = a2.size(0) if trans_a else a2.size(1)
+    dev = a.device
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    if mode in ("n", "m") and out2 is None:
+        out2 = torch.empty((M, N), dtype=torch.float32, device=dev)
+    cin = _rowmajor(cin) if cin is not None else None
+    cin2 = _rowmajor(cin2) if cin2 is not None else None
+    ws, ws_bytes = None, 0
+    if mode == "m":
+        ws_bytes = min(lib.incagg_gemm_workspace_bytes(M, N, K), 1 << 28)
+        ws = _gemm_workspace(dev, ws_bytes)
+        ws_bytes = ws.numel()
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_gemm_tf32x3_dual(
+        code, int(trans_a), int(trans_b), M, N, K, K2, ptr(a), _ld(a), ptr(a2), _ld(a2) if a2 is not None else 0,
+        ptr(b), _ld(b), ptr(b2), _ld(b2) if b2 is not None else 0, float(alpha), float(alpha2), float(scale_b),
+        float(scale_b2), ptr(cin), _ld(cin) if cin is not None else 0, float(beta), ptr(cin2),
+        _ld(cin2) if cin2 is not None else 0, float(beta2), int(relu), ptr(out), _ld(out), ptr(out2),
+        _ld(out2) if out2 is not None else 0, ptr(ws), ws_bytes, _stream()))
+    return (out, out2) if mode in ("n", "m") else out
+
+
 # --------------------------------------------------------------------------------------------
 # rows: gather / scatter / slices
 # --------------------------------------------------------------------------------------------

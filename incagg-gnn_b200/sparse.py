@@ -242,7 +242,10 @@ def _transposed_product(adj: SparseTensor, grad_out: Tensor, n_src: int, grad_ro
     t_plan = adj.t_plan()
     if grad_rows is None or grad_rows >= n_src:
         return ops.spmm_raw(t_rowptr, t_col, t_val, grad_out, "sum", rows=n_src, plan=t_plan)
-    gx = torch.zeros((n_src, grad_out.size(1)), dtype=grad_out.dtype, device=grad_out.device)
+    # Rows >= grad_rows of x are constants (history rows placed there by push_and_pull, whose
+    # backward reads only the first `grad_rows` rows of this gradient): they are neither computed nor
+    # zero-filled (a [B+H, F] fill per layer per step otherwise).
+    gx = torch.empty((n_src, grad_out.size(1)), dtype=grad_out.dtype, device=grad_out.device)
     ops.spmm_raw(t_rowptr, t_col, t_val, grad_out, "sum", rows=grad_rows, out=gx[:grad_rows],
                  plan=adj.t_plan_prefix(grad_rows))
     return gx

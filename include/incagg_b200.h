@@ -137,6 +137,25 @@ int incagg_gemm_tf32x3(int transA, int transB, int64_t M, int64_t N, int64_t K, 
                        int64_t ldcin, float beta, const float* bias, int relu, float* D, int64_t ldd,
                        void* workspace, size_t workspace_bytes, incagg_stream_t stream);
 
+/*
+ * Two GEMMs that share an operand in ONE launch (the dense half of a GCNII layer, reference
+ * GCN2Conv: out = (1-b)((1-a)h + a x0) + b((1-a) h W1 + a x0 W2), and its gradients):
+ *   mode 1 (K-concatenation)  D  = alpha * (A·(scaleB B) + A2·(scaleB2 B2)) + beta Cin + beta2 Cin2
+ *                             A [M,K], A2 [M,K2]: forward  [h | x0] · [c1 W1 ; c2 W2]
+ *   mode 2 (N-concatenation)  D  = alpha  * A·(scaleB  B ) + beta  Cin
+ *                             D2 = alpha2 * A·(scaleB2 B2) + beta2 Cin2   (shared A): input gradients
+ *   mode 3 (M-concatenation)  D  = alpha  * op(A )·B ,  D2 = alpha2 * op(A2)·B   (shared B; split-K with
+ *                             the workspace): weight gradients  [h | x0]^T · g
+ * Same layout flags, accuracy and epilogue rules as incagg_gemm_tf32x3; M2 = M, N2 = N.
+ */
+int incagg_gemm_tf32x3_dual(int mode, int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t K2,
+                            const float* A, int64_t lda, const float* A2, int64_t lda2, const float* B,
+                            int64_t ldb, const float* B2, int64_t ldb2, float alpha, float alpha2,
+                            float scaleB, float scaleB2, const float* Cin, int64_t ldcin, float beta,
+                            const float* Cin2, int64_t ldcin2, float beta2, int relu, float* D, int64_t ldd,
+                            float* D2, int64_t ldd2, void* workspace, size_t workspace_bytes,
+                            incagg_stream_t stream);
+
 /* ---- CSR transpose (CSC view for the backward SpMM) ------------------- */
 /*
  * Counting-sort transpose of a [rows x cols] CSR with nnz entries.

@@ -225,6 +225,33 @@ def test_gemm_epilogue_and_views(ops, cuda):
     assert float(dst[:, :128].abs().max()) == 0.
 
 
+def test_gemm_dual_modes(ops, cuda):
+    """K- / N- / M-concatenated GEMMs (the fused GCNII layer) against fp64."""
+    g = torch.Generator().manual_seed(12)
+    M, C = 700, 128
+    h = torch.randn(M, C, generator=g).to(cuda)
+    x0 = torch.randn(M, C, generator=g).to(cuda)
+    w1 = torch.randn(C, C, generator=g).to(cuda)
+    w2 = torch.randn(C, C, generator=g).to(cuda)
+    gr = torch.randn(M, C, generator=g).to(cuda)
+    c1, c2, e1, e2 = 0.45, 0.05, 0.54, 0.06
+    d = lambda t: t.double()
+    rel = lambda o, r: float((d(o) - r).abs().max() / r.abs().max())
+    out = ops.gemm_dual("k", h, w1, x0, w2, scale_b=c1, scale_b2=c2, cin=h, beta=e1, cin2=x0, beta2=e2, relu=True)
+    ref = torch.relu(c1 * d(h) @ d(w1) + c2 * d(x0) @ d(w2) + e1 * d(h) + e2 * d(x0))
+    assert rel(out, ref) <= RTOL
+    gh, gx0 = ops.gemm_dual("n", gr, w1, b2=w2, trans_b=True, scale_b=c1, scale_b2=c2, cin=gr, beta=e1, cin2=gr, beta2=e2)
+    assert rel(gh, c1 * d(gr) @ d(w1).t() + e1 * d(gr)) <= RTOL
+    assert rel(gx0, c2 * d(gr) @ d(w2).t() + e2 * d(gr)) <= RTOL
+    for rows in (700, 20000):   # without and with split-K
+        hh = torch.randn(rows, C, generator=g).to(cuda)
+        xx = torch.randn(rows, C, generator=g).to(cuda)
+        gg = torch.randn(rows, C, generator=g).to(cuda)
+        gw1, gw2 = ops.gemm_dual("m", hh, gg, a2=xx, trans_a=True, alpha=c1, alpha2=c2)
+        assert rel(gw1, c1 * d(hh).t() @ d(gg)) <= RTOL
+        assert rel(gw2, c2 * d(xx).t() @ d(gg)) <= RTOL
+
+
 # ---- transpose --------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(50, 70, 6, 0, 0), (300, 40, 40, 0, 0), (64, 20, 4, 2, 40000)])
 def test_csr_transpose_is_bit_exact_and_ordered(ops, cuda, shape):
