@@ -68,6 +68,8 @@ __device__ __forceinline__ int warp_bitonic_sort(int v) {
   return v;
 }
 
+constexpr int MED_SORT = 1024;  // segments of 33 .. 1024 entries: small CTAs, 4 KB static smem
+
 __global__ void __launch_bounds__(TR_THREADS)
 sort_segments_kernel(const int32_t* __restrict__ t_rowptr, int64_t cols, int32_t* t_perm,
                      int32_t* __restrict__ long_rows, int32_t* long_count, int long_capacity) {
@@ -83,9 +85,15 @@ sort_segments_kernel(const int32_t* __restrict__ t_rowptr, int64_t cols, int32_t
     if (lane < L) t_perm[s + lane] = v;
     return;
   }
+  // two lists sharing one array: medium segments grow from the front, big ones from the back
   if (lane == 0) {
-    const int slot = atomicAdd(long_count, 1);
-    if (slot < long_capacity) long_rows[slot] = (int32_t)c;
+    if (L <= MED_SORT) {
+      const int slot = atomicAdd(long_count, 1);
+      long_rows[slot] = (int32_t)c;
+    } else {
+      const int slot = atomicAdd(long_count + 1, 1);
+      long_rows[long_capacity - 1 - slot] = (int32_t)c;
+    }
   }
 }
 
@@ -99,7 +107,7 @@ template <typename Get, typename Put>
 __device__ __forceinline__ void bitonic_uniform(int L, int P, Get get, Put put) {
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < P; i += TR_THREADS) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
         const int partner = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
         if (partner > i && partner < L) {  // i < partner < L: both real keys
           const int a = get(i), b = get(partner);
@@ -111,14 +119,37 @@ __device__ __forceinline__ void bitonic_uniform(int L, int P, Get get, Put put) 
   }
 }
 
+// Medium segments (33 .. 1024 entries, the bulk of the deferred ones): 128-thread CTAs, 4 KB smem,
+// many CTAs per SM.
+constexpr int MED_THREADS = 128;
+__global__ void __launch_bounds__(MED_THREADS)
+sort_medium_segments_kernel(const int32_t* __restrict__ t_rowptr, int32_t* t_perm,
+                            const int32_t* __restrict__ long_rows, const int32_t* __restrict__ long_count) {
+  __shared__ int32_t sm[MED_SORT];
+  const int n_med = long_count[0];
+  for (int li = blockIdx.x; li < n_med; li += gridDim.x) {
+    const int c = long_rows[li];
+    const int s = t_rowptr[c], e = t_rowptr[c + 1];
+    const int L = e - s;
+    int P = 64;
+    while (P < L) P <<= 1;
+    int32_t* g = t_perm + s;
+    for (int i = threadIdx.x; i < L; i += MED_THREADS) sm[i] = g[i];
+    __syncthreads();
+    bitonic_uniform(L, P, [&](int i) { return sm[i]; }, [&](int i, int v) { sm[i] = v; });
+    for (int i = threadIdx.x; i < L; i += MED_THREADS) g[i] = sm[i];
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(TR_THREADS)
 sort_long_segments_kernel(const int32_t* __restrict__ t_rowptr, int32_t* t_perm,
                           const int32_t* __restrict__ long_rows, const int32_t* __restrict__ long_count,
                           int long_capacity) {
   extern __shared__ int32_t sm[];
-  const int n_long = min(*long_count, long_capacity);
+  const int n_long = long_count[1];
   for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
-    const int c = long_rows[li];
+    const int c = long_rows[long_capacity - 1 - li];
     const int s = t_rowptr[c], e = t_rowptr[c + 1];
     const int L = e - s;
     int P = 64;
@@ -233,7 +264,7 @@ extern "C" int incagg_csr_transpose(const int32_t* rowptr, const int32_t* col, c
   fill_kernel<<<(unsigned)((rows + wpb - 1) / wpb), TR_THREADS, 0, st>>>(rowptr, col, rows, cols,
                                                                         w.cursor, perm);
   IA_LAUNCH_CHECK();
-  IA_CUDA(cudaMemsetAsync(w.long_cnt, 0, sizeof(int32_t), st));
+  IA_CUDA(cudaMemsetAsync(w.long_cnt, 0, 2 * sizeof(int32_t), st));
   if (cols > 0) {
     sort_segments_kernel<<<(unsigned)((cols + wpb - 1) / wpb), TR_THREADS, 0, st>>>(
         t_rowptr, cols, perm, w.long_rows, w.long_cnt, (int)cols);
@@ -245,6 +276,8 @@ extern "C" int incagg_csr_transpose(const int32_t* rowptr, const int32_t* col, c
                                    (int)(BIG_SORT * sizeof(int32_t))));
       smem_set = true;
     }
+    sort_medium_segments_kernel<<<sm_count() * 12, MED_THREADS, 0, st>>>(t_rowptr, perm, w.long_rows, w.long_cnt);
+    IA_LAUNCH_CHECK();
     sort_long_segments_kernel<<<sm_count(), TR_THREADS, BIG_SORT * sizeof(int32_t), st>>>(
         t_rowptr, perm, w.long_rows, w.long_cnt, (int)cols);
     IA_LAUNCH_CHECK();

@@ -19,15 +19,26 @@ import torch  # noqa: E402
 
 
 def timeit(fn, flush, reps=5, cold=True):
+    """Device time of one call: the call is captured in a CUDA graph (so multi-launch operations are
+    not measured by their host launch overhead) and replayed between events; `cold` flushes L2 first."""
     fn()
     torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
     ts = []
     for i in range(reps):
         if cold:
             flush.fill_(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        g.replay()
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e-3)
@@ -74,9 +85,9 @@ def main():
         idx = torch.cat([torch.arange(int(ptr[i]), int(ptr[i + 1]), device=dev) for i in ids])
         B = idx.numel()
         nnz_b = int(rowptr64[int(ptr[ids[-1] + 1])] - rowptr64[int(ptr[ids[0]])])
-        fn = lambda: ops.relabel_one_hop(rowptr64, adj.col, adj.value, idx, True, ws=ws, out_int32=True, nnz_b=nnz_b)
-        rp, col, val, n_id = fn()
+        rp, col, val, n_id = ops.relabel_one_hop(rowptr64, adj.col, adj.value, idx, True, ws=ws, out_int32=True, nnz_b=nnz_b)
         H = n_id.numel() - B
+        fn = lambda: ops.relabel_one_hop(rowptr64, adj.col, adj.value, idx, True, ws=ws, out_int32=True, nnz_b=nnz_b, known=H)
         t_c, t_w = timeit(fn, flush), timeit(fn, flush, cold=False)
         by = nnz_b * (4 + 4 + 4 + 4) + B * 16 + (B + H) * 8
         agg.setdefault("relabel_one_hop", []).append((by, t_c, t_w))
@@ -106,6 +117,9 @@ def main():
         agg.setdefault("history_push_slices", []).append((B * 2 * F * 4, timeit(fn, flush), timeit(fn, flush, cold=False)))
         xs = torch.randn(B, F, device=dev)
         rpb, colb, valb, _ = ops.relabel_one_hop_within_batch(rowptr64, adj.col, adj.value, idx, True, ws=ws, out_int32=True, nnz_b=nnz_b)
+        kept = colb.numel()
+        fnw = lambda: ops.relabel_one_hop_within_batch(rowptr64, adj.col, adj.value, idx, True, ws=ws, out_int32=True, nnz_b=nnz_b, known=kept)
+        agg.setdefault("relabel_within_batch", []).append((nnz_b * 8 + kept * 8 + B * 16, timeit(fnw, flush), timeit(fnw, flush, cold=False)))
         m_in, m_ag = torch.randn(n, F, device=dev), torch.randn(n, F, device=dev)
         o0 = int(off[0])
         planb = ops.spmm_plan(rpb, B, colb.numel())
