@@ -1,0 +1,199 @@
+// Small fused kernels around the GEMMs of the training step (sm_100a): what PyTorch would issue as
+// ~20 tiny launches (mask cast, sums, log-softmax, NLL, their backward) or as a slow strided
+// reduction becomes one or two launches each.
+//
+//   incagg_relu_bwd_colsum   gm = g * (y > 0)  and  colsum[c] = sum_r gm[r, c]   (ReLU backward of the
+//                            first Linear fused with its bias gradient; reference gcn2.py:87 lins[0])
+//   incagg_masked_ce         mean cross-entropy over the rows selected by a mask, and d loss / d logits
+//                            (reference main.py:80  criterion(out[train_mask], y[train_mask]))
+#include <float.h>
+
+#include "common.cuh"
+
+namespace incagg {
+
+constexpr int CS_THREADS = 256;
+constexpr int CS_ROWS_PER_BLOCK = 256;
+
+// Each block owns CS_ROWS_PER_BLOCK rows; thread t owns column chunk (t % cvec) of row group
+// (t / cvec), walks its rows with a fixed stride and the block combines through shared memory in a
+// fixed order -> partial[block][cols].  float4 along the row: coalesced.
+__global__ void __launch_bounds__(CS_THREADS)
+relu_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
+                       int64_t rows, int cols, float* __restrict__ gm, int64_t ldo,
+                       float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [groups][cols]
+  const int cvec = cols / 4;
+  const int groups = CS_THREADS / cvec;
+  const int grp = threadIdx.x / cvec, cv = threadIdx.x % cvec;
+  const int64_t r0 = (int64_t)blockIdx.x * CS_ROWS_PER_BLOCK;
+  const int64_t r1 = min(rows, r0 + CS_ROWS_PER_BLOCK);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (grp < groups) {
+    for (int64_t r = r0 + grp; r < r1; r += groups) {
+      float4 v = *reinterpret_cast<const float4*>(g + r * ldg + cv * 4);
+      if (y) {
+        const float4 m = *reinterpret_cast<const float4*>(y + r * ldy + cv * 4);
+        v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+        v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+        if (gm) *reinterpret_cast<float4*>(gm + r * ldo + cv * 4) = v;
+      }
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(sm + grp * cols + cv * 4) = acc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += CS_THREADS) {
+    float s = 0.f;
+    for (int k = 0; k < groups; ++k) s += sm[k * cols + c];
+    partial[(int64_t)blockIdx.x * cols + c] = s;
+  }
+}
+
+__global__ void colsum_finish_kernel(const float* __restrict__ partial, int nblocks, int cols,
+                                     float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * cols + c];
+  out[c] = s;
+}
+
+// ---- masked cross-entropy ---------------------------------------------------------------------------
+__global__ void mask_count_kernel(const uint8_t* __restrict__ mask, int64_t n, float* __restrict__ count) {
+  __shared__ int s_tot;
+  if (threadIdx.x == 0) s_tot = 0;
+  __syncthreads();
+  int c = 0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) c += mask[i] ? 1 : 0;
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_tot, c);  // integer: order-independent
+  __syncthreads();
+  if (threadIdx.x == 0) *count = (float)s_tot;
+}
+
+// One warp per row: log-sum-exp, loss_i = w_i (lse - z_y), dlogits = w_i / max(n,1) (softmax - onehot).
+// Per-block loss partials (fixed order inside the block) -> partial[block].
+constexpr int CE_THREADS = 256;
+__global__ void __launch_bounds__(CE_THREADS)
+masked_ce_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ y,
+                 const uint8_t* __restrict__ mask, int64_t rows, int C, const float* __restrict__ count,
+                 float* __restrict__ dlogits, int64_t ldd, float* __restrict__ partial) {
+  __shared__ float s_loss[CE_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * (CE_THREADS / 32) + w;
+  const float inv_n = 1.f / fmaxf(*count, 1.f);
+  float loss = 0.f;
+  if (row < rows) {
+    const float* z = logits + row * ld;
+    float mx = -FLT_MAX;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, z[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += __expf(z[c] - mx);
+    se = warp_sum(se);
+    const float lse = mx + __logf(se);
+    const bool on = mask[row] != 0;
+    const int64_t t = y[row];
+    if (on) loss = lse - z[t];
+    const float wgt = on ? inv_n : 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float p = __expf(z[c] - lse);
+      dlogits[row * ldd + c] = wgt * (p - (c == t ? 1.f : 0.f));
+    }
+  }
+  if (lane == 0) s_loss[w] = loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < CE_THREADS / 32; ++k) s += s_loss[k];
+    partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void ce_finish_kernel(const float* __restrict__ partial, int nblocks, const float* __restrict__ count,
+                                 float* __restrict__ out /* [2]: loss sum, mean loss */) {
+  // one block, fixed order
+  __shared__ double s[256];
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) acc += (double)partial[b];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < blockDim.x; ++k) t += s[k];
+    out[0] = (float)t;
+    out[1] = (float)(t / (double)fmaxf(*count, 1.f));
+  }
+}
+
+}  // namespace incagg
+
+using namespace incagg;
+
+extern "C" size_t incagg_colsum_workspace_bytes(int64_t rows, int32_t cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  return sizeof(float) * (size_t)((rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK) * (size_t)cols;
+}
+
+extern "C" int incagg_relu_bwd_colsum(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows,
+                                      int32_t cols, float* gm, int64_t ldo, float* colsum, void* workspace,
+                                      size_t workspace_bytes, incagg_stream_t stream) {
+  IA_CHECK_ARG(rows >= 0 && cols > 0, "bad size");
+  IA_CHECK_ARG(colsum != nullptr, "colsum is NULL");
+  cudaStream_t st = as_stream(stream);
+  if (rows == 0) {
+    IA_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * (size_t)cols, st));
+    return INCAGG_OK;
+  }
+  IA_CHECK_ARG(g != nullptr, "g is NULL");
+  IA_CHECK_ARG(cols % 4 == 0 && cols <= 1024, "cols must be a multiple of 4 and <= 1024");
+  IA_CHECK_ARG(ldg % 4 == 0 && aligned16(g), "g must be 16-byte aligned with ld % 4 == 0");
+  IA_CHECK_ARG(y == nullptr || (ldy % 4 == 0 && aligned16(y)), "y must be 16-byte aligned with ld % 4 == 0");
+  IA_CHECK_ARG(gm == nullptr || (ldo % 4 == 0 && aligned16(gm)), "gm must be 16-byte aligned with ld % 4 == 0");
+  IA_CHECK_ARG(workspace != nullptr && workspace_bytes >= incagg_colsum_workspace_bytes(rows, cols),
+               "workspace too small");
+  const int nblocks = (int)((rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK);
+  const int cvec = cols / 4;
+  IA_CHECK_ARG(cvec <= CS_THREADS, "too many columns");
+  const int groups = CS_THREADS / cvec;
+  float* partial = static_cast<float*>(workspace);
+  relu_bwd_colsum_kernel<<<nblocks, CS_THREADS, sizeof(float) * (size_t)groups * cols, st>>>(
+      g, ldg, y, ldy, rows, cols, gm, ldo, partial);
+  IA_LAUNCH_CHECK();
+  colsum_finish_kernel<<<(cols + 127) / 128, 128, 0, st>>>(partial, nblocks, cols, colsum);
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}
+
+extern "C" size_t incagg_masked_ce_workspace_bytes(int64_t rows) {
+  if (rows <= 0) return 16;
+  return sizeof(float) * (size_t)((rows + CE_THREADS / 32 - 1) / (CE_THREADS / 32)) + 16;
+}
+
+extern "C" int incagg_masked_ce(const float* logits, int64_t ld, const int64_t* y, const uint8_t* mask,
+                                int64_t rows, int32_t C, float* dlogits, int64_t ldd, float* out3,
+                                void* workspace, size_t workspace_bytes, incagg_stream_t stream) {
+  IA_CHECK_ARG(rows >= 0 && C > 0, "bad size");
+  IA_CHECK_ARG(out3 != nullptr, "out is NULL");
+  IA_CHECK_ARG(workspace != nullptr && workspace_bytes >= incagg_masked_ce_workspace_bytes(rows),
+               "workspace too small");
+  cudaStream_t st = as_stream(stream);
+  // out3 = {loss sum, mean loss, count}
+  float* count = out3 + 2;
+  if (rows == 0) {
+    IA_CUDA(cudaMemsetAsync(out3, 0, 3 * sizeof(float), st));
+    return INCAGG_OK;
+  }
+  IA_CHECK_ARG(logits && y && mask && dlogits, "NULL argument");
+  mask_count_kernel<<<1, 1024, 0, st>>>(mask, rows, count);
+  IA_LAUNCH_CHECK();
+  const int nblocks = (int)((rows + CE_THREADS / 32 - 1) / (CE_THREADS / 32));
+  float* partial = static_cast<float*>(workspace);
+  masked_ce_kernel<<<nblocks, CE_THREADS, 0, st>>>(logits, ld, y, mask, rows, C, count, dlogits, ldd, partial);
+  IA_LAUNCH_CHECK();
+  ce_finish_kernel<<<1, 256, 0, st>>>(partial, nblocks, count, out3);
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}

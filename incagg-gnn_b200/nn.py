@@ -35,15 +35,20 @@ class _LinearTC(torch.autograd.Function):
     def backward(ctx, g):
         x, weight, y = ctx.saved_tensors
         g = g.contiguous()
-        if ctx.relu:
-            g = torch.ops.aten.threshold_backward(g, y, 0.)  # ReLU backward, one kernel
         gx = gw = gb = None
+        want_gb = ctx.has_bias and ctx.needs_input_grad[2]
+        if want_gb and ops.colsum_supported(g) and (not ctx.relu or ops.colsum_supported(y)):
+            # ReLU backward and the bias gradient in one pass over g
+            g, gb = ops.relu_bwd_colsum(g, y if ctx.relu else None)
+        else:
+            if ctx.relu:
+                g = torch.ops.aten.threshold_backward(g, y, 0.)  # ReLU backward, one kernel
+            if want_gb:
+                gb = g.sum(0)
         if ctx.needs_input_grad[0]:
             gx = ops.gemm(g, weight)                      # [M,N] x [N,K]
         if ctx.needs_input_grad[1]:
             gw = ops.gemm(g, x, trans_a=True)             # g^T x : [N,M] x [M,K]
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g.sum(0)
         return gx, gw, gb, None
 
 
@@ -104,6 +109,28 @@ class _GCN2Dense(torch.autograd.Function):
                                     cin=g, beta=(1. - b) * (1. - a), cin2=g, beta2=(1. - b) * a)
             gw1, gw2 = ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a)
         return gh, gx0, gw1, gw2, None, None, None
+
+
+class _MaskedCE(torch.autograd.Function):
+    """Mean cross-entropy over the masked rows (main.py:80) with its gradient produced by the same
+    fused kernels (3 launches instead of ~20 tiny ones)."""
+
+    @staticmethod
+    def forward(ctx, logits, y, mask):
+        out3, dl = ops.masked_ce_raw(logits, y, mask)
+        ctx.save_for_backward(dl)
+        ctx.mark_non_differentiable(out3)
+        return out3[1], out3
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_out3):
+        (dl,) = ctx.saved_tensors
+        return dl * g_loss, None, None
+
+
+def masked_cross_entropy(logits: Tensor, y: Tensor, mask: Tensor):
+    """-> (mean CE over rows with mask, [loss sum, mean, count]) ; logits [B, C] fp32, y int64."""
+    return _MaskedCE.apply(logits, y, mask)
 
 
 def glorot_(w: Tensor) -> Tensor:

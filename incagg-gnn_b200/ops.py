@@ -245,6 +245,49 @@ def gemm_dual(mode: str, a: Tensor, b: Tensor, a2: Optional[Tensor] = None, b2: 
     return (out, out2) if mode in ("n", "m") else out
 
 
+def relu_bwd_colsum(g: Tensor, y: Optional[Tensor] = None):
+    """(g * (y > 0), its column sums) in one pass; y=None: (g, column sums of g).  Rows 16-byte aligned,
+    cols % 4 == 0 (callers fall back to torch otherwise)."""
+    _require_cuda(g, y)
+    g = _rowmajor(g)
+    rows, cols = g.shape
+    gm = None
+    if y is not None:
+        y = _rowmajor(y)
+        gm = torch.empty_like(g)
+    colsum = torch.empty(cols, dtype=torch.float32, device=g.device)
+    nb = lib.incagg_colsum_workspace_bytes(rows, cols)
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=g.device)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_relu_bwd_colsum(ptr(g), _ld(g), ptr(y), _ld(y) if y is not None else 0, rows, cols,
+                                     ptr(gm), _ld(gm) if gm is not None else 0, ptr(colsum), ptr(ws),
+                                     ws.numel(), _stream()))
+    return (gm if gm is not None else g), colsum
+
+
+def colsum_supported(t: Tensor) -> bool:
+    return (t.dim() == 2 and t.dtype == torch.float32 and t.size(1) % 4 == 0 and t.size(1) <= 1024
+            and t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0)
+
+
+def masked_ce_raw(logits: Tensor, y: Tensor, mask: Tensor):
+    """-> (out3 = [loss sum, mean loss, count], dlogits) for the rows with mask != 0."""
+    _require_cuda(logits, y, mask)
+    logits = _rowmajor(logits)
+    assert y.dtype == torch.int64 and y.is_contiguous()
+    m8 = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+    m8 = m8.contiguous()
+    rows, C = logits.shape
+    dl = torch.empty_like(logits)
+    out3 = torch.empty(3, dtype=torch.float32, device=logits.device)
+    nb = lib.incagg_masked_ce_workspace_bytes(rows)
+    ws = torch.empty(nb, dtype=torch.uint8, device=logits.device)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_masked_ce(ptr(logits), _ld(logits), ptr(y), ptr(m8), rows, C, ptr(dl), _ld(dl), ptr(out3),
+                               ptr(ws), nb, _stream()))
+    return out3, dl
+
+
 # --------------------------------------------------------------------------------------------
 # rows: gather / scatter / slices
 # --------------------------------------------------------------------------------------------

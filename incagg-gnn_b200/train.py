@@ -62,36 +62,15 @@ def mini_train(model, loader, criterion, optimizer, max_steps, grad_norm=None, e
     total_loss = torch.zeros((), dtype=torch.float64, device=model.device)
     total_examples = torch.zeros((), dtype=torch.float64, device=model.device)
     steps = 0
-    for i, (batch, batch_size, n_id, offset, count) in enumerate(loader):
-        x = batch.x.to(model.device)
-        adj_t = batch.adj_t.to(model.device)
-        y = batch.y[:batch_size].to(model.device)
-        train_mask = batch.train_mask[:batch_size].to(model.device)
-        adj_t = dropout(adj_t, p=edge_dropout)
-        if VR_update:
-            ret = model.VR_call(x, adj_t, batch_size, n_id, offset, count, drift_norm=drift_norm,
-                                epoch=epoch, batch_idx=i)
-        else:
-            ret = model(x, adj_t, batch_size, n_id, offset, count, drift_norm=drift_norm,
-                        aggregate_combined=aggregate_combined, use_aggregation=use_aggregation)
-        out = ret['out']
-        optimizer.zero_grad(set_to_none=True)
-        # mean CE over the training rows of the batch == criterion(out[mask], y[mask]) (main.py:80)
-        # written mask-weighted so that the row count never has to reach the host
-        w = train_mask.to(out.dtype)
-        n = w.sum()
-        if y.dim() == 1:
-            per_row = torch.nn.functional.cross_entropy(out, y, reduction='none')
-        else:
-            per_row = torch.nn.functional.binary_cross_entropy_with_logits(
-                out, y.to(out.dtype), reduction='none').mean(dim=-1)
-        loss = (per_row * w).sum() / n.clamp(min=1.)
-        loss.backward()
-        if grad_norm is not None:
-            torch.nn.utils.clip_grad_norm_(model.parameters(), grad_norm)
-        optimizer.step()
-        total_loss += loss.detach().double() * n
-        total_examples += n
+    for i, sub in enumerate(loader):
+        batch, batch_size, n_id, offset, count = sub
+        if edge_dropout > 0.:
+            batch.adj_t = dropout(batch.adj_t.to(model.device), p=edge_dropout)
+        # forward (model.VR_call / model.__call__) -> masked CE -> backward -> clip -> optimizer step
+        ln, n = train_step(model, sub, optimizer, VR_update=VR_update, grad_norm=grad_norm, epoch=epoch,
+                           batch_idx=i)
+        total_loss += ln.double()
+        total_examples += n.double()
         steps += 1
         if (i + 1) >= max_steps and (i + 1) < len(loader):
             break
@@ -113,13 +92,16 @@ def forward_backward(model, sub, optimizer, VR_update=False, averager=None, epoc
         averager.zero()  # gradients are views into the averager's flat buffer
     else:
         optimizer.zero_grad(set_to_none=True)
+    if y.dim() == 1 and out.dtype == torch.float32:
+        # criterion(out[mask], y[mask]) as one fused masked cross-entropy (loss + gradient kernels)
+        from .nn import masked_cross_entropy
+        loss, out3 = masked_cross_entropy(out, y, train_mask)
+        loss.backward()
+        return out3[0], out3[2]
     w = train_mask.to(out.dtype)
     n = w.sum()
-    if y.dim() == 1:
-        per_row = torch.nn.functional.cross_entropy(out, y, reduction='none')
-    else:
-        per_row = torch.nn.functional.binary_cross_entropy_with_logits(
-            out, y.to(out.dtype), reduction='none').mean(dim=-1)
+    per_row = torch.nn.functional.binary_cross_entropy_with_logits(
+        out, y.to(out.dtype), reduction='none').mean(dim=-1)
     loss = (per_row * w).sum() / n.clamp(min=1.)
     loss.backward()
     return loss.detach() * n, n

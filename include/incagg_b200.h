@@ -156,6 +156,26 @@ int incagg_gemm_tf32x3_dual(int mode, int transA, int transB, int64_t M, int64_t
                             float* D2, int64_t ldd2, void* workspace, size_t workspace_bytes,
                             incagg_stream_t stream);
 
+/* ---- small fused kernels of the training step ------------------------------ */
+/*
+ * ReLU backward fused with the bias gradient of the Linear in front of it (gcn2.py:87 lins[0]):
+ *   gm[r, c] = y[r, c] > 0 ? g[r, c] : 0 ;  colsum[c] = sum_r gm[r, c]   (fixed order: deterministic)
+ * y == NULL: plain column sums of g (gm unused).  cols % 4 == 0, 16-byte aligned rows.
+ */
+size_t incagg_colsum_workspace_bytes(int64_t rows, int32_t cols);
+int incagg_relu_bwd_colsum(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows,
+                           int32_t cols, float* gm, int64_t ldo, float* colsum, void* workspace,
+                           size_t workspace_bytes, incagg_stream_t stream);
+/*
+ * Mean cross-entropy over the rows whose mask byte is non-zero (main.py:80
+ * criterion(out[train_mask], y[train_mask])) and its gradient:
+ *   out3 = {sum_i w_i CE_i, that sum / max(n, 1), n}, dlogits[i, c] = w_i / max(n,1) (softmax - onehot).
+ */
+size_t incagg_masked_ce_workspace_bytes(int64_t rows);
+int incagg_masked_ce(const float* logits, int64_t ld, const int64_t* y, const uint8_t* mask, int64_t rows,
+                     int32_t C, float* dlogits, int64_t ldd, float* out3, void* workspace,
+                     size_t workspace_bytes, incagg_stream_t stream);
+
 /* ---- CSR transpose (CSC view for the backward SpMM) ------------------- */
 /*
  * Counting-sort transpose of a [rows x cols] CSR with nnz entries.

@@ -471,3 +471,32 @@ def test_gather_rows_sharded_matches_unsharded(ops, cuda):
     ops.gather_rows_sharded(shards[2:], bounds[2:], idx, out2)
     inside = (idx >= 130)
     assert torch.equal(out2[inside], table[idx[inside]]) and float(out2[~inside].abs().max()) == 0.
+
+
+def test_relu_bwd_colsum_and_masked_ce(ops, cuda):
+    g = torch.Generator().manual_seed(4)
+    G = torch.randn(3000, 128, generator=g).to(cuda)
+    Y = torch.randn(3000, 128, generator=g).to(cuda)
+    gm, cs = ops.relu_bwd_colsum(G, Y)
+    ref = G * (Y > 0)
+    assert torch.equal(gm, ref)
+    assert float((cs.double() - ref.double().sum(0)).abs().max() / ref.double().sum(0).abs().max()) <= RTOL
+    _, cs2 = ops.relu_bwd_colsum(G[:, :40].contiguous())
+    r2 = G[:, :40].double().sum(0)
+    assert float((cs2.double() - r2).abs().max() / r2.abs().max()) <= RTOL
+    # masked cross-entropy: value and gradient vs torch
+    logits = torch.randn(2000, 47, generator=g).to(cuda).requires_grad_(True)
+    y = torch.randint(0, 47, (2000,), generator=g).to(cuda)
+    mask = (torch.rand(2000, generator=g) < 0.6).to(cuda)
+    from incagg_gnn_b200.nn import masked_cross_entropy
+    loss, out3 = masked_cross_entropy(logits, y, mask)
+    (loss * 2.0).backward()
+    l2 = logits.detach().double().requires_grad_(True)
+    ref_loss = torch.nn.functional.cross_entropy(l2[mask], y[mask])
+    (ref_loss * 2.0).backward()
+    assert abs(float(loss) - float(ref_loss)) <= RTOL * abs(float(ref_loss))
+    assert float(out3[2]) == float(mask.sum())
+    assert float((logits.grad.double() - l2.grad).abs().max() / l2.grad.abs().max()) <= 1e-5
+    # empty mask: zero loss, zero gradient
+    loss0, o0 = masked_cross_entropy(logits.detach(), y, torch.zeros_like(mask))
+    assert float(loss0) == 0. and float(o0[2]) == 0.
