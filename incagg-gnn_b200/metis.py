@@ -1,11 +1,17 @@
 """``metis`` / ``permute`` (reference: torch_geometric_autoscale/metis.py:14-63).
 
-The reference calls ``torch.ops.torch_sparse.partition`` (METIS k-way), which is not available in
-this image.  Partitioning is the step immediately *before* the hot path: the synthetic graphs of
-``synthetic.py`` are generated already clustered (contiguous equal blocks), for which ``metis`` returns
-the identity permutation and the block boundaries.  For other graphs a deterministic stand-in orders
-nodes by a BFS sweep and cuts the order into ``num_parts`` equal ranges (locality, not min-cut)."""
+The reference calls ``torch.ops.torch_sparse.partition`` (METIS k-way through torch_sparse, which is
+not available here).  This module calls METIS itself: ``csrc/metis_shim.c`` links the
+``libmetis_static.a`` that ships with the CUDA toolkit (``METIS_PartGraphKway`` /
+``METIS_PartGraphRecursive``, default options, exactly the call torch_sparse makes) and the result is
+turned into ``(perm, ptr)`` the way the reference does (``cluster.sort()``, ``ind2ptr``).
+Partitioning is the step immediately *before* the hot path.  The synthetic graphs of ``synthetic.py``
+are generated already clustered (contiguous equal blocks); for them ``metis`` returns the identity
+permutation and the block boundaries unless ``force=True``.  If the METIS library is missing, a
+deterministic locality ordering (reverse Cuthill-McKee, equal cuts) stands in."""
 import copy
+import ctypes
+import os
 import time
 from typing import Tuple
 
@@ -35,17 +41,63 @@ def _bfs_order(rowptr: Tensor, col: Tensor) -> Tensor:
     return torch.from_numpy(np.ascontiguousarray(reverse_cuthill_mckee(m, symmetric_mode=False))).long()
 
 
+_METIS = None
+
+
+def _metis_lib():
+    global _METIS
+    if _METIS is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libincagg_metis.so')
+        if os.path.exists(path):
+            lib = ctypes.CDLL(path)
+            lib.incagg_metis_partition.restype = ctypes.c_int
+            lib.incagg_metis_partition.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                   ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+            _METIS = lib
+        else:
+            _METIS = False
+    return _METIS
+
+
+def metis_available() -> bool:
+    return bool(_metis_lib())
+
+
+def partition(rowptr: Tensor, col: Tensor, num_parts: int, recursive: bool = False):
+    """torch.ops.torch_sparse.partition(rowptr, col, None, num_parts, recursive): cluster id per node
+    (METIS k-way).  Returns (cluster, edgecut)."""
+    lib = _metis_lib()
+    if not lib:
+        raise RuntimeError('libincagg_metis.so is not built (make -C incagg-gnn_b200/csrc metis)')
+    rowptr = rowptr.cpu().to(torch.int64).contiguous()
+    col = col.cpu().to(torch.int64).contiguous()
+    n = rowptr.numel() - 1
+    part = torch.empty(n, dtype=torch.int64)
+    cut = ctypes.c_int64(-1)
+    rc = lib.incagg_metis_partition(n, rowptr.data_ptr(), col.data_ptr(), int(num_parts), int(recursive),
+                                    part.data_ptr(), ctypes.byref(cut))
+    if rc != 1:
+        raise RuntimeError(f'METIS failed with status {rc}')
+    return part, int(cut.value)
+
+
 def metis(adj_t: SparseTensor, num_parts: int, recursive: bool = False,
-          log: bool = True) -> Tuple[Tensor, Tensor]:
+          log: bool = True, force: bool = False) -> Tuple[Tensor, Tensor]:
     r"""Returns the "clustered" permutation :obj:`perm` and the cluster slices :obj:`ptr`."""
     if log:
         t = time.perf_counter()
-        print(f'Computing partitioning with {num_parts} parts...', end=' ', flush=True)
+        print(f'Computing METIS partitioning with {num_parts} parts...', end=' ', flush=True)
     num_nodes = adj_t.size(0)
     if num_parts <= 1:
         perm, ptr = torch.arange(num_nodes), torch.tensor([0, num_nodes])
-    elif getattr(adj_t, 'clustered_parts', None) == num_parts:
+    elif getattr(adj_t, 'clustered_parts', None) == num_parts and not force:
         perm, ptr = torch.arange(num_nodes), block_ptr(num_nodes, num_parts)
+    elif metis_available():
+        rowptr, col, _ = adj_t.csr()
+        cluster, _ = partition(rowptr, col, num_parts, recursive)
+        cluster, perm = cluster.sort()                                    # metis.py:32
+        ptr = torch.zeros(num_parts + 1, dtype=torch.int64)               # ind2ptr, metis.py:33
+        torch.cumsum(torch.bincount(cluster, minlength=num_parts), 0, out=ptr[1:])
     else:
         rowptr, col, _ = adj_t.csr()
         perm = _bfs_order(rowptr, col)

@@ -246,7 +246,7 @@ def mini_test(model, loader, use_aggregation=True, VR_update=False):
 def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_device='cuda',
           overrides: Optional[Dict[str, Any]] = None, log: bool = False, data_device=None,
           shuffle: bool = True, host_resident: bool = False, data=None, rank: int = 0,
-          world_size: int = 1, transport: str = 'p2p'):
+          world_size: int = 1, transport: str = 'p2p', force_metis: bool = False):
     """Everything main.py:140-201 sets up for one named config on synthetic data: returns a dict
     with data, ptr, loaders, model, optimizer, criterion and the config."""
     conf = dict(CONFIGS[config])
@@ -261,8 +261,11 @@ def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_dev
         raw = data
         data = data.to(device)
         data.adj_t.clustered_parts = getattr(raw.adj_t, 'clustered_parts', None)
-        perm, ptr = metis(data.adj_t, num_parts=conf['num_parts'], log=log)
+        # force_metis: run the real METIS k-way partitioner even on a pre-clustered synthetic graph
+        perm, ptr = metis(data.adj_t, num_parts=conf['num_parts'], log=log, force=force_metis)
         data = permute(data, perm, log=log)
+        if force_metis:
+            raw = data.to('cpu')  # the partition-ordered graph is what the oracle is given
         if conf['loop']:
             data.adj_t = set_diag(data.adj_t)
         if conf['norm']:

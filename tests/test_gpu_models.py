@@ -21,7 +21,7 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
 
 
-def _setup(cuda, config, scale, overrides=None, history_device='cuda', num_parts=None):
+def _setup(cuda, config, scale, overrides=None, history_device='cuda', num_parts=None, force_metis=False):
     import incagg_gnn_b200  # noqa: F401
     from incagg_gnn_b200.train import build
     from oracle import gas
@@ -36,7 +36,7 @@ def _setup(cuda, config, scale, overrides=None, history_device='cuda', num_parts
     if num_parts is not None:
         ov['num_parts'] = num_parts
     run = build(config, device=cuda, seed=0, scale=scale, overrides=ov, data_device='cpu', shuffle=False,
-                history_device=history_device)
+                history_device=history_device, force_metis=force_metis)
     conf, raw = run['conf'], run['raw']
     # oracle-side inputs: same raw graph, same preprocessing, on the CPU
     rp, col, _ = raw.adj_t.csr()
@@ -221,3 +221,24 @@ def test_graphed_trainer_matches_eager(cuda, vr):
         assert _rel(a, b) <= 1e-5
     for a, b in zip(res[False][2], res[True][2]):
         assert _rel(a, b) <= 1e-5
+
+
+def test_metis_partitioned_graph_matches_oracle(cuda):
+    """Same parity run on a graph partitioned by the real METIS (non-identity permutation, unequal
+    partition sizes): refresh tables, logits and one IncAgg + one GAS epoch."""
+    from incagg_gnn_b200.train import mini_train, mini_test
+    for vr in (True, False):
+        run, gas, omodel, adj, raw = _setup(cuda, 'C3', 64, dict(VR_update=vr), num_parts=6, force_metis=True)
+        ptr = run['ptr']
+        sizes = (ptr[1:] - ptr[:-1]).tolist()
+        assert len(set(sizes)) > 1, "METIS parts are not all the same size"
+        model = run['model']
+        out = mini_test(model, run['eval_loader'], VR_update=vr)
+        ev = _oracle_batches(gas, adj, raw, ptr, _groups(6, 1), False)
+        o_out = omodel.mini_inference(ev, vr=vr)
+        assert _rel(out, o_out) <= RTOL
+        tr = _oracle_batches(gas, adj, raw, ptr, _groups(6, 1), vr)
+        o_opt = torch.optim.Adam(omodel.parameters(), lr=run['conf']['lr'])
+        o_res = gas.train_epoch(omodel, tr, o_opt, vr=vr)
+        res = mini_train(model, run['train_loader'], run['criterion'], run['optimizer'], run['max_steps'], VR_update=vr)
+        assert abs(res['loss'] - o_res['loss']) <= RTOL * abs(o_res['loss']), (res['loss'], o_res['loss'])

@@ -65,20 +65,37 @@ def test_synthetic_graph_shape_and_determinism():
     assert b.batch_size == 500 and 0 < b.n_id.numel() - 500 < 4500
 
 
-def test_metis_standin_and_permute():
-    data, ptr = tga.synthetic_graph(1200, 9000, 4, 3, 6, seed=2)
+def test_metis_and_permute():
+    from incagg_gnn_b200.metis import metis_available, block_ptr
+    data, ptr = tga.synthetic_graph(6000, 60000, 4, 3, 6, seed=2)
+    # a pre-clustered synthetic graph: identity permutation, block boundaries (no METIS call)
     perm, p2 = tga.metis(data.adj_t, 6, log=False)
-    assert torch.equal(perm, torch.arange(1200)) and torch.equal(p2, ptr)
-    # a graph that is not pre-clustered gets a locality order and equal cuts
-    perm3, p3 = tga.metis(data.adj_t, 4, log=False)
-    assert sorted(perm3.tolist()) == list(range(1200)) and p3.tolist() == [0, 300, 600, 900, 1200]
-    d3 = tga.permute(data, perm3, log=False)
-    assert torch.equal(d3.x, data.x[perm3]) and d3.adj_t.nnz() == data.adj_t.nnz()
+    assert torch.equal(perm, torch.arange(6000)) and torch.equal(p2, ptr)
+    # hide the structure behind a random relabelling; real METIS (libmetis_static.a through
+    # csrc/metis_shim.c, the call torch_sparse.partition makes) must find it again
+    assert metis_available(), "libincagg_metis.so not built"
+    shuffle = torch.randperm(6000, generator=torch.Generator().manual_seed(5))
+    shuf = tga.permute(data, shuffle, log=False)
+    assert torch.equal(shuf.x, data.x[shuffle]) and shuf.adj_t.nnz() == data.adj_t.nnz()
+    perm3, p3 = tga.metis(shuf.adj_t, 6, log=False)
+    assert sorted(perm3.tolist()) == list(range(6000))
+    assert p3[0] == 0 and p3[-1] == 6000 and bool((p3[1:] > p3[:-1]).all())
+    sizes = (p3[1:] - p3[:-1]).float()
+    assert float(sizes.max() / sizes.mean()) < 1.1                      # balanced parts
+    d3 = tga.permute(shuf, perm3, log=False)
+
+    def cut(adj, bounds):
+        r, c = adj.storage.row(), adj.storage.col()
+        return float((torch.bucketize(r, bounds[1:], right=True) != torch.bucketize(c, bounds[1:], right=True)).float().mean())
+
+    assert cut(d3.adj_t, p3) < 0.25 < 0.7 < cut(shuf.adj_t, block_ptr(6000, 6))   # planted p_inter = 0.15
     # permuted adjacency: edge (i, j) of the new graph is edge (perm[i], perm[j]) of the old one
     r, c = d3.adj_t.storage.row(), d3.adj_t.storage.col()
-    old = set((data.adj_t.storage.row() * 1200 + data.adj_t.storage.col()).tolist())
-    assert set((perm3[r] * 1200 + perm3[c]).tolist()) == old
-    assert data.x is not d3.x and torch.equal(data.x, tga.synthetic_graph(1200, 9000, 4, 3, 6, seed=2)[0].x)
+    old = set((shuf.adj_t.storage.row() * 6000 + shuf.adj_t.storage.col()).tolist())
+    assert set((perm3[r] * 6000 + perm3[c]).tolist()) == old
+    # deterministic
+    perm4, p4 = tga.metis(shuf.adj_t, 6, log=False)
+    assert torch.equal(perm3, perm4) and torch.equal(p3, p4)
 
 
 def test_no_cpu_fallback_on_the_product_path():
