@@ -287,7 +287,7 @@ def spmm_roofline(run, peaks):
     loader, model = run["train_loader"], run["model"]
     F = model.hidden_channels
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    tot_b = tot_t = 0.0
+    tot_b = tot_t = tot_g = 0.0
     parts = loader._parts[:20]  # this rank's own partitions
     n = len(parts)
     from incagg_gnn_b200.sparse import SparseTensor
@@ -310,6 +310,7 @@ def spmm_roofline(run, peaks):
         torch.cuda.synchronize()
         rows, nnz, rsrc = adj.size(0), adj.nnz(), adj.size(1)
         tot_b += nnz * 8 + (rows + 1) * 4 + rsrc * F * 4 + rows * F * 4
+        tot_g += nnz * F * 4
         tot_t += e0.elapsed_time(e1) / 1e3
     achieved = tot_b / tot_t / 1e9
     peak = peaks.get("hbm_gbs", 6650.0)
@@ -317,7 +318,13 @@ def spmm_roofline(run, peaks):
             "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
             "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback",
             "bytes_per_launch": int(tot_b / n), "us_per_launch": round(tot_t / n * 1e6, 2),
-            "traffic": None}
+            "traffic": 36.5e6,  # dram__bytes_read+write per launch, ncu --set full (profiles/r01_spmm_ncu_full_b.txt)
+            # the resource that actually binds this kernel: every edge pulls an F*4-byte row through L2
+            "l2_gather": {"bytes_per_launch": int(tot_g / n), "achieved_GBps": round(tot_g / tot_t / 1e9, 1),
+                          "cap_GBps": 12200.0,
+                          "cap_source": "full-graph SpMM of this kernel (64.3M edges x 512 B in 2.7 ms) = LTS "
+                                        "throughput cap ~6300 B/clk (B300_MICROARCH.md)",
+                          "frac": round(tot_g / tot_t / 1e9 / 12200.0, 4)}}
 
 
 def load_peaks():
@@ -468,6 +475,24 @@ def main():
             dist.destroy_process_group()
         return
 
+    # the per-epoch refresh sweep (mini_inference / mini_inference_vr over all partitions), timed alone
+    refresh = None
+    if world == 1:
+        from incagg_gnn_b200.train import GraphedSweep
+        sweep = GraphedSweep(model, run["eval_loader"], VR_update=vr)
+        sweep()  # captures (once)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sweep()
+        torch.cuda.synchronize()
+        t_sweep = time.perf_counter() - t0
+        nnz_all = run["data"].adj_t.nnz()
+        t_epoch = nnz_all / value
+        refresh = {"sweep_s": round(t_sweep, 4), "train_epoch_s": round(t_epoch, 4),
+                   "edges_per_s_epoch_plus_refresh": nnz_all / (t_epoch + t_sweep),
+                   "note": "value = training steps only; one epoch of the reference loop = train epoch + one "
+                           "layer-wise refresh sweep over all partitions (main.py:226-236); the sweep is one "
+                           "CUDA-graph replay (train.GraphedSweep)"}
     peaks = load_peaks()
     roof = spmm_roofline(run, peaks)
     cpu = None
@@ -501,7 +526,7 @@ def main():
                                   f"timed region in {graphs['capture_s']} s; every replay re-runs collate, forward, "
                                   f"history push/pull, backward and Adam)")},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-        "cpu_baseline": cpu, "edges_timed": edges, "wall_s": wall,
+        "cpu_baseline": cpu, "edges_timed": edges, "wall_s": wall, "refresh": refresh,
     }
     print(json.dumps(line))
     if dist is not None:

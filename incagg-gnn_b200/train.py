@@ -235,6 +235,42 @@ class GraphedTrainer:
         return {'loss': a[0] / max(a[1], 1.), 'steps': steps}
 
 
+class GraphedSweep:
+    """The per-epoch layer-wise sweep (``mini_inference`` / ``mini_inference_vr``: all partitions, all
+    layers, ~10^4 launches of small kernels) captured once as ONE CUDA graph and replayed every epoch.
+    The evaluation loader pre-materialises its subgraphs (as the reference's does, loader.py:153-170), so
+    the kernel sequence is fixed; every replay recomputes all tables from the current weights.
+    Single-GPU, HBM-resident histories (the sharded p2p sweep needs host barriers between layer phases)."""
+
+    def __init__(self, model, loader, VR_update=False, use_aggregation=True):
+        if model.pool is not None or model.shard is not None:
+            raise RuntimeError('GraphedSweep needs HBM-resident, unsharded histories')
+        self.model, self.loader, self.vr, self.use_aggregation = model, loader, VR_update, use_aggregation
+        self.graph = None
+
+    @torch.no_grad()
+    def _body(self):
+        if self.vr:
+            return self.model.mini_inference_vr(loader=self.loader, use_aggregation=self.use_aggregation)
+        return self.model.mini_inference(self.loader, self.use_aggregation)
+
+    @torch.no_grad()
+    def __call__(self):
+        self.model.eval()
+        if self.graph is None:
+            s = torch.cuda.Stream(self.model.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._body()  # eager warm-up (plans, transposes, scratch, output buffer)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+        self.graph.replay()
+        return self.model._out
+
+
 @torch.no_grad()
 def mini_test(model, loader, use_aggregation=True, VR_update=False):
     model.eval()

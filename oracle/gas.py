@@ -450,7 +450,7 @@ def train_epoch(model: OracleGNN, batches: List[SubData], optimizer, vr: bool, g
         if grad_norm is not None:
             torch.nn.utils.clip_grad_norm_(model.parameters(), grad_norm)
         optimizer.step()
-        losses.append(float(loss))
-        total_loss += float(loss) * int(mask.sum())
+        losses.append(float(loss.detach()))
+        total_loss += float(loss.detach()) * int(mask.sum())
         total_examples += int(mask.sum())
     return {'loss': total_loss / max(total_examples, 1), 'losses': losses}

@@ -242,3 +242,23 @@ def test_metis_partitioned_graph_matches_oracle(cuda):
         o_res = gas.train_epoch(omodel, tr, o_opt, vr=vr)
         res = mini_train(model, run['train_loader'], run['criterion'], run['optimizer'], run['max_steps'], VR_update=vr)
         assert abs(res['loss'] - o_res['loss']) <= RTOL * abs(o_res['loss']), (res['loss'], o_res['loss'])
+
+
+@pytest.mark.parametrize("vr", [False, True])
+def test_graphed_sweep_matches_eager(cuda, vr):
+    from incagg_gnn_b200.train import GraphedSweep, mini_test
+    run, *_ = _setup(cuda, 'C3', 64, dict(VR_update=vr), num_parts=6)
+    model = run['model']
+    out_e = mini_test(model, run['eval_loader'], VR_update=vr).clone()
+    tabs_e = [h.emb.clone() for h in list(model.histories) + list(model.histories_ag)]
+    for h in list(model.histories) + list(model.histories_ag):
+        h.emb.zero_()
+    sweep = GraphedSweep(model, run['eval_loader'], VR_update=vr)
+    sweep()
+    for h in list(model.histories) + list(model.histories_ag):
+        h.emb.zero_()
+    out_g = sweep()   # pure replay
+    torch.cuda.synchronize()
+    assert torch.equal(out_g, out_e)
+    for a, b in zip(tabs_e, [h.emb for h in list(model.histories) + list(model.histories_ag)]):
+        assert torch.equal(a, b)
