@@ -105,7 +105,7 @@ struct SpmmParams {
   // multi extras: slab k = blockIdx.y / tiles_per_slab uses reducers[k]
   int32_t slab_F;
   int32_t tiles_per_slab;
-  int32_t reducers[8];
+  int32_t reducers[16];
   // degree-bucket plan (see SpmmPlan) and the scratch area of split rows
   const SpmmPlan* plan;
   const int4* items;        // work items of the plan
@@ -722,7 +722,7 @@ extern "C" int incagg_spmm_multi(const int32_t* rowptr, const int32_t* col, cons
                                  const float* X, int64_t ldx, float* out, int64_t ldo, int64_t rows,
                                  int32_t F, int32_t K, const int32_t* reducers, const void* plan,
                                  incagg_stream_t stream) {
-  IA_CHECK_ARG(K >= 1 && K <= 8, "K must be in [1, 8] (got %d)", K);
+  IA_CHECK_ARG(K >= 1 && K <= 16, "K must be in [1, 16] (got %d)", K);
   IA_CHECK_ARG(reducers != nullptr, "reducers is NULL");
   int rc = check_common(rowptr, col, X, out, ldx, ldo, rows, F * K);
   if (rc != INCAGG_OK) return rc;

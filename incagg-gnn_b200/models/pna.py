@@ -58,25 +58,57 @@ class PNAConv(torch.nn.Module):
             h = h * (self.avg_deg['log'] / ((deg + 1).log() + EPS))
         return h
 
+    STD_EPS = 1e-5
+
+    def _aggregate_one(self, adj_t: SparseTensor, h: Tensor, aggr: str) -> Tensor:
+        """One aggregator with autograd.  'std' / 'var' are composed from two mean aggregations,
+        sqrt(relu(mean(h^2) - mean(h)^2) + eps) (PyG's definition); torch_sparse.matmul itself has
+        sum / mean / min / max only, so these two go beyond the reference."""
+        if aggr in ('std', 'var'):
+            m1 = spmm(adj_t, h, reduce='mean')
+            m2 = spmm(adj_t, h * h, reduce='mean')
+            var = (m2 - m1 * m1).relu()
+            return var if aggr == 'var' else (var + self.STD_EPS).sqrt()
+        return spmm(adj_t, h, reduce=aggr)
+
     def message_and_aggregate(self, adj_t: SparseTensor, x: Tensor) -> Tensor:
         deg = adj_t.storage.rowcount().to(x.dtype).view(-1, 1)
         combos = list(product(self.aggregators, self.scalers))
-        fused = not torch.is_grad_enabled() and len(combos) <= 8 and self.out_channels % 4 == 0
+        # slabs of the fused multi-aggregator launch: one per combo, two for std / var
+        slabs = []
+        for k, (aggr, _) in enumerate(combos):
+            slabs += [(k, 'mean', False), (k, 'mean', True)] if aggr in ('std', 'var') else [(k, aggr, False)]
+        fused = not torch.is_grad_enabled() and len(slabs) <= 16 and self.out_channels % 4 == 0
         out = 0
         if fused:
+            # inference sweeps: the K pre_lin outputs are written side by side by the GEMM epilogues
+            # (bias + ReLU fused, strided output), all K reductions run in ONE SpMM launch
             Fo = self.out_channels
-            hs = torch.empty((x.size(0), len(combos) * Fo), dtype=x.dtype, device=x.device)
-            for k, pre_lin in enumerate(self.pre_lins):
-                hs[:, k * Fo:(k + 1) * Fo] = pre_lin(x).relu_()
+            hs = torch.empty((x.size(0), len(slabs) * Fo), dtype=x.dtype, device=x.device)
+            for j, (k, _, squared) in enumerate(slabs):
+                dst = hs[:, j * Fo:(j + 1) * Fo]
+                if squared:
+                    torch.mul(hs[:, (j - 1) * Fo:j * Fo], hs[:, (j - 1) * Fo:j * Fo], out=dst)
+                else:
+                    pl = self.pre_lins[k]
+                    ops.gemm(x, pl.weight, trans_b=True, bias=pl.bias, relu=True, out=dst)
             agg = ops.spmm_multi_raw(adj_t.rowptr, adj_t.col, adj_t.value, hs, Fo,
-                                     [a for a, _ in combos], rows=adj_t.size(0), plan=adj_t.plan())
+                                     [r for _, r, _ in slabs], rows=adj_t.size(0), plan=adj_t.plan())
+            j = 0
             for k, ((aggr, scaler), post_lin) in enumerate(zip(combos, self.post_lins)):
-                h = post_lin(agg[:, k * Fo:(k + 1) * Fo])
+                a = agg[:, j * Fo:(j + 1) * Fo]
+                if aggr in ('std', 'var'):
+                    m2 = agg[:, (j + 1) * Fo:(j + 2) * Fo]
+                    var = (m2 - a * a).relu()
+                    a = var if aggr == 'var' else (var + self.STD_EPS).sqrt()
+                    j += 1
+                j += 1
+                h = post_lin(a)
                 out = out + self._scale(h, scaler, deg)
             return out
         for (aggr, scaler), pre_lin, post_lin in zip(combos, self.pre_lins, self.post_lins):
-            h = pre_lin(x).relu_()
-            h = spmm(adj_t, h, reduce=aggr)
+            h = pre_lin(x, relu=True)
+            h = self._aggregate_one(adj_t, h, aggr)
             h = post_lin(h)
             out = out + self._scale(h, scaler, deg)
         return out

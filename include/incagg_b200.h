@@ -112,7 +112,7 @@ int incagg_spmm_minmax_bwd(const int32_t* col, const float* val, const int32_t* 
 /*
  * Fused multi-aggregator propagate for PNA (reference pna.py:66-84 runs K separate
  * matmul(reduce=aggr) passes).  X is [n_src, K*F]; slab k (columns k*F..(k+1)*F)
- * is reduced with reducers[k] (host array of K INCAGG_REDUCE_* codes, K <= 8);
+ * is reduced with reducers[k] (host array of K INCAGG_REDUCE_* codes, K <= 16);
  * the CSR structure is read once.  No arg output (forward / inference use).
  */
 int incagg_spmm_multi(const int32_t* rowptr, const int32_t* col, const float* val, const float* X,

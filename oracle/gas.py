@@ -243,7 +243,12 @@ class OracleGNN:
         out = 0
         for k, (aggr, scaler) in enumerate(product(self.aggregators, self.scalers)):
             h = self.lin(f'convs.{l}.pre_lins.{k}', x).relu()
-            h = spmm(adj, h, aggr)
+            if aggr in ('std', 'var'):  # PyG's definition (an extension: torch_sparse has no std)
+                m1, m2 = spmm(adj, h, 'mean'), spmm(adj, h * h, 'mean')
+                var = (m2 - m1 * m1).relu()
+                h = var if aggr == 'var' else (var + 1e-5).sqrt()
+            else:
+                h = spmm(adj, h, aggr)
             h = self.lin(f'convs.{l}.post_lins.{k}', h)
             if scaler == 'amplification':
                 h = h * ((deg + 1).log() / self.avg_deg_log)

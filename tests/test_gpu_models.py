@@ -115,8 +115,9 @@ def test_gas_sweep_and_epoch_match_oracle(cuda, config, scale, parts, bs):
     ov = dict(VR_update=False, batch_size=bs)
     if config == 'C4':
         ov['architecture'] = dict(hidden_channels=256)
-    if config == 'C5':
-        ov['architecture'] = dict(hidden_channels=64)
+    if config == 'C5':  # all five aggregators of the north star, two scalers
+        ov['architecture'] = dict(hidden_channels=64, aggregators=['sum', 'mean', 'min', 'max', 'std'],
+                                  scalers=['identity', 'amplification'])
     run, gas, omodel, adj, raw = _setup(cuda, config, scale, ov, num_parts=parts)
     model, ptr = run['model'], run['ptr']
     out = mini_test(model, run['eval_loader'], VR_update=False)
