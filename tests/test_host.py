@@ -127,3 +127,22 @@ def test_utils():
     y = torch.tensor([0, 1, 1])
     assert abs(tga.compute_micro_f1(logits, y) - 2 / 3) < 1e-9
     assert tga.index2mask(torch.tensor([1, 3]), 5).tolist() == [False, True, False, True, False]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU port of the reference path, no GPU needed) prints one JSON
+    line with the keys the driver reads."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--scale", "128",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "edges/s" and line["value"] > 0
+    assert line["metric"].startswith("edges/s") and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["config"]["workload"].startswith("C3")
