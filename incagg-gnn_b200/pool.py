@@ -1,156 +1,157 @@
-"""``AsyncIOPool`` — pinned-host <-> device history staging (reference: pool.py:15-134).
+"""``AsyncIOPool`` — pinned-host <-> device history staging (reference: pool.py:15-134, over
+csrc/async.cpp).  Same constructor, same five methods, same FIFO semantics:
 
-Same slots / FIFO state machine / method names (§3.5 of SURVEY.md).  Differences:
-  * dependencies are CUDA events between the pull / push side streams and the compute stream; the
-    reference's ``torch.cuda.synchronize(<Stream>)`` (a whole-device sync in torch 2.x, F8) and the
-    trailing ``cudaStreamSynchronize`` of read/write_async are gone,
-  * the indexed part of a pull is gathered by a kernel straight out of the pinned table (UVA), so no
-    pinned bounce buffer per slot is allocated (``_cpu_buffer`` is kept for API compatibility and
-    allocates lazily only if somebody asks for it).
+    async_pull(src, offset, count, index)   enqueue a pull; at most ``pool_size`` are in flight, the rest
+                                            wait in the queue until ``free_pull`` releases a slot
+    synchronize_pull() -> Tensor            device buffer of the OLDEST pull: rows [0, sum(count)) are the
+                                            slices, the following |index| rows are src[index]
+    free_pull()                             release the oldest pull's slot, start the next queued pull
+    async_push(src, offset, count, dst)     dst[offset_i : +count_i] <- src rows, on a side stream
+    synchronize_push(idx=None)              wait for one / all outstanding pushes
+
+What differs from the reference is how ordering is enforced: every slot owns a pull stream, a push
+stream and three CUDA events (filled / released / pushed), and all dependencies between the side
+streams and the compute stream are event waits.  The reference's ``torch.cuda.synchronize(<Stream>)``
+(a whole-device synchronisation in torch 2.x) and the trailing ``cudaStreamSynchronize`` of
+``read_async`` / ``write_async`` do not exist here, and the indexed part of a pull is gathered by a
+kernel straight out of the pinned table (UVA), so no pinned bounce buffer per slot is needed.
 """
-from typing import Optional, Callable
+from collections import deque
+from typing import Callable, Deque, List, NamedTuple, Optional
 
 import torch
 from torch import Tensor
-from torch.cuda import Stream
 
 from . import ops
+
+
+class _PullRequest(NamedTuple):
+    slot: int
+    src: Tensor
+    offset: Optional[Tensor]
+    count: Optional[Tensor]
+    index: Tensor
+
+
+class _Slot:
+    """Resources of one pool slot, created lazily on the pool's device."""
+
+    def __init__(self, rows: int, width: int):
+        self.rows, self.width = rows, width
+        self.buffer: Optional[Tensor] = None            # [rows, width] on the device
+        self.pull_stream: Optional[torch.cuda.Stream] = None
+        self.push_stream: Optional[torch.cuda.Stream] = None
+        self.filled: Optional[torch.cuda.Event] = None    # the pull into `buffer` has completed
+        self.released: Optional[torch.cuda.Event] = None  # the consumer has finished reading `buffer`
+        self.pushed: Optional[torch.cuda.Event] = None    # the push issued from this slot has completed
+        self.push_src: Optional[Tensor] = None            # keeps the pushed tensor alive (pool.py:107)
+
+    def materialise(self, device: torch.device) -> None:
+        if self.buffer is None:
+            if device.type != 'cuda':
+                raise RuntimeError('AsyncIOPool needs a CUDA device (move the model with .to(device))')
+            self.buffer = torch.empty(self.rows, self.width, device=device)
+            self.pull_stream = torch.cuda.Stream(device)
+            self.push_stream = torch.cuda.Stream(device)
 
 
 class AsyncIOPool(torch.nn.Module):
     def __init__(self, pool_size: int, buffer_size: int, embedding_dim: int):
         super().__init__()
-        self.pool_size = pool_size
-        self.buffer_size = buffer_size
-        self.embedding_dim = embedding_dim
-
+        self.pool_size, self.buffer_size, self.embedding_dim = pool_size, buffer_size, embedding_dim
         self._device = torch.device('cpu')
-        self._pull_queue = []
-        self._push_cache = [None] * pool_size
-        self._push_streams = [None] * pool_size
-        self._pull_streams = [None] * pool_size
-        self._cpu_buffers = [None] * pool_size
-        self._cuda_buffers = [None] * pool_size
-        self._pull_events = [None] * pool_size   # pull into slot finished
-        self._free_events = [None] * pool_size   # consumer finished reading slot
-        self._push_events = [None] * pool_size   # push from slot finished
-        self._pull_index = -1
-        self._push_index = -1
+        self._slots: List[_Slot] = [_Slot(buffer_size, embedding_dim) for _ in range(pool_size)]
+        self._pull_queue: Deque[_PullRequest] = deque()
+        self._next_pull = 0   # slot assigned to the next async_pull (round robin)
+        self._next_push = 0
 
-    def _apply(self, fn: Callable) -> None:
+    def _apply(self, fn: Callable) -> 'AsyncIOPool':
         self._device = fn(torch.zeros(1)).device
         return self
 
-    def _pull_stream(self, idx: int) -> Stream:
-        if self._pull_streams[idx] is None:
-            assert str(self._device)[:4] == 'cuda'
-            self._pull_streams[idx] = torch.cuda.Stream(self._device)
-        return self._pull_streams[idx]
+    def _slot(self, i: int) -> _Slot:
+        s = self._slots[i]
+        s.materialise(self._device)
+        return s
 
-    def _push_stream(self, idx: int) -> Stream:
-        if self._push_streams[idx] is None:
-            assert str(self._device)[:4] == 'cuda'
-            self._push_streams[idx] = torch.cuda.Stream(self._device)
-        return self._push_streams[idx]
+    def _compute_stream(self) -> torch.cuda.Stream:
+        return torch.cuda.current_stream(self._device)
 
-    def _cpu_buffer(self, idx: int) -> Tensor:
-        if self._cpu_buffers[idx] is None:
-            self._cpu_buffers[idx] = torch.empty(self.buffer_size, self.embedding_dim, pin_memory=True)
-        return self._cpu_buffers[idx]
-
-    def _cuda_buffer(self, idx: int) -> Tensor:
-        if self._cuda_buffers[idx] is None:
-            assert str(self._device)[:4] == 'cuda'
-            self._cuda_buffers[idx] = torch.empty(self.buffer_size, self.embedding_dim,
-                                                  device=self._device)
-        return self._cuda_buffers[idx]
-
+    # ---- pulls --------------------------------------------------------------------------------
     @torch.no_grad()
     def async_pull(self, src: Tensor, offset: Optional[Tensor], count: Optional[Tensor],
                    index: Tensor) -> None:
-        # Start pulling `src` at ([offset, count] and index positions (pool.py:64-74):
-        self._pull_index = (self._pull_index + 1) % self.pool_size
-        data = (self._pull_index, src, offset, count, index)
-        self._pull_queue.append(data)
-        if len(self._pull_queue) <= self.pool_size:
-            self._async_pull(self._pull_index, src, offset, count, index)
+        req = _PullRequest(self._next_pull, src, offset, count, index)
+        self._next_pull = (self._next_pull + 1) % self.pool_size
+        self._pull_queue.append(req)
+        if len(self._pull_queue) <= self.pool_size:  # a slot is free: start right away
+            self._start_pull(req)
 
-    @torch.no_grad()
-    def _async_pull(self, idx: int, src: Tensor, offset: Optional[Tensor], count: Optional[Tensor],
-                    index: Tensor) -> None:
-        stream = self._pull_stream(idx)
-        # the slot may still be read by the consumer of its previous content, and the table may
-        # still be written by an outstanding push:
-        if self._free_events[idx] is not None:
-            stream.wait_event(self._free_events[idx])
-        for ev in self._push_events:
-            if ev is not None:
-                stream.wait_event(ev)
-        if index.is_cuda:
-            stream.wait_stream(torch.cuda.current_stream(self._device))
+    def _start_pull(self, req: _PullRequest) -> None:
+        slot = self._slot(req.slot)
+        stream = slot.pull_stream
+        if slot.released is not None:          # previous content of the buffer still being read?
+            stream.wait_event(slot.released)
+        for other in self._slots:              # the table may still be written by an outstanding push
+            if other.pushed is not None:
+                stream.wait_event(other.pushed)
+        if req.index.is_cuda:                  # device-resident index produced on the compute stream
+            stream.wait_stream(self._compute_stream())
         with torch.cuda.stream(stream):
-            ops.read_async(src, offset, count, index, self._cuda_buffer(idx), None)
-            ops._PENDING_READS.pop()  # this pool tracks its own events
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            self._pull_events[idx] = ev
+            ops.read_async(req.src, req.offset, req.count, req.index, slot.buffer, None)
+            ops._PENDING_READS.pop()           # this pool keeps its own completion events
+            slot.filled = torch.cuda.Event()
+            slot.filled.record(stream)
 
     @torch.no_grad()
     def synchronize_pull(self) -> Tensor:
-        idx = self._pull_queue[0][0]
-        # the compute stream waits for the copy; the host does not (reference: device-wide sync)
-        torch.cuda.current_stream(self._device).wait_event(self._pull_events[idx])
-        return self._cuda_buffer(idx)
+        slot = self._slot(self._pull_queue[0].slot)
+        # the COMPUTE STREAM waits for the copy; the host does not block
+        self._compute_stream().wait_event(slot.filled)
+        return slot.buffer
 
     @torch.no_grad()
     def free_pull(self) -> None:
-        # Free the buffer space and start pulling from remaining queue (pool.py:90-99):
-        idx = self._pull_queue[0][0]
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self._device))
-        self._free_events[idx] = ev
-        self._pull_queue.pop(0)
+        done = self._pull_queue.popleft()
+        slot = self._slot(done.slot)
+        slot.released = torch.cuda.Event()
+        slot.released.record(self._compute_stream())
         if len(self._pull_queue) >= self.pool_size:
-            data = self._pull_queue[self.pool_size - 1]
-            idx, src, offset, count, index = data
-            self._async_pull(idx, src, offset, count, index)
-        elif len(self._pull_queue) == 0:
-            self._pull_index = -1
+            # the request that has just moved into the in-flight window reuses the released slot
+            self._start_pull(self._pull_queue[self.pool_size - 1])
+        elif not self._pull_queue:
+            self._next_pull = 0
 
+    # ---- pushes -------------------------------------------------------------------------------
     @torch.no_grad()
     def async_push(self, src: Tensor, offset: Tensor, count: Tensor, dst: Tensor) -> None:
-        # Start pushing `src` to ([offset, count] and index positions to `dst` (pool.py:101-109):
-        self._push_index = (self._push_index + 1) % self.pool_size
-        self.synchronize_push(self._push_index)
-        src = src.contiguous()
-        self._push_cache[self._push_index] = src
-        stream = self._push_stream(self._push_index)
-        stream.wait_stream(torch.cuda.current_stream(self._device))  # src must be produced first
-        with torch.cuda.stream(stream):
-            ops.write_async(src, offset, count, dst)
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            self._push_events[self._push_index] = ev
+        i = self._next_push
+        self._next_push = (self._next_push + 1) % self.pool_size
+        self.synchronize_push(i)               # at most one outstanding push per slot
+        slot = self._slot(i)
+        slot.push_src = src.contiguous()
+        slot.push_stream.wait_stream(self._compute_stream())  # src must have been produced
+        with torch.cuda.stream(slot.push_stream):
+            ops.write_async(slot.push_src, offset, count, dst)
+            slot.pushed = torch.cuda.Event()
+            slot.pushed.record(slot.push_stream)
 
     @torch.no_grad()
     def synchronize_push(self, idx: Optional[int] = None) -> None:
-        # Synchronize the push command of stream `idx` or all commands (pool.py:111-123):
         if idx is None:
-            for idx in range(self.pool_size):
-                self.synchronize_push(idx)
-            self._push_index = -1
-        else:
-            ev = self._push_events[idx]
-            if ev is not None:
-                ev.synchronize()  # this stream's work only, not the device
-                self._push_events[idx] = None
-            self._push_cache[idx] = None
+            for i in range(self.pool_size):
+                self.synchronize_push(i)
+            self._next_push = 0
+            return
+        slot = self._slots[idx]
+        if slot.pushed is not None:
+            slot.pushed.synchronize()          # this slot's push only, never the whole device
+            slot.pushed = None
+        slot.push_src = None
 
     def forward(self, *args, **kwargs):
         raise NotImplementedError
 
-    def __repr__(self):
-        return (f'{self.__class__.__name__}(pool_size={self.pool_size}, '
-                f'buffer_size={self.buffer_size}, '
-                f'embedding_dim={self.embedding_dim}, '
-                f'device={self._device})')
+    def extra_repr(self) -> str:
+        return (f'pool_size={self.pool_size}, buffer_size={self.buffer_size}, '
+                f'embedding_dim={self.embedding_dim}, device={self._device}')

@@ -146,3 +146,24 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert line["config"]["workload"].startswith("C3")
+
+
+def test_gen_masks_and_edge_dropout():
+    torch.manual_seed(0)
+    y = torch.randint(0, 4, (400,))
+    tr, va, te = tga.gen_masks(y, train_per_class=5, val_per_class=7, num_splits=3)
+    assert tr.shape == (400, 3) and bool((tr.sum(0) == 20).all()) and bool((va.sum(0) == 28).all())
+    assert not bool((tr & va).any()) and bool((tr | va | te).all()) and not bool((te & (tr | va)).any())
+    for c in range(4):
+        assert bool((tr[y == c].sum(0) == 5).all())
+    adj = tga.SparseTensor(row=torch.tensor([0, 0, 1, 2]), col=torch.tensor([1, 2, 0, 0]), sparse_sizes=(3, 3))
+    assert tga.dropout(adj, 0.0) is adj and tga.dropout(adj, 0.5, training=False) is adj
+    d = tga.dropout(adj, 0.5)
+    assert d.nnz() <= 4 and d.sparse_sizes() == (3, 3)
+    w = adj.set_value(torch.ones(4))
+    dw = tga.dropout(w, 0.5)
+    assert dw.nnz() == 4 and set(dw.value.tolist()) <= {0.0, 2.0}
+    y2 = torch.tensor([[1., 0.], [0., 1.], [1., 1.]])
+    lg = torch.tensor([[2., -1.], [1., 3.], [-1., 2.]])
+    # tp = 3, predicted = 4, actual = 4 -> p = r = 0.75
+    assert abs(tga.compute_micro_f1(lg, y2) - 0.75) < 1e-9
