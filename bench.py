@@ -148,7 +148,7 @@ def timed_steps_graphed(run, mode, warmup, steps, dist):
     averager = None
     if dist is not None:
         from incagg_gnn_b200.parallel import GradAverager
-        averager = GradAverager(model.parameters(), run["shard"])
+        averager = GradAverager(model.parameters(), run["shard"], flat=getattr(opt, "flat_g", None))
     tr = GraphedTrainer(model, loader, opt, VR_update=(mode == "incagg"), grad_norm=conf["grad_norm"],
                         averager=averager)
     rp_host, ptr = loader._rowptr_host, loader.ptr
@@ -214,7 +214,7 @@ def timed_steps(run, mode, warmup, steps, dist, e2e=False):
     averager = None
     if dist is not None:
         from incagg_gnn_b200.parallel import GradAverager
-        averager = GradAverager(model.parameters(), run["shard"])
+        averager = GradAverager(model.parameters(), run["shard"], flat=getattr(opt, "flat_g", None))
     h2d = d2h = 0
 
     def one_step(sub):

@@ -62,6 +62,8 @@ _PROTOS = {
     "incagg_relu_bwd_colsum": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, P, c_int64, P, P, c_size_t, P]),
     "incagg_masked_ce_workspace_bytes": (c_size_t, [c_int64]),
     "incagg_masked_ce": (c_int, [P, c_int64, P, P, c_int64, c_int32, P, c_int64, P, P, c_size_t, P]),
+    "incagg_adam_step": (c_int, [P, P, P, P, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float,
+                                 c_float, P, P, P]),
     "incagg_csr_transpose_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "incagg_csr_transpose": (c_int, [P, P, P, c_int64, c_int64, c_int64, P, P, P, P, P, c_size_t, P]),
     "incagg_gather_rows": (c_int, [P, c_int64, c_int64, P, c_int64, P, c_int64, c_int64, P]),

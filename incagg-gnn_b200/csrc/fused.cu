@@ -197,3 +197,62 @@ extern "C" int incagg_masked_ce(const float* logits, int64_t ld, const int64_t* 
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
+
+// ---- fused Adam over flat buffers ---------------------------------------------------------------------
+// torch.optim.Adam (main.py:196-201: two parameter groups that differ in weight decay only) issues
+// ~12 multi-tensor launches per step; with all parameters / gradients / moments in flat buffers the
+// update is one launch.  Same arithmetic as torch's (non-amsgrad, L2 weight decay added to the gradient):
+//   g += wd p ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
+//   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// The step counter lives on the device (CUDA-graph friendly): the kernel reads step[0] + 1 and a
+// single thread of the last block stores it back after the grid has read it (arrival counter).
+namespace incagg {
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, int64_t n_decay, float lr, float b1, float b2,
+                            float eps, float wd_first, float wd_rest, float* step, unsigned int* arrivals) {
+  const float t = step[0] + 1.f;
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    float gi = g[i];
+    const float wd = i < n_decay ? wd_first : wd_rest;
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float m0 = m[i];
+    const float mi = m0 + (1.f - b1) * (gi - m0);          // torch: exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+  // every block has read `step` before the last arriver overwrites it
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(arrivals, 1u);
+    if (prev == gridDim.x - 1) {
+      step[0] = t;
+      *arrivals = 0u;
+    }
+  }
+}
+}  // namespace incagg
+
+extern "C" int incagg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                int64_t n_first_group, float lr, float beta1, float beta2, float eps,
+                                float wd_first_group, float wd_rest, float* step_dev, void* arrivals_dev,
+                                incagg_stream_t stream) {
+  IA_CHECK_ARG(n >= 0 && n_first_group >= 0 && n_first_group <= n, "bad sizes");
+  if (n == 0) return INCAGG_OK;
+  IA_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && step_dev && arrivals_dev, "NULL argument");
+  const int threads = 256;
+  int64_t want = (n + threads - 1) / threads;
+  const int blocks = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
+  incagg::adam_kernel<<<blocks, threads, 0, as_stream(stream)>>>(
+      params, grads, exp_avg, exp_avg_sq, n, n_first_group, lr, beta1, beta2, eps, wd_first_group, wd_rest,
+      step_dev, static_cast<unsigned int*>(arrivals_dev));
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}

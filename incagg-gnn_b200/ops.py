@@ -288,6 +288,16 @@ def masked_ce_raw(logits: Tensor, y: Tensor, mask: Tensor):
     return out3, dl
 
 
+def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, n_first: int, lr: float, beta1: float, beta2: float,
+              eps: float, wd_first: float, wd_rest: float, step: Tensor, arrivals: Tensor) -> None:
+    """One fused Adam update over flat fp32 buffers (include/incagg_b200.h, incagg_adam_step)."""
+    _require_cuda(p, g, m, v, step, arrivals)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), int(n_first), float(lr), float(beta1),
+                               float(beta2), float(eps), float(wd_first), float(wd_rest), ptr(step), ptr(arrivals),
+                               _stream()))
+
+
 # --------------------------------------------------------------------------------------------
 # rows: gather / scatter / slices
 # --------------------------------------------------------------------------------------------

@@ -201,11 +201,16 @@ class GradAverager:
     ``zero() -> backward (accumulates in place) -> all_reduce(flat) -> flat /= W`` without any packing
     copies, and the buffer addresses are static (CUDA-graph friendly)."""
 
-    def __init__(self, params, shard: Shard):
+    def __init__(self, params, shard: Shard, flat: Optional[Tensor] = None):
+        """`flat`: an existing flat gradient buffer that every ``p.grad`` already views (e.g.
+        ``train.FlatAdam.flat_g``); otherwise one is created and the gradients re-pointed into it."""
         self.params = [p for p in params if p.requires_grad]
         self.shard = shard
         p0 = self.params[0]
         self.numel = sum(p.numel() for p in self.params)
+        if flat is not None:
+            self.flat = flat
+            return
         self.flat = torch.zeros(self.numel, dtype=p0.dtype, device=p0.device)
         o = 0
         for p in self.params:

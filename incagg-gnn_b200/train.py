@@ -54,6 +54,59 @@ CONFIGS: Dict[str, Dict[str, Any]] = {
 }
 
 
+class FlatAdam:
+    """``torch.optim.Adam`` (the reference's optimizer, main.py:196-201: a weight-decayed and a
+    non-decayed parameter group) with every parameter, gradient and moment in ONE flat buffer each and
+    the update as a single kernel launch (``incagg_adam_step``) instead of ~12 multi-tensor launches.
+    Parameters and ``.grad`` become views into the flat buffers (static addresses: CUDA-graph friendly,
+    and the gradient all-reduce of ``parallel.GradAverager`` runs on the same buffer without copies).
+    Same update arithmetic as torch's Adam (no amsgrad; L2 weight decay added to the gradient)."""
+
+    def __init__(self, param_groups, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        groups = [dict(g) for g in param_groups]
+        assert 1 <= len(groups) <= 2, 'FlatAdam handles the one or two parameter groups of main.py'
+        seen, flat_list = set(), []
+        for g in groups:
+            ps = [p for p in g['params'] if p.requires_grad and id(p) not in seen]
+            seen.update(id(p) for p in ps)
+            g['params'] = ps
+            g.setdefault('weight_decay', 0.)
+            g['lr'], g['betas'], g['eps'], g['capturable'] = lr, betas, eps, True
+            flat_list += ps
+        assert flat_list and all(p.is_cuda and p.dtype == torch.float32 for p in flat_list)
+        self.param_groups = groups
+        self.params = flat_list
+        dev = flat_list[0].device
+        n = sum(p.numel() for p in flat_list)
+        self.n_first = sum(p.numel() for p in groups[0]['params'])
+        self.flat_p = torch.empty(n, device=dev)
+        self.flat_g = torch.zeros(n, device=dev)
+        self.exp_avg = torch.zeros(n, device=dev)
+        self.exp_avg_sq = torch.zeros(n, device=dev)
+        self.step_t = torch.zeros(1, device=dev)
+        self._arrivals = torch.zeros(1, dtype=torch.int32, device=dev)
+        o = 0
+        for p in flat_list:
+            k = p.numel()
+            self.flat_p[o:o + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[o:o + k].view_as(p)
+            p.grad = self.flat_g[o:o + k].view_as(p)
+            o += k
+        self.state = {'step': self.step_t, 'exp_avg': self.exp_avg, 'exp_avg_sq': self.exp_avg_sq}
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.flat_g.zero_()  # the views stay in place
+
+    @torch.no_grad()
+    def step(self):
+        from . import ops
+        g0 = self.param_groups[0]
+        wd_rest = self.param_groups[1]['weight_decay'] if len(self.param_groups) > 1 else g0['weight_decay']
+        ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.n_first, g0['lr'],
+                      g0['betas'][0], g0['betas'][1], g0['eps'], g0['weight_decay'], wd_rest, self.step_t,
+                      self._arrivals)
+
+
 def mini_train(model, loader, criterion, optimizer, max_steps, grad_norm=None, edge_dropout=0.0,
                epoch=0, VR_update=False, drift_norm=2, aggregate_combined=True,
                use_aggregation=True) -> Dict[str, float]:
@@ -282,7 +335,7 @@ def mini_test(model, loader, use_aggregation=True, VR_update=False):
 def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_device='cuda',
           overrides: Optional[Dict[str, Any]] = None, log: bool = False, data_device=None,
           shuffle: bool = True, host_resident: bool = False, data=None, rank: int = 0,
-          world_size: int = 1, transport: str = 'p2p', force_metis: bool = False):
+          world_size: int = 1, transport: str = 'p2p', force_metis: bool = False, fused_adam: bool = True):
     """Everything main.py:140-201 sets up for one named config on synthetic data: returns a dict
     with data, ptr, loaders, model, optimizer, criterion and the config."""
     conf = dict(CONFIGS[config])
@@ -331,10 +384,12 @@ def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_dev
                 **conf['architecture'], **kwargs).to(device)
     if shard is not None:
         model.shard_histories(shard, transport=transport)
-    optimizer = torch.optim.Adam([
-        dict(params=model.reg_modules.parameters(), weight_decay=conf['reg_weight_decay']),
-        dict(params=model.nonreg_modules.parameters(), weight_decay=conf['nonreg_weight_decay']),
-    ], lr=conf['lr'], capturable=torch.device(device).type == 'cuda')  # step counter on the device
+    groups = [dict(params=list(model.reg_modules.parameters()), weight_decay=conf['reg_weight_decay']),
+              dict(params=list(model.nonreg_modules.parameters()), weight_decay=conf['nonreg_weight_decay'])]
+    if fused_adam and torch.device(device).type == 'cuda':
+        optimizer = FlatAdam(groups, lr=conf['lr'])   # Adam as one launch over flat buffers
+    else:
+        optimizer = torch.optim.Adam(groups, lr=conf['lr'], capturable=torch.device(device).type == 'cuda')
     max_steps = conf['max_steps'] if conf['max_steps'] != -1 else int(conf['num_parts'] / conf['batch_size'])
     return dict(conf=conf, data=data, raw=raw, ptr=ptr, shard=shard, train_loader=train_loader, eval_loader=eval_loader,
                 model=model, optimizer=optimizer, criterion=criterion, max_steps=max_steps,

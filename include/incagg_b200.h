@@ -176,6 +176,17 @@ int incagg_masked_ce(const float* logits, int64_t ld, const int64_t* y, const ui
                      int32_t C, float* dlogits, int64_t ldd, float* out3, void* workspace,
                      size_t workspace_bytes, incagg_stream_t stream);
 
+/*
+ * One Adam step (torch.optim.Adam arithmetic, main.py:196-201) over flat fp32 buffers of n elements:
+ * the first n_first_group elements use weight decay wd_first_group, the rest wd_rest.  step_dev is a
+ * device float holding the number of steps taken (incremented by the call); arrivals_dev a zeroed
+ * device uint32 scratch.  One launch.
+ */
+int incagg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     int64_t n_first_group, float lr, float beta1, float beta2, float eps,
+                     float wd_first_group, float wd_rest, float* step_dev, void* arrivals_dev,
+                     incagg_stream_t stream);
+
 /* ---- CSR transpose (CSC view for the backward SpMM) ------------------- */
 /*
  * Counting-sort transpose of a [rows x cols] CSR with nnz entries.

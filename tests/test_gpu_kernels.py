@@ -500,3 +500,29 @@ def test_relu_bwd_colsum_and_masked_ce(ops, cuda):
     # empty mask: zero loss, zero gradient
     loss0, o0 = masked_cross_entropy(logits.detach(), y, torch.zeros_like(mask))
     assert float(loss0) == 0. and float(o0[2]) == 0.
+
+
+def test_flat_adam_matches_torch_adam(ops, cuda):
+    """The fused one-launch Adam (incagg_adam_step) follows torch.optim.Adam step by step (two groups
+    with different weight decay, as main.py:196-201 builds them)."""
+    from incagg_gnn_b200.train import FlatAdam
+    g = torch.Generator().manual_seed(6)
+    shapes = [(64, 32), (32,), (48, 64), (7,)]
+    init = [torch.randn(*s, generator=g) for s in shapes]
+    pa = [torch.nn.Parameter(t.clone().to(cuda)) for t in init]
+    pb = [torch.nn.Parameter(t.clone().to(cuda).double()) for t in init]
+    ours = FlatAdam([dict(params=pa[:2], weight_decay=0.01), dict(params=pa[2:], weight_decay=0.0)], lr=0.01)
+    ref = torch.optim.Adam([dict(params=pb[:2], weight_decay=0.01), dict(params=pb[2:], weight_decay=0.0)], lr=0.01)
+    for step in range(6):
+        grads = [torch.randn(*s, generator=g) for s in shapes]
+        ours.zero_grad()
+        for p, gr in zip(pa, grads):
+            p.grad.add_(gr.to(cuda))          # accumulate into the flat views, as autograd does
+        for p, gr in zip(pb, grads):
+            p.grad = gr.to(cuda).double()
+        ours.step()
+        ref.step()
+        for a, b in zip(pa, pb):
+            assert float((a.detach().double() - b.detach()).abs().max()) <= 2e-6, step
+    assert float(ours.step_t) == 6.0
+    assert pa[0].data_ptr() == ours.flat_p.data_ptr() and pa[0].grad.data_ptr() == ours.flat_g.data_ptr()

@@ -43,7 +43,7 @@ for transport, vr in itertools.product(("nccl", "p2p"), (False, True)):
     ok &= same
     # one training epoch in lockstep
     model, opt = sharded["model"], sharded["optimizer"]
-    avg = GradAverager(model.parameters(), sh)
+    avg = GradAverager(model.parameters(), sh, flat=getattr(opt, "flat_g", None))
     model.train()
     tot = 0.0
     for batch, B, n_id, offset, count in sharded["train_loader"]:
