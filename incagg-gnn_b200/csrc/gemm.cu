@@ -298,6 +298,7 @@ gemm_tf32x3_kernel(const GemmParams p) {
   }
   if (p.dual == DUAL_M && bx >= p.tiles1) {
     bx -= p.tiles1; Aptr = p.A2; lda = p.lda2; Dptr = p.D2; ldd = p.ldd2; alpha_e = p.alpha2;
+    Cin = p.Cin2; ldcin = p.ldcin2; beta_e = p.beta2;
   }
   const int64_t m0 = (int64_t)bx * G_BM, n0 = (int64_t)by * BN;
   const int64_t num_kb_total = (p.dual == DUAL_K) ? (p.kb1 + (p.K2 + G_BK - 1) / G_BK) : (p.K + G_BK - 1) / G_BK;
@@ -483,7 +484,9 @@ __global__ void gemm_splitk_reduce_kernel(const GemmParams p, int splits) {
       if (p.relu) x = fmaxf(x, 0.f);
       p.D[m * p.ldd + n] = x;
     } else {
-      p.D2[m * p.ldd2 + n] = p.alpha2 * acc;
+      float x = p.alpha2 * acc;
+      if (p.Cin2 && p.beta2 != 0.f) x += p.beta2 * p.Cin2[m * p.ldcin2 + n];
+      p.D2[m * p.ldd2 + n] = x;
     }
   }
 }

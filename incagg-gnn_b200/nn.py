@@ -19,6 +19,16 @@ from .sparse import SparseTensor, spmm
 
 
 # ---- dense transforms on the tensor cores ---------------------------------------------------------
+def _grad_buffer(param) -> Optional[Tensor]:
+    """The persistent gradient buffer of a parameter whose ``.grad`` is a view into a flat buffer
+    (train.FlatAdam marks its parameters): weight-gradient GEMMs then accumulate straight into it through
+    their epilogue (Cin = D = grad, beta = 1) and return no gradient to autograd, which saves one
+    elementwise ``grad += new`` launch per parameter per step."""
+    if getattr(param, '_flat_grad', False) and param.grad is not None:
+        return param.grad
+    return None
+
+
 class _LinearTC(torch.autograd.Function):
     """y = x W^T + b (optionally ReLU) on the tcgen05 3xTF32 GEMM; backward = two more GEMMs of the
     same kernel (input gradient g W, weight gradient g^T x with deterministic split-K)."""
@@ -29,6 +39,7 @@ class _LinearTC(torch.autograd.Function):
         ctx.relu = relu
         ctx.save_for_backward(x, weight, y if relu else None)
         ctx.has_bias = bias is not None
+        ctx.weight_param = weight
         return y
 
     @staticmethod
@@ -48,7 +59,11 @@ class _LinearTC(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = ops.gemm(g, weight)                      # [M,N] x [N,K]
         if ctx.needs_input_grad[1]:
-            gw = ops.gemm(g, x, trans_a=True)             # g^T x : [N,M] x [M,K]
+            buf = _grad_buffer(ctx.weight_param)
+            if buf is not None:                           # accumulate in the GEMM epilogue
+                ops.gemm(g, x, trans_a=True, cin=buf, beta=1., out=buf)
+            else:
+                gw = ops.gemm(g, x, trans_a=True)         # g^T x : [N,M] x [M,K]
         return gx, gw, gb, None
 
 
@@ -89,6 +104,7 @@ class _GCN2Dense(torch.autograd.Function):
                                 cin=h, beta=(1. - b) * (1. - a), cin2=x0, beta2=(1. - b) * a, relu=relu)
             ctx.save_for_backward(h, x0, w1, w2, out if relu else None, None)
         ctx.a, ctx.b, ctx.relu, ctx.shared = a, b, relu, w2 is None
+        ctx.w1_param, ctx.w2_param = w1, w2
         return out
 
     @staticmethod
@@ -107,7 +123,12 @@ class _GCN2Dense(torch.autograd.Function):
         else:
             gh, gx0 = ops.gemm_dual("n", g, w1, b2=w2, trans_b=True, scale_b=b * (1. - a), scale_b2=b * a,
                                     cin=g, beta=(1. - b) * (1. - a), cin2=g, beta2=(1. - b) * a)
-            gw1, gw2 = ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a)
+            b1, b2 = _grad_buffer(ctx.w1_param), _grad_buffer(ctx.w2_param)
+            if b1 is not None and b2 is not None:         # accumulate into the flat gradient buffers
+                ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a,
+                              cin=b1, beta=1., cin2=b2, beta2=1., out=b1, out2=b2)
+            else:
+                gw1, gw2 = ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a)
         return gh, gx0, gw1, gw2, None, None, None
 
 

@@ -91,6 +91,7 @@ class FlatAdam:
             self.flat_p[o:o + k].copy_(p.detach().reshape(-1))
             p.data = self.flat_p[o:o + k].view_as(p)
             p.grad = self.flat_g[o:o + k].view_as(p)
+            p._flat_grad = True   # nn._grad_buffer: weight-gradient GEMMs accumulate into the view
             o += k
         self.state = {'step': self.step_t, 'exp_avg': self.exp_avg, 'exp_avg_sq': self.exp_avg_sq}
 

@@ -144,8 +144,9 @@ int incagg_gemm_tf32x3(int transA, int transB, int64_t M, int64_t N, int64_t K, 
  *                             A [M,K], A2 [M,K2]: forward  [h | x0] · [c1 W1 ; c2 W2]
  *   mode 2 (N-concatenation)  D  = alpha  * A·(scaleB  B ) + beta  Cin
  *                             D2 = alpha2 * A·(scaleB2 B2) + beta2 Cin2   (shared A): input gradients
- *   mode 3 (M-concatenation)  D  = alpha  * op(A )·B ,  D2 = alpha2 * op(A2)·B   (shared B; split-K with
- *                             the workspace): weight gradients  [h | x0]^T · g
+ *   mode 3 (M-concatenation)  D  = alpha  * op(A )·B + beta Cin ,  D2 = alpha2 * op(A2)·B + beta2 Cin2
+ *                             (shared B; split-K with the workspace): weight gradients  [h | x0]^T · g,
+ *                             accumulated in place into the gradient buffers when Cin == D
  * Same layout flags, accuracy and epilogue rules as incagg_gemm_tf32x3; M2 = M, N2 = N.
  */
 int incagg_gemm_tf32x3_dual(int mode, int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t K2,
