@@ -165,12 +165,6 @@ def pull_halo_rows(table_local: Tensor, plan: HaloPlan, out: Tensor, width: Opti
     return out
 
 
-def idle_exchange(shard: Shard) -> None:
-    """Take part in one halo exchange without needing rows (a rank that has run out of batches while
-    others still pull).  Serves whatever the others request from an empty request of its own."""
-    raise NotImplementedError('ranks run the same number of steps (Shard.steps_per_epoch)')
-
-
 def open_peer_views(t: Tensor, shard: Shard):
     """Map every rank's copy of a (differently sized) table into this process: returns one tensor per
     rank (this rank's own tensor at its index).  The peers' storages are opened through CUDA IPC *in
