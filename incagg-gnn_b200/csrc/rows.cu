@@ -13,6 +13,8 @@
 //   * contiguous slices between pinned host memory and the device go through cudaMemcpyAsync
 //     (DMA engines, overlappable with kernels); device<->device slices use one kernel launch
 //     for up to 64 slices instead of one memcpy per slice.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace incagg {
@@ -147,6 +149,86 @@ slice_rows_kernel(const char* __restrict__ src, int64_t src_ld, char* __restrict
     for (int u = 0; u < ROWS_UNROLL; ++u)
       if (doff[u] >= 0) *reinterpret_cast<V*>(dst + doff[u]) = v[u];
   }
+}
+
+// ---- TMA bulk slice copies ------------------------------------------------------------------------
+// A partition's rows are one contiguous byte range on both sides when the tables are dense
+// (ld == row bytes): the push / pull of a slice is then a plain byte-range copy, which the TMA engine
+// does without occupying load/store units: cp.async.bulk global -> shared (completion counted on an
+// mbarrier) and cp.async.bulk shared -> global (bulk groups), a ring of BULK_STAGES chunks per CTA,
+// one elected thread issues everything.  Needs 16-byte aligned addresses and sizes.
+constexpr int BULK_CHUNK = 16384;
+constexpr int BULK_STAGES = 4;
+
+struct BulkTable {
+  int64_t src_off[MAX_SLICES];      // byte offset of each slice in src
+  int64_t dst_off[MAX_SLICES];      // byte offset of each slice in dst
+  int64_t chunk_prefix[MAX_SLICES + 1];  // chunks before slice i
+  int64_t bytes[MAX_SLICES];
+  int k;
+};
+
+__device__ __forceinline__ uint32_t rows_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__global__ void __launch_bounds__(32)
+slice_bulk_kernel(const char* __restrict__ src, char* __restrict__ dst, const BulkTable tab) {
+  extern __shared__ __align__(128) char bulk_smem[];
+  __shared__ uint64_t bar[BULK_STAGES];
+  if (threadIdx.x != 0) return;  // one thread drives the TMA engine
+  for (int s = 0; s < BULK_STAGES; ++s)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rows_smem_u32(&bar[s])));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  const int64_t n_chunks = tab.chunk_prefix[tab.k];
+  const int64_t first = blockIdx.x, step = gridDim.x;
+  // chunk index -> (src pointer, dst pointer, bytes)
+  auto locate = [&](int64_t c, const char*& sp, char*& dp, uint32_t& nb) {
+    int lo = 0, hi = tab.k;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (tab.chunk_prefix[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int64_t within = (c - tab.chunk_prefix[lo]) * BULK_CHUNK;
+    const int64_t left = tab.bytes[lo] - within;
+    nb = (uint32_t)(left < BULK_CHUNK ? left : BULK_CHUNK);
+    sp = src + tab.src_off[lo] + within;
+    dp = dst + tab.dst_off[lo] + within;
+  };
+  auto issue_load = [&](int64_t c, int stage) {
+    const char* sp; char* dp; uint32_t nb;
+    locate(c, sp, dp, nb);
+    const uint32_t b = rows_smem_u32(&bar[stage]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(nb) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(rows_smem_u32(bulk_smem + (size_t)stage * BULK_CHUNK)), "l"(sp), "r"(nb), "r"(b)
+                 : "memory");
+  };
+  // prologue: fill the ring
+  int64_t next = first;
+  for (int s = 0; s < BULK_STAGES && next < n_chunks; ++s, next += step) issue_load(next, s);
+  int it = 0;
+  for (int64_t c = first; c < n_chunks; c += step, ++it) {
+    const int stage = it % BULK_STAGES;
+    const uint32_t parity = (uint32_t)((it / BULK_STAGES) & 1);
+    const uint32_t b = rows_smem_u32(&bar[stage]);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_LOAD:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_LOAD;\n\tbra WAIT_LOAD;\n\tDONE_LOAD:\n\t}" ::"r"(b), "r"(parity) : "memory");
+    const char* sp; char* dp; uint32_t nb;
+    locate(c, sp, dp, nb);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dp), "r"(rows_smem_u32(bulk_smem + (size_t)stage * BULK_CHUNK)), "r"(nb) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (next < n_chunks) {
+      // the stage is reloaded only after its store has finished READING shared memory
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      issue_load(next, stage);
+      next += step;
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before exit
 }
 
 static int pick_vb(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t row_bytes) {
@@ -298,6 +380,40 @@ extern "C" int incagg_copy_slices(const void* src, int64_t src_ld_bytes, int64_t
                                   (size_t)row_bytes, (size_t)c, cudaMemcpyDefault, st));
       }
       p += c;
+    }
+    return INCAGG_OK;
+  }
+  // Device <-> device, dense rows on both sides, 16-byte aligned: TMA bulk copies.
+  static const bool use_bulk = []() { const char* e = getenv("INCAGG_SLICE_BULK"); return !(e && e[0] == '0'); }();
+  if (use_bulk && src_ld_bytes == row_bytes && dst_ld_bytes == row_bytes && row_bytes % 16 == 0 &&
+      (reinterpret_cast<uintptr_t>(src) % 16) == 0 && (reinterpret_cast<uintptr_t>(dst) % 16) == 0 &&
+      packed * row_bytes >= 4 * BULK_CHUNK) {
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+      IA_CUDA(cudaFuncSetAttribute(slice_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   BULK_STAGES * BULK_CHUNK));
+      attr_set = true;
+    }
+    int64_t pk = 0;
+    for (int64_t i0 = 0; i0 < k; i0 += MAX_SLICES) {
+      BulkTable tab;
+      const int kk = (int)((k - i0) < MAX_SLICES ? (k - i0) : MAX_SLICES);
+      tab.k = kk;
+      tab.chunk_prefix[0] = 0;
+      for (int i = 0; i < kk; ++i) {
+        const int64_t o = offset[i0 + i] * row_bytes, c = count[i0 + i] * row_bytes, pb = pk * row_bytes;
+        tab.src_off[i] = direction == 0 ? o : pb;
+        tab.dst_off[i] = direction == 0 ? pb : o;
+        tab.bytes[i] = c;
+        tab.chunk_prefix[i + 1] = tab.chunk_prefix[i] + (c + BULK_CHUNK - 1) / BULK_CHUNK;
+        pk += count[i0 + i];
+      }
+      const int64_t n_chunks = tab.chunk_prefix[kk];
+      if (n_chunks == 0) continue;
+      int64_t grid = (int64_t)sm_count() * 3;  // 64 KB of shared memory per CTA -> 3 CTAs per SM
+      if (grid > n_chunks) grid = n_chunks;
+      slice_bulk_kernel<<<(unsigned)grid, 32, BULK_STAGES * BULK_CHUNK, st>>>(s, d, tab);
+      IA_LAUNCH_CHECK();
     }
     return INCAGG_OK;
   }

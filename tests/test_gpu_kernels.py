@@ -526,3 +526,34 @@ def test_flat_adam_matches_torch_adam(ops, cuda):
             assert float((a.detach().double() - b.detach()).abs().max()) <= 2e-6, step
     assert float(ours.step_t) == 6.0
     assert pa[0].data_ptr() == ours.flat_p.data_ptr() and pa[0].grad.data_ptr() == ours.flat_g.data_ptr()
+
+
+def test_copy_slices_tma_bulk_path(ops, cuda):
+    """Dense device<->device slices large enough for the cp.async.bulk (TMA) kernel: ragged chunk tails,
+    many slices, both directions, bit-exact."""
+    g = torch.Generator().manual_seed(9)
+    N, D = 60000, 128
+    table = torch.randn(N, D, generator=g).to(cuda)
+    offset = torch.tensor([20000, 30000, 7, 45000, 59990])   # disjoint ranges (partitions never overlap)
+    count = torch.tensor([4097, 123, 16385, 1, 10])          # chunk = 32 rows of 512 B: ragged tails
+    total = int(count.sum())
+    packed = torch.zeros(total, D, device=cuda)
+    ops.copy_slices(table, packed, offset, count, 0)
+    exp = torch.cat([table[o:o + c] for o, c in zip(offset.tolist(), count.tolist())])
+    assert torch.equal(packed, exp)
+    new = torch.randn(total, D, generator=g).to(cuda)
+    t2 = table.clone()
+    ops.copy_slices(new, t2, offset, count, 1)
+    ref = table.clone()
+    s = 0
+    for o, c in zip(offset.tolist(), count.tolist()):
+        ref[o:o + c] = new[s:s + c]
+        s += c
+    assert torch.equal(t2, ref)
+    # > 64 slices in one call
+    k = 200
+    off = torch.arange(k) * 250
+    cnt = torch.full((k,), 100, dtype=torch.int64)
+    pk = torch.zeros(100 * k, D, device=cuda)
+    ops.copy_slices(table, pk, off, cnt, 0)
+    assert torch.equal(pk, torch.cat([table[o:o + 100] for o in off.tolist()]))
