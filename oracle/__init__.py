@@ -16,6 +16,11 @@ Contents
     reference nor installed here, and the reference pins no version and holds no test vectors for
     them; the restatement follows their published semantics and is anchored on the
     reference's call sites.
+  * ``run_ref_async.py`` + ``build_ref_async.sh``: the reference's own ``read_async`` / ``write_async``
+    (csrc/async.cpp + csrc/cuda/async_cuda.cu) compiled for sm_100a into ``oracle/_ref/ref_async.so`` and
+    run on the GPU box in a subprocess.  PINNED: the product's transfer ops and the restatement in
+    ``gas.py`` (``pull_slices_and_index`` / ``push_slices``) reproduce its output byte for byte
+    (tests/test_gpu_ref_async.py).
   * ``gas.py``: pure-torch (CPU, fp32/fp64) restatement of History push/pull (history.py:33-65),
     push_and_pull's synchronous branch (models/base.py:411-426), the GAS and IncAgg training steps
     and the layer-wise sweeps of GCN / GCN2 / APPNP / GraphSAGE / PNA (files and lines cited per
