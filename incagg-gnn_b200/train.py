@@ -132,16 +132,41 @@ def mini_train(model, loader, criterion, optimizer, max_steps, grad_norm=None, e
     return {'loss': tl / max(te, 1.), 'steps': steps}
 
 
+_SIDE_STREAMS = {}
+
+
+def _backward_prep(adj_t, batch_size, VR_update):
+    """Fork: build adj_t's transposed CSR + SpMM plans on a side stream.  Returns the stream to join."""
+    if not adj_t.col.is_cuda or adj_t.nnz() == 0:
+        return None
+    dev = adj_t.col.device
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        adj_t.t_csr()
+        adj_t.t_plan()
+        if not VR_update and batch_size < adj_t.size(1):
+            adj_t.t_plan_prefix(batch_size)
+    return side
+
+
 def forward_backward(model, sub, optimizer, VR_update=False, averager=None, epoch=0, batch_idx=0):
     """Forward + loss + backward of one mini_train iteration on an already collated batch.  Returns
     (loss * n_train, n_train) as device scalars (no host synchronisation)."""
     batch, batch_size, n_id, offset, count = sub
     x, adj_t = batch.x, batch.adj_t
     y, train_mask = batch.y[:batch_size], batch.train_mask[:batch_size]
+    # The transposed CSR and the plans that only the backward pass needs are built on a side stream
+    # while the forward pass runs (a fork / join that CUDA-graph capture records as parallel branches).
+    side = _backward_prep(adj_t, batch_size, VR_update)
     if VR_update:
         out = model.VR_call(x, adj_t, batch_size, n_id, offset, count, epoch=epoch, batch_idx=batch_idx)['out']
     else:
         out = model(x, adj_t, batch_size, n_id, offset, count)['out']
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)
     if averager is not None:
         averager.zero()  # gradients are views into the averager's flat buffer
     else:
