@@ -34,7 +34,6 @@ namespace incagg {
 
 constexpr int G_BM = 128;
 constexpr int G_BK = 32;     // 32 tf32 = 128 bytes = one swizzle row
-constexpr int G_STAGES = 3;
 constexpr int G_THREADS = 256;
 
 enum { DUAL_NONE = 0, DUAL_K = 1, DUAL_N = 2, DUAL_M = 3 };
@@ -151,10 +150,17 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Round to TF32 (10 explicit mantissa bits), ties away from zero = cvt.rna.tf32.f32.  ptxas expands
+// the cvt into four instructions (it special-cases Inf / NaN); on the bit pattern it is one add and
+// one mask, and Inf / NaN keep their class (0x7f800000 + 0x1000 masks back to Inf).
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
 // ---- tile loader ----------------------------------------------------------------------------------
@@ -176,14 +182,23 @@ __device__ __noinline__ float4 ldg4_guarded(const float* p, int valid) {
   if (valid > 3) r.w = __ldg(p + 3);
   return r;
 }
+// edge tiles: a whole in-range, aligned float4 is still one vector load; only the straddling ones
+// (and unaligned sources) take the scalar path
+__device__ __forceinline__ float4 ldg4_edge(const float* p, int valid, bool vec_ok) {
+  if (valid >= 4 && vec_ok) return __ldg(reinterpret_cast<const float4*>(p));
+  if (valid <= 0) return make_float4(0.f, 0.f, 0.f, 0.f);
+  return ldg4_guarded(p, valid);
+}
 
 // Thread -> element mapping.
 //   !TRANS: chunk c = tid & 7 (16 bytes of the 128-byte k-row), row r = (tid >> 3) + 32 i.  A quarter
 //           warp writes the 8 chunks of one row: the XOR swizzle keeps them on distinct banks.
-//   TRANS : a warp owns a 4 (k) x 32 (rows) patch: kq = lane >> 3, m4 = lane & 7 -> one float4 along
-//           the rows; patch index wt = warp + 8 i, k-group = wt & 7, row-group = wt >> 3.  The four
-//           elements of a float4 go to four different tile rows; element j = (t + (m4 >> 1)) & 3 is
-//           written in store instruction t, which spreads the 32 lanes over all 32 banks.
+//   TRANS : a warp owns a 16 (k) x 8 (rows) patch: kq = lane & 3, cq = (lane >> 2) & 3 -> k = 16 kh +
+//           4 cq + kq, mh = lane >> 4 -> one float4 along the rows (two lanes read one 32-byte sector
+//           of a k-row); patch index ub = warp + 8 i, kh = ub & 1, row group mg = 2 (ub >> 1) + mh.
+//           Element j of the float4 goes to tile row 4 mg + j at 16-byte chunk (k >> 2) ^ (row & 7) =
+//           4 (kh ^ mh) + (cq ^ j): for a fixed j the 32 lanes hit 32 different banks, so the four
+//           scalar stores use compile-time register indices and no conflicts.
 template <int ROWS, bool TRANS>
 __device__ __forceinline__ void load_tile(const float* __restrict__ src, int64_t ld, int64_t row0,
                                           int64_t rows_total, int64_t k0, int64_t k_end, bool vec_ok,
@@ -198,72 +213,68 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ src, int64_t
 #pragma unroll
       for (int i = 0; i < ROWS / 32; ++i) t.v[i] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(32 * i) * ld));
     } else {
+      const int kvalid = (int)min((int64_t)4, k_end - k);
 #pragma unroll
       for (int i = 0; i < ROWS / 32; ++i) {
         const int64_t r = row0 + (tid >> 3) + 32 * i;
-        const int valid = (r < rows_total) ? (int)min((int64_t)4, k_end - k) : 0;
-        t.v[i] = ldg4_guarded(base + (int64_t)(32 * i) * ld, valid);
+        t.v[i] = ldg4_edge(base + (int64_t)(32 * i) * ld, (r < rows_total) ? kvalid : 0, vec_ok);
       }
     }
   } else {
     const int lane = tid & 31, warp = tid >> 5;
-    const int kq = lane >> 3, m4 = lane & 7;
+    const int kl = (lane & 15), mh = lane >> 4;
     if (fast) {
 #pragma unroll
       for (int i = 0; i < ROWS / 32; ++i) {
-        const int wt = warp + 8 * i;
-        t.v[i] = __ldg(reinterpret_cast<const float4*>(src + (k0 + (wt & 7) * 4 + kq) * ld + row0 + (wt >> 3) * 32 + m4 * 4));
+        const int ub = warp + 8 * i;
+        t.v[i] = __ldg(reinterpret_cast<const float4*>(src + (k0 + (ub & 1) * 16 + kl) * ld + row0 + ((ub >> 1) * 2 + mh) * 4));
       }
     } else {
 #pragma unroll
       for (int i = 0; i < ROWS / 32; ++i) {
-        const int wt = warp + 8 * i;
-        const int64_t k = k0 + (wt & 7) * 4 + kq;
-        const int64_t r = row0 + (wt >> 3) * 32 + m4 * 4;
-        const int valid = (k < k_end) ? (int)min((int64_t)4, rows_total - r) : 0;
-        t.v[i] = ldg4_guarded(src + k * ld + r, valid);
+        const int ub = warp + 8 * i;
+        const int64_t k = k0 + (ub & 1) * 16 + kl;
+        const int64_t r = row0 + ((ub >> 1) * 2 + mh) * 4;
+        t.v[i] = ldg4_edge(src + k * ld + r, (k < k_end) ? (int)min((int64_t)4, rows_total - r) : 0, vec_ok);
       }
     }
   }
 }
 
-// Split into hi / lo TF32 parts and store into the two swizzled K-major tiles.
+// Split into hi / lo TF32 parts and store into the two swizzled K-major tiles (shared-window addresses).
 template <int ROWS, bool TRANS>
-__device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, char* hi, char* lo, float scale = 1.f) {
+__device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, uint32_t hi, uint32_t lo, float scale = 1.f) {
   const int tid = threadIdx.x;
   if constexpr (!TRANS) {
-    const int c = tid & 7;
+    const int c = tid & 7, r0 = tid >> 3;  // r & 7 = r0 & 7 for every i
+    const uint32_t off0 = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));
 #pragma unroll
     for (int i = 0; i < ROWS / 32; ++i) {
-      const int r = (tid >> 3) + 32 * i;
       float4 x = t.v[i];
       x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
       float4 h, l;
       h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
       l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
-      const int off = r * 128 + ((c ^ (r & 7)) << 4);
-      *reinterpret_cast<float4*>(hi + off) = h;
-      *reinterpret_cast<float4*>(lo + off) = l;
+      sts128(hi + off0 + i * 32 * 128, h);
+      sts128(lo + off0 + i * 32 * 128, l);
     }
   } else {
     const int lane = tid & 31, warp = tid >> 5;
-    const int kq = lane >> 3, m4 = lane & 7;
+    const int kq = lane & 3, cq = (lane >> 2) & 3, mh = lane >> 4;
 #pragma unroll
     for (int i = 0; i < ROWS / 32; ++i) {
-      const int wt = warp + 8 * i;
-      const int k = (wt & 7) * 4 + kq;
-      const int rbase = (wt >> 3) * 32 + m4 * 4;
-      const float4 x = t.v[i];
+      const int ub = warp + 8 * i;
+      const int kc = (ub & 1) * 4 + cq;                 // 16-byte chunk of k within the 128-byte row
+      const int rbase = ((ub >> 1) * 2 + mh) * 4;       // rbase & 7 = 4 mh
+      const float xs[4] = {t.v[i].x, t.v[i].y, t.v[i].z, t.v[i].w};
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int j = (s + (m4 >> 1)) & 3;
-        const float xv = (j == 0 ? x.x : (j == 1 ? x.y : (j == 2 ? x.z : x.w))) * scale;
-        const int r = rbase + j;
+      for (int j = 0; j < 4; ++j) {
+        const float xv = xs[j] * scale;
         const float h = to_tf32(xv);
         const float l = to_tf32(xv - h);
-        const int off = r * 128 + (((k >> 2) ^ (r & 7)) << 4) + (k & 3) * 4;
-        *reinterpret_cast<float*>(hi + off) = h;
-        *reinterpret_cast<float*>(lo + off) = l;
+        const uint32_t off = (uint32_t)((rbase + j) * 128 + ((kc ^ (mh * 4 + j)) << 4) + kq * 4);
+        sts32(hi + off, h);
+        sts32(lo + off, l);
       }
     }
   }
@@ -271,9 +282,15 @@ __device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, char* hi, ch
 
 // TA: A is stored [K, M] (contiguous along m).  TBK: B is stored [K, N] (contiguous along n), i.e.
 // transB == 0 of the C ABI; both make the loader transpose on the way into shared memory.
+// BN = 128: three stages, one CTA per SM.  BN = 64: two stages (96 KB), two CTAs per SM - the small
+// problems of this path (16 K rows) are latency-bound single waves, and a second resident CTA
+// overlaps one CTA's loads / splits with the other's MMAs and epilogue.
+template <int BN> struct GemmCfg { static constexpr int STAGES = (BN == 64) ? 2 : 3; static constexpr int MIN_CTAS = (BN == 64) ? 2 : 1; };
+
 template <int BN, bool TA, bool TBK>
-__global__ void __launch_bounds__(G_THREADS, 1)
+__global__ void __launch_bounds__(G_THREADS, GemmCfg<BN>::MIN_CTAS)
 gemm_tf32x3_kernel(const GemmParams p) {
+  constexpr int G_STAGES = GemmCfg<BN>::STAGES;
   extern __shared__ __align__(1024) char smem_raw[];
   // 1024-byte alignment of every tile (the swizzle is a function of the absolute smem address)
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -337,11 +354,12 @@ gemm_tf32x3_kernel(const GemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_slot;
+  const uint32_t smem_base = smem_u32(smem);
 
 #pragma unroll 1
   for (int kb = 0; kb < num_kb; ++kb) {
     const int s = kb % G_STAGES;
-    char* st = smem + (size_t)s * STAGE_BYTES;
+    const uint32_t st = smem_base + (uint32_t)(s * STAGE_BYTES);
     if (kb >= G_STAGES) mbar_wait(&mma_done[s], (uint32_t)(((kb / G_STAGES) - 1) & 1));  // stage free?
     store_tile<G_BM, TA>(ra, st, st + A_BYTES);
     store_tile<BN, TBK>(rb, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES,
@@ -353,7 +371,7 @@ gemm_tf32x3_kernel(const GemmParams p) {
     if (warp == 0) {
       if (lane == 0) {
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_BYTES;
+        const uint32_t a_hi = st, a_lo = a_hi + A_BYTES;
         const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
         const uint64_t d_ahi = umma_desc(a_hi), d_alo = umma_desc(a_lo);
         const uint64_t d_bhi = umma_desc(b_hi), d_blo = umma_desc(b_lo);
@@ -494,7 +512,7 @@ __global__ void gemm_splitk_reduce_kernel(const GemmParams p, int splits) {
 template <int BN, bool TA, bool TBK>
 static int launch_gemm_t(const GemmParams& p, int splits, cudaStream_t st) {
   constexpr int STAGE_BYTES = 2 * G_BM * 128 + 2 * BN * 128;
-  constexpr int SMEM = G_STAGES * STAGE_BYTES + 1024;
+  constexpr int SMEM = GemmCfg<BN>::STAGES * STAGE_BYTES + 1024;
   static thread_local bool attr_set = false;
   if (!attr_set) {
     IA_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, TA, TBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -517,8 +535,12 @@ static int launch_gemm(const GemmParams& p, int splits, cudaStream_t st) {
 }
 
 static int run_gemm(GemmParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  const int bn = (p.N <= 64) ? 64 : 128;
-  const int64_t mt = (p.M + G_BM - 1) / G_BM, nt = (p.N + bn - 1) / bn;
+  // 64-wide n-tiles (two CTAs per SM) whenever 128-wide ones would not fill one wave
+  const int64_t mt = (p.M + G_BM - 1) / G_BM;
+  const int64_t tiles128 = mt * ((p.N + 127) / 128) * (p.dual == DUAL_M || p.dual == DUAL_N ? 2 : 1);
+  static const int force_bn = getenv("INCAGG_GEMM_BN") ? atoi(getenv("INCAGG_GEMM_BN")) : 0;
+  const int bn = force_bn ? ((p.N <= 64) ? 64 : force_bn) : ((p.N <= 64 || tiles128 <= sm_count()) ? 64 : 128);
+  const int64_t nt = (p.N + bn - 1) / bn;
   p.tiles1 = (int)(p.dual == DUAL_N ? nt : mt);
   const int64_t gx = mt * (p.dual == DUAL_M ? 2 : 1), gy = nt * (p.dual == DUAL_N ? 2 : 1);
   p.Mpad = gx * G_BM;

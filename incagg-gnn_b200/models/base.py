@@ -74,6 +74,7 @@ class ScalableGNN(torch.nn.Module):
         self.pool_ag: Optional[AsyncIOPool] = None
 
         self._async = False
+        self._pull_stream = None
         self.__out: Optional[Tensor] = None
         self.shard = None      # parallel.Shard when the history tables are sharded over ranks
         self._row_lo = 0       # first global row of this rank's shard
@@ -262,6 +263,35 @@ class ScalableGNN(torch.nn.Module):
         out = _PushPull.apply(x, fill, batch_size, n_tail)
         self.pool.free_pull()
         return out, 0.
+
+    def pull_ahead(self, histories, x: Tensor, batch_size: Optional[int], n_id: Optional[Tensor]):
+        """GAS steps pull the halo rows n_id[B:] and push the batch rows n_id[:B]: disjoint rows, so no
+        pull depends on anything the step computes.  All of a step's pulls are therefore issued up
+        front on a side stream (a parallel branch of the captured graph), each into the tail of a
+        [B + H, F] buffer whose head the layer's GEMM later writes in place.  Returns one
+        (buffer, event) per history - the consumer waits for the event - or None when the step does
+        not take this path (host histories / NCCL transport / full-batch)."""
+        if (n_id is None or batch_size is None or self._async or not x.is_cuda
+                or not self.emb_device.type == 'cuda' or getattr(n_id, 'halo_plan', None) is not None):
+            return None
+        n_tail = n_id.numel() - batch_size
+        main = torch.cuda.current_stream(x.device)
+        side = self._pull_stream
+        if side is None:
+            side = self._pull_stream = torch.cuda.Stream(x.device)
+        bufs = [torch.empty((batch_size + n_tail, h.emb.size(1)), dtype=x.dtype, device=x.device)
+                for h in histories]
+        side.wait_stream(main)
+        idx = n_id[batch_size:]
+        out = []
+        with torch.cuda.stream(side):
+            for h, buf in zip(histories, bufs):
+                if n_tail > 0:
+                    self._pull_rows(h.emb, idx, n_id, buf[batch_size:])
+                ev = torch.cuda.Event()
+                ev.record(side)
+                out.append((buf, ev))
+        return out
 
     def push_only(self, history, x: Tensor, batch_size: Optional[int] = None,
                   n_id: Optional[Tensor] = None, offset: Optional[Tensor] = None,

@@ -81,12 +81,20 @@ class GCN2(ScalableGNN):
         x0b = x_0[:adj_t.size(0)]
         if use_aggregation:
             adj_t = select_edges(adj_t, batch_size, aggregate_combined)
+            ahead = self.pull_ahead(self.histories[:self.num_layers - 1], x, batch_size, n_id) if fuse else None
             for i, (conv, hist) in enumerate(zip(self.convs[:-1], self.histories)):
                 # rows >= B of x are constants (pulled history) after the first push_and_pull
-                h = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=fuse)
-                x = h if fuse else self._post(i, h, x)
-                x, t = self.push_and_pull(hist, x, batch_size, n_id, offset, count)
-                t_all += t
+                if ahead is not None:
+                    # the layer GEMM writes rows [0, B) of the buffer whose tail the early pull fills
+                    buf, pulled = ahead[i]
+                    x = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=True, out_full=buf)
+                    hist.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
+                    torch.cuda.current_stream().wait_event(pulled)
+                else:
+                    h = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=fuse)
+                    x = h if fuse else self._post(i, h, x)
+                    x, t = self.push_and_pull(hist, x, batch_size, n_id, offset, count)
+                    t_all += t
                 x = F.dropout(x, p=self.dropout, training=self.training)
             h = self.convs[-1](x, x0b, adj_t,
                                grad_rows=batch_size if self.num_layers > 1 else None, relu=fuse)

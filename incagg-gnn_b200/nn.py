@@ -94,25 +94,38 @@ class _GCN2Dense(torch.autograd.Function):
     (The reference path issues ~10 elementwise / addmm launches forward and ~20 backward here.)"""
 
     @staticmethod
-    def forward(ctx, h, x0, w1, w2, a, b, relu):
+    def forward(ctx, h, x0, w1, w2, a, b, relu, out_full=None):
+        # out_full: a [B + H, F] buffer whose tail rows (pulled history) are filled by someone else;
+        # the GEMM writes its B rows into the head and the whole buffer is the output, so the next
+        # layer's input needs no concatenation.  Only the head rows carry gradient.
+        rows = h.size(0)
+        dst = out_full[:rows] if out_full is not None else None
         if w2 is None:
             s = torch.lerp(h, x0, a)
-            out = ops.gemm(s, w1, alpha=b, cin=s, beta=1. - b, relu=relu)
-            ctx.save_for_backward(h, x0, w1, w2, out if relu else None, s)
+            out = ops.gemm(s, w1, alpha=b, cin=s, beta=1. - b, relu=relu, out=dst)
+            keep = out if out_full is None else out_full   # (a saved view of a dirty base is rejected)
+            ctx.save_for_backward(h, x0, w1, w2, keep if relu else None, s)
         else:
             out = ops.gemm_dual("k", h, w1, x0, w2, scale_b=b * (1. - a), scale_b2=b * a,
-                                cin=h, beta=(1. - b) * (1. - a), cin2=x0, beta2=(1. - b) * a, relu=relu)
-            ctx.save_for_backward(h, x0, w1, w2, out if relu else None, None)
+                                cin=h, beta=(1. - b) * (1. - a), cin2=x0, beta2=(1. - b) * a, relu=relu,
+                                out=dst)
+            keep = out if out_full is None else out_full
+            ctx.save_for_backward(h, x0, w1, w2, keep if relu else None, None)
         ctx.a, ctx.b, ctx.relu, ctx.shared = a, b, relu, w2 is None
         ctx.w1_param, ctx.w2_param = w1, w2
+        ctx.rows = rows
+        if out_full is not None:
+            ctx.mark_dirty(out_full)
+            return out_full
         return out
 
     @staticmethod
     def backward(ctx, g):
         h, x0, w1, w2, out, s = ctx.saved_tensors
         a, b = ctx.a, ctx.b
-        g = g.contiguous()
+        g = g[:ctx.rows].contiguous()
         if ctx.relu:
+            out = out[:ctx.rows]
             g = torch.ops.aten.threshold_backward(g, out, 0.)  # ReLU backward, one kernel
         gh = gx0 = gw1 = gw2 = None
         if ctx.shared:
@@ -129,7 +142,7 @@ class _GCN2Dense(torch.autograd.Function):
                               cin=b1, beta=1., cin2=b2, beta2=1., out=b1, out2=b2)
             else:
                 gw1, gw2 = ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a)
-        return gh, gx0, gw1, gw2, None, None, None
+        return gh, gx0, gw1, gw2, None, None, None, None
 
 
 class _MaskedCE(torch.autograd.Function):
@@ -211,7 +224,8 @@ class GCN2Conv(torch.nn.Module):
         if self.weight2 is not None:
             glorot_(self.weight2)
 
-    def forward_after_propagate(self, h: Tensor, x_0: Tensor, relu: bool = False) -> Tensor:
+    def forward_after_propagate(self, h: Tensor, x_0: Tensor, relu: bool = False,
+                                out_full: Optional[Tensor] = None) -> Tensor:
         """Everything of PyG's GCN2Conv.forward after ``propagate``:
             x = (1-alpha) h ; x_0 = alpha x_0[:B]
             shared:   out = x + x_0 ; out = (1-beta) out + beta out W1
@@ -220,15 +234,16 @@ class GCN2Conv(torch.nn.Module):
         follows in the models when there is no batch norm / residual in between)."""
         x_0 = x_0[:h.size(0)]
         return _GCN2Dense.apply(h.contiguous(), x_0.contiguous(), self.weight1, self.weight2,
-                                float(self.alpha), float(self.beta), relu)
+                                float(self.alpha), float(self.beta), relu, out_full)
 
     def forward_no_neighbor(self, x: Tensor, x_0: Tensor, relu: bool = False) -> Tensor:
         return self.forward_after_propagate(x, x_0, relu)
 
     def forward(self, x: Tensor, x_0: Tensor, adj_t: SparseTensor,
-                grad_rows: Optional[int] = None, relu: bool = False) -> Tensor:
+                grad_rows: Optional[int] = None, relu: bool = False,
+                out_full: Optional[Tensor] = None) -> Tensor:
         h = spmm(adj_t, x, reduce='sum', grad_rows=grad_rows)
-        return self.forward_after_propagate(h, x_0, relu)
+        return self.forward_after_propagate(h, x_0, relu, out_full)
 
 
 class SAGEConv(torch.nn.Module):
