@@ -155,8 +155,9 @@ def timed_steps_graphed(run, mode, warmup, steps, dist):
     groups = loader._batches_of_epoch()
     tr.warmup(groups[0])
     t0 = time.perf_counter()
-    for ids in groups:
-        tr.capture(ids)
+    if loader.fixed_batches:
+        for ids in groups:
+            tr.capture(ids)
     torch.cuda.synchronize()
     t_capture = time.perf_counter() - t0
 
@@ -384,7 +385,8 @@ def main():
         per_step = _lib.launch_count() - l0
         sec, edges, _, _, wall, n_graphs, t_cap = timed_steps_graphed(run, args.mode, args.warmup, args.steps, dist)
         launches = per_step * args.steps
-        graphs = {"captured": n_graphs, "capture_s": round(t_cap, 2)}
+        # (shuffled multi-partition groups never repeat: GraphedTrainer issues those steps eagerly)
+        graphs = {"captured": n_graphs, "capture_s": round(t_cap, 2)} if n_graphs else None
     clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks of the device time; edges summed over ranks

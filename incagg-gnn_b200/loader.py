@@ -131,6 +131,12 @@ class SubgraphLoader:
         nnz_b = sum(int(rp[hi]) - int(rp[lo]) for lo, hi in ranges)  # partitions are contiguous rows
         return n_id, offset, count, nnz_b
 
+    @property
+    def fixed_batches(self) -> bool:
+        """True when every epoch draws its batches from one fixed set (single partitions, or groups
+        formed in sequential order): the precondition for replaying a captured step per batch."""
+        return self.batch_size == 1 or not self.shuffle
+
     def _finish(self, rowptr, col, value, n_id, batch_size, offset, count) -> SubData:
         adj_t = SparseTensor(rowptr=rowptr, col=col, value=value,
                              sparse_sizes=(rowptr.numel() - 1, n_id.numel()), is_sorted=True)

@@ -54,10 +54,12 @@ class APPNP(ScalableGNN):
             adj_t = select_edges(adj_t, batch_size, aggregate_combined)
             x = self._mlp(x)
             x_0 = x[:adj_t.size(0)]
+            ahead = self.pull_ahead(self.histories, x, batch_size, n_id, width=x.size(1))
             for i, history in enumerate(self.histories):
                 x = (1 - self.alpha) * spmm(adj_t, x, grad_rows=batch_size if i > 0 else None) \
                     + self.alpha * x_0
-                x, t = self.push_and_pull(history, x, batch_size, n_id, offset, count)
+                x, t = self.push_and_pull(history, x, batch_size, n_id, offset, count,
+                                          ahead=ahead[i] if ahead else None)
                 t_all += t
             x = (1 - self.alpha) * spmm(adj_t, x, grad_rows=batch_size) + self.alpha * x_0
         else:

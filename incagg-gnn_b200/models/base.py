@@ -15,6 +15,7 @@ History-slot map follows the fork as written: GCN pushes/pulls layer
 ``histories[l+1]``, GCN2/APPNP/PNA at ``histories[l]``; the sweeps write layer-l output to
 ``histories[l+1]``; IncAgg reads ``histories[l]`` / ``histories_ag[l]``.
 """
+import os
 import time
 import warnings
 from typing import Optional, Callable, Dict, Any
@@ -28,13 +29,19 @@ from ..pool import AsyncIOPool
 from ..sparse import SparseTensor
 
 
+_NO_AHEAD = os.environ.get('INCAGG_NO_AHEAD') == '1'   # A/B switch: issue the pulls in line
+
+
 class _PushPull(torch.autograd.Function):
     """cat([x[:B], pulled]) without the intermediate: the pulled rows are gathered straight into
     the tail of the output buffer.  grad flows to x[:B] only (base.py:426,451)."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, fill_tail, batch_size: int, n_tail: int):
-        out = torch.empty((batch_size + n_tail, x.size(1)), dtype=x.dtype, device=x.device)
+    def forward(ctx, x: Tensor, fill_tail, batch_size: int, n_tail: int, out: Optional[Tensor] = None):
+        if out is None:
+            out = torch.empty((batch_size + n_tail, x.size(1)), dtype=x.dtype, device=x.device)
+        else:  # a buffer whose tail an early pull (pull_ahead) is filling
+            ctx.mark_dirty(out)
         out[:batch_size].copy_(x[:batch_size])
         if n_tail > 0:
             fill_tail(out[batch_size:])
@@ -45,10 +52,10 @@ class _PushPull(torch.autograd.Function):
     def backward(ctx, grad_out):
         B = ctx.batch_size
         if ctx.n_in == B:
-            return grad_out[:B], None, None, None
+            return grad_out[:B], None, None, None, None
         g = grad_out.new_zeros((ctx.n_in, grad_out.size(1)))
         g[:B] = grad_out[:B]
-        return g, None, None, None
+        return g, None, None, None, None
 
 
 class ScalableGNN(torch.nn.Module):
@@ -236,8 +243,10 @@ class ScalableGNN(torch.nn.Module):
     # ------------------------------------------------------------------------------------------
     def push_and_pull(self, history, x: Tensor, batch_size: Optional[int] = None,
                       n_id: Optional[Tensor] = None, offset: Optional[Tensor] = None,
-                      count: Optional[Tensor] = None):
-        r"""Pushes and pulls information from :obj:`x` to :obj:`history` and vice versa."""
+                      count: Optional[Tensor] = None, ahead=None):
+        r"""Pushes and pulls information from :obj:`x` to :obj:`history` and vice versa.
+        ``ahead`` = this history's (buffer, event) of :meth:`pull_ahead`: the pull is already under
+        way on the side stream."""
         if n_id is None and x.size(0) != self.num_nodes:
             return x  # Do nothing...
         if n_id is None and x.size(0) == self.num_nodes:
@@ -248,6 +257,13 @@ class ScalableGNN(torch.nn.Module):
             history.push(x, n_id)
             return x
         n_tail = n_id.numel() - batch_size
+        if ahead is not None:
+            buf, pulled = ahead
+            history.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
+
+            def fill(dst):
+                torch.cuda.current_stream().wait_event(pulled)
+            return _PushPull.apply(x, fill, batch_size, n_tail, buf), 0.
         if not self._async:  # synchronous branch = the semantic definition (base.py:411-426)
             history.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
             idx = n_id[batch_size:]
@@ -264,14 +280,15 @@ class ScalableGNN(torch.nn.Module):
         self.pool.free_pull()
         return out, 0.
 
-    def pull_ahead(self, histories, x: Tensor, batch_size: Optional[int], n_id: Optional[Tensor]):
+    def pull_ahead(self, histories, x: Tensor, batch_size: Optional[int], n_id: Optional[Tensor],
+                   width: Optional[int] = None):
         """GAS steps pull the halo rows n_id[B:] and push the batch rows n_id[:B]: disjoint rows, so no
         pull depends on anything the step computes.  All of a step's pulls are therefore issued up
         front on a side stream (a parallel branch of the captured graph), each into the tail of a
         [B + H, F] buffer whose head the layer's GEMM later writes in place.  Returns one
         (buffer, event) per history - the consumer waits for the event - or None when the step does
         not take this path (host histories / NCCL transport / full-batch)."""
-        if (n_id is None or batch_size is None or self._async or not x.is_cuda
+        if (_NO_AHEAD or n_id is None or batch_size is None or self._async or not x.is_cuda
                 or not self.emb_device.type == 'cuda' or getattr(n_id, 'halo_plan', None) is not None):
             return None
         n_tail = n_id.numel() - batch_size
@@ -279,7 +296,7 @@ class ScalableGNN(torch.nn.Module):
         side = self._pull_stream
         if side is None:
             side = self._pull_stream = torch.cuda.Stream(x.device)
-        bufs = [torch.empty((batch_size + n_tail, h.emb.size(1)), dtype=x.dtype, device=x.device)
+        bufs = [torch.empty((batch_size + n_tail, width or h.emb.size(1)), dtype=x.dtype, device=x.device)
                 for h in histories]
         side.wait_stream(main)
         idx = n_id[batch_size:]

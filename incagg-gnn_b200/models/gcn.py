@@ -111,10 +111,12 @@ class GCN(ScalableGNN):
         t_all = 0
         if use_aggregation:
             adj_t = select_edges(adj_t, batch_size, aggregate_combined)
+            ahead = self.pull_ahead(self._gas_pull_histories(), x, batch_size, n_id)
             for i, conv in enumerate(self.convs[:-1]):
                 h = conv(x, adj_t, grad_rows=self._grad_rows(i, batch_size))
                 x = self._post(i, h, x)
-                x, t = self.push_and_pull(self.histories[i + 1], x, batch_size, n_id, offset, count)
+                x, t = self.push_and_pull(self.histories[i + 1], x, batch_size, n_id, offset, count,
+                                          ahead=ahead[i] if ahead else None)
                 t_all += t
                 x = F.dropout(x, p=self.dropout, training=self.training)
             h = self.convs[-1](x, adj_t, grad_rows=self._grad_rows(self.num_layers - 1, batch_size))

@@ -158,14 +158,17 @@ class PNA(ScalableGNN):
         t_all = 0
         if self.drop_input:
             x = F.dropout(x, p=self.dropout, training=self.training)
-        for conv, bn, hist in zip(self.convs[:-1], self.bns, self.histories):
+        hists = list(self.histories)[:len(self.convs) - 1]
+        ahead = self.pull_ahead(hists, x, batch_size, n_id)
+        for i, (conv, bn, hist) in enumerate(zip(self.convs[:-1], self.bns, self.histories)):
             h = conv(x, adj_t)
             if self.batch_norm:
                 h = bn(h)
             if self.residual and h.size(-1) == x.size(-1):
                 h = h + x[:h.size(0)]
             x = h.relu_()
-            x, t = self.push_and_pull(hist, x, batch_size, n_id, offset, count)
+            x, t = self.push_and_pull(hist, x, batch_size, n_id, offset, count,
+                                      ahead=ahead[i] if ahead else None)
             t_all += t
             x = F.dropout(x, p=self.dropout, training=self.training)
         x = self.convs[-1](x, adj_t)

@@ -9,6 +9,7 @@ Differences from the reference loop, none of which change results:
 """
 from typing import Any, Dict, Optional
 
+import os
 import torch
 
 from . import models
@@ -137,7 +138,7 @@ _SIDE_STREAMS = {}
 
 def _backward_prep(adj_t, batch_size, VR_update):
     """Fork: build adj_t's transposed CSR + SpMM plans on a side stream.  Returns the stream to join."""
-    if not adj_t.col.is_cuda or adj_t.nnz() == 0:
+    if not adj_t.col.is_cuda or adj_t.nnz() == 0 or os.environ.get('INCAGG_NO_AHEAD') == '1':
         return None
     dev = adj_t.col.device
     side = _SIDE_STREAMS.get(dev)
@@ -291,7 +292,8 @@ class GraphedTrainer:
         key = tuple(ids)
         g = self.graphs.get(key)
         if g is None:
-            if len(self.graphs) >= self.MAX_GRAPHS:  # ever-changing groups (shuffled batch_size > 1)
+            # shuffled groups of several partitions never repeat: nothing to replay, issue eagerly
+            if not self.loader.fixed_batches or len(self.graphs) >= self.MAX_GRAPHS:
                 self.model.train()
                 return self._body(ids)
             self.capture(ids)
