@@ -336,8 +336,28 @@ def load_peaks():
         return {}
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly one JSON line: libraries that write to fd 1 on their own (NCCL prints its
+    version banner there) are pointed at stderr for the rest of the run."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
     args = parse_args()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -542,7 +562,7 @@ def main():
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
         "cpu_baseline": cpu, "edges_timed": edges, "wall_s": wall, "refresh": refresh,
     }
-    print(json.dumps(line))
+    _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -625,7 +645,7 @@ def reference_arm(args, rank, world):
                          "sample": f"{steps} training steps, {edges} edges in {sec:.1f} s"},
         "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 if __name__ == "__main__":

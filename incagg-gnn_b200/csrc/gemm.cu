@@ -480,32 +480,55 @@ gemm_tf32x3_kernel(const GemmParams p) {
   if (warp == 0) tmem_dealloc(tmem_acc, BN);
 }
 
-// D = alpha * sum_z partial[z] + beta * Cin + bias (+ReLU): fixed summation order -> deterministic.
-// Partial slabs are [Mpad][N] with Mpad = gridDim.x * 128 rows; for DUAL_M the rows of the second
-// output start at tiles1 * 128.
-__global__ void gemm_splitk_reduce_kernel(const GemmParams p, int splits) {
+// D = alpha * sum_z partial[z] + beta * Cin + bias (+ReLU).  A block of 8 warps owns 32 consecutive
+// outputs of one row segment: warp w sums the partials z = w, w + 8, ... (independent coalesced loads),
+// the eight sums are combined through shared memory in warp order - a fixed association, so the result
+// is deterministic.  Partial slabs are [Mpad][N] with Mpad = gridDim.x * 128 rows; for DUAL_M the rows
+// of the second output start at tiles1 * 128.
+constexpr int RED_WARPS = 8;
+__global__ void __launch_bounds__(RED_WARPS * 32)
+gemm_splitk_reduce_kernel(const GemmParams p, int splits, int n_chunks) {
+  __shared__ float part[RED_WARPS][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t sets = (p.dual == DUAL_M) ? 2 : 1;
-  const int64_t total = sets * p.M * p.N;
+  const int64_t items = sets * p.M * n_chunks;             // one item = 32 columns of one output row
   const int64_t slab = p.Mpad * p.N;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t set = i / (p.M * p.N);
-    const int64_t j = i - set * p.M * p.N;
-    const int64_t m = j / p.N, n = j - m * p.N;
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    const int64_t set = it / (p.M * n_chunks);
+    const int64_t j = it - set * p.M * n_chunks;
+    const int64_t m = j / n_chunks;
+    const int64_t n = (j - m * n_chunks) * 32 + lane;
     const int64_t prow = m + (set ? (int64_t)p.tiles1 * G_BM : 0);
     float acc = 0.f;
-    for (int z = 0; z < splits; ++z) acc += p.partial[(int64_t)z * slab + prow * p.N + n];
-    if (set == 0) {
-      float x = p.alpha * acc;
-      if (p.Cin && p.beta != 0.f) x += p.beta * p.Cin[m * p.ldcin + n];
-      if (p.bias) x += p.bias[n];
-      if (p.relu) x = fmaxf(x, 0.f);
-      p.D[m * p.ldd + n] = x;
-    } else {
-      float x = p.alpha2 * acc;
-      if (p.Cin2 && p.beta2 != 0.f) x += p.beta2 * p.Cin2[m * p.ldcin2 + n];
-      p.D2[m * p.ldd2 + n] = x;
+    if (n < p.N) {
+      const float* src = p.partial + prow * p.N + n;
+      int z = w;
+      for (; z + 3 * RED_WARPS < splits; z += 4 * RED_WARPS) {
+        const float a0 = src[(int64_t)z * slab], a1 = src[(int64_t)(z + RED_WARPS) * slab];
+        const float a2 = src[(int64_t)(z + 2 * RED_WARPS) * slab], a3 = src[(int64_t)(z + 3 * RED_WARPS) * slab];
+        acc += a0; acc += a1; acc += a2; acc += a3;
+      }
+      for (; z < splits; z += RED_WARPS) acc += src[(int64_t)z * slab];
     }
+    part[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && n < p.N) {
+      float t = part[0][lane];
+#pragma unroll
+      for (int i = 1; i < RED_WARPS; ++i) t += part[i][lane];
+      if (set == 0) {
+        float x = p.alpha * t;
+        if (p.Cin && p.beta != 0.f) x += p.beta * p.Cin[m * p.ldcin + n];
+        if (p.bias) x += p.bias[n];
+        if (p.relu) x = fmaxf(x, 0.f);
+        p.D[m * p.ldd + n] = x;
+      } else {
+        float x = p.alpha2 * t;
+        if (p.Cin2 && p.beta2 != 0.f) x += p.beta2 * p.Cin2[m * p.ldcin2 + n];
+        p.D2[m * p.ldd2 + n] = x;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -535,11 +558,11 @@ static int launch_gemm(const GemmParams& p, int splits, cudaStream_t st) {
 }
 
 static int run_gemm(GemmParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  // 64-wide n-tiles (two CTAs per SM) whenever 128-wide ones would not fill one wave
+  // 64-wide n-tiles only for narrow outputs: on the 16 K-row problems of this path, splitting 128
+  // columns over two co-resident CTAs measured slower (the A tile is split into hi / lo twice)
   const int64_t mt = (p.M + G_BM - 1) / G_BM;
-  const int64_t tiles128 = mt * ((p.N + 127) / 128) * (p.dual == DUAL_M || p.dual == DUAL_N ? 2 : 1);
   static const int force_bn = getenv("INCAGG_GEMM_BN") ? atoi(getenv("INCAGG_GEMM_BN")) : 0;
-  const int bn = force_bn ? ((p.N <= 64) ? 64 : force_bn) : ((p.N <= 64 || tiles128 <= sm_count()) ? 64 : 128);
+  const int bn = (p.N <= 64 || force_bn == 64) ? 64 : 128;
   const int64_t nt = (p.N + bn - 1) / bn;
   p.tiles1 = (int)(p.dual == DUAL_N ? nt : mt);
   const int64_t gx = mt * (p.dual == DUAL_M ? 2 : 1), gy = nt * (p.dual == DUAL_N ? 2 : 1);
@@ -565,9 +588,10 @@ static int run_gemm(GemmParams& p, void* workspace, size_t workspace_bytes, cuda
   int rc = (bn == 64) ? launch_gemm<64>(p, splits, st) : launch_gemm<128>(p, splits, st);
   if (rc != INCAGG_OK) return rc;
   if (splits > 1) {
-    const int64_t total = p.M * p.N * (p.dual == DUAL_M ? 2 : 1);
-    const int blocks = (int)((total + 255) / 256 < (int64_t)sm_count() * 8 ? (total + 255) / 256 : (int64_t)sm_count() * 8);
-    gemm_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p, splits);
+    const int n_chunks = (int)((p.N + 31) / 32);
+    const int64_t items = p.M * n_chunks * (p.dual == DUAL_M ? 2 : 1);
+    const int blocks = (int)(items < (int64_t)sm_count() * 8 ? items : (int64_t)sm_count() * 8);
+    gemm_splitk_reduce_kernel<<<blocks, RED_WARPS * 32, 0, st>>>(p, splits, n_chunks);
     IA_LAUNCH_CHECK();
   }
   return INCAGG_OK;
