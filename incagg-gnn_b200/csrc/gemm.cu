@@ -573,7 +573,8 @@ static int run_gemm(GemmParams& p, void* workspace, size_t workspace_bytes, cuda
   const int64_t tiles = gx * gy;
   int splits = 1;
   if (num_kb >= 16 && tiles < sm_count() && p.dual != DUAL_K && p.dual != DUAL_N) {
-    int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+    // one wave: (tiles x splits) CTAs <= SM count (one CTA per SM is resident)
+    int64_t want = (int64_t)sm_count() / tiles;
     if (want > num_kb / 4) want = num_kb / 4;
     if (want > 128) want = 128;
     if (want > 1 && workspace != nullptr &&

@@ -232,7 +232,8 @@ class GCN2Conv(torch.nn.Module):
             unshared: out = (1-beta) x + beta x W1 + (1-beta) x_0 + beta x_0 W2
         evaluated by the fused tensor-core block (``relu=True`` also applies the activation that
         follows in the models when there is no batch norm / residual in between)."""
-        x_0 = x_0[:h.size(0)]
+        if x_0.size(0) != h.size(0):  # (a no-op slice would still cost a zero-fill + copy in backward)
+            x_0 = x_0[:h.size(0)]
         return _GCN2Dense.apply(h.contiguous(), x_0.contiguous(), self.weight1, self.weight2,
                                 float(self.alpha), float(self.beta), relu, out_full)
 
