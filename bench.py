@@ -435,7 +435,7 @@ def main():
         mini_test(run_h["model"], run_h["eval_loader"], VR_update=vr)
         ld = run_h["train_loader"]
         tr = GraphedTrainer(run_h["model"], ld, run_h["optimizer"], VR_update=vr,
-                            grad_norm=run_h["conf"]["grad_norm"])
+                            grad_norm=run_h["conf"]["grad_norm"], pipeline_collate=True)
         groups = ld._batches_of_epoch()
         tr.warmup(groups[0])
         for ids in groups:
@@ -443,8 +443,7 @@ def main():
         torch.cuda.synchronize()
         k = args.steps
         order = [g for _ in range(k // len(groups) + 2) for g in ld._batches_of_epoch()]
-        for ids in order[:min(args.warmup, 5)]:
-            tr.step(ids)
+        tr.run(order[:min(args.warmup, 5)])
         torch.cuda.synchronize()
         seq = order[5:5 + k]
         rp_host, ptr_h = ld._rowptr_host, ld.ptr
@@ -466,13 +465,14 @@ def main():
         results = []
         torch.cuda.synchronize()
         ev0.record()
-        for i, ids in enumerate(seq):
-            tr.step(ids)
+        def read_back(i):
             host_res[i & 1].copy_(tr.acc, non_blocking=True)
             res_ev[i & 1].record()
             if i > 0:
                 res_ev[(i - 1) & 1].synchronize()
                 results.append(float(host_res[(i - 1) & 1][0]))
+
+        tr.run(seq, after_step=read_back)
         res_ev[(k - 1) & 1].synchronize()
         results.append(float(host_res[(k - 1) & 1][0]))
         ev1.record()
@@ -484,7 +484,8 @@ def main():
                "layout": "graph (CSR), features, labels and masks in pinned host memory, read through UVA by the "
                          "collate kernels every step; history tables HBM-resident; every step's result (loss "
                          "sum, count) copied to pinned memory and read by the host, the read of step i-1 "
-                         "overlapping step i; CUDA-graph replay per batch"}
+                         "overlapping step i; CUDA-graph replay per batch, the collate graph of step i+1 (the host-memory "
+                         "reads) replayed on a side stream while step i computes"}
         del tr, run_h
         torch.cuda.empty_cache()
         # the reference's all-host layout (pinned history tables + AsyncIOPool), eager

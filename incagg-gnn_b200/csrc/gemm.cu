@@ -36,7 +36,7 @@ constexpr int G_BM = 128;
 constexpr int G_BK = 32;     // 32 tf32 = 128 bytes = one swizzle row
 constexpr int G_THREADS = 256;
 
-enum { DUAL_NONE = 0, DUAL_K = 1, DUAL_N = 2, DUAL_M = 3 };
+enum { DUAL_NONE = 0, DUAL_K = 1, DUAL_N = 2, DUAL_M = 3, DUAL_NC = 4 };  // NC: internal, see gemm_nc_kernel
 
 struct GemmParams {
   const float* A; int64_t lda; int transA;   // transA = 0: A is [M,K] row-major; 1: stored [K,M]
@@ -60,6 +60,7 @@ struct GemmParams {
   int64_t K2;
   int tiles1;                                // DUAL_N / DUAL_M: tiles (y resp. x) of the first set
   int64_t Mpad;                              // rows of one split-K partial slab
+  int64_t ldp;                               // row stride of a partial slab (N; 256 for DUAL_NC)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -395,9 +396,9 @@ gemm_tf32x3_kernel(const GemmParams p) {
   const int cbase = (warp >> 2) * CW;
   const bool splitk = p.partial != nullptr;
   // split-K partial slab row: the global m-tile index (blockIdx.x), so DUAL_M sets do not collide
-  float* drow = splitk ? p.partial + ((int64_t)blockIdx.z * p.Mpad + (int64_t)blockIdx.x * G_BM + (warp & 3) * 32 + lane) * p.N
+  float* drow = splitk ? p.partial + ((int64_t)blockIdx.z * p.Mpad + (int64_t)blockIdx.x * G_BM + (warp & 3) * 32 + lane) * p.ldp
                        : Dptr + m * ldd;
-  const int64_t ldd_eff = splitk ? p.N : ldd;
+  const int64_t ldd_eff = splitk ? p.ldp : ldd;
   const bool vecD = (ldd_eff % 4 == 0) && aligned16(splitk ? (const void*)p.partial : (const void*)Dptr);
   const bool use_cin = !splitk && Cin && beta_e != 0.f;
   const bool vecC = use_cin && (ldcin % 4 == 0) && aligned16(Cin);
@@ -480,6 +481,148 @@ gemm_tf32x3_kernel(const GemmParams p) {
   if (warp == 0) tmem_dealloc(tmem_acc, BN);
 }
 
+
+// ---- N-concatenated pair: D = alpha op(A) (sB B) + beta Cin,  D2 = alpha2 op(A) (sB2 B2) + beta2 Cin2 ----
+// One CTA owns a 128-row tile of the shared operand A and BOTH outputs: the B tile is 256 rows
+// (rows 0..127 from B, 128..255 from B2; N <= 128 each), the accumulator 128 x 256 in TMEM, the MMA
+// shape 128 x 256 x 8.  A is split into hi / lo once instead of once per output, and the grid has
+// half the CTAs (the 16 K-row problems fit one wave).
+template <bool TA, bool TBK>
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_nc_kernel(const GemmParams p) {
+  constexpr int STAGES = 2, BN = 256, HALF = 128;
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = G_BM * 128, B_BYTES = BN * 128, BH_BYTES = HALF * 128;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  __shared__ uint64_t mma_done[STAGES];
+  __shared__ uint64_t acc_ready;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int64_t m0 = (int64_t)blockIdx.x * G_BM;
+  const int64_t num_kb_total = (p.K + G_BK - 1) / G_BK;
+  const int64_t kb_lo = (int64_t)blockIdx.z * p.kb_per_split;
+  const int64_t kb_hi = min(num_kb_total, kb_lo + p.kb_per_split);
+  const int num_kb = (int)(kb_hi - kb_lo);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&mma_done[s], 1);
+    mbar_init(&acc_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_slot, BN);
+
+  const bool vecA = (p.lda % 4 == 0) && aligned16(p.A);
+  const bool vecB = (p.ldb % 4 == 0) && aligned16(p.B), vecB2 = (p.ldb2 % 4 == 0) && aligned16(p.B2);
+  constexpr uint32_t IDESC = umma_idesc(G_BM, BN);
+
+  TileRegs<G_BM> ra;
+  TileRegs<HALF> rb, rb2;
+  auto load_kb = [&](int64_t kbg) {
+    load_tile<G_BM, TA>(p.A, p.lda, m0, p.M, kbg * G_BK, p.K, vecA, ra);
+    load_tile<HALF, TBK>(p.B, p.ldb, 0, p.N, kbg * G_BK, p.K, vecB, rb);
+    load_tile<HALF, TBK>(p.B2, p.ldb2, 0, p.N, kbg * G_BK, p.K, vecB2, rb2);
+  };
+  if (num_kb > 0) load_kb(kb_lo);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+#pragma unroll 1
+  for (int kb = 0; kb < num_kb; ++kb) {
+    const int s = kb % STAGES;
+    const uint32_t st = smem_base + (uint32_t)(s * STAGE_BYTES);
+    if (kb >= STAGES) mbar_wait(&mma_done[s], (uint32_t)(((kb / STAGES) - 1) & 1));
+    const uint32_t b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+    store_tile<G_BM, TA>(ra, st, st + A_BYTES);
+    store_tile<HALF, TBK>(rb, b_hi, b_lo, p.scaleB);
+    store_tile<HALF, TBK>(rb2, b_hi + BH_BYTES, b_lo + BH_BYTES, p.scaleB2);
+    if (kb + 1 < num_kb) load_kb(kb_lo + kb + 1);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) {
+        tc_fence_after();
+        const uint64_t d_ahi = umma_desc(st), d_alo = umma_desc(st + A_BYTES);
+        const uint64_t d_bhi = umma_desc(b_hi), d_blo = umma_desc(b_lo);
+#pragma unroll
+        for (int k = 0; k < G_BK / 8; ++k) {
+          const uint64_t ko = (uint64_t)(k * 2);
+          umma_tf32(tmem_acc, d_alo + ko, d_bhi + ko, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_tf32(tmem_acc, d_ahi + ko, d_blo + ko, IDESC, 1u);
+          umma_tf32(tmem_acc, d_ahi + ko, d_bhi + ko, IDESC, 1u);
+        }
+        umma_commit(&mma_done[s]);
+        if (kb == num_kb - 1) umma_commit(&acc_ready);
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- epilogue: warps 0-3 write output 1 (TMEM columns 0..127), warps 4-7 output 2 (128..255);
+  //      warp w reads TMEM lanes 32 (w & 3) .. +31 = its rows ----
+  const int set = warp >> 2;
+  const int64_t m = m0 + (warp & 3) * 32 + lane;
+  const bool splitk = p.partial != nullptr;
+  const float* Cin = set ? p.Cin2 : p.Cin;
+  const int64_t ldcin = set ? p.ldcin2 : p.ldcin;
+  float* Dptr = set ? p.D2 : p.D;
+  const int64_t ldd = set ? p.ldd2 : p.ldd;
+  const float alpha = set ? p.alpha2 : p.alpha, beta = set ? p.beta2 : p.beta;
+  const bool use_cin = !splitk && Cin && beta != 0.f;
+  const bool full_n = (p.N == HALF);
+  const bool vecD = full_n && (splitk || ((ldd % 4 == 0) && aligned16(Dptr)));
+  const bool vecC = use_cin && full_n && (ldcin % 4 == 0) && aligned16(Cin);
+  float* prow = splitk ? p.partial + ((int64_t)blockIdx.z * p.Mpad + m) * p.ldp + set * HALF : nullptr;
+  if (num_kb > 0) mbar_wait(&acc_ready, 0);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c0 = 0; c0 < HALF; c0 += 32) {
+    float v[32];
+    if (num_kb > 0) {
+      tmem_ld32(tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(set * HALF + c0), v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    }
+    if (m >= p.M) continue;
+    if (splitk) {  // raw partial sums, slab row m, columns set * 128 + n
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(prow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else if (vecD) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 o = make_float4(alpha * v[i], alpha * v[i + 1], alpha * v[i + 2], alpha * v[i + 3]);
+        if (use_cin) {
+          const float* cp = Cin + m * ldcin + c0 + i;
+          const float4 t = vecC ? __ldg(reinterpret_cast<const float4*>(cp)) : make_float4(cp[0], cp[1], cp[2], cp[3]);
+          o.x += beta * t.x; o.y += beta * t.y; o.z += beta * t.z; o.w += beta * t.w;
+        }
+        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(Dptr + m * ldd + c0 + i) = o;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i) {
+        const int64_t n = c0 + i;
+        if (n >= p.N) break;
+        float x = alpha * v[i];
+        if (use_cin) x += beta * Cin[m * ldcin + n];
+        if (p.relu) x = fmaxf(x, 0.f);
+        Dptr[m * ldd + n] = x;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_acc, BN);
+}
+
 // D = alpha * sum_z partial[z] + beta * Cin + bias (+ReLU).  A block of 8 warps owns 32 consecutive
 // outputs of one row segment: warp w sums the partials z = w, w + 8, ... (independent coalesced loads),
 // the eight sums are combined through shared memory in warp order - a fixed association, so the result
@@ -490,18 +633,19 @@ __global__ void __launch_bounds__(RED_WARPS * 32)
 gemm_splitk_reduce_kernel(const GemmParams p, int splits, int n_chunks) {
   __shared__ float part[RED_WARPS][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t sets = (p.dual == DUAL_M) ? 2 : 1;
+  const int64_t sets = (p.dual == DUAL_M || p.dual == DUAL_NC) ? 2 : 1;
   const int64_t items = sets * p.M * n_chunks;             // one item = 32 columns of one output row
-  const int64_t slab = p.Mpad * p.N;
+  const int64_t slab = p.Mpad * p.ldp;
   for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
     const int64_t set = it / (p.M * n_chunks);
     const int64_t j = it - set * p.M * n_chunks;
     const int64_t m = j / n_chunks;
     const int64_t n = (j - m * n_chunks) * 32 + lane;
-    const int64_t prow = m + (set ? (int64_t)p.tiles1 * G_BM : 0);
+    // DUAL_M: the second output's rows follow the first's; DUAL_NC: its columns start at 128
+    const int64_t prow = m + ((set && p.dual == DUAL_M) ? (int64_t)p.tiles1 * G_BM : 0);
     float acc = 0.f;
     if (n < p.N) {
-      const float* src = p.partial + prow * p.N + n;
+      const float* src = p.partial + prow * p.ldp + n + ((set && p.dual == DUAL_NC) ? 128 : 0);
       int z = w;
       for (; z + 3 * RED_WARPS < splits; z += 4 * RED_WARPS) {
         const float a0 = src[(int64_t)z * slab], a1 = src[(int64_t)(z + RED_WARPS) * slab];
@@ -525,6 +669,7 @@ gemm_splitk_reduce_kernel(const GemmParams p, int splits, int n_chunks) {
       } else {
         float x = p.alpha2 * t;
         if (p.Cin2 && p.beta2 != 0.f) x += p.beta2 * p.Cin2[m * p.ldcin2 + n];
+        if (p.relu && p.dual == DUAL_NC) x = fmaxf(x, 0.f);
         p.D2[m * p.ldd2 + n] = x;
       }
     }
@@ -550,6 +695,25 @@ static int launch_gemm_t(const GemmParams& p, int splits, cudaStream_t st) {
   return INCAGG_OK;
 }
 
+template <bool TA, bool TBK>
+static int launch_nc_t(const GemmParams& p, int splits, cudaStream_t st) {
+  constexpr int SMEM = 2 * (2 * G_BM * 128 + 2 * 256 * 128) + 1024;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    IA_CUDA(cudaFuncSetAttribute(gemm_nc_kernel<TA, TBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((p.M + G_BM - 1) / G_BM), 1, (unsigned)splits);
+  gemm_nc_kernel<TA, TBK><<<grid, G_THREADS, SMEM, st>>>(p);
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}
+static int launch_nc(const GemmParams& p, int splits, cudaStream_t st) {
+  const bool ta = p.transA != 0, tbk = p.transB == 0;
+  if (ta) return tbk ? launch_nc_t<true, true>(p, splits, st) : launch_nc_t<true, false>(p, splits, st);
+  return tbk ? launch_nc_t<false, true>(p, splits, st) : launch_nc_t<false, false>(p, splits, st);
+}
+
 template <int BN>
 static int launch_gemm(const GemmParams& p, int splits, cudaStream_t st) {
   const bool ta = p.transA != 0, tbk = p.transB == 0;
@@ -558,39 +722,47 @@ static int launch_gemm(const GemmParams& p, int splits, cudaStream_t st) {
 }
 
 static int run_gemm(GemmParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  static const bool no_nc = getenv("INCAGG_GEMM_NO_NC") != nullptr;   // A/B switch
+  // N-concatenated pairs with N <= 128 run in the pair kernel (one CTA owns both outputs).  (Running
+  // the M-concatenated weight gradients there as the transposed problem measured slower: 26 vs 24 us.)
+  if (!no_nc && p.dual == DUAL_N && p.N <= 128 && p.bias == nullptr) {
+    p.dual = DUAL_NC;
+  }
+  const bool nc = p.dual == DUAL_NC;
+  static const int force_bn = getenv("INCAGG_GEMM_BN") ? atoi(getenv("INCAGG_GEMM_BN")) : 0;
   // 64-wide n-tiles only for narrow outputs: on the 16 K-row problems of this path, splitting 128
   // columns over two co-resident CTAs measured slower (the A tile is split into hi / lo twice)
+  const int bn = nc ? 256 : ((p.N <= 64 || force_bn == 64) ? 64 : 128);
   const int64_t mt = (p.M + G_BM - 1) / G_BM;
-  static const int force_bn = getenv("INCAGG_GEMM_BN") ? atoi(getenv("INCAGG_GEMM_BN")) : 0;
-  const int bn = (p.N <= 64 || force_bn == 64) ? 64 : 128;
-  const int64_t nt = (p.N + bn - 1) / bn;
+  const int64_t nt = nc ? 1 : (p.N + bn - 1) / bn;
   p.tiles1 = (int)(p.dual == DUAL_N ? nt : mt);
   const int64_t gx = mt * (p.dual == DUAL_M ? 2 : 1), gy = nt * (p.dual == DUAL_N ? 2 : 1);
   p.Mpad = gx * G_BM;
+  p.ldp = nc ? 256 : p.N;
   if (p.dual == DUAL_K) p.kb1 = (int)((p.K + G_BK - 1) / G_BK);
   const int64_t num_kb = (p.K + G_BK - 1) / G_BK + (p.dual == DUAL_K ? (p.K2 + G_BK - 1) / G_BK : 0);
   // split-K when the output has few tiles and the reduction is long (weight gradients)
   const int64_t tiles = gx * gy;
   int splits = 1;
-  if (num_kb >= 16 && tiles < sm_count() && p.dual != DUAL_K && p.dual != DUAL_N) {
+  if (num_kb >= 16 && tiles < sm_count() && p.dual != DUAL_K && p.dual != DUAL_N && workspace != nullptr) {
     // one wave: (tiles x splits) CTAs <= SM count (one CTA per SM is resident)
     int64_t want = (int64_t)sm_count() / tiles;
     if (want > num_kb / 4) want = num_kb / 4;
     if (want > 128) want = 128;
-    if (want > 1 && workspace != nullptr &&
-        workspace_bytes >= sizeof(float) * (size_t)p.Mpad * (size_t)p.N * (size_t)want)
-      splits = (int)want;
+    const int64_t fit = (int64_t)(workspace_bytes / (sizeof(float) * (size_t)p.Mpad * (size_t)p.ldp));
+    if (want > fit) want = fit;
+    if (want > 1) splits = (int)want;
   }
   p.kb_per_split = (int)((num_kb + splits - 1) / splits);
   if (p.kb_per_split < 1) p.kb_per_split = 1;
   splits = (int)((num_kb + p.kb_per_split - 1) / p.kb_per_split);
   if (splits < 1) splits = 1;
   p.partial = splits > 1 ? static_cast<float*>(workspace) : nullptr;
-  int rc = (bn == 64) ? launch_gemm<64>(p, splits, st) : launch_gemm<128>(p, splits, st);
+  int rc = nc ? launch_nc(p, splits, st) : ((bn == 64) ? launch_gemm<64>(p, splits, st) : launch_gemm<128>(p, splits, st));
   if (rc != INCAGG_OK) return rc;
   if (splits > 1) {
     const int n_chunks = (int)((p.N + 31) / 32);
-    const int64_t items = p.M * n_chunks * (p.dual == DUAL_M ? 2 : 1);
+    const int64_t items = p.M * n_chunks * ((p.dual == DUAL_M || nc) ? 2 : 1);
     const int blocks = (int)(items < (int64_t)sm_count() * 8 ? items : (int64_t)sm_count() * 8);
     gemm_splitk_reduce_kernel<<<blocks, RED_WARPS * 32, 0, st>>>(p, splits, n_chunks);
     IA_LAUNCH_CHECK();

@@ -231,6 +231,24 @@ slice_bulk_kernel(const char* __restrict__ src, char* __restrict__ dst, const Bu
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before exit
 }
 
+static bool is_host_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;  // unregistered pageable memory
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeUnregistered;
+}
+
+// A gather whose source is pinned host memory (zero-copy over PCIe) is bound by the link, not by
+// the SMs: ~110 KB in flight saturate it.  A full-size grid would park 2 K threads on every SM for
+// the whole transfer and keep the training kernels of the concurrent step off the GPU, so such
+// launches use a few CTAs only (INCAGG_HOST_GATHER_CTAS, default 48: 0.8 MB in flight).
+static int host_gather_ctas() {
+  static const int v = getenv("INCAGG_HOST_GATHER_CTAS") ? atoi(getenv("INCAGG_HOST_GATHER_CTAS")) : 48;
+  return v < 1 ? 1 : v;
+}
+
 static int pick_vb(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t row_bytes) {
   auto ok = [&](int vb) {
     return row_bytes % vb == 0 && lda % vb == 0 && ldb % vb == 0 &&
@@ -259,7 +277,8 @@ static int index_rows(const void* src, int64_t src_ld, const int64_t* idx, int64
   const int64_t nvec64 = row_bytes / vb;
   IA_CHECK_ARG(nvec64 <= 0x7fffffff, "row too wide");
   const int nvec = (int)nvec64;
-  const int grid = grid_for(n * nvec64);
+  int grid = grid_for(n * nvec64);
+  if (is_host_ptr(MODE == 0 ? src : (const void*)dst) && grid > host_gather_ctas()) grid = host_gather_ctas();
   const char* s = static_cast<const char*>(src);
   char* d = static_cast<char*>(dst);
   if (vb == 16)
@@ -274,15 +293,6 @@ static int index_rows(const void* src, int64_t src_ld, const int64_t* idx, int64
     index_rows_kernel<1, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
-}
-
-static bool is_host_ptr(const void* p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return true;  // unregistered pageable memory
-  }
-  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeUnregistered;
 }
 
 }  // namespace incagg

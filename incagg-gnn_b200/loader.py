@@ -89,6 +89,27 @@ class SubgraphLoader:
                 self._val = self._val.pin_memory()
         self._ws = ops.RelabelWorkspace(adj.size(0), self.device)
         self._known_sizes = {}
+        self._host_graph = not adj.col.is_cuda
+        # host-resident node attributes narrower than 16 bytes per row (labels, masks) are packed
+        # into one pinned record table: one PCIe gather per step instead of one per attribute (each
+        # of them is bound by the latency of ~10^5 tiny reads, not by bytes)
+        self._packed, self._packed_fields = None, []
+        narrow = [(k, v) for k, v in data
+                  if isinstance(v, Tensor) and v.dim() >= 1 and v.size(0) == data.num_nodes and not v.is_cuda
+                  and v.is_pinned() and v[0].numel() * v.element_size() <= 8]
+        if len(narrow) > 1:
+            off = 0
+            for k, v in narrow:
+                w = v[0].numel() * v.element_size()
+                off = (off + w - 1) // w * w          # natural alignment of the field
+                self._packed_fields.append((k, v.dtype, tuple(v.shape[1:]), off, w))
+                off += w
+            rec = (off + 15) // 16 * 16
+            packed = torch.zeros((data.num_nodes, rec), dtype=torch.uint8)
+            for (k, dt, shp, o, w), (_, v) in zip(self._packed_fields, narrow):
+                src = v.view(torch.uint8) if v.dtype == torch.bool else v
+                packed[:, o:o + w] = src.contiguous().view(data.num_nodes, -1).view(torch.uint8)
+            self._packed = packed.pin_memory()
 
         n_local = len(self._parts)
         sampler = RandomSampler(range(n_local)) if shuffle else SequentialSampler(range(n_local))
@@ -137,6 +158,25 @@ class SubgraphLoader:
         formed in sequential order): the precondition for replaying a captured step per batch."""
         return self.batch_size == 1 or not self.shuffle
 
+    def _graph_window(self, batch_ids):
+        """Host-resident graph, one contiguous partition: bulk-copy its CSR rows (three DMA transfers)
+        and let the relabel kernels run on the device copy instead of chasing rowptr -> col through
+        PCIe.  Returns (rowptr, col, value, window) for ops.relabel_*."""
+        if not self._host_graph or len(batch_ids) != 1:
+            return self._rowptr64, self._col, self._val, None
+        lo, hi = int(self.ptr[batch_ids[0]]), int(self.ptr[batch_ids[0] + 1])
+        e0, e1 = int(self._rowptr_host[lo]), int(self._rowptr_host[hi])
+        dev = self.device
+        rp = torch.empty(hi - lo + 1, dtype=torch.int64, device=dev)
+        rp.copy_(self._rowptr64[lo:hi + 1], non_blocking=True)
+        col = torch.empty(e1 - e0, dtype=self._col.dtype, device=dev)
+        col.copy_(self._col[e0:e1], non_blocking=True)
+        val = None
+        if self._val is not None:
+            val = torch.empty(e1 - e0, dtype=self._val.dtype, device=dev)
+            val.copy_(self._val[e0:e1], non_blocking=True)
+        return rp, col, val, (lo, e0, self._rowptr64.numel() - 1)
+
     def _finish(self, rowptr, col, value, n_id, batch_size, offset, count) -> SubData:
         adj_t = SparseTensor(rowptr=rowptr, col=col, value=value,
                              sparse_sizes=(rowptr.numel() - 1, n_id.numel()), is_sorted=True)
@@ -144,7 +184,17 @@ class SubgraphLoader:
             from .parallel import HaloPlan
             n_id.halo_plan = HaloPlan(n_id[batch_size:], self.shard)
         data = self.data.__class__(adj_t=adj_t)
+        packed_keys = ()
+        if self._packed is not None:
+            rec = ops.gather_rows(self._packed, n_id)             # [n, record bytes] uint8
+            packed_keys = {f[0] for f in self._packed_fields}
+            for k, dt, shp, o, w in self._packed_fields:
+                col = rec[:, o:o + w].contiguous()
+                col = col.view(torch.uint8 if dt == torch.bool else dt).view((n_id.numel(),) + shp)
+                data[k] = col.view(torch.bool) if dt == torch.bool else col
         for k, v in self.data:
+            if k in packed_keys:
+                continue
             if isinstance(v, Tensor) and v.size(0) == self.data.num_nodes:
                 if not (v.is_cuda or v.is_pinned()):
                     raise RuntimeError(f'data.{k} must be a CUDA or pinned host tensor')
@@ -164,9 +214,10 @@ class SubgraphLoader:
         batch_size = n_id.numel()
         key = ('gas',) + tuple(batch_ids)
         with torch.cuda.device(self.device):
+            g_rowptr, g_col, g_val, window = self._graph_window(batch_ids)
             rowptr, col, value, n_id = ops.relabel_one_hop(
-                self._rowptr64, self._col, self._val, n_id, self.bipartite, ws=self._ws,
-                out_int32=True, nnz_b=nnz_b, known=self._known_sizes.get(key))
+                g_rowptr, g_col, g_val, n_id, self.bipartite, ws=self._ws,
+                out_int32=True, nnz_b=nnz_b, known=self._known_sizes.get(key), window=window)
             self._remember(key, self._ws.last_count)
             return self._finish(rowptr, col, value, n_id, batch_size, offset, count)
 
@@ -176,9 +227,10 @@ class SubgraphLoader:
         batch_size = n_id.numel()
         key = ('ib',) + tuple(batch_ids)
         with torch.cuda.device(self.device):
+            g_rowptr, g_col, g_val, window = self._graph_window(batch_ids)
             rowptr, col, value, n_id = ops.relabel_one_hop_within_batch(
-                self._rowptr64, self._col, self._val, n_id, self.bipartite, ws=self._ws,
-                out_int32=True, nnz_b=nnz_b, known=self._known_sizes.get(key))
+                g_rowptr, g_col, g_val, n_id, self.bipartite, ws=self._ws,
+                out_int32=True, nnz_b=nnz_b, known=self._known_sizes.get(key), window=window)
             self._remember(key, self._ws.last_count)
             return self._finish(rowptr, col, value, n_id, batch_size, offset, count)
 

@@ -427,7 +427,7 @@ def _workspace_for(num_nodes: int, device) -> RelabelWorkspace:
 
 def _relabel(within: bool, rowptr: Tensor, col: Tensor, value: Optional[Tensor], idx: Tensor,
              bipartite: bool, ws: Optional[RelabelWorkspace], out_int32: bool,
-             nnz_b: Optional[int], known: Optional[int] = None):
+             nnz_b: Optional[int], known: Optional[int] = None, window=None):
     """`known`: the data-dependent output size of this very batch from an earlier call (number of
     halo ids for relabel_one_hop, number of kept edges for the within-batch variant).  With it the call
     needs no device->host readback, i.e. no synchronisation (and can be captured in a CUDA graph)."""
@@ -450,12 +450,23 @@ def _relabel(within: bool, rowptr: Tensor, col: Tensor, value: Optional[Tensor],
     dev = idx.device
     N = rowptr.numel() - 1
     B = idx.numel()
+    # `window = (row_lo, edge_lo, num_nodes)`: rowptr / col / value hold only rows [row_lo, row_lo + len)
+    # and their edges [edge_lo, ...) of the global CSR (a staged copy of one contiguous partition).  The
+    # kernels read rowptr[v], rowptr[v + 1] and col / value[rowptr[v] .. rowptr[v + 1]) for v in idx only,
+    # so they are handed the base addresses the full arrays would have.
+    p_rowptr, p_col, p_val = ptr(rowptr), ptr(col), ptr(value)
+    if window is not None:
+        row_lo, edge_lo, N = (int(v) for v in window)
+        p_rowptr -= row_lo * 8
+        p_col -= edge_lo * col.element_size()
+        if p_val is not None:
+            p_val -= edge_lo * 4
     if ws is None:
         ws = _workspace_for(N, dev)
     st = _stream()
     if nnz_b is None:
         LAUNCHES["calls"] += 1
-        check(lib.incagg_relabel_degree_sum(ptr(rowptr), ptr(idx), B, N, ptr(ws.counts), ptr(ws.buf), st))
+        check(lib.incagg_relabel_degree_sum(p_rowptr, ptr(idx), B, N, ptr(ws.counts), ptr(ws.buf), st))
         nnz_b = int(ws.counts[0].item())
     odt = torch.int32 if out_int32 else torch.int64
     ow = 4 if out_int32 else 8
@@ -466,7 +477,7 @@ def _relabel(within: bool, rowptr: Tensor, col: Tensor, value: Optional[Tensor],
     LAUNCHES["calls"] += 1
     if within:
         check(lib.incagg_relabel_one_hop_within_batch(
-            ptr(rowptr), ptr(col), cw, ptr(value), ptr(idx), B, N, nnz_b, ptr(out_rowptr),
+            p_rowptr, p_col, cw, p_val, ptr(idx), B, N, nnz_b, ptr(out_rowptr),
             ptr(out_col), ow, ptr(out_val), ptr(ws.counts), ptr(ws.buf), st))
         if known is None:
             ws.counts_host.copy_(ws.counts, non_blocking=True)
@@ -487,7 +498,7 @@ def _relabel(within: bool, rowptr: Tensor, col: Tensor, value: Optional[Tensor],
     n_id_buf = torch.empty(B + (min(nnz_b, N) if known is None else int(known)), dtype=torch.int64,
                            device=dev)
     check(lib.incagg_relabel_one_hop(
-        ptr(rowptr), ptr(col), cw, ptr(value), ptr(idx), B, N, nnz_b, ptr(out_rowptr), ptr(out_col),
+        p_rowptr, p_col, cw, p_val, ptr(idx), B, N, nnz_b, ptr(out_rowptr), ptr(out_col),
         ow, ptr(out_val), ptr(n_id_buf), ptr(ws.counts), ptr(ws.buf), st))
     if known is None:
         ws.counts_host.copy_(ws.counts, non_blocking=True)
@@ -503,16 +514,17 @@ def _relabel(within: bool, rowptr: Tensor, col: Tensor, value: Optional[Tensor],
 
 
 def relabel_one_hop(rowptr, col, value, idx, bipartite: bool = True, ws=None,
-                    out_int32: bool = False, nnz_b: Optional[int] = None, known: Optional[int] = None):
+                    out_int32: bool = False, nnz_b: Optional[int] = None, known: Optional[int] = None,
+                    window=None):
     """GPU relabel_one_hop (csrc/cpu/relabel_cpu.cpp:3-108), bit-exact."""
-    return _relabel(False, rowptr, col, value, idx, bipartite, ws, out_int32, nnz_b, known)
+    return _relabel(False, rowptr, col, value, idx, bipartite, ws, out_int32, nnz_b, known, window)
 
 
 def relabel_one_hop_within_batch(rowptr, col, value, idx, bipartite: bool = True, ws=None,
                                  out_int32: bool = False, nnz_b: Optional[int] = None,
-                                 known: Optional[int] = None):
+                                 known: Optional[int] = None, window=None):
     """GPU relabel_one_hop_within_batch (csrc/cpu/relabel_cpu.cpp:111-214), bit-exact."""
-    return _relabel(True, rowptr, col, value, idx, bipartite, ws, out_int32, nnz_b, known)
+    return _relabel(True, rowptr, col, value, idx, bipartite, ws, out_int32, nnz_b, known, window)
 
 
 # --------------------------------------------------------------------------------------------

@@ -163,6 +163,13 @@ class SparseTensor:
             self._t = (t_rowptr, t_col, t_val)
         return self._t
 
+    def drop_caches(self) -> None:
+        """Forget the derived structures (transposed CSR, plans).  A captured step keeps recomputing
+        them inside its graph; dropping the Python references hands their memory back to the pool."""
+        self._t = self._plan = self._t_plan = None
+        self.__dict__.pop('_t_prefix_plans', None)
+        self.__dict__.pop('_stripped', None)
+
     def plan(self) -> Tensor:
         """SpMM plan of this structure (one small launch, cached)."""
         if getattr(self, '_plan', None) is None:

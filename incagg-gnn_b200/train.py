@@ -222,13 +222,27 @@ class GraphedTrainer:
     eagerly between them (collate + forward + backward | all_reduce | scale + clip + Adam).  Halo rows
     of other ranks are read by the captured gather kernels straight out of the peers' HBM (p2p
     transport), so the graphs contain no collective.
+
+    ``pipeline_collate=True`` (host-resident inputs): the collate of a batch - the kernels that read
+    the graph, features, labels and masks out of pinned host memory over PCIe - is captured as its own
+    graph with its own memory pool and persistent outputs, and :meth:`run` replays the collate of
+    step i+1 on a side stream while step i computes (what the reference's DataLoader workers +
+    ``non_blocking`` copies do for its loop).  Every step still moves its inputs host -> device.
     """
 
-    def __init__(self, model, loader, optimizer, VR_update=False, grad_norm=None, averager=None):
+    def __init__(self, model, loader, optimizer, VR_update=False, grad_norm=None, averager=None,
+                 pipeline_collate=False):
         self.model, self.loader, self.optimizer = model, loader, optimizer
         self.vr, self.grad_norm, self.averager = VR_update, grad_norm, averager
         self.graphs = {}
         self.pool = None
+        self.pipeline = bool(pipeline_collate)
+        if self.pipeline and averager is not None:
+            raise RuntimeError('pipeline_collate is the single-GPU host-resident mode')
+        self.pool_in = None          # memory pool of the collate graphs
+        self.in_graphs = {}          # batch -> (collate graph, its persistent SubData)
+        self._in_stream = None
+        self._in_done, self._step_done = {}, {}
         self.acc = torch.zeros(2, dtype=torch.float64, device=model.device)  # sum(loss * n), sum(n)
         for g in optimizer.param_groups:
             if not g.get('capturable', False):
@@ -241,6 +255,50 @@ class GraphedTrainer:
 
     def _body_b(self):
         apply_update(self.model, self.optimizer, self.grad_norm, self.averager)
+
+    def _step_on(self, sub):
+        ln, n = forward_backward(self.model, sub, self.optimizer, self.vr, None)
+        self.acc += torch.stack([ln.double(), n.double()])
+        apply_update(self.model, self.optimizer, self.grad_norm, None)
+
+    def _launch_collate(self, key):
+        """Replay the collate graph of batch `key` on the side stream (after the last step that read
+        its output buffers)."""
+        side = self._in_stream
+        with torch.cuda.stream(side):
+            prev = self._step_done.get(key)
+            if prev is not None:
+                side.wait_event(prev)
+            self.in_graphs[key][0].replay()
+            ev = torch.cuda.Event()
+            ev.record(side)
+        self._in_done[key] = ev
+
+    def run(self, seq, after_step=None):
+        """Steps over the batches `seq` in order; with ``pipeline_collate`` the collate of step i+1
+        overlaps step i.  ``after_step(i)`` runs on the host after step i has been issued."""
+        if not self.pipeline:
+            for i, ids in enumerate(seq):
+                self.step(ids)
+                if after_step is not None:
+                    after_step(i)
+            return
+        keys = [tuple(ids) for ids in seq]
+        for k in keys:
+            self.capture(k)
+        main = torch.cuda.current_stream(self.model.device)
+        self._in_stream.wait_stream(main)
+        self._launch_collate(keys[0])
+        for i, k in enumerate(keys):
+            main.wait_event(self._in_done[k])
+            self.graphs[k][0].replay()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._step_done[k] = ev
+            if i + 1 < len(keys):
+                self._launch_collate(keys[i + 1])
+            if after_step is not None:
+                after_step(i)
 
     def _body(self, ids):
         self._body_a(ids)
@@ -273,7 +331,20 @@ class GraphedTrainer:
             self.loader._collate(list(ids))
         if self.pool is None:
             self.pool = torch.cuda.graph_pool_handle()
-        if self.averager is None:
+        if self.pipeline:
+            if self.pool_in is None:
+                self.pool_in = torch.cuda.graph_pool_handle()
+                self._in_stream = torch.cuda.Stream(self.model.device)
+            gi = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gi, pool=self.pool_in):
+                sub = self.loader._collate(list(ids))
+            self.in_graphs[key] = (gi, sub)   # the outputs stay allocated: the step graph reads them
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.pool):
+                self._step_on(sub)
+            sub.data.adj_t.drop_caches()
+            self.graphs[key] = (g, None)
+        elif self.averager is None:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=self.pool):
                 self._body(ids)
@@ -290,6 +361,8 @@ class GraphedTrainer:
 
     def step(self, ids):
         key = tuple(ids)
+        if self.pipeline:
+            return self.run([ids])
         g = self.graphs.get(key)
         if g is None:
             # shuffled groups of several partitions never repeat: nothing to replay, issue eagerly

@@ -224,6 +224,67 @@ def test_graphed_trainer_matches_eager(cuda, vr):
         assert _rel(a, b) <= 1e-5
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize('vr', [False, True])
+def test_pipelined_collate_matches_plain_replay(cuda, vr):
+    """pipeline_collate=True (collate graph of step i+1 replayed on a side stream while step i runs)
+    gives bit-identical weights, losses and history tables to the one-graph-per-step replay: same
+    kernels on the same data, only their placement on streams differs."""
+    from incagg_gnn_b200.train import GraphedTrainer, mini_test
+    res = {}
+    for pipelined in (False, True):
+        run, *_ = _setup(cuda, 'C3', 64, dict(VR_update=vr), num_parts=6)
+        model = run['model']
+        mini_test(model, run['eval_loader'], VR_update=vr)
+        tr = GraphedTrainer(model, run['train_loader'], run['optimizer'], VR_update=vr,
+                            pipeline_collate=pipelined)
+        groups = run['train_loader']._batches_of_epoch()
+        tr.warmup(groups[0], steps=1)
+        seq = [groups[i % 6] for i in (0, 3, 1, 1, 5, 2, 4, 0, 0, 3)]   # repeats exercise buffer reuse
+        tr.run(seq)
+        torch.cuda.synchronize()
+        res[pipelined] = (tr.acc.clone(), [p.detach().clone() for p in model.parameters()],
+                          [h.emb.clone() for h in model.histories])
+    assert torch.equal(res[False][0], res[True][0])
+    for a, b in zip(res[False][1], res[True][1]):
+        assert torch.equal(a, b)
+    for a, b in zip(res[False][2], res[True][2]):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('bs,vr', [(1, False), (1, True), (2, False)])
+def test_host_resident_collate_matches_device_resident(cuda, bs, vr):
+    """Inputs in pinned host memory (graph staged by DMA for single partitions, features gathered
+    through UVA, labels + masks gathered as one packed record) collate to exactly the batches the
+    HBM-resident loader produces."""
+    from incagg_gnn_b200.train import build
+    subs = {}
+    for host in (False, True):
+        run = build('C3', device=cuda, seed=0, scale=64, shuffle=False, host_resident=host,
+                    history_device='cuda', overrides=dict(VR_update=vr, num_parts=6, batch_size=bs))
+        ld = run['train_loader']
+        if host:
+            assert ld._host_graph and ld._packed is not None and len(ld._packed_fields) >= 2
+        subs[host] = [ld._collate(list(ids)) for ids in ld._batches_of_epoch()]
+        subs[host] += [ld._collate(list(ids)) for ids in ld._batches_of_epoch()]  # sizes known: no sync
+    torch.cuda.synchronize()
+    assert len(subs[True]) == len(subs[False]) > 0
+    for a, b in zip(subs[False], subs[True]):
+        assert a.batch_size == b.batch_size
+        assert torch.equal(a.n_id, b.n_id)
+        assert torch.equal(a.offset, b.offset) and torch.equal(a.count, b.count)
+        assert torch.equal(a.data.adj_t.rowptr, b.data.adj_t.rowptr)
+        assert torch.equal(a.data.adj_t.col, b.data.adj_t.col)
+        assert torch.equal(a.data.adj_t.value, b.data.adj_t.value)
+        keys_a = sorted(k for k, v in a.data if isinstance(v, torch.Tensor))
+        keys_b = sorted(k for k, v in b.data if isinstance(v, torch.Tensor))
+        assert keys_a == keys_b and 'y' in keys_a and 'train_mask' in keys_a
+        for k in keys_a:
+            assert a.data[k].dtype == b.data[k].dtype and a.data[k].shape == b.data[k].shape, k
+            assert torch.equal(a.data[k], b.data[k]), k
+
+
 def test_metis_partitioned_graph_matches_oracle(cuda):
     """Same parity run on a graph partitioned by the real METIS (non-identity permutation, unequal
     partition sizes): refresh tables, logits and one IncAgg + one GAS epoch."""

@@ -52,3 +52,14 @@ for name, M, N, K, ta, tb, use_cin in shapes:
     flops = 2.0 * M * N * K
     print(json.dumps(dict(gemm=name, M=M, N=N, K=K, us_ours=round(t_ours, 2), us_cublas_fp32=round(t_torch, 2),
                           tflops_ours=round(flops / t_ours / 1e6, 1), tflops_cublas=round(flops / t_torch / 1e6, 1))), flush=True)
+
+# the fused GCNII pairs (ops.gemm_dual): input gradients g.[W1^T | W2^T] and weight gradients [h | x0]^T.g
+M, F = 16384, 128
+g = torch.randn(M, F, device=dev); h = torch.randn(M, F, device=dev); x0 = torch.randn(M, F, device=dev)
+w1 = torch.randn(F, F, device=dev); w2 = torch.randn(F, F, device=dev)
+o1 = torch.empty(M, F, device=dev); o2 = torch.empty(M, F, device=dev)
+d1 = torch.zeros(F, F, device=dev); d2 = torch.zeros(F, F, device=dev)
+t_k = timeit(lambda: ops.gemm_dual("k", h, w1, x0, w2, scale_b=0.3, scale_b2=0.2, cin=h, beta=0.5, cin2=x0, beta2=0.1, relu=True, out=o1))
+t_n = timeit(lambda: ops.gemm_dual("n", g, w1, b2=w2, trans_b=True, scale_b=0.3, scale_b2=0.2, cin=g, beta=0.5, cin2=g, beta2=0.1, out=o1, out2=o2))
+t_m = timeit(lambda: ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=0.3, alpha2=0.2, cin=d1, beta=1., cin2=d2, beta2=1., out=d1, out2=d2))
+print(json.dumps(dict(gemm="GCNII pairs (16384 x 128)", us_dual_k=round(t_k, 2), us_dual_n=round(t_n, 2), us_dual_m=round(t_m, 2))), flush=True)
