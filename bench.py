@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--scale", type=int, default=1, help="divide nodes and edges (debug only)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="collate inside each step's graph instead of overlapping it with the previous step")
     ap.add_argument("--no-graphs", action="store_true", help="issue every step eagerly from Python")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo rows: NVLink peer loads in the gather kernel, or NCCL all-to-all-v")
@@ -150,7 +152,7 @@ def timed_steps_graphed(run, mode, warmup, steps, dist):
         from incagg_gnn_b200.parallel import GradAverager
         averager = GradAverager(model.parameters(), run["shard"], flat=getattr(opt, "flat_g", None))
     tr = GraphedTrainer(model, loader, opt, VR_update=(mode == "incagg"), grad_norm=conf["grad_norm"],
-                        averager=averager)
+                        averager=averager, pipeline_collate=loader.fixed_batches and not NO_PIPELINE)
     rp_host, ptr = loader._rowptr_host, loader.ptr
     groups = loader._batches_of_epoch()
     tr.warmup(groups[0])
@@ -167,8 +169,7 @@ def timed_steps_graphed(run, mode, warmup, steps, dist):
                 yield ids
 
     it = stream_of_ids()
-    for _ in range(warmup):
-        tr.step(next(it))
+    tr.run([next(it) for _ in range(warmup)])
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -181,8 +182,7 @@ def timed_steps_graphed(run, mode, warmup, steps, dist):
         torch.cuda.profiler.start()
     t0 = time.perf_counter()
     ev0.record()
-    for ids in seq:
-        tr.step(ids)
+    tr.run(seq)
     ev1.record()
     torch.cuda.synchronize()
     if prof:
@@ -337,6 +337,7 @@ def load_peaks():
 
 
 _REAL_STDOUT = None
+NO_PIPELINE = False   # --no-pipeline: collate inside the step graph instead of one step ahead
 
 
 def _claim_stdout():
@@ -356,7 +357,9 @@ def _emit(line: dict):
 
 
 def main():
+    global NO_PIPELINE
     args = parse_args()
+    NO_PIPELINE = args.no_pipeline
     _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -559,7 +562,9 @@ def main():
                    "step_issue": ("eager (Python launches)" if graphs is None else
                                   f"CUDA graph per partition batch ({graphs['captured']} graphs captured before the "
                                   f"timed region in {graphs['capture_s']} s; every replay re-runs collate, forward, "
-                                  f"history push/pull, backward and Adam)")},
+                                  f"history push/pull, backward and Adam"
+                                  + ("" if NO_PIPELINE else "; the collate graph of step i+1 is replayed on a side "
+                                     "stream while step i computes") + ")")},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
         "cpu_baseline": cpu, "edges_timed": edges, "wall_s": wall, "refresh": refresh,
     }

@@ -223,11 +223,12 @@ class GraphedTrainer:
     of other ranks are read by the captured gather kernels straight out of the peers' HBM (p2p
     transport), so the graphs contain no collective.
 
-    ``pipeline_collate=True`` (host-resident inputs): the collate of a batch - the kernels that read
-    the graph, features, labels and masks out of pinned host memory over PCIe - is captured as its own
-    graph with its own memory pool and persistent outputs, and :meth:`run` replays the collate of
-    step i+1 on a side stream while step i computes (what the reference's DataLoader workers +
-    ``non_blocking`` copies do for its loop).  Every step still moves its inputs host -> device.
+    ``pipeline_collate=True``: the collate of a batch (relabel + gathers; with host-resident inputs
+    the kernels and DMA transfers that read the graph, features, labels and masks out of pinned host
+    memory over PCIe) is captured as its own graph with its own memory pool and persistent outputs,
+    and :meth:`run` replays the collate of step i+1 on a side stream while step i computes - what the
+    reference's DataLoader workers + ``non_blocking`` copies do for its loop.  Every step still
+    collates its batch (and moves its inputs host -> device); nothing is reused between steps.
     """
 
     def __init__(self, model, loader, optimizer, VR_update=False, grad_norm=None, averager=None,
@@ -237,8 +238,6 @@ class GraphedTrainer:
         self.graphs = {}
         self.pool = None
         self.pipeline = bool(pipeline_collate)
-        if self.pipeline and averager is not None:
-            raise RuntimeError('pipeline_collate is the single-GPU host-resident mode')
         self.pool_in = None          # memory pool of the collate graphs
         self.in_graphs = {}          # batch -> (collate graph, its persistent SubData)
         self._in_stream = None
@@ -257,9 +256,10 @@ class GraphedTrainer:
         apply_update(self.model, self.optimizer, self.grad_norm, self.averager)
 
     def _step_on(self, sub):
-        ln, n = forward_backward(self.model, sub, self.optimizer, self.vr, None)
+        ln, n = forward_backward(self.model, sub, self.optimizer, self.vr, self.averager)
         self.acc += torch.stack([ln.double(), n.double()])
-        apply_update(self.model, self.optimizer, self.grad_norm, None)
+        if self.averager is None:
+            apply_update(self.model, self.optimizer, self.grad_norm, None)
 
     def _launch_collate(self, key):
         """Replay the collate graph of batch `key` on the side stream (after the last step that read
@@ -284,6 +284,8 @@ class GraphedTrainer:
                     after_step(i)
             return
         keys = [tuple(ids) for ids in seq]
+        if not keys:
+            return
         for k in keys:
             self.capture(k)
         main = torch.cuda.current_stream(self.model.device)
@@ -291,12 +293,16 @@ class GraphedTrainer:
         self._launch_collate(keys[0])
         for i, k in enumerate(keys):
             main.wait_event(self._in_done[k])
-            self.graphs[k][0].replay()
+            g = self.graphs[k]
+            g[0].replay()
             ev = torch.cuda.Event()
             ev.record(main)
             self._step_done[k] = ev
             if i + 1 < len(keys):
                 self._launch_collate(keys[i + 1])
+            if g[1] is not None:
+                self.averager.all_reduce()  # NCCL, eager, between the two graphs
+                g[1].replay()
             if after_step is not None:
                 after_step(i)
 
@@ -339,11 +345,15 @@ class GraphedTrainer:
             with torch.cuda.graph(gi, pool=self.pool_in):
                 sub = self.loader._collate(list(ids))
             self.in_graphs[key] = (gi, sub)   # the outputs stay allocated: the step graph reads them
-            g = torch.cuda.CUDAGraph()
+            g, gb = torch.cuda.CUDAGraph(), None
             with torch.cuda.graph(g, pool=self.pool):
                 self._step_on(sub)
             sub.data.adj_t.drop_caches()
-            self.graphs[key] = (g, None)
+            if self.averager is not None:
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb, pool=self.pool):
+                    self._body_b()
+            self.graphs[key] = (g, gb)
         elif self.averager is None:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=self.pool):
@@ -380,6 +390,12 @@ class GraphedTrainer:
         """One epoch in the loader's (shuffled) batch order.  Returns the mean training loss."""
         self.acc.zero_()
         steps = 0
+        if self.pipeline and self.loader.fixed_batches:
+            seq = self.loader._batches_of_epoch()
+            seq = seq if max_steps is None else seq[:max_steps]
+            self.run(seq)
+            a = self.acc.tolist()
+            return {'loss': a[0] / max(a[1], 1.), 'steps': len(seq)}
         for ids in self.loader._batches_of_epoch():
             self.step(ids)
             steps += 1
