@@ -452,6 +452,7 @@ def mini_test(model, loader, use_aggregation=True, VR_update=False):
 def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_device='cuda',
           overrides: Optional[Dict[str, Any]] = None, log: bool = False, data_device=None,
           shuffle: bool = True, host_resident: bool = False, data=None, rank: int = 0,
+          eval_batch_size: Optional[int] = None,
           world_size: int = 1, transport: str = 'p2p', force_metis: bool = False, fused_adam: bool = True):
     """Everything main.py:140-201 sets up for one named config on synthetic data: returns a dict
     with data, ptr, loaders, model, optimizer, criterion and the config."""
@@ -489,8 +490,11 @@ def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_dev
     train_loader = SubgraphLoader(data, ptr, batch_size=conf['batch_size'], shuffle=shuffle,
                                   num_neighbors=-1, type='train', IB=conf['VR_update'], log=log,
                                   device=device, shard=shard, halo_plans=(transport == 'nccl'))
-    eval_loader = EvalSubgraphLoader(data, ptr, batch_size=conf['batch_size'], log=log, device=device,
-                                     shard=shard, halo_plans=(transport == 'nccl'))
+    # eval_batch_size: partitions merged into one batch of the layer-wise sweeps.  The reference sizes
+    # it for the GPU memory of its day (= the training batch size); with the tables HBM-resident a
+    # sweep over few large batches computes the same rows with far fewer, fuller launches.
+    eval_loader = EvalSubgraphLoader(data, ptr, batch_size=eval_batch_size or conf['batch_size'], log=log,
+                                     device=device, shard=shard, halo_plans=(transport == 'nccl'))
     buffer_size = max(n_id.numel() for _, _, n_id, _, _ in eval_loader) * 2
     kwargs = {}
     if conf['model'][:3] == 'PNA':

@@ -285,6 +285,25 @@ def test_host_resident_collate_matches_device_resident(cuda, bs, vr):
             assert torch.equal(a.data[k], b.data[k]), k
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize('vr', [False, True])
+def test_sweep_with_merged_eval_batches_matches_per_partition(cuda, vr):
+    """The layer-wise sweep over ONE merged evaluation batch (all partitions) refreshes the same
+    tables and logits as the sweep over single partitions: same rows, same per-row edge order; only
+    the split of very long rows may differ (fp32 re-association), hence 1e-6 instead of bit-equal."""
+    from incagg_gnn_b200.train import build, mini_test
+    res = {}
+    for merged in (False, True):
+        run = build('C3', device=cuda, seed=0, scale=64, shuffle=False,
+                    overrides=dict(VR_update=vr, num_parts=6), eval_batch_size=6 if merged else None)
+        assert len(run['eval_loader']) == (1 if merged else 6)
+        model = run['model']
+        out = mini_test(model, run['eval_loader'], VR_update=vr).clone()
+        res[merged] = [out] + [h.emb.clone() for h in list(model.histories) + list(model.histories_ag)]
+    for a, b in zip(res[False], res[True]):
+        assert _rel(a, b) <= 1e-6
+
+
 def test_metis_partitioned_graph_matches_oracle(cuda):
     """Same parity run on a graph partitioned by the real METIS (non-identity permutation, unequal
     partition sizes): refresh tables, logits and one IncAgg + one GAS epoch."""
