@@ -225,7 +225,7 @@ class GraphedTrainer:
 
     ``pipeline_collate=True``: the collate of a batch (relabel + gathers; with host-resident inputs
     the kernels and DMA transfers that read the graph, features, labels and masks out of pinned host
-    memory over PCIe) is captured as its own graph with its own memory pool and persistent outputs,
+    memory over PCIe) is captured as its own graph with a private memory pool and persistent outputs,
     and :meth:`run` replays the collate of step i+1 on a side stream while step i computes - what the
     reference's DataLoader workers + ``non_blocking`` copies do for its loop.  Every step still
     collates its batch (and moves its inputs host -> device); nothing is reused between steps.
@@ -238,7 +238,6 @@ class GraphedTrainer:
         self.graphs = {}
         self.pool = None
         self.pipeline = bool(pipeline_collate)
-        self.pool_in = None          # memory pool of the collate graphs
         self.in_graphs = {}          # batch -> (collate graph, its persistent SubData)
         self._in_stream = None
         self._in_done, self._step_done = {}, {}
@@ -338,11 +337,14 @@ class GraphedTrainer:
         if self.pool is None:
             self.pool = torch.cuda.graph_pool_handle()
         if self.pipeline:
-            if self.pool_in is None:
-                self.pool_in = torch.cuda.graph_pool_handle()
+            if self._in_stream is None:
                 self._in_stream = torch.cuda.Stream(self.model.device)
+            # Every collate graph gets a memory pool of its OWN: its outputs are read by a step graph
+            # that runs concurrently with the NEXT collate, so they must not share addresses with
+            # another collate graph's temporaries (which a common pool would hand out again as soon
+            # as they are freed at capture time).
             gi = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gi, pool=self.pool_in):
+            with torch.cuda.graph(gi):
                 sub = self.loader._collate(list(ids))
             self.in_graphs[key] = (gi, sub)   # the outputs stay allocated: the step graph reads them
             g, gb = torch.cuda.CUDAGraph(), None
