@@ -37,6 +37,35 @@ class SubData(NamedTuple):
                        self.n_id, self.offset, self.count)
 
 
+def pack_node_records(fields):
+    """Pack narrow per-node attributes ``[(name, tensor[N, ...])]`` (row size <= 8 bytes each: labels,
+    masks) into one ``uint8 [N, R]`` record table, R a multiple of 16 bytes, every field at its
+    natural alignment.  Returns ``(table, [(name, dtype, trailing shape, byte offset, bytes)])``."""
+    n = fields[0][1].size(0)
+    layout, off = [], 0
+    for k, v in fields:
+        w = v[0].numel() * v.element_size()
+        off = (off + w - 1) // w * w
+        layout.append((k, v.dtype, tuple(v.shape[1:]), off, w))
+        off += w
+    rec = (off + 15) // 16 * 16
+    table = torch.zeros((n, rec), dtype=torch.uint8)
+    for (k, dt, shp, o, w), (_, v) in zip(layout, fields):
+        src = v.view(torch.uint8) if v.dtype == torch.bool else v
+        table[:, o:o + w] = src.contiguous().view(n, -1).view(torch.uint8)
+    return table, layout
+
+
+def unpack_node_records(rec: Tensor, layout):
+    """Inverse of :func:`pack_node_records` on a (gathered) record table: ``{name: tensor}``."""
+    out, n = {}, rec.size(0)
+    for k, dt, shp, o, w in layout:
+        col = rec[:, o:o + w].contiguous()
+        col = col.view(torch.uint8 if dt == torch.bool else dt).view((n,) + shp)
+        out[k] = col.view(torch.bool) if dt == torch.bool else col
+    return out
+
+
 class SubgraphLoader:
     r"""A simple subgraph loader that, given a pre-partioned :obj:`data` object,
     generates subgraphs from mini-batches in :obj:`ptr` (including their 1-hop
@@ -98,17 +127,7 @@ class SubgraphLoader:
                   if isinstance(v, Tensor) and v.dim() >= 1 and v.size(0) == data.num_nodes and not v.is_cuda
                   and v.is_pinned() and v[0].numel() * v.element_size() <= 8]
         if len(narrow) > 1:
-            off = 0
-            for k, v in narrow:
-                w = v[0].numel() * v.element_size()
-                off = (off + w - 1) // w * w          # natural alignment of the field
-                self._packed_fields.append((k, v.dtype, tuple(v.shape[1:]), off, w))
-                off += w
-            rec = (off + 15) // 16 * 16
-            packed = torch.zeros((data.num_nodes, rec), dtype=torch.uint8)
-            for (k, dt, shp, o, w), (_, v) in zip(self._packed_fields, narrow):
-                src = v.view(torch.uint8) if v.dtype == torch.bool else v
-                packed[:, o:o + w] = src.contiguous().view(data.num_nodes, -1).view(torch.uint8)
+            packed, self._packed_fields = pack_node_records(narrow)
             self._packed = packed.pin_memory()
 
         n_local = len(self._parts)
@@ -188,10 +207,8 @@ class SubgraphLoader:
         if self._packed is not None:
             rec = ops.gather_rows(self._packed, n_id)             # [n, record bytes] uint8
             packed_keys = {f[0] for f in self._packed_fields}
-            for k, dt, shp, o, w in self._packed_fields:
-                col = rec[:, o:o + w].contiguous()
-                col = col.view(torch.uint8 if dt == torch.bool else dt).view((n_id.numel(),) + shp)
-                data[k] = col.view(torch.bool) if dt == torch.bool else col
+            for k, v in unpack_node_records(rec, self._packed_fields).items():
+                data[k] = v
         for k, v in self.data:
             if k in packed_keys:
                 continue

@@ -167,3 +167,37 @@ def test_gen_masks_and_edge_dropout():
     lg = torch.tensor([[2., -1.], [1., 3.], [-1., 2.]])
     # tp = 3, predicted = 4, actual = 4 -> p = r = 0.75
     assert abs(tga.compute_micro_f1(lg, y2) - 0.75) < 1e-9
+
+
+def test_node_record_packing_roundtrip():
+    """Labels + masks packed into 16-byte records (one host gather per step instead of four) unpack to
+    the original columns, for any subset of rows and for 2-D narrow attributes."""
+    import torch
+    from incagg_gnn_b200.loader import pack_node_records, unpack_node_records
+    g = torch.Generator().manual_seed(3)
+    n = 1000
+    fields = [('y', torch.randint(-5, 47, (n,), generator=g)),
+              ('train_mask', torch.rand(n, generator=g) < 0.6),
+              ('val_mask', torch.rand(n, generator=g) < 0.2),
+              ('w', torch.randn(n, generator=g)),
+              ('pair', torch.randint(0, 2 ** 15, (n, 2), generator=g).to(torch.int16)),
+              ('flag', torch.randint(0, 255, (n,), generator=g).to(torch.uint8))]
+    table, layout = pack_node_records(fields)
+    assert table.dtype == torch.uint8 and table.size(0) == n and table.size(1) % 16 == 0
+    for (k, dt, shp, o, w) in layout:
+        assert o % w == 0                    # natural alignment
+    idx = torch.randperm(n, generator=g)[:137]
+    got = unpack_node_records(table[idx], layout)
+    for k, v in fields:
+        assert got[k].dtype == v.dtype and got[k].shape == v[idx].shape
+        assert torch.equal(got[k], v[idx]), k
+
+
+def test_fixed_batches_rule():
+    """Per-batch graph capture needs a fixed set of batches: single partitions or sequential groups."""
+    from incagg_gnn_b200.loader import SubgraphLoader
+    class L:  # the property only reads these two attributes
+        fixed_batches = SubgraphLoader.fixed_batches
+    for bs, shuffle, want in [(1, True, True), (1, False, True), (4, False, True), (4, True, False)]:
+        l = L(); l.batch_size, l.shuffle = bs, shuffle
+        assert l.fixed_batches is want
