@@ -7,7 +7,9 @@ the reference's locally patched GCN2Conv:
 ``forward_after_propagate(h, x_0)`` = everything in ``GCN2Conv.forward`` after ``propagate``;
 ``forward_no_neighbor(x, x_0)`` = the same with ``h = x``.
 """
+import contextlib
 import math
+import os
 from typing import Optional
 
 import torch
@@ -81,6 +83,34 @@ class Linear(torch.nn.Linear):
         return linear(x, self.weight, self.bias, relu)
 
 
+# Weight gradients on a side stream -----------------------------------------------------------------
+# Inside train.forward_backward the M-concatenated weight-gradient GEMMs of the GCNII layers
+# ([h | x0]^T g, accumulated into the flat gradient buffer) are issued on a side stream: nothing in the
+# rest of the backward pass reads them, so they overlap the SpMM^T / input-gradient chain (a GEMM call is
+# bound by one CTA per SM moving its tiles, the SpMM by the L2 gather path: they share an SM well).
+# The operands are kept alive until the join at the end of the backward pass.
+_WGRAD = {'stream': None, 'keep': []}
+_WGRAD_STREAMS = {}
+
+
+@contextlib.contextmanager
+def weight_grads_on_side_stream(device):
+    device = torch.device(device)
+    if device.type != 'cuda' or os.environ.get('INCAGG_WGRAD_STREAM', '1') == '0':
+        yield
+        return
+    side = _WGRAD_STREAMS.get(device)
+    if side is None:
+        side = _WGRAD_STREAMS[device] = torch.cuda.Stream(device)
+    _WGRAD['stream'] = side
+    try:
+        yield
+    finally:
+        _WGRAD['stream'] = None
+        torch.cuda.current_stream(device).wait_stream(side)
+        _WGRAD['keep'].clear()
+
+
 class _GCN2Dense(torch.autograd.Function):
     """The dense half of GCN2Conv after the propagation, fused around the tensor-core GEMM:
         s   = (1-a) h + a x0
@@ -138,8 +168,16 @@ class _GCN2Dense(torch.autograd.Function):
                                     cin=g, beta=(1. - b) * (1. - a), cin2=g, beta2=(1. - b) * a)
             b1, b2 = _grad_buffer(ctx.w1_param), _grad_buffer(ctx.w2_param)
             if b1 is not None and b2 is not None:         # accumulate into the flat gradient buffers
-                ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a,
-                              cin=b1, beta=1., cin2=b2, beta2=1., out=b1, out2=b2)
+                side = _WGRAD['stream']
+                if side is not None:
+                    side.wait_stream(torch.cuda.current_stream(g.device))
+                    with torch.cuda.stream(side):
+                        ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a,
+                                      cin=b1, beta=1., cin2=b2, beta2=1., out=b1, out2=b2, ws_slot=1)
+                    _WGRAD['keep'].append((h, x0, g))
+                else:
+                    ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a,
+                                  cin=b1, beta=1., cin2=b2, beta2=1., out=b1, out2=b2)
             else:
                 gw1, gw2 = ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a)
         return gh, gx0, gw1, gw2, None, None, None, None

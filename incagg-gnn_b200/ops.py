@@ -162,10 +162,11 @@ def csr_transpose(rowptr: Tensor, col: Tensor, val: Optional[Tensor], rows: int,
 _GEMM_WS = {}
 
 
-def _gemm_workspace(device, nbytes: int) -> Tensor:
-    ws = _GEMM_WS.get(device)
+def _gemm_workspace(device, nbytes: int, slot: int = 0) -> Tensor:
+    """Split-K scratch, one per (device, slot): GEMMs issued on different streams use different slots."""
+    ws = _GEMM_WS.get((device, slot))
     if ws is None or ws.numel() < nbytes:
-        ws = _GEMM_WS[device] = torch.empty(max(nbytes, 1 << 24), dtype=torch.uint8, device=device)
+        ws = _GEMM_WS[(device, slot)] = torch.empty(max(nbytes, 1 << 24), dtype=torch.uint8, device=device)
     return ws
 
 
@@ -209,7 +210,7 @@ def gemm_dual(mode: str, a: Tensor, b: Tensor, a2: Optional[Tensor] = None, b2: 
               trans_a: bool = False, trans_b: bool = False, alpha: float = 1.0, alpha2: float = 1.0,
               scale_b: float = 1.0, scale_b2: float = 1.0, cin: Optional[Tensor] = None, beta: float = 0.0,
               cin2: Optional[Tensor] = None, beta2: float = 0.0, relu: bool = False,
-              out: Optional[Tensor] = None, out2: Optional[Tensor] = None):
+              out: Optional[Tensor] = None, out2: Optional[Tensor] = None, ws_slot: int = 0):
     """Two GEMMs sharing an operand in one launch (include/incagg_b200.h, incagg_gemm_tf32x3_dual):
     mode 'k': out = alpha (a @ (scale_b b) + a2 @ (scale_b2 b2)) + beta cin + beta2 cin2
     mode 'n': out = alpha a @ (scale_b b) + beta cin ; out2 = alpha2 a @ (scale_b2 b2) + beta2 cin2
@@ -233,7 +234,7 @@ def gemm_dual(mode: str, a: Tensor, b: Tensor, a2: Optional[Tensor] = None, b2: 
     ws, ws_bytes = None, 0
     if mode == "m":
         ws_bytes = min(lib.incagg_gemm_workspace_bytes(M, N, K), 1 << 28)
-        ws = _gemm_workspace(dev, ws_bytes)
+        ws = _gemm_workspace(dev, ws_bytes, ws_slot)
         ws_bytes = ws.numel()
     LAUNCHES["calls"] += 1
     check(lib.incagg_gemm_tf32x3_dual(

@@ -9,6 +9,7 @@ Differences from the reference loop, none of which change results:
 """
 from typing import Any, Dict, Optional
 
+import contextlib
 import os
 import torch
 
@@ -174,9 +175,12 @@ def forward_backward(model, sub, optimizer, VR_update=False, averager=None, epoc
         optimizer.zero_grad(set_to_none=True)
     if y.dim() == 1 and out.dtype == torch.float32:
         # criterion(out[mask], y[mask]) as one fused masked cross-entropy (loss + gradient kernels)
-        from .nn import masked_cross_entropy
+        from .nn import masked_cross_entropy, weight_grads_on_side_stream
         loss, out3 = masked_cross_entropy(out, y, train_mask)
-        loss.backward()
+        # (single-GPU path; with a gradient averager the step keeps the one-stream backward that the
+        # multi-GPU runs of this round were measured and checked with)
+        with (weight_grads_on_side_stream(out.device) if averager is None else contextlib.nullcontext()):
+            loss.backward()
         return out3[0], out3[2]
     w = train_mask.to(out.dtype)
     n = w.sum()
