@@ -1,8 +1,7 @@
-"""incagg-gnn_b200 — B200-native implementation of IncAgg-GNN's per-batch propagation hot path
+"""incagg_gnn_b200 — B200-native implementation of IncAgg-GNN's per-batch propagation hot path
 behind the reference's ``torch_geometric_autoscale`` Python API (reference ``__init__.py:20-33``).
 
-The directory name carries a hyphen, so import it through the root-level shim ``incagg_gnn_b200``
-(``import incagg_gnn_b200 as tga``).  Importing the package loads the C-ABI CUDA library
+``import incagg_gnn_b200 as tga`` from the repository root.  Importing the package loads the C-ABI CUDA library
 ``csrc/libincagg_b200.so`` and fails loudly when it has not been built: there is no CPU fallback.
 """
 __version__ = '0.1.0'

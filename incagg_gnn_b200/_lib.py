@@ -27,10 +27,13 @@ class IncAggError(RuntimeError):
 
 
 def _load():
+    # the library links the CUDA runtime dynamically (libcudart.so.12): importing torch first makes the
+    # loader reuse the copy torch ships, whatever LD_LIBRARY_PATH says
+    import torch  # noqa: F401
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found: the CUDA extension is not built. Run "
-            "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C incagg-gnn_b200/csrc`). "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C incagg_gnn_b200/csrc`). "
             "There is no CPU fallback for the hot path.")
     return ctypes.CDLL(LIB_PATH)
 

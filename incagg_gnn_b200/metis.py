@@ -68,7 +68,7 @@ def partition(rowptr: Tensor, col: Tensor, num_parts: int, recursive: bool = Fal
     (METIS k-way).  Returns (cluster, edgecut)."""
     lib = _metis_lib()
     if not lib:
-        raise RuntimeError('libincagg_metis.so is not built (make -C incagg-gnn_b200/csrc metis)')
+        raise RuntimeError('libincagg_metis.so is not built (make -C incagg_gnn_b200/csrc metis)')
     rowptr = rowptr.cpu().to(torch.int64).contiguous()
     col = col.cpu().to(torch.int64).contiguous()
     n = rowptr.numel() - 1

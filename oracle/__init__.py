@@ -2,7 +2,7 @@
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
 legs may import this package, and only as the checker / the timed CPU baseline.  The product package
-(``incagg-gnn_b200/``) never imports it and has no CPU fallback.
+(``incagg_gnn_b200/``) never imports it and has no CPU fallback.
 
 Contents
   * ``relabel_oracle.c`` -> ``liboracle.so``: plain-C restatement of ``relabel_one_hop`` /

@@ -2,7 +2,7 @@
  * relabel_oracle.c — CPU restatement (plain C) of the reference's relabel ops.
  *
  * TEST INFRASTRUCTURE ONLY.  Nothing on the product path may link or call this file; it is the
- * checker that the CUDA kernels in incagg-gnn_b200/csrc/relabel.cu are compared against (tests/,
+ * checker that the CUDA kernels in incagg_gnn_b200/csrc/relabel.cu are compared against (tests/,
  * __graft_entry__.smoke(), bench.py's cpu_baseline leg).
  *
  * Follows (reference paths relative to the reference repo):

@@ -30,7 +30,7 @@ def test_argument_errors_do_not_need_a_gpu():
 
 
 def test_product_does_not_import_the_oracle():
-    pkg = os.path.join(ROOT, "incagg-gnn_b200")
+    pkg = os.path.join(ROOT, "incagg_gnn_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
