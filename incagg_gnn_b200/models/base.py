@@ -380,6 +380,10 @@ class ScalableGNN(torch.nn.Module):
         if self.shard is not None and self.shard.world_size > 1 and getattr(self, 'transport', '') == 'p2p':
             # peers read this rank's rows directly: a layer phase must be complete on every rank before
             # the next one starts (the NCCL transport gets this ordering from its collectives)
+            hook = getattr(self, '_sweep_phase_hook', None)
+            if hook is not None:   # train.GraphedSweep: one CUDA graph per layer phase, it barriers itself
+                hook()
+                return
             import torch.distributed as dist
             torch.cuda.current_stream(self.device).synchronize()
             dist.barrier(group=self.shard.group)

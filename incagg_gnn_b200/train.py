@@ -20,40 +20,46 @@ from .preprocess import gcn_norm, set_diag
 from .synthetic import get_data
 from .utils import dropout
 
-# Hyper-parameters per BASELINE config (values from the reference YAML where the fork has them).
-CONFIGS: Dict[str, Dict[str, Any]] = {
-    # C1: no flickr entry in conf/model/gcn.yaml -> 2 layers, hidden 256
-    'C1': dict(model='GCN', dataset='flickr', loop=True, norm=True, VR_update=False,
-               architecture=dict(num_layers=2, hidden_channels=256, dropout=0.0, drop_input=False,
-                                 batch_norm=False, residual=False),
-               num_parts=24, batch_size=12, max_steps=-1, pool_size=2, lr=0.01,
-               reg_weight_decay=0., nonreg_weight_decay=0., grad_norm=None),
-    # C2: conf/model/appnp.yaml:7-22, IncAgg
-    'C2': dict(model='APPNP', dataset='arxiv', loop=False, norm=True, VR_update=True,
-               architecture=dict(num_layers=5, hidden_channels=256, alpha=0.1, dropout=0.3),
-               num_parts=80, batch_size=40, max_steps=-1, pool_size=2, lr=0.01,
-               reg_weight_decay=0., nonreg_weight_decay=0., grad_norm=1.0),
-    # C3: conf/model/gcn2.yaml:51-71 (headline metric)
-    'C3': dict(model='GCN2', dataset='products', loop=True, norm=True, VR_update=False,
-               architecture=dict(num_layers=5, hidden_channels=128, dropout=0.0, drop_input=False,
-                                 batch_norm=False, residual=False, shared_weights=False, alpha=0.1,
-                                 theta=0.5),
-               num_parts=150, batch_size=1, max_steps=-1, pool_size=1, lr=0.001,
-               reg_weight_decay=0., nonreg_weight_decay=0., grad_norm=None),
-    # C4: conf/model/graphsage.yaml:7-24
-    'C4': dict(model='GraphSAGE', dataset='reddit', loop=True, norm=True, VR_update=False,
-               architecture=dict(num_layers=2, hidden_channels=1024, dropout=0.5, drop_input=False,
-                                 batch_norm=False, residual=False),
-               num_parts=200, batch_size=100, max_steps=2, pool_size=2, lr=0.01,
-               reg_weight_decay=0., nonreg_weight_decay=0., grad_norm=None),
-    # C5: no PNA yaml in the fork; layer shape of conf/model/gcn.yaml:65-83
-    'C5': dict(model='PNA', dataset='amazonproducts', loop=True, norm=True, VR_update=False,
-               architecture=dict(num_layers=3, hidden_channels=256, dropout=0.3, drop_input=False,
-                                 batch_norm=False, residual=False,
-                                 aggregators=['sum', 'mean', 'min', 'max'], scalers=['identity']),
-               num_parts=200, batch_size=100, max_steps=-1, pool_size=1, lr=0.005,
-               reg_weight_decay=0., nonreg_weight_decay=0., grad_norm=None),
-}
+CONFIG_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'conf', 'configs.yaml')
+
+
+def _parse_scalar(text: str):
+    import yaml
+    return yaml.safe_load(text)
+
+
+def apply_overrides(conf: Dict[str, Any], overrides) -> Dict[str, Any]:
+    """hydra-style command-line overrides (reference main.py:112-122 runs under @hydra.main):
+    ``++key=value`` / ``key=value`` set a top-level entry, ``++architecture.hidden_channels=64`` a
+    nested one; values are parsed as YAML scalars / lists.  Returns a new dict."""
+    import copy
+    out = copy.deepcopy(conf)
+    for item in overrides or ():
+        key, sep, value = item.lstrip('+').partition('=')
+        if not sep or not key:
+            raise ValueError(f'override {item!r} is not of the form [++]key=value')
+        node = out
+        parts = key.split('.')
+        for k in parts[:-1]:
+            node = node.setdefault(k, {})
+            if not isinstance(node, dict):
+                raise ValueError(f'override {item!r}: {k!r} is not a section')
+        node[parts[-1]] = _parse_scalar(value)
+    return out
+
+
+def load_configs(path: Optional[str] = None, overrides=None) -> Dict[str, Dict[str, Any]]:
+    """The per-config hyper-parameters (conf/configs.yaml, values from the reference's
+    conf/model/*.yaml where the fork has them), with optional hydra-style overrides applied to every
+    config."""
+    import yaml
+    with open(path or CONFIG_FILE) as f:
+        table = yaml.safe_load(f)
+    return {k: apply_overrides(v, overrides) for k, v in table.items()}
+
+
+# Hyper-parameters per BASELINE config
+CONFIGS: Dict[str, Dict[str, Any]] = load_configs()
 
 
 class FlatAdam:
@@ -413,16 +419,25 @@ class GraphedTrainer:
 
 class GraphedSweep:
     """The per-epoch layer-wise sweep (``mini_inference`` / ``mini_inference_vr``: all partitions, all
-    layers, ~10^4 launches of small kernels) captured once as ONE CUDA graph and replayed every epoch.
-    The evaluation loader pre-materialises its subgraphs (as the reference's does, loader.py:153-170), so
-    the kernel sequence is fixed; every replay recomputes all tables from the current weights.
-    Single-GPU, HBM-resident histories (the sharded p2p sweep needs host barriers between layer phases)."""
+    layers, ~10^4 launches of small kernels) captured once and replayed every epoch.  The evaluation
+    loader pre-materialises its subgraphs (as the reference's does, loader.py:153-170), so the kernel
+    sequence is fixed; every replay recomputes all tables from the current weights.
+
+    Single GPU: ONE graph.  Sharded tables (p2p transport): peers read this rank's rows directly, so a
+    layer phase must be complete on every rank before the next one starts; the sweep is captured as one
+    graph PER LAYER PHASE (cut where the eager sweep synchronises, ``ScalableGNN._sweep_sync``) and the
+    replays are separated by a stream synchronisation + ``dist.barrier`` (L + 1 barriers per sweep)."""
 
     def __init__(self, model, loader, VR_update=False, use_aggregation=True):
-        if model.pool is not None or model.shard is not None:
-            raise RuntimeError('GraphedSweep needs HBM-resident, unsharded histories')
+        if model.pool is not None:
+            raise RuntimeError('GraphedSweep needs HBM-resident histories')
+        if model.shard is not None and model.shard.world_size > 1 and getattr(model, 'transport', '') != 'p2p':
+            raise RuntimeError('GraphedSweep on sharded tables needs the p2p transport (NCCL collectives '
+                               'of the all-to-all-v transport are issued eagerly)')
         self.model, self.loader, self.vr, self.use_aggregation = model, loader, VR_update, use_aggregation
         self.graph = None
+        self.phases = None
+        self.sharded = model.shard is not None and model.shard.world_size > 1
 
     @torch.no_grad()
     def _body(self):
@@ -430,20 +445,62 @@ class GraphedSweep:
             return self.model.mini_inference_vr(loader=self.loader, use_aggregation=self.use_aggregation)
         return self.model.mini_inference(self.loader, self.use_aggregation)
 
+    def _phase_barrier(self):
+        import torch.distributed as dist
+        torch.cuda.current_stream(self.model.device).synchronize()
+        dist.barrier(group=self.model.shard.group)
+
+    @torch.no_grad()
+    def _capture_phases(self):
+        """One graph per layer phase: the capture is cut at every ``_sweep_sync`` of the sweep."""
+        dev = self.model.device
+        pool = torch.cuda.graph_pool_handle()
+        phases, cur, dirty = [], [None], [False]
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+
+        def begin():
+            cur[0] = torch.cuda.CUDAGraph()
+            cur[0].capture_begin(pool=pool)
+
+        def cut():
+            cur[0].capture_end()
+            phases.append(cur[0])
+            begin()
+
+        with torch.cuda.stream(s):
+            begin()
+            self.model._sweep_phase_hook = cut
+            try:
+                self._body()
+            finally:
+                self.model._sweep_phase_hook = None
+                cur[0].capture_end()   # the sweep ends with a cut: this last graph is empty, not kept
+        torch.cuda.current_stream(dev).wait_stream(s)
+        return phases
+
     @torch.no_grad()
     def __call__(self):
         self.model.eval()
-        if self.graph is None:
+        if self.graph is None and self.phases is None:
             s = torch.cuda.Stream(self.model.device)
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 self._body()  # eager warm-up (plans, transposes, scratch, output buffer)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._body()
-        self.graph.replay()
+            if self.sharded:
+                self.phases = self._capture_phases()
+            else:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._body()
+        if self.sharded:
+            for g in self.phases:
+                g.replay()
+                self._phase_barrier()
+        else:
+            self.graph.replay()
         return self.model._out
 
 

@@ -38,8 +38,53 @@ class Adj(NamedTuple):
         return torch.repeat_interleave(torch.arange(self.rows), deg)
 
 
+# How sum / mean aggregation is executed.  'gather' is the definition the parity tests use (gather the
+# messages, index_add them: any dtype, plain autograd).  'csr' is what the timed CPU baseline uses: the
+# same product through ATen's CSR kernels (`torch.sparse_csr_tensor @ X`, multi-threaded), with the
+# backward pass as a product with the transposed CSR that is built once per structure and reused by
+# every layer - what torch_sparse does (csr2csc cached in the SparseTensor's storage).  The two agree
+# to rounding (tests/test_oracle.py::test_csr_baseline_matches_the_definition).
+SPMM_IMPL = 'gather'
+_CSR_CACHE: Dict[int, tuple] = {}
+
+
+def _csr_pair(adj: Adj, dtype):
+    key = (adj.rowptr.data_ptr(), adj.col.data_ptr(), 0 if adj.val is None else adj.val.data_ptr(), dtype)
+    hit = _CSR_CACHE.get(key)
+    if hit is not None and hit[0] is adj.rowptr:
+        return hit[1], hit[2]
+    val = torch.ones(adj.col.numel(), dtype=dtype) if adj.val is None else adj.val.to(dtype)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')   # "sparse CSR support is in beta state"
+        a = torch.sparse_csr_tensor(adj.rowptr, adj.col, val, size=(adj.rows, adj.cols))
+        at = a.t().to_sparse_csr()
+    if len(_CSR_CACHE) > 64:
+        _CSR_CACHE.clear()
+    _CSR_CACHE[key] = (adj.rowptr, a, at)
+    return a, at
+
+
+class _CsrMatmul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, a, at):
+        ctx.at = at
+        return a @ x
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.at @ g.contiguous(), None, None
+
+
 def spmm(adj: Adj, x: Tensor, reduce: str = 'sum') -> Tensor:
     """torch_sparse.matmul(adj, x, reduce) with autograd w.r.t. x (edge values are constants)."""
+    if SPMM_IMPL == 'csr' and reduce in ('sum', 'add', 'mean') and adj.col.numel() > 0:
+        a, at = _csr_pair(adj, x.dtype)
+        out = _CsrMatmul.apply(x, a, at)
+        if reduce == 'mean':
+            deg = (adj.rowptr[1:] - adj.rowptr[:-1]).clamp(min=1).to(x.dtype)
+            out = out / deg.unsqueeze(1)
+        return out
     row = adj.row()
     msg = x[adj.col]
     if adj.val is not None:
@@ -157,19 +202,25 @@ class SubData(NamedTuple):
 
 
 def collate(graph: Adj, x: Tensor, y: Tensor, train_mask: Tensor, ptr: Tensor, batch_ids: List[int],
-            within_batch: bool = False) -> SubData:
-    """compute_subgraph (GAS, loader.py:172-192) / compute_subgraph_IB (IncAgg, :194-214)."""
+            within_batch: bool = False, relabel_fn=None) -> SubData:
+    """compute_subgraph (GAS, loader.py:172-192) / compute_subgraph_IB (IncAgg, :194-214).
+    `relabel_fn(rowptr, col, value, idx, bipartite)` on torch tensors replaces the C restatement (the
+    timed reference arm passes the reference's own compiled op, oracle/_ref/ref_relabel.so)."""
     batch_id = torch.tensor(batch_ids)
     n_id = torch.cat([torch.arange(int(ptr[b]), int(ptr[b + 1])) for b in batch_ids])
     batch_size = n_id.numel()
     offset = ptr[batch_id]
     count = ptr[batch_id + 1] - ptr[batch_id]
-    fn = _rl.relabel_one_hop_within_batch if within_batch else _rl.relabel_one_hop
-    val = None if graph.val is None else graph.val.numpy()
-    rp, c, v, nid = fn(graph.rowptr.numpy(), graph.col.numpy(), val, n_id.numpy(), True)
-    n_id = torch.from_numpy(np.ascontiguousarray(nid))
-    adj = Adj(torch.from_numpy(rp), torch.from_numpy(c), None if v is None else torch.from_numpy(v),
-              batch_size, n_id.numel())
+    if relabel_fn is not None:
+        rp, c, v, n_id = relabel_fn(graph.rowptr, graph.col, graph.val, n_id, True)
+        adj = Adj(rp, c, v, batch_size, n_id.numel())
+    else:
+        fn = _rl.relabel_one_hop_within_batch if within_batch else _rl.relabel_one_hop
+        val = None if graph.val is None else graph.val.numpy()
+        rp, c, v, nid = fn(graph.rowptr.numpy(), graph.col.numpy(), val, n_id.numpy(), True)
+        n_id = torch.from_numpy(np.ascontiguousarray(nid))
+        adj = Adj(torch.from_numpy(rp), torch.from_numpy(c), None if v is None else torch.from_numpy(v),
+                  batch_size, n_id.numel())
     return SubData(x.index_select(0, n_id), y.index_select(0, n_id), train_mask.index_select(0, n_id),
                    adj, batch_size, n_id, offset, count)
 

@@ -122,3 +122,20 @@ def ref_relabel(fn: str, rowptr, col, value, idx, bipartite=True):
         subprocess.check_call([sys.executable, "-c", _REF_SCRIPT, _REF_PATH, fin, fout])
         d = np.load(fout)
         return d["rowptr"], d["col"], (d["value"] if value is not None else None), d["n_id"]
+
+
+def ref_ops_in_process():
+    """The reference's compiled relabel ops loaded into THIS process (torch.ops.load_library).  Only
+    for processes that never import the product package, whose operator names are the same ones
+    (bench.py --impl reference).  Returns (relabel_one_hop, relabel_one_hop_within_batch) taking and
+    returning torch tensors, exactly the reference's signatures (csrc/relabel.cpp:10-38)."""
+    import sys
+    import torch
+    if "incagg_gnn_b200" in sys.modules:
+        raise RuntimeError("the product package registers the same operator names; run the reference's "
+                           "op in a subprocess (ref_relabel) instead")
+    if not ref_available():
+        raise FileNotFoundError(_REF_PATH)
+    torch.ops.load_library(_REF_PATH)
+    ns = torch.ops.torch_geometric_autoscale
+    return ns.relabel_one_hop, ns.relabel_one_hop_within_batch

@@ -143,7 +143,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "edges/s" and line["value"] > 0
     assert line["metric"].startswith("edges/s") and line["higher_is_better"] is True
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["warmup"] == 1 and line["steps"] == 2
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert line["config"]["workload"].startswith("C3")
 
@@ -201,3 +202,56 @@ def test_fixed_batches_rule():
     for bs, shuffle, want in [(1, True, True), (1, False, True), (4, False, True), (4, True, False)]:
         l = L(); l.batch_size, l.shuffle = bs, shuffle
         assert l.fixed_batches is want
+
+
+def test_hydra_style_overrides_and_yaml_table():
+    """conf/configs.yaml + `++key=value` overrides (the reference runs under hydra, main.py:112-122)."""
+    from incagg_gnn_b200.train import CONFIGS, apply_overrides, load_configs
+    c = apply_overrides(CONFIGS['C3'], ['++architecture.hidden_channels=64', 'lr=0.1', '++grad_norm=null',
+                                        '++architecture.aggregators=[sum, max]'])
+    assert c['architecture']['hidden_channels'] == 64 and c['lr'] == 0.1 and c['grad_norm'] is None
+    assert c['architecture']['aggregators'] == ['sum', 'max']
+    assert CONFIGS['C3']['architecture']['hidden_channels'] == 128      # the table itself is untouched
+    assert load_configs(overrides=['batch_size=3'])['C1']['batch_size'] == 3
+    with pytest.raises(ValueError):
+        apply_overrides(CONFIGS['C3'], ['nonsense'])
+
+
+def test_bench_cpu_baseline_accepts_sharded_history_tables():
+    """bench.cpu_baseline() on the run dict of a world_size=2 rank: the model holds only its own rows of
+    every history table (round 1's multi-GPU bench died here with a shape error)."""
+    import importlib
+    import os
+    import sys
+    from types import SimpleNamespace
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    from incagg_gnn_b200.parallel import Shard
+    from incagg_gnn_b200.train import CONFIGS
+    conf = dict(CONFIGS['C3'])
+    conf['num_parts'] = 8
+    data, fin, fout = tga.get_data('', 'products', seed=0, scale=256, num_parts=8)
+    data.adj_t = tga.gcn_norm(tga.set_diag(data.adj_t), add_self_loops=False)
+    from incagg_gnn_b200.metis import block_ptr
+    ptr = block_ptr(data.num_nodes, 8)
+    a = conf['architecture']
+    H, L = a['hidden_channels'], a['num_layers']
+    g = torch.Generator().manual_seed(0)
+    state = {'lins.0.weight': torch.randn(H, fin, generator=g) * 0.1, 'lins.0.bias': torch.zeros(H),
+             'lins.1.weight': torch.randn(fout, H, generator=g) * 0.1, 'lins.1.bias': torch.zeros(fout)}
+    for l in range(L):
+        state[f'convs.{l}.weight1'] = torch.randn(H, H, generator=g) * 0.1
+        state[f'convs.{l}.weight2'] = torch.randn(H, H, generator=g) * 0.1
+    for rank in (0, 1):
+        shard = Shard(ptr, rank, 2)
+        hist = [SimpleNamespace(emb=torch.randn(shard.num_local, H, generator=g), row_offset=shard.lo)
+                for _ in range(L)]
+        model = SimpleNamespace(histories=hist, histories_ag=hist, state_dict=lambda: state)
+        run = dict(data=data, ptr=ptr, conf=conf, model=model, in_channels=fin, out_channels=fout, shard=shard)
+        for mode in ('gas', 'incagg'):
+            v, edges, sec = bench.cpu_baseline(run, mode, 2, 2)
+            assert v > 0 and edges > 0
+    full = bench.full_table(hist[0], data.num_nodes)
+    assert full.shape == (data.num_nodes, H) and torch.equal(full[shard.lo:shard.hi], hist[0].emb)
+    assert float(full[:shard.lo].abs().sum()) == 0.

@@ -168,3 +168,50 @@ def test_incagg_equals_gas_right_after_refresh(kind):
                 # written) and APPNP-GAS does L+1 propagations: not comparable.
                 o_gas = model.forward(full)
                 torch.testing.assert_close(o_vr, o_gas[:ib.batch_size], rtol=1e-9, atol=1e-9)
+
+
+def test_csr_baseline_matches_the_definition():
+    """The timed CPU baseline runs sum / mean aggregation through ATen's CSR kernels (forward) and the
+    cached transposed CSR (backward); same values and gradients as the gather + index_add definition."""
+    import torch
+    from oracle import gas
+    g = torch.Generator().manual_seed(5)
+    rows, cols, F = 300, 500, 24
+    deg = torch.randint(0, 12, (rows,), generator=g)
+    rowptr = torch.zeros(rows + 1, dtype=torch.int64)
+    rowptr[1:] = deg.cumsum(0)
+    col = torch.randint(0, cols, (int(rowptr[-1]),), generator=g)
+    val = torch.rand(col.numel(), generator=g)
+    x = torch.randn(cols, F, generator=g, dtype=torch.float64)
+    w = torch.randn(rows, F, generator=g, dtype=torch.float64)
+    for reduce in ('sum', 'mean'):
+        for v in (val, None):
+            adj = gas.Adj(rowptr, col, v, rows, cols)
+            res = {}
+            for impl in ('gather', 'csr'):
+                gas.SPMM_IMPL = impl
+                xi = x.clone().requires_grad_(True)
+                out = gas.spmm(adj, xi, reduce)
+                (out * w).sum().backward()
+                res[impl] = (out.detach(), xi.grad)
+            gas.SPMM_IMPL = 'gather'
+            assert torch.allclose(res['gather'][0], res['csr'][0], rtol=1e-12, atol=1e-12)
+            assert torch.allclose(res['gather'][1], res['csr'][1], rtol=1e-12, atol=1e-12)
+
+
+def test_reference_arm_inputs_equal_the_product_inputs():
+    """oracle/synth.py (the generator of `bench.py --impl reference`, which must not import the product)
+    produces the product generator's graph, features, labels and masks bit for bit."""
+    import torch
+    import incagg_gnn_b200 as tga
+    from oracle import synth
+    for name, scale, parts in (('products', 64, 8), ('arxiv', 8, 10)):
+        a = synth.make_inputs(name, seed=3, scale=scale, num_parts=parts)
+        d, f, c = tga.get_data('', name, seed=3, scale=scale, num_parts=parts)
+        rp, col, _ = d.adj_t.csr()
+        assert torch.equal(rp, a.rowptr) and torch.equal(col, a.col)
+        assert torch.equal(d.x, a.x) and torch.equal(d.y, a.y) and torch.equal(d.train_mask, a.train_mask)
+        assert (f, c) == (a.num_features, a.num_classes)
+        from incagg_gnn_b200.metis import block_ptr
+        assert torch.equal(block_ptr(d.num_nodes, parts), a.ptr)
+    assert synth.SHAPES == tga.SHAPES
