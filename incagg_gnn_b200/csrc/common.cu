@@ -1,5 +1,6 @@
 // Library-level entry points and error plumbing.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -33,6 +34,11 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* v = getenv("INCAGG_PDL"); return v != nullptr && v[0] == '1'; }();
+  return on;
 }
 
 }  // namespace incagg

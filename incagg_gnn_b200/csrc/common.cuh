@@ -107,4 +107,40 @@ constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
 inline int64_t scan_num_tiles(int64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// Consecutive kernels of the library on one stream (or consecutive kernel nodes of a captured graph)
+// leave the GPU idle for a launch latency between them.  With INCAGG_PDL=1 every launch carries the
+// programmatic-stream-serialization attribute and every kernel starts with
+//     griddepcontrol.launch_dependents   (the next kernel's CTAs may be scheduled as SMs free up)
+//     griddepcontrol.wait                (block until the previous grid has completed and flushed)
+// so the next kernel's launch and prologue overlap this kernel's tail; all global memory accesses come
+// after the wait, which keeps the stream's semantics.  Without the attribute both instructions are
+// no-ops.  Kernels of other libraries in between (ATen) are ordinary launches and fully serialise.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_trigger();
+  pdl_wait();
+}
+bool pdl_enabled();   // common.cu: INCAGG_PDL=1
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  if (!pdl_enabled()) {
+    kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace incagg

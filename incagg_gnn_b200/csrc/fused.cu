@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(CS_THREADS)
 relu_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
                        int64_t rows, int cols, float* __restrict__ gm, int64_t ldo,
                        float* __restrict__ partial) {
+  pdl_prologue();
   extern __shared__ float sm[];  // [groups][cols]
   const int cvec = cols / 4;
   const int groups = CS_THREADS / cvec;
@@ -52,6 +53,7 @@ relu_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __
 
 __global__ void colsum_finish_kernel(const float* __restrict__ partial, int nblocks, int cols,
                                      float* __restrict__ out) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   float s = 0.f;
@@ -61,6 +63,7 @@ __global__ void colsum_finish_kernel(const float* __restrict__ partial, int nblo
 
 // ---- masked cross-entropy ---------------------------------------------------------------------------
 __global__ void mask_count_kernel(const uint8_t* __restrict__ mask, int64_t n, float* __restrict__ count) {
+  pdl_prologue();
   __shared__ int s_tot;
   if (threadIdx.x == 0) s_tot = 0;
   __syncthreads();
@@ -79,6 +82,7 @@ __global__ void __launch_bounds__(CE_THREADS)
 masked_ce_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ y,
                  const uint8_t* __restrict__ mask, int64_t rows, int C, const float* __restrict__ count,
                  float* __restrict__ dlogits, int64_t ldd, float* __restrict__ partial) {
+  pdl_prologue();
   __shared__ float s_loss[CE_THREADS / 32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.x * (CE_THREADS / 32) + w;
@@ -114,6 +118,7 @@ masked_ce_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __
 
 __global__ void ce_finish_kernel(const float* __restrict__ partial, int nblocks, const float* __restrict__ count,
                                  float* __restrict__ out /* [2]: loss sum, mean loss */) {
+  pdl_prologue();
   // one block, fixed order
   __shared__ double s[256];
   double acc = 0.0;
@@ -159,10 +164,10 @@ extern "C" int incagg_relu_bwd_colsum(const float* g, int64_t ldg, const float* 
   IA_CHECK_ARG(cvec <= CS_THREADS, "too many columns");
   const int groups = CS_THREADS / cvec;
   float* partial = static_cast<float*>(workspace);
-  relu_bwd_colsum_kernel<<<nblocks, CS_THREADS, sizeof(float) * (size_t)groups * cols, st>>>(
+  launch(relu_bwd_colsum_kernel, dim3(nblocks), dim3(CS_THREADS), (size_t)(sizeof(float) * (size_t)groups * cols), st, 
       g, ldg, y, ldy, rows, cols, gm, ldo, partial);
   IA_LAUNCH_CHECK();
-  colsum_finish_kernel<<<(cols + 127) / 128, 128, 0, st>>>(partial, nblocks, cols, colsum);
+  launch(colsum_finish_kernel, dim3((cols + 127) / 128), dim3(128), (size_t)(0), st, partial, nblocks, cols, colsum);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -187,13 +192,13 @@ extern "C" int incagg_masked_ce(const float* logits, int64_t ld, const int64_t* 
     return INCAGG_OK;
   }
   IA_CHECK_ARG(logits && y && mask && dlogits, "NULL argument");
-  mask_count_kernel<<<1, 1024, 0, st>>>(mask, rows, count);
+  launch(mask_count_kernel, dim3(1), dim3(1024), (size_t)(0), st, mask, rows, count);
   IA_LAUNCH_CHECK();
   const int nblocks = (int)((rows + CE_THREADS / 32 - 1) / (CE_THREADS / 32));
   float* partial = static_cast<float*>(workspace);
-  masked_ce_kernel<<<nblocks, CE_THREADS, 0, st>>>(logits, ld, y, mask, rows, C, count, dlogits, ldd, partial);
+  launch(masked_ce_kernel, dim3(nblocks), dim3(CE_THREADS), (size_t)(0), st, logits, ld, y, mask, rows, C, count, dlogits, ldd, partial);
   IA_LAUNCH_CHECK();
-  ce_finish_kernel<<<1, 256, 0, st>>>(partial, nblocks, count, out3);
+  launch(ce_finish_kernel, dim3(1), dim3(256), (size_t)(0), st, partial, nblocks, count, out3);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -210,6 +215,7 @@ namespace incagg {
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, int64_t n_decay, float lr, float b1, float b2,
                             float eps, float wd_first, float wd_rest, float* step, unsigned int* arrivals) {
+  pdl_prologue();
   const float t = step[0] + 1.f;
   const float bc1 = 1.f - powf(b1, t);
   const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
@@ -250,7 +256,7 @@ extern "C" int incagg_adam_step(float* params, const float* grads, float* exp_av
   const int threads = 256;
   int64_t want = (n + threads - 1) / threads;
   const int blocks = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
-  incagg::adam_kernel<<<blocks, threads, 0, as_stream(stream)>>>(
+  launch(incagg::adam_kernel, dim3(blocks), dim3(threads), (size_t)(0), as_stream(stream), 
       params, grads, exp_avg, exp_avg_sq, n, n_first_group, lr, beta1, beta2, eps, wd_first_group, wd_rest,
       step_dev, static_cast<unsigned int*>(arrivals_dev));
   IA_LAUNCH_CHECK();

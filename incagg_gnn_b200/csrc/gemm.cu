@@ -291,6 +291,7 @@ template <int BN> struct GemmCfg { static constexpr int STAGES = (BN == 64) ? 2 
 template <int BN, bool TA, bool TBK>
 __global__ void __launch_bounds__(G_THREADS, GemmCfg<BN>::MIN_CTAS)
 gemm_tf32x3_kernel(const GemmParams p) {
+  pdl_trigger();  // the wait comes after the on-chip set-up (barriers, TMEM), before the first global access
   constexpr int G_STAGES = GemmCfg<BN>::STAGES;
   extern __shared__ __align__(1024) char smem_raw[];
   // 1024-byte alignment of every tile (the swizzle is a function of the absolute smem address)
@@ -350,6 +351,7 @@ gemm_tf32x3_kernel(const GemmParams p) {
   // the global loads of k-block kb+1 are in flight while kb is split, stored and multiplied
   TileRegs<G_BM> ra;
   TileRegs<BN> rb;
+  pdl_wait();
   if (num_kb > 0) load_kb(kb_lo, ra, rb);
   tc_fence_before();
   __syncthreads();
@@ -490,6 +492,7 @@ gemm_tf32x3_kernel(const GemmParams p) {
 template <bool TA, bool TBK>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_nc_kernel(const GemmParams p) {
+  pdl_trigger();  // the wait comes after the on-chip set-up (barriers, TMEM), before the first global access
   constexpr int STAGES = 2, BN = 256, HALF = 128;
   extern __shared__ __align__(1024) char smem_raw[];
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -525,6 +528,7 @@ gemm_nc_kernel(const GemmParams p) {
     load_tile<HALF, TBK>(p.B, p.ldb, 0, p.N, kbg * G_BK, p.K, vecB, rb);
     load_tile<HALF, TBK>(p.B2, p.ldb2, 0, p.N, kbg * G_BK, p.K, vecB2, rb2);
   };
+  pdl_wait();
   if (num_kb > 0) load_kb(kb_lo);
   tc_fence_before();
   __syncthreads();
@@ -631,6 +635,7 @@ gemm_nc_kernel(const GemmParams p) {
 constexpr int RED_WARPS = 8;
 __global__ void __launch_bounds__(RED_WARPS * 32)
 gemm_splitk_reduce_kernel(const GemmParams p, int splits, int n_chunks) {
+  pdl_prologue();
   __shared__ float part[RED_WARPS][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t sets = (p.dual == DUAL_M || p.dual == DUAL_NC) ? 2 : 1;
@@ -690,7 +695,7 @@ static int launch_gemm_t(const GemmParams& p, int splits, cudaStream_t st) {
   if (p.dual == DUAL_M) gx *= 2;
   if (p.dual == DUAL_N) gy *= 2;
   dim3 grid(gx, gy, (unsigned)splits);
-  gemm_tf32x3_kernel<BN, TA, TBK><<<grid, G_THREADS, SMEM, st>>>(p);
+  launch(gemm_tf32x3_kernel<BN, TA, TBK>, dim3(grid), dim3(G_THREADS), (size_t)(SMEM), st, p);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -704,7 +709,7 @@ static int launch_nc_t(const GemmParams& p, int splits, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid((unsigned)((p.M + G_BM - 1) / G_BM), 1, (unsigned)splits);
-  gemm_nc_kernel<TA, TBK><<<grid, G_THREADS, SMEM, st>>>(p);
+  launch(gemm_nc_kernel<TA, TBK>, dim3(grid), dim3(G_THREADS), (size_t)(SMEM), st, p);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -764,7 +769,7 @@ static int run_gemm(GemmParams& p, void* workspace, size_t workspace_bytes, cuda
     const int n_chunks = (int)((p.N + 31) / 32);
     const int64_t items = p.M * n_chunks * ((p.dual == DUAL_M || nc) ? 2 : 1);
     const int blocks = (int)(items < (int64_t)sm_count() * 8 ? items : (int64_t)sm_count() * 8);
-    gemm_splitk_reduce_kernel<<<blocks, RED_WARPS * 32, 0, st>>>(p, splits, n_chunks);
+    launch(gemm_splitk_reduce_kernel, dim3(blocks), dim3(RED_WARPS * 32), (size_t)(0), st, p, splits, n_chunks);
     IA_LAUNCH_CHECK();
   }
   return INCAGG_OK;

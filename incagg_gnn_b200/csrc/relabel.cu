@@ -55,6 +55,7 @@ static RelabelWs carve_ws(void* ws, int64_t n) {
 }
 
 __global__ void ws_init_kernel(int32_t* map, int32_t* first_pos, int64_t n) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     map[i] = -1;
@@ -65,6 +66,7 @@ __global__ void ws_init_kernel(int32_t* map, int32_t* first_pos, int64_t n) {
 // map[idx[i]] = i (largest i wins) and deg[i] = degree of idx[i].
 __global__ void mark_kernel(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ idx,
                             int64_t B, int32_t* map, int64_t* __restrict__ deg) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   const int64_t v = idx[i];
@@ -74,6 +76,7 @@ __global__ void mark_kernel(const int64_t* __restrict__ rowptr, const int64_t* _
 
 __global__ void degree_sum_kernel(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ idx,
                                   int64_t B, unsigned long long* out) {
+  pdl_prologue();
   int64_t s = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -88,6 +91,7 @@ __global__ void degree_sum_kernel(const int64_t* __restrict__ rowptr, const int6
 template <typename OT>
 __global__ void write_rowptr_kernel(const int64_t* __restrict__ excl, const int64_t* __restrict__ total,
                                     int64_t B, OT* __restrict__ out_rowptr) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) out_rowptr[i] = (OT)excl[i];
   if (i == B) out_rowptr[B] = (OT)(*total);
@@ -101,6 +105,7 @@ map_edges_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__ col,
                  const float* __restrict__ val, const int64_t* __restrict__ idx, int64_t B,
                  const int64_t* __restrict__ row_start, const int32_t* __restrict__ map,
                  int32_t* first_pos, OT* __restrict__ out_col, float* __restrict__ out_val) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * RL_WARPS + (threadIdx.x >> 5);
   if (i >= B) return;
@@ -128,6 +133,7 @@ count_first_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__ co
                    const int64_t* __restrict__ idx, int64_t B, const int64_t* __restrict__ row_start,
                    const int32_t* __restrict__ first_pos, const OT* __restrict__ out_col,
                    int64_t* __restrict__ row_first) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * RL_WARPS + (threadIdx.x >> 5);
   if (i >= B) return;
@@ -150,6 +156,7 @@ assign_halo_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__ co
                    const int64_t* __restrict__ idx, int64_t B, const int64_t* __restrict__ row_start,
                    const int64_t* __restrict__ row_first_excl, const int32_t* __restrict__ first_pos,
                    const OT* __restrict__ out_col, int32_t* map, int64_t* __restrict__ n_id_out) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * RL_WARPS + (threadIdx.x >> 5);
   if (i >= B) return;
@@ -183,6 +190,7 @@ fill_halo_cols_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__
                       const int64_t* __restrict__ idx, int64_t B,
                       const int64_t* __restrict__ row_start, const int32_t* __restrict__ map,
                       OT* __restrict__ out_col) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * RL_WARPS + (threadIdx.x >> 5);
   if (i >= B) return;
@@ -200,6 +208,7 @@ fill_halo_cols_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__
 __global__ void finish_kernel(const int64_t* __restrict__ idx, int64_t B,
                               const int64_t* __restrict__ H_dev, int64_t* __restrict__ n_id_out,
                               int32_t* map, int32_t* first_pos) {
+  pdl_prologue();
   const int64_t H = H_dev ? *H_dev : 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B + H;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -221,6 +230,7 @@ __global__ void __launch_bounds__(RL_THREADS)
 count_kept_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__ col,
                   const int64_t* __restrict__ idx, int64_t B, const int32_t* __restrict__ map,
                   int64_t* __restrict__ row_kept) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * RL_WARPS + (threadIdx.x >> 5);
   if (i >= B) return;
@@ -240,6 +250,7 @@ compact_kept_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__ c
                     const float* __restrict__ val, const int64_t* __restrict__ idx, int64_t B,
                     const int32_t* __restrict__ map, const int64_t* __restrict__ row_start,
                     OT* __restrict__ out_col, float* __restrict__ out_val) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * RL_WARPS + (threadIdx.x >> 5);
   if (i >= B) return;
@@ -262,6 +273,7 @@ compact_kept_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__ c
 
 __global__ void store_counts_kernel(const int64_t* a, const int64_t* b, int64_t b_const,
                                     int64_t* counts_out) {
+  pdl_prologue();
   counts_out[0] = a ? *a : 0;
   counts_out[1] = b ? *b : b_const;
 }
@@ -297,32 +309,32 @@ static int relabel_one_hop_impl(const int64_t* rowptr, const CT* col, const floa
     IA_CUDA(cudaMemsetAsync(counts_out, 0, 2 * sizeof(int64_t), st));
     return INCAGG_OK;
   }
-  mark_kernel<<<blocks_for(B, 256), 256, 0, st>>>(rowptr, idx, B, w.map, w.rowtmp);
+  launch(mark_kernel, dim3(blocks_for(B, 256)), dim3(256), (size_t)(0), st, rowptr, idx, B, w.map, w.rowtmp);
   IA_LAUNCH_CHECK();
   int64_t* row_start = w.rowtmp;  // becomes the exclusive prefix of the degrees
   int rc = exclusive_scan_i64(w.rowtmp, row_start, B, w.scan, w.total, st);
   if (rc != INCAGG_OK) return rc;
-  write_rowptr_kernel<OT><<<blocks_for(B + 1, 256), 256, 0, st>>>(row_start, w.total, B, out_rowptr);
+  launch(write_rowptr_kernel<OT>, dim3(blocks_for(B + 1, 256)), dim3(256), (size_t)(0), st, row_start, w.total, B, out_rowptr);
   IA_LAUNCH_CHECK();
   const unsigned rb = blocks_for(B, RL_WARPS);
   int64_t* row_first = w.rowtmp2;
-  map_edges_kernel<CT, OT><<<rb, RL_THREADS, 0, st>>>(rowptr, col, val, idx, B, row_start, w.map,
+  launch(map_edges_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, val, idx, B, row_start, w.map,
                                                       w.first_pos, out_col, out_val);
   IA_LAUNCH_CHECK();
-  count_first_kernel<CT, OT><<<rb, RL_THREADS, 0, st>>>(rowptr, col, idx, B, row_start,
+  launch(count_first_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, idx, B, row_start,
                                                         w.first_pos, out_col, row_first);
   IA_LAUNCH_CHECK();
   rc = exclusive_scan_i64(row_first, row_first, B, w.scan, w.total + 1, st);
   if (rc != INCAGG_OK) return rc;
-  assign_halo_kernel<CT, OT><<<rb, RL_THREADS, 0, st>>>(rowptr, col, idx, B, row_start, row_first,
+  launch(assign_halo_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, idx, B, row_start, row_first,
                                                         w.first_pos, out_col, w.map, n_id_out);
   IA_LAUNCH_CHECK();
-  fill_halo_cols_kernel<CT, OT><<<rb, RL_THREADS, 0, st>>>(rowptr, col, idx, B, row_start, w.map,
+  launch(fill_halo_cols_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, idx, B, row_start, w.map,
                                                            out_col);
   IA_LAUNCH_CHECK();
-  store_counts_kernel<<<1, 1, 0, st>>>(w.total + 1, w.total, 0, counts_out);
+  launch(store_counts_kernel, dim3(1), dim3(1), (size_t)(0), st, w.total + 1, w.total, 0, counts_out);
   IA_LAUNCH_CHECK();
-  finish_kernel<<<sm_count() * 4, 256, 0, st>>>(idx, B, w.total + 1, n_id_out, w.map, w.first_pos);
+  launch(finish_kernel, dim3(sm_count() * 4), dim3(256), (size_t)(0), st, idx, B, w.total + 1, n_id_out, w.map, w.first_pos);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -338,21 +350,21 @@ static int relabel_within_impl(const int64_t* rowptr, const CT* col, const float
     IA_CUDA(cudaMemsetAsync(counts_out, 0, 2 * sizeof(int64_t), st));
     return INCAGG_OK;
   }
-  mark_kernel<<<blocks_for(B, 256), 256, 0, st>>>(rowptr, idx, B, w.map, nullptr);
+  launch(mark_kernel, dim3(blocks_for(B, 256)), dim3(256), (size_t)(0), st, rowptr, idx, B, w.map, nullptr);
   IA_LAUNCH_CHECK();
   const unsigned rb = blocks_for(B, RL_WARPS);
-  count_kept_kernel<CT><<<rb, RL_THREADS, 0, st>>>(rowptr, col, idx, B, w.map, w.rowtmp);
+  launch(count_kept_kernel<CT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, idx, B, w.map, w.rowtmp);
   IA_LAUNCH_CHECK();
   int rc = exclusive_scan_i64(w.rowtmp, w.rowtmp, B, w.scan, w.total, st);
   if (rc != INCAGG_OK) return rc;
-  write_rowptr_kernel<OT><<<blocks_for(B + 1, 256), 256, 0, st>>>(w.rowtmp, w.total, B, out_rowptr);
+  launch(write_rowptr_kernel<OT>, dim3(blocks_for(B + 1, 256)), dim3(256), (size_t)(0), st, w.rowtmp, w.total, B, out_rowptr);
   IA_LAUNCH_CHECK();
-  compact_kept_kernel<CT, OT><<<rb, RL_THREADS, 0, st>>>(rowptr, col, val, idx, B, w.map, w.rowtmp,
+  launch(compact_kept_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, val, idx, B, w.map, w.rowtmp,
                                                          out_col, out_val);
   IA_LAUNCH_CHECK();
-  store_counts_kernel<<<1, 1, 0, st>>>(nullptr, w.total, 0, counts_out);
+  launch(store_counts_kernel, dim3(1), dim3(1), (size_t)(0), st, nullptr, w.total, 0, counts_out);
   IA_LAUNCH_CHECK();
-  finish_kernel<<<sm_count() * 4, 256, 0, st>>>(idx, B, nullptr, nullptr, w.map, w.first_pos);
+  launch(finish_kernel, dim3(sm_count() * 4), dim3(256), (size_t)(0), st, idx, B, nullptr, nullptr, w.map, w.first_pos);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -374,7 +386,7 @@ extern "C" int incagg_relabel_workspace_init(void* workspace, int64_t num_nodes,
   IA_CHECK_ARG(workspace != nullptr && num_nodes >= 0, "bad workspace arguments");
   if (num_nodes == 0) return INCAGG_OK;
   RelabelWs w = carve_ws(workspace, num_nodes);
-  ws_init_kernel<<<sm_count() * 8, 256, 0, as_stream(stream)>>>(w.map, w.first_pos, num_nodes);
+  launch(ws_init_kernel, dim3(sm_count() * 8), dim3(256), (size_t)(0), as_stream(stream), w.map, w.first_pos, num_nodes);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -390,7 +402,7 @@ extern "C" int incagg_relabel_degree_sum(const int64_t* rowptr, const int64_t* i
   IA_CHECK_ARG(rowptr && idx, "NULL argument");
   const unsigned blocks = blocks_for(B, 256) < (unsigned)(sm_count() * 8) ? blocks_for(B, 256)
                                                                             : (unsigned)(sm_count() * 8);
-  degree_sum_kernel<<<blocks, 256, 0, st>>>(rowptr, idx, B,
+  launch(degree_sum_kernel, dim3(blocks), dim3(256), (size_t)(0), st, rowptr, idx, B,
                                             reinterpret_cast<unsigned long long*>(degsum_out));
   IA_LAUNCH_CHECK();
   return INCAGG_OK;

@@ -34,6 +34,7 @@ template <int VB, int MODE>
 __global__ void __launch_bounds__(ROWS_THREADS)
 index_rows_kernel(const char* __restrict__ src, int64_t src_ld, const int64_t* __restrict__ idx,
                   int64_t n, char* __restrict__ dst, int64_t dst_ld, int nvec, int64_t limit_rows) {
+  pdl_prologue();
   using V = typename Bytes<VB>::type;
   const int64_t total = n * nvec;
   const int64_t stride = (int64_t)gridDim.x * ROWS_THREADS;
@@ -78,6 +79,7 @@ template <int VB>
 __global__ void __launch_bounds__(ROWS_THREADS)
 sharded_gather_kernel(const ShardTable tab, int64_t src_ld, const int64_t* __restrict__ idx, int64_t n,
                       char* __restrict__ dst, int64_t dst_ld, int nvec) {
+  pdl_prologue();
   using V = typename Bytes<VB>::type;
   const int64_t total = n * nvec;
   const int64_t stride = (int64_t)gridDim.x * ROWS_THREADS;
@@ -119,6 +121,7 @@ template <int VB>
 __global__ void __launch_bounds__(ROWS_THREADS)
 slice_rows_kernel(const char* __restrict__ src, int64_t src_ld, char* __restrict__ dst,
                   int64_t dst_ld, int nvec, int direction, const SliceTable tab) {
+  pdl_prologue();
   using V = typename Bytes<VB>::type;
   const int64_t total = tab.prefix[tab.k] * nvec;
   const int64_t stride = (int64_t)gridDim.x * ROWS_THREADS;
@@ -174,6 +177,7 @@ __device__ __forceinline__ uint32_t rows_smem_u32(const void* p) {
 
 __global__ void __launch_bounds__(32)
 slice_bulk_kernel(const char* __restrict__ src, char* __restrict__ dst, const BulkTable tab) {
+  pdl_prologue();
   extern __shared__ __align__(128) char bulk_smem[];
   __shared__ uint64_t bar[BULK_STAGES];
   if (threadIdx.x != 0) return;  // one thread drives the TMA engine
@@ -282,15 +286,15 @@ static int index_rows(const void* src, int64_t src_ld, const int64_t* idx, int64
   const char* s = static_cast<const char*>(src);
   char* d = static_cast<char*>(dst);
   if (vb == 16)
-    index_rows_kernel<16, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+    launch(index_rows_kernel<16, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
   else if (vb == 8)
-    index_rows_kernel<8, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+    launch(index_rows_kernel<8, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
   else if (vb == 4)
-    index_rows_kernel<4, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+    launch(index_rows_kernel<4, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
   else if (vb == 2)
-    index_rows_kernel<2, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+    launch(index_rows_kernel<2, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
   else
-    index_rows_kernel<1, MODE><<<grid, ROWS_THREADS, 0, st>>>(s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+    launch(index_rows_kernel<1, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -334,7 +338,7 @@ extern "C" int incagg_gather_rows_sharded(const void* const* shard_ptrs, const i
   const int grid = grid_for(n * nvec64);
   cudaStream_t st = as_stream(stream);
   char* d = static_cast<char*>(dst);
-#define IA_SG(VB_) sharded_gather_kernel<VB_><<<grid, ROWS_THREADS, 0, st>>>(tab, src_ld_bytes, idx, n, d, dst_ld_bytes, nvec)
+#define IA_SG(VB_) launch(sharded_gather_kernel<VB_>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, tab, src_ld_bytes, idx, n, d, dst_ld_bytes, nvec)
   if (vb == 16) IA_SG(16); else if (vb == 8) IA_SG(8); else if (vb == 4) IA_SG(4); else if (vb == 2) IA_SG(2); else IA_SG(1);
 #undef IA_SG
   IA_LAUNCH_CHECK();
@@ -422,7 +426,7 @@ extern "C" int incagg_copy_slices(const void* src, int64_t src_ld_bytes, int64_t
       if (n_chunks == 0) continue;
       int64_t grid = (int64_t)sm_count() * 3;  // 64 KB of shared memory per CTA -> 3 CTAs per SM
       if (grid > n_chunks) grid = n_chunks;
-      slice_bulk_kernel<<<(unsigned)grid, 32, BULK_STAGES * BULK_CHUNK, st>>>(s, d, tab);
+      launch(slice_bulk_kernel, dim3((unsigned)grid), dim3(32), (size_t)(BULK_STAGES * BULK_CHUNK), st, s, d, tab);
       IA_LAUNCH_CHECK();
     }
     return INCAGG_OK;
@@ -447,15 +451,15 @@ extern "C" int incagg_copy_slices(const void* src, int64_t src_ld_bytes, int64_t
       char* dp = direction == 0 ? d + p * dst_ld_bytes : d;
       const int grid = grid_for(rows_here * nvec);
       if (vb == 16)
-        slice_rows_kernel<16><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
+        launch(slice_rows_kernel<16>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
       else if (vb == 8)
-        slice_rows_kernel<8><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
+        launch(slice_rows_kernel<8>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
       else if (vb == 4)
-        slice_rows_kernel<4><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
+        launch(slice_rows_kernel<4>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
       else if (vb == 2)
-        slice_rows_kernel<2><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
+        launch(slice_rows_kernel<2>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
       else
-        slice_rows_kernel<1><<<grid, ROWS_THREADS, 0, st>>>(sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
+        launch(slice_rows_kernel<1>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, sp, src_ld_bytes, dp, dst_ld_bytes, nvec, direction, tab);
       IA_LAUNCH_CHECK();
     }
     p += rows_here;

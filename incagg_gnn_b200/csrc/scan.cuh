@@ -8,6 +8,7 @@ namespace incagg {
 
 static __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_tile_sums_kernel(const int64_t* __restrict__ in, int64_t n, int64_t* __restrict__ tile_sums) {
+  pdl_prologue();
   const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
   int64_t s = 0;
 #pragma unroll
@@ -23,6 +24,7 @@ scan_tile_sums_kernel(const int64_t* __restrict__ in, int64_t n, int64_t* __rest
 // One block: exclusive scan of the tile sums in place; grand total to *total_out.
 static __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_tiles_kernel(int64_t* __restrict__ tile_sums, int64_t num_tiles, int64_t* __restrict__ total_out) {
+  pdl_prologue();
   int64_t carry = 0;
   for (int64_t b = 0; b < num_tiles; b += SCAN_BLOCK) {
     const int64_t i = b + threadIdx.x;
@@ -40,6 +42,7 @@ scan_tiles_kernel(int64_t* __restrict__ tile_sums, int64_t num_tiles, int64_t* _
 static __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_apply_kernel(const int64_t* in, int64_t n, const int64_t* __restrict__ tile_offsets,
                   int64_t* out) {
+  pdl_prologue();
   const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int64_t v[SCAN_ITEMS];
   int64_t s = 0;
@@ -64,6 +67,7 @@ scan_apply_kernel(const int64_t* in, int64_t n, const int64_t* __restrict__ tile
 static __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_apply_self_kernel(const int64_t* in, int64_t n, const int64_t* __restrict__ tile_sums, int64_t num_tiles,
                        int64_t* out, int64_t* __restrict__ total_out) {
+  pdl_prologue();
   __shared__ int64_t s_off;
   // offset of this tile = sum of tile_sums[0 .. blockIdx.x); the last block also publishes the total
   int64_t part = 0, all = 0;
@@ -108,18 +112,18 @@ static inline int exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n,
   }
   if (scan_num_tiles(n) <= SCAN_BLOCK) {
     const int64_t tiles = scan_num_tiles(n);
-    scan_tile_sums_kernel<<<(unsigned)tiles, SCAN_BLOCK, 0, st>>>(in, n, scratch);
+    launch(scan_tile_sums_kernel, dim3((unsigned)tiles), dim3(SCAN_BLOCK), (size_t)(0), st, in, n, scratch);
     IA_LAUNCH_CHECK();
-    scan_apply_self_kernel<<<(unsigned)tiles, SCAN_BLOCK, 0, st>>>(in, n, scratch, tiles, out, total_out);
+    launch(scan_apply_self_kernel, dim3((unsigned)tiles), dim3(SCAN_BLOCK), (size_t)(0), st, in, n, scratch, tiles, out, total_out);
     IA_LAUNCH_CHECK();
     return INCAGG_OK;
   }
   const int64_t tiles = scan_num_tiles(n);
-  scan_tile_sums_kernel<<<(unsigned)tiles, SCAN_BLOCK, 0, st>>>(in, n, scratch);
+  launch(scan_tile_sums_kernel, dim3((unsigned)tiles), dim3(SCAN_BLOCK), (size_t)(0), st, in, n, scratch);
   IA_LAUNCH_CHECK();
-  scan_tiles_kernel<<<1, SCAN_BLOCK, 0, st>>>(scratch, tiles, total_out);
+  launch(scan_tiles_kernel, dim3(1), dim3(SCAN_BLOCK), (size_t)(0), st, scratch, tiles, total_out);
   IA_LAUNCH_CHECK();
-  scan_apply_kernel<<<(unsigned)tiles, SCAN_BLOCK, 0, st>>>(in, n, scratch, out);
+  launch(scan_apply_kernel, dim3((unsigned)tiles), dim3(SCAN_BLOCK), (size_t)(0), st, in, n, scratch, out);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }

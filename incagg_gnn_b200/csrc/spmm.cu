@@ -311,6 +311,7 @@ __device__ __forceinline__ void tile_info(const SpmmParams& p, int y, int& op, i
 template <int REDUCE, int VEC, int G, int NCH, bool DELTA, bool ARG>
 __global__ void __launch_bounds__(SPMM_THREADS, (NCH == 1 && !ARG) ? SPMM_MIN_CTAS : 1)
 spmm_kernel(const SpmmParams p) {
+  pdl_prologue();
   constexpr int COVER = G * VEC * NCH;
   const int lane = threadIdx.x & 31;
   const int long_row = p.plan->long_row;
@@ -448,6 +449,7 @@ spmm_kernel(const SpmmParams p) {
 // Plan construction: one thread per row appends the row's work items.
 __global__ void spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t rows, SpmmPlan* plan,
                                  int4* __restrict__ items, int long_row, int chunk, int capacity) {
+  pdl_prologue();
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (chunk <= 0) {
     // adaptive chunk: small enough that one CTA trip is a few microseconds on batch-sized
@@ -478,6 +480,7 @@ __global__ void minmax_bwd_kernel(const int32_t* __restrict__ col, const float* 
                                   const int32_t* __restrict__ arg, int64_t lda,
                                   const float* __restrict__ grad_out, int64_t ldg,
                                   float* __restrict__ grad_x, int64_t ldx, int64_t rows, int F) {
+  pdl_prologue();
   const int64_t total = rows * F;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -520,7 +523,7 @@ static int build_plan(const int32_t* rowptr, int64_t rows, void* plan, int64_t c
   if (rows == 0) return INCAGG_OK;
   SpmmPlan* hdr = static_cast<SpmmPlan*>(plan);
   int4* items = reinterpret_cast<int4*>(hdr + 1);
-  spmm_plan_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(rowptr, rows, hdr, items,
+  launch(spmm_plan_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), (size_t)(0), st, rowptr, rows, hdr, items,
                                                                   long_row_edges(), chunk_edges(),
                                                                   (int)capacity);
   IA_LAUNCH_CHECK();
@@ -589,7 +592,7 @@ static int launch_cfg(SpmmParams& p, int n_tiles, int64_t items_bound, cudaStrea
   p.long_grid = (int)lg;
   IA_CHECK_ARG(blocks + lg <= 0x7fffffff, "too many rows for one launch");
   dim3 grid((unsigned)(blocks + lg), (unsigned)n_tiles);
-  spmm_kernel<REDUCE, VEC, G, NCH, DELTA, ARG><<<grid, SPMM_THREADS, 0, st>>>(p);
+  launch(spmm_kernel<REDUCE, VEC, G, NCH, DELTA, ARG>, dim3(grid), dim3(SPMM_THREADS), (size_t)(0), st, p);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -750,7 +753,7 @@ extern "C" int incagg_spmm_minmax_bwd(const int32_t* col, const float* val, cons
   const int threads = 256;
   const int64_t want = (total + threads - 1) / threads;
   const int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
-  minmax_bwd_kernel<<<blocks, threads, 0, as_stream(stream)>>>(col, val, arg, lda, grad_out, ldg,
+  launch(minmax_bwd_kernel, dim3(blocks), dim3(threads), (size_t)(0), as_stream(stream), col, val, arg, lda, grad_out, ldg,
                                                                grad_x, ldx, rows, F);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;

@@ -13,6 +13,7 @@ constexpr int TR_THREADS = 256;
 
 __global__ void col_hist_kernel(const int32_t* __restrict__ col, int64_t nnz, int64_t cols,
                                 unsigned long long* __restrict__ hist) {
+  pdl_prologue();
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int32_t c = col[e];
@@ -23,6 +24,7 @@ __global__ void col_hist_kernel(const int32_t* __restrict__ col, int64_t nnz, in
 __global__ void write_trowptr_kernel(const int64_t* __restrict__ excl, const int64_t* __restrict__ total,
                                      int64_t cols, int32_t* __restrict__ t_rowptr,
                                      int32_t* __restrict__ cursor) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < cols) {
     t_rowptr[i] = (int32_t)excl[i];
@@ -35,6 +37,7 @@ __global__ void write_trowptr_kernel(const int64_t* __restrict__ excl, const int
 __global__ void __launch_bounds__(TR_THREADS)
 fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t rows,
             int64_t cols, int32_t* cursor, int32_t* __restrict__ t_perm) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (TR_THREADS / 32) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -73,6 +76,7 @@ constexpr int MED_SORT = 1024;  // segments of 33 .. 1024 entries: small CTAs, 4
 __global__ void __launch_bounds__(TR_THREADS)
 sort_segments_kernel(const int32_t* __restrict__ t_rowptr, int64_t cols, int32_t* t_perm,
                      int32_t* __restrict__ long_rows, int32_t* long_count, int long_capacity) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t c = (int64_t)blockIdx.x * (TR_THREADS / 32) + (threadIdx.x >> 5);
   if (c >= cols) return;
@@ -125,6 +129,7 @@ constexpr int MED_THREADS = 128;
 __global__ void __launch_bounds__(MED_THREADS)
 sort_medium_segments_kernel(const int32_t* __restrict__ t_rowptr, int32_t* t_perm,
                             const int32_t* __restrict__ long_rows, const int32_t* __restrict__ long_count) {
+  pdl_prologue();
   __shared__ int32_t sm[MED_SORT];
   const int n_med = long_count[0];
   for (int li = blockIdx.x; li < n_med; li += gridDim.x) {
@@ -146,6 +151,7 @@ __global__ void __launch_bounds__(TR_THREADS)
 sort_long_segments_kernel(const int32_t* __restrict__ t_rowptr, int32_t* t_perm,
                           const int32_t* __restrict__ long_rows, const int32_t* __restrict__ long_count,
                           int long_capacity) {
+  pdl_prologue();
   extern __shared__ int32_t sm[];
   const int n_long = long_count[1];
   for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
@@ -174,6 +180,7 @@ __global__ void gather_transposed_kernel(const int32_t* __restrict__ rowptr, int
                                          const float* __restrict__ val,
                                          const int32_t* __restrict__ t_perm, int64_t nnz,
                                          int32_t* __restrict__ t_col, float* __restrict__ t_val) {
+  pdl_prologue();
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nnz;
        q += (int64_t)gridDim.x * blockDim.x) {
     const int32_t ed = t_perm[q];
@@ -249,24 +256,24 @@ extern "C" int incagg_csr_transpose(const int32_t* rowptr, const int32_t* col, c
     IA_CHECK_ARG(rowptr && col && t_col, "NULL argument");
     const int64_t want = (nnz + 255) / 256;
     const int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
-    col_hist_kernel<<<blocks, 256, 0, st>>>(col, nnz, cols,
+    launch(col_hist_kernel, dim3(blocks), dim3(256), (size_t)(0), st, col, nnz, cols,
                                             reinterpret_cast<unsigned long long*>(w.hist));
     IA_LAUNCH_CHECK();
   }
   int rc = exclusive_scan_i64(w.hist, w.hist, cols, w.scan, w.total, st);
   if (rc != INCAGG_OK) return rc;
-  write_trowptr_kernel<<<(unsigned)((cols + 1 + 255) / 256), 256, 0, st>>>(w.hist, w.total, cols,
+  launch(write_trowptr_kernel, dim3((unsigned)((cols + 1 + 255) / 256)), dim3(256), (size_t)(0), st, w.hist, w.total, cols,
                                                                            t_rowptr, w.cursor);
   IA_LAUNCH_CHECK();
   if (nnz == 0) return INCAGG_OK;
   int32_t* perm = t_perm ? t_perm : w.perm;
   const int wpb = TR_THREADS / 32;
-  fill_kernel<<<(unsigned)((rows + wpb - 1) / wpb), TR_THREADS, 0, st>>>(rowptr, col, rows, cols,
+  launch(fill_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(TR_THREADS), (size_t)(0), st, rowptr, col, rows, cols,
                                                                         w.cursor, perm);
   IA_LAUNCH_CHECK();
   IA_CUDA(cudaMemsetAsync(w.long_cnt, 0, 2 * sizeof(int32_t), st));
   if (cols > 0) {
-    sort_segments_kernel<<<(unsigned)((cols + wpb - 1) / wpb), TR_THREADS, 0, st>>>(
+    launch(sort_segments_kernel, dim3((unsigned)((cols + wpb - 1) / wpb)), dim3(TR_THREADS), (size_t)(0), st, 
         t_rowptr, cols, perm, w.long_rows, w.long_cnt, (int)cols);
     IA_LAUNCH_CHECK();
     static thread_local bool smem_set = false;
@@ -276,16 +283,16 @@ extern "C" int incagg_csr_transpose(const int32_t* rowptr, const int32_t* col, c
                                    (int)(BIG_SORT * sizeof(int32_t))));
       smem_set = true;
     }
-    sort_medium_segments_kernel<<<sm_count() * 12, MED_THREADS, 0, st>>>(t_rowptr, perm, w.long_rows, w.long_cnt);
+    launch(sort_medium_segments_kernel, dim3(sm_count() * 12), dim3(MED_THREADS), (size_t)(0), st, t_rowptr, perm, w.long_rows, w.long_cnt);
     IA_LAUNCH_CHECK();
-    sort_long_segments_kernel<<<sm_count(), TR_THREADS, BIG_SORT * sizeof(int32_t), st>>>(
+    launch(sort_long_segments_kernel, dim3(sm_count()), dim3(TR_THREADS), (size_t)(BIG_SORT * sizeof(int32_t)), st, 
         t_rowptr, perm, w.long_rows, w.long_cnt, (int)cols);
     IA_LAUNCH_CHECK();
   }
   {
     const int64_t want = (nnz + 255) / 256;
     const int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
-    gather_transposed_kernel<<<blocks, 256, 0, st>>>(rowptr, rows, val, perm, nnz, t_col, t_val);
+    launch(gather_transposed_kernel, dim3(blocks), dim3(256), (size_t)(0), st, rowptr, rows, val, perm, nnz, t_col, t_val);
     IA_LAUNCH_CHECK();
   }
   return INCAGG_OK;
