@@ -88,14 +88,21 @@ class GCN2(ScalableGNN):
                     # the layer GEMM writes rows [0, B) of the buffer whose tail the early pull fills
                     buf, pulled = ahead[i]
                     x = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=True, out_full=buf)
-                    hist.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
-                    torch.cuda.current_stream().wait_event(pulled)
+                    # the push only reads the rows the GEMM just wrote and nothing in this step reads
+                    # the table rows it writes: it rides on the pull stream, joined after the loop
+                    main, side = torch.cuda.current_stream(), self._pull_stream
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        hist.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
+                    main.wait_event(pulled)
                 else:
                     h = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=fuse)
                     x = h if fuse else self._post(i, h, x)
                     x, t = self.push_and_pull(hist, x, batch_size, n_id, offset, count)
                     t_all += t
                 x = F.dropout(x, p=self.dropout, training=self.training)
+            if ahead is not None:
+                torch.cuda.current_stream().wait_stream(self._pull_stream)   # pushes done before the step ends
             h = self.convs[-1](x, x0b, adj_t,
                                grad_rows=batch_size if self.num_layers > 1 else None, relu=fuse)
         else:  # no neighbour information (gcn2.py:151-181)
