@@ -37,7 +37,7 @@ int sm_count() {
 
 }  // namespace incagg
 
-extern "C" int incagg_version(void) { return 101; }
+extern "C" int incagg_version(void) { return 102; }
 
 extern "C" int64_t incagg_launch_count(void) { return (int64_t)incagg::launches(); }
 

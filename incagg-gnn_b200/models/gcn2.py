@@ -87,7 +87,10 @@ class GCN2(ScalableGNN):
                 if ahead is not None:
                     # the layer GEMM writes rows [0, B) of the buffer whose tail the early pull fills
                     buf, pulled = ahead[i]
-                    x = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=True, out_full=buf)
+                    # the ReLU of layer i rides in its GEMM epilogue; its backward mask rides in the
+                    # epilogue of the transposed SpMM of layer i + 1 (x passes only through dropout in between)
+                    x = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=True, out_full=buf,
+                             relu_input=i > 0, defer_relu_bwd=True)
                     hist.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
                     torch.cuda.current_stream().wait_event(pulled)
                 else:
@@ -97,7 +100,8 @@ class GCN2(ScalableGNN):
                     t_all += t
                 x = F.dropout(x, p=self.dropout, training=self.training)
             h = self.convs[-1](x, x0b, adj_t,
-                               grad_rows=batch_size if self.num_layers > 1 else None, relu=fuse)
+                               grad_rows=batch_size if self.num_layers > 1 else None, relu=fuse,
+                               relu_input=ahead is not None and self.num_layers > 1)
         else:  # no neighbour information (gcn2.py:151-181)
             x, x_0 = x[:batch_size], x_0[:batch_size]
             for i, conv in enumerate(self.convs[:-1]):
