@@ -50,6 +50,7 @@ _PROTOS = {
     "incagg_spmm_plan_bytes": (c_size_t, [c_int64, c_int64]),
     "incagg_spmm_plan": (c_int, [P, c_int64, c_int64, P, c_size_t, P]),
     "incagg_spmm_csr": (c_int, [c_int, P, P, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, P, P]),
+    "incagg_spmm_csr_gated": (c_int, [c_int, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, c_int64, P]),
     "incagg_spmm_delta": (c_int, [c_int, P, P, P, P, c_int64, P, c_int64, P, c_int64, P, P, c_int64,
                                   c_int64, c_int32, P, P]),
     "incagg_spmm_minmax_bwd": (c_int, [P, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, P]),

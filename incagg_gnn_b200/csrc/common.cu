@@ -43,7 +43,7 @@ bool pdl_enabled() {
 
 }  // namespace incagg
 
-extern "C" int incagg_version(void) { return 101; }
+extern "C" int incagg_version(void) { return 102; }
 
 extern "C" int64_t incagg_launch_count(void) { return (int64_t)incagg::launches(); }
 

@@ -96,6 +96,10 @@ struct SpmmParams {
   int64_t lda;
   int64_t rows;
   int32_t F;
+  // optional output gate: out[r, f] = 0 where gate[r, f] <= 0 (the ReLU mask of the backward pass of
+  // a layer whose activation was fused into the producer of x)
+  const float* gate;
+  int64_t ld_gate;
   // delta extras
   const float* m_in;
   int64_t ld_in;
@@ -267,6 +271,12 @@ __device__ __forceinline__ void finish_row(const SpmmParams& p, int op, int64_t 
         load_vec<VEC>(ag + f, m);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) o[i] += m[i];
+      }
+      if (p.gate != nullptr) {  // uniform branch
+        float gt[VEC];
+        load_vec<VEC>(p.gate + row * p.ld_gate + f, gt);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = (gt[i] > 0.f) ? o[i] : 0.f;
       }
       store_vec<VEC>(p.out + row * p.ldo + f, o);
       if constexpr (ARG) {
@@ -633,6 +643,10 @@ static int pick_vec(const SpmmParams& p, int width) {
     a16 = a16 && aligned16(p.arg) && p.lda % 4 == 0;
     a8 = a8 && aligned8(p.arg) && p.lda % 2 == 0;
   }
+  if (p.gate) {
+    a16 = a16 && aligned16(p.gate) && p.ld_gate % 4 == 0;
+    a8 = a8 && aligned8(p.gate) && p.ld_gate % 2 == 0;
+  }
   if (p.m_in) {
     a16 = a16 && aligned16(p.m_in) && aligned16(p.m_ag) && p.ld_in % 4 == 0 && p.ld_ag % 4 == 0;
     a8 = a8 && aligned8(p.m_in) && aligned8(p.m_ag) && p.ld_in % 2 == 0 && p.ld_ag % 2 == 0;
@@ -670,19 +684,21 @@ extern "C" int incagg_spmm_plan(const int32_t* rowptr, int64_t rows, int64_t nnz
                     as_stream(stream));
 }
 
-extern "C" int incagg_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col,
-                               const float* val, const float* X, int64_t ldx, float* out,
-                               int64_t ldo, int32_t* arg_out, int64_t lda, int64_t rows, int32_t F,
-                               const void* plan, incagg_stream_t stream) {
+static int spmm_csr_impl(int reduce, const int32_t* rowptr, const int32_t* col, const float* val,
+                         const float* X, int64_t ldx, float* out, int64_t ldo, int32_t* arg_out, int64_t lda,
+                         int64_t rows, int32_t F, const void* plan, const float* gate, int64_t ld_gate,
+                         incagg_stream_t stream) {
   int rc = check_common(rowptr, col, X, out, ldx, ldo, rows, F);
   if (rc != INCAGG_OK) return rc;
   if (rows == 0 || F == 0) return INCAGG_OK;
   IA_CHECK_ARG(reduce >= 0 && reduce <= 3, "unknown reducer %d", reduce);
   IA_CHECK_ARG(arg_out == nullptr || lda >= F, "lda smaller than F");
+  IA_CHECK_ARG(gate == nullptr || ld_gate >= F, "ld_gate smaller than F");
   SpmmParams p{};
   p.rowptr = rowptr; p.col = col; p.val = val; p.X = X; p.ldx = ldx; p.out = out; p.ldo = ldo;
   p.arg = (reduce == R_MIN || reduce == R_MAX) ? arg_out : nullptr;
   p.lda = lda; p.rows = rows; p.F = F;
+  p.gate = gate; p.ld_gate = ld_gate;
   p.plan = static_cast<const SpmmPlan*>(plan);
   const int vec = pick_vec(p, F);
   cudaStream_t st = as_stream(stream);
@@ -697,6 +713,24 @@ extern "C" int incagg_spmm_csr(int reduce, const int32_t* rowptr, const int32_t*
       return p.arg ? dispatch_shape<R_MAX, false, true>(p, F, vec, 1, ib, st)
                    : dispatch_shape<R_MAX, false, false>(p, F, vec, 1, ib, st);
   }
+}
+
+extern "C" int incagg_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col,
+                               const float* val, const float* X, int64_t ldx, float* out,
+                               int64_t ldo, int32_t* arg_out, int64_t lda, int64_t rows, int32_t F,
+                               const void* plan, incagg_stream_t stream) {
+  return spmm_csr_impl(reduce, rowptr, col, val, X, ldx, out, ldo, arg_out, lda, rows, F, plan, nullptr, 0,
+                       stream);
+}
+
+extern "C" int incagg_spmm_csr_gated(int reduce, const int32_t* rowptr, const int32_t* col,
+                                     const float* val, const float* X, int64_t ldx, float* out,
+                                     int64_t ldo, int64_t rows, int32_t F, const void* plan,
+                                     const float* gate, int64_t ld_gate, incagg_stream_t stream) {
+  IA_CHECK_ARG(reduce == R_SUM || reduce == R_MEAN, "gated SpMM supports sum / mean (got %d)", reduce);
+  IA_CHECK_ARG(gate != nullptr, "gate is NULL");
+  return spmm_csr_impl(reduce, rowptr, col, val, X, ldx, out, ldo, nullptr, 0, rows, F, plan, gate, ld_gate,
+                       stream);
 }
 
 extern "C" int incagg_spmm_delta(int reduce, const int32_t* rowptr, const int32_t* col,

@@ -87,7 +87,10 @@ class GCN2(ScalableGNN):
                 if ahead is not None:
                     # the layer GEMM writes rows [0, B) of the buffer whose tail the early pull fills
                     buf, pulled = ahead[i]
-                    x = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=True, out_full=buf)
+                    # the ReLU of layer i rides in its GEMM epilogue; its backward mask rides in the
+                    # epilogue of the transposed SpMM of layer i + 1 (x passes only through dropout in between)
+                    x = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=True, out_full=buf,
+                             relu_input=i > 0, defer_relu_bwd=True)
                     # the push only reads the rows the GEMM just wrote and nothing in this step reads
                     # the table rows it writes: it rides on the pull stream, joined after the loop
                     main, side = torch.cuda.current_stream(), self._pull_stream
@@ -104,7 +107,8 @@ class GCN2(ScalableGNN):
             if ahead is not None:
                 torch.cuda.current_stream().wait_stream(self._pull_stream)   # pushes done before the step ends
             h = self.convs[-1](x, x0b, adj_t,
-                               grad_rows=batch_size if self.num_layers > 1 else None, relu=fuse)
+                               grad_rows=batch_size if self.num_layers > 1 else None, relu=fuse,
+                               relu_input=ahead is not None and self.num_layers > 1)
         else:  # no neighbour information (gcn2.py:151-181)
             x, x_0 = x[:batch_size], x_0[:batch_size]
             for i, conv in enumerate(self.convs[:-1]):

@@ -124,7 +124,10 @@ class _GCN2Dense(torch.autograd.Function):
     (The reference path issues ~10 elementwise / addmm launches forward and ~20 backward here.)"""
 
     @staticmethod
-    def forward(ctx, h, x0, w1, w2, a, b, relu, out_full=None):
+    def forward(ctx, h, x0, w1, w2, a, b, relu, out_full=None, defer_relu_bwd=False):
+        # defer_relu_bwd: the ReLU is applied here, but its backward mask is left to the one consumer
+        # of the output (an SpMM with relu_input=True, which gates its input gradient by [out > 0] in
+        # its epilogue): this node then receives an already masked gradient.
         # out_full: a [B + H, F] buffer whose tail rows (pulled history) are filled by someone else;
         # the GEMM writes its B rows into the head and the whole buffer is the output, so the next
         # layer's input needs no concatenation.  Only the head rows carry gradient.
@@ -134,14 +137,14 @@ class _GCN2Dense(torch.autograd.Function):
             s = torch.lerp(h, x0, a)
             out = ops.gemm(s, w1, alpha=b, cin=s, beta=1. - b, relu=relu, out=dst)
             keep = out if out_full is None else out_full   # (a saved view of a dirty base is rejected)
-            ctx.save_for_backward(h, x0, w1, w2, keep if relu else None, s)
+            ctx.save_for_backward(h, x0, w1, w2, keep if (relu and not defer_relu_bwd) else None, s)
         else:
             out = ops.gemm_dual("k", h, w1, x0, w2, scale_b=b * (1. - a), scale_b2=b * a,
                                 cin=h, beta=(1. - b) * (1. - a), cin2=x0, beta2=(1. - b) * a, relu=relu,
                                 out=dst)
             keep = out if out_full is None else out_full
-            ctx.save_for_backward(h, x0, w1, w2, keep if relu else None, None)
-        ctx.a, ctx.b, ctx.relu, ctx.shared = a, b, relu, w2 is None
+            ctx.save_for_backward(h, x0, w1, w2, keep if (relu and not defer_relu_bwd) else None, None)
+        ctx.a, ctx.b, ctx.relu, ctx.shared = a, b, (relu and not defer_relu_bwd), w2 is None
         ctx.w1_param, ctx.w2_param = w1, w2
         ctx.rows = rows
         if out_full is not None:
@@ -180,7 +183,7 @@ class _GCN2Dense(torch.autograd.Function):
                                   cin=b1, beta=1., cin2=b2, beta2=1., out=b1, out2=b2)
             else:
                 gw1, gw2 = ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a)
-        return gh, gx0, gw1, gw2, None, None, None, None
+        return gh, gx0, gw1, gw2, None, None, None, None, None
 
 
 class _MaskedCE(torch.autograd.Function):
@@ -263,7 +266,7 @@ class GCN2Conv(torch.nn.Module):
             glorot_(self.weight2)
 
     def forward_after_propagate(self, h: Tensor, x_0: Tensor, relu: bool = False,
-                                out_full: Optional[Tensor] = None) -> Tensor:
+                                out_full: Optional[Tensor] = None, defer_relu_bwd: bool = False) -> Tensor:
         """Everything of PyG's GCN2Conv.forward after ``propagate``:
             x = (1-alpha) h ; x_0 = alpha x_0[:B]
             shared:   out = x + x_0 ; out = (1-beta) out + beta out W1
@@ -273,16 +276,20 @@ class GCN2Conv(torch.nn.Module):
         if x_0.size(0) != h.size(0):  # (a no-op slice would still cost a zero-fill + copy in backward)
             x_0 = x_0[:h.size(0)]
         return _GCN2Dense.apply(h.contiguous(), x_0.contiguous(), self.weight1, self.weight2,
-                                float(self.alpha), float(self.beta), relu, out_full)
+                                float(self.alpha), float(self.beta), relu, out_full,
+                                bool(defer_relu_bwd and relu))
 
     def forward_no_neighbor(self, x: Tensor, x_0: Tensor, relu: bool = False) -> Tensor:
         return self.forward_after_propagate(x, x_0, relu)
 
     def forward(self, x: Tensor, x_0: Tensor, adj_t: SparseTensor,
                 grad_rows: Optional[int] = None, relu: bool = False,
-                out_full: Optional[Tensor] = None) -> Tensor:
-        h = spmm(adj_t, x, reduce='sum', grad_rows=grad_rows)
-        return self.forward_after_propagate(h, x_0, relu, out_full)
+                out_full: Optional[Tensor] = None, relu_input: bool = False,
+                defer_relu_bwd: bool = False) -> Tensor:
+        """relu_input: x is the ReLU output of a layer called with defer_relu_bwd=True (the two flags
+        come in pairs: producer defers, this layer's SpMM applies the mask in its backward)."""
+        h = spmm(adj_t, x, reduce='sum', grad_rows=grad_rows, relu_input=relu_input)
+        return self.forward_after_propagate(h, x_0, relu, out_full, defer_relu_bwd)
 
 
 class SAGEConv(torch.nn.Module):

@@ -67,8 +67,9 @@ def spmm_plan(rowptr: Tensor, rows: Optional[int] = None, nnz: int = -1) -> Tens
 
 def spmm_raw(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, reduce: str = "sum",
              rows: Optional[int] = None, out: Optional[Tensor] = None,
-             return_arg: bool = False, plan: Optional[Tensor] = None):
-    """out[i] = reduce_e val[e] * x[col[e]] over a CSR with int32 rowptr/col (device)."""
+             return_arg: bool = False, plan: Optional[Tensor] = None, gate: Optional[Tensor] = None):
+    """out[i] = reduce_e val[e] * x[col[e]] over a CSR with int32 rowptr/col (device).
+    `gate` ([rows, F] float32, sum / mean only): out is zeroed where gate <= 0 in the kernel's epilogue."""
     _require_cuda(rowptr, col, val, x)
     assert rowptr.dtype == torch.int32 and col.dtype == torch.int32
     squeeze = x.dim() == 1
@@ -81,6 +82,15 @@ def spmm_raw(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, redu
     if return_arg and reduce in ("min", "max"):
         arg = torch.empty((n_rows, F), dtype=torch.int32, device=x.device)
     LAUNCHES["calls"] += 1
+    if gate is not None:
+        if reduce not in ("sum", "mean") or gate.dtype != torch.float32 or gate.dim() != 2 \
+                or gate.stride(1) != 1 or gate.size(0) < n_rows or gate.size(1) < F:
+            raise RuntimeError("spmm: gate must be a row-major float32 [rows, >= F] tensor (sum / mean)")
+        _require_cuda(gate)
+        check(lib.incagg_spmm_csr_gated(REDUCE[reduce], ptr(rowptr), ptr(col), ptr(val), ptr(x), _ld(x),
+                                        ptr(out), _ld(out), n_rows, F, ptr(plan), ptr(gate), gate.stride(0),
+                                        _stream()))
+        return out.squeeze(1) if squeeze else out
     check(lib.incagg_spmm_csr(REDUCE[reduce], ptr(rowptr), ptr(col), ptr(val), ptr(x), _ld(x),
                               ptr(out), _ld(out), ptr(arg), F if arg is not None else 0, n_rows, F,
                               ptr(plan), _stream()))

@@ -214,16 +214,21 @@ class SparseTensor:
 
 class _SpMM(torch.autograd.Function):
     """reduce(A, x) with grad only w.r.t. x (edge values carry no gradient in the reference's
-    pipelines: gcn_norm weights are constants)."""
+    pipelines: gcn_norm weights are constants).  ``relu_input``: x is the output of a ReLU that its
+    producer fused into its own epilogue and whose backward it leaves to this node: the gradient
+    w.r.t. x is returned already multiplied by [x > 0] (one kernel, sum / mean)."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, adj: SparseTensor, reduce: str, grad_rows: Optional[int]):
+    def forward(ctx, x: Tensor, adj: SparseTensor, reduce: str, grad_rows: Optional[int],
+                relu_input: bool = False):
         ctx.adj, ctx.reduce, ctx.n_src, ctx.grad_rows = adj, reduce, x.size(0), grad_rows
+        ctx.relu_input = bool(relu_input)
         if reduce in ("min", "max"):
             out, arg = ops.spmm_raw(adj.rowptr, adj.col, adj.value, x, reduce, rows=adj.size(0),
                                     return_arg=True, plan=adj.plan())
-            ctx.save_for_backward(arg)
+            ctx.save_for_backward(arg, x if relu_input else None)
             return out
+        ctx.save_for_backward(None, x if relu_input else None)
         return ops.spmm_raw(adj.rowptr, adj.col, adj.value, x, reduce, rows=adj.size(0),
                             plan=adj.plan())
 
@@ -231,48 +236,66 @@ class _SpMM(torch.autograd.Function):
     def backward(ctx, grad_out: Tensor):
         adj, reduce = ctx.adj, ctx.reduce
         if not ctx.needs_input_grad[0]:
-            return None, None, None, None
+            return None, None, None, None, None
         grad_out = grad_out.contiguous()
+        arg, x = ctx.saved_tensors
         if reduce in ("min", "max"):
-            (arg,) = ctx.saved_tensors
-            return ops.spmm_minmax_bwd_raw(adj.col, adj.value, arg, grad_out, ctx.n_src), None, None, None
+            gx = ops.spmm_minmax_bwd_raw(adj.col, adj.value, arg, grad_out, ctx.n_src)
+            if ctx.relu_input:
+                gx = torch.ops.aten.threshold_backward(gx, x, 0.)
+            return gx, None, None, None, None
         if reduce == "mean":
             deg = (adj.rowptr[1:] - adj.rowptr[:-1]).clamp_(min=1).to(grad_out.dtype)
             grad_out = grad_out / deg.unsqueeze(1)
-        return _transposed_product(adj, grad_out, ctx.n_src, ctx.grad_rows), None, None, None
+        gate = None
+        if ctx.relu_input:
+            if x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1:
+                gate = x
+            else:  # layout the kernel's epilogue does not read: mask afterwards
+                gx = _transposed_product(adj, grad_out, ctx.n_src, ctx.grad_rows)
+                rows = gx.size(0) if ctx.grad_rows is None else min(ctx.grad_rows, gx.size(0))
+                gx[:rows] = torch.ops.aten.threshold_backward(gx[:rows], x[:rows].to(gx.dtype), 0.)
+                return gx, None, None, None, None
+        return _transposed_product(adj, grad_out, ctx.n_src, ctx.grad_rows, gate=gate), None, None, None, None
 
 
-def _transposed_product(adj: SparseTensor, grad_out: Tensor, n_src: int, grad_rows: Optional[int]):
+def _transposed_product(adj: SparseTensor, grad_out: Tensor, n_src: int, grad_rows: Optional[int],
+                        gate: Optional[Tensor] = None):
     """grad_x = A^T grad_out.  With grad_rows = k only the first k source rows are computed (the
-    rest of x was a constant, e.g. pulled history rows) and the remainder is returned as zeros."""
+    rest of x was a constant, e.g. pulled history rows) and the remainder is returned as zeros.
+    `gate` (= x when x is the output of a fused ReLU): the result is zeroed where gate <= 0."""
     t_rowptr, t_col, t_val = adj.t_csr()
     t_plan = adj.t_plan()
     if grad_rows is None or grad_rows >= n_src:
-        return ops.spmm_raw(t_rowptr, t_col, t_val, grad_out, "sum", rows=n_src, plan=t_plan)
+        return ops.spmm_raw(t_rowptr, t_col, t_val, grad_out, "sum", rows=n_src, plan=t_plan, gate=gate)
     # Rows >= grad_rows of x are constants (history rows placed there by push_and_pull, whose
     # backward reads only the first `grad_rows` rows of this gradient): they are neither computed nor
     # zero-filled (a [B+H, F] fill per layer per step otherwise).
     gx = torch.empty((n_src, grad_out.size(1)), dtype=grad_out.dtype, device=grad_out.device)
     ops.spmm_raw(t_rowptr, t_col, t_val, grad_out, "sum", rows=grad_rows, out=gx[:grad_rows],
-                 plan=adj.t_plan_prefix(grad_rows))
+                 plan=adj.t_plan_prefix(grad_rows), gate=gate)
     return gx
 
 
-def spmm(adj: SparseTensor, x: Tensor, reduce: str = "sum", grad_rows: Optional[int] = None) -> Tensor:
+def spmm(adj: SparseTensor, x: Tensor, reduce: str = "sum", grad_rows: Optional[int] = None,
+         relu_input: bool = False) -> Tensor:
     """torch_sparse.matmul / torch_geometric.utils.spmm replacement (graphsage.py:30,634)."""
     if reduce == "add":
         reduce = "sum"
     if x.size(0) < adj.size(1):
         raise RuntimeError(f"spmm: x has {x.size(0)} rows but the adjacency has {adj.size(1)} columns")
-    return _SpMM.apply(x, adj, reduce, grad_rows)
+    return _SpMM.apply(x, adj, reduce, grad_rows, relu_input)
 
 
 class _SpMMDelta(torch.autograd.Function):
     """h = reduce(A, x - M_in) + M_ag, fused (gcn2.py:255).  M_in / M_ag are constants."""
 
     @staticmethod
-    def forward(ctx, x, adj, m_in, m_ag, n_id, reduce):
+    def forward(ctx, x, adj, m_in, m_ag, n_id, reduce, relu_input=False):
         ctx.adj, ctx.reduce, ctx.n_src = adj, reduce, x.size(0)
+        ctx.save_for_backward(x if (relu_input and x.dtype == torch.float32 and x.dim() == 2
+                                    and x.stride(1) == 1) else None)
+        ctx.relu_input = bool(relu_input)
         return ops.spmm_delta_raw(adj.rowptr, adj.col, adj.value, x, m_in, m_ag, n_id, reduce,
                                   rows=adj.size(0), plan=adj.plan())
 
@@ -283,11 +306,15 @@ class _SpMMDelta(torch.autograd.Function):
         if ctx.reduce == "mean":
             deg = (adj.rowptr[1:] - adj.rowptr[:-1]).clamp_(min=1).to(grad_out.dtype)
             grad_out = grad_out / deg.unsqueeze(1)
-        return _transposed_product(adj, grad_out, ctx.n_src, None), None, None, None, None, None
+        (gate,) = ctx.saved_tensors
+        if ctx.relu_input and gate is None:
+            raise RuntimeError('spmm_delta(relu_input=True) needs a row-major float32 x')
+        return (_transposed_product(adj, grad_out, ctx.n_src, None, gate=gate),
+                None, None, None, None, None, None)
 
 
 def spmm_delta(adj: SparseTensor, x: Tensor, m_in: Tensor, m_ag: Tensor,
-               n_id: Optional[Tensor] = None, reduce: str = "sum") -> Tensor:
+               n_id: Optional[Tensor] = None, reduce: str = "sum", relu_input: bool = False) -> Tensor:
     """Fused incremental-aggregation update  A_BB (x - M_in) + M_ag  (one kernel instead of the
     reference's sub + SpMM + add + two clones)."""
-    return _SpMMDelta.apply(x, adj, m_in, m_ag, n_id, reduce)
+    return _SpMMDelta.apply(x, adj, m_in, m_ag, n_id, reduce, relu_input)

@@ -88,6 +88,16 @@ int incagg_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col, const
                     int64_t lda, int64_t rows, int32_t F, const void* plan, incagg_stream_t stream);
 
 /*
+ * incagg_spmm_csr (sum / mean) whose epilogue zeroes out[r, f] where gate[r, f] <= 0.  Backward of a
+ * layer whose ReLU was fused into the producer of X (the GEMM epilogue of the previous layer):
+ * grad_X = (A^T grad_out) * [X > 0] in one launch instead of the SpMM plus torch's threshold_backward
+ * (reference: the `.relu_()` after every conv, gcn2.py:139, and its autograd backward).
+ */
+int incagg_spmm_csr_gated(int reduce, const int32_t* rowptr, const int32_t* col, const float* val,
+                          const float* X, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t F,
+                          const void* plan, const float* gate, int64_t ld_gate, incagg_stream_t stream);
+
+/*
  * Fused incremental-aggregation update (reference: gcn.py:241, gcn2.py:255,
  * appnp.py:122, graphsage.py:634):
  *     out[i] = reduce_e val[e] * (x[col[e]] - M_in[g(col[e])]) + M_ag[g(i)]

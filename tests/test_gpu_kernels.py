@@ -64,6 +64,49 @@ def test_spmm_matches_oracle(ops, cuda, reduce, F):
         assert np.array_equal(arg.cpu().numpy().astype(np.int64), ref_arg)
 
 
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+@pytest.mark.parametrize("F", [24, 128, 130])
+def test_spmm_gated_epilogue(ops, cuda, reduce, F):
+    """incagg_spmm_csr_gated: the plain result, zeroed where gate <= 0 - bit-identical to masking the
+    ungated kernel's output afterwards (long rows and a prefix of the rows included)."""
+    rng = np.random.default_rng(F + len(reduce))
+    rowptr, col, val = _rand_csr(rng, 300, 500, 20, long_rows=2, long_len=3000)
+    X = _dev(rng.standard_normal((500, F)).astype(np.float32), cuda)
+    gate_full = _dev(rng.standard_normal((300, F + 6)).astype(np.float32), cuda)
+    gate = gate_full[:, :F]                       # a view with a leading dimension wider than F
+    rp, c, v = _dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32), _dev(val, cuda)
+    plain = ops.spmm_raw(rp, c, v, X, reduce)
+    gated = ops.spmm_raw(rp, c, v, X, reduce, gate=gate)
+    want = torch.where(gate > 0, plain, torch.zeros_like(plain))
+    assert torch.equal(gated, want)
+    # first 100 rows only, into a slice of a larger buffer (the backward over the in-batch rows)
+    buf = torch.full((300, F), 7.0, device=cuda)
+    ops.spmm_raw(rp[:101], c, v, X, reduce, rows=100, out=buf[:100], gate=gate)
+    assert torch.equal(buf[:100], want[:100]) and float(buf[100:].min()) == 7.0
+
+
+def test_spmm_relu_input_backward_matches_separate_mask(cuda):
+    """autograd: spmm(..., relu_input=True) returns A^T g masked by [x > 0], for full and prefix rows."""
+    import incagg_gnn_b200 as tga
+    from incagg_gnn_b200.sparse import spmm
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n_dst, n_src, F, B = 200, 350, 64, 120
+    dense = (torch.rand(n_dst, n_src, generator=g) < 0.05).float() * torch.rand(n_dst, n_src, generator=g)
+    row, col = dense.nonzero(as_tuple=True)
+    adj = tga.SparseTensor(row=row.to(cuda), col=col.to(cuda), value=dense[row, col].to(cuda),
+                           sparse_sizes=(n_dst, n_src), is_sorted=True)
+    x0 = torch.randn(n_src, F, generator=g).to(cuda)
+    go = torch.randn(n_dst, F, generator=g).to(cuda)
+    for grad_rows in (None, B):
+        xa = x0.clone().requires_grad_(True)
+        spmm(adj, xa, grad_rows=grad_rows, relu_input=True).backward(go)
+        xb = x0.clone().requires_grad_(True)
+        spmm(adj, xb, grad_rows=grad_rows).backward(go)
+        rows = n_src if grad_rows is None else grad_rows
+        want = torch.where(x0[:rows] > 0, xb.grad[:rows], torch.zeros_like(xb.grad[:rows]))
+        assert torch.equal(xa.grad[:rows], want)
+
+
 @pytest.mark.parametrize("has_val", [True, False])
 def test_spmm_without_values_and_empty(ops, cuda, has_val):
     rng = np.random.default_rng(11)
