@@ -36,6 +36,13 @@ int sm_count() {
   return cached[dev];
 }
 
+static int g_tune[INCAGG_TUNE_COUNT];
+static bool g_tune_set[INCAGG_TUNE_COUNT];
+int tune_get(int key, int dflt) {
+  if (key < 0 || key >= INCAGG_TUNE_COUNT || !g_tune_set[key]) return dflt;
+  return g_tune[key];
+}
+
 bool pdl_enabled() {
   static const bool on = [] { const char* v = getenv("INCAGG_PDL"); return v != nullptr && v[0] == '1'; }();
   return on;
@@ -43,7 +50,14 @@ bool pdl_enabled() {
 
 }  // namespace incagg
 
-extern "C" int incagg_version(void) { return 102; }
+extern "C" int incagg_version(void) { return 103; }
+
+extern "C" int incagg_tune_set(int key, int value) {
+  IA_CHECK_ARG(key >= 0 && key < INCAGG_TUNE_COUNT, "unknown tuning key %d", key);
+  incagg::g_tune[key] = value;
+  incagg::g_tune_set[key] = true;
+  return INCAGG_OK;
+}
 
 extern "C" int64_t incagg_launch_count(void) { return (int64_t)incagg::launches(); }
 

@@ -39,6 +39,7 @@ int set_err(int code, const char* fmt, ...);
 inline cudaStream_t as_stream(incagg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();  // cached SM count of the current device (148 on B200)
+int tune_get(int key, int dflt);  // experiment knobs (incagg_tune_set); `dflt` when unset
 void count_launch();  // process-wide count of kernels launched by this library
 unsigned long long launches();
 

@@ -17,9 +17,15 @@
 //   * int32 indices (half the index traffic of the reference's int64 path);
 //   * rows longer than LONG_ROW edges are split across the warps of a CTA by a second
 //     kernel (degree-bucketed scheduling) and combined in a fixed order -> deterministic.
+// Wide sum / mean products (F > 64, 16-byte aligned rows: the GCNII / GraphSAGE / PNA layer widths) run
+// through the merge-path kernel `spmm_stream_kernel` instead: the edge array is cut into equal
+// pieces, one per resident warp, and every warp streams its piece with a software-pipelined ring of
+// D 128-bit row gathers that never drains at row boundaries (see the kernel's comment).
 #include <float.h>
 #include <stdlib.h>
 #include <limits.h>
+#include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -77,9 +83,21 @@ struct SpmmPlan {
   int32_t long_row;
   int32_t chunk;
   int32_t capacity;   // size of the item array
+  // merge-path partition of the edge array (spmm_stream_kernel): warp slot w owns the edges
+  // [e_base + w * q, e_base + (w + 1) * q) and starts in row wrow[w]
+  int32_t n_wslots;
+  int32_t q;          // edges per warp slot (a multiple of 32)
+  int32_t e_base;     // rowptr[0]
+  int32_t e_end;      // rowptr[rows]
   int32_t pad[3];
   // followed by int4 items[capacity]: {row, chunk index, scratch base or -1, number of chunks}
+  // followed by int32 wrow[WS_MAX_SLOTS + 1]
 };
+static_assert(sizeof(SpmmPlan) == 48, "plan header is three int4");
+constexpr int WS_WARPS = 8;           // warps per CTA of the stream kernel
+constexpr int WS_TILE_F = 128;        // features per tile: 32 lanes x float4
+constexpr int WS_MAX_SLOTS = 8192;    // upper bound of warp slots (148 SMs x 32 warps = 4736)
+constexpr int WS_MAX_TILES = 8;       // feature tiles the partial-row scratch is sized for (F <= 1024)
 constexpr int PART_STRIDE = 512;        // floats per scratch slot (= widest tile, 32 lanes * 4 * 4)
 constexpr int PART_SLOTS = 16384;       // scratch slots per device (32 MB values + 32 MB args)
 constexpr int PLAN_SCRATCH_CAP = 8192;  // slots one plan may hand out (times the feature tiles)
@@ -119,6 +137,10 @@ struct SpmmParams {
   int32_t* part_arg;        // same shape, winning edge of min/max partials
   int32_t* part_done;       // [part_slots] arrival counters (left at zero by every call)
   int32_t part_slots;
+  // stream kernel: partial sums of rows cut by a warp boundary, arrival counters, mean flag
+  float* ws_part;           // [tiles][n_wslots][2][WS_TILE_F]
+  int32_t* ws_done;         // [tiles][n_wslots]
+  int32_t mean;
 };
 
 
@@ -456,22 +478,271 @@ spmm_kernel(const SpmmParams p) {
   }
 }
 
+// ---- merge-path kernel for wide sum / mean products ---------------------------------------------
+//
+// The row-per-warp kernel above leaves the memory system idle at every row end (a 26-edge row is six
+// rounds of four gathers plus a serial remainder, and a new row starts with two dependent index
+// loads), and rows of very different lengths make the tail of a batch-sized launch long.  Here the
+// EDGE array is the unit of scheduling (merge-path SpMM): warp slot w owns the `q` consecutive edges
+// [e_base + w q, e_base + (w + 1) q) whatever rows they belong to, the grid is one resident wave, so
+// every warp does the same amount of work and finishes at the same time.  Inside its piece a warp
+//   * fetches col / val in coalesced blocks of 32 edges, two blocks ahead (lane i keeps edge i of
+//     the block; consumers read them with shuffles);
+//   * keeps a ring of D independent 128-bit gathers of X rows in flight (one 512-byte row segment
+//     per warp instruction): the load of edge j + D is issued right after edge j has been consumed,
+//     across row boundaries, so the ring never drains (D = 16 -> 8 KB in flight per warp, 128 KB per
+//     SM with 16 resident warps);
+//   * walks the rows its edges belong to through a 64-entry register window of rowptr (refilled a
+//     window ahead) and writes a row as soon as its last edge is consumed.
+// Rows cut by a piece boundary: every piece that holds a part of the row stores its partial sum
+// (head part = slot 0, tail part = slot 1 of the warp), bumps the arrival counter of the row's first
+// piece, and the last one to arrive adds the partials IN PIECE ORDER and writes the row - wait-free,
+// and independent of scheduling (deterministic).  Empty rows are written (as zeros, plus M_ag for the
+// delta form) by the piece that passes over them.
+struct WsHeader {
+  int n_w, q, e_base, e_end, capacity;
+};
+// What the row epilogue needs, by value (taking the address of the kernel's parameter struct would
+// copy it to local memory).
+struct WsOut {
+  float* out;
+  const float* m_ag;
+  const float* gate;
+  float* ws_part;
+  int32_t* ws_done;
+  int64_t ldo, ld_ag, ld_gate;
+  int mean;
+};
+
+__device__ __forceinline__ void ws_finish(const WsOut& o, int row, int deg, float4 a, int f, bool fok) {
+  if (!fok) return;
+  if (o.mean) {
+    const float inv = 1.f / (float)max(deg, 1);
+    a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+  }
+  if (o.m_ag != nullptr) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(o.m_ag + (int64_t)row * o.ld_ag + f));
+    a.x += m.x; a.y += m.y; a.z += m.z; a.w += m.w;
+  }
+  if (o.gate != nullptr) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(o.gate + (int64_t)row * o.ld_gate + f));
+    a.x = g.x > 0.f ? a.x : 0.f; a.y = g.y > 0.f ? a.y : 0.f;
+    a.z = g.z > 0.f ? a.z : 0.f; a.w = g.w > 0.f ? a.w : 0.f;
+  }
+  *reinterpret_cast<float4*>(o.out + (int64_t)row * o.ldo + f) = a;
+}
+
+// A row whose last edge has been consumed (or the last row of the piece).  Rows that lie inside the
+// piece are written; of a row cut by a piece boundary this piece's partial is stored and the last
+// piece to arrive combines them.  Not inlined: it is called from every slot of the unrolled ring.
+__device__ __noinline__ void ws_row_done(const WsOut o, const WsHeader h, int w, int tile, int row, int rs,
+                                         int re, int e0, int e1, float4 a, int f, bool fok) {
+  if (rs >= e0 && re <= e1) {
+    ws_finish(o, row, re - rs, a, f, fok);
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int first = (rs - h.e_base) / h.q, last = (re - 1 - h.e_base) / h.q;
+  const int which = (w == first) ? 1 : 0;
+  const int64_t tbase = (int64_t)tile * h.n_w;
+  float* part = o.ws_part + ((tbase + w) * 2 + which) * WS_TILE_F + lane * 4;
+  *reinterpret_cast<float4*>(part) = a;
+  __threadfence();
+  int prev = 0;
+  if (lane == 0) prev = atomicAdd(o.ws_done + tbase + first, 1);
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  if (prev != last - first) return;
+  __threadfence();
+  float4 s = __ldcg(reinterpret_cast<const float4*>(o.ws_part + ((tbase + first) * 2 + 1) * WS_TILE_F + lane * 4));
+  for (int ww = first + 1; ww <= last; ++ww) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(o.ws_part + ((tbase + ww) * 2) * WS_TILE_F + lane * 4));
+    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+  }
+  if (lane == 0) o.ws_done[tbase + first] = 0;  // clean for the next call
+  ws_finish(o, row, re - rs, s, f, fok);
+}
+
+template <int D, int MINB, bool DELTA>
+__global__ void __launch_bounds__(WS_WARPS * 32, MINB)
+spmm_stream_kernel(const SpmmParams p) {
+  pdl_prologue();
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * WS_WARPS + (threadIdx.x >> 5);
+  const int tile = blockIdx.y;
+  const int f = tile * WS_TILE_F + lane * 4;
+  const bool fok = f < p.F;
+  const int4 h1 = __ldg(reinterpret_cast<const int4*>(p.plan) + 1);  // capacity, n_wslots, q, e_base
+  const int4 h2 = __ldg(reinterpret_cast<const int4*>(p.plan) + 2);  // e_end
+  WsHeader h;
+  h.capacity = h1.x; h.n_w = h1.y; h.q = h1.z; h.e_base = h1.w; h.e_end = h2.x;
+  const int rows = (int)p.rows;
+  if (w >= h.n_w) return;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  WsOut o;
+  o.out = p.out; o.m_ag = p.m_ag; o.gate = p.gate; o.ws_part = p.ws_part; o.ws_done = p.ws_done;
+  o.ldo = p.ldo; o.ld_ag = p.ld_ag; o.ld_gate = p.ld_gate; o.mean = p.mean;
+  if (h.e_base == h.e_end) {  // a structure without edges: every row is empty
+    for (int r = w; r < rows; r += h.n_w) ws_finish(o, r, 0, zero4, f, fok);
+    return;
+  }
+  const int e0 = h.e_base + w * h.q;
+  if (e0 >= h.e_end) return;
+  const int e1 = min(e0 + h.q, h.e_end);
+
+  // col / val blocks: lane i holds edge (block start + i); blocks 0, 1, 2 of the piece
+  int c0, c1, c2;
+  float v0, v1, v2;
+  auto load_blk = [&](int start, int& c, float& v) {
+    const int idx = start + lane;
+    c = 0;
+    v = 0.f;
+    if (idx < e1) {
+      c = ldg_stream(p.col + idx);
+      v = p.val ? ldg_stream(p.val + idx) : 1.f;
+    }
+  };
+  load_blk(e0, c0, v0);
+  load_blk(e0 + 32, c1, v1);
+  load_blk(e0 + 64, c2, v2);
+  const int* wrow = reinterpret_cast<const int*>(p.items + h.capacity);
+  int r = __ldg(wrow + w);  // the row that holds edge e0
+  // rowptr window: lane i holds rowptr[rwin + i] (cur) and rowptr[rwin + 32 + i] (nxt)
+  int rwin = r;
+  int rp_cur = __ldg(p.rowptr + min(rwin + lane, rows));
+  int rp_nxt = __ldg(p.rowptr + min(rwin + 32 + lane, rows));
+  auto win = [&](int i) {  // rowptr[rwin + i], 0 <= i < 64
+    const int a = __shfl_sync(FULL, rp_cur, i & 31), b = __shfl_sync(FULL, rp_nxt, i & 31);
+    return i < 32 ? a : b;
+  };
+
+  // row c of X / M_in starts at byte c * row_bytes (< 2^32, checked by the host): one IMAD.WIDE.U32
+  // (lanes past F in the last tile gather column 0 instead - unconditional loads - and never store)
+  const int f_ld = fok ? f : 0;
+  const char* Xb = reinterpret_cast<const char*>(p.X + f_ld);
+  const char* Mb = DELTA ? reinterpret_cast<const char*>(p.m_in + f_ld) : nullptr;
+  const unsigned x_bytes = (unsigned)p.ldx * 4u, m_bytes = DELTA ? (unsigned)p.ld_in * 4u : 0u;
+  float4 x[D];
+  float4 m[DELTA ? D : 1];
+  auto issue = [&](int c, int slot) {
+    x[slot] = __ldg(reinterpret_cast<const float4*>(Xb + (size_t)(unsigned)c * x_bytes));
+    if constexpr (DELTA) m[slot] = __ldg(reinterpret_cast<const float4*>(Mb + (size_t)(unsigned)c * m_bytes));
+  };
+#pragma unroll
+  for (int u = 0; u < D; ++u) {
+    x[u] = zero4;
+    if constexpr (DELTA) m[u] = zero4;
+  }
+  // prologue: the first D gathers (D <= 32: all in block 0)
+#pragma unroll
+  for (int u = 0; u < D; ++u) {
+    const int c = __shfl_sync(FULL, c0, u);
+    if (e0 + u < e1) issue(c, u);
+  }
+  if (w == 0)  // empty rows in front of the first edge
+    for (int rr = 0; rr < r; ++rr) ws_finish(o, rr, 0, zero4, f, fok);
+  int row_start = win(0), row_end = win(1);
+  float4 acc = zero4;
+  auto next_row = [&]() {
+    ++r;
+    if (r - rwin >= 32) {  // slide the window
+      rwin += 32;
+      rp_cur = rp_nxt;
+      rp_nxt = __ldg(p.rowptr + min(rwin + 32 + lane, rows));
+    }
+    row_start = row_end;
+    row_end = win(r + 1 - rwin);
+  };
+  // One block of 32 edges starting at jb (block 0 of the index registers).  LAST = the piece ends in
+  // this block: only then the end of the piece has to be tested per edge (q is a multiple of 32, so
+  // every other block is full and its refills stay inside the piece).
+  auto do_block = [&](int jb, auto last_tag) {
+    constexpr bool LAST = decltype(last_tag)::value;
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      const int jj = jb + u;
+      if (!LAST || jj < e1) {  // uniform
+        while (jj >= row_end) {  // the last edge of the current row has been consumed
+          ws_row_done(o, h, w, tile, r, row_start, row_end, e0, e1, acc, f, fok);
+          acc = zero4;
+          next_row();
+        }
+        const float v = __shfl_sync(FULL, v0, u);
+        const int s = u % D;
+        if constexpr (DELTA) {
+          acc.x = fmaf(v, x[s].x - m[s].x, acc.x); acc.y = fmaf(v, x[s].y - m[s].y, acc.y);
+          acc.z = fmaf(v, x[s].z - m[s].z, acc.z); acc.w = fmaf(v, x[s].w - m[s].w, acc.w);
+        } else {
+          acc.x = fmaf(v, x[s].x, acc.x); acc.y = fmaf(v, x[s].y, acc.y);
+          acc.z = fmaf(v, x[s].z, acc.z); acc.w = fmaf(v, x[s].w, acc.w);
+        }
+        // refill the ring slot with the gather of edge jj + D
+        const int c = (u + D < 32) ? __shfl_sync(FULL, c0, (u + D) & 31) : __shfl_sync(FULL, c1, (u + D) & 31);
+        if (!LAST || jj + D < e1) issue(c, s);
+      }
+    }
+  };
+  for (int jb = e0; jb < e1; jb += 32) {
+    if (jb + 32 + D <= e1) do_block(jb, std::false_type{});
+    else do_block(jb, std::true_type{});
+    c0 = c1; v0 = v1;  // rotate the index blocks, fetch the block three ahead
+    c1 = c2; v1 = v2;
+    load_blk(jb + 96, c2, v2);
+  }
+  // the row of the last edge: complete if it ends exactly here, else a tail (or middle) part
+  ws_row_done(o, h, w, tile, r, row_start, row_end, e0, e1, acc, f, fok);
+  // empty rows that follow, up to the first row the next piece starts in
+  if (row_end <= e1) {
+    while (r + 1 < rows) {
+      next_row();
+      if (row_end > e1) break;
+      ws_finish(o, r, 0, zero4, f, fok);
+    }
+  }
+}
+
 // Plan construction: one thread per row appends the row's work items.
 __global__ void spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t rows, SpmmPlan* plan,
-                                 int4* __restrict__ items, int long_row, int chunk, int capacity) {
+                                 int4* __restrict__ items, int long_row, int chunk, int capacity,
+                                 int n_wslots) {
   pdl_prologue();
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int e_base = rowptr[0], e_end = rowptr[rows];
+  const int64_t nnz = (int64_t)e_end - e_base;
   if (chunk <= 0) {
     // adaptive chunk: small enough that one CTA trip is a few microseconds on batch-sized
     // structures, large enough that the split rows of a whole graph fit the scratch area
-    const int64_t nnz = (int64_t)rowptr[rows] - rowptr[0];
     chunk = 256;
     while (chunk < 4096 && (int64_t)chunk * (PLAN_SCRATCH_CAP / 2) < nnz) chunk <<= 1;
   }
+  // merge-path partition: q edges per warp slot, a multiple of 32 (aligned index blocks)
+  int64_t q64 = (nnz + n_wslots - 1) / n_wslots;
+  q64 = (q64 + 31) / 32 * 32;
+  if (q64 < 32) q64 = 32;
+  const int q = (int)q64;
   if (row == 0) {
     plan->long_row = long_row;
     plan->chunk = chunk;
     plan->capacity = capacity;
+    plan->n_wslots = n_wslots;
+    plan->q = q;
+    plan->e_base = e_base;
+    plan->e_end = e_end;
+  }
+  if (row <= n_wslots) {
+    // wrow[w] = the row that holds edge e_base + w q: the largest r with rowptr[r] <= that edge
+    int* wrow = reinterpret_cast<int*>(items + capacity);
+    const int64_t tgt = (int64_t)e_base + row * q64;
+    int r = (int)rows;
+    if (tgt < e_end) {
+      int lo = 0, hi = (int)rows;  // invariant: rowptr[lo] <= tgt < rowptr[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (rowptr[mid] <= tgt) lo = mid; else hi = mid;
+      }
+      r = lo;
+    }
+    wrow[row] = r;
   }
   if (row >= rows) return;
   const int deg = rowptr[row + 1] - rowptr[row];
@@ -515,6 +786,19 @@ static int env_int(const char* name, int dflt) {
 static int long_row_edges() { static int v = env_int("INCAGG_SPMM_LONG_ROW", 64); return v; }
 static int chunk_edges() { static int v = env_int("INCAGG_SPMM_CHUNK", 0); return v; }  // 0 = adaptive
 
+// Stream (merge-path) kernel configuration: variant 0 = ring of 16 gathers, 2 CTAs (16 warps) per SM;
+// 1 = ring of 8, 4 CTAs; 2 = ring of 8, 3 CTAs.  The number of warp slots is one resident wave.
+static int stream_variant() {
+  static int dflt = env_int("INCAGG_SPMM_STREAM", 0);  // -1: row-per-warp kernel everywhere
+  return incagg::tune_get(INCAGG_TUNE_SPMM_STREAM_VARIANT, dflt);
+}
+static int stream_min_f() { return incagg::tune_get(INCAGG_TUNE_SPMM_STREAM_MIN_F, 65); }
+static int stream_ctas_per_sm(int variant) { return variant == 1 ? 4 : (variant == 2 ? 3 : 2); }
+static int stream_wslots() {
+  int n = sm_count() * stream_ctas_per_sm(stream_variant()) * WS_WARPS;
+  return n > WS_MAX_SLOTS ? WS_MAX_SLOTS : n;
+}
+
 // Upper bound of the work items of a structure: one per row longer than LONG_ROW plus the extra
 // chunks of split rows.  nnz < 0 = unknown.
 static int64_t plan_capacity(int64_t rows, int64_t nnz) {
@@ -525,6 +809,9 @@ static int64_t plan_capacity(int64_t rows, int64_t nnz) {
   }
   return long_rows + PLAN_SCRATCH_CAP + 8;
 }
+static size_t plan_bytes_for(int64_t capacity) {
+  return sizeof(SpmmPlan) + sizeof(int4) * (size_t)capacity + sizeof(int32_t) * (WS_MAX_SLOTS + 1);
+}
 
 static int build_plan(const int32_t* rowptr, int64_t rows, void* plan, int64_t capacity,
                       cudaStream_t st) {
@@ -533,9 +820,10 @@ static int build_plan(const int32_t* rowptr, int64_t rows, void* plan, int64_t c
   if (rows == 0) return INCAGG_OK;
   SpmmPlan* hdr = static_cast<SpmmPlan*>(plan);
   int4* items = reinterpret_cast<int4*>(hdr + 1);
-  launch(spmm_plan_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), (size_t)(0), st, rowptr, rows, hdr, items,
-                                                                  long_row_edges(), chunk_edges(),
-                                                                  (int)capacity);
+  const int n_w = stream_wslots();
+  const int64_t threads = rows > n_w + 1 ? rows : n_w + 1;
+  launch(spmm_plan_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), (size_t)(0), st, rowptr, rows, hdr,
+         items, long_row_edges(), chunk_edges(), (int)capacity, n_w);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -544,22 +832,30 @@ struct SpmmScratch {
   float* part_val = nullptr;
   int32_t* part_arg = nullptr;
   int32_t* part_done = nullptr;
+  float* ws_part = nullptr;     // stream kernel: [WS_MAX_TILES][WS_MAX_SLOTS][2][WS_TILE_F]
+  int32_t* ws_done = nullptr;   // [WS_MAX_TILES][WS_MAX_SLOTS]
   void* plan = nullptr;  // temporary plan of calls that pass none
   int64_t plan_capacity = 0;
 };
-// Per-device scratch (allocated once / grown on demand, reused by every call: kernels of one stream
-// serialise).  Concurrent SpMM calls on different streams of one device must not share a thread.
+// Per-device scratch of split rows, shared by all host threads (allocated once / the temporary plan
+// grown on demand).  It is reused by every call, so SpMM launches that use it must be ordered on the
+// device: the Python layer serialises SpMM calls issued on different streams (ops._order_spmm).
 static int get_scratch(SpmmScratch** out, int64_t want_plan_capacity) {
-  static thread_local SpmmScratch scratch[16];
+  static SpmmScratch scratch[16];
+  static std::mutex mu;
   int dev = 0;
   IA_CUDA(cudaGetDevice(&dev));
   IA_CHECK_ARG(dev >= 0 && dev < 16, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
   SpmmScratch& s = scratch[dev];
   if (s.part_val == nullptr) {
     IA_CUDA(cudaMalloc(&s.part_val, sizeof(float) * (size_t)PART_SLOTS * PART_STRIDE));
     IA_CUDA(cudaMalloc(&s.part_arg, sizeof(int32_t) * (size_t)PART_SLOTS * PART_STRIDE));
     IA_CUDA(cudaMalloc(&s.part_done, sizeof(int32_t) * (size_t)PART_SLOTS));
     IA_CUDA(cudaMemset(s.part_done, 0, sizeof(int32_t) * (size_t)PART_SLOTS));
+    IA_CUDA(cudaMalloc(&s.ws_part, sizeof(float) * (size_t)WS_MAX_TILES * WS_MAX_SLOTS * 2 * WS_TILE_F));
+    IA_CUDA(cudaMalloc(&s.ws_done, sizeof(int32_t) * (size_t)WS_MAX_TILES * WS_MAX_SLOTS));
+    IA_CUDA(cudaMemset(s.ws_done, 0, sizeof(int32_t) * (size_t)WS_MAX_TILES * WS_MAX_SLOTS));
   }
   if (want_plan_capacity > s.plan_capacity) {
     int64_t cap = s.plan_capacity ? s.plan_capacity : (1 << 16);
@@ -567,10 +863,48 @@ static int get_scratch(SpmmScratch** out, int64_t want_plan_capacity) {
     if (s.plan) IA_CUDA(cudaFree(s.plan));  // synchronises the device: earlier users are done
     s.plan = nullptr;
     s.plan_capacity = 0;
-    IA_CUDA(cudaMalloc(&s.plan, sizeof(SpmmPlan) + sizeof(int4) * (size_t)cap));
+    IA_CUDA(cudaMalloc(&s.plan, plan_bytes_for(cap)));
     s.plan_capacity = cap;
   }
   *out = &s;
+  return INCAGG_OK;
+}
+
+// Wide sum / mean products through the merge-path kernel.  Returns 1 when the call does not qualify
+// (the caller falls through to the row kernel), an error code, or INCAGG_OK after the launch.
+static int try_stream(SpmmParams& p, int reduce, int vec, cudaStream_t st) {
+  if (stream_variant() < 0) return 1;
+  if (vec != 4 || p.F < stream_min_f() || p.F > WS_TILE_F * WS_MAX_TILES) return 1;
+  if ((reduce != R_SUM && reduce != R_MEAN) || p.arg != nullptr || p.n_id != nullptr) return 1;
+  if (p.rows >= 0x7fffffff || p.ldx >= (1ll << 30) || p.ld_in >= (1ll << 30)) return 1;
+  SpmmScratch* sc = nullptr;
+  const bool own_plan = (p.plan == nullptr);
+  int rc = get_scratch(&sc, own_plan ? plan_capacity(p.rows, -1) : 0);
+  if (rc != INCAGG_OK) return rc;
+  if (own_plan) {
+    rc = build_plan(p.rowptr, p.rows, sc->plan, sc->plan_capacity, st);
+    if (rc != INCAGG_OK) return rc;
+    p.plan = static_cast<const SpmmPlan*>(sc->plan);
+  }
+  p.items = reinterpret_cast<const int4*>(p.plan + 1);
+  p.ws_part = sc->ws_part;
+  p.ws_done = sc->ws_done;
+  p.mean = (reduce == R_MEAN);
+  const int variant = stream_variant();
+  const int n_w = stream_wslots();
+  const int tiles = (p.F + WS_TILE_F - 1) / WS_TILE_F;
+  dim3 grid((unsigned)((n_w + WS_WARPS - 1) / WS_WARPS), (unsigned)tiles);
+  const bool delta = p.m_in != nullptr;
+#define IA_STREAM(D_, MINB_)                                                                         \
+  do {                                                                                               \
+    if (delta) launch(spmm_stream_kernel<(D_) / 2, MINB_, true>, grid, dim3(WS_WARPS * 32), (size_t)(0), st, p); \
+    else launch(spmm_stream_kernel<D_, MINB_, false>, grid, dim3(WS_WARPS * 32), (size_t)(0), st, p);   \
+  } while (0)
+  if (variant == 1) IA_STREAM(8, 4);
+  else if (variant == 2) IA_STREAM(8, 3);
+  else IA_STREAM(16, 2);
+#undef IA_STREAM
+  IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
 
@@ -671,7 +1005,7 @@ using namespace incagg;
 
 extern "C" size_t incagg_spmm_plan_bytes(int64_t rows, int64_t nnz) {
   if (rows < 0) return 0;
-  return sizeof(SpmmPlan) + sizeof(int4) * (size_t)plan_capacity(rows, nnz);
+  return plan_bytes_for(plan_capacity(rows, nnz));
 }
 
 extern "C" int incagg_spmm_plan(const int32_t* rowptr, int64_t rows, int64_t nnz, void* plan,
@@ -680,8 +1014,8 @@ extern "C" int incagg_spmm_plan(const int32_t* rowptr, int64_t rows, int64_t nnz
   IA_CHECK_ARG(plan != nullptr && plan_bytes >= incagg_spmm_plan_bytes(rows, nnz), "plan buffer too small");
   IA_CHECK_ARG(rows == 0 || rowptr != nullptr, "rowptr is NULL");
   IA_CHECK_ARG((reinterpret_cast<uintptr_t>(plan) & 15) == 0, "plan buffer must be 16-byte aligned");
-  return build_plan(rowptr, rows, plan, (int64_t)((plan_bytes - sizeof(SpmmPlan)) / sizeof(int4)),
-                    as_stream(stream));
+  // (the item capacity must be the one plan_bytes was computed for: wrow[] lies behind the items)
+  return build_plan(rowptr, rows, plan, plan_capacity(rows, nnz), as_stream(stream));
 }
 
 static int spmm_csr_impl(int reduce, const int32_t* rowptr, const int32_t* col, const float* val,
@@ -703,6 +1037,8 @@ static int spmm_csr_impl(int reduce, const int32_t* rowptr, const int32_t* col, 
   const int vec = pick_vec(p, F);
   cudaStream_t st = as_stream(stream);
   const int64_t ib = INT64_MAX;
+  rc = try_stream(p, reduce, vec, st);
+  if (rc != 1) return rc;
   switch (reduce) {
     case R_SUM: return dispatch_shape<R_SUM, false, false>(p, F, vec, 1, ib, st);
     case R_MEAN: return dispatch_shape<R_MEAN, false, false>(p, F, vec, 1, ib, st);
@@ -751,6 +1087,8 @@ extern "C" int incagg_spmm_delta(int reduce, const int32_t* rowptr, const int32_
   p.plan = static_cast<const SpmmPlan*>(plan);
   const int vec = pick_vec(p, F);
   cudaStream_t st = as_stream(stream);
+  rc = try_stream(p, reduce, vec, st);
+  if (rc != 1) return rc;
   if (reduce == R_SUM) return dispatch_shape<R_SUM, true, false>(p, F, vec, 1, INT64_MAX, st);
   return dispatch_shape<R_MEAN, true, false>(p, F, vec, 1, INT64_MAX, st);
 }

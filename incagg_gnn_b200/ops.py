@@ -53,6 +53,34 @@ def _ld(t: Tensor) -> int:
 # --------------------------------------------------------------------------------------------
 # SpMM
 # --------------------------------------------------------------------------------------------
+TUNE = {"spmm_stream_variant": 0, "spmm_stream_min_f": 1}
+
+
+def tune(key: str, value: int) -> None:
+    """Experiment knobs of the kernels (include/incagg_b200.h INCAGG_TUNE_*).  Plans built before a
+    knob that changes the warp partition was set must be rebuilt (SparseTensor.drop_caches)."""
+    check(lib.incagg_tune_set(TUNE[key], int(value)))
+
+
+# The SpMM kernels keep the partial sums of rows that are split over several CTAs / warps in one
+# scratch area per device, so two SpMM launches must not run concurrently.  Launches on one stream
+# serialise by themselves; when a call arrives on another stream than the previous one, the new
+# stream first waits for everything issued so far on the old one.  (Inside a CUDA-graph capture the
+# step's SpMMs are all issued on the capturing stream.)
+_SPMM_LAST = {}
+
+
+def _order_spmm() -> None:
+    dev = _cur_dev()
+    st = _raw_stream(dev)
+    last = _SPMM_LAST.get(dev)
+    if last is not None and last != st and not torch.cuda.is_current_stream_capturing():
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.ExternalStream(last, device=dev))
+        torch.cuda.current_stream(dev).wait_event(ev)
+    _SPMM_LAST[dev] = st
+
+
 def spmm_plan(rowptr: Tensor, rows: Optional[int] = None, nnz: int = -1) -> Tensor:
     """Degree-bucket plan of a CSR structure (built once, reused by every SpMM over it)."""
     _require_cuda(rowptr)
@@ -82,6 +110,7 @@ def spmm_raw(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, redu
     if return_arg and reduce in ("min", "max"):
         arg = torch.empty((n_rows, F), dtype=torch.int32, device=x.device)
     LAUNCHES["calls"] += 1
+    _order_spmm()
     if gate is not None:
         if reduce not in ("sum", "mean") or gate.dtype != torch.float32 or gate.dim() != 2 \
                 or gate.stride(1) != 1 or gate.size(0) < n_rows or gate.size(1) < F:
@@ -113,6 +142,7 @@ def spmm_delta_raw(rowptr, col, val, x, m_in, m_ag, n_id=None, reduce="sum", row
     if out is None:
         out = torch.empty((n_rows, F), dtype=torch.float32, device=x.device)
     LAUNCHES["calls"] += 1
+    _order_spmm()
     check(lib.incagg_spmm_delta(REDUCE[reduce], ptr(rowptr), ptr(col), ptr(val), ptr(x), _ld(x),
                                 ptr(m_in), m_in.stride(0), ptr(m_ag), m_ag.stride(0), ptr(n_id),
                                 ptr(out), _ld(out), n_rows, F, ptr(plan), _stream()))
@@ -131,6 +161,7 @@ def spmm_multi_raw(rowptr, col, val, x, F: int, reducers, rows=None, out=None, p
     import ctypes
     red = (ctypes.c_int32 * K)(*[REDUCE[r] for r in reducers])
     LAUNCHES["calls"] += 1
+    _order_spmm()
     check(lib.incagg_spmm_multi(ptr(rowptr), ptr(col), ptr(val), ptr(x), _ld(x), ptr(out), _ld(out),
                                 n_rows, F, K, ctypes.cast(red, ctypes.c_void_p), ptr(plan), _stream()))
     return out

@@ -55,6 +55,13 @@ const char* incagg_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (every entry point counts
  * its own launches; DMA copies issued through cudaMemcpyAsync are not kernels and not counted). */
 int64_t incagg_launch_count(void);
+/* Experiment knobs of the kernels (not part of the reference-facing surface; the defaults are what the
+ * product runs with).  Plans built before a knob that changes the warp partition was set must be
+ * rebuilt. */
+#define INCAGG_TUNE_SPMM_STREAM_VARIANT 0 /* merge-path SpMM: -1 off, 0 ring 16 x 16 warps/SM, 1 ring 8 x 32, 2 ring 8 x 24 */
+#define INCAGG_TUNE_SPMM_STREAM_MIN_F 1   /* smallest feature width routed to the merge-path kernel (65) */
+#define INCAGG_TUNE_COUNT 8
+int incagg_tune_set(int key, int value);
 /* SM count and compute capability of the current device. */
 int incagg_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

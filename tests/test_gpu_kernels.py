@@ -107,6 +107,88 @@ def test_spmm_relu_input_backward_matches_separate_mask(cuda):
         assert torch.equal(xa.grad[:rows], want)
 
 
+def _csr_from_deg(rng, deg, cols):
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    col = rng.integers(0, cols, rowptr[-1]).astype(np.int64)
+    val = rng.standard_normal(rowptr[-1]).astype(np.float32)
+    return rowptr, col, val
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("F", [68, 128, 200, 602])
+def test_spmm_merge_path_kernel_edge_cases(ops, cuda, variant, F):
+    """The merge-path (edge stream) kernel that serves wide sum / mean products: rows cut by piece
+    boundaries, one row that spans many pieces, empty rows at the front / between / at the end and at
+    piece boundaries, pieces of exactly 32 edges, a structure without edges, unweighted edges, a gate,
+    the delta form - against the fp64 oracle, and bit-identical from run to run (deterministic)."""
+    ops.tune("spmm_stream_variant", variant)
+    try:
+        rng = np.random.default_rng(1000 * variant + F)
+        cols = 3000
+        X = rng.standard_normal((cols, F)).astype(np.float32)
+        Xd = _dev(X, cuda)
+        shapes = {
+            "ragged": np.concatenate([[0, 0, 0], rng.integers(0, 40, 4000), [0, 0]]),
+            "giant": np.concatenate([rng.integers(0, 6, 50), [150000], rng.integers(0, 6, 50), [0]]),
+            "all_32": np.full(6000, 32),
+            "tiny": np.array([0, 3, 0, 1, 0]),
+            "one_row": np.array([70000]),
+            "sparse_rows": (rng.random(20000) < 0.02).astype(np.int64) * 50,
+        }
+        for name, deg in shapes.items():
+            rowptr, col, val = _csr_from_deg(rng, deg, cols)
+            rp, c, v = _dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32), _dev(val, cuda)
+            for reduce, vv, vd in (("sum", val, v), ("mean", None, None)):
+                out = ops.spmm_raw(rp, c, vd, Xd, reduce)
+                ref = oracle.spmm(rowptr, col, vv, X, reduce, dtype=np.float64)
+                assert _rel_err(out.cpu().numpy(), ref) <= RTOL, (name, reduce)
+                again = ops.spmm_raw(rp, c, vd, Xd, reduce)
+                assert torch.equal(out, again), (name, reduce, "not deterministic")
+            # gate in the epilogue = masking the plain result
+            rows = len(deg)
+            gate = _dev(rng.standard_normal((rows, F)).astype(np.float32), cuda)
+            plain = ops.spmm_raw(rp, c, v, Xd, "sum")
+            assert torch.equal(ops.spmm_raw(rp, c, v, Xd, "sum", gate=gate),
+                               torch.where(gate > 0, plain, torch.zeros_like(plain))), name
+        # no edges at all
+        z = ops.spmm_raw(torch.zeros(41, dtype=torch.int32, device=cuda),
+                         torch.zeros(0, dtype=torch.int32, device=cuda), None, Xd, "sum")
+        assert z.shape == (40, F) and float(z.abs().max()) == 0.
+        # delta form on a square in-batch structure
+        B = 2500
+        rowptr, col, val = _csr_from_deg(rng, np.concatenate([[0], rng.integers(0, 60, B - 2), [0]]), B)
+        m_in = rng.standard_normal((B, F)).astype(np.float32)
+        m_ag = rng.standard_normal((B, F)).astype(np.float32)
+        got = ops.spmm_delta_raw(_dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32), _dev(val, cuda),
+                                 _dev(X[:B], cuda), _dev(m_in, cuda), _dev(m_ag, cuda), None, "sum")
+        ref = oracle.spmm_delta(rowptr, col, val, X[:B], m_in, m_ag, "sum", dtype=np.float64)
+        assert _rel_err(got.cpu().numpy(), ref) <= RTOL
+    finally:
+        ops.tune("spmm_stream_variant", 0)
+
+
+def test_spmm_merge_path_equals_row_kernel_on_a_products_sized_batch(ops, cuda):
+    """Both SpMM kernels on one full-size C3-like batch (16 K rows, ~0.4 M edges, F = 128): equal to
+    rounding, each equal to the fp64 oracle within 1e-5."""
+    rng = np.random.default_rng(3)
+    B, R, F = 16327, 62000, 128
+    deg = np.minimum(rng.zipf(1.6, B) + 8, 900)
+    rowptr, col, val = _csr_from_deg(rng, deg, R)
+    val = np.abs(val) * 0.1
+    X = rng.standard_normal((R, F)).astype(np.float32)
+    rp, c, v, Xd = _dev(rowptr, cuda, torch.int32), _dev(col, cuda, torch.int32), _dev(val, cuda), _dev(X, cuda)
+    ref = oracle.spmm(rowptr, col, val, X, "sum", dtype=np.float64)
+    outs = {}
+    try:
+        for variant in (-1, 0):
+            ops.tune("spmm_stream_variant", variant)
+            outs[variant] = ops.spmm_raw(rp, c, v, Xd, "sum").cpu().numpy()
+            assert _rel_err(outs[variant], ref) <= RTOL
+    finally:
+        ops.tune("spmm_stream_variant", 0)
+    assert _rel_err(outs[0], outs[-1].astype(np.float64)) <= 1e-6
+
+
 @pytest.mark.parametrize("has_val", [True, False])
 def test_spmm_without_values_and_empty(ops, cuda, has_val):
     rng = np.random.default_rng(11)
