@@ -480,121 +480,108 @@ spmm_kernel(const SpmmParams p) {
 
 // ---- merge-path kernel for wide sum / mean products ---------------------------------------------
 //
-// The row-per-warp kernel above leaves the memory system idle at every row end (a 26-edge row is six
-// rounds of four gathers plus a serial remainder, and a new row starts with two dependent index
-// loads), and rows of very different lengths make the tail of a batch-sized launch long.  Here the
-// EDGE array is the unit of scheduling (merge-path SpMM): warp slot w owns the `q` consecutive edges
-// [e_base + w q, e_base + (w + 1) q) whatever rows they belong to, the grid is one resident wave, so
-// every warp does the same amount of work and finishes at the same time.  Inside its piece a warp
-//   * fetches col / val in coalesced blocks of 32 edges, two blocks ahead (lane i keeps edge i of
-//     the block; consumers read them with shuffles);
+// The row-per-warp kernel above spends ~30 instructions per edge, leaves the memory system idle at
+// every row end (a 26-edge row is six rounds of four gathers plus a serial remainder, and a new row
+// starts with two dependent index loads), and rows of very different lengths make the tail of a
+// batch-sized launch long.  Here the EDGE array is the unit of scheduling (merge-path SpMM): warp
+// slot w owns the `q` consecutive edges [e_base + w q, e_base + (w + 1) q) whatever rows they belong
+// to, the grid is one resident wave, so every warp does the same amount of work and finishes at the
+// same time.  Inside its piece a warp
+//   * stages (col, val) pairs in a 128-entry shared-memory ring, fetched in coalesced blocks of 32
+//     edges three blocks ahead; a consumer reads its pair with one broadcast LDS.64;
 //   * keeps a ring of D independent 128-bit gathers of X rows in flight (one 512-byte row segment
 //     per warp instruction): the load of edge j + D is issued right after edge j has been consumed,
-//     across row boundaries, so the ring never drains (D = 16 -> 8 KB in flight per warp, 128 KB per
-//     SM with 16 resident warps);
-//   * walks the rows its edges belong to through a 64-entry register window of rowptr (refilled a
-//     window ahead) and writes a row as soon as its last edge is consumed.
+//     across row boundaries, so the ring never drains (~10 instructions per edge);
+//   * walks the rows its edges belong to through a 64-entry shared-memory window of rowptr (refilled
+//     32 rows ahead) and writes a row as soon as its last edge is consumed.
 // Rows cut by a piece boundary: every piece that holds a part of the row stores its partial sum
-// (head part = slot 0, tail part = slot 1 of the warp), bumps the arrival counter of the row's first
-// piece, and the last one to arrive adds the partials IN PIECE ORDER and writes the row - wait-free,
-// and independent of scheduling (deterministic).  Empty rows are written (as zeros, plus M_ag for the
-// delta form) by the piece that passes over them.
+// (head part = slot 0, tail part = slot 1 of the warp) when it has finished its piece, bumps the
+// arrival counter of the row's first piece, and the last one to arrive adds the partials IN PIECE
+// ORDER and writes the row - wait-free, and independent of scheduling (deterministic).  Empty rows
+// are written (as zeros, plus M_ag for the delta form) by the piece that passes over them.
 struct WsHeader {
   int n_w, q, e_base, e_end, capacity;
 };
-// What the row epilogue needs, by value (taking the address of the kernel's parameter struct would
-// copy it to local memory).
-struct WsOut {
-  float* out;
-  const float* m_ag;
-  const float* gate;
-  float* ws_part;
-  int32_t* ws_done;
-  int64_t ldo, ld_ag, ld_gate;
-  int mean;
-};
 
-__device__ __forceinline__ void ws_finish(const WsOut& o, int row, int deg, float4 a, int f, bool fok) {
+__device__ __forceinline__ void ws_finish(const SpmmParams& p, int row, int deg, float4 a, int f, bool fok) {
   if (!fok) return;
-  if (o.mean) {
+  if (p.mean) {
     const float inv = 1.f / (float)max(deg, 1);
     a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
   }
-  if (o.m_ag != nullptr) {
-    const float4 m = __ldg(reinterpret_cast<const float4*>(o.m_ag + (int64_t)row * o.ld_ag + f));
+  if (p.m_ag != nullptr) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(p.m_ag + (int64_t)row * p.ld_ag + f));
     a.x += m.x; a.y += m.y; a.z += m.z; a.w += m.w;
   }
-  if (o.gate != nullptr) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(o.gate + (int64_t)row * o.ld_gate + f));
+  if (p.gate != nullptr) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + (int64_t)row * p.ld_gate + f));
     a.x = g.x > 0.f ? a.x : 0.f; a.y = g.y > 0.f ? a.y : 0.f;
     a.z = g.z > 0.f ? a.z : 0.f; a.w = g.w > 0.f ? a.w : 0.f;
   }
-  *reinterpret_cast<float4*>(o.out + (int64_t)row * o.ldo + f) = a;
+  *reinterpret_cast<float4*>(p.out + (int64_t)row * p.ldo + f) = a;
 }
 
-// A row whose last edge has been consumed (or the last row of the piece).  Rows that lie inside the
-// piece are written; of a row cut by a piece boundary this piece's partial is stored and the last
-// piece to arrive combines them.  Not inlined: it is called from every slot of the unrolled ring.
-__device__ __noinline__ void ws_row_done(const WsOut o, const WsHeader h, int w, int tile, int row, int rs,
-                                         int re, int e0, int e1, float4 a, int f, bool fok) {
-  if (rs >= e0 && re <= e1) {
-    ws_finish(o, row, re - rs, a, f, fok);
-    return;
-  }
+// Part of a row that is cut by a piece boundary.  The partial sum is already in the warp's slot
+// (slot 0 = head part of a row that started in an earlier piece, slot 1 = tail / middle part); here,
+// at the end of the piece, it is published: the arrival counter of the row's first piece is bumped
+// and the last piece to arrive adds the partials in piece order and writes the row.
+__device__ __noinline__ void ws_publish(const SpmmParams& p, int w, int tile, int row, int f, bool fok) {
   const int lane = threadIdx.x & 31;
-  const int first = (rs - h.e_base) / h.q, last = (re - 1 - h.e_base) / h.q;
-  const int which = (w == first) ? 1 : 0;
-  const int64_t tbase = (int64_t)tile * h.n_w;
-  float* part = o.ws_part + ((tbase + w) * 2 + which) * WS_TILE_F + lane * 4;
-  *reinterpret_cast<float4*>(part) = a;
+  const int4 h1 = __ldg(reinterpret_cast<const int4*>(p.plan) + 1);  // capacity, n_wslots, q, e_base
+  const int n_w = h1.y, q = h1.z, e_base = h1.w;
+  const int rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
+  const int first = (rs - e_base) / q, last = (re - 1 - e_base) / q;
+  const int64_t tbase = (int64_t)tile * n_w;
   __threadfence();
   int prev = 0;
-  if (lane == 0) prev = atomicAdd(o.ws_done + tbase + first, 1);
+  if (lane == 0) prev = atomicAdd(p.ws_done + tbase + first, 1);
   prev = __shfl_sync(0xffffffffu, prev, 0);
   if (prev != last - first) return;
   __threadfence();
-  float4 s = __ldcg(reinterpret_cast<const float4*>(o.ws_part + ((tbase + first) * 2 + 1) * WS_TILE_F + lane * 4));
+  float4 s = __ldcg(reinterpret_cast<const float4*>(p.ws_part + ((tbase + first) * 2 + 1) * WS_TILE_F + lane * 4));
   for (int ww = first + 1; ww <= last; ++ww) {
-    const float4 t = __ldcg(reinterpret_cast<const float4*>(o.ws_part + ((tbase + ww) * 2) * WS_TILE_F + lane * 4));
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(p.ws_part + ((tbase + ww) * 2) * WS_TILE_F + lane * 4));
     s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
   }
-  if (lane == 0) o.ws_done[tbase + first] = 0;  // clean for the next call
-  ws_finish(o, row, re - rs, s, f, fok);
+  if (lane == 0) p.ws_done[tbase + first] = 0;  // clean for the next call
+  ws_finish(p, row, re - rs, s, f, fok);
 }
 
 template <int D, int MINB, bool DELTA>
 __global__ void __launch_bounds__(WS_WARPS * 32, MINB)
-spmm_stream_kernel(const SpmmParams p) {
+spmm_stream_kernel(const __grid_constant__ SpmmParams p) {
   pdl_prologue();
-  constexpr unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * WS_WARPS + (threadIdx.x >> 5);
-  const int tile = blockIdx.y;
-  const int f = tile * WS_TILE_F + lane * 4;
+  __shared__ int s_c[WS_WARPS][128];    // col of 4 index blocks of 32 edges
+  __shared__ float s_v[WS_WARPS][128];  // val
+  __shared__ int s_rp[WS_WARPS][64];    // rowptr window
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int w = blockIdx.x * WS_WARPS + wi;
+  const int f = blockIdx.y * WS_TILE_F + lane * 4;
   const bool fok = f < p.F;
-  const int4 h1 = __ldg(reinterpret_cast<const int4*>(p.plan) + 1);  // capacity, n_wslots, q, e_base
-  const int4 h2 = __ldg(reinterpret_cast<const int4*>(p.plan) + 2);  // e_end
-  WsHeader h;
-  h.capacity = h1.x; h.n_w = h1.y; h.q = h1.z; h.e_base = h1.w; h.e_end = h2.x;
   const int rows = (int)p.rows;
-  if (w >= h.n_w) return;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  WsOut o;
-  o.out = p.out; o.m_ag = p.m_ag; o.gate = p.gate; o.ws_part = p.ws_part; o.ws_done = p.ws_done;
-  o.ldo = p.ldo; o.ld_ag = p.ld_ag; o.ld_gate = p.ld_gate; o.mean = p.mean;
-  if (h.e_base == h.e_end) {  // a structure without edges: every row is empty
-    for (int r = w; r < rows; r += h.n_w) ws_finish(o, r, 0, zero4, f, fok);
-    return;
+  int e0, e1;
+  float* my_part;  // this warp's two partial-row slots
+  {
+    const int4 h1 = __ldg(reinterpret_cast<const int4*>(p.plan) + 1);  // capacity, n_wslots, q, e_base
+    const int4 h2 = __ldg(reinterpret_cast<const int4*>(p.plan) + 2);  // e_end
+    if (w >= h1.y) return;
+    if (h1.w == h2.x) {  // a structure without edges: every row is empty
+      for (int r = w; r < rows; r += h1.y) ws_finish(p, r, 0, zero4, f, fok);
+      return;
+    }
+    e0 = h1.w + w * h1.z;
+    if (e0 >= h2.x) return;
+    e1 = min(e0 + h1.z, h2.x);
+    my_part = p.ws_part + (((int64_t)blockIdx.y * h1.y + w) * 2) * WS_TILE_F + lane * 4;
   }
-  const int e0 = h.e_base + w * h.q;
-  if (e0 >= h.e_end) return;
-  const int e1 = min(e0 + h.q, h.e_end);
+  int* sc = s_c[wi];
+  float* sv = s_v[wi];
+  int* rpw = s_rp[wi];
 
-  // col / val blocks: lane i holds edge (block start + i); blocks 0, 1, 2 of the piece
-  int c0, c1, c2;
-  float v0, v1, v2;
-  auto load_blk = [&](int start, int& c, float& v) {
-    const int idx = start + lane;
+  // index blocks: block b = edges [e0 + 32 b, e0 + 32 b + 32), ring position (32 b + lane) & 127
+  auto ld_blk = [&](int b, int& c, float& v) {
+    const int idx = e0 + b * 32 + lane;
     c = 0;
     v = 0.f;
     if (idx < e1) {
@@ -602,102 +589,127 @@ spmm_stream_kernel(const SpmmParams p) {
       v = p.val ? ldg_stream(p.val + idx) : 1.f;
     }
   };
-  load_blk(e0, c0, v0);
-  load_blk(e0 + 32, c1, v1);
-  load_blk(e0 + 64, c2, v2);
-  const int* wrow = reinterpret_cast<const int*>(p.items + h.capacity);
-  int r = __ldg(wrow + w);  // the row that holds edge e0
-  // rowptr window: lane i holds rowptr[rwin + i] (cur) and rowptr[rwin + 32 + i] (nxt)
-  int rwin = r;
-  int rp_cur = __ldg(p.rowptr + min(rwin + lane, rows));
-  int rp_nxt = __ldg(p.rowptr + min(rwin + 32 + lane, rows));
-  auto win = [&](int i) {  // rowptr[rwin + i], 0 <= i < 64
-    const int a = __shfl_sync(FULL, rp_cur, i & 31), b = __shfl_sync(FULL, rp_nxt, i & 31);
-    return i < 32 ? a : b;
-  };
+  int r, rbase, rp_pre, cn;
+  float vn;
+  {
+    int c1, c2;
+    float v1, v2;
+    ld_blk(0, cn, vn);
+    ld_blk(1, c1, v1);
+    ld_blk(2, c2, v2);
+    const int capacity = __ldg(reinterpret_cast<const int*>(p.plan) + 4);
+    r = __ldg(reinterpret_cast<const int*>(p.items + capacity) + w);  // wrow[w]: the row that holds edge e0
+    // rowptr window: the ring holds rowptr[rbase .. rbase + 63], rp_pre the next 32 entries
+    rbase = r;
+    const int rp_a = __ldg(p.rowptr + min(rbase + lane, rows));
+    const int rp_b = __ldg(p.rowptr + min(rbase + 32 + lane, rows));
+    rp_pre = __ldg(p.rowptr + min(rbase + 64 + lane, rows));
+    sc[lane] = cn; sv[lane] = vn;
+    sc[32 + lane] = c1; sv[32 + lane] = v1;
+    sc[64 + lane] = c2; sv[64 + lane] = v2;
+    ld_blk(3, cn, vn);  // stays in registers until block 0 has been consumed
+    rpw[(rbase + lane) & 63] = rp_a;
+    rpw[(rbase + 32 + lane) & 63] = rp_b;
+  }
+  __syncwarp();
 
   // row c of X / M_in starts at byte c * row_bytes (< 2^32, checked by the host): one IMAD.WIDE.U32
   // (lanes past F in the last tile gather column 0 instead - unconditional loads - and never store)
-  const int f_ld = fok ? f : 0;
-  const char* Xb = reinterpret_cast<const char*>(p.X + f_ld);
-  const char* Mb = DELTA ? reinterpret_cast<const char*>(p.m_in + f_ld) : nullptr;
+  const char* Xb = reinterpret_cast<const char*>(p.X + (fok ? f : 0));
+  const char* Mb = DELTA ? reinterpret_cast<const char*>(p.m_in + (fok ? f : 0)) : nullptr;
   const unsigned x_bytes = (unsigned)p.ldx * 4u, m_bytes = DELTA ? (unsigned)p.ld_in * 4u : 0u;
   float4 x[D];
   float4 m[DELTA ? D : 1];
-  auto issue = [&](int c, int slot) {
-    x[slot] = __ldg(reinterpret_cast<const float4*>(Xb + (size_t)(unsigned)c * x_bytes));
-    if constexpr (DELTA) m[slot] = __ldg(reinterpret_cast<const float4*>(Mb + (size_t)(unsigned)c * m_bytes));
+  auto issue = [&](int pos, int slot) {  // gather of the edge at ring position `pos`
+    const unsigned c = (unsigned)sc[pos & 127];
+    x[slot] = __ldg(reinterpret_cast<const float4*>(Xb + (size_t)c * x_bytes));
+    if constexpr (DELTA) m[slot] = __ldg(reinterpret_cast<const float4*>(Mb + (size_t)c * m_bytes));
   };
 #pragma unroll
   for (int u = 0; u < D; ++u) {
     x[u] = zero4;
     if constexpr (DELTA) m[u] = zero4;
   }
-  // prologue: the first D gathers (D <= 32: all in block 0)
+  // prologue: the first D gathers
 #pragma unroll
-  for (int u = 0; u < D; ++u) {
-    const int c = __shfl_sync(FULL, c0, u);
-    if (e0 + u < e1) issue(c, u);
-  }
+  for (int u = 0; u < D; ++u)
+    if (e0 + u < e1) issue(u, u);
   if (w == 0)  // empty rows in front of the first edge
-    for (int rr = 0; rr < r; ++rr) ws_finish(o, rr, 0, zero4, f, fok);
-  int row_start = win(0), row_end = win(1);
+    for (int rr = 0; rr < r; ++rr) ws_finish(p, rr, 0, zero4, f, fok);
+  int row_start = rpw[r & 63], row_end = rpw[(r + 1) & 63];
+  const bool head_cut = row_start < e0;  // the first row started in an earlier piece
   float4 acc = zero4;
   auto next_row = [&]() {
     ++r;
-    if (r - rwin >= 32) {  // slide the window
-      rwin += 32;
-      rp_cur = rp_nxt;
-      rp_nxt = __ldg(p.rowptr + min(rwin + 32 + lane, rows));
+    if (r - rbase >= 32) {  // slide the window: entries [rbase, rbase + 32) are no longer needed
+      rpw[(rbase + 64 + lane) & 63] = rp_pre;
+      rbase += 32;
+      rp_pre = __ldg(p.rowptr + min(rbase + 64 + lane, rows));
+      __syncwarp();
     }
     row_start = row_end;
-    row_end = win(r + 1 - rwin);
+    row_end = rpw[(r + 1) & 63];
   };
-  // One block of 32 edges starting at jb (block 0 of the index registers).  LAST = the piece ends in
-  // this block: only then the end of the piece has to be tested per edge (q is a multiple of 32, so
-  // every other block is full and its refills stay inside the piece).
-  auto do_block = [&](int jb, auto last_tag) {
+  auto row_done = [&]() {  // the last edge of row r has been consumed (the row ends inside this piece)
+    if (row_start >= e0) ws_finish(p, r, row_end - row_start, acc, f, fok);
+    else *reinterpret_cast<float4*>(my_part) = acc;  // head part, published at the end of the piece
+    acc = zero4;
+    next_row();
+  };
+  // One group of D edges starting at j (ring slot u = edge j + u).  LAST: the piece ends within the
+  // next two groups, so the end of the piece is tested per edge.
+  auto do_group = [&](int j, auto last_tag) {
     constexpr bool LAST = decltype(last_tag)::value;
 #pragma unroll
-    for (int u = 0; u < 32; ++u) {
-      const int jj = jb + u;
+    for (int u = 0; u < D; ++u) {
+      const int jj = j + u;
       if (!LAST || jj < e1) {  // uniform
-        while (jj >= row_end) {  // the last edge of the current row has been consumed
-          ws_row_done(o, h, w, tile, r, row_start, row_end, e0, e1, acc, f, fok);
-          acc = zero4;
-          next_row();
-        }
-        const float v = __shfl_sync(FULL, v0, u);
-        const int s = u % D;
+        while (jj >= row_end) row_done();
+        const float v = sv[(jj - e0) & 127];
         if constexpr (DELTA) {
-          acc.x = fmaf(v, x[s].x - m[s].x, acc.x); acc.y = fmaf(v, x[s].y - m[s].y, acc.y);
-          acc.z = fmaf(v, x[s].z - m[s].z, acc.z); acc.w = fmaf(v, x[s].w - m[s].w, acc.w);
+          acc.x = fmaf(v, x[u].x - m[u].x, acc.x); acc.y = fmaf(v, x[u].y - m[u].y, acc.y);
+          acc.z = fmaf(v, x[u].z - m[u].z, acc.z); acc.w = fmaf(v, x[u].w - m[u].w, acc.w);
         } else {
-          acc.x = fmaf(v, x[s].x, acc.x); acc.y = fmaf(v, x[s].y, acc.y);
-          acc.z = fmaf(v, x[s].z, acc.z); acc.w = fmaf(v, x[s].w, acc.w);
+          acc.x = fmaf(v, x[u].x, acc.x); acc.y = fmaf(v, x[u].y, acc.y);
+          acc.z = fmaf(v, x[u].z, acc.z); acc.w = fmaf(v, x[u].w, acc.w);
         }
-        // refill the ring slot with the gather of edge jj + D
-        const int c = (u + D < 32) ? __shfl_sync(FULL, c0, (u + D) & 31) : __shfl_sync(FULL, c1, (u + D) & 31);
-        if (!LAST || jj + D < e1) issue(c, s);
+        if (!LAST || jj + D < e1) issue(jj + D - e0, u);  // refill the slot with edge jj + D
       }
     }
   };
-  for (int jb = e0; jb < e1; jb += 32) {
-    if (jb + 32 + D <= e1) do_block(jb, std::false_type{});
-    else do_block(jb, std::true_type{});
-    c0 = c1; v0 = v1;  // rotate the index blocks, fetch the block three ahead
-    c1 = c2; v1 = v2;
-    load_blk(jb + 96, c2, v2);
+  for (int j = e0; j < e1; j += D) {
+    const int off = j - e0;
+    if ((off & 31) == 0 && off != 0) {
+      // block off/32 - 1 is consumed: its ring slot takes the block held in registers (three ahead)
+      const int b = (off >> 5) + 2;
+      sc[(b * 32 + lane) & 127] = cn;
+      sv[(b * 32 + lane) & 127] = vn;
+      ld_blk(b + 1, cn, vn);
+      __syncwarp();
+    }
+    if (j + 2 * D <= e1) do_group(j, std::false_type{});
+    else do_group(j, std::true_type{});
   }
-  // the row of the last edge: complete if it ends exactly here, else a tail (or middle) part
-  ws_row_done(o, h, w, tile, r, row_start, row_end, e0, e1, acc, f, fok);
+  // the row of the last edge: complete if it lies inside the piece, else a tail (or middle) part
+  const bool tail_inside = row_end <= e1 && row_start >= e0;
+  const int t_row = r;
+  if (tail_inside) ws_finish(p, r, row_end - row_start, acc, f, fok);
+  else *reinterpret_cast<float4*>(my_part + (row_start >= e0 ? WS_TILE_F : 0)) = acc;
   // empty rows that follow, up to the first row the next piece starts in
   if (row_end <= e1) {
     while (r + 1 < rows) {
       next_row();
       if (row_end > e1) break;
-      ws_finish(o, r, 0, zero4, f, fok);
+      ws_finish(p, r, 0, zero4, f, fok);
     }
+  }
+  // publish the parts of cut rows (the head part only if that row also ended inside this piece;
+  // a row that covers the whole piece is the "tail" case above with slot 0)
+  if (head_cut || !tail_inside) {
+    const int capacity = __ldg(reinterpret_cast<const int*>(p.plan) + 4);
+    const int r0 = __ldg(reinterpret_cast<const int*>(p.items + capacity) + w);
+    if (head_cut && (r0 != t_row || tail_inside)) ws_publish(p, w, blockIdx.y, r0, f, fok);
+    if (!tail_inside) ws_publish(p, w, blockIdx.y, t_row, f, fok);
   }
 }
 
@@ -787,13 +799,16 @@ static int long_row_edges() { static int v = env_int("INCAGG_SPMM_LONG_ROW", 64)
 static int chunk_edges() { static int v = env_int("INCAGG_SPMM_CHUNK", 0); return v; }  // 0 = adaptive
 
 // Stream (merge-path) kernel configuration: variant 0 = ring of 16 gathers, 2 CTAs (16 warps) per SM;
-// 1 = ring of 8, 4 CTAs; 2 = ring of 8, 3 CTAs.  The number of warp slots is one resident wave.
+// 1 = ring of 8, 4 CTAs; 2 = ring of 8, 3 CTAs; 3 = ring of 4, 5 CTAs; 4 = ring of 4, 6 CTAs.  The
+// number of warp slots is one resident wave.
 static int stream_variant() {
   static int dflt = env_int("INCAGG_SPMM_STREAM", 0);  // -1: row-per-warp kernel everywhere
   return incagg::tune_get(INCAGG_TUNE_SPMM_STREAM_VARIANT, dflt);
 }
 static int stream_min_f() { return incagg::tune_get(INCAGG_TUNE_SPMM_STREAM_MIN_F, 65); }
-static int stream_ctas_per_sm(int variant) { return variant == 1 ? 4 : (variant == 2 ? 3 : 2); }
+static int stream_ctas_per_sm(int variant) {
+  return variant == 1 ? 4 : (variant == 2 ? 3 : (variant == 3 ? 5 : (variant == 4 ? 6 : 2)));
+}
 static int stream_wslots() {
   int n = sm_count() * stream_ctas_per_sm(stream_variant()) * WS_WARPS;
   return n > WS_MAX_SLOTS ? WS_MAX_SLOTS : n;
@@ -902,6 +917,8 @@ static int try_stream(SpmmParams& p, int reduce, int vec, cudaStream_t st) {
   } while (0)
   if (variant == 1) IA_STREAM(8, 4);
   else if (variant == 2) IA_STREAM(8, 3);
+  else if (variant == 3) IA_STREAM(4, 5);
+  else if (variant == 4) IA_STREAM(4, 6);
   else IA_STREAM(16, 2);
 #undef IA_STREAM
   IA_LAUNCH_CHECK();

@@ -78,11 +78,22 @@ def test_spmm_gated_epilogue(ops, cuda, reduce, F):
     plain = ops.spmm_raw(rp, c, v, X, reduce)
     gated = ops.spmm_raw(rp, c, v, X, reduce, gate=gate)
     want = torch.where(gate > 0, plain, torch.zeros_like(plain))
-    assert torch.equal(gated, want)
+    # (the unaligned gate view selects the 8-byte-vector kernel, the plain call may run the merge-path
+    # kernel: same zero pattern, values equal to rounding)
+    assert torch.equal(gated == 0, want == 0)
+    assert float((gated - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    # same layout for both calls -> the same kernel -> bit-identical
+    gate_al = gate.contiguous() if F % 4 == 0 else gate
+    gated2 = ops.spmm_raw(rp, c, v, X, reduce, gate=gate_al)
+    if F % 4 == 0:
+        assert torch.equal(gated2, want)
     # first 100 rows only, into a slice of a larger buffer (the backward over the in-batch rows)
     buf = torch.full((300, F), 7.0, device=cuda)
-    ops.spmm_raw(rp[:101], c, v, X, reduce, rows=100, out=buf[:100], gate=gate)
-    assert torch.equal(buf[:100], want[:100]) and float(buf[100:].min()) == 7.0
+    ops.spmm_raw(rp[:101], c, v, X, reduce, rows=100, out=buf[:100], gate=gate_al)
+    plain100 = ops.spmm_raw(rp[:101], c, v, X, reduce, rows=100)
+    assert torch.equal(buf[:100], torch.where(gate_al[:100] > 0, plain100, torch.zeros_like(plain100)))
+    assert float(buf[100:].min()) == 7.0
+    assert float((buf[:100] - want[:100]).abs().max()) <= 1e-5 * float(want.abs().max())
 
 
 def test_spmm_relu_input_backward_matches_separate_mask(cuda):
@@ -114,7 +125,7 @@ def _csr_from_deg(rng, deg, cols):
     return rowptr, col, val
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("F", [68, 128, 200, 602])
 def test_spmm_merge_path_kernel_edge_cases(ops, cuda, variant, F):
     """The merge-path (edge stream) kernel that serves wide sum / mean products: rows cut by piece

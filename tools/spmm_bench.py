@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-VARIANTS = {"rows": -1, "stream16x2": 0, "stream8x4": 1, "stream8x3": 2}
+VARIANTS = {"rows": -1, "stream16x2": 0, "stream8x4": 1, "stream8x3": 2, "stream4x5": 3, "stream4x6": 4}
 
 
 def main():
@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--batches", type=int, default=12)
     ap.add_argument("--batch-parts", type=int, default=1)
     ap.add_argument("--cases", default="fwd,bwd,delta,full")
-    ap.add_argument("--variants", default="rows,stream16x2,stream8x4,stream8x3")
+    ap.add_argument("--variants", default="rows,stream16x2,stream8x4,stream8x3,stream4x5,stream4x6")
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     import incagg_gnn_b200 as tga
