@@ -489,9 +489,9 @@ spmm_kernel(const SpmmParams p) {
 // same time.  Inside its piece a warp
 //   * stages (col, val) pairs in a 128-entry shared-memory ring, fetched in coalesced blocks of 32
 //     edges three blocks ahead; a consumer reads its pair with one broadcast LDS.64;
-//   * keeps a ring of D independent 128-bit gathers of X rows in flight (one 512-byte row segment
-//     per warp instruction): the load of edge j + D is issued right after edge j has been consumed,
-//     across row boundaries, so the ring never drains (~10 instructions per edge);
+//   * keeps two register buffers of D independent 128-bit gathers of X rows (one 512-byte row segment
+//     per warp instruction): while one buffer is consumed the other is in flight, and a consumed
+//     buffer is refilled at once - across row boundaries, so the pipeline never drains;
 //   * walks the rows its edges belong to through a 64-entry shared-memory window of rowptr (refilled
 //     32 rows ahead) and writes a row as soon as its last edge is consumed.
 // Rows cut by a piece boundary: every piece that holds a part of the row stores its partial sum
@@ -618,22 +618,26 @@ spmm_stream_kernel(const __grid_constant__ SpmmParams p) {
   const char* Xb = reinterpret_cast<const char*>(p.X + (fok ? f : 0));
   const char* Mb = DELTA ? reinterpret_cast<const char*>(p.m_in + (fok ? f : 0)) : nullptr;
   const unsigned x_bytes = (unsigned)p.ldx * 4u, m_bytes = DELTA ? (unsigned)p.ld_in * 4u : 0u;
-  float4 x[D];
-  float4 m[DELTA ? D : 1];
-  auto issue = [&](int pos, int slot) {  // gather of the edge at ring position `pos`
+  // Two register buffers of D gathers each: while buffer A is consumed, buffer B is in flight, and A
+  // is refilled as soon as it has been consumed (batches, not a rolling ring: the hardware tracks
+  // outstanding loads with a few counting scoreboards, so "wait for the oldest of D loads" would wait
+  // for all of them).
+  float4 xa[D], xb[D];
+  float4 ma[DELTA ? D : 1], mb[DELTA ? D : 1];
+  auto gather = [&](int pos, float4& xo, float4& mo) {  // gather of the edge at ring position `pos`
     const unsigned c = (unsigned)sc[pos & 127];
-    x[slot] = __ldg(reinterpret_cast<const float4*>(Xb + (size_t)c * x_bytes));
-    if constexpr (DELTA) m[slot] = __ldg(reinterpret_cast<const float4*>(Mb + (size_t)c * m_bytes));
+    xo = __ldg(reinterpret_cast<const float4*>(Xb + (size_t)c * x_bytes));
+    if constexpr (DELTA) mo = __ldg(reinterpret_cast<const float4*>(Mb + (size_t)c * m_bytes));
   };
 #pragma unroll
   for (int u = 0; u < D; ++u) {
-    x[u] = zero4;
-    if constexpr (DELTA) m[u] = zero4;
+    xa[u] = zero4; xb[u] = zero4;
+    if constexpr (DELTA) { ma[u] = zero4; mb[u] = zero4; }
   }
   // prologue: the first D gathers
 #pragma unroll
   for (int u = 0; u < D; ++u)
-    if (e0 + u < e1) issue(u, u);
+    if (e0 + u < e1) gather(u, xa[u], ma[DELTA ? u : 0]);
   if (w == 0)  // empty rows in front of the first edge
     for (int rr = 0; rr < r; ++rr) ws_finish(p, rr, 0, zero4, f, fok);
   int row_start = rpw[r & 63], row_end = rpw[(r + 1) & 63];
@@ -656,28 +660,38 @@ spmm_stream_kernel(const __grid_constant__ SpmmParams p) {
     acc = zero4;
     next_row();
   };
-  // One group of D edges starting at j (ring slot u = edge j + u).  LAST: the piece ends within the
-  // next two groups, so the end of the piece is tested per edge.
-  auto do_group = [&](int j, auto last_tag) {
+  // LAST: the piece ends within the edges this iteration touches, so its end is tested per edge.
+  auto issue_group = [&](int jg, float4 (&xo)[D], float4 (&mo)[DELTA ? D : 1], auto last_tag) {
+    constexpr bool LAST = decltype(last_tag)::value;
+#pragma unroll
+    for (int u = 0; u < D; ++u)
+      if (!LAST || jg + u < e1) gather(jg + u - e0, xo[u], mo[DELTA ? u : 0]);
+  };
+  auto consume_group = [&](int jg, const float4 (&xi)[D], const float4 (&mi)[DELTA ? D : 1], auto last_tag) {
     constexpr bool LAST = decltype(last_tag)::value;
 #pragma unroll
     for (int u = 0; u < D; ++u) {
-      const int jj = j + u;
+      const int jj = jg + u;
       if (!LAST || jj < e1) {  // uniform
         while (jj >= row_end) row_done();
         const float v = sv[(jj - e0) & 127];
         if constexpr (DELTA) {
-          acc.x = fmaf(v, x[u].x - m[u].x, acc.x); acc.y = fmaf(v, x[u].y - m[u].y, acc.y);
-          acc.z = fmaf(v, x[u].z - m[u].z, acc.z); acc.w = fmaf(v, x[u].w - m[u].w, acc.w);
+          acc.x = fmaf(v, xi[u].x - mi[u].x, acc.x); acc.y = fmaf(v, xi[u].y - mi[u].y, acc.y);
+          acc.z = fmaf(v, xi[u].z - mi[u].z, acc.z); acc.w = fmaf(v, xi[u].w - mi[u].w, acc.w);
         } else {
-          acc.x = fmaf(v, x[u].x, acc.x); acc.y = fmaf(v, x[u].y, acc.y);
-          acc.z = fmaf(v, x[u].z, acc.z); acc.w = fmaf(v, x[u].w, acc.w);
+          acc.x = fmaf(v, xi[u].x, acc.x); acc.y = fmaf(v, xi[u].y, acc.y);
+          acc.z = fmaf(v, xi[u].z, acc.z); acc.w = fmaf(v, xi[u].w, acc.w);
         }
-        if (!LAST || jj + D < e1) issue(jj + D - e0, u);  // refill the slot with edge jj + D
       }
     }
   };
-  for (int j = e0; j < e1; j += D) {
+  auto do_pair = [&](int j, auto last_tag) {
+    issue_group(j + D, xb, mb, last_tag);
+    consume_group(j, xa, ma, last_tag);
+    issue_group(j + 2 * D, xa, ma, last_tag);
+    consume_group(j + D, xb, mb, last_tag);
+  };
+  for (int j = e0; j < e1; j += 2 * D) {
     const int off = j - e0;
     if ((off & 31) == 0 && off != 0) {
       // block off/32 - 1 is consumed: its ring slot takes the block held in registers (three ahead)
@@ -687,8 +701,8 @@ spmm_stream_kernel(const __grid_constant__ SpmmParams p) {
       ld_blk(b + 1, cn, vn);
       __syncwarp();
     }
-    if (j + 2 * D <= e1) do_group(j, std::false_type{});
-    else do_group(j, std::true_type{});
+    if (j + 3 * D <= e1) do_pair(j, std::false_type{});
+    else do_pair(j, std::true_type{});
   }
   // the row of the last edge: complete if it lies inside the piece, else a tail (or middle) part
   const bool tail_inside = row_end <= e1 && row_start >= e0;
@@ -798,16 +812,16 @@ static int env_int(const char* name, int dflt) {
 static int long_row_edges() { static int v = env_int("INCAGG_SPMM_LONG_ROW", 64); return v; }
 static int chunk_edges() { static int v = env_int("INCAGG_SPMM_CHUNK", 0); return v; }  // 0 = adaptive
 
-// Stream (merge-path) kernel configuration: variant 0 = ring of 16 gathers, 2 CTAs (16 warps) per SM;
-// 1 = ring of 8, 4 CTAs; 2 = ring of 8, 3 CTAs; 3 = ring of 4, 5 CTAs; 4 = ring of 4, 6 CTAs.  The
-// number of warp slots is one resident wave.
+// Stream (merge-path) kernel configuration (gathers per buffer x CTAs of 8 warps per SM):
+// variant 0 = 8 x 2, 1 = 4 x 4, 2 = 4 x 3, 3 = 2 x 5, 4 = 2 x 6, 5 = 16 x 1.  The number of warp slots is
+// one resident wave.
 static int stream_variant() {
   static int dflt = env_int("INCAGG_SPMM_STREAM", 0);  // -1: row-per-warp kernel everywhere
   return incagg::tune_get(INCAGG_TUNE_SPMM_STREAM_VARIANT, dflt);
 }
 static int stream_min_f() { return incagg::tune_get(INCAGG_TUNE_SPMM_STREAM_MIN_F, 65); }
 static int stream_ctas_per_sm(int variant) {
-  return variant == 1 ? 4 : (variant == 2 ? 3 : (variant == 3 ? 5 : (variant == 4 ? 6 : 2)));
+  return variant == 1 ? 4 : (variant == 2 ? 3 : (variant == 3 ? 5 : (variant == 4 ? 6 : (variant == 5 ? 1 : 2))));
 }
 static int stream_wslots() {
   int n = sm_count() * stream_ctas_per_sm(stream_variant()) * WS_WARPS;
@@ -912,14 +926,15 @@ static int try_stream(SpmmParams& p, int reduce, int vec, cudaStream_t st) {
   const bool delta = p.m_in != nullptr;
 #define IA_STREAM(D_, MINB_)                                                                         \
   do {                                                                                               \
-    if (delta) launch(spmm_stream_kernel<(D_) / 2, MINB_, true>, grid, dim3(WS_WARPS * 32), (size_t)(0), st, p); \
+    if (delta) launch(spmm_stream_kernel<((D_) > 1 ? (D_) / 2 : 1), MINB_, true>, grid, dim3(WS_WARPS * 32), (size_t)(0), st, p); \
     else launch(spmm_stream_kernel<D_, MINB_, false>, grid, dim3(WS_WARPS * 32), (size_t)(0), st, p);   \
   } while (0)
-  if (variant == 1) IA_STREAM(8, 4);
-  else if (variant == 2) IA_STREAM(8, 3);
-  else if (variant == 3) IA_STREAM(4, 5);
-  else if (variant == 4) IA_STREAM(4, 6);
-  else IA_STREAM(16, 2);
+  if (variant == 1) IA_STREAM(4, 4);
+  else if (variant == 2) IA_STREAM(4, 3);
+  else if (variant == 3) IA_STREAM(2, 5);
+  else if (variant == 4) IA_STREAM(2, 6);
+  else if (variant == 5) IA_STREAM(16, 1);
+  else IA_STREAM(8, 2);
 #undef IA_STREAM
   IA_LAUNCH_CHECK();
   return INCAGG_OK;

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-VARIANTS = {"rows": -1, "stream16x2": 0, "stream8x4": 1, "stream8x3": 2, "stream4x5": 3, "stream4x6": 4}
+VARIANTS = {"rows": -1, "s8x2": 0, "s4x4": 1, "s4x3": 2, "s2x5": 3, "s2x6": 4, "s16x1": 5}
 
 
 def main():
@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--batches", type=int, default=12)
     ap.add_argument("--batch-parts", type=int, default=1)
     ap.add_argument("--cases", default="fwd,bwd,delta,full")
-    ap.add_argument("--variants", default="rows,stream16x2,stream8x4,stream8x3,stream4x5,stream4x6")
+    ap.add_argument("--variants", default="rows,s8x2,s4x4,s4x3,s2x5,s2x6,s16x1")
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     import incagg_gnn_b200 as tga
