@@ -9,7 +9,8 @@ import re
 from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_char_p, c_float
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libincagg_b200.so")
+# (INCAGG_B200_LIB: an alternative build of the same library, for kernel experiments)
+LIB_PATH = os.environ.get("INCAGG_B200_LIB") or os.path.join(_HERE, "csrc", "libincagg_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "incagg_b200.h")
 
 REDUCE = {"sum": 0, "add": 0, "mean": 1, "min": 2, "max": 3}

@@ -101,6 +101,8 @@ constexpr int WS_MAX_TILES = 8;       // feature tiles the partial-row scratch i
 constexpr int PART_STRIDE = 512;        // floats per scratch slot (= widest tile, 32 lanes * 4 * 4)
 constexpr int PART_SLOTS = 16384;       // scratch slots per device (32 MB values + 32 MB args)
 constexpr int PLAN_SCRATCH_CAP = 8192;  // slots one plan may hand out (times the feature tiles)
+constexpr int ROW_GRAB = 4;             // short rows (x 32 / G) a warp fetches per trip to the row counter
+constexpr int ROW_COUNTERS = 1024;      // feature tiles with a row counter of their own (gridDim.y)
 
 struct SpmmParams {
   const int32_t* rowptr;
@@ -138,6 +140,7 @@ struct SpmmParams {
   int32_t* part_done;       // [part_slots] arrival counters (left at zero by every call)
   int32_t part_slots;
   // stream kernel: partial sums of rows cut by a warp boundary, arrival counters, mean flag
+  int32_t* row_counter;     // [ROW_COUNTERS + 1] next short row per feature tile, CTAs done (zero between calls)
   float* ws_part;           // [tiles][n_wslots][2][WS_TILE_F]
   int32_t* ws_done;         // [tiles][n_wslots]
   int32_t mean;
@@ -175,11 +178,21 @@ __device__ __forceinline__ void red_update(int op, float (&acc)[VEC], int32_t (&
 
 // One G-lane group walks edges [s, e) of one row and accumulates NCH vectors per lane.
 // lane_g: lane index inside the group; gmask: shuffle mask of the group.
+// Row c of X starts at byte c * (ldx * 4): the product of two 32-bit values (the host checks
+// ldx < 2^30), one IMAD.WIDE.U32 per gather instead of a 64-bit multiply-add chain.
 template <int REDUCE, int VEC, int G, int NCH, bool DELTA, bool ARG>
 __device__ __forceinline__ void walk_edges(const SpmmParams& p, int op, int s, int e, int fbase,
                                            int F, int lane_g, unsigned gmask,
                                            float (&acc)[NCH][VEC], int32_t (&arg)[NCH][VEC]) {
   constexpr int UNROLL = (NCH >= 4) ? 2 : 4;
+  const unsigned x_bytes = (unsigned)p.ldx * 4u;
+  const unsigned m_bytes = DELTA ? (unsigned)p.ld_in * 4u : 0u;
+  const int f0 = fbase + lane_g * VEC;  // column of chunk 0; chunk k is G * VEC columns further
+  const char* Xb = reinterpret_cast<const char*>(p.X + f0);
+  const char* Mb = DELTA ? reinterpret_cast<const char*>(p.m_in + f0) : nullptr;
+  bool fok[NCH];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) fok[k] = f0 + k * G * VEC < F;
   for (int base = s; base < e; base += G) {
     const int my_e = base + lane_g;
     int my_c = 0;
@@ -201,12 +214,11 @@ __device__ __forceinline__ void walk_edges(const SpmmParams& p, int op, int s, i
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const float* xr = p.X + (int64_t)c[u] * p.ldx;
+        const float* xr = reinterpret_cast<const float*>(Xb + (size_t)(unsigned)c[u] * x_bytes);
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
-          const int f = fbase + (k * G + lane_g) * VEC;
-          if (f < F) {
-            load_vec<VEC>(xr + f, x[u][k]);
+          if (fok[k]) {
+            load_vec<VEC>(xr + k * G * VEC, x[u][k]);
           } else {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) x[u][k][i] = 0.f;
@@ -216,14 +228,13 @@ __device__ __forceinline__ void walk_edges(const SpmmParams& p, int op, int s, i
       if constexpr (DELTA) {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          const int64_t g = p.n_id ? p.n_id[c[u]] : (int64_t)c[u];
-          const float* mr = p.m_in + g * p.ld_in;
+          const unsigned g = p.n_id ? (unsigned)p.n_id[c[u]] : (unsigned)c[u];
+          const float* mr = reinterpret_cast<const float*>(Mb + (size_t)g * m_bytes);
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
-            const int f = fbase + (k * G + lane_g) * VEC;
-            if (f < F) {
+            if (fok[k]) {
               float m[VEC];
-              load_vec<VEC>(mr + f, m);
+              load_vec<VEC>(mr + k * G * VEC, m);
 #pragma unroll
               for (int i = 0; i < VEC; ++i) x[u][k][i] -= m[i];
             }
@@ -239,21 +250,20 @@ __device__ __forceinline__ void walk_edges(const SpmmParams& p, int op, int s, i
     for (; j < cnt; ++j) {
       const int c = __shfl_sync(gmask, my_c, j, G);
       const float v = __shfl_sync(gmask, my_v, j, G);
-      const float* xr = p.X + (int64_t)c * p.ldx;
+      const float* xr = reinterpret_cast<const float*>(Xb + (size_t)(unsigned)c * x_bytes);
       const float* mr = nullptr;
       if constexpr (DELTA) {
-        const int64_t g = p.n_id ? p.n_id[c] : (int64_t)c;
-        mr = p.m_in + g * p.ld_in;
+        const unsigned g = p.n_id ? (unsigned)p.n_id[c] : (unsigned)c;
+        mr = reinterpret_cast<const float*>(Mb + (size_t)g * m_bytes);
       }
 #pragma unroll
       for (int k = 0; k < NCH; ++k) {
-        const int f = fbase + (k * G + lane_g) * VEC;
-        if (f < F) {
+        if (fok[k]) {
           float x[VEC];
-          load_vec<VEC>(xr + f, x);
+          load_vec<VEC>(xr + k * G * VEC, x);
           if constexpr (DELTA) {
             float m[VEC];
-            load_vec<VEC>(mr + f, m);
+            load_vec<VEC>(mr + k * G * VEC, m);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) x[i] -= m[i];
           }
@@ -352,22 +362,44 @@ spmm_kernel(const SpmmParams p) {
 
   if ((int)blockIdx.x >= p.long_grid) {
     // ---- short rows ----
-    constexpr int GROUPS = SPMM_THREADS / G;
+    // The CTAs of this part are one resident wave; every warp fetches its next ROW_GRAB * (32 / G)
+    // rows from a counter until the rows are used up, so no warp slot idles while a CTA waits for
+    // its longest row (rows differ in length by two orders of magnitude) and there is no tail of
+    // partially filled waves.  Which warp computes a row does not affect the result.
+    constexpr int RPW = 32 / G;  // rows a warp works on at a time
     const int lane_g = threadIdx.x % G;
     const int sub = lane / G;  // group index inside the warp
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
-    const int64_t row = (int64_t)(blockIdx.x - p.long_grid) * GROUPS + threadIdx.x / G;
-    if (row >= p.rows) return;
-    const int s = __ldg(p.rowptr + row), e = __ldg(p.rowptr + row + 1);
-    if (e - s > long_row) return;  // owned by the plan's items
-    float acc[NCH][VEC];
-    int32_t arg[NCH][VEC];
+    int32_t* counter = p.row_counter + blockIdx.y;
+    for (;;) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(counter, ROW_GRAB * RPW);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if ((int64_t)base >= p.rows) break;
+#pragma unroll 1
+      for (int i = 0; i < ROW_GRAB; ++i) {
+        const int64_t row = (int64_t)base + i * RPW + sub;
+        if (row >= p.rows) break;  // (uniform per group; groups of a warp do not communicate)
+        const int s = __ldg(p.rowptr + row), e = __ldg(p.rowptr + row + 1);
+        if (e - s > long_row) continue;  // owned by the plan's items
+        float acc[NCH][VEC];
+        int32_t arg[NCH][VEC];
 #pragma unroll
-    for (int k = 0; k < NCH; ++k)
+        for (int k = 0; k < NCH; ++k)
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { acc[k][i] = red_init<REDUCE>(op); arg[k][i] = -1; }
-    walk_edges<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, s, e, fbase, flim, lane_g, gmask, acc, arg);
-    finish_row<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, row, e - s, fbase, flim, lane_g, acc, arg);
+          for (int ii = 0; ii < VEC; ++ii) { acc[k][ii] = red_init<REDUCE>(op); arg[k][ii] = -1; }
+        walk_edges<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, s, e, fbase, flim, lane_g, gmask, acc, arg);
+        finish_row<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, row, e - s, fbase, flim, lane_g, acc, arg);
+      }
+    }
+    // the last CTA of the launch to get here leaves the counters at zero for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int n_short = (int)(gridDim.x - p.long_grid) * (int)gridDim.y;
+      if (atomicAdd(p.row_counter + ROW_COUNTERS, 1) == n_short - 1) {
+        for (int t = 0; t <= ROW_COUNTERS; ++t) p.row_counter[t] = 0;
+      }
+    }
     return;
   }
 
@@ -1176,6 +1208,7 @@ struct SpmmScratch {
   float* part_val = nullptr;
   int32_t* part_arg = nullptr;
   int32_t* part_done = nullptr;
+  int32_t* row_counter = nullptr;
   float* ws_part = nullptr;     // stream kernel: [WS_MAX_TILES][WS_MAX_SLOTS][2][WS_TILE_F]
   int32_t* ws_done = nullptr;   // [WS_MAX_TILES][WS_MAX_SLOTS]
   void* plan = nullptr;  // temporary plan of calls that pass none
@@ -1197,6 +1230,8 @@ static int get_scratch(SpmmScratch** out, int64_t want_plan_capacity) {
     IA_CUDA(cudaMalloc(&s.part_arg, sizeof(int32_t) * (size_t)PART_SLOTS * PART_STRIDE));
     IA_CUDA(cudaMalloc(&s.part_done, sizeof(int32_t) * (size_t)PART_SLOTS));
     IA_CUDA(cudaMemset(s.part_done, 0, sizeof(int32_t) * (size_t)PART_SLOTS));
+    IA_CUDA(cudaMalloc(&s.row_counter, sizeof(int32_t) * (ROW_COUNTERS + 1)));
+    IA_CUDA(cudaMemset(s.row_counter, 0, sizeof(int32_t) * (ROW_COUNTERS + 1)));
     IA_CUDA(cudaMalloc(&s.ws_part, sizeof(float) * (size_t)WS_MAX_TILES * WS_MAX_SLOTS * 2 * WS_TILE_F));
     IA_CUDA(cudaMalloc(&s.ws_done, sizeof(int32_t) * (size_t)WS_MAX_TILES * WS_MAX_SLOTS));
     IA_CUDA(cudaMemset(s.ws_done, 0, sizeof(int32_t) * (size_t)WS_MAX_TILES * WS_MAX_SLOTS));
@@ -1295,13 +1330,25 @@ static int launch_cfg(SpmmParams& p, int n_tiles, int64_t items_bound, cudaStrea
   p.part_done = sc->part_done;
   p.part_slots = PART_SLOTS;
   p.n_tiles = n_tiles;
+  p.row_counter = sc->row_counter;
+  IA_CHECK_ARG(n_tiles <= ROW_COUNTERS, "too many feature tiles (%d)", n_tiles);
+  IA_CHECK_ARG(p.ldx < (1ll << 30) && p.ld_in < (1ll << 30), "row stride too large");
   // CTAs that walk the plan's items: never more than the items can be, at most 8 per SM
   int64_t lg = (int64_t)env_int("INCAGG_SPMM_LONG_CTAS", 8) * sm_count();
   if (items_bound < lg) lg = items_bound;
   if (lg < 1) lg = 1;
   p.long_grid = (int)lg;
-  IA_CHECK_ARG(blocks + lg <= 0x7fffffff, "too many rows for one launch");
-  dim3 grid((unsigned)(blocks + lg), (unsigned)n_tiles);
+  // CTAs of the short rows: one resident wave, rows are handed out dynamically
+  static int ctas_per_sm = 0;  // (per template instance)
+  if (ctas_per_sm == 0) {
+    int n = 0;
+    IA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmm_kernel<REDUCE, VEC, G, NCH, DELTA, ARG>,
+                                                          SPMM_THREADS, 0));
+    ctas_per_sm = n > 0 ? n : 1;
+  }
+  int64_t n_short = (int64_t)ctas_per_sm * sm_count();
+  if (blocks < n_short) n_short = blocks;
+  dim3 grid((unsigned)(n_short + lg), (unsigned)n_tiles);
   launch(spmm_kernel<REDUCE, VEC, G, NCH, DELTA, ARG>, dim3(grid), dim3(SPMM_THREADS), (size_t)(0), st, p);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
