@@ -47,6 +47,7 @@ _PROTOS = {
     "incagg_last_error": (c_char_p, []),
     "incagg_launch_count": (c_int64, []),
     "incagg_tune_set": (c_int, [c_int, c_int]),
+    "incagg_device_errors": (c_int, [P, c_int]),
     "incagg_device_info": (c_int, [P, P, P]),
     "incagg_enable_peer_access": (c_int, [c_int]),
     "incagg_spmm_plan_bytes": (c_size_t, [c_int64, c_int64]),

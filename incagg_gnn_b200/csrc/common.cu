@@ -36,6 +36,19 @@ int sm_count() {
   return cached[dev];
 }
 
+int32_t* device_error_word() {
+  static int32_t* words[16] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (words[dev] == nullptr) {
+    int32_t* w = nullptr;
+    if (cudaMalloc(&w, sizeof(int32_t)) != cudaSuccess) return nullptr;
+    cudaMemset(w, 0, sizeof(int32_t));
+    words[dev] = w;
+  }
+  return words[dev];
+}
+
 static int g_tune[INCAGG_TUNE_COUNT];
 static bool g_tune_set[INCAGG_TUNE_COUNT];
 int tune_get(int key, int dflt) {
@@ -56,6 +69,15 @@ extern "C" int incagg_tune_set(int key, int value) {
   IA_CHECK_ARG(key >= 0 && key < INCAGG_TUNE_COUNT, "unknown tuning key %d", key);
   incagg::g_tune[key] = value;
   incagg::g_tune_set[key] = true;
+  return INCAGG_OK;
+}
+
+extern "C" int incagg_device_errors(int32_t* out, int reset) {
+  IA_CHECK_ARG(out != nullptr, "out is NULL");
+  int32_t* w = incagg::device_error_word();
+  IA_CHECK_ARG(w != nullptr, "no device error word");
+  IA_CUDA(cudaMemcpy(out, w, sizeof(int32_t), cudaMemcpyDeviceToHost));  // synchronises with the device
+  if (reset && *out != 0) IA_CUDA(cudaMemset(w, 0, sizeof(int32_t)));
   return INCAGG_OK;
 }
 

@@ -40,6 +40,10 @@ inline cudaStream_t as_stream(incagg_stream_t s) { return reinterpret_cast<cudaS
 
 int sm_count();  // cached SM count of the current device (148 on B200)
 int tune_get(int key, int dflt);  // experiment knobs (incagg_tune_set); `dflt` when unset
+// Device-side error word of the current device (one int32, zero = no error): kernels OR a bit into it
+// when they meet an index outside its table (INCAGG_DEVERR_*), the host reads it with
+// incagg_device_errors().  Allocated on first use; nullptr if that fails.
+int32_t* device_error_word();
 void count_launch();  // process-wide count of kernels launched by this library
 unsigned long long launches();
 

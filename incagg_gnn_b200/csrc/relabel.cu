@@ -32,6 +32,7 @@ struct RelabelWs {
   int64_t* rowtmp2;    // [N+1] per-row counts of first-seen halo edges -> exclusive prefix
   int64_t* scan;       // [scan tiles] scratch of exclusive_scan_i64
   int64_t* total;      // [2]
+  int64_t* ids;        // [N]  the batch ids with ids outside [0, N) replaced by -1 (see mark_kernel)
 };
 
 static size_t ws_scan_slots(int64_t n) { return (size_t)scan_num_tiles(n + 1) + 8; }
@@ -51,6 +52,8 @@ static RelabelWs carve_ws(void* ws, int64_t n) {
   w.scan = reinterpret_cast<int64_t*>(p);
   p += sizeof(int64_t) * ws_scan_slots(n);
   w.total = reinterpret_cast<int64_t*>(p);
+  p += sizeof(int64_t) * 8;
+  w.ids = reinterpret_cast<int64_t*>(p);
   return w;
 }
 
@@ -65,23 +68,33 @@ __global__ void ws_init_kernel(int32_t* map, int32_t* first_pos, int64_t n) {
 
 // map[idx[i]] = i (largest i wins) and deg[i] = degree of idx[i].
 __global__ void mark_kernel(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ idx,
-                            int64_t B, int32_t* map, int64_t* __restrict__ deg) {
+                            int64_t B, int32_t* map, int64_t* __restrict__ deg, int64_t num_nodes,
+                            int32_t* __restrict__ err, int64_t* __restrict__ ids) {
   pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   const int64_t v = idx[i];
+  if (v < 0 || v >= num_nodes) {
+    // the reference would read out of bounds here: set the error bit and treat the id as a node
+    // without edges (the later kernels read `ids`, where it is -1)
+    if (err) atomicOr(err, INCAGG_DEVERR_NODE_ID);
+    if (deg) deg[i] = 0;
+    ids[i] = -1;
+    return;
+  }
+  ids[i] = v;
   atomicMax(map + v, (int32_t)i);
   if (deg) deg[i] = rowptr[v + 1] - rowptr[v];
 }
 
 __global__ void degree_sum_kernel(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ idx,
-                                  int64_t B, unsigned long long* out) {
+                                  int64_t B, unsigned long long* out, int64_t num_nodes) {
   pdl_prologue();
   int64_t s = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v = idx[i];
-    s += rowptr[v + 1] - rowptr[v];
+    if (v >= 0 && v < num_nodes) s += rowptr[v + 1] - rowptr[v];
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0 && s != 0) atomicAdd(out, (unsigned long long)s);
@@ -110,6 +123,7 @@ map_edges_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__ col,
   const int64_t i = (int64_t)blockIdx.x * RL_WARPS + (threadIdx.x >> 5);
   if (i >= B) return;
   const int64_t v = idx[i];
+  if (v < 0) return;  // id outside the graph (flagged by mark_kernel)
   const int64_t s = rowptr[v], e = rowptr[v + 1];
   const int64_t p0 = row_start[i];
   for (int64_t j = s + lane; j < e; j += 32) {
@@ -138,6 +152,10 @@ count_first_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__ co
   const int64_t i = (int64_t)blockIdx.x * RL_WARPS + (threadIdx.x >> 5);
   if (i >= B) return;
   const int64_t v = idx[i];
+  if (v < 0) {  // id outside the graph (flagged by mark_kernel): no edges
+    if (lane == 0) row_first[i] = 0;
+    return;
+  }
   const int64_t s = rowptr[v], e = rowptr[v + 1];
   const int64_t p0 = row_start[i];
   int cnt = 0;
@@ -161,6 +179,7 @@ assign_halo_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__ co
   const int64_t i = (int64_t)blockIdx.x * RL_WARPS + (threadIdx.x >> 5);
   if (i >= B) return;
   const int64_t v = idx[i];
+  if (v < 0) return;  // id outside the graph (flagged by mark_kernel)
   const int64_t s = rowptr[v], e = rowptr[v + 1];
   const int64_t p0 = row_start[i];
   int64_t rank0 = row_first_excl[i];
@@ -195,6 +214,7 @@ fill_halo_cols_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__
   const int64_t i = (int64_t)blockIdx.x * RL_WARPS + (threadIdx.x >> 5);
   if (i >= B) return;
   const int64_t v = idx[i];
+  if (v < 0) return;  // id outside the graph (flagged by mark_kernel)
   const int64_t s = rowptr[v], e = rowptr[v + 1];
   const int64_t p0 = row_start[i];
   for (int64_t j = s + lane; j < e; j += 32) {
@@ -207,7 +227,7 @@ fill_halo_cols_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__
 // of halo nodes.
 __global__ void finish_kernel(const int64_t* __restrict__ idx, int64_t B,
                               const int64_t* __restrict__ H_dev, int64_t* __restrict__ n_id_out,
-                              int32_t* map, int32_t* first_pos) {
+                              int32_t* map, int32_t* first_pos, int64_t num_nodes) {
   pdl_prologue();
   const int64_t H = H_dev ? *H_dev : 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B + H;
@@ -215,7 +235,7 @@ __global__ void finish_kernel(const int64_t* __restrict__ idx, int64_t B,
     if (i < B) {
       const int64_t v = idx[i];
       if (n_id_out) n_id_out[i] = v;
-      map[v] = -1;
+      if (v >= 0 && v < num_nodes) map[v] = -1;
     } else {
       const int64_t v = n_id_out[i];
       map[v] = -1;
@@ -235,6 +255,10 @@ count_kept_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__ col
   const int64_t i = (int64_t)blockIdx.x * RL_WARPS + (threadIdx.x >> 5);
   if (i >= B) return;
   const int64_t v = idx[i];
+  if (v < 0) {  // id outside the graph (flagged by mark_kernel): no edges
+    if (lane == 0) row_kept[i] = 0;
+    return;
+  }
   const int64_t s = rowptr[v], e = rowptr[v + 1];
   int cnt = 0;
   for (int64_t j = s + lane; j < e; j += 32)
@@ -255,6 +279,7 @@ compact_kept_kernel(const int64_t* __restrict__ rowptr, const CT* __restrict__ c
   const int64_t i = (int64_t)blockIdx.x * RL_WARPS + (threadIdx.x >> 5);
   if (i >= B) return;
   const int64_t v = idx[i];
+  if (v < 0) return;  // id outside the graph (flagged by mark_kernel)
   const int64_t s = rowptr[v], e = rowptr[v + 1];
   int64_t p = row_start[i];
   for (int64_t jb = s; jb < e; jb += 32) {
@@ -309,7 +334,7 @@ static int relabel_one_hop_impl(const int64_t* rowptr, const CT* col, const floa
     IA_CUDA(cudaMemsetAsync(counts_out, 0, 2 * sizeof(int64_t), st));
     return INCAGG_OK;
   }
-  launch(mark_kernel, dim3(blocks_for(B, 256)), dim3(256), (size_t)(0), st, rowptr, idx, B, w.map, w.rowtmp);
+  launch(mark_kernel, dim3(blocks_for(B, 256)), dim3(256), (size_t)(0), st, rowptr, idx, B, w.map, w.rowtmp, N, device_error_word(), w.ids);
   IA_LAUNCH_CHECK();
   int64_t* row_start = w.rowtmp;  // becomes the exclusive prefix of the degrees
   int rc = exclusive_scan_i64(w.rowtmp, row_start, B, w.scan, w.total, st);
@@ -318,23 +343,23 @@ static int relabel_one_hop_impl(const int64_t* rowptr, const CT* col, const floa
   IA_LAUNCH_CHECK();
   const unsigned rb = blocks_for(B, RL_WARPS);
   int64_t* row_first = w.rowtmp2;
-  launch(map_edges_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, val, idx, B, row_start, w.map,
+  launch(map_edges_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, val, w.ids, B, row_start, w.map,
                                                       w.first_pos, out_col, out_val);
   IA_LAUNCH_CHECK();
-  launch(count_first_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, idx, B, row_start,
+  launch(count_first_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, w.ids, B, row_start,
                                                         w.first_pos, out_col, row_first);
   IA_LAUNCH_CHECK();
   rc = exclusive_scan_i64(row_first, row_first, B, w.scan, w.total + 1, st);
   if (rc != INCAGG_OK) return rc;
-  launch(assign_halo_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, idx, B, row_start, row_first,
+  launch(assign_halo_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, w.ids, B, row_start, row_first,
                                                         w.first_pos, out_col, w.map, n_id_out);
   IA_LAUNCH_CHECK();
-  launch(fill_halo_cols_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, idx, B, row_start, w.map,
+  launch(fill_halo_cols_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, w.ids, B, row_start, w.map,
                                                            out_col);
   IA_LAUNCH_CHECK();
   launch(store_counts_kernel, dim3(1), dim3(1), (size_t)(0), st, w.total + 1, w.total, 0, counts_out);
   IA_LAUNCH_CHECK();
-  launch(finish_kernel, dim3(sm_count() * 4), dim3(256), (size_t)(0), st, idx, B, w.total + 1, n_id_out, w.map, w.first_pos);
+  launch(finish_kernel, dim3(sm_count() * 4), dim3(256), (size_t)(0), st, idx, B, w.total + 1, n_id_out, w.map, w.first_pos, N);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -350,21 +375,21 @@ static int relabel_within_impl(const int64_t* rowptr, const CT* col, const float
     IA_CUDA(cudaMemsetAsync(counts_out, 0, 2 * sizeof(int64_t), st));
     return INCAGG_OK;
   }
-  launch(mark_kernel, dim3(blocks_for(B, 256)), dim3(256), (size_t)(0), st, rowptr, idx, B, w.map, nullptr);
+  launch(mark_kernel, dim3(blocks_for(B, 256)), dim3(256), (size_t)(0), st, rowptr, idx, B, w.map, nullptr, N, device_error_word(), w.ids);
   IA_LAUNCH_CHECK();
   const unsigned rb = blocks_for(B, RL_WARPS);
-  launch(count_kept_kernel<CT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, idx, B, w.map, w.rowtmp);
+  launch(count_kept_kernel<CT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, w.ids, B, w.map, w.rowtmp);
   IA_LAUNCH_CHECK();
   int rc = exclusive_scan_i64(w.rowtmp, w.rowtmp, B, w.scan, w.total, st);
   if (rc != INCAGG_OK) return rc;
   launch(write_rowptr_kernel<OT>, dim3(blocks_for(B + 1, 256)), dim3(256), (size_t)(0), st, w.rowtmp, w.total, B, out_rowptr);
   IA_LAUNCH_CHECK();
-  launch(compact_kept_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, val, idx, B, w.map, w.rowtmp,
+  launch(compact_kept_kernel<CT, OT>, dim3(rb), dim3(RL_THREADS), (size_t)(0), st, rowptr, col, val, w.ids, B, w.map, w.rowtmp,
                                                          out_col, out_val);
   IA_LAUNCH_CHECK();
   launch(store_counts_kernel, dim3(1), dim3(1), (size_t)(0), st, nullptr, w.total, 0, counts_out);
   IA_LAUNCH_CHECK();
-  launch(finish_kernel, dim3(sm_count() * 4), dim3(256), (size_t)(0), st, idx, B, nullptr, nullptr, w.map, w.first_pos);
+  launch(finish_kernel, dim3(sm_count() * 4), dim3(256), (size_t)(0), st, idx, B, nullptr, nullptr, w.map, w.first_pos, N);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -378,7 +403,7 @@ extern "C" size_t incagg_relabel_workspace_bytes(int64_t num_nodes) {
   // map + first_pos + two per-row int64 arrays (degree prefix, first-edge counts) + scan scratch
   // + 2 totals; mirrors carve_ws().
   return sizeof(int32_t) * 2 * (size_t)num_nodes + 16 + sizeof(int64_t) * (2 * (size_t)num_nodes + 2) +
-         sizeof(int64_t) * (ws_scan_slots(num_nodes) + 8);
+         sizeof(int64_t) * (ws_scan_slots(num_nodes) + 8) + sizeof(int64_t) * ((size_t)num_nodes + 8);
 }
 
 extern "C" int incagg_relabel_workspace_init(void* workspace, int64_t num_nodes,
@@ -394,7 +419,7 @@ extern "C" int incagg_relabel_workspace_init(void* workspace, int64_t num_nodes,
 extern "C" int incagg_relabel_degree_sum(const int64_t* rowptr, const int64_t* idx, int64_t B,
                                          int64_t num_nodes, int64_t* degsum_out, void* workspace,
                                          incagg_stream_t stream) {
-  (void)workspace; (void)num_nodes;
+  (void)workspace;
   IA_CHECK_ARG(B >= 0 && degsum_out != nullptr, "bad arguments");
   cudaStream_t st = as_stream(stream);
   IA_CUDA(cudaMemsetAsync(degsum_out, 0, sizeof(int64_t), st));
@@ -403,7 +428,7 @@ extern "C" int incagg_relabel_degree_sum(const int64_t* rowptr, const int64_t* i
   const unsigned blocks = blocks_for(B, 256) < (unsigned)(sm_count() * 8) ? blocks_for(B, 256)
                                                                             : (unsigned)(sm_count() * 8);
   launch(degree_sum_kernel, dim3(blocks), dim3(256), (size_t)(0), st, rowptr, idx, B,
-                                            reinterpret_cast<unsigned long long*>(degsum_out));
+                                            reinterpret_cast<unsigned long long*>(degsum_out), num_nodes);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }

@@ -33,7 +33,8 @@ constexpr int ROWS_UNROLL = 4;
 template <int VB, int MODE>
 __global__ void __launch_bounds__(ROWS_THREADS)
 index_rows_kernel(const char* __restrict__ src, int64_t src_ld, const int64_t* __restrict__ idx,
-                  int64_t n, char* __restrict__ dst, int64_t dst_ld, int nvec, int64_t limit_rows) {
+                  int64_t n, char* __restrict__ dst, int64_t dst_ld, int nvec, int64_t limit_rows,
+                  int32_t* __restrict__ err) {
   pdl_prologue();
   using V = typename Bytes<VB>::type;
   const int64_t total = n * nvec;
@@ -55,6 +56,12 @@ index_rows_kernel(const char* __restrict__ src, int64_t src_ld, const int64_t* _
           const int64_t drow = (MODE == 0) ? r : j;
           v[u] = *reinterpret_cast<const V*>(src + srow * src_ld + (int64_t)c * VB);
           doff[u] = drow * dst_ld + (int64_t)c * VB;
+        } else {  // the reference raises here: flag it; a gather returns a zero row, a scatter skips it
+          if (c == 0 && err) atomicOr(err, INCAGG_DEVERR_ROW_INDEX);
+          if (MODE == 0) {
+            v[u] = V{};
+            doff[u] = r * dst_ld + (int64_t)c * VB;
+          }
         }
       }
     }
@@ -78,7 +85,7 @@ struct ShardTable {
 template <int VB>
 __global__ void __launch_bounds__(ROWS_THREADS)
 sharded_gather_kernel(const ShardTable tab, int64_t src_ld, const int64_t* __restrict__ idx, int64_t n,
-                      char* __restrict__ dst, int64_t dst_ld, int nvec) {
+                      char* __restrict__ dst, int64_t dst_ld, int nvec, int32_t* __restrict__ err) {
   pdl_prologue();
   using V = typename Bytes<VB>::type;
   const int64_t total = n * nvec;
@@ -99,6 +106,10 @@ sharded_gather_kernel(const ShardTable tab, int64_t src_ld, const int64_t* __res
           int s = 0;
           while (j >= tab.bounds[s + 1]) ++s;
           v[u] = *reinterpret_cast<const V*>(tab.base[s] + (j - tab.bounds[s]) * src_ld + (int64_t)c * VB);
+          doff[u] = r * dst_ld + (int64_t)c * VB;
+        } else {  // id owned by no shard: zero row + error flag
+          if (c == 0 && err) atomicOr(err, INCAGG_DEVERR_ROW_INDEX);
+          v[u] = V{};
           doff[u] = r * dst_ld + (int64_t)c * VB;
         }
       }
@@ -285,16 +296,17 @@ static int index_rows(const void* src, int64_t src_ld, const int64_t* idx, int64
   if (is_host_ptr(MODE == 0 ? src : (const void*)dst) && grid > host_gather_ctas()) grid = host_gather_ctas();
   const char* s = static_cast<const char*>(src);
   char* d = static_cast<char*>(dst);
+  int32_t* err = device_error_word();
   if (vb == 16)
-    launch(index_rows_kernel<16, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+    launch(index_rows_kernel<16, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows, err);
   else if (vb == 8)
-    launch(index_rows_kernel<8, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+    launch(index_rows_kernel<8, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows, err);
   else if (vb == 4)
-    launch(index_rows_kernel<4, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+    launch(index_rows_kernel<4, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows, err);
   else if (vb == 2)
-    launch(index_rows_kernel<2, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+    launch(index_rows_kernel<2, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows, err);
   else
-    launch(index_rows_kernel<1, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows);
+    launch(index_rows_kernel<1, MODE>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, s, src_ld, idx, n, d, dst_ld, nvec, limit_rows, err);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
@@ -338,7 +350,7 @@ extern "C" int incagg_gather_rows_sharded(const void* const* shard_ptrs, const i
   const int grid = grid_for(n * nvec64);
   cudaStream_t st = as_stream(stream);
   char* d = static_cast<char*>(dst);
-#define IA_SG(VB_) launch(sharded_gather_kernel<VB_>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, tab, src_ld_bytes, idx, n, d, dst_ld_bytes, nvec)
+#define IA_SG(VB_) launch(sharded_gather_kernel<VB_>, dim3(grid), dim3(ROWS_THREADS), (size_t)(0), st, tab, src_ld_bytes, idx, n, d, dst_ld_bytes, nvec, device_error_word())
   if (vb == 16) IA_SG(16); else if (vb == 8) IA_SG(8); else if (vb == 4) IA_SG(4); else if (vb == 2) IA_SG(2); else IA_SG(1);
 #undef IA_SG
   IA_LAUNCH_CHECK();

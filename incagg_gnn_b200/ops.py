@@ -30,6 +30,22 @@ def _stream() -> int:
     return _raw_stream(_cur_dev())
 
 
+def check_device_errors(reset: bool = True) -> None:
+    """Raises RuntimeError if a kernel met an index outside its table since the last check (the
+    reference raises at the faulty index_select / index_put; kernels record it in a device-side word,
+    write zeros for a gathered row and skip a scattered one).  Synchronises with the device."""
+    import ctypes
+    word = ctypes.c_int32(0)
+    check(lib.incagg_device_errors(ctypes.cast(ctypes.pointer(word), ctypes.c_void_p), int(reset)))
+    if word.value:
+        what = []
+        if word.value & 1:
+            what.append("gather / scatter row index outside the table")
+        if word.value & 2:
+            what.append("relabel: batch node id outside [0, num_nodes)")
+        raise RuntimeError("incagg_b200 device error: " + "; ".join(what))
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -201,13 +217,19 @@ def csr_transpose(rowptr: Tensor, col: Tensor, val: Optional[Tensor], rows: int,
 # dense X·W on the tensor cores (tcgen05, 3xTF32)
 # --------------------------------------------------------------------------------------------
 _GEMM_WS = {}
+_GEMM_WS_RETIRED = []
 
 
 def _gemm_workspace(device, nbytes: int, slot: int = 0) -> Tensor:
     """Split-K scratch, one per (device, slot): GEMMs issued on different streams use different slots."""
     ws = _GEMM_WS.get((device, slot))
     if ws is None or ws.numel() < nbytes:
-        ws = _GEMM_WS[(device, slot)] = torch.empty(max(nbytes, 1 << 24), dtype=torch.uint8, device=device)
+        # Always the 256 MB cap the callers clamp to: the buffer is allocated once (by an eager warm-up
+        # step) and never replaced, so the address a captured CUDA graph has baked in stays valid.  A
+        # buffer that had to be replaced all the same is kept alive for the graphs that reference it.
+        if ws is not None:
+            _GEMM_WS_RETIRED.append(ws)
+        ws = _GEMM_WS[(device, slot)] = torch.empty(max(nbytes, 1 << 28), dtype=torch.uint8, device=device)
     return ws
 
 

@@ -137,6 +137,8 @@ def mini_train(model, loader, criterion, optimizer, max_steps, grad_norm=None, e
         if (i + 1) >= max_steps and (i + 1) < len(loader):
             break
     tl, te = float(total_loss), float(total_examples)
+    from . import ops
+    ops.check_device_errors()  # an index outside a table anywhere in the epoch raises here
     return {'loss': tl / max(te, 1.), 'steps': steps}
 
 
@@ -407,6 +409,8 @@ class GraphedTrainer:
             seq = seq if max_steps is None else seq[:max_steps]
             self.run(seq)
             a = self.acc.tolist()
+            from . import ops
+            ops.check_device_errors()
             return {'loss': a[0] / max(a[1], 1.), 'steps': len(seq)}
         for ids in self.loader._batches_of_epoch():
             self.step(ids)

@@ -62,6 +62,13 @@ int64_t incagg_launch_count(void);
 #define INCAGG_TUNE_SPMM_STREAM_MIN_F 1   /* smallest feature width routed to the merge-path kernel (65) */
 #define INCAGG_TUNE_COUNT 8
 int incagg_tune_set(int key, int value);
+/* Device-side error word of the current device.  The reference raises on an index outside its table
+ * (index_select, emb[n_id] = x); kernels cannot raise, so they record the fact: a gather writes zeros
+ * for the row, a scatter / relabel skips it, and the bit below is set.  Reading synchronises with the
+ * device; `reset` != 0 clears the word.  (ops.check_device_errors() raises RuntimeError on non-zero.) */
+#define INCAGG_DEVERR_ROW_INDEX 1 /* gather / scatter / sharded gather: row id outside the table */
+#define INCAGG_DEVERR_NODE_ID 2   /* relabel: batch node id outside [0, num_nodes) */
+int incagg_device_errors(int32_t* out, int reset);
 /* SM count and compute capability of the current device. */
 int incagg_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -693,3 +693,35 @@ def test_copy_slices_tma_bulk_path(ops, cuda):
     pk = torch.zeros(100 * k, D, device=cuda)
     ops.copy_slices(table, pk, off, cnt, 0)
     assert torch.equal(pk, torch.cat([table[o:o + 100] for o in off.tolist()]))
+
+
+def test_out_of_range_ids_are_flagged_not_silently_skipped(ops, cuda):
+    """The reference raises on an id outside its table (index_select, emb[n_id] = x).  The kernels
+    record it in the device error word: a gathered row is zeros (not uninitialised memory), a scattered
+    row is skipped, relabel treats the id as a node without edges - and ops.check_device_errors()
+    raises."""
+    ops.check_device_errors()  # clean to start with
+    table = torch.arange(40, dtype=torch.float32, device=cuda).reshape(10, 4)
+    idx = torch.tensor([3, 12, -1, 9], device=cuda)
+    out = ops.gather_rows(table, idx)
+    assert torch.equal(out[0], table[3]) and torch.equal(out[3], table[9])
+    assert float(out[1].abs().sum()) == 0. and float(out[2].abs().sum()) == 0.
+    with pytest.raises(RuntimeError, match="row index"):
+        ops.check_device_errors()
+    ops.check_device_errors()  # the word was reset
+    dst = torch.zeros(10, 4, device=cuda)
+    ops.scatter_rows(torch.ones(4, 4, device=cuda), idx, dst)
+    assert float(dst.sum()) == 8. and float(dst[3].sum()) == 4. and float(dst[9].sum()) == 4.
+    with pytest.raises(RuntimeError, match="row index"):
+        ops.check_device_errors()
+    # relabel with a batch id outside the graph
+    rowptr = torch.tensor([0, 2, 4, 6, 8, 10, 12], device=cuda)
+    col = torch.tensor([1, 5, 0, 2, 1, 3, 2, 4, 3, 5, 4, 0], device=cuda)
+    rp, c, v, n_id = ops.relabel_one_hop(rowptr, col, None, torch.tensor([1, 77, 2], device=cuda), True)
+    assert rp.tolist() == [0, 2, 2, 4] and n_id.tolist()[:3] == [1, 77, 2]
+    with pytest.raises(RuntimeError, match="node id"):
+        ops.check_device_errors()
+    # and a clean call afterwards is clean
+    r = ops.relabel_one_hop(rowptr, col, None, torch.tensor([1, 2], device=cuda), True)
+    assert r[0].tolist() == [0, 2, 4] and r[1].tolist() == [2, 1, 0, 3] and r[3].tolist() == [1, 2, 0, 3]
+    ops.check_device_errors()

@@ -1,0 +1,279 @@
+"""Parity at BASELINE sizes and over time.
+
+  * one FULL-SIZE C3 partition (products shape, 2.45 M nodes / 64.3 M non-zeros): GPU relabel vs the C
+    oracle bit for bit, SpMM sum forward / transposed backward / IncAgg delta vs an fp64 CSR product;
+  * one FULL-DEGREE C4 batch (reddit shape, average degree ~492, F = 602 and 1024) and C5 slabs
+    (amazon-products shape, four aggregators over F = 256 slabs);
+  * a 5-epoch GCNII trajectory (train epoch + refresh sweep + micro-F1 per epoch) on the /16 twin against
+    oracle/gas.py in fp64, GAS and IncAgg;
+  * ``push_only`` and the ``aggregate_combined=False`` branch.
+
+Tolerances: bit-exact for relabel / copies; 1e-5 relative (fp32 vs fp64) for aggregation outputs and the
+early per-epoch losses, a stated drift bound for later epochs.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _rel(got, ref):
+    got = np.asarray(got, np.float64)
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def _csr64(rowptr, col, val, shape):
+    """fp64 CSR matrix (scipy): the same definition as oracle.spmm(sum), usable at 10^7 edges
+    (cross-checked against oracle.spmm in test_fp64_csr_helper_equals_the_oracle_definition)."""
+    from scipy.sparse import csr_matrix
+    v = np.ones(len(col), np.float64) if val is None else np.asarray(val, np.float64)
+    return csr_matrix((v, np.asarray(col, np.int64), np.asarray(rowptr, np.int64)), shape=shape)
+
+
+def test_fp64_csr_helper_equals_the_oracle_definition():
+    rng = np.random.default_rng(0)
+    deg = rng.integers(0, 9, 200)
+    rowptr = np.concatenate([[0], np.cumsum(deg)])
+    col = rng.integers(0, 300, rowptr[-1])
+    val = rng.standard_normal(rowptr[-1]).astype(np.float32)
+    X = rng.standard_normal((300, 17)).astype(np.float32)
+    a = _csr64(rowptr, col, val, (200, 300)) @ X.astype(np.float64)
+    b = oracle.spmm(rowptr, col, val, X, "sum", dtype=np.float64)
+    assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()
+
+
+@pytest.fixture(scope="module")
+def products(cuda):
+    import incagg_gnn_b200 as tga
+    data, ptr = tga.synthetic_graph(*tga.SHAPES['products'][:4], 150, seed=0, device=cuda)
+    adj = tga.gcn_norm(tga.set_diag(data.adj_t))
+    rowptr = adj.rowptr.to(torch.int64)
+    host = (rowptr.cpu().numpy(), adj.col.cpu().numpy().astype(np.int64), adj.value.cpu().numpy())
+    return adj, rowptr, ptr, host
+
+
+@pytest.mark.parametrize("part", [0, 77, 149])
+def test_full_size_c3_partition_matches_oracle(cuda, products, part):
+    from incagg_gnn_b200 import ops
+    from incagg_gnn_b200.sparse import SparseTensor
+    adj, rowptr, ptr, (h_rp, h_col, h_val) = products
+    lo, hi = int(ptr[part]), int(ptr[part + 1])
+    idx = torch.arange(lo, hi, device=cuda)
+    F = 128
+    # --- relabel_one_hop / _within_batch: bit-exact against the C restatement of relabel_cpu.cpp ---
+    got = ops.relabel_one_hop(rowptr, adj.col, adj.value, idx, True)
+    exp = oracle.relabel_one_hop(h_rp, h_col, h_val, idx.cpu().numpy(), True)
+    for g, e in zip(got, exp):
+        assert np.array_equal(g.cpu().numpy(), e)
+    gotw = ops.relabel_one_hop_within_batch(rowptr, adj.col, adj.value, idx, True)
+    expw = oracle.relabel_one_hop_within_batch(h_rp, h_col, h_val, idx.cpu().numpy(), True)
+    for g, e in zip(gotw, expw):
+        assert np.array_equal(g.cpu().numpy(), e)
+    b_rp, b_col, b_val, n_id = exp
+    B, R = hi - lo, n_id.size
+    assert B > 16000 and b_col.size > 300000
+    a = SparseTensor(rowptr=got[0], col=got[1], value=got[2], sparse_sizes=(B, R), is_sorted=True)
+    A64 = _csr64(b_rp, b_col, b_val, (B, R))
+    g = torch.Generator(device='cpu').manual_seed(part)
+    x = torch.randn(R, F, generator=g)
+    go = torch.randn(B, F, generator=g)
+    # --- forward, both kernels ---
+    ref = A64 @ x.numpy().astype(np.float64)
+    for variant in (-1, 0):
+        ops.tune("spmm_stream_variant", variant)
+        a.drop_caches()
+        out = ops.spmm_raw(a.rowptr, a.col, a.value, x.to(cuda), "sum", plan=a.plan())
+        assert _rel(out.cpu().numpy(), ref) <= RTOL, variant
+    # --- backward through autograd: A^T g, all source rows and the in-batch prefix ---
+    ref_b = A64.T @ go.numpy().astype(np.float64)
+    for variant in (-1, 0):
+        ops.tune("spmm_stream_variant", variant)
+        a.drop_caches()
+        xg = x.to(cuda).requires_grad_(True)
+        (a @ xg).backward(go.to(cuda))
+        assert _rel(xg.grad.cpu().numpy(), ref_b) <= RTOL
+        xg2 = x.to(cuda).requires_grad_(True)
+        a.matmul(xg2, grad_rows=B).backward(go.to(cuda))
+        assert _rel(xg2.grad[:B].cpu().numpy(), ref_b[:B]) <= RTOL
+    # --- IncAgg delta on the in-batch structure ---
+    w_rp, w_col, w_val, _ = expw
+    aw = SparseTensor(rowptr=gotw[0], col=gotw[1], value=gotw[2], sparse_sizes=(B, B), is_sorted=True)
+    m_in, m_ag = torch.randn(B, F, generator=g), torch.randn(B, F, generator=g)
+    ref_d = _csr64(w_rp, w_col, w_val, (B, B)) @ (x[:B].numpy().astype(np.float64) - m_in.numpy()) + m_ag.numpy()
+    for variant in (-1, 0):
+        ops.tune("spmm_stream_variant", variant)
+        aw.drop_caches()
+        out = ops.spmm_delta_raw(aw.rowptr, aw.col, aw.value, x[:B].to(cuda).contiguous(), m_in.to(cuda),
+                                 m_ag.to(cuda), None, "sum", plan=aw.plan())
+        assert _rel(out.cpu().numpy(), ref_d) <= RTOL
+    ops.tune("spmm_stream_variant", 0)
+
+
+@pytest.mark.parametrize("F", [602, 1024])
+def test_full_degree_c4_batch_matches_oracle(cuda, F):
+    """Reddit shape (232,965 nodes, 114.6 M non-zeros, average degree ~492): a batch of 20 of the 200
+    partitions (23 K rows, ~11 M edges, halo = most of the graph), mean aggregation as GraphSAGE uses it
+    (values stripped), feature widths of the first layer (602) and the hidden layers (1024)."""
+    import incagg_gnn_b200 as tga
+    from incagg_gnn_b200 import ops
+    from incagg_gnn_b200.sparse import SparseTensor
+    data, ptr = tga.synthetic_graph(*tga.SHAPES['reddit'][:4], 200, seed=0, device=cuda)
+    adj = tga.set_diag(data.adj_t)
+    rowptr = adj.rowptr.to(torch.int64)
+    idx = torch.arange(int(ptr[40]), int(ptr[60]), device=cuda)
+    rp, col, _, n_id = ops.relabel_one_hop(rowptr, adj.col, None, idx, True, out_int32=True)
+    B, R = idx.numel(), n_id.numel()
+    assert col.numel() > 8_000_000 and col.numel() / B > 300
+    a = SparseTensor(rowptr=rp, col=col, value=None, sparse_sizes=(B, R), is_sorted=True)
+    g = torch.Generator(device='cpu').manual_seed(F)
+    x = torch.randn(R, F, generator=g)
+    A64 = _csr64(rp.cpu().numpy(), col.cpu().numpy(), None, (B, R))
+    deg = np.maximum(np.diff(rp.cpu().numpy()), 1)[:, None]
+    ref = (A64 @ x.numpy().astype(np.float64)) / deg
+    out = a.matmul(x.to(cuda), reduce="mean")
+    assert _rel(out.cpu().numpy(), ref) <= RTOL
+    # max aggregation (PNA / SAGE-max): values exact, equal to the fp32 definition on a row sample
+    out_max = a.matmul(x.to(cuda), reduce="max").cpu().numpy()
+    rp_h, col_h = rp.cpu().numpy(), col.cpu().numpy()
+    xs = x.numpy()
+    for r in (0, 1, B // 2, B - 1):
+        seg = xs[col_h[rp_h[r]:rp_h[r + 1]]]
+        assert np.array_equal(out_max[r], seg.max(0))
+
+
+def test_c5_slab_set_matches_oracle(cuda):
+    """Amazon-products shape (1.57 M nodes, 264 M non-zeros): four partitions of 200 as one batch,
+    K = 4 slabs of F = 256 reduced with sum / mean / min / max in one launch (PNA, pna.py:66-84)."""
+    import incagg_gnn_b200 as tga
+    from incagg_gnn_b200 import ops
+    data, ptr = tga.synthetic_graph(*tga.SHAPES['amazonproducts'][:4], 200, seed=0, device=cuda)
+    adj = tga.set_diag(data.adj_t)
+    rowptr = adj.rowptr.to(torch.int64)
+    idx = torch.arange(int(ptr[10]), int(ptr[14]), device=cuda)
+    rp, col, _, n_id = ops.relabel_one_hop(rowptr, adj.col, None, idx, True, out_int32=True)
+    B, R, F, K = idx.numel(), n_id.numel(), 256, 4
+    assert col.numel() > 4_000_000
+    g = torch.Generator(device='cpu').manual_seed(5)
+    x = torch.randn(R, K * F, generator=g)
+    out = ops.spmm_multi_raw(rp, col, None, x.to(cuda), F, ["sum", "mean", "min", "max"]).cpu().numpy()
+    rp_h, col_h = rp.cpu().numpy(), col.cpu().numpy()
+    A64 = _csr64(rp_h, col_h, None, (B, R))
+    x64 = x.numpy().astype(np.float64)
+    deg = np.maximum(np.diff(rp_h), 1)[:, None]
+    assert _rel(out[:, :F], A64 @ x64[:, :F]) <= RTOL
+    assert _rel(out[:, F:2 * F], (A64 @ x64[:, F:2 * F]) / deg) <= RTOL
+    xs = x.numpy()
+    for r in (0, B // 3, B - 1):
+        seg = xs[col_h[rp_h[r]:rp_h[r + 1]]]
+        assert np.array_equal(out[r, 2 * F:3 * F], seg[:, 2 * F:3 * F].min(0))
+        assert np.array_equal(out[r, 3 * F:], seg[:, 3 * F:].max(0))
+
+
+# ---- five epochs of the reference loop --------------------------------------------------------------
+@pytest.mark.parametrize("vr", [False, True])
+def test_gcn2_five_epoch_trajectory_matches_oracle(cuda, vr):
+    """main.py:226-261 on the /16 products twin (153 K nodes, 4 M non-zeros, 150 partitions, batch 1,
+    GCNII 5 x 128): every epoch = mini_train over all partitions + the layer-wise sweep (refresh of the
+    history tables; logits) + accuracy on the train / val / test masks.  fp32 GPU path vs fp64 oracle:
+    epoch losses within 1e-5 for the first two epochs; later epochs within 2e-4 (750 Adam steps whose
+    sign-like early updates amplify fp32 rounding of tiny gradients); accuracies within 0.2 % absolute."""
+    from test_gpu_models import _setup, _oracle_batches, _groups
+    from incagg_gnn_b200.train import mini_train, mini_test
+    import incagg_gnn_b200 as tga
+    run, gas, omodel, adj, raw = _setup(cuda, 'C3', 16, dict(VR_update=vr))
+    model, ptr, conf = run['model'], run['ptr'], run['conf']
+    P = conf['num_parts']
+    ev = _oracle_batches(gas, adj, raw, ptr, _groups(P, 1), False)
+    tr = _oracle_batches(gas, adj, raw, ptr, _groups(P, 1), True) if vr else ev
+    o_opt = torch.optim.Adam(omodel.parameters(), lr=conf['lr'])
+    mini_test(model, run['eval_loader'], VR_update=vr)            # main.py:211-215: fill the tables
+    omodel.mini_inference(ev, vr=vr)
+    data = run['data']
+    y = raw.y
+    masks = {k: getattr(raw, k) for k in ('train_mask', 'val_mask', 'test_mask')}
+    for epoch in range(5):
+        res = mini_train(model, run['train_loader'], run['criterion'], run['optimizer'], run['max_steps'],
+                         grad_norm=conf['grad_norm'], VR_update=vr, epoch=epoch)
+        o_res = gas.train_epoch(omodel, tr, o_opt, vr=vr, grad_norm=conf['grad_norm'])
+        tol = RTOL if epoch < 2 else 2e-4
+        assert abs(res['loss'] - o_res['loss']) <= tol * abs(o_res['loss']), (epoch, res['loss'], o_res['loss'])
+        out = mini_test(model, run['eval_loader'], VR_update=vr).cpu()
+        o_out = omodel.mini_inference(ev, vr=vr).float()
+        for name, m in masks.items():
+            acc = tga.compute_micro_f1(out, y, m)
+            o_acc = tga.compute_micro_f1(o_out, y, m)
+            assert abs(acc - o_acc) <= 2e-3, (epoch, name, acc, o_acc)
+    assert res['loss'] < 3.85   # it trains: ln(47) = 3.85 is the loss of a uniform prediction
+
+
+# ---- push_only, aggregate_combined = False ---------------------------------------------------------------
+@pytest.mark.parametrize("history_device", ['cuda', None])
+def test_push_only(cuda, history_device):
+    """ScalableGNN.push_only (models/base.py:458-499): the batch rows of x land in the history table at
+    their global rows (partition slices), nothing else changes, x[:B] is returned; also through the
+    pinned-host AsyncIOPool branch."""
+    from test_gpu_models import _setup
+    run, *_ = _setup(cuda, 'C3', 64, dict(VR_update=False), history_device=history_device, num_parts=6)
+    model = run['model']
+    sub = next(iter(run['train_loader']))
+    batch, B, n_id, offset, count = sub
+    hist = model.histories[2]
+    before = hist.emb.clone()
+    x = torch.randn(n_id.numel(), model.hidden_channels, device=cuda)
+    model._async = model.pool is not None
+    out, _ = model.push_only(hist, x, B, n_id, offset, count)
+    if model.pool is not None:
+        model.pool.synchronize_push()
+    model._async = False
+    torch.cuda.synchronize()
+    assert torch.equal(out, x[:B])
+    o, c = int(offset[0]), int(count[0])
+    assert c == B
+    assert torch.equal(hist.emb[o:o + c].to(cuda), x[:B])
+    after = hist.emb.clone()
+    after[o:o + c] = before[o:o + c]
+    assert torch.equal(after, before)
+    # full-table and index forms (base.py:462-470)
+    full = torch.randn(model.num_nodes, model.hidden_channels, device=cuda)
+    r = model.push_only(hist, full)
+    assert torch.equal(hist.emb.to(cuda), full) and torch.equal(r[0], full)
+    ids = torch.tensor([5, 1, 9], device=cuda)
+    rows = torch.randn(3, model.hidden_channels, device=cuda)
+    model.push_only(hist, rows, None, ids)
+    assert torch.equal(hist.emb[ids.to(hist.emb.device)].to(cuda), rows)
+
+
+@pytest.mark.parametrize("config,scale,parts,bs", [('C3', 64, 6, 1), ('C1', 8, 6, 3), ('C2', 16, 8, 4),
+                                                   ('C4', 64, 8, 4)])
+def test_aggregate_combined_false_matches_oracle(cuda, config, scale, parts, bs):
+    """aggregate_combined=False (gcn.py:117-141): only edges with both ends in the batch are aggregated,
+    the [B, B+H] shape is kept.  Forward logits of a GAS step vs the oracle, both settings."""
+    from test_gpu_models import _setup, _oracle_batches, _groups
+    from incagg_gnn_b200.train import mini_test
+    ov = dict(VR_update=False, batch_size=bs)
+    if config == 'C4':
+        ov['architecture'] = dict(hidden_channels=256)
+    run, gas, omodel, adj, raw = _setup(cuda, config, scale, ov, num_parts=parts)
+    model, ptr = run['model'], run['ptr']
+    mini_test(model, run['eval_loader'], VR_update=False)
+    ev = _oracle_batches(gas, adj, raw, ptr, _groups(parts, bs), False)
+    omodel.mini_inference(ev, vr=False)
+    model.eval()
+    with torch.no_grad():
+        for combined in (True, False):
+            for sub, ob in zip(run['eval_loader'], ev):
+                batch, B, n_id, offset, count = sub
+                out = model(batch.x, batch.adj_t, B, n_id, offset, count, aggregate_combined=combined)['out']
+                ref = omodel.forward(ob, aggregate_combined=combined)
+                assert float((out.cpu().double() - ref).abs().max()) <= RTOL * float(ref.abs().max()), \
+                    (config, combined)
+    # the two settings really differ (the halo contributes)
+    sub, ob = next(iter(run['eval_loader'])), ev[0]
+    a = omodel.forward(ob, aggregate_combined=True)
+    b = omodel.forward(ob, aggregate_combined=False)
+    assert float((a - b).abs().max()) > 1e-3 * float(a.abs().max())
