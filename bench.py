@@ -174,8 +174,8 @@ def timed_steps_graphed(run, mode, warmup, steps, dist):
     model, opt, loader, conf = run["model"], run["optimizer"], run["train_loader"], run["conf"]
     averager = None
     if dist is not None:
-        from incagg_gnn_b200.parallel import GradAverager
-        averager = GradAverager(model.parameters(), run["shard"], flat=getattr(opt, "flat_g", None))
+        from incagg_gnn_b200.parallel import make_grad_sync
+        averager = make_grad_sync(model, opt, run["shard"], conf["grad_norm"], TRANSPORT)
     tr = GraphedTrainer(model, loader, opt, VR_update=(mode == "incagg"), grad_norm=conf["grad_norm"],
                         averager=averager, pipeline_collate=loader.fixed_batches and not NO_PIPELINE)
     rp_host, ptr = loader._rowptr_host, loader.ptr
@@ -239,8 +239,9 @@ def timed_steps(run, mode, warmup, steps, dist, e2e=False):
 
     averager = None
     if dist is not None:
-        from incagg_gnn_b200.parallel import GradAverager
-        averager = GradAverager(model.parameters(), run["shard"], flat=getattr(opt, "flat_g", None))
+        from incagg_gnn_b200.parallel import make_grad_sync
+        averager = make_grad_sync(model, opt, run["shard"], conf["grad_norm"], TRANSPORT)
+    fused = getattr(averager, "fused", False)
     h2d = d2h = 0
 
     def one_step(sub):
@@ -259,11 +260,14 @@ def timed_steps(run, mode, warmup, steps, dist, e2e=False):
         w = m.to(out.dtype)
         loss = (torch.nn.functional.cross_entropy(out, y, reduction="none") * w).sum() / w.sum().clamp(min=1.)
         loss.backward()
-        if averager is not None:
-            averager()  # NCCL all-reduce of the flat gradient buffer (p.grad are views into it)
-        if conf["grad_norm"] is not None:
-            torch.nn.utils.clip_grad_norm_(model.parameters(), conf["grad_norm"])
-        opt.step()
+        if fused:
+            averager.step()  # peer-memory all-reduce + Adam, one kernel (parallel.FusedGradSync)
+        else:
+            if averager is not None:
+                averager()  # NCCL all-reduce of the flat gradient buffer (p.grad are views into it)
+            if conf["grad_norm"] is not None:
+                torch.nn.utils.clip_grad_norm_(model.parameters(), conf["grad_norm"])
+            opt.step()
         if e2e:
             lv = float(loss)  # device -> host read of the step's result
             d2h += 4
@@ -363,6 +367,7 @@ def load_peaks():
 
 _REAL_STDOUT = None
 NO_PIPELINE = False   # --no-pipeline: collate inside the step graph instead of one step ahead
+TRANSPORT = "p2p"
 
 
 def _claim_stdout():
@@ -382,9 +387,10 @@ def _emit(line: dict):
 
 
 def main():
-    global NO_PIPELINE
+    global NO_PIPELINE, TRANSPORT
     args = parse_args()
     NO_PIPELINE = args.no_pipeline
+    TRANSPORT = args.transport
     _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -465,9 +471,9 @@ def main():
         ld = run_h["train_loader"]
         averager_h = None
         if dist is not None:
-            from incagg_gnn_b200.parallel import GradAverager
-            averager_h = GradAverager(run_h["model"].parameters(), run_h["shard"],
-                                      flat=getattr(run_h["optimizer"], "flat_g", None))
+            from incagg_gnn_b200.parallel import make_grad_sync
+            averager_h = make_grad_sync(run_h["model"], run_h["optimizer"], run_h["shard"],
+                                        run_h["conf"]["grad_norm"], args.transport)
         tr = GraphedTrainer(run_h["model"], ld, run_h["optimizer"], VR_update=vr,
                             grad_norm=run_h["conf"]["grad_norm"], averager=averager_h, pipeline_collate=True)
         groups = ld._batches_of_epoch()
@@ -630,7 +636,11 @@ def main():
                                                   f", sharded by partition over {world} ranks; halo rows via "
                                                   + ("NVLink peer loads inside the gather kernel (CUDA IPC)"
                                                      if args.transport == "p2p" else "NCCL all-to-all-v")
-                                                  + ", gradients NCCL all-reduce"),
+                                                  + (", gradients exchanged through NVLink peer memory inside the "
+                                                     "Adam kernel (one graph per step, no collective call)"
+                                                     if args.transport == "p2p" and conf["grad_norm"] is None
+                                                     and os.environ.get("INCAGG_FUSED_ALLREDUCE", "1") != "0"
+                                                     else ", gradients NCCL all-reduce")),
                    "step_issue": ("eager (Python launches)" if graphs is None else
                                   f"CUDA graph per partition batch ({graphs['captured']} graphs captured before the "
                                   f"timed region in {graphs['capture_s']} s; every replay re-runs collate, forward, "

@@ -48,6 +48,10 @@ _PROTOS = {
     "incagg_launch_count": (c_int64, []),
     "incagg_tune_set": (c_int, [c_int, c_int]),
     "incagg_device_errors": (c_int, [P, c_int]),
+    "incagg_allreduce_adam_blocks": (c_int, []),
+    "incagg_allreduce_adam_max_ranks": (c_int, []),
+    "incagg_allreduce_adam_step": (c_int, [P, P, c_int, c_int, P, P, P, P, c_int64, c_int64, c_float, c_float,
+                                           c_float, c_float, c_float, c_float, P, P, P]),
     "incagg_device_info": (c_int, [P, P, P]),
     "incagg_enable_peer_access": (c_int, [c_int]),
     "incagg_spmm_plan_bytes": (c_size_t, [c_int64, c_int64]),

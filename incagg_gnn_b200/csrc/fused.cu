@@ -262,3 +262,131 @@ extern "C" int incagg_adam_step(float* params, const float* grads, float* exp_av
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }
+
+
+// ---- gradient all-reduce over NVLink peer memory fused with the Adam update ---------------------------
+//
+// Data-parallel step on W GPUs of one NVSwitch box: the gradient buffers are small (GCNII 5 x 128:
+// 0.2 M floats), so a ring / tree collective is all latency.  One kernel per rank does the whole
+// exchange and the optimizer update:
+//   1. block b copies its slice of the local gradient into a staging buffer (two buffers, selected by
+//      the parity of the step number) and publishes "slice b of step t is staged" in every peer's
+//      signal array with a system-scope release store;
+//   2. it waits until every peer has published the same slice (acquire loads on its own signal array,
+//      which the peers write over NVLink), then reads the peers' staged slices straight out of their
+//      HBM (volatile loads: the lines of step t-2 may still sit in this SM's L1);
+//   3. the contributions are added IN RANK ORDER (bit-identical sums on every rank, so the replicas
+//      stay identical without a broadcast), divided by W and fed to the Adam update of the slice.
+// There is no barrier at the end: a staging buffer is rewritten at step t + 2, which a rank can only
+// reach after every peer has entered step t + 1, i.e. (stream order) finished reading step t.
+// The blocks of one launch do not depend on each other (each slice has its own signals), so no
+// co-residency of the grid is assumed; ranks run on different GPUs (one process per GPU).
+// A wait that lasts longer than ~10 s sets INCAGG_DEVERR_PEER_TIMEOUT and proceeds instead of hanging.
+namespace incagg {
+constexpr int AR_MAX_RANKS = 16;
+constexpr int AR_BLOCKS = 32;
+struct ArPeers {
+  float* stage[AR_MAX_RANKS];     // [2][n] staging buffers of every rank (own + peers, IPC-mapped)
+  int32_t* signal[AR_MAX_RANKS];  // [AR_BLOCKS][AR_MAX_RANKS] signal arrays of every rank
+};
+
+__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+allreduce_adam_kernel(const ArPeers peers, int rank, int world, float* __restrict__ g, float* __restrict__ p,
+                      float* __restrict__ m, float* __restrict__ v, int64_t n, int64_t n_decay, float lr,
+                      float b1, float b2, float eps, float wd_first, float wd_rest, float* step,
+                      unsigned int* arrivals, int32_t* err) {
+  pdl_prologue();
+  const float t = step[0] + 1.f;
+  const int epoch = (int)t;
+  const int64_t par = (int64_t)(epoch & 1) * n;
+  // slice of this block (multiples of 4 elements)
+  int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  per = (per + 3) / 4 * 4;
+  const int64_t lo = min(n, (int64_t)blockIdx.x * per), hi = min(n, lo + per);
+  float* mine = peers.stage[rank] + par;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) mine[i] = g[i];
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
+    st_release_sys(peers.signal[threadIdx.x] + blockIdx.x * AR_MAX_RANKS + rank, epoch);
+    const int32_t* flag = peers.signal[rank] + blockIdx.x * AR_MAX_RANKS + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < epoch) {
+      if (clock64() - t0 > (1ll << 34)) {  // ~10 s: a peer is gone; do not hang the GPU
+        if (err) atomicOr(err, INCAGG_DEVERR_PEER_TIMEOUT);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / bc1;
+  const float inv_w = 1.f / (float)world;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    float gi = 0.f;
+    for (int r = 0; r < world; ++r) {
+      const float c = (r == rank) ? g[i] : __ldcv(peers.stage[r] + par + i);
+      gi += c;
+    }
+    gi *= inv_w;
+    g[i] = gi;  // the averaged gradient stays readable (p.grad)
+    float pi = p[i];
+    const float wd = i < n_decay ? wd_first : wd_rest;
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float m0 = m[i];
+    const float mi = m0 + (1.f - b1) * (gi - m0);
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(arrivals, 1u);
+    if (prev == gridDim.x - 1) {
+      step[0] = t;
+      *arrivals = 0u;
+    }
+  }
+}
+}  // namespace incagg
+
+extern "C" int incagg_allreduce_adam_blocks(void) { return incagg::AR_BLOCKS; }
+extern "C" int incagg_allreduce_adam_max_ranks(void) { return incagg::AR_MAX_RANKS; }
+
+extern "C" int incagg_allreduce_adam_step(void* const* stage_ptrs, void* const* signal_ptrs, int rank, int world,
+                                          float* grads, float* params, float* exp_avg, float* exp_avg_sq,
+                                          int64_t n, int64_t n_first_group, float lr, float beta1, float beta2,
+                                          float eps, float wd_first_group, float wd_rest, float* step_dev,
+                                          void* arrivals_dev, incagg_stream_t stream) {
+  using namespace incagg;
+  IA_CHECK_ARG(world >= 1 && world <= AR_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world size");
+  IA_CHECK_ARG(n >= 0 && n_first_group >= 0 && n_first_group <= n, "bad sizes");
+  if (n == 0) return INCAGG_OK;
+  IA_CHECK_ARG(stage_ptrs && signal_ptrs && grads && params && exp_avg && exp_avg_sq && step_dev && arrivals_dev,
+               "NULL argument");
+  ArPeers peers;
+  for (int r = 0; r < AR_MAX_RANKS; ++r) {
+    peers.stage[r] = r < world ? static_cast<float*>(stage_ptrs[r]) : nullptr;
+    peers.signal[r] = r < world ? static_cast<int32_t*>(signal_ptrs[r]) : nullptr;
+    IA_CHECK_ARG(r >= world || (peers.stage[r] && peers.signal[r]), "rank %d: NULL staging / signal buffer", r);
+  }
+  launch(allreduce_adam_kernel, dim3(AR_BLOCKS), dim3(256), (size_t)(0), as_stream(stream), peers, rank, world, grads,
+         params, exp_avg, exp_avg_sq, n, n_first_group, lr, beta1, beta2, eps, wd_first_group, wd_rest, step_dev,
+         static_cast<unsigned int*>(arrivals_dev), device_error_word());
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}

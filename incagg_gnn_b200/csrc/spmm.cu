@@ -141,6 +141,7 @@ struct SpmmParams {
   int32_t part_slots;
   // stream kernel: partial sums of rows cut by a warp boundary, arrival counters, mean flag
   int32_t* row_counter;     // [ROW_COUNTERS + 1] next short row per feature tile, CTAs done (zero between calls)
+  int32_t dynamic;          // short rows handed out through row_counter (large structures)
   float* ws_part;           // [tiles][n_wslots][2][WS_TILE_F]
   int32_t* ws_done;         // [tiles][n_wslots]
   int32_t mean;
@@ -362,22 +363,34 @@ spmm_kernel(const SpmmParams p) {
 
   if ((int)blockIdx.x >= p.long_grid) {
     // ---- short rows ----
-    // The CTAs of this part are one resident wave; every warp fetches its next ROW_GRAB * (32 / G)
-    // rows from a counter until the rows are used up, so no warp slot idles while a CTA waits for
-    // its longest row (rows differ in length by two orders of magnitude) and there is no tail of
-    // partially filled waves.  Which warp computes a row does not affect the result.
+    // Batch-sized structures (a few waves of CTAs): every warp owns 32 / G rows, fixed by its position
+    // in the grid.  Large structures (a whole-graph sweep, tens of waves): the CTAs are one resident
+    // wave and every warp fetches its next ROW_GRAB * (32 / G) rows from a counter until the rows are
+    // used up, so no warp slot idles while a CTA waits for its longest row (rows differ in length by
+    // two orders of magnitude).  Measured on the products shape: dynamic 2.36 ms vs 3.03 ms on the
+    // 64 M-edge graph, but 47 us vs 35 us on a 0.43 M-edge batch (the trip to the counter adds a
+    // dependent latency per grab that two or three grabs per warp do not amortise).  Which warp
+    // computes a row does not affect the result.
     constexpr int RPW = 32 / G;  // rows a warp works on at a time
     const int lane_g = threadIdx.x % G;
     const int sub = lane / G;  // group index inside the warp
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
     int32_t* counter = p.row_counter + blockIdx.y;
+    const int n_i = p.dynamic ? ROW_GRAB : 1;
+    bool first = true;
     for (;;) {
       int base = 0;
-      if (lane == 0) base = atomicAdd(counter, ROW_GRAB * RPW);
-      base = __shfl_sync(0xffffffffu, base, 0);
+      if (p.dynamic) {
+        if (lane == 0) base = atomicAdd(counter, ROW_GRAB * RPW);
+        base = __shfl_sync(0xffffffffu, base, 0);
+      } else {  // static assignment: every warp owns RPW rows, the grid covers all rows
+        if (!first) break;
+        first = false;
+        base = (int)(((int64_t)(blockIdx.x - p.long_grid) * (SPMM_THREADS / 32) + (threadIdx.x >> 5)) * RPW);
+      }
       if ((int64_t)base >= p.rows) break;
 #pragma unroll 1
-      for (int i = 0; i < ROW_GRAB; ++i) {
+      for (int i = 0; i < n_i; ++i) {
         const int64_t row = (int64_t)base + i * RPW + sub;
         if (row >= p.rows) break;  // (uniform per group; groups of a warp do not communicate)
         const int s = __ldg(p.rowptr + row), e = __ldg(p.rowptr + row + 1);
@@ -392,6 +405,7 @@ spmm_kernel(const SpmmParams p) {
         finish_row<REDUCE, VEC, G, NCH, DELTA, ARG>(p, op, row, e - s, fbase, flim, lane_g, acc, arg);
       }
     }
+    if (!p.dynamic) return;
     // the last CTA of the launch to get here leaves the counters at zero for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1161,9 +1175,18 @@ static int chunk_edges() { static int v = env_int("INCAGG_SPMM_CHUNK", 0); retur
 // Stream (merge-path) kernel configuration (gathers per buffer x CTAs of 8 warps per SM):
 // variant 0 = 8 x 2, 1 = 4 x 4, 2 = 4 x 3, 3 = 2 x 5, 4 = 2 x 6, 5 = 16 x 1.  The number of warp slots is
 // one resident wave.
+// Which kernel serves wide sum / mean products.  -2 (default) = by measurement on the products shape
+// (profiles/r02_spmm_variants.md): the row kernel for plain products (35 us vs 35-41 us per batch,
+// 2.4-3.0 ms vs 4.7 ms on the whole graph), the merge-path kernel (variant 2) for the incremental-
+// aggregation delta form (44 us vs 49 us); -1 = row kernel everywhere; >= 0 = that merge-path variant.
 static int stream_variant() {
-  static int dflt = env_int("INCAGG_SPMM_STREAM", 0);  // -1: row-per-warp kernel everywhere
+  static int dflt = env_int("INCAGG_SPMM_STREAM", -2);
   return incagg::tune_get(INCAGG_TUNE_SPMM_STREAM_VARIANT, dflt);
+}
+static int stream_variant_for(bool delta) {
+  const int v = stream_variant();
+  if (v == -2) return delta ? 2 : -1;
+  return v;
 }
 static int stream_min_f() { return incagg::tune_get(INCAGG_TUNE_SPMM_STREAM_MIN_F, 65); }
 static int stream_ctas_per_sm(int variant) {
@@ -1171,7 +1194,8 @@ static int stream_ctas_per_sm(int variant) {
   return variant == 1 ? 4 : (variant == 2 ? 3 : (variant == 3 ? 5 : (variant == 4 ? 6 : (variant == 5 ? 1 : 2))));
 }
 static int stream_wslots() {
-  int n = sm_count() * stream_ctas_per_sm(stream_variant()) * WS_WARPS;
+  const int v = stream_variant();
+  int n = sm_count() * stream_ctas_per_sm(v == -2 ? 2 : v) * WS_WARPS;
   return n > WS_MAX_SLOTS ? WS_MAX_SLOTS : n;
 }
 
@@ -1252,7 +1276,8 @@ static int get_scratch(SpmmScratch** out, int64_t want_plan_capacity) {
 // Wide sum / mean products through the merge-path kernel.  Returns 1 when the call does not qualify
 // (the caller falls through to the row kernel), an error code, or INCAGG_OK after the launch.
 static int try_stream(SpmmParams& p, int reduce, int vec, cudaStream_t st) {
-  if (stream_variant() < 0) return 1;
+  const int variant = stream_variant_for(p.m_in != nullptr);
+  if (variant < 0) return 1;
   if (vec != 4 || p.F < stream_min_f() || p.F > WS_TILE_F * WS_MAX_TILES) return 1;
   if ((reduce != R_SUM && reduce != R_MEAN) || p.arg != nullptr || p.n_id != nullptr) return 1;
   if (p.rows >= 0x7fffffff || p.ldx >= (1ll << 30) || p.ld_in >= (1ll << 30)) return 1;
@@ -1269,7 +1294,6 @@ static int try_stream(SpmmParams& p, int reduce, int vec, cudaStream_t st) {
   p.ws_part = sc->ws_part;
   p.ws_done = sc->ws_done;
   p.mean = (reduce == R_MEAN);
-  const int variant = stream_variant();
   const int n_w = stream_wslots();
   const int tiles = (p.F + WS_TILE_F - 1) / WS_TILE_F;
   dim3 grid((unsigned)((n_w + WS_WARPS - 1) / WS_WARPS), (unsigned)tiles);
@@ -1346,8 +1370,11 @@ static int launch_cfg(SpmmParams& p, int n_tiles, int64_t items_bound, cudaStrea
                                                           SPMM_THREADS, 0));
     ctas_per_sm = n > 0 ? n : 1;
   }
+  // dynamic row hand-out pays off from ~8 waves of CTAs on (INCAGG_SPMM_DYNAMIC=0/1 forces it)
+  static int force_dyn = env_int("INCAGG_SPMM_DYNAMIC", -1);
   int64_t n_short = (int64_t)ctas_per_sm * sm_count();
-  if (blocks < n_short) n_short = blocks;
+  p.dynamic = force_dyn >= 0 ? force_dyn : (blocks > 8 * n_short);
+  if (!p.dynamic || blocks < n_short) n_short = blocks;
   dim3 grid((unsigned)(n_short + lg), (unsigned)n_tiles);
   launch(spmm_kernel<REDUCE, VEC, G, NCH, DELTA, ARG>, dim3(grid), dim3(SPMM_THREADS), (size_t)(0), st, p);
   IA_LAUNCH_CHECK();

@@ -43,6 +43,8 @@ def check_device_errors(reset: bool = True) -> None:
             what.append("gather / scatter row index outside the table")
         if word.value & 2:
             what.append("relabel: batch node id outside [0, num_nodes)")
+        if word.value & 4:
+            what.append("fused gradient all-reduce: a peer rank did not arrive within ~10 s")
         raise RuntimeError("incagg_b200 device error: " + "; ".join(what))
 
 
@@ -360,6 +362,23 @@ def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, n_first: int, lr: floa
     check(lib.incagg_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), int(n_first), float(lr), float(beta1),
                                float(beta2), float(eps), float(wd_first), float(wd_rest), ptr(step), ptr(arrivals),
                                _stream()))
+
+
+def allreduce_adam_step(stage_views, signal_views, rank: int, g: Tensor, p: Tensor, m: Tensor, v: Tensor,
+                        n_first: int, lr: float, beta1: float, beta2: float, eps: float, wd_first: float,
+                        wd_rest: float, step: Tensor, arrivals: Tensor) -> None:
+    """Gradient all-reduce over NVLink peer memory fused with the Adam update (incagg_allreduce_adam_step).
+    stage_views[r] / signal_views[r]: rank r's staging / signal tensors (peers opened through CUDA IPC)."""
+    import ctypes
+    _require_cuda(g, p, m, v, step, arrivals, *stage_views, *signal_views)
+    W = len(stage_views)
+    st = (ctypes.c_void_p * W)(*[t.data_ptr() for t in stage_views])
+    sg = (ctypes.c_void_p * W)(*[t.data_ptr() for t in signal_views])
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_allreduce_adam_step(ctypes.cast(st, ctypes.c_void_p), ctypes.cast(sg, ctypes.c_void_p),
+                                         int(rank), W, ptr(g), ptr(p), ptr(m), ptr(v), p.numel(), int(n_first),
+                                         float(lr), float(beta1), float(beta2), float(eps), float(wd_first),
+                                         float(wd_rest), ptr(step), ptr(arrivals), _stream()))
 
 
 # --------------------------------------------------------------------------------------------

@@ -227,3 +227,74 @@ class GradAverager:
     def __call__(self):
         self.all_reduce()
         self.scale()
+
+
+class FusedGradSync:
+    """Gradient exchange of the data-parallel step WITHOUT a collective call: one kernel per rank
+    (``incagg_allreduce_adam_step``) stages its gradient slice, signals the peers through NVLink peer
+    memory, reads the peers' slices out of their HBM, adds them in rank order, and applies the Adam
+    update - all-reduce, scaling and optimizer in a single launch that a CUDA graph can contain, so a
+    training step at N GPUs is ONE graph replay (the NCCL path splits it into two graphs around a
+    host-issued ``all_reduce``).  Needs ``train.FlatAdam`` (flat parameter / gradient / moment buffers)
+    and no gradient clipping; every rank computes bit-identical parameters.
+
+    Same surface as :class:`GradAverager` where the training loop touches it (``zero``), plus ``step``
+    which replaces ``all_reduce`` + ``scale`` + ``optimizer.step``."""
+
+    fused = True
+
+    def __init__(self, optimizer, shard: Shard):
+        from . import _lib
+        if not hasattr(optimizer, 'flat_g'):
+            raise RuntimeError('FusedGradSync needs train.FlatAdam (flat gradient / moment buffers)')
+        if shard.world_size > _lib.lib.incagg_allreduce_adam_max_ranks():
+            raise RuntimeError('too many ranks for the fused gradient exchange')
+        self.opt, self.shard = optimizer, shard
+        self.flat = optimizer.flat_g
+        n = self.flat.numel()
+        dev = self.flat.device
+        self.stage = torch.zeros(2 * n, dtype=torch.float32, device=dev)
+        self.signal = torch.zeros(_lib.lib.incagg_allreduce_adam_blocks() * _lib.lib.incagg_allreduce_adam_max_ranks(),
+                                  dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        self.stage_views = open_peer_views(self.stage, shard)
+        self.signal_views = open_peer_views(self.signal, shard)
+        # the step counters of all ranks must agree (they are the epoch numbers of the signals)
+        if shard.world_size > 1:
+            t = optimizer.step_t.clone()
+            dist.broadcast(t, _global_rank(0, shard), group=shard.group)
+            if float(t) != float(optimizer.step_t):
+                raise RuntimeError('FusedGradSync: the ranks have taken different numbers of optimizer steps')
+            dist.barrier(group=shard.group)   # every signal array is zeroed and mapped before the first step
+
+    def zero(self):
+        self.flat.zero_()
+
+    def step(self):
+        from . import ops
+        o = self.opt
+        g0 = o.param_groups[0]
+        wd_rest = o.param_groups[1]['weight_decay'] if len(o.param_groups) > 1 else g0['weight_decay']
+        ops.allreduce_adam_step(self.stage_views, self.signal_views, self.shard.rank, o.flat_g, o.flat_p,
+                                o.exp_avg, o.exp_avg_sq, o.n_first, g0['lr'], g0['betas'][0], g0['betas'][1],
+                                g0['eps'], g0['weight_decay'], wd_rest, o.step_t, o._arrivals)
+
+    # GradAverager surface, for loops written against it
+    def all_reduce(self):
+        raise RuntimeError('FusedGradSync exchanges gradients inside step()')
+
+    def scale(self):
+        pass
+
+    def __call__(self):
+        raise RuntimeError('FusedGradSync: call step() instead of averager() + optimizer.step()')
+
+
+def make_grad_sync(model, optimizer, shard: Shard, grad_norm=None, transport: str = 'p2p'):
+    """The gradient exchange of a sharded run: the fused peer-memory kernel when it applies (p2p
+    transport, FlatAdam, no clipping), else one NCCL all_reduce per step."""
+    import os
+    if (shard.world_size > 1 and transport == 'p2p' and grad_norm is None and hasattr(optimizer, 'flat_g')
+            and os.environ.get('INCAGG_FUSED_ALLREDUCE', '1') != '0'):
+        return FusedGradSync(optimizer, shard)
+    return GradAverager(model.parameters(), shard, flat=getattr(optimizer, 'flat_g', None))

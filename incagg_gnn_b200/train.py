@@ -187,7 +187,8 @@ def forward_backward(model, sub, optimizer, VR_update=False, averager=None, epoc
         loss, out3 = masked_cross_entropy(out, y, train_mask)
         # (single-GPU path; with a gradient averager the step keeps the one-stream backward that the
         # multi-GPU runs of this round were measured and checked with)
-        with (weight_grads_on_side_stream(out.device) if averager is None else contextlib.nullcontext()):
+        one_graph = averager is None or getattr(averager, 'fused', False)
+        with (weight_grads_on_side_stream(out.device) if one_graph else contextlib.nullcontext()):
             loss.backward()
         return out3[0], out3[2]
     w = train_mask.to(out.dtype)
@@ -201,6 +202,10 @@ def forward_backward(model, sub, optimizer, VR_update=False, averager=None, epoc
 
 def apply_update(model, optimizer, grad_norm=None, averager=None):
     """Second half of the iteration: (averaged) gradients -> clip -> optimizer step."""
+    if getattr(averager, 'fused', False):   # all-reduce + scaling + Adam in one peer-memory kernel
+        assert grad_norm is None
+        averager.step()
+        return
     if averager is not None:
         averager.scale()
     if grad_norm is not None:
@@ -212,7 +217,7 @@ def train_step(model, sub, optimizer, VR_update=False, grad_norm=None, averager=
                batch_idx=0):
     """One iteration of the mini_train loop body on an already collated batch."""
     ln, n = forward_backward(model, sub, optimizer, VR_update, averager, epoch, batch_idx)
-    if averager is not None:
+    if averager is not None and not getattr(averager, 'fused', False):
         averager.all_reduce()
     apply_update(model, optimizer, grad_norm, averager)
     return ln, n
@@ -266,11 +271,17 @@ class GraphedTrainer:
     def _body_b(self):
         apply_update(self.model, self.optimizer, self.grad_norm, self.averager)
 
+    @property
+    def _two_graphs(self) -> bool:
+        """NCCL gradient all-reduce: issued eagerly between two graphs of a step.  Single GPU, or the
+        fused peer-memory exchange (parallel.FusedGradSync): the whole step is one graph."""
+        return self.averager is not None and not getattr(self.averager, 'fused', False)
+
     def _step_on(self, sub):
         ln, n = forward_backward(self.model, sub, self.optimizer, self.vr, self.averager)
         self.acc += torch.stack([ln.double(), n.double()])
-        if self.averager is None:
-            apply_update(self.model, self.optimizer, self.grad_norm, None)
+        if not self._two_graphs:
+            apply_update(self.model, self.optimizer, self.grad_norm, self.averager)
 
     def _launch_collate(self, key):
         """Replay the collate graph of batch `key` on the side stream (after the last step that read
@@ -319,7 +330,7 @@ class GraphedTrainer:
 
     def _body(self, ids):
         self._body_a(ids)
-        if self.averager is not None:
+        if self._two_graphs:
             self.averager.all_reduce()
         self._body_b()
 
@@ -363,12 +374,12 @@ class GraphedTrainer:
             with torch.cuda.graph(g, pool=self.pool):
                 self._step_on(sub)
             sub.data.adj_t.drop_caches()
-            if self.averager is not None:
+            if self._two_graphs:
                 gb = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gb, pool=self.pool):
                     self._body_b()
             self.graphs[key] = (g, gb)
-        elif self.averager is None:
+        elif not self._two_graphs:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=self.pool):
                 self._body(ids)

@@ -58,7 +58,7 @@ int64_t incagg_launch_count(void);
 /* Experiment knobs of the kernels (not part of the reference-facing surface; the defaults are what the
  * product runs with).  Plans built before a knob that changes the warp partition was set must be
  * rebuilt. */
-#define INCAGG_TUNE_SPMM_STREAM_VARIANT 0 /* merge-path SpMM: -1 off, else gathers per buffer x warps/SM: 0 = 8 x 16, 1 = 4 x 32, 2 = 4 x 24, 3 = 2 x 40, 4 = 2 x 48, 5 = 16 x 8; two edges per warp instruction (pairs per buffer x warps/SM): 10 = 4 x 16, 11 = 2 x 24, 12 = 2 x 32, 13 = 8 x 8 */
+#define INCAGG_TUNE_SPMM_STREAM_VARIANT 0 /* merge-path SpMM: -2 auto (delta form only, variant 2), -1 off, else gathers per buffer x warps/SM: 0 = 8 x 16, 1 = 4 x 32, 2 = 4 x 24, 3 = 2 x 40, 4 = 2 x 48, 5 = 16 x 8; two edges per warp instruction (pairs per buffer x warps/SM): 10 = 4 x 16, 11 = 2 x 24, 12 = 2 x 32, 13 = 8 x 8 */
 #define INCAGG_TUNE_SPMM_STREAM_MIN_F 1   /* smallest feature width routed to the merge-path kernel (65) */
 #define INCAGG_TUNE_COUNT 8
 int incagg_tune_set(int key, int value);
@@ -68,6 +68,7 @@ int incagg_tune_set(int key, int value);
  * device; `reset` != 0 clears the word.  (ops.check_device_errors() raises RuntimeError on non-zero.) */
 #define INCAGG_DEVERR_ROW_INDEX 1 /* gather / scatter / sharded gather: row id outside the table */
 #define INCAGG_DEVERR_NODE_ID 2   /* relabel: batch node id outside [0, num_nodes) */
+#define INCAGG_DEVERR_PEER_TIMEOUT 4 /* fused all-reduce: a peer rank did not show up within ~10 s */
 int incagg_device_errors(int32_t* out, int reset);
 /* SM count and compute capability of the current device. */
 int incagg_device_info(int* sm_count, int* cc_major, int* cc_minor);
@@ -211,6 +212,24 @@ int incagg_adam_step(float* params, const float* grads, float* exp_avg, float* e
                      int64_t n_first_group, float lr, float beta1, float beta2, float eps,
                      float wd_first_group, float wd_rest, float* step_dev, void* arrivals_dev,
                      incagg_stream_t stream);
+
+/*
+ * Data-parallel step on `world` GPUs of one NVSwitch box (SURVEY.md 8e "gradients are all-reduced"; the
+ * reference itself is single-GPU): gradient all-reduce over NVLink peer memory FUSED with the Adam
+ * update, one launch per rank, no NCCL call.  stage_ptrs[r] / signal_ptrs[r]: rank r's staging buffer
+ * (2 * n floats) and signal array (incagg_allreduce_adam_blocks() * incagg_allreduce_adam_max_ranks()
+ * int32, zero-initialised), the peers' mapped into this process through CUDA IPC.  Contributions are
+ * added in rank order and divided by `world`: every rank computes bit-identical parameters.  `grads`
+ * holds the averaged gradient afterwards.  All ranks must call it once per step, in step order, each on
+ * its own GPU.  Other arguments as incagg_adam_step.
+ */
+int incagg_allreduce_adam_blocks(void);
+int incagg_allreduce_adam_max_ranks(void);
+int incagg_allreduce_adam_step(void* const* stage_ptrs, void* const* signal_ptrs, int rank, int world,
+                               float* grads, float* params, float* exp_avg, float* exp_avg_sq, int64_t n,
+                               int64_t n_first_group, float lr, float beta1, float beta2, float eps,
+                               float wd_first_group, float wd_rest, float* step_dev, void* arrivals_dev,
+                               incagg_stream_t stream);
 
 /* ---- CSR transpose (CSC view for the backward SpMM) ------------------- */
 /*

@@ -111,7 +111,7 @@ def test_full_size_c3_partition_matches_oracle(cuda, products, part):
         out = ops.spmm_delta_raw(aw.rowptr, aw.col, aw.value, x[:B].to(cuda).contiguous(), m_in.to(cuda),
                                  m_ag.to(cuda), None, "sum", plan=aw.plan())
         assert _rel(out.cpu().numpy(), ref_d) <= RTOL
-    ops.tune("spmm_stream_variant", 0)
+    ops.tune("spmm_stream_variant", -2)
 
 
 @pytest.mark.parametrize("F", [602, 1024])

@@ -64,6 +64,77 @@ for transport, vr in itertools.product(("nccl", "p2p"), (False, True)):
     print(f"[rank {rank}] {transport} {'IncAgg' if vr else 'GAS'} epoch: loss sum {tot:.4f}, params identical across ranks: {same_p}", flush=True)
     ok &= same_p and fin
     if transport == "p2p":
+        # the fused peer-memory gradient exchange (all-reduce + Adam in one kernel, no NCCL call) against
+        # the NCCL all-reduce + Adam of the loop above: same step from the same state on a twin model
+        from incagg_gnn_b200.parallel import FusedGradSync
+        twin = build("C3", device=dev, seed=0, scale=32, overrides=ov, rank=rank, world_size=world, shuffle=False,
+                     transport=transport)
+        twin["model"].load_state_dict(model.state_dict(), strict=False)
+        for h_t, h_s in zip(list(twin["model"].histories) + list(twin["model"].histories_ag),
+                            list(model.histories) + list(model.histories_ag)):
+            h_t.emb.copy_(h_s.emb)
+        t_opt = twin["optimizer"]
+        t_opt.exp_avg.copy_(opt.exp_avg); t_opt.exp_avg_sq.copy_(opt.exp_avg_sq); t_opt.step_t.copy_(opt.step_t)
+        torch.cuda.synchronize(); dist.barrier()
+        fsync = FusedGradSync(t_opt, twin["shard"])
+        twin["model"].train()
+        worst = 0.0
+        for (batch, B, n_id, offset, count), (batch2, B2, n_id2, offset2, count2) in zip(sharded["train_loader"],
+                                                                                     twin["train_loader"]):
+            for mdl, o, sync, bt, args_ in ((model, opt, avg, batch, (B, n_id, offset, count)),
+                                            (twin["model"], t_opt, fsync, batch2, (B2, n_id2, offset2, count2))):
+                out = (mdl.VR_call if vr else mdl)(bt.x, bt.adj_t, *args_)["out"]
+                msk = bt.train_mask[:args_[0]]
+                loss = torch.nn.functional.cross_entropy(out[msk], bt.y[:args_[0]][msk])
+                sync.zero()
+                loss.backward()
+                if sync is fsync:
+                    sync.step()
+                else:
+                    sync()
+                    o.step()
+            a = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+            b = torch.cat([p.detach().reshape(-1) for p in twin["model"].parameters()])
+            worst = max(worst, float((a - b).abs().max() / a.abs().max()))
+        del loss, out
+        flat = torch.cat([p.detach().reshape(-1) for p in twin["model"].parameters()])
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        same_f = torch.equal(flat, ref)
+        from incagg_gnn_b200 import ops as _ops
+        _ops.check_device_errors()
+        print(f"[rank {rank}] p2p {'IncAgg' if vr else 'GAS'} fused gradient exchange: params identical across ranks: "
+              f"{same_f}, max rel. difference to the NCCL path over the epoch: {worst:.2e}", flush=True)
+        ok &= same_f and worst < 1e-4
+        # one-graph steps with the fused exchange captured
+        from incagg_gnn_b200.train import GraphedTrainer
+        trf = GraphedTrainer(twin["model"], twin["train_loader"], t_opt, VR_update=vr, averager=fsync,
+                             pipeline_collate=True)
+        trf.warmup(twin["train_loader"]._batches_of_epoch()[0], steps=1)
+        f1 = trf.epoch()
+        f2 = trf.epoch()
+        flat = torch.cat([p.detach().reshape(-1) for p in twin["model"].parameters()])
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        same_fg = torch.equal(flat, ref)
+        assert all(g[1] is None for g in trf.graphs.values())
+        print(f"[rank {rank}] p2p {'IncAgg' if vr else 'GAS'} one-graph steps (fused exchange, pipelined collate): "
+              f"losses {f1['loss']:.4f} {f2['loss']:.4f}, params identical: {same_fg}", flush=True)
+        ok &= same_fg and f2['loss'] == f2['loss']
+        # graphed sweep over the sharded tables (one graph per layer phase) == eager sharded sweep
+        from incagg_gnn_b200.train import GraphedSweep
+        out_e = mini_test(twin["model"], twin["eval_loader"], VR_update=vr).clone()
+        tabs_e = [h.emb.clone() for h in list(twin["model"].histories) + list(twin["model"].histories_ag)]
+        sweep = GraphedSweep(twin["model"], twin["eval_loader"], VR_update=vr)
+        sweep()
+        out_g = sweep().clone()
+        torch.cuda.synchronize()
+        same_sw = torch.equal(out_g, out_e) and all(
+            torch.equal(a_, h.emb) for a_, h in zip(tabs_e, list(twin["model"].histories) + list(twin["model"].histories_ag)))
+        print(f"[rank {rank}] p2p {'IncAgg' if vr else 'GAS'} phase-graphed sharded sweep == eager sharded sweep: {same_sw} "
+              f"({len(sweep.phases)} phase graphs)", flush=True)
+        ok &= same_sw
+        del twin, trf, fsync, sweep
         # CUDA-graph replays with the peer gathers and the NCCL gradient all-reduce captured
         from incagg_gnn_b200.train import GraphedTrainer
         tr = GraphedTrainer(model, sharded["train_loader"], opt, VR_update=vr, averager=avg)
