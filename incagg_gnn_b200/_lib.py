@@ -62,6 +62,8 @@ _PROTOS = {
                                   c_int64, c_int32, P, P]),
     "incagg_spmm_minmax_bwd": (c_int, [P, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, P]),
     "incagg_spmm_multi": (c_int, [P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, c_int32, P, P, P]),
+    "incagg_spmm_multi_arg": (c_int, [P, P, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, c_int32, P, P,
+                                      P]),
     "incagg_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "incagg_gemm_tf32x3": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, P, c_int64, P, c_int64, c_float, P,
                                    c_int64, c_float, P, c_int, P, c_int64, P, c_size_t, P]),

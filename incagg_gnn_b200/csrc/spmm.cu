@@ -1533,25 +1533,43 @@ extern "C" int incagg_spmm_delta(int reduce, const int32_t* rowptr, const int32_
   return dispatch_shape<R_MEAN, true, false>(p, F, vec, 1, INT64_MAX, st);
 }
 
-extern "C" int incagg_spmm_multi(const int32_t* rowptr, const int32_t* col, const float* val,
-                                 const float* X, int64_t ldx, float* out, int64_t ldo, int64_t rows,
-                                 int32_t F, int32_t K, const int32_t* reducers, const void* plan,
-                                 incagg_stream_t stream) {
+static int spmm_multi_impl(const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
+                           int64_t ldx, float* out, int64_t ldo, int32_t* arg_out, int64_t lda, int64_t rows,
+                           int32_t F, int32_t K, const int32_t* reducers, const void* plan,
+                           incagg_stream_t stream) {
   IA_CHECK_ARG(K >= 1 && K <= 16, "K must be in [1, 16] (got %d)", K);
   IA_CHECK_ARG(reducers != nullptr, "reducers is NULL");
   int rc = check_common(rowptr, col, X, out, ldx, ldo, rows, F * K);
   if (rc != INCAGG_OK) return rc;
   if (rows == 0 || F == 0) return INCAGG_OK;
+  IA_CHECK_ARG(arg_out == nullptr || lda >= (int64_t)F * K, "lda smaller than K * F");
   SpmmParams p{};
   p.rowptr = rowptr; p.col = col; p.val = val; p.X = X; p.ldx = ldx; p.out = out; p.ldo = ldo;
   p.rows = rows; p.F = F * K; p.slab_F = F;
+  p.arg = arg_out; p.lda = lda;
   for (int k = 0; k < K; ++k) {
     IA_CHECK_ARG(reducers[k] >= 0 && reducers[k] <= 3, "unknown reducer %d", reducers[k]);
     p.reducers[k] = reducers[k];
   }
   p.plan = static_cast<const SpmmPlan*>(plan);
   const int vec = pick_vec(p, F);  // slab starts k*F keep the alignment of F
+  if (arg_out != nullptr) return dispatch_shape<R_RUNTIME, false, true>(p, F, vec, K, INT64_MAX, as_stream(stream));
   return dispatch_shape<R_RUNTIME, false, false>(p, F, vec, K, INT64_MAX, as_stream(stream));
+}
+
+extern "C" int incagg_spmm_multi(const int32_t* rowptr, const int32_t* col, const float* val,
+                                 const float* X, int64_t ldx, float* out, int64_t ldo, int64_t rows,
+                                 int32_t F, int32_t K, const int32_t* reducers, const void* plan,
+                                 incagg_stream_t stream) {
+  return spmm_multi_impl(rowptr, col, val, X, ldx, out, ldo, nullptr, 0, rows, F, K, reducers, plan, stream);
+}
+
+extern "C" int incagg_spmm_multi_arg(const int32_t* rowptr, const int32_t* col, const float* val,
+                                     const float* X, int64_t ldx, float* out, int64_t ldo, int32_t* arg_out,
+                                     int64_t lda, int64_t rows, int32_t F, int32_t K, const int32_t* reducers,
+                                     const void* plan, incagg_stream_t stream) {
+  IA_CHECK_ARG(arg_out != nullptr, "arg_out is NULL");
+  return spmm_multi_impl(rowptr, col, val, X, ldx, out, ldo, arg_out, lda, rows, F, K, reducers, plan, stream);
 }
 
 extern "C" int incagg_spmm_minmax_bwd(const int32_t* col, const float* val, const int32_t* arg,

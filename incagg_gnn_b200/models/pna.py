@@ -4,8 +4,11 @@ PNA has no working IncAgg path in the reference; its GAS ``forward`
 ``forward_layer`` are what is built here.  ``PNAConv.message_and_aggregate`` runs K =
 |aggregators| x |scalers| separate  pre_lin -> relu -> matmul(reduce) -> post_lin -> scaler  passes in
 the reference; here the K pre_lin outputs are written side by side into one ``[n, K*F]`` operand and
-the K reductions run in ONE launch of the multi-aggregator SpMM kernel when no gradient is needed
-(inference sweeps); the training path keeps per-aggregator autograd through the same SpMM kernels.
+the K reductions run in ONE launch of the multi-aggregator SpMM kernel - in the inference sweeps and
+in training (``sparse.spmm_multi``: the backward pass is one transposed SpMM over the sum / mean slabs
+plus one scatter over the min / max slabs).  In training the K pre_lin GEMMs are one GEMM over the
+row-concatenated weights, and the K post_lin GEMMs of one scaler one GEMM over the column-concatenated
+weights (out = sum_k agg_k W_k^T = [agg_0 | ... | agg_K-1] [W_0 | ... | W_K-1]^T).
 """
 from itertools import product
 from typing import Optional, List
@@ -16,8 +19,8 @@ import torch.nn.functional as F
 from torch.nn import ModuleList, BatchNorm1d
 
 from .. import ops
-from ..nn import Linear
-from ..sparse import SparseTensor, spmm
+from ..nn import Linear, linear
+from ..sparse import SparseTensor, spmm, spmm_multi
 from .base import ScalableGNN
 
 EPS = 1e-5
@@ -106,10 +109,35 @@ class PNAConv(torch.nn.Module):
                 h = post_lin(a)
                 out = out + self._scale(h, scaler, deg)
             return out
+        if (all(a in ('sum', 'add', 'mean', 'min', 'max') for a in self.aggregators) and len(combos) <= 16
+                and self.out_channels % 4 == 0 and x.is_cuda and x.dtype == torch.float32):
+            return self._fused_training_path(adj_t, x, combos, deg)
         for (aggr, scaler), pre_lin, post_lin in zip(combos, self.pre_lins, self.post_lins):
             h = pre_lin(x, relu=True)
             h = self._aggregate_one(adj_t, h, aggr)
             h = post_lin(h)
+            out = out + self._scale(h, scaler, deg)
+        return out
+
+    def _fused_training_path(self, adj_t: SparseTensor, x: Tensor, combos, deg: Tensor) -> Tensor:
+        """sum / mean / min / max aggregators with autograd: 1 GEMM (all pre_lins, bias + ReLU in the
+        epilogue) -> 1 multi-aggregator SpMM -> 1 GEMM per scaler (its post_lins), instead of K of each."""
+        Fo, K = self.out_channels, len(combos)
+        # slabs grouped by scaler, so that the slabs one post GEMM consumes are adjacent columns
+        groups = [[k for k, (_, sc) in enumerate(combos) if sc == scaler] for scaler in self.scalers]
+        order = [k for ks in groups for k in ks]
+        w_pre = torch.cat([self.pre_lins[k].weight for k in order], 0)     # [K*Fo, in]
+        b_pre = torch.cat([self.pre_lins[k].bias for k in order], 0)
+        hs = linear(x, w_pre, b_pre, relu=True)                            # [n, K*Fo]
+        agg = spmm_multi(adj_t, hs, Fo, [combos[k][0] for k in order])     # [rows, K*Fo]
+        out = 0
+        c0 = 0
+        for scaler, ks in zip(self.scalers, groups):
+            a_s = agg if len(ks) == K else agg[:, c0 * Fo:(c0 + len(ks)) * Fo]
+            c0 += len(ks)
+            w_post = torch.cat([self.post_lins[k].weight for k in ks], 1)  # [Fo, len(ks)*Fo]
+            b_post = torch.stack([self.post_lins[k].bias for k in ks], 0).sum(0)
+            h = linear(a_s, w_post, b_post)
             out = out + self._scale(h, scaler, deg)
         return out
 

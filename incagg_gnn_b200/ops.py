@@ -167,8 +167,9 @@ def spmm_delta_raw(rowptr, col, val, x, m_in, m_ag, n_id=None, reduce="sum", row
     return out
 
 
-def spmm_multi_raw(rowptr, col, val, x, F: int, reducers, rows=None, out=None, plan=None):
-    """x is [n_src, K*F]; slab k reduced with reducers[k] ('sum'|'mean'|'min'|'max')."""
+def spmm_multi_raw(rowptr, col, val, x, F: int, reducers, rows=None, out=None, plan=None, return_arg=False):
+    """x is [n_src, K*F]; slab k reduced with reducers[k] ('sum'|'mean'|'min'|'max').  return_arg: also
+    the winning edge of every min / max column ([rows, K*F] int32; -1 elsewhere)."""
     _require_cuda(rowptr, col, val, x)
     x = _f32c(x)
     K = len(reducers)
@@ -180,15 +181,23 @@ def spmm_multi_raw(rowptr, col, val, x, F: int, reducers, rows=None, out=None, p
     red = (ctypes.c_int32 * K)(*[REDUCE[r] for r in reducers])
     LAUNCHES["calls"] += 1
     _order_spmm()
+    if return_arg:
+        arg = torch.empty((n_rows, K * F), dtype=torch.int32, device=x.device)
+        check(lib.incagg_spmm_multi_arg(ptr(rowptr), ptr(col), ptr(val), ptr(x), _ld(x), ptr(out), _ld(out),
+                                        ptr(arg), K * F, n_rows, F, K, ctypes.cast(red, ctypes.c_void_p), ptr(plan),
+                                        _stream()))
+        return out, arg
     check(lib.incagg_spmm_multi(ptr(rowptr), ptr(col), ptr(val), ptr(x), _ld(x), ptr(out), _ld(out),
                                 n_rows, F, K, ctypes.cast(red, ctypes.c_void_p), ptr(plan), _stream()))
     return out
 
 
-def spmm_minmax_bwd_raw(col, val, arg, grad_out, n_src: int):
+def spmm_minmax_bwd_raw(col, val, arg, grad_out, n_src: int, out: Optional[Tensor] = None):
+    """Routes min / max gradients to the winning source rows.  `out` ([n_src, F] view, row-major,
+    ZERO-filled by the caller): accumulate there instead of into a fresh tensor."""
     grad_out = _f32c(grad_out)
     F = grad_out.size(1)
-    grad_x = torch.zeros((n_src, F), dtype=torch.float32, device=grad_out.device)
+    grad_x = out if out is not None else torch.zeros((n_src, F), dtype=torch.float32, device=grad_out.device)
     LAUNCHES["calls"] += 1
     check(lib.incagg_spmm_minmax_bwd(ptr(col), ptr(val), ptr(arg), arg.stride(0), ptr(grad_out),
                                      _ld(grad_out), ptr(grad_x), _ld(grad_x), grad_out.size(0), F,

@@ -318,3 +318,68 @@ def spmm_delta(adj: SparseTensor, x: Tensor, m_in: Tensor, m_ag: Tensor,
     """Fused incremental-aggregation update  A_BB (x - M_in) + M_ag  (one kernel instead of the
     reference's sub + SpMM + add + two clones)."""
     return _SpMMDelta.apply(x, adj, m_in, m_ag, n_id, reduce, relu_input)
+
+
+class _SpMMMulti(torch.autograd.Function):
+    """K slabs of ``hs`` ([n_src, K*F]) reduced with K reducers in ONE launch (PNA, pna.py:66-84 runs K
+    separate passes).  Backward: the sum / mean slabs go through the transposed CSR - one launch per run
+    of adjacent sum / mean slabs, mean gradients pre-divided by the row degree - and the min / max slabs
+    are routed to their winning source rows (one atomic-scatter launch per run of adjacent min / max
+    slabs) with the edge indices the forward launch recorded."""
+
+    @staticmethod
+    def forward(ctx, hs: Tensor, adj: SparseTensor, F: int, reducers):
+        reducers = tuple('sum' if r == 'add' else r for r in reducers)
+        need_arg = any(r in ('min', 'max') for r in reducers) and hs.requires_grad
+        ctx.adj, ctx.F, ctx.reducers, ctx.n_src = adj, F, reducers, hs.size(0)
+        if need_arg:
+            out, arg = ops.spmm_multi_raw(adj.rowptr, adj.col, adj.value, hs, F, list(reducers),
+                                          rows=adj.size(0), plan=adj.plan(), return_arg=True)
+            ctx.save_for_backward(arg)
+        else:
+            out = ops.spmm_multi_raw(adj.rowptr, adj.col, adj.value, hs, F, list(reducers),
+                                     rows=adj.size(0), plan=adj.plan())
+            ctx.save_for_backward(None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        adj, F, reducers, n_src = ctx.adj, ctx.F, ctx.reducers, ctx.n_src
+        (arg,) = ctx.saved_tensors
+        g = g.contiguous()
+        K = len(reducers)
+        linear = [r in ('sum', 'mean') for r in reducers]
+        gx = torch.empty((n_src, K * F), dtype=g.dtype, device=g.device)
+        if not all(linear):
+            gx.zero_()  # the min / max scatter accumulates
+        k = 0
+        t_rowptr = t_col = t_val = t_plan = None
+        while k < K:
+            e = k
+            while e < K and linear[e] == linear[k]:
+                e += 1
+            cols = slice(k * F, e * F)
+            if linear[k]:
+                gs = g[:, cols]
+                if any(reducers[j] == 'mean' for j in range(k, e)):
+                    gs = gs.clone()
+                    deg = (adj.rowptr[1:] - adj.rowptr[:-1]).clamp_(min=1).to(g.dtype).unsqueeze(1)
+                    for j in range(k, e):
+                        if reducers[j] == 'mean':
+                            gs[:, (j - k) * F:(j - k + 1) * F] /= deg
+                if t_rowptr is None:
+                    t_rowptr, t_col, t_val = adj.t_csr()
+                    t_plan = adj.t_plan()
+                ops.spmm_raw(t_rowptr, t_col, t_val, gs, "sum", rows=n_src, out=gx[:, cols], plan=t_plan)
+            else:
+                ops.spmm_minmax_bwd_raw(adj.col, adj.value, arg[:, cols], g[:, cols], n_src, out=gx[:, cols])
+            k = e
+        return gx, None, None, None
+
+
+def spmm_multi(adj: SparseTensor, hs: Tensor, F: int, reducers) -> Tensor:
+    """[rows, K*F] = slab k of ``hs`` reduced over the neighbours with reducers[k], one launch, with
+    autograd w.r.t. ``hs``."""
+    if hs.size(0) < adj.size(1):
+        raise RuntimeError(f"spmm_multi: hs has {hs.size(0)} rows but the adjacency has {adj.size(1)} columns")
+    return _SpMMMulti.apply(hs, adj, F, tuple(reducers))

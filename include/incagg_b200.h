@@ -143,6 +143,13 @@ int incagg_spmm_minmax_bwd(const int32_t* col, const float* val, const int32_t* 
 int incagg_spmm_multi(const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
                       int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t F, int32_t K,
                       const int32_t* reducers, const void* plan, incagg_stream_t stream);
+/* The same launch, also returning the winning edge of every min / max slab column in arg_out
+ * ([rows, K*F] int32, -1 for empty rows; columns of sum / mean slabs are -1): what the backward pass
+ * of a training step routes the min / max gradients with (incagg_spmm_minmax_bwd). */
+int incagg_spmm_multi_arg(const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
+                          int64_t ldx, float* out, int64_t ldo, int32_t* arg_out, int64_t lda, int64_t rows,
+                          int32_t F, int32_t K, const int32_t* reducers, const void* plan,
+                          incagg_stream_t stream);
 
 /* ---- dense feature transform on the tensor cores ----------------------- */
 /*

@@ -108,16 +108,20 @@ def test_incagg_refresh_and_epoch_match_oracle(cuda, config, scale, parts, bs):
 
 
 @pytest.mark.parametrize("config,scale,parts,bs", [('C3', 64, 6, 1), ('C1', 8, 6, 3), ('C2', 16, 8, 4),
-                                                   ('C4', 64, 8, 4), ('C5', 256, 8, 4)])
+                                                   ('C4', 64, 8, 4), ('C5', 256, 8, 4), ('C5fused', 256, 8, 4)])
 def test_gas_sweep_and_epoch_match_oracle(cuda, config, scale, parts, bs):
     """mini_inference logits + histories, then one GAS training epoch (push_and_pull every layer)."""
     from incagg_gnn_b200.train import mini_train, mini_test
     ov = dict(VR_update=False, batch_size=bs)
     if config == 'C4':
         ov['architecture'] = dict(hidden_channels=256)
-    if config == 'C5':  # all five aggregators of the north star, two scalers
+    if config == 'C5':  # all five aggregators of the north star, two scalers (std: per-aggregator path)
         ov['architecture'] = dict(hidden_channels=64, aggregators=['sum', 'mean', 'min', 'max', 'std'],
                                   scalers=['identity', 'amplification'])
+    if config == 'C5fused':  # the training step through the fused multi-aggregator launch + its backward
+        config = 'C5'
+        ov['architecture'] = dict(hidden_channels=64, aggregators=['sum', 'mean', 'min', 'max'],
+                                  scalers=['identity', 'amplification', 'attenuation'])
     run, gas, omodel, adj, raw = _setup(cuda, config, scale, ov, num_parts=parts)
     model, ptr = run['model'], run['ptr']
     out = mini_test(model, run['eval_loader'], VR_update=False)
