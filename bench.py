@@ -52,8 +52,12 @@ def parse_args():
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo rows: NVLink peer loads in the gather kernel, or NCCL all-to-all-v")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=6)
-    return ap.parse_args()
+    ap.add_argument("--cpu-steps", type=int, default=None)
+    args = ap.parse_args()
+    args.cpu_steps_given = args.cpu_steps is not None
+    if args.cpu_steps is None:
+        args.cpu_steps = 6
+    return args
 
 
 # ---- clocks ----------------------------------------------------------------------------------------
@@ -127,8 +131,11 @@ def cpu_baseline(run, mode: str, n_steps: int, threads: int):
     rp, col, val = [t.cpu() if t is not None else None for t in data.adj_t.csr()]
     adj = gas.Adj(rp, col, val, data.num_nodes, data.num_nodes)
     x, y, mask = data.x.cpu(), data.y.cpu(), data.train_mask.cpu()
+    kwargs = dict(conf["architecture"])
+    if conf["model"] == "PNA":
+        kwargs["deg"] = adj.rowptr[1:] - adj.rowptr[:-1]
     model = gas.OracleGNN(conf["model"], run["model"].state_dict(), data.num_nodes, run["in_channels"],
-                          out_channels=run["out_channels"], dtype=torch.float32, **conf["architecture"])
+                          out_channels=run["out_channels"], dtype=torch.float32, **kwargs)
     for l in range(model.num_layers):
         model.histories[l].emb.copy_(full_table(run["model"].histories[l], data.num_nodes))
         if mode == "incagg":
@@ -150,6 +157,16 @@ def cpu_baseline(run, mode: str, n_steps: int, threads: int):
             edges += sum(int(adj.rowptr[int(ptr[p + 1])] - adj.rowptr[int(ptr[p])]) for p in group)
     gas.SPMM_IMPL = "gather"
     return edges / t_total, edges, t_total
+
+
+MODEL_LABEL = {"GCN2": "GCNII", "GCN": "GCN", "APPNP": "APPNP", "GraphSAGE": "GraphSAGE", "PNA": "PNA"}
+DATASET_LABEL = {"amazonproducts": "amazon-products"}
+
+
+def metric_text(conf) -> str:
+    """BASELINE.json's metric for the headline config (C3); the same wording for the other configs."""
+    return (f"edges/s (train epoch, {MODEL_LABEL.get(conf['model'], conf['model'])}, "
+            f"{DATASET_LABEL.get(conf['dataset'], conf['dataset'])}-shape)")
 
 
 def workload_text(config: str, model: str, mode: str, dataset: str, nodes: int, nnz: int, parts: int,
@@ -539,7 +556,7 @@ def main():
         del tr, run_h
         torch.cuda.empty_cache()
     if e2e is not None and world == 1:
-        # the reference's all-host layout (pinned history tables + AsyncIOPool), eager
+        # the reference's all-host layout: history tables in pinned host memory too
         run_h = build(args.config, device=dev, seed=args.seed, scale=args.scale,
                       overrides=dict(VR_update=vr), shuffle=True, host_resident=True,
                       history_device=None, data=data_pack)
@@ -547,11 +564,46 @@ def main():
         mini_test(run_h["model"], run_h["eval_loader"], VR_update=vr)
         torch.cuda.synchronize()
         k2 = min(args.steps, 40)
+        # (a) the reference's own protocol: AsyncIOPool slots, steps issued eagerly
         s3, ed3, h2d3, d2h3, _ = timed_steps(run_h, args.mode, min(args.warmup, 5), k2, dist, e2e=True)
         e2e["host_histories"] = {"value": ed3 / s3, "unit": "edges/s", "h2d_bytes_per_step": int(h2d3 / k2),
                                  "d2h_bytes_per_step": int(d2h3 / k2), "steps": k2,
                                  "layout": "reference layout: all history tables in pinned host memory too, "
                                            "AsyncIOPool staging, eager issue"}
+        # (b) the same tables, the step as CUDA-graph replays: halo rows gathered out of host memory
+        # through UVA, pushes as DMA slice copies; the pulls of step i+1 ride in its collate graph, i.e.
+        # they cross PCIe while step i computes (GAS mode; rows pushed by the step in flight are read one
+        # step staler than in the sequential loop)
+        if run_h["train_loader"].fixed_batches:
+            ld = run_h["train_loader"]
+            trh = GraphedTrainer(run_h["model"], ld, run_h["optimizer"], VR_update=vr,
+                                 grad_norm=run_h["conf"]["grad_norm"], pipeline_collate=True, host_prefetch=True)
+            groups = ld._batches_of_epoch()
+            trh.warmup(groups[0])
+            for ids in groups:
+                trh.capture(ids)
+            torch.cuda.synchronize()
+            order = [g for _ in range(k2 // len(groups) + 2) for g in ld._batches_of_epoch()]
+            trh.run(order[:5])
+            torch.cuda.synchronize()
+            seq = order[5:5 + k2]
+            ed4 = sum(int(ld._rowptr_host[int(ld.ptr[b + 1])]) - int(ld._rowptr_host[int(ld.ptr[b])])
+                      for ids in seq for b in ids)
+            host_res = torch.zeros(2, dtype=torch.float64).pin_memory()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            trh.run(seq, after_step=lambda i: host_res.copy_(trh.acc, non_blocking=True))
+            e1.record()
+            torch.cuda.synchronize()
+            s4 = e0.elapsed_time(e1) / 1e3
+            assert float(host_res[0]) == float(host_res[0])
+            e2e["host_histories_graphed"] = {
+                "value": ed4 / s4, "unit": "edges/s", "steps": k2, "ms_per_step": s4 / k2 * 1e3,
+                "h2d_bytes_per_step": int(h2d3 / k2), "d2h_bytes_per_step": int(d2h3 / k2),
+                "layout": "all history tables in pinned host memory; CUDA-graph replay per batch, halo rows "
+                          "gathered from host memory through UVA one step ahead (in the collate graph of the "
+                          "next batch), pushes as DMA slice copies inside the step graph"}
+            del trh
         del run_h
         torch.cuda.empty_cache()
 
@@ -613,7 +665,9 @@ def main():
     peaks = load_peaks()
     roof = spmm_roofline(run, peaks)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and (args.config == "C3" or args.cpu_steps_given):
+        # (the other configs step over half a graph of 10^8 edges per batch: minutes per CPU step, so
+        # their CPU leg runs only when --cpu-steps is given)
         threads = os.cpu_count() or 1
         v, ed, tt = cpu_baseline(run, args.mode, args.cpu_steps, threads)
         cpu = {"value": v, "unit": "edges/s", "cores": threads, "kind": "port",
@@ -622,7 +676,7 @@ def main():
                          f"CSR SpMM forward and transposed-CSR backward)"}
     conf = run["conf"]
     line = {
-        "metric": "edges/s (train epoch, GCNII, products-shape)", "value": value, "unit": "edges/s",
+        "metric": metric_text(conf), "value": value, "unit": "edges/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -723,9 +777,24 @@ def reference_arm(args, rank, world):
             st[f"convs.{l}.lin_r.weight"] = glorot(dims[l + 1], dims[l])
     elif conf["model"] == "APPNP":
         pass  # lins.0 / lins.1 only
+    elif conf["model"] == "PNA":
+        st = {}
+        K = len(a["aggregators"]) * len(a["scalers"])
+        dims = [fin] + [H] * (L - 1) + [fout]
+        for l in range(L):
+            for k in range(K):
+                st[f"convs.{l}.pre_lins.{k}.weight"] = glorot(dims[l + 1], dims[l])
+                st[f"convs.{l}.pre_lins.{k}.bias"] = torch.zeros(dims[l + 1])
+                st[f"convs.{l}.post_lins.{k}.weight"] = glorot(dims[l + 1], dims[l + 1])
+                st[f"convs.{l}.post_lins.{k}.bias"] = torch.zeros(dims[l + 1])
+            st[f"convs.{l}.lin.weight"] = glorot(dims[l + 1], dims[l])
+            st[f"convs.{l}.lin.bias"] = torch.zeros(dims[l + 1])
     else:
         raise SystemExit(f"reference arm: no weight initialiser for model {conf['model']}")
-    model = gas.OracleGNN(conf["model"], st, N, fin, out_channels=fout, dtype=torch.float32, **a)
+    okw = dict(a)
+    if conf["model"] == "PNA":
+        okw["deg"] = adj.rowptr[1:] - adj.rowptr[:-1]
+    model = gas.OracleGNN(conf["model"], st, N, fin, out_channels=fout, dtype=torch.float32, **okw)
     opt = torch.optim.Adam(model.parameters(), lr=conf["lr"])
     vr = args.mode == "incagg"
     bs = conf["batch_size"]
@@ -747,7 +816,7 @@ def reference_arm(args, rank, world):
     sec = time.perf_counter() - t0
     v = edges / sec
     line = {
-        "impl": "reference", "metric": "edges/s (train epoch, GCNII, products-shape)", "value": v,
+        "impl": "reference", "metric": metric_text(conf), "value": v,
         "unit": "edges/s", "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": sec / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",

@@ -323,8 +323,11 @@ __device__ __forceinline__ void finish_row(const SpmmParams& p, int op, int64_t 
 #define SPMM_THREADS_N 256
 #endif
 constexpr int SPMM_THREADS = SPMM_THREADS_N;
+// 5 CTAs = 40 warps per SM and <= 51 registers per thread.  Measured per products batch (forward, cold L2):
+// 6 CTAs (40 registers: ptxas interleaves the four gathers of a round with their FMAs) 42 us,
+// 5 CTAs (48 registers: all four gathers issued first) 33 us, 4 CTAs (56 registers) 40 us.
 #ifndef SPMM_MIN_CTAS
-#define SPMM_MIN_CTAS (1536 / SPMM_THREADS_N)
+#define SPMM_MIN_CTAS (1280 / SPMM_THREADS_N)
 #endif
 
 // Feature tile -> (reducer, first feature, feature limit).  For the multi-aggregator launch

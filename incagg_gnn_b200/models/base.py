@@ -85,6 +85,11 @@ class ScalableGNN(torch.nn.Module):
         self.__out: Optional[Tensor] = None
         self.shard = None      # parallel.Shard when the history tables are sharded over ranks
         self._row_lo = 0       # first global row of this rank's shard
+        # Pinned-host tables WITHOUT the pool's slot / queue protocol: the gather kernel reads the halo
+        # rows straight out of host memory (UVA) on the pull stream, pushes are DMA slice copies, all of
+        # it enqueued like any other kernel - which is what lets a CUDA graph contain the whole step
+        # (train.GraphedTrainer sets this for host-resident tables).  Same bytes, same order per step.
+        self._direct_host = False
 
     def shard_histories(self, shard, transport: str = 'p2p') -> 'ScalableGNN':
         """Keep only this rank's rows ``[shard.lo, shard.hi)`` of every history table (HBM-resident
@@ -164,9 +169,9 @@ class ScalableGNN(torch.nn.Module):
             return self.mini_inference(loader, use_aggregation)
 
         self._async = (self.pool is not None and batch_size is not None and n_id is not None
-                       and offset is not None and count is not None)
+                       and offset is not None and count is not None and not self._direct_host)
         if (batch_size is not None and not self._async and str(self.emb_device) == 'cpu'
-                and str(self.device)[:4] == 'cuda'):
+                and str(self.device)[:4] == 'cuda' and not self._direct_host):
             warnings.warn('Asynchronous I/O disabled, although history and model sit on different devices.')
 
         if self._async:
@@ -199,7 +204,7 @@ class ScalableGNN(torch.nn.Module):
         if loader is not None:
             return self.mini_inference(loader)
         self._async = (self.pool is not None and batch_size is not None and n_id is not None
-                       and offset is not None and count is not None)
+                       and offset is not None and count is not None and not self._direct_host)
         if self._async:
             empty = torch.empty(0, dtype=torch.int64)
             for i in range(len(self.histories)):  # M_in / M_ag slices of the batch (base.py:318-323)
@@ -225,8 +230,15 @@ class ScalableGNN(torch.nn.Module):
             return m_in, m_ag, None
         hist, hist_ag = self.histories[layer].emb, self.histories_ag[layer].emb
         if not hist.is_cuda:
-            raise RuntimeError('IncAgg step with host-resident histories needs the AsyncIOPool '
-                               '(pool_size and buffer_size must be set)')
+            if not self._direct_host:
+                raise RuntimeError('IncAgg step with host-resident histories needs the AsyncIOPool '
+                                   '(pool_size and buffer_size must be set)')
+            # the batch's own rows of M_in / M_ag: partition slices, staged host -> device by DMA
+            m_in = torch.empty((batch_size, hist.size(1)), dtype=hist.dtype, device=self.device)
+            m_ag = torch.empty((batch_size, hist_ag.size(1)), dtype=hist_ag.dtype, device=self.device)
+            ops.copy_slices(hist, m_in, offset, count, 0)
+            ops.copy_slices(hist_ag, m_ag, offset, count, 0)
+            return m_in[:, :width], m_ag[:, :width], None
         if offset is not None and offset.numel() == 1:
             o = int(offset[0]) - self._row_lo
             return hist[o:o + batch_size, :width], hist_ag[o:o + batch_size, :width], None
@@ -262,7 +274,8 @@ class ScalableGNN(torch.nn.Module):
             history.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
 
             def fill(dst):
-                torch.cuda.current_stream().wait_event(pulled)
+                if pulled is not None:   # (None: pulled by an earlier graph, already complete)
+                    torch.cuda.current_stream().wait_event(pulled)
             return _PushPull.apply(x, fill, batch_size, n_tail, buf), 0.
         if not self._async:  # synchronous branch = the semantic definition (base.py:411-426)
             history.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
@@ -288,8 +301,12 @@ class ScalableGNN(torch.nn.Module):
         [B + H, F] buffer whose head the layer's GEMM later writes in place.  Returns one
         (buffer, event) per history - the consumer waits for the event - or None when the step does
         not take this path (host histories / NCCL transport / full-batch)."""
+        pre = getattr(n_id, 'prefetched_pulls', None)
+        if pre is not None:  # pulled one step ahead (train.GraphedTrainer host_prefetch): nothing to issue
+            return pre
         if (_NO_AHEAD or n_id is None or batch_size is None or self._async or not x.is_cuda
-                or not self.emb_device.type == 'cuda' or getattr(n_id, 'halo_plan', None) is not None):
+                or not (self.emb_device.type == 'cuda' or self._direct_host)
+                or getattr(n_id, 'halo_plan', None) is not None):
             return None
         n_tail = n_id.numel() - batch_size
         main = torch.cuda.current_stream(x.device)
@@ -308,6 +325,25 @@ class ScalableGNN(torch.nn.Module):
                 ev = torch.cuda.Event()
                 ev.record(side)
                 out.append((buf, ev))
+        return out
+
+    def prefetch_pulls(self, batch_size: int, n_id: Tensor, dtype=torch.float32):
+        """The halo pulls of a GAS step, issued outside the step (train.GraphedTrainer replays them with
+        the collate of the NEXT batch on a side stream, so with pinned-host tables the PCIe transfer of
+        step i + 1 overlaps the compute of step i).  The buffers are attached to ``n_id`` and picked up
+        by :meth:`pull_ahead`.  Rows pushed by the step in flight are read one step staler than in the
+        sequential loop (or mid-copy: every 16-byte piece is one of the two valid versions) - the
+        staleness GAS is built on, but not the reference's exact schedule: an opt-in mode."""
+        hists = self._gas_pull_histories()
+        n_tail = n_id.numel() - batch_size
+        idx = n_id[batch_size:]
+        out = []
+        for h in hists:
+            buf = torch.empty((batch_size + n_tail, h.emb.size(1)), dtype=dtype, device=self.device)
+            if n_tail > 0:
+                self._pull_rows(h.emb, idx, n_id, buf[batch_size:])
+            out.append((buf, None))
+        n_id.prefetched_pulls = out
         return out
 
     def push_only(self, history, x: Tensor, batch_size: Optional[int] = None,

@@ -94,10 +94,13 @@ class GCN2(ScalableGNN):
                     # the push only reads the rows the GEMM just wrote and nothing in this step reads
                     # the table rows it writes: it rides on the pull stream, joined after the loop
                     main, side = torch.cuda.current_stream(), self._pull_stream
+                    if side is None:
+                        side = self._pull_stream = torch.cuda.Stream(x.device)
                     side.wait_stream(main)
                     with torch.cuda.stream(side):
                         hist.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
-                    main.wait_event(pulled)
+                    if pulled is not None:
+                        main.wait_event(pulled)
                 else:
                     h = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=fuse)
                     x = h if fuse else self._post(i, h, x)

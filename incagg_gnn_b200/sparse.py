@@ -169,6 +169,22 @@ class SparseTensor:
         self._t = self._plan = self._t_plan = None
         self.__dict__.pop('_t_prefix_plans', None)
         self.__dict__.pop('_stripped', None)
+        self.__dict__.pop('_t_mean_val', None)
+
+    def t_mean_values(self) -> Tensor:
+        """Values of the transposed structure for the backward pass of a MEAN aggregation:
+        d mean_i / d x_j = val_ij / max(deg_i, 1), i.e. the transposed entry (j, i) carries
+        val_ij / deg_i.  Built once per structure (one gather), so the backward is a plain transposed
+        sum-SpMM instead of a per-step division of the incoming gradient by the degrees."""
+        v = self.__dict__.get('_t_mean_val')
+        if v is None:
+            t_rowptr, t_col, t_val = self.t_csr()
+            inv = 1.0 / (self.rowptr[1:] - self.rowptr[:-1]).clamp(min=1).to(torch.float32)
+            v = inv[t_col.long()]
+            if t_val is not None:
+                v = v * t_val
+            self.__dict__['_t_mean_val'] = v
+        return v
 
     def plan(self) -> Tensor:
         """SpMM plan of this structure (one small launch, cached)."""
@@ -244,27 +260,28 @@ class _SpMM(torch.autograd.Function):
             if ctx.relu_input:
                 gx = torch.ops.aten.threshold_backward(gx, x, 0.)
             return gx, None, None, None, None
-        if reduce == "mean":
-            deg = (adj.rowptr[1:] - adj.rowptr[:-1]).clamp_(min=1).to(grad_out.dtype)
-            grad_out = grad_out / deg.unsqueeze(1)
+        mean = reduce == "mean"
         gate = None
         if ctx.relu_input:
             if x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1:
                 gate = x
             else:  # layout the kernel's epilogue does not read: mask afterwards
-                gx = _transposed_product(adj, grad_out, ctx.n_src, ctx.grad_rows)
+                gx = _transposed_product(adj, grad_out, ctx.n_src, ctx.grad_rows, mean=mean)
                 rows = gx.size(0) if ctx.grad_rows is None else min(ctx.grad_rows, gx.size(0))
                 gx[:rows] = torch.ops.aten.threshold_backward(gx[:rows], x[:rows].to(gx.dtype), 0.)
                 return gx, None, None, None, None
-        return _transposed_product(adj, grad_out, ctx.n_src, ctx.grad_rows, gate=gate), None, None, None, None
+        return (_transposed_product(adj, grad_out, ctx.n_src, ctx.grad_rows, gate=gate, mean=mean),
+                None, None, None, None)
 
 
 def _transposed_product(adj: SparseTensor, grad_out: Tensor, n_src: int, grad_rows: Optional[int],
-                        gate: Optional[Tensor] = None):
+                        gate: Optional[Tensor] = None, mean: bool = False):
     """grad_x = A^T grad_out.  With grad_rows = k only the first k source rows are computed (the
     rest of x was a constant, e.g. pulled history rows) and the remainder is returned as zeros.
     `gate` (= x when x is the output of a fused ReLU): the result is zeroed where gate <= 0."""
     t_rowptr, t_col, t_val = adj.t_csr()
+    if mean:  # mean aggregation: the 1 / deg factor rides in the transposed values
+        t_val = adj.t_mean_values()
     t_plan = adj.t_plan()
     if grad_rows is None or grad_rows >= n_src:
         return ops.spmm_raw(t_rowptr, t_col, t_val, grad_out, "sum", rows=n_src, plan=t_plan, gate=gate)
@@ -303,13 +320,10 @@ class _SpMMDelta(torch.autograd.Function):
     def backward(ctx, grad_out):
         adj = ctx.adj
         grad_out = grad_out.contiguous()
-        if ctx.reduce == "mean":
-            deg = (adj.rowptr[1:] - adj.rowptr[:-1]).clamp_(min=1).to(grad_out.dtype)
-            grad_out = grad_out / deg.unsqueeze(1)
         (gate,) = ctx.saved_tensors
         if ctx.relu_input and gate is None:
             raise RuntimeError('spmm_delta(relu_input=True) needs a row-major float32 x')
-        return (_transposed_product(adj, grad_out, ctx.n_src, None, gate=gate),
+        return (_transposed_product(adj, grad_out, ctx.n_src, None, gate=gate, mean=ctx.reduce == "mean"),
                 None, None, None, None, None, None)
 
 
@@ -360,17 +374,20 @@ class _SpMMMulti(torch.autograd.Function):
                 e += 1
             cols = slice(k * F, e * F)
             if linear[k]:
-                gs = g[:, cols]
-                if any(reducers[j] == 'mean' for j in range(k, e)):
-                    gs = gs.clone()
-                    deg = (adj.rowptr[1:] - adj.rowptr[:-1]).clamp_(min=1).to(g.dtype).unsqueeze(1)
-                    for j in range(k, e):
-                        if reducers[j] == 'mean':
-                            gs[:, (j - k) * F:(j - k + 1) * F] /= deg
                 if t_rowptr is None:
                     t_rowptr, t_col, t_val = adj.t_csr()
                     t_plan = adj.t_plan()
-                ops.spmm_raw(t_rowptr, t_col, t_val, gs, "sum", rows=n_src, out=gx[:, cols], plan=t_plan)
+                # adjacent slabs with the same transposed values share a launch: sum slabs use val,
+                # mean slabs val / deg (SparseTensor.t_mean_values)
+                j = k
+                while j < e:
+                    j2 = j
+                    while j2 < e and reducers[j2] == reducers[j]:
+                        j2 += 1
+                    sub = slice(j * F, j2 * F)
+                    tv = adj.t_mean_values() if reducers[j] == 'mean' else t_val
+                    ops.spmm_raw(t_rowptr, t_col, tv, g[:, sub], "sum", rows=n_src, out=gx[:, sub], plan=t_plan)
+                    j = j2
             else:
                 ops.spmm_minmax_bwd_raw(adj.col, adj.value, arg[:, cols], g[:, cols], n_src, out=gx[:, cols])
             k = e

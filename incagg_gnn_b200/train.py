@@ -249,8 +249,17 @@ class GraphedTrainer:
     """
 
     def __init__(self, model, loader, optimizer, VR_update=False, grad_norm=None, averager=None,
-                 pipeline_collate=False):
+                 pipeline_collate=False, host_prefetch=False):
+        """``host_prefetch`` (with ``pipeline_collate``, GAS mode): the halo pulls of a step are part
+        of its collate graph, i.e. they run one step ahead on the side stream - with pinned-host history
+        tables the PCIe reads of step i + 1 overlap the compute of step i (see
+        ``ScalableGNN.prefetch_pulls`` for what that changes)."""
         self.model, self.loader, self.optimizer = model, loader, optimizer
+        self.host_prefetch = bool(host_prefetch) and bool(pipeline_collate) and not VR_update
+        if model.pool is not None:
+            # pinned-host tables: the step is captured with the direct UVA / DMA path instead of the
+            # pool's slot protocol (whose host-side queue cannot be part of a graph)
+            model._direct_host = True
         self.vr, self.grad_norm, self.averager = VR_update, grad_norm, averager
         self.graphs = {}
         self.pool = None
@@ -369,6 +378,8 @@ class GraphedTrainer:
             gi = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gi):
                 sub = self.loader._collate(list(ids))
+                if self.host_prefetch:
+                    self.model.prefetch_pulls(sub.batch_size, sub.n_id)
             self.in_graphs[key] = (gi, sub)   # the outputs stay allocated: the step graph reads them
             g, gb = torch.cuda.CUDAGraph(), None
             with torch.cuda.graph(g, pool=self.pool):

@@ -602,11 +602,14 @@ def test_gather_rows_sharded_matches_unsharded(ops, cuda):
     out = torch.full((400, D), float("nan"), device=cuda)
     ops.gather_rows_sharded(shards, bounds, idx, out)
     assert torch.equal(out, table[idx])
-    # a window of the id space: ids outside [bounds[0], bounds[-1]) are skipped
-    out2 = torch.zeros(400, D, device=cuda)
+    # ids owned by no shard (a window of the id space): zero rows, and the device error word is set
+    ops.check_device_errors()
+    out2 = torch.full((400, D), float("nan"), device=cuda)
     ops.gather_rows_sharded(shards[2:], bounds[2:], idx, out2)
     inside = (idx >= 130)
     assert torch.equal(out2[inside], table[idx[inside]]) and float(out2[~inside].abs().max()) == 0.
+    with pytest.raises(RuntimeError, match="row index"):
+        ops.check_device_errors()
 
 
 def test_relu_bwd_colsum_and_masked_ce(ops, cuda):

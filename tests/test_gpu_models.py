@@ -347,3 +347,43 @@ def test_graphed_sweep_matches_eager(cuda, vr):
     assert torch.equal(out_g, out_e)
     for a, b in zip(tabs_e, [h.emb for h in list(model.histories) + list(model.histories_ag)]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("vr", [False, True])
+def test_graphed_steps_on_pinned_host_tables_match_the_pool_path(cuda, vr):
+    """Pinned-host history tables: the CUDA-graph step (halo rows gathered from host memory through UVA,
+    pushes as DMA slice copies, no pool slots) gives the losses and tables of the reference's
+    AsyncIOPool protocol issued eagerly; with host_prefetch (pulls one step ahead, GAS) it still trains
+    and stays close (rows pushed by the step in flight are read one step staler)."""
+    from incagg_gnn_b200.train import GraphedTrainer, mini_train, mini_test
+    res = {}
+    for mode in ("pool", "graphed", "prefetch"):
+        if mode == "prefetch" and vr:
+            continue
+        run, *_ = _setup(cuda, 'C3', 64, dict(VR_update=vr), history_device=None, num_parts=6)
+        model = run['model']
+        assert model.pool is not None and not model.histories[0].emb.is_cuda
+        mini_test(model, run['eval_loader'], VR_update=vr)
+        tr = GraphedTrainer(model, run['train_loader'], run['optimizer'], VR_update=vr,
+                            pipeline_collate=(mode != "pool"), host_prefetch=(mode == "prefetch"))
+        if mode == "pool":
+            model._direct_host = False   # the reference's protocol, eager
+        # one eager step on the first batch in every variant (scratch buffers exist before a capture,
+        # and all variants start the compared epochs from the same state)
+        tr.warmup(run['train_loader']._batches_of_epoch()[0], steps=1)
+        if mode == "pool":
+            losses = [mini_train(model, run['train_loader'], run['criterion'], run['optimizer'],
+                                 run['max_steps'], VR_update=vr)['loss'] for _ in range(2)]
+        else:
+            losses = [tr.epoch()['loss'] for _ in range(2)]
+        torch.cuda.synchronize()
+        if model.pool is not None:
+            model.pool.synchronize_push()
+        res[mode] = (losses, [h.emb.clone() for h in model.histories])
+    for a, b in zip(res["pool"][0], res["graphed"][0]):
+        assert abs(a - b) <= 1e-6 * abs(a), (a, b)
+    for x, y in zip(res["pool"][1], res["graphed"][1]):
+        assert _rel(x, y) <= 1e-5
+    if not vr:
+        for a, b in zip(res["pool"][0], res["prefetch"][0]):
+            assert b == b and abs(a - b) <= 5e-2 * abs(a), (a, b)
