@@ -365,13 +365,31 @@ def spmm_roofline(run, peaks):
             "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
             "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback",
             "bytes_per_launch": int(tot_b / n), "us_per_launch": round(tot_t / n * 1e6, 2),
-            "traffic": 36.5e6,  # dram__bytes_read+write per launch, ncu --set full (profiles/r01_spmm_ncu_full_b.txt)
-            # the resource that actually binds this kernel: every edge pulls an F*4-byte row through L2
-            "l2_gather": {"bytes_per_launch": int(tot_g / n), "achieved_GBps": round(tot_g / tot_t / 1e9, 1),
-                          "cap_GBps": 12200.0,
-                          "cap_source": "full-graph SpMM of this kernel (64.3M edges x 512 B in 2.7 ms) = LTS "
-                                        "throughput cap ~6300 B/clk (B300_MICROARCH.md)",
-                          "frac": round(tot_g / tot_t / 1e9 / 12200.0, 4)}}
+            # dram__bytes_read + dram__bytes_write per launch, ncu --set full of this kernel on these batches
+            # (profiles/r02_step_kernels_ncu_full.txt): 0.82 x the algorithmic bytes, the output stays in L2
+            "traffic": 36.6e6,
+            # what the counters show (profiles/r02_spmm_variants.md): every edge pulls an F*4-byte row
+            # through L2 (bytes below; floor = that traffic at the ~12.4 TB/s the L2 -> SM path sustains);
+            # no memory unit is above a third of its peak, the launch is paced by the instruction stream of
+            # the gather loop at the occupancy its registers allow
+            "l2_to_sm": {"bytes_per_launch": int(tot_g / n), "achieved_GBps": round(tot_g / tot_t / 1e9, 1),
+                         "floor_us_at_12400_GBps": round(tot_g / n / 12.4e12 * 1e6, 2)},
+            "limiter": "instruction issue of the gather loop (ncu: issue slots 36-51 % busy at 40 warps/SM, "
+                       "L2 26-32 %, DRAM 12-14 % of peak)"}
+
+
+def release_memory():
+    """Between the legs of the run: destroy what the previous leg left behind (trainer <-> model cycles
+    keep CUDA graphs and pinned buffers alive until a garbage collection) and hand cached device and
+    pinned-host blocks back while no graph capture is in progress."""
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    try:
+        torch._C._host_emptyCache()
+    except Exception as exc:  # a failed cudaFreeHost is not sticky; say so and go on
+        print(f"[bench] pinned-host cache release: {str(exc).splitlines()[0]}", file=sys.stderr)
 
 
 def load_peaks():
@@ -469,6 +487,57 @@ def main():
         sec, edges = float(t), float(e)
     value = edges / sec
 
+    # the per-epoch refresh sweep (mini_inference / mini_inference_vr over all partitions), timed alone
+    refresh = None
+    from incagg_gnn_b200.train import GraphedSweep
+    from incagg_gnn_b200.loader import EvalSubgraphLoader
+
+    def time_sweep(loader):
+        sweep = GraphedSweep(model, loader, VR_update=vr)
+        sweep()  # captures (once)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        sweep()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:  # max over ranks (the sharded sweep barriers between layer phases)
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t)
+        return dt
+
+    nnz_all = run["data"].adj_t.nnz()
+    t_epoch = nnz_all / value
+    if world == 1:
+        t_parts = time_sweep(run["eval_loader"])
+        # the same sweep with all partitions merged into ONE evaluation batch (the reference sizes its
+        # eval batches for a 2021 GPU; the tables and every intermediate of a whole-graph layer fit HBM)
+        n_parts = run["ptr"].numel() - 1
+        merged = EvalSubgraphLoader(run["data"], run["ptr"], batch_size=n_parts, log=False, device=dev)
+        t_sweep = time_sweep(merged)
+        del merged
+        torch.cuda.empty_cache()
+        refresh = {"sweep_s": round(t_sweep, 4), "sweep_per_partition_batches_s": round(t_parts, 4),
+                   "train_epoch_s": round(t_epoch, 4),
+                   "edges_per_s_epoch_plus_refresh": nnz_all / (t_epoch + t_sweep),
+                   "note": "value = training steps only; one epoch of the reference loop = train epoch + one "
+                           "layer-wise refresh sweep over all partitions (main.py:226-236); the sweep is one "
+                           "CUDA-graph replay (train.GraphedSweep); sweep_s merges all partitions into one "
+                           f"evaluation batch (EvalSubgraphLoader batch_size={n_parts}), "
+                           "sweep_per_partition_batches_s uses the training batch size as the reference does"}
+    elif args.transport == "p2p":
+        # sharded tables: every rank sweeps its own partitions, halo rows read from the peers' shards;
+        # one CUDA graph per layer phase, a barrier between phases
+        t_sweep = time_sweep(run["eval_loader"])
+        refresh = {"sweep_s": round(t_sweep, 4), "train_epoch_s": round(t_epoch, 4),
+                   "edges_per_s_epoch_plus_refresh": nnz_all / (t_epoch + t_sweep),
+                   "note": f"sharded sweep over {world} ranks (each rank its own partitions, per-partition "
+                           "evaluation batches), one CUDA graph per layer phase + barrier, max over ranks"}
+
+    release_memory()
+
     e2e = None
     if not args.no_e2e:
         # End to end through the public API with HOST buffers: the graph (CSR), features, labels and
@@ -553,8 +622,8 @@ def main():
                          "sum, count) copied to pinned memory and read by the host, the read of step i-1 "
                          "overlapping step i; CUDA-graph replay per batch, the collate graph of step i+1 (the host-memory "
                          "reads) replayed on a side stream while step i computes"}
-        del tr, run_h
-        torch.cuda.empty_cache()
+        del tr, run_h, ld
+        release_memory()
     if e2e is not None and world == 1:
         # the reference's all-host layout: history tables in pinned host memory too
         run_h = build(args.config, device=dev, seed=args.seed, scale=args.scale,
@@ -574,7 +643,10 @@ def main():
         # through UVA, pushes as DMA slice copies; the pulls of step i+1 ride in its collate graph, i.e.
         # they cross PCIe while step i computes (GAS mode; rows pushed by the step in flight are read one
         # step staler than in the sequential loop)
-        if run_h["train_loader"].fixed_batches:
+        release_memory()
+        try:
+            if not run_h["train_loader"].fixed_batches:
+                raise RuntimeError("batches are not fixed (shuffled multi-partition groups): steps are eager")
             ld = run_h["train_loader"]
             trh = GraphedTrainer(run_h["model"], ld, run_h["optimizer"], VR_update=vr,
                                  grad_norm=run_h["conf"]["grad_norm"], pipeline_collate=True, host_prefetch=True)
@@ -604,57 +676,10 @@ def main():
                           "gathered from host memory through UVA one step ahead (in the collate graph of the "
                           "next batch), pushes as DMA slice copies inside the step graph"}
             del trh
+        except Exception as exc:
+            e2e["host_histories_graphed"] = {"error": str(exc).splitlines()[0]}
         del run_h
-        torch.cuda.empty_cache()
-
-    # the per-epoch refresh sweep (mini_inference / mini_inference_vr over all partitions), timed alone
-    refresh = None
-    from incagg_gnn_b200.train import GraphedSweep
-    from incagg_gnn_b200.loader import EvalSubgraphLoader
-
-    def time_sweep(loader):
-        sweep = GraphedSweep(model, loader, VR_update=vr)
-        sweep()  # captures (once)
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        t0 = time.perf_counter()
-        sweep()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if dist is not None:  # max over ranks (the sharded sweep barriers between layer phases)
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t)
-        return dt
-
-    nnz_all = run["data"].adj_t.nnz()
-    t_epoch = nnz_all / value
-    if world == 1:
-        t_parts = time_sweep(run["eval_loader"])
-        # the same sweep with all partitions merged into ONE evaluation batch (the reference sizes its
-        # eval batches for a 2021 GPU; the tables and every intermediate of a whole-graph layer fit HBM)
-        n_parts = run["ptr"].numel() - 1
-        merged = EvalSubgraphLoader(run["data"], run["ptr"], batch_size=n_parts, log=False, device=dev)
-        t_sweep = time_sweep(merged)
-        del merged
-        torch.cuda.empty_cache()
-        refresh = {"sweep_s": round(t_sweep, 4), "sweep_per_partition_batches_s": round(t_parts, 4),
-                   "train_epoch_s": round(t_epoch, 4),
-                   "edges_per_s_epoch_plus_refresh": nnz_all / (t_epoch + t_sweep),
-                   "note": "value = training steps only; one epoch of the reference loop = train epoch + one "
-                           "layer-wise refresh sweep over all partitions (main.py:226-236); the sweep is one "
-                           "CUDA-graph replay (train.GraphedSweep); sweep_s merges all partitions into one "
-                           f"evaluation batch (EvalSubgraphLoader batch_size={n_parts}), "
-                           "sweep_per_partition_batches_s uses the training batch size as the reference does"}
-    elif args.transport == "p2p":
-        # sharded tables: every rank sweeps its own partitions, halo rows read from the peers' shards;
-        # one CUDA graph per layer phase, a barrier between phases
-        t_sweep = time_sweep(run["eval_loader"])
-        refresh = {"sweep_s": round(t_sweep, 4), "train_epoch_s": round(t_epoch, 4),
-                   "edges_per_s_epoch_plus_refresh": nnz_all / (t_epoch + t_sweep),
-                   "note": f"sharded sweep over {world} ranks (each rank its own partitions, per-partition "
-                           "evaluation batches), one CUDA graph per layer phase + barrier, max over ranks"}
+        release_memory()
 
     if rank != 0:
         if dist is not None:
