@@ -690,7 +690,8 @@ def main():
     peaks = load_peaks()
     roof = spmm_roofline(run, peaks)
     cpu = None
-    if not args.no_cpu_baseline and (args.config == "C3" or args.cpu_steps_given):
+    if not args.no_cpu_baseline and world == 1 and (args.config == "C3" or args.cpu_steps_given):
+        # (rank 0 at N = 1 only: at N > 1 the other ranks' processes wait in a barrier on the same cores)
         # (the other configs step over half a graph of 10^8 edges per batch: minutes per CPU step, so
         # their CPU leg runs only when --cpu-steps is given)
         threads = os.cpu_count() or 1

@@ -313,7 +313,12 @@ allreduce_adam_kernel(const ArPeers peers, int rank, int world, float* __restric
   per = (per + 3) / 4 * 4;
   const int64_t lo = min(n, (int64_t)blockIdx.x * per), hi = min(n, lo + per);
   float* mine = peers.stage[rank] + par;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) mine[i] = g[i];
+  if ((n % 4 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+    for (int64_t i = lo + 4 * (int64_t)threadIdx.x; i < hi; i += 4 * (int64_t)blockDim.x)
+      *reinterpret_cast<float4*>(mine + i) = *reinterpret_cast<const float4*>(g + i);
+  } else {
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) mine[i] = g[i];
+  }
   __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
@@ -333,13 +338,9 @@ allreduce_adam_kernel(const ArPeers peers, int rank, int world, float* __restric
   const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
   const float step_size = lr / bc1;
   const float inv_w = 1.f / (float)world;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    float gi = 0.f;
-    for (int r = 0; r < world; ++r) {
-      const float c = (r == rank) ? g[i] : __ldcv(peers.stage[r] + par + i);
-      gi += c;
-    }
-    gi *= inv_w;
+  // four elements per thread and trip; the W peer loads of a trip are issued back to back (volatile
+  // 128-bit loads over NVLink) before any of them is used
+  auto adam = [&](int64_t i, float gi) {
     g[i] = gi;  // the averaged gradient stays readable (p.grad)
     float pi = p[i];
     const float wd = i < n_decay ? wd_first : wd_rest;
@@ -351,6 +352,34 @@ allreduce_adam_kernel(const ArPeers peers, int rank, int world, float* __restric
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     p[i] = pi - step_size * (mi / denom);
+  };
+  const bool vec_ok = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+  if (vec_ok) {
+    for (int64_t i = lo + 4 * (int64_t)threadIdx.x; i < hi; i += 4 * (int64_t)blockDim.x) {
+      float4 c[AR_MAX_RANKS];
+#pragma unroll
+      for (int r = 0; r < AR_MAX_RANKS; ++r) {
+        if (r < world) {
+          c[r] = (r == rank) ? *reinterpret_cast<const float4*>(g + i)
+                             : __ldcv(reinterpret_cast<const float4*>(peers.stage[r] + par + i));
+        }
+      }
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < AR_MAX_RANKS; ++r) {
+        if (r < world) { sum.x += c[r].x; sum.y += c[r].y; sum.z += c[r].z; sum.w += c[r].w; }
+      }
+      adam(i, sum.x * inv_w);
+      adam(i + 1, sum.y * inv_w);
+      adam(i + 2, sum.z * inv_w);
+      adam(i + 3, sum.w * inv_w);
+    }
+  } else {
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      float gi = 0.f;
+      for (int r = 0; r < world; ++r) gi += (r == rank) ? g[i] : __ldcv(peers.stage[r] + par + i);
+      adam(i, gi * inv_w);
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -582,7 +582,16 @@ def build(config: str, device='cuda', seed: int = 0, scale: int = 1, history_dev
     # eval_batch_size: partitions merged into one batch of the layer-wise sweeps.  The reference sizes
     # it for the GPU memory of its day (= the training batch size); with the tables HBM-resident a
     # sweep over few large batches computes the same rows with far fewer, fuller launches.
-    eval_loader = EvalSubgraphLoader(data, ptr, batch_size=eval_batch_size or conf['batch_size'], log=log,
+    ebs = eval_batch_size or conf['batch_size']
+    if shard is not None and world_size > 1:
+        # merged evaluation batches must not straddle two ranks: the largest block size <= ebs that
+        # divides every rank's number of partitions
+        import math
+        g = 0
+        for r in range(world_size):
+            g = math.gcd(g, shard.part_bounds[r + 1] - shard.part_bounds[r])
+        ebs = max(d for d in range(1, min(ebs, g) + 1) if g % d == 0)
+    eval_loader = EvalSubgraphLoader(data, ptr, batch_size=ebs, log=log,
                                      device=device, shard=shard, halo_plans=(transport == 'nccl'))
     buffer_size = max(n_id.numel() for _, _, n_id, _, _ in eval_loader) * 2
     kwargs = {}
