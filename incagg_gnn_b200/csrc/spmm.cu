@@ -776,6 +776,195 @@ spmm_stream_kernel(const __grid_constant__ SpmmParams p) {
   }
 }
 
+// ---- merge-path kernel with the source rows landed in shared memory by bulk copies -----------------
+//
+// The kernels above keep every in-flight 512-byte row gather in 128 registers (32 lanes x float4), so
+// the register file caps an SM at ~160-200 outstanding gathers - 80-100 KB, about half of what the
+// latency of the L2 / HBM path needs to keep that path busy.  Here the landing zone is shared memory:
+// every warp owns a ring of WB_STAGES stages of WB_STAGE_ROWS rows (6 x 8 x 512 B = 24 KB; 8 warps =
+// 192 KB per SM, i.e. 384 rows in flight), filled by `cp.async.bulk` global -> shared copies (one per
+// edge, issued by the first lanes of the warp, completion counted in bytes on the stage's mbarrier) and
+// drained with one LDS.128 + 4 FMA per edge.  Address generation and the transfers leave the 32-lane
+// instruction stream; the partition of the edge array, the index rings, the row bookkeeping and the
+// deterministic combination of rows cut by a piece boundary are those of spmm_stream_kernel.
+constexpr int WB_WARPS = 8;
+constexpr int WB_STAGE_ROWS = 8;
+constexpr int WB_STAGES = 6;
+constexpr int WB_SMEM_BYTES = WB_WARPS * WB_STAGES * WB_STAGE_ROWS * WS_TILE_F * 4;  // 196,608
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(ptr));
+}
+
+__global__ void __launch_bounds__(WB_WARPS * 32, 1)
+spmm_bulk_kernel(const __grid_constant__ SpmmParams p) {
+  pdl_prologue();
+  extern __shared__ __align__(128) float wb_ring[];
+  __shared__ int s_c[WB_WARPS][128];
+  __shared__ float s_v[WB_WARPS][128];
+  __shared__ int s_rp[WB_WARPS][64];
+  __shared__ uint64_t s_bar[WB_WARPS][WB_STAGES];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int w = blockIdx.x * WB_WARPS + wi;
+  const int f = blockIdx.y * WS_TILE_F + lane * 4;
+  const bool fok = f < p.F;
+  const int rows = (int)p.rows;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int e0, e1;
+  float* my_part;
+  {
+    const int4 h1 = __ldg(reinterpret_cast<const int4*>(p.plan) + 1);  // capacity, n_wslots, q, e_base
+    const int4 h2 = __ldg(reinterpret_cast<const int4*>(p.plan) + 2);  // e_end
+    if (w >= h1.y) return;
+    if (h1.w == h2.x) {
+      for (int r = w; r < rows; r += h1.y) ws_finish(p, r, 0, zero4, f, fok);
+      return;
+    }
+    e0 = h1.w + w * h1.z;
+    if (e0 >= h2.x) return;
+    e1 = min(e0 + h1.z, h2.x);
+    my_part = p.ws_part + (((int64_t)blockIdx.y * h1.y + w) * 2) * WS_TILE_F + lane * 4;
+  }
+  int* sc = s_c[wi];
+  float* sv = s_v[wi];
+  int* rpw = s_rp[wi];
+  uint64_t* bar = s_bar[wi];
+  float* ring = wb_ring + (size_t)wi * WB_STAGES * WB_STAGE_ROWS * WS_TILE_F;
+  if (lane == 0) {
+    for (int st = 0; st < WB_STAGES; ++st)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[st])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  auto ld_blk = [&](int b, int& c, float& v) {
+    const int idx = e0 + b * 32 + lane;
+    c = 0;
+    v = 0.f;
+    if (idx < e1) {
+      c = ldg_stream(p.col + idx);
+      v = p.val ? ldg_stream(p.val + idx) : 1.f;
+    }
+  };
+  int r, rbase, rp_pre, cn;
+  float vn;
+  {
+    int c1, c2;
+    float v1, v2;
+    ld_blk(0, cn, vn);
+    ld_blk(1, c1, v1);
+    ld_blk(2, c2, v2);
+    const int capacity = __ldg(reinterpret_cast<const int*>(p.plan) + 4);
+    r = __ldg(reinterpret_cast<const int*>(p.items + capacity) + w);
+    rbase = r;
+    const int rp_a = __ldg(p.rowptr + min(rbase + lane, rows));
+    const int rp_b = __ldg(p.rowptr + min(rbase + 32 + lane, rows));
+    rp_pre = __ldg(p.rowptr + min(rbase + 64 + lane, rows));
+    sc[lane] = cn; sv[lane] = vn;
+    sc[32 + lane] = c1; sv[32 + lane] = v1;
+    sc[64 + lane] = c2; sv[64 + lane] = v2;
+    ld_blk(3, cn, vn);
+    rpw[(rbase + lane) & 63] = rp_a;
+    rpw[(rbase + 32 + lane) & 63] = rp_b;
+  }
+  __syncwarp();
+
+  // this tile's slice of a source row: row_bytes at byte offset c * x_bytes + tile * 512
+  const char* Xt = reinterpret_cast<const char*>(p.X + blockIdx.y * WS_TILE_F);
+  const unsigned x_bytes = (unsigned)p.ldx * 4u;
+  const unsigned row_bytes = (unsigned)min(WS_TILE_F, p.F - (int)blockIdx.y * WS_TILE_F) * 4u;
+  const int n_groups = (e1 - e0 + WB_STAGE_ROWS - 1) / WB_STAGE_ROWS;
+  // stage g % WB_STAGES <- the rows of edges [e0 + 8 g, e0 + 8 g + 8): lane u issues the copy of edge u
+  auto arm = [&](int g) {
+    if (g >= n_groups) return;
+    const int stage = g % WB_STAGES;
+    const int base = e0 + g * WB_STAGE_ROWS;
+    const int cnt = min(WB_STAGE_ROWS, e1 - base);
+    const uint32_t b = smem_u32(&bar[stage]);
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(cnt * row_bytes) : "memory");
+    if (lane < cnt) {
+      const unsigned c = (unsigned)sc[(base + lane - e0) & 127];
+      const char* src = Xt + (size_t)c * x_bytes;
+      const uint32_t dst = smem_u32(ring + ((size_t)stage * WB_STAGE_ROWS + lane) * WS_TILE_F);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(src), "r"(row_bytes), "r"(b) : "memory");
+    }
+  };
+#pragma unroll 1
+  for (int g = 0; g < WB_STAGES; ++g) arm(g);
+  if (w == 0)
+    for (int rr = 0; rr < r; ++rr) ws_finish(p, rr, 0, zero4, f, fok);
+  int row_start = rpw[r & 63], row_end = rpw[(r + 1) & 63];
+  const bool head_cut = row_start < e0;
+  float4 acc = zero4;
+  auto next_row = [&]() {
+    ++r;
+    if (r - rbase >= 32) {
+      rpw[(rbase + 64 + lane) & 63] = rp_pre;
+      rbase += 32;
+      rp_pre = __ldg(p.rowptr + min(rbase + 64 + lane, rows));
+      __syncwarp();
+    }
+    row_start = row_end;
+    row_end = rpw[(r + 1) & 63];
+  };
+  auto row_done = [&]() {
+    if (row_start >= e0) ws_finish(p, r, row_end - row_start, acc, f, fok);
+    else *reinterpret_cast<float4*>(my_part) = acc;
+    acc = zero4;
+    next_row();
+  };
+#pragma unroll 1
+  for (int g = 0; g < n_groups; ++g) {
+    const int off = g * WB_STAGE_ROWS;
+    if ((off & 31) == 0 && off != 0) {  // rotate the index blocks
+      const int b = (off >> 5) + 2;
+      sc[(b * 32 + lane) & 127] = cn;
+      sv[(b * 32 + lane) & 127] = vn;
+      ld_blk(b + 1, cn, vn);
+      __syncwarp();
+    }
+    const int stage = g % WB_STAGES;
+    const uint32_t parity = (uint32_t)((g / WB_STAGES) & 1);
+    const uint32_t b = smem_u32(&bar[stage]);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WB_DONE;\n\tbra WB_WAIT;\n\tWB_DONE:\n\t}" ::"r"(b), "r"(parity) : "memory");
+    const int base = e0 + off;
+    const float* st = ring + (size_t)stage * WB_STAGE_ROWS * WS_TILE_F + lane * 4;
+#pragma unroll
+    for (int u = 0; u < WB_STAGE_ROWS; ++u) {
+      const int jj = base + u;
+      if (jj < e1) {  // uniform
+        while (jj >= row_end) row_done();
+        const float v = sv[(jj - e0) & 127];
+        const float4 x = *reinterpret_cast<const float4*>(st + u * WS_TILE_F);
+        acc.x = fmaf(v, x.x, acc.x); acc.y = fmaf(v, x.y, acc.y);
+        acc.z = fmaf(v, x.z, acc.z); acc.w = fmaf(v, x.w, acc.w);
+      }
+    }
+    __syncwarp();            // every lane has read the stage
+    arm(g + WB_STAGES);      // refill it
+  }
+  const bool tail_inside = row_end <= e1 && row_start >= e0;
+  const int t_row = r;
+  if (tail_inside) ws_finish(p, r, row_end - row_start, acc, f, fok);
+  else *reinterpret_cast<float4*>(my_part + (row_start >= e0 ? WS_TILE_F : 0)) = acc;
+  if (row_end <= e1) {
+    while (r + 1 < rows) {
+      next_row();
+      if (row_end > e1) break;
+      ws_finish(p, r, 0, zero4, f, fok);
+    }
+  }
+  if (head_cut || !tail_inside) {
+    const int capacity = __ldg(reinterpret_cast<const int*>(p.plan) + 4);
+    const int r0 = __ldg(reinterpret_cast<const int*>(p.items + capacity) + w);
+    if (head_cut && (r0 != t_row || tail_inside)) ws_publish(p, w, blockIdx.y, r0, f, fok);
+    if (!tail_inside) ws_publish(p, w, blockIdx.y, t_row, f, fok);
+  }
+}
+
 // ---- merge-path kernel, two edges per warp instruction -------------------------------------------
 //
 // Same partition and the same shared-memory index rings as spmm_stream_kernel, but a 128-feature tile
@@ -1193,6 +1382,7 @@ static int stream_variant_for(bool delta) {
 }
 static int stream_min_f() { return incagg::tune_get(INCAGG_TUNE_SPMM_STREAM_MIN_F, 65); }
 static int stream_ctas_per_sm(int variant) {
+  if (variant >= 20) return 1;   // bulk-copy kernel: one CTA of 8 warps with a 192 KB ring per SM
   if (variant >= 10) return variant == 11 ? 3 : (variant == 12 ? 4 : (variant == 13 ? 1 : 2));
   return variant == 1 ? 4 : (variant == 2 ? 3 : (variant == 3 ? 5 : (variant == 4 ? 6 : (variant == 5 ? 1 : 2))));
 }
@@ -1301,6 +1491,20 @@ static int try_stream(SpmmParams& p, int reduce, int vec, cudaStream_t st) {
   const int tiles = (p.F + WS_TILE_F - 1) / WS_TILE_F;
   dim3 grid((unsigned)((n_w + WS_WARPS - 1) / WS_WARPS), (unsigned)tiles);
   const bool delta = p.m_in != nullptr;
+  if (variant >= 20) {
+    // rows landed in shared memory by bulk copies: 16-byte aligned row slices, no delta form
+    if (delta || p.F % 4 != 0 || p.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(p.X) & 15) != 0) return 1;
+    static bool attr_set[16] = {false};
+    int dev = 0;
+    IA_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 16 && !attr_set[dev]) {
+      IA_CUDA(cudaFuncSetAttribute(spmm_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WB_SMEM_BYTES));
+      attr_set[dev] = true;
+    }
+    launch(spmm_bulk_kernel, grid, dim3(WB_WARPS * 32), (size_t)WB_SMEM_BYTES, st, p);
+    IA_LAUNCH_CHECK();
+    return INCAGG_OK;
+  }
   if (variant >= 10) {
     // two edges per warp instruction: needs 8-float column groups and 32-byte aligned rows
     const bool ok8 = p.F % 8 == 0 && p.ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(p.X) & 31) == 0 &&
