@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 VARIANTS = {"rows": -1, "s8x2": 0, "s4x4": 1, "s4x3": 2, "s2x5": 3, "s2x6": 4, "s16x1": 5,
-            "p4x2": 10, "p2x3": 11, "p2x4": 12, "p8x1": 13, "bulk": 20}
+            "p4x2": 10, "p2x3": 11, "p2x4": 12, "p8x1": 13, "bulk": 20, "cpa16x3": 21, "cpa8x6": 22}
 
 
 def main():
