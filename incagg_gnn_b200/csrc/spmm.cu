@@ -776,676 +776,10 @@ spmm_stream_kernel(const __grid_constant__ SpmmParams p) {
   }
 }
 
-// ---- merge-path kernel with the source rows landed in shared memory by bulk copies -----------------
-//
-// The kernels above keep every in-flight 512-byte row gather in 128 registers (32 lanes x float4), so
-// the register file caps an SM at ~160-200 outstanding gathers - 80-100 KB, about half of what the
-// latency of the L2 / HBM path needs to keep that path busy.  Here the landing zone is shared memory:
-// every warp owns a ring of WB_STAGES stages of WB_STAGE_ROWS rows (6 x 8 x 512 B = 24 KB; 8 warps =
-// 192 KB per SM, i.e. 384 rows in flight), filled by `cp.async.bulk` global -> shared copies (one per
-// edge, issued by the first lanes of the warp, completion counted in bytes on the stage's mbarrier) and
-// drained with one LDS.128 + 4 FMA per edge.  Address generation and the transfers leave the 32-lane
-// instruction stream; the partition of the edge array, the index rings, the row bookkeeping and the
-// deterministic combination of rows cut by a piece boundary are those of spmm_stream_kernel.
-constexpr int WB_WARPS = 8;
-constexpr int WB_STAGE_ROWS = 8;
-constexpr int WB_STAGES = 6;
-constexpr int WB_SMEM_BYTES = WB_WARPS * WB_STAGES * WB_STAGE_ROWS * WS_TILE_F * 4;  // 196,608
-
-__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(ptr));
-}
-
-__global__ void __launch_bounds__(WB_WARPS * 32, 1)
-spmm_bulk_kernel(const __grid_constant__ SpmmParams p) {
-  pdl_prologue();
-  extern __shared__ __align__(128) float wb_ring[];
-  __shared__ int s_c[WB_WARPS][128];
-  __shared__ float s_v[WB_WARPS][128];
-  __shared__ int s_rp[WB_WARPS][64];
-  __shared__ uint64_t s_bar[WB_WARPS][WB_STAGES];
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int w = blockIdx.x * WB_WARPS + wi;
-  const int f = blockIdx.y * WS_TILE_F + lane * 4;
-  const bool fok = f < p.F;
-  const int rows = (int)p.rows;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  int e0, e1;
-  float* my_part;
-  {
-    const int4 h1 = __ldg(reinterpret_cast<const int4*>(p.plan) + 1);  // capacity, n_wslots, q, e_base
-    const int4 h2 = __ldg(reinterpret_cast<const int4*>(p.plan) + 2);  // e_end
-    if (w >= h1.y) return;
-    if (h1.w == h2.x) {
-      for (int r = w; r < rows; r += h1.y) ws_finish(p, r, 0, zero4, f, fok);
-      return;
-    }
-    e0 = h1.w + w * h1.z;
-    if (e0 >= h2.x) return;
-    e1 = min(e0 + h1.z, h2.x);
-    my_part = p.ws_part + (((int64_t)blockIdx.y * h1.y + w) * 2) * WS_TILE_F + lane * 4;
-  }
-  int* sc = s_c[wi];
-  float* sv = s_v[wi];
-  int* rpw = s_rp[wi];
-  uint64_t* bar = s_bar[wi];
-  float* ring = wb_ring + (size_t)wi * WB_STAGES * WB_STAGE_ROWS * WS_TILE_F;
-  if (lane == 0) {
-    for (int st = 0; st < WB_STAGES; ++st)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[st])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  auto ld_blk = [&](int b, int& c, float& v) {
-    const int idx = e0 + b * 32 + lane;
-    c = 0;
-    v = 0.f;
-    if (idx < e1) {
-      c = ldg_stream(p.col + idx);
-      v = p.val ? ldg_stream(p.val + idx) : 1.f;
-    }
-  };
-  int r, rbase, rp_pre, cn;
-  float vn;
-  {
-    int c1, c2;
-    float v1, v2;
-    ld_blk(0, cn, vn);
-    ld_blk(1, c1, v1);
-    ld_blk(2, c2, v2);
-    const int capacity = __ldg(reinterpret_cast<const int*>(p.plan) + 4);
-    r = __ldg(reinterpret_cast<const int*>(p.items + capacity) + w);
-    rbase = r;
-    const int rp_a = __ldg(p.rowptr + min(rbase + lane, rows));
-    const int rp_b = __ldg(p.rowptr + min(rbase + 32 + lane, rows));
-    rp_pre = __ldg(p.rowptr + min(rbase + 64 + lane, rows));
-    sc[lane] = cn; sv[lane] = vn;
-    sc[32 + lane] = c1; sv[32 + lane] = v1;
-    sc[64 + lane] = c2; sv[64 + lane] = v2;
-    ld_blk(3, cn, vn);
-    rpw[(rbase + lane) & 63] = rp_a;
-    rpw[(rbase + 32 + lane) & 63] = rp_b;
-  }
-  __syncwarp();
-
-  // this tile's slice of a source row: row_bytes at byte offset c * x_bytes + tile * 512
-  const char* Xt = reinterpret_cast<const char*>(p.X + blockIdx.y * WS_TILE_F);
-  const unsigned x_bytes = (unsigned)p.ldx * 4u;
-  const unsigned row_bytes = (unsigned)min(WS_TILE_F, p.F - (int)blockIdx.y * WS_TILE_F) * 4u;
-  const int n_groups = (e1 - e0 + WB_STAGE_ROWS - 1) / WB_STAGE_ROWS;
-  // stage g % WB_STAGES <- the rows of edges [e0 + 8 g, e0 + 8 g + 8): lane u issues the copy of edge u
-  auto arm = [&](int g) {
-    if (g >= n_groups) return;
-    const int stage = g % WB_STAGES;
-    const int base = e0 + g * WB_STAGE_ROWS;
-    const int cnt = min(WB_STAGE_ROWS, e1 - base);
-    const uint32_t b = smem_u32(&bar[stage]);
-    if (lane == 0)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(cnt * row_bytes) : "memory");
-    if (lane < cnt) {
-      const unsigned c = (unsigned)sc[(base + lane - e0) & 127];
-      const char* src = Xt + (size_t)c * x_bytes;
-      const uint32_t dst = smem_u32(ring + ((size_t)stage * WB_STAGE_ROWS + lane) * WS_TILE_F);
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(dst), "l"(src), "r"(row_bytes), "r"(b) : "memory");
-    }
-  };
-#pragma unroll 1
-  for (int g = 0; g < WB_STAGES; ++g) arm(g);
-  if (w == 0)
-    for (int rr = 0; rr < r; ++rr) ws_finish(p, rr, 0, zero4, f, fok);
-  int row_start = rpw[r & 63], row_end = rpw[(r + 1) & 63];
-  const bool head_cut = row_start < e0;
-  float4 acc = zero4;
-  auto next_row = [&]() {
-    ++r;
-    if (r - rbase >= 32) {
-      rpw[(rbase + 64 + lane) & 63] = rp_pre;
-      rbase += 32;
-      rp_pre = __ldg(p.rowptr + min(rbase + 64 + lane, rows));
-      __syncwarp();
-    }
-    row_start = row_end;
-    row_end = rpw[(r + 1) & 63];
-  };
-  auto row_done = [&]() {
-    if (row_start >= e0) ws_finish(p, r, row_end - row_start, acc, f, fok);
-    else *reinterpret_cast<float4*>(my_part) = acc;
-    acc = zero4;
-    next_row();
-  };
-#pragma unroll 1
-  for (int g = 0; g < n_groups; ++g) {
-    const int off = g * WB_STAGE_ROWS;
-    if ((off & 31) == 0 && off != 0) {  // rotate the index blocks
-      const int b = (off >> 5) + 2;
-      sc[(b * 32 + lane) & 127] = cn;
-      sv[(b * 32 + lane) & 127] = vn;
-      ld_blk(b + 1, cn, vn);
-      __syncwarp();
-    }
-    const int stage = g % WB_STAGES;
-    const uint32_t parity = (uint32_t)((g / WB_STAGES) & 1);
-    const uint32_t b = smem_u32(&bar[stage]);
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tWB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WB_DONE;\n\tbra WB_WAIT;\n\tWB_DONE:\n\t}" ::"r"(b), "r"(parity) : "memory");
-    const int base = e0 + off;
-    const float* st = ring + (size_t)stage * WB_STAGE_ROWS * WS_TILE_F + lane * 4;
-#pragma unroll
-    for (int u = 0; u < WB_STAGE_ROWS; ++u) {
-      const int jj = base + u;
-      if (jj < e1) {  // uniform
-        while (jj >= row_end) row_done();
-        const float v = sv[(jj - e0) & 127];
-        const float4 x = *reinterpret_cast<const float4*>(st + u * WS_TILE_F);
-        acc.x = fmaf(v, x.x, acc.x); acc.y = fmaf(v, x.y, acc.y);
-        acc.z = fmaf(v, x.z, acc.z); acc.w = fmaf(v, x.w, acc.w);
-      }
-    }
-    __syncwarp();            // every lane has read the stage
-    arm(g + WB_STAGES);      // refill it
-  }
-  const bool tail_inside = row_end <= e1 && row_start >= e0;
-  const int t_row = r;
-  if (tail_inside) ws_finish(p, r, row_end - row_start, acc, f, fok);
-  else *reinterpret_cast<float4*>(my_part + (row_start >= e0 ? WS_TILE_F : 0)) = acc;
-  if (row_end <= e1) {
-    while (r + 1 < rows) {
-      next_row();
-      if (row_end > e1) break;
-      ws_finish(p, r, 0, zero4, f, fok);
-    }
-  }
-  if (head_cut || !tail_inside) {
-    const int capacity = __ldg(reinterpret_cast<const int*>(p.plan) + 4);
-    const int r0 = __ldg(reinterpret_cast<const int*>(p.items + capacity) + w);
-    if (head_cut && (r0 != t_row || tail_inside)) ws_publish(p, w, blockIdx.y, r0, f, fok);
-    if (!tail_inside) ws_publish(p, w, blockIdx.y, t_row, f, fok);
-  }
-}
-
-// Same idea with Ampere-style asynchronous copies instead of the bulk-copy engine: `cp.async.cg` 16 bytes
-// per lane (one warp instruction = one 512-byte row, L2 -> shared memory, no register), completion by
-// commit / wait groups, which are ordered per thread - the rolling pipeline the counting scoreboards of
-// plain loads cannot express.  (The bulk-copy engine serves a 512-byte copy every ~43 cycles per SM,
-// measured: spmm_bulk_kernel takes 66 us where the row kernel takes 33.)
-template <int WARPS, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32, 1)
-spmm_cpasync_kernel(const __grid_constant__ SpmmParams p) {
-  pdl_prologue();
-  extern __shared__ __align__(128) float wb_ring[];
-  __shared__ int s_c[WARPS][128];
-  __shared__ float s_v[WARPS][128];
-  __shared__ int s_rp[WARPS][64];
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int w = blockIdx.x * WARPS + wi;
-  const int f = blockIdx.y * WS_TILE_F + lane * 4;
-  const bool fok = f < p.F;
-  const int rows = (int)p.rows;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  int e0, e1;
-  float* my_part;
-  {
-    const int4 h1 = __ldg(reinterpret_cast<const int4*>(p.plan) + 1);  // capacity, n_wslots, q, e_base
-    const int4 h2 = __ldg(reinterpret_cast<const int4*>(p.plan) + 2);  // e_end
-    if (w >= h1.y) return;
-    if (h1.w == h2.x) {
-      for (int r = w; r < rows; r += h1.y) ws_finish(p, r, 0, zero4, f, fok);
-      return;
-    }
-    e0 = h1.w + w * h1.z;
-    if (e0 >= h2.x) return;
-    e1 = min(e0 + h1.z, h2.x);
-    my_part = p.ws_part + (((int64_t)blockIdx.y * h1.y + w) * 2) * WS_TILE_F + lane * 4;
-  }
-  int* sc = s_c[wi];
-  float* sv = s_v[wi];
-  int* rpw = s_rp[wi];
-  float* ring = wb_ring + (size_t)wi * STAGES * WB_STAGE_ROWS * WS_TILE_F;
-  auto ld_blk = [&](int b, int& c, float& v) {
-    const int idx = e0 + b * 32 + lane;
-    c = 0;
-    v = 0.f;
-    if (idx < e1) {
-      c = ldg_stream(p.col + idx);
-      v = p.val ? ldg_stream(p.val + idx) : 1.f;
-    }
-  };
-  int r, rbase, rp_pre, cn;
-  float vn;
-  {
-    int c1, c2;
-    float v1, v2;
-    ld_blk(0, cn, vn);
-    ld_blk(1, c1, v1);
-    ld_blk(2, c2, v2);
-    const int capacity = __ldg(reinterpret_cast<const int*>(p.plan) + 4);
-    r = __ldg(reinterpret_cast<const int*>(p.items + capacity) + w);
-    rbase = r;
-    const int rp_a = __ldg(p.rowptr + min(rbase + lane, rows));
-    const int rp_b = __ldg(p.rowptr + min(rbase + 32 + lane, rows));
-    rp_pre = __ldg(p.rowptr + min(rbase + 64 + lane, rows));
-    sc[lane] = cn; sv[lane] = vn;
-    sc[32 + lane] = c1; sv[32 + lane] = v1;
-    sc[64 + lane] = c2; sv[64 + lane] = v2;
-    ld_blk(3, cn, vn);
-    rpw[(rbase + lane) & 63] = rp_a;
-    rpw[(rbase + 32 + lane) & 63] = rp_b;
-  }
-  __syncwarp();
-
-  // this tile's slice of a source row: row_bytes at byte offset c * x_bytes + tile * 512
-  const char* Xt = reinterpret_cast<const char*>(p.X + blockIdx.y * WS_TILE_F);
-  const unsigned x_bytes = (unsigned)p.ldx * 4u;
-  const unsigned row_bytes = (unsigned)min(WS_TILE_F, p.F - (int)blockIdx.y * WS_TILE_F) * 4u;
-  const int n_groups = (e1 - e0 + WB_STAGE_ROWS - 1) / WB_STAGE_ROWS;
-  // stage g % STAGES <- the rows of edges [e0 + 8 g, e0 + 8 g + 8): every lane copies ITS 16 bytes of each
-  // row (cp.async, L2 -> shared memory without a register) and later reads exactly those bytes back, so
-  // no lane depends on another lane's copies; one commit group per stage, also when it is empty
-  const unsigned my_off = (unsigned)lane * 16u;
-  const bool my_ok = my_off < row_bytes;
-  auto arm = [&](int g) {
-    if (g < n_groups && my_ok) {
-      const int stage = g % STAGES;
-      const int base = e0 + g * WB_STAGE_ROWS;
-      const int cnt = min(WB_STAGE_ROWS, e1 - base);
-#pragma unroll
-      for (int u = 0; u < WB_STAGE_ROWS; ++u) {
-        if (u < cnt) {
-          const unsigned c = (unsigned)sc[(base + u - e0) & 127];
-          const char* src = Xt + (size_t)c * x_bytes + my_off;
-          const uint32_t dst = smem_u32(ring + ((size_t)stage * WB_STAGE_ROWS + u) * WS_TILE_F) + my_off;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-#pragma unroll 1
-  for (int g = 0; g < STAGES; ++g) arm(g);
-  if (w == 0)
-    for (int rr = 0; rr < r; ++rr) ws_finish(p, rr, 0, zero4, f, fok);
-  int row_start = rpw[r & 63], row_end = rpw[(r + 1) & 63];
-  const bool head_cut = row_start < e0;
-  float4 acc = zero4;
-  auto next_row = [&]() {
-    ++r;
-    if (r - rbase >= 32) {
-      rpw[(rbase + 64 + lane) & 63] = rp_pre;
-      rbase += 32;
-      rp_pre = __ldg(p.rowptr + min(rbase + 64 + lane, rows));
-      __syncwarp();
-    }
-    row_start = row_end;
-    row_end = rpw[(r + 1) & 63];
-  };
-  auto row_done = [&]() {
-    if (row_start >= e0) ws_finish(p, r, row_end - row_start, acc, f, fok);
-    else *reinterpret_cast<float4*>(my_part) = acc;
-    acc = zero4;
-    next_row();
-  };
-#pragma unroll 1
-  for (int g = 0; g < n_groups; ++g) {
-    const int off = g * WB_STAGE_ROWS;
-    if ((off & 31) == 0 && off != 0) {  // rotate the index blocks
-      const int b = (off >> 5) + 2;
-      sc[(b * 32 + lane) & 127] = cn;
-      sv[(b * 32 + lane) & 127] = vn;
-      ld_blk(b + 1, cn, vn);
-      __syncwarp();
-    }
-    const int stage = g % STAGES;
-    // the copies of this stage are done when at most STAGES - 1 newer groups are still pending
-    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
-    const int base = e0 + off;
-    const float* st = ring + (size_t)stage * WB_STAGE_ROWS * WS_TILE_F + lane * 4;
-#pragma unroll
-    for (int u = 0; u < WB_STAGE_ROWS; ++u) {
-      const int jj = base + u;
-      if (jj < e1) {  // uniform
-        while (jj >= row_end) row_done();
-        const float v = sv[(jj - e0) & 127];
-        const float4 x = *reinterpret_cast<const float4*>(st + u * WS_TILE_F);
-        acc.x = fmaf(v, x.x, acc.x); acc.y = fmaf(v, x.y, acc.y);
-        acc.z = fmaf(v, x.z, acc.z); acc.w = fmaf(v, x.w, acc.w);
-      }
-    }
-    arm(g + STAGES);      // refill the stage (each lane overwrites only bytes it has just read)
-  }
-  const bool tail_inside = row_end <= e1 && row_start >= e0;
-  const int t_row = r;
-  if (tail_inside) ws_finish(p, r, row_end - row_start, acc, f, fok);
-  else *reinterpret_cast<float4*>(my_part + (row_start >= e0 ? WS_TILE_F : 0)) = acc;
-  if (row_end <= e1) {
-    while (r + 1 < rows) {
-      next_row();
-      if (row_end > e1) break;
-      ws_finish(p, r, 0, zero4, f, fok);
-    }
-  }
-  if (head_cut || !tail_inside) {
-    const int capacity = __ldg(reinterpret_cast<const int*>(p.plan) + 4);
-    const int r0 = __ldg(reinterpret_cast<const int*>(p.items + capacity) + w);
-    if (head_cut && (r0 != t_row || tail_inside)) ws_publish(p, w, blockIdx.y, r0, f, fok);
-    if (!tail_inside) ws_publish(p, w, blockIdx.y, t_row, f, fok);
-  }
-}
-
-// ---- merge-path kernel, two edges per warp instruction -------------------------------------------
-//
-// Same partition and the same shared-memory index rings as spmm_stream_kernel, but a 128-feature tile
-// is covered by HALF a warp (16 lanes x 8 floats, one 256-bit load per lane): the two halves of a warp
-// take the even and the odd edges of the piece, so one warp instruction gathers two 512-byte rows and
-// the per-edge instruction count halves (the row kernel and the one-edge-per-instruction stream kernel
-// are bound by instruction issue, ~25-30 instructions per edge, not by memory).  The two halves keep
-// separate partial sums of the current row; at the end of a row they are added (8 shuffles) and lanes
-// 0-15 write the row.  A pair of edges that straddles a row end is handled by the two halves in turn.
-struct F8 {
-  float4 lo, hi;
-};
-__device__ __forceinline__ F8 ldg256(const void* ptr) {
-  F8 r;
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z),
-                 "=f"(r.hi.w)
-               : "l"(ptr));
-  return r;
-}
-__device__ __forceinline__ void f8_fma(F8& a, float v, const F8& x) {
-  a.lo.x = fmaf(v, x.lo.x, a.lo.x); a.lo.y = fmaf(v, x.lo.y, a.lo.y);
-  a.lo.z = fmaf(v, x.lo.z, a.lo.z); a.lo.w = fmaf(v, x.lo.w, a.lo.w);
-  a.hi.x = fmaf(v, x.hi.x, a.hi.x); a.hi.y = fmaf(v, x.hi.y, a.hi.y);
-  a.hi.z = fmaf(v, x.hi.z, a.hi.z); a.hi.w = fmaf(v, x.hi.w, a.hi.w);
-}
-__device__ __forceinline__ void f8_fma_delta(F8& a, float v, const F8& x, const F8& m) {
-  a.lo.x = fmaf(v, x.lo.x - m.lo.x, a.lo.x); a.lo.y = fmaf(v, x.lo.y - m.lo.y, a.lo.y);
-  a.lo.z = fmaf(v, x.lo.z - m.lo.z, a.lo.z); a.lo.w = fmaf(v, x.lo.w - m.lo.w, a.lo.w);
-  a.hi.x = fmaf(v, x.hi.x - m.hi.x, a.hi.x); a.hi.y = fmaf(v, x.hi.y - m.hi.y, a.hi.y);
-  a.hi.z = fmaf(v, x.hi.z - m.hi.z, a.hi.z); a.hi.w = fmaf(v, x.hi.w - m.hi.w, a.hi.w);
-}
-__device__ __forceinline__ F8 f8_zero() {
-  F8 r;
-  r.lo = make_float4(0.f, 0.f, 0.f, 0.f);
-  r.hi = r.lo;
-  return r;
-}
-// sum of the two halves of the warp (every lane gets the total of its column group)
-__device__ __forceinline__ F8 f8_fold(const F8& a) {
-  F8 r;
-  r.lo.x = a.lo.x + __shfl_xor_sync(0xffffffffu, a.lo.x, 16); r.lo.y = a.lo.y + __shfl_xor_sync(0xffffffffu, a.lo.y, 16);
-  r.lo.z = a.lo.z + __shfl_xor_sync(0xffffffffu, a.lo.z, 16); r.lo.w = a.lo.w + __shfl_xor_sync(0xffffffffu, a.lo.w, 16);
-  r.hi.x = a.hi.x + __shfl_xor_sync(0xffffffffu, a.hi.x, 16); r.hi.y = a.hi.y + __shfl_xor_sync(0xffffffffu, a.hi.y, 16);
-  r.hi.z = a.hi.z + __shfl_xor_sync(0xffffffffu, a.hi.z, 16); r.hi.w = a.hi.w + __shfl_xor_sync(0xffffffffu, a.hi.w, 16);
-  return r;
-}
-
-// Row epilogue for 8 features per lane (lanes 0-15 of the warp store).  Not inlined: one copy.
-__device__ __noinline__ void wp_finish(const SpmmParams& p, int row, int deg, F8 a, int f, bool store) {
-  if (!store) return;
-  if (p.mean) {
-    const float inv = 1.f / (float)max(deg, 1);
-    a.lo.x *= inv; a.lo.y *= inv; a.lo.z *= inv; a.lo.w *= inv;
-    a.hi.x *= inv; a.hi.y *= inv; a.hi.z *= inv; a.hi.w *= inv;
-  }
-  if (p.m_ag != nullptr) {
-    const float4* mp = reinterpret_cast<const float4*>(p.m_ag + (int64_t)row * p.ld_ag + f);
-    const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-    a.lo.x += m0.x; a.lo.y += m0.y; a.lo.z += m0.z; a.lo.w += m0.w;
-    a.hi.x += m1.x; a.hi.y += m1.y; a.hi.z += m1.z; a.hi.w += m1.w;
-  }
-  if (p.gate != nullptr) {
-    const float4* gp = reinterpret_cast<const float4*>(p.gate + (int64_t)row * p.ld_gate + f);
-    const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
-    a.lo.x = g0.x > 0.f ? a.lo.x : 0.f; a.lo.y = g0.y > 0.f ? a.lo.y : 0.f;
-    a.lo.z = g0.z > 0.f ? a.lo.z : 0.f; a.lo.w = g0.w > 0.f ? a.lo.w : 0.f;
-    a.hi.x = g1.x > 0.f ? a.hi.x : 0.f; a.hi.y = g1.y > 0.f ? a.hi.y : 0.f;
-    a.hi.z = g1.z > 0.f ? a.hi.z : 0.f; a.hi.w = g1.w > 0.f ? a.hi.w : 0.f;
-  }
-  float4* op = reinterpret_cast<float4*>(p.out + (int64_t)row * p.ldo + f);
-  op[0] = a.lo;
-  op[1] = a.hi;
-}
-
-// Publication of a cut row's part (see ws_publish); 8 features per lane, lanes 0-15 hold the columns.
-__device__ __noinline__ void wp_publish(const SpmmParams& p, int w, int tile, int row, int f, bool store) {
-  const int lane = threadIdx.x & 31;
-  const int4 h1 = __ldg(reinterpret_cast<const int4*>(p.plan) + 1);  // capacity, n_wslots, q, e_base
-  const int n_w = h1.y, q = h1.z, e_base = h1.w;
-  const int rs = __ldg(p.rowptr + row), re = __ldg(p.rowptr + row + 1);
-  const int first = (rs - e_base) / q, last = (re - 1 - e_base) / q;
-  const int64_t tbase = (int64_t)tile * n_w;
-  __threadfence();
-  int prev = 0;
-  if (lane == 0) prev = atomicAdd(p.ws_done + tbase + first, 1);
-  prev = __shfl_sync(0xffffffffu, prev, 0);
-  if (prev != last - first) return;
-  __threadfence();
-  const int l16 = lane & 15;
-  const float4* sp = reinterpret_cast<const float4*>(p.ws_part + ((tbase + first) * 2 + 1) * WS_TILE_F + l16 * 8);
-  F8 s;
-  s.lo = __ldcg(sp);
-  s.hi = __ldcg(sp + 1);
-  for (int ww = first + 1; ww <= last; ++ww) {
-    const float4* tp = reinterpret_cast<const float4*>(p.ws_part + ((tbase + ww) * 2) * WS_TILE_F + l16 * 8);
-    const float4 t0 = __ldcg(tp), t1 = __ldcg(tp + 1);
-    s.lo.x += t0.x; s.lo.y += t0.y; s.lo.z += t0.z; s.lo.w += t0.w;
-    s.hi.x += t1.x; s.hi.y += t1.y; s.hi.z += t1.z; s.hi.w += t1.w;
-  }
-  if (lane == 0) p.ws_done[tbase + first] = 0;  // clean for the next call
-  wp_finish(p, row, re - rs, s, f, store);
-}
-
-// Row bookkeeping of a piece: current row, its edge range, and the rowptr window (shared-memory ring
-// of rowptr[rbase .. rbase + 63], the next 32 entries prefetched in rp_pre).
-struct RowState {
-  int r, rbase, rp_pre, row_start, row_end;
-};
-// The last edge of row st.r has been consumed (the row ends inside this piece): fold the two halves,
-// write the row (or park the head part of a row that started in an earlier piece) and step to the
-// next row.  One copy, called from every slot of the unrolled gather buffers.
-__device__ __noinline__ RowState wp_row_close(const SpmmParams& p, RowState st, F8 acc, int e0, float* my_part,
-                                              int* rpw, int f, bool store) {
-  const int lane = threadIdx.x & 31;
-  const F8 tot = f8_fold(acc);
-  if (st.row_start >= e0) {
-    wp_finish(p, st.r, st.row_end - st.row_start, tot, f, store);
-  } else if (lane < 16) {  // head part, published at the end of the piece
-    reinterpret_cast<float4*>(my_part)[0] = tot.lo;
-    reinterpret_cast<float4*>(my_part)[1] = tot.hi;
-  }
-  ++st.r;
-  if (st.r - st.rbase >= 32) {  // slide the window: entries [rbase, rbase + 32) are no longer needed
-    const int rows = (int)p.rows;
-    rpw[(st.rbase + 64 + lane) & 63] = st.rp_pre;
-    st.rbase += 32;
-    st.rp_pre = __ldg(p.rowptr + min(st.rbase + 64 + lane, rows));
-    __syncwarp();
-  }
-  st.row_start = st.row_end;
-  st.row_end = rpw[(st.r + 1) & 63];
-  return st;
-}
-
-template <int D, int MINB, bool DELTA>
-__global__ void __launch_bounds__(WS_WARPS * 32, MINB)
-spmm_pair_kernel(const __grid_constant__ SpmmParams p) {
-  pdl_prologue();
-  __shared__ int s_c[WS_WARPS][128];    // col of 4 index blocks of 32 edges
-  __shared__ float s_v[WS_WARPS][128];  // val
-  __shared__ int s_rp[WS_WARPS][64];    // rowptr window
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int half = lane >> 4;
-  const int w = blockIdx.x * WS_WARPS + wi;
-  const int f = blockIdx.y * WS_TILE_F + (lane & 15) * 8;
-  const bool fok = f < p.F;               // F is a multiple of 8
-  const bool store = fok && half == 0;    // lanes 0-15 write rows
-  const int rows = (int)p.rows;
-  int e0, e1;
-  float* my_part;  // this warp's two partial-row slots
-  {
-    const int4 h1 = __ldg(reinterpret_cast<const int4*>(p.plan) + 1);  // capacity, n_wslots, q, e_base
-    const int4 h2 = __ldg(reinterpret_cast<const int4*>(p.plan) + 2);  // e_end
-    if (w >= h1.y) return;
-    if (h1.w == h2.x) {  // a structure without edges: every row is empty
-      for (int r = w; r < rows; r += h1.y) wp_finish(p, r, 0, f8_zero(), f, store);
-      return;
-    }
-    e0 = h1.w + w * h1.z;
-    if (e0 >= h2.x) return;
-    e1 = min(e0 + h1.z, h2.x);
-    my_part = p.ws_part + (((int64_t)blockIdx.y * h1.y + w) * 2) * WS_TILE_F + (lane & 15) * 8;
-  }
-  int* sc = s_c[wi];
-  float* sv = s_v[wi];
-  int* rpw = s_rp[wi];
-  auto ld_blk = [&](int b, int& c, float& v) {
-    const int idx = e0 + b * 32 + lane;
-    c = 0;
-    v = 0.f;
-    if (idx < e1) {
-      c = ldg_stream(p.col + idx);
-      v = p.val ? ldg_stream(p.val + idx) : 1.f;
-    }
-  };
-  int r, rbase, rp_pre, cn;
-  float vn;
-  {
-    int c1, c2;
-    float v1, v2;
-    ld_blk(0, cn, vn);
-    ld_blk(1, c1, v1);
-    ld_blk(2, c2, v2);
-    const int capacity = __ldg(reinterpret_cast<const int*>(p.plan) + 4);
-    r = __ldg(reinterpret_cast<const int*>(p.items + capacity) + w);  // wrow[w]: the row that holds edge e0
-    rbase = r;
-    const int rp_a = __ldg(p.rowptr + min(rbase + lane, rows));
-    const int rp_b = __ldg(p.rowptr + min(rbase + 32 + lane, rows));
-    rp_pre = __ldg(p.rowptr + min(rbase + 64 + lane, rows));
-    sc[lane] = cn; sv[lane] = vn;
-    sc[32 + lane] = c1; sv[32 + lane] = v1;
-    sc[64 + lane] = c2; sv[64 + lane] = v2;
-    ld_blk(3, cn, vn);
-    rpw[(rbase + lane) & 63] = rp_a;
-    rpw[(rbase + 32 + lane) & 63] = rp_b;
-  }
-  __syncwarp();
-
-  const char* Xb = reinterpret_cast<const char*>(p.X + (fok ? f : 0));
-  const char* Mb = DELTA ? reinterpret_cast<const char*>(p.m_in + (fok ? f : 0)) : nullptr;
-  const unsigned x_bytes = (unsigned)p.ldx * 4u, m_bytes = DELTA ? (unsigned)p.ld_in * 4u : 0u;
-  F8 xa[D], xb[D];
-  F8 ma[DELTA ? D : 1], mb[DELTA ? D : 1];
-  auto gather = [&](int pos, F8& xo, F8& mo) {  // this half's edge of the pair at ring position `pos`
-    const unsigned c = (unsigned)sc[(pos + half) & 127];
-    xo = ldg256(Xb + (size_t)c * x_bytes);
-    if constexpr (DELTA) mo = ldg256(Mb + (size_t)c * m_bytes);
-  };
-#pragma unroll
-  for (int u = 0; u < D; ++u) {
-    xa[u] = f8_zero(); xb[u] = f8_zero();
-    if constexpr (DELTA) { ma[u] = f8_zero(); mb[u] = f8_zero(); }
-  }
-#pragma unroll
-  for (int u = 0; u < D; ++u)  // prologue: the first D pairs (edges past e1 read edge 0 of the ring: unused)
-    gather(e0 + 2 * u + half < e1 ? 2 * u : -half, xa[u], ma[DELTA ? u : 0]);
-  if (w == 0)  // empty rows in front of the first edge
-    for (int rr = 0; rr < r; ++rr) wp_finish(p, rr, 0, f8_zero(), f, store);
-  RowState st;
-  st.r = r; st.rbase = rbase; st.rp_pre = rp_pre;
-  st.row_start = rpw[r & 63]; st.row_end = rpw[(r + 1) & 63];
-  const bool head_cut = st.row_start < e0;  // the first row started in an earlier piece
-  F8 acc = f8_zero();
-  auto issue_group = [&](int jg, F8 (&xo)[D], F8 (&mo)[DELTA ? D : 1], auto last_tag) {
-    constexpr bool LAST = decltype(last_tag)::value;
-#pragma unroll
-    for (int u = 0; u < D; ++u)
-      if (!LAST || jg + 2 * u < e1) gather(jg + 2 * u - e0, xo[u], mo[DELTA ? u : 0]);
-  };
-  auto consume_group = [&](int jg, const F8 (&xi)[D], const F8 (&mi)[DELTA ? D : 1], auto last_tag) {
-    constexpr bool LAST = decltype(last_tag)::value;
-#pragma unroll
-    for (int u = 0; u < D; ++u) {
-      const int ja = jg + 2 * u;  // the pair (ja, ja + 1); this half owns edge ja + half
-      if (!LAST || ja < e1) {     // uniform
-        const float v = sv[(ja + half - e0) & 127];
-        const bool mine = !LAST || ja + half < e1;
-        if (ja + 1 < st.row_end || (LAST && ja + 1 >= e1 && ja < st.row_end)) {
-          // both edges belong to the current row: the common case, no bookkeeping
-          if (mine) {
-            if constexpr (DELTA) f8_fma_delta(acc, v, xi[u], mi[DELTA ? u : 0]);
-            else f8_fma(acc, v, xi[u]);
-          }
-        } else {
-          // a row ends at or before one of the two edges: the halves take their edges in turn
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            if (!LAST || ja + h < e1) {
-              while (ja + h >= st.row_end) {
-                st = wp_row_close(p, st, acc, e0, my_part, rpw, f, store);
-                acc = f8_zero();
-              }
-              if (half == h) {
-                if constexpr (DELTA) f8_fma_delta(acc, v, xi[u], mi[DELTA ? u : 0]);
-                else f8_fma(acc, v, xi[u]);
-              }
-            }
-          }
-        }
-      }
-    }
-  };
-  auto do_pair = [&](int j, auto last_tag) {
-    issue_group(j + 2 * D, xb, mb, last_tag);
-    consume_group(j, xa, ma, last_tag);
-    issue_group(j + 4 * D, xa, ma, last_tag);
-    consume_group(j + 2 * D, xb, mb, last_tag);
-  };
-  for (int j = e0; j < e1; j += 4 * D) {
-    const int off = j - e0;
-    if ((off & 31) == 0 && off != 0) {
-      const int b = (off >> 5) + 2;
-      sc[(b * 32 + lane) & 127] = cn;
-      sv[(b * 32 + lane) & 127] = vn;
-      ld_blk(b + 1, cn, vn);
-      __syncwarp();
-    }
-    if (j + 6 * D <= e1) do_pair(j, std::false_type{});
-    else do_pair(j, std::true_type{});
-  }
-  // the row of the last edge: complete if it lies inside the piece, else a tail (or middle) part
-  const bool tail_inside = st.row_end <= e1 && st.row_start >= e0;
-  const int t_row = st.r;
-  if (tail_inside) {
-    st = wp_row_close(p, st, acc, e0, my_part, rpw, f, store);
-    // empty rows that follow, up to the first row the next piece starts in
-    while (st.row_end <= e1 && st.r < rows) st = wp_row_close(p, st, f8_zero(), e0, my_part, rpw, f, store);
-  } else {
-    const F8 tot = f8_fold(acc);
-    if (half == 0) {
-      float4* pp = reinterpret_cast<float4*>(my_part + (st.row_start >= e0 ? WS_TILE_F : 0));
-      pp[0] = tot.lo;
-      pp[1] = tot.hi;
-    }
-    if (st.row_end <= e1) {  // (a head row that ends exactly at the end of the piece) empty rows that follow
-      st.r += 1;  // step over it without writing: it is published below
-      st.row_start = st.row_end;
-      st.row_end = __ldg(p.rowptr + min(st.r + 1, rows));
-      while (st.row_end <= e1 && st.r < rows) {
-        wp_finish(p, st.r, 0, f8_zero(), f, store);
-        st.r += 1;
-        st.row_end = __ldg(p.rowptr + min(st.r + 1, rows));
-      }
-    }
-  }
-  if (head_cut || !tail_inside) {
-    const int capacity = __ldg(reinterpret_cast<const int*>(p.plan) + 4);
-    const int r0 = __ldg(reinterpret_cast<const int*>(p.items + capacity) + w);
-    if (head_cut && (r0 != t_row || tail_inside)) wp_publish(p, w, blockIdx.y, r0, f, store);
-    if (!tail_inside) wp_publish(p, w, blockIdx.y, t_row, f, store);
-  }
-}
+// Measured alternatives of this kernel that are not shipped (profiles/r02_spmm_variants.md; the code is in
+// the history: two edges per warp instruction with 256-bit gathers per half-warp, commit 07d9d4e; source
+// rows landed in a shared-memory ring by cp.async.bulk, df70b15, or by cp.async, c7a49a7): all of them are
+// bound by the per-warp instruction stream, none beats the row kernel on plain products.
 
 // Plan construction: one thread per row appends the row's work items.
 __global__ void spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t rows, SpmmPlan* plan,
@@ -1550,9 +884,6 @@ static int stream_variant_for(bool delta) {
 }
 static int stream_min_f() { return incagg::tune_get(INCAGG_TUNE_SPMM_STREAM_MIN_F, 65); }
 static int stream_ctas_per_sm(int variant) {
-  if (variant == 21) return 2;   // cp.async kernel: one CTA of 16 warps (wslots = sm * 2 * 8)
-  if (variant >= 20) return 1;   // bulk-copy / cp.async kernels: one CTA of 8 warps with a 192 KB ring per SM
-  if (variant >= 10) return variant == 11 ? 3 : (variant == 12 ? 4 : (variant == 13 ? 1 : 2));
   return variant == 1 ? 4 : (variant == 2 ? 3 : (variant == 3 ? 5 : (variant == 4 ? 6 : (variant == 5 ? 1 : 2))));
 }
 static int stream_wslots() {
@@ -1660,56 +991,6 @@ static int try_stream(SpmmParams& p, int reduce, int vec, cudaStream_t st) {
   const int tiles = (p.F + WS_TILE_F - 1) / WS_TILE_F;
   dim3 grid((unsigned)((n_w + WS_WARPS - 1) / WS_WARPS), (unsigned)tiles);
   const bool delta = p.m_in != nullptr;
-  if (variant >= 20) {
-    // rows landed in shared memory by bulk copies: 16-byte aligned row slices, no delta form
-    if (delta || p.F % 4 != 0 || p.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(p.X) & 15) != 0) return 1;
-    static bool attr_set[16] = {false};
-    int dev = 0;
-    IA_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 16 && !attr_set[dev]) {
-      IA_CUDA(cudaFuncSetAttribute(spmm_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WB_SMEM_BYTES));
-      attr_set[dev] = true;
-    }
-    if (variant == 21) {        // 16 warps x 3 stages x 8 rows
-      static bool set21[16] = {false};
-      if (dev >= 0 && dev < 16 && !set21[dev]) {
-        IA_CUDA(cudaFuncSetAttribute(spmm_cpasync_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WB_SMEM_BYTES));
-        set21[dev] = true;
-      }
-      dim3 g21((unsigned)((n_w + 15) / 16), (unsigned)tiles);
-      launch(spmm_cpasync_kernel<16, 3>, g21, dim3(16 * 32), (size_t)WB_SMEM_BYTES, st, p);
-    } else if (variant == 22) { // 8 warps x 6 stages x 8 rows
-      static bool set22[16] = {false};
-      if (dev >= 0 && dev < 16 && !set22[dev]) {
-        IA_CUDA(cudaFuncSetAttribute(spmm_cpasync_kernel<8, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, WB_SMEM_BYTES));
-        set22[dev] = true;
-      }
-      launch(spmm_cpasync_kernel<8, 6>, grid, dim3(8 * 32), (size_t)WB_SMEM_BYTES, st, p);
-    } else {
-      launch(spmm_bulk_kernel, grid, dim3(WB_WARPS * 32), (size_t)WB_SMEM_BYTES, st, p);
-    }
-    IA_LAUNCH_CHECK();
-    return INCAGG_OK;
-  }
-  if (variant >= 10) {
-    // two edges per warp instruction: needs 8-float column groups and 32-byte aligned rows
-    const bool ok8 = p.F % 8 == 0 && p.ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(p.X) & 31) == 0 &&
-                     p.ldo % 4 == 0 &&
-                     (!delta || (p.ld_in % 8 == 0 && (reinterpret_cast<uintptr_t>(p.m_in) & 31) == 0));
-    if (!ok8) return 1;
-#define IA_PAIR(D_, MINB_)                                                                           \
-  do {                                                                                               \
-    if (delta) launch(spmm_pair_kernel<((D_) > 1 ? (D_) / 2 : 1), MINB_, true>, grid, dim3(WS_WARPS * 32), (size_t)(0), st, p); \
-    else launch(spmm_pair_kernel<D_, MINB_, false>, grid, dim3(WS_WARPS * 32), (size_t)(0), st, p);     \
-  } while (0)
-    if (variant == 11) IA_PAIR(2, 3);        // 2 pairs per buffer, 24 warps per SM
-    else if (variant == 12) IA_PAIR(2, 4);   // 32 warps per SM
-    else if (variant == 13) IA_PAIR(8, 1);   // 8 pairs per buffer, 8 warps per SM
-    else IA_PAIR(4, 2);                      // 10: 4 pairs per buffer, 16 warps per SM
-#undef IA_PAIR
-    IA_LAUNCH_CHECK();
-    return INCAGG_OK;
-  }
 #define IA_STREAM(D_, MINB_)                                                                         \
   do {                                                                                               \
     if (delta) launch(spmm_stream_kernel<((D_) > 1 ? (D_) / 2 : 1), MINB_, true>, grid, dim3(WS_WARPS * 32), (size_t)(0), st, p); \

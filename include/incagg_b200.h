@@ -58,7 +58,7 @@ int64_t incagg_launch_count(void);
 /* Experiment knobs of the kernels (not part of the reference-facing surface; the defaults are what the
  * product runs with).  Plans built before a knob that changes the warp partition was set must be
  * rebuilt. */
-#define INCAGG_TUNE_SPMM_STREAM_VARIANT 0 /* merge-path SpMM: -2 auto (delta form only, variant 2), -1 off, else gathers per buffer x warps/SM: 0 = 8 x 16, 1 = 4 x 32, 2 = 4 x 24, 3 = 2 x 40, 4 = 2 x 48, 5 = 16 x 8; two edges per warp instruction (pairs per buffer x warps/SM): 10 = 4 x 16, 11 = 2 x 24, 12 = 2 x 32, 13 = 8 x 8; 20 = rows landed in a shared-memory ring by cp.async.bulk (8 warps x 48 rows in flight per SM), 21 / 22 = by cp.async (16 warps x 24 rows / 8 warps x 48 rows) */
+#define INCAGG_TUNE_SPMM_STREAM_VARIANT 0 /* merge-path SpMM: -2 auto (delta form only, variant 2), -1 off, else gathers per buffer x warps/SM: 0 = 8 x 16, 1 = 4 x 32, 2 = 4 x 24, 3 = 2 x 40, 4 = 2 x 48, 5 = 16 x 8 */
 #define INCAGG_TUNE_SPMM_STREAM_MIN_F 1   /* smallest feature width routed to the merge-path kernel (65) */
 #define INCAGG_TUNE_COUNT 8
 int incagg_tune_set(int key, int value);

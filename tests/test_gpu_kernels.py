@@ -125,8 +125,8 @@ def _csr_from_deg(rng, deg, cols):
     return rowptr, col, val
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 10, 11, 12, 13, 20, 21, 22])
-@pytest.mark.parametrize("F", [68, 128, 200, 600])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("F", [68, 128, 200, 604])
 def test_spmm_merge_path_kernel_edge_cases(ops, cuda, variant, F):
     """The merge-path (edge stream) kernel that serves wide sum / mean products: rows cut by piece
     boundaries, one row that spans many pieces, empty rows at the front / between / at the end and at

@@ -17,8 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-VARIANTS = {"rows": -1, "s8x2": 0, "s4x4": 1, "s4x3": 2, "s2x5": 3, "s2x6": 4, "s16x1": 5,
-            "p4x2": 10, "p2x3": 11, "p2x4": 12, "p8x1": 13, "bulk": 20, "cpa16x3": 21, "cpa8x6": 22}
+VARIANTS = {"rows": -1, "s8x2": 0, "s4x4": 1, "s4x3": 2, "s2x5": 3, "s2x6": 4, "s16x1": 5}
 
 
 def main():
@@ -28,7 +27,7 @@ def main():
     ap.add_argument("--batches", type=int, default=12)
     ap.add_argument("--batch-parts", type=int, default=1)
     ap.add_argument("--cases", default="fwd,bwd,delta,full")
-    ap.add_argument("--variants", default="rows,s4x3,p4x2,p2x3,p2x4,p8x1")
+    ap.add_argument("--variants", default="rows,s8x2,s4x3")
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     import incagg_gnn_b200 as tga
