@@ -39,6 +39,15 @@ int set_err(int code, const char* fmt, ...);
 inline cudaStream_t as_stream(incagg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();  // cached SM count of the current device (148 on B200)
+// True exactly once per (flag array, current device): function attributes such as the dynamic
+// shared-memory limit are per device, so a "done" flag must be too.
+inline bool first_use_on_device(bool (&done)[16]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
 int tune_get(int key, int dflt);  // experiment knobs (incagg_tune_set); `dflt` when unset
 // Device-side error word of the current device (one int32, zero = no error): kernels OR a bit into it
 // when they meet an index outside its table (INCAGG_DEVERR_*), the host reads it with

@@ -686,10 +686,9 @@ template <int BN, bool TA, bool TBK>
 static int launch_gemm_t(const GemmParams& p, int splits, cudaStream_t st) {
   constexpr int STAGE_BYTES = 2 * G_BM * 128 + 2 * BN * 128;
   constexpr int SMEM = GemmCfg<BN>::STAGES * STAGE_BYTES + 1024;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[16] = {false};
+  if (first_use_on_device(attr_set)) {
     IA_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, TA, TBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
   }
   unsigned gx = (unsigned)((p.M + G_BM - 1) / G_BM), gy = (unsigned)((p.N + BN - 1) / BN);
   if (p.dual == DUAL_M) gx *= 2;
@@ -703,10 +702,9 @@ static int launch_gemm_t(const GemmParams& p, int splits, cudaStream_t st) {
 template <bool TA, bool TBK>
 static int launch_nc_t(const GemmParams& p, int splits, cudaStream_t st) {
   constexpr int SMEM = 2 * (2 * G_BM * 128 + 2 * 256 * 128) + 1024;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[16] = {false};
+  if (first_use_on_device(attr_set)) {
     IA_CUDA(cudaFuncSetAttribute(gemm_nc_kernel<TA, TBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
   }
   dim3 grid((unsigned)((p.M + G_BM - 1) / G_BM), 1, (unsigned)splits);
   launch(gemm_nc_kernel<TA, TBK>, dim3(grid), dim3(G_THREADS), (size_t)(SMEM), st, p);

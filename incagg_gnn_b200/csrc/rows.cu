@@ -414,11 +414,10 @@ extern "C" int incagg_copy_slices(const void* src, int64_t src_ld_bytes, int64_t
   if (use_bulk && src_ld_bytes == row_bytes && dst_ld_bytes == row_bytes && row_bytes % 16 == 0 &&
       (reinterpret_cast<uintptr_t>(src) % 16) == 0 && (reinterpret_cast<uintptr_t>(dst) % 16) == 0 &&
       packed * row_bytes >= 4 * BULK_CHUNK) {
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[16] = {false};
+    if (first_use_on_device(attr_set)) {
       IA_CUDA(cudaFuncSetAttribute(slice_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    BULK_STAGES * BULK_CHUNK));
-      attr_set = true;
     }
     int64_t pk = 0;
     for (int64_t i0 = 0; i0 < k; i0 += MAX_SLICES) {
