@@ -281,71 +281,12 @@ __device__ __forceinline__ void store_tile(const TileRegs<ROWS>& t, uint32_t hi,
   }
 }
 
-// ---- raw-tile staging (BN = 128 kernel) ----------------------------------------------------------
-// With the next k-block's tile held in registers, only one k-block (32 KB per CTA) is in flight while the
-// current one is split and multiplied, and 40 % of the warp time is spent waiting for those loads (ncu:
-// long_scoreboard).  The raw fp32 tiles of the next GEMM_STAGING k-blocks are therefore fetched with
-// cp.async into a thread-private staging area in shared memory (thread t copies exactly the float4s it
-// will split: slot (i * 256 + t) * 16, conflict-free and without any cross-thread dependency), and read
-// back into registers when their turn comes.  Ragged or unaligned tiles are loaded directly instead.
-constexpr int GEMM_STAGING = 3;
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-template <int ROWS>
-__device__ __forceinline__ bool tile_is_fast(int64_t row0, int64_t rows_total, int64_t k0, int64_t k_end, bool vec_ok) {
-  return vec_ok && (row0 + ROWS <= rows_total) && (k0 + G_BK <= k_end);
-}
-// same thread -> element mapping as load_tile's fast path
-template <int ROWS, bool TRANS>
-__device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t k0,
-                                           uint32_t slot) {
-  const int tid = threadIdx.x;
-  if constexpr (!TRANS) {
-    const float* base = src + (row0 + (tid >> 3)) * ld + k0 + (tid & 7) * 4;
-#pragma unroll
-    for (int i = 0; i < ROWS / 32; ++i) cp_async16(slot + (uint32_t)((i * G_THREADS + tid) * 16), base + (int64_t)(32 * i) * ld);
-  } else {
-    const int lane = tid & 31, warp = tid >> 5;
-    const int kl = (lane & 15), mh = lane >> 4;
-#pragma unroll
-    for (int i = 0; i < ROWS / 32; ++i) {
-      const int ub = warp + 8 * i;
-      cp_async16(slot + (uint32_t)((i * G_THREADS + tid) * 16),
-                 src + (k0 + (ub & 1) * 16 + kl) * ld + row0 + ((ub >> 1) * 2 + mh) * 4);
-    }
-  }
-}
-template <int ROWS>
-__device__ __forceinline__ void unstage_tile(uint32_t slot, TileRegs<ROWS>& t) {
-  const int tid = threadIdx.x;
-#pragma unroll
-  for (int i = 0; i < ROWS / 32; ++i) t.v[i] = lds128(slot + (uint32_t)((i * G_THREADS + tid) * 16));
-}
-
 // TA: A is stored [K, M] (contiguous along m).  TBK: B is stored [K, N] (contiguous along n), i.e.
 // transB == 0 of the C ABI; both make the loader transpose on the way into shared memory.
 // BN = 128: three stages, one CTA per SM.  BN = 64: two stages (96 KB), two CTAs per SM - the small
 // problems of this path (16 K rows) are latency-bound single waves, and a second resident CTA
 // overlaps one CTA's loads / splits with the other's MMAs and epilogue.
-// BN = 128 with raw-tile staging: two operand stages (128 KB) + GEMM_STAGING raw k-blocks (96 KB).
-#ifndef GEMM_STAGED_128
-#define GEMM_STAGED_128 1   // 0: the round-1 pipeline (next k-block in registers, three operand stages)
-#endif
-template <int BN> struct GemmCfg {
-  static constexpr bool STAGED = (BN == 128) && (GEMM_STAGED_128 != 0);
-  static constexpr int STAGES = (BN == 128 && !STAGED) ? 3 : 2;
-  static constexpr int MIN_CTAS = (BN == 64) ? 2 : 1;
-  static constexpr int RAW_BYTES = STAGED ? GEMM_STAGING * (G_BM * 128 + BN * 128) : 0;  // raw fp32 k-blocks
-};
+template <int BN> struct GemmCfg { static constexpr int STAGES = (BN == 64) ? 2 : 3; static constexpr int MIN_CTAS = (BN == 64) ? 2 : 1; };
 
 template <int BN, bool TA, bool TBK>
 __global__ void __launch_bounds__(G_THREADS, GemmCfg<BN>::MIN_CTAS)
@@ -407,75 +348,26 @@ gemm_tf32x3_kernel(const GemmParams p) {
       load_tile<BN, TBK>(Bptr, ldb, n0, p.N, kbg * G_BK, p.K, vecB, b);
     }
   };
-  // k-block -> (A source, B source) of its segment, for the staged path
-  struct KbSrc {
-    const float* a; int64_t lda; const float* b; int64_t ldb; int64_t k0, k_end;
-  };
-  auto kb_src = [&](int64_t kbg) {
-    KbSrc o;
-    if (p.dual == DUAL_K && kbg >= p.kb1) {
-      o.a = p.A2; o.lda = p.lda2; o.b = p.B2; o.ldb = p.ldb2; o.k0 = (kbg - p.kb1) * G_BK; o.k_end = p.K2;
-    } else {
-      o.a = Aptr; o.lda = lda; o.b = Bptr; o.ldb = ldb; o.k0 = kbg * G_BK; o.k_end = p.K;
-    }
-    return o;
-  };
+  // the global loads of k-block kb+1 are in flight while kb is split, stored and multiplied
   TileRegs<G_BM> ra;
   TileRegs<BN> rb;
   pdl_wait();
-  const uint32_t smem_base = smem_u32(smem);
-  constexpr int RAW_SLOT = G_BM * 128 + BN * 128;                       // one raw k-block: A tile + B tile
-  const uint32_t raw_base = smem_base + (uint32_t)(G_STAGES * STAGE_BYTES);
-  // raw k-block kbg -> staging slot (cp.async; only whole, aligned tiles: the others are loaded directly)
-  auto stage_kb = [&](int kb_rel) {
-    const KbSrc o = kb_src(kb_lo + kb_rel);
-    const uint32_t slot = raw_base + (uint32_t)((kb_rel % GEMM_STAGING) * RAW_SLOT);
-    if (tile_is_fast<G_BM>(m0, Mrows, o.k0, o.k_end, vecA)) stage_tile<G_BM, TA>(o.a, o.lda, m0, o.k0, slot);
-    if (tile_is_fast<BN>(n0, p.N, o.k0, o.k_end, vecB)) stage_tile<BN, TBK>(o.b, o.ldb, n0, o.k0, slot + G_BM * 128);
-  };
-  auto fetch_kb = [&](int kb_rel) {
-    const KbSrc o = kb_src(kb_lo + kb_rel);
-    const uint32_t slot = raw_base + (uint32_t)((kb_rel % GEMM_STAGING) * RAW_SLOT);
-    if (tile_is_fast<G_BM>(m0, Mrows, o.k0, o.k_end, vecA)) unstage_tile<G_BM>(slot, ra);
-    else load_tile<G_BM, TA>(o.a, o.lda, m0, Mrows, o.k0, o.k_end, vecA, ra);
-    if (tile_is_fast<BN>(n0, p.N, o.k0, o.k_end, vecB)) unstage_tile<BN>(slot + G_BM * 128, rb);
-    else load_tile<BN, TBK>(o.b, o.ldb, n0, p.N, o.k0, o.k_end, vecB, rb);
-  };
-  if constexpr (GemmCfg<BN>::STAGED) {
-#pragma unroll
-    for (int j = 0; j < GEMM_STAGING; ++j) {  // one commit group per k-block, also when nothing was staged
-      if (j < num_kb) stage_kb(j);
-      cp_async_commit();
-    }
-  } else {
-    // the global loads of k-block kb+1 are in flight (registers) while kb is split, stored and multiplied
-    if (num_kb > 0) load_kb(kb_lo, ra, rb);
-  }
+  if (num_kb > 0) load_kb(kb_lo, ra, rb);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_slot;
+  const uint32_t smem_base = smem_u32(smem);
 
 #pragma unroll 1
   for (int kb = 0; kb < num_kb; ++kb) {
     const int s = kb % G_STAGES;
     const uint32_t st = smem_base + (uint32_t)(s * STAGE_BYTES);
     if (kb >= G_STAGES) mbar_wait(&mma_done[s], (uint32_t)(((kb / G_STAGES) - 1) & 1));  // stage free?
-    if constexpr (GemmCfg<BN>::STAGED) {
-      cp_async_wait<GEMM_STAGING - 1>();   // this thread's copies of k-block kb have landed
-      fetch_kb(kb);
-    }
     store_tile<G_BM, TA>(ra, st, st + A_BYTES);
     store_tile<BN, TBK>(rb, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES,
                         (p.dual == DUAL_K && kb_lo + kb >= p.kb1) ? p.scaleB2 : scaleB);
-    if constexpr (GemmCfg<BN>::STAGED) {
-      // the staging slot of k-block kb has been consumed (its values went through the split above):
-      // refill it with k-block kb + GEMM_STAGING
-      if (kb + GEMM_STAGING < num_kb) stage_kb(kb + GEMM_STAGING);
-      cp_async_commit();
-    } else {
-      if (kb + 1 < num_kb) load_kb(kb_lo + kb + 1, ra, rb);
-    }
+    if (kb + 1 < num_kb) load_kb(kb_lo + kb + 1, ra, rb);
     fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     tc_fence_before();
     __syncthreads();
@@ -499,7 +391,6 @@ gemm_tf32x3_kernel(const GemmParams p) {
       __syncwarp();
     }
   }
-  if constexpr (GemmCfg<BN>::STAGED) cp_async_wait<0>();
 
   // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (its rows), columns half (w >> 2) ----
   constexpr int CW = BN / 2;             // columns per warp
@@ -794,7 +685,7 @@ gemm_splitk_reduce_kernel(const GemmParams p, int splits, int n_chunks) {
 template <int BN, bool TA, bool TBK>
 static int launch_gemm_t(const GemmParams& p, int splits, cudaStream_t st) {
   constexpr int STAGE_BYTES = 2 * G_BM * 128 + 2 * BN * 128;
-  constexpr int SMEM = GemmCfg<BN>::STAGES * STAGE_BYTES + GemmCfg<BN>::RAW_BYTES + 1024;
+  constexpr int SMEM = GemmCfg<BN>::STAGES * STAGE_BYTES + 1024;
   static bool attr_set[16] = {false};
   if (first_use_on_device(attr_set)) {
     IA_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, TA, TBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
