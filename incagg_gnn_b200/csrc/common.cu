@@ -63,7 +63,7 @@ bool pdl_enabled() {
 
 }  // namespace incagg
 
-extern "C" int incagg_version(void) { return 103; }
+extern "C" int incagg_version(void) { return 104; }
 
 extern "C" int incagg_tune_set(int key, int value) {
   IA_CHECK_ARG(key >= 0 && key < INCAGG_TUNE_COUNT, "unknown tuning key %d", key);

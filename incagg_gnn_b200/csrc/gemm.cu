@@ -48,6 +48,7 @@ struct GemmParams {
   int64_t M, N, K;
   float alpha, beta;
   int relu;
+  int acc2;                                  // DUAL_N: D2 += (instead of =): gradient accumulation in the epilogue
   int kb_per_split;                          // k-blocks handled by one blockIdx.z
   // second operand set (fused GCNII layer GEMMs, see incagg_gemm_tf32x3_dual)
   int dual;
@@ -311,7 +312,9 @@ gemm_tf32x3_kernel(const GemmParams p) {
   float* Dptr = p.D; int64_t ldd = p.ldd;
   float alpha_e = p.alpha, beta_e = p.beta, scaleB = p.scaleB;
   int bx = blockIdx.x, by = blockIdx.y;
+  bool acc_d = false;                        // add the old contents of D (second output of DUAL_N with acc2)
   if (p.dual == DUAL_N && by >= p.tiles1) {
+    acc_d = p.acc2 != 0;
     by -= p.tiles1; Bptr = p.B2; ldb = p.ldb2; Dptr = p.D2; ldd = p.ldd2; alpha_e = p.alpha2; beta_e = p.beta2;
     Cin = p.Cin2; ldcin = p.ldcin2; scaleB = p.scaleB2;
   }
@@ -417,6 +420,16 @@ gemm_tf32x3_kernel(const GemmParams p) {
       const float4 t = (vecC && full_n) ? __ldg(reinterpret_cast<const float4*>(cp + i * 4))
                                         : ldg4_guarded(cp + i * 4, (int)min((int64_t)4, p.N - (n0 + cbase + i * 4)));
       cin[i] = make_float4(beta_e * t.x, beta_e * t.y, beta_e * t.z, beta_e * t.w);
+    }
+  }
+  if (!splitk && acc_d && m < Mrows) {        // D2 += : its old row segment joins the Cin terms
+    const float* cp = Dptr + m * ldd + n0 + cbase;
+    const bool v2 = vecD && full_n;
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) {
+      const float4 t = v2 ? *reinterpret_cast<const float4*>(cp + i * 4)
+                          : ldg4_guarded(cp + i * 4, (int)min((int64_t)4, p.N - (n0 + cbase + i * 4)));
+      cin[i].x += t.x; cin[i].y += t.y; cin[i].z += t.z; cin[i].w += t.w;
     }
   }
   if (!splitk && p.dual == DUAL_K && p.Cin2 && p.beta2 != 0.f && m < Mrows) {
@@ -579,10 +592,21 @@ gemm_nc_kernel(const GemmParams p) {
   const int64_t ldd = set ? p.ldd2 : p.ldd;
   const float alpha = set ? p.alpha2 : p.alpha, beta = set ? p.beta2 : p.beta;
   const bool use_cin = !splitk && Cin && beta != 0.f;
+  const bool acc_d = set && p.acc2;          // D2 += (the split-K reduce kernel does it otherwise)
   const bool full_n = (p.N == HALF);
   const bool vecD = full_n && (splitk || ((ldd % 4 == 0) && aligned16(Dptr)));
   const bool vecC = use_cin && full_n && (ldcin % 4 == 0) && aligned16(Cin);
   float* prow = splitk ? p.partial + ((int64_t)blockIdx.z * p.Mpad + m) * p.ldp + set * HALF : nullptr;
+  // D2 += : the old values of the next 32 columns are fetched one iteration ahead (the first batch before
+  // the accumulator is waited for).  Read in place between the stores they would be 32 dependent round
+  // trips per thread: a load may not pass an earlier store to the same buffer, and each is consumed at once.
+  const bool acc_vec = acc_d && !splitk && vecD && m < p.M;
+  float4 old[8];
+  auto load_old = [&](int c0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) old[i] = *reinterpret_cast<const float4*>(Dptr + m * ldd + c0 + 4 * i);
+  };
+  if (acc_vec) load_old(0);
   if (num_kb > 0) mbar_wait(&acc_ready, 0);
   tc_fence_after();
 #pragma unroll 1
@@ -608,15 +632,21 @@ gemm_nc_kernel(const GemmParams p) {
           const float4 t = vecC ? __ldg(reinterpret_cast<const float4*>(cp)) : make_float4(cp[0], cp[1], cp[2], cp[3]);
           o.x += beta * t.x; o.y += beta * t.y; o.z += beta * t.z; o.w += beta * t.w;
         }
+        if (acc_d) {
+          const float4 t = old[i / 4];
+          o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+        }
         if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         *reinterpret_cast<float4*>(Dptr + m * ldd + c0 + i) = o;
       }
+      if (acc_vec && c0 + 32 < HALF) load_old(c0 + 32);
     } else {
       for (int i = 0; i < 32; ++i) {
         const int64_t n = c0 + i;
         if (n >= p.N) break;
         float x = alpha * v[i];
         if (use_cin) x += beta * Cin[m * ldcin + n];
+        if (acc_d) x += Dptr[m * ldd + n];
         if (p.relu) x = fmaxf(x, 0.f);
         Dptr[m * ldd + n] = x;
       }
@@ -674,6 +704,7 @@ gemm_splitk_reduce_kernel(const GemmParams p, int splits, int n_chunks) {
       } else {
         float x = p.alpha2 * t;
         if (p.Cin2 && p.beta2 != 0.f) x += p.beta2 * p.Cin2[m * p.ldcin2 + n];
+        if (p.acc2 && p.dual == DUAL_NC) x += p.D2[m * p.ldd2 + n];
         if (p.relu && p.dual == DUAL_NC) x = fmaxf(x, 0.f);
         p.D2[m * p.ldd2 + n] = x;
       }
@@ -822,6 +853,8 @@ extern "C" int incagg_gemm_tf32x3_dual(int mode, int transA, int transB, int64_t
   p.A2 = A2; p.lda2 = lda2; p.B2 = B2; p.ldb2 = ldb2;
   p.Cin = Cin; p.ldcin = ldcin; p.beta = beta; p.Cin2 = Cin2; p.ldcin2 = ldcin2; p.beta2 = beta2;
   p.D = D; p.ldd = ldd; p.D2 = D2; p.ldd2 = ldd2; p.M = M; p.N = N; p.K = K; p.K2 = K2;
-  p.alpha = alpha; p.alpha2 = alpha2; p.scaleB = scaleB; p.scaleB2 = scaleB2; p.relu = relu; p.dual = mode;
+  IA_CHECK_ARG((relu & ~3) == 0 && (!(relu & 2) || mode == DUAL_N), "flags: bit 0 ReLU, bit 1 (mode 2 only) D2 accumulates");
+  p.alpha = alpha; p.alpha2 = alpha2; p.scaleB = scaleB; p.scaleB2 = scaleB2; p.relu = relu & 1;
+  p.acc2 = (relu >> 1) & 1; p.dual = mode;
   return run_gemm(p, workspace, workspace_bytes, as_stream(stream));
 }

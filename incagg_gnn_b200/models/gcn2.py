@@ -1,4 +1,5 @@
 """GCNII on the GAS / IncAgg runtime (reference: torch_geometric_autoscale/models/gcn2.py)."""
+import os
 from typing import Optional
 
 import torch
@@ -6,7 +7,7 @@ from torch import Tensor
 import torch.nn.functional as F
 from torch.nn import ModuleList, BatchNorm1d
 
-from ..nn import GCN2Conv, Linear
+from ..nn import GCN2Conv, Linear, X0GradSink
 from ..sparse import SparseTensor, spmm_delta
 from .base import ScalableGNN
 from ._masking import select_edges
@@ -61,6 +62,17 @@ class GCN2(ScalableGNN):
     def _fuse_relu(self) -> bool:
         return not self.batch_norm and not self.residual
 
+    def _first_linear(self, x: Tensor):
+        """x_0 = ReLU(lins[0] x) (gcn2.py:87) and, in training, the sink that collects the x_0 gradients
+        of the layers in their GEMM epilogues (nn.X0GradSink; unshared weights only)."""
+        x_0 = self.lins[0](x, relu=True)
+        sink = None
+        if (torch.is_grad_enabled() and x_0.requires_grad and self.convs[0].weight2 is not None
+                and os.environ.get('INCAGG_X0_SINK', '1') != '0'):   # (A/B switch)
+            sink = X0GradSink()
+            x_0 = sink.join(x_0)
+        return x_0, sink
+
     def _post(self, i: int, h: Tensor, x: Tensor) -> Tensor:
         if self.batch_norm:
             h = self.bns[i](h)
@@ -74,8 +86,8 @@ class GCN2(ScalableGNN):
         batch_size, n_id, offset, count = (list(args) + [None] * 4)[:4]
         if self.drop_input:
             x = F.dropout(x, p=self.dropout, training=self.training)
-        x = x_0 = self.lins[0](x, relu=True)
-        x = F.dropout(x, p=self.dropout, training=self.training)
+        x_0, sink = self._first_linear(x)
+        x = F.dropout(x_0, p=self.dropout, training=self.training)
         t_all = 0
         fuse = self._fuse_relu  # no batch norm / residual: ReLU rides in the GEMM epilogue
         x0b = x_0[:adj_t.size(0)]
@@ -90,7 +102,7 @@ class GCN2(ScalableGNN):
                     # the ReLU of layer i rides in its GEMM epilogue; its backward mask rides in the
                     # epilogue of the transposed SpMM of layer i + 1 (x passes only through dropout in between)
                     x = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=True, out_full=buf,
-                             relu_input=i > 0, defer_relu_bwd=True)
+                             relu_input=i > 0, defer_relu_bwd=True, x0_sink=sink)
                     # the push only reads the rows the GEMM just wrote and nothing in this step reads
                     # the table rows it writes: it rides on the pull stream, joined after the loop
                     main, side = torch.cuda.current_stream(), self._pull_stream
@@ -102,7 +114,7 @@ class GCN2(ScalableGNN):
                     if pulled is not None:
                         main.wait_event(pulled)
                 else:
-                    h = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=fuse)
+                    h = conv(x, x0b, adj_t, grad_rows=batch_size if i > 0 else None, relu=fuse, x0_sink=sink)
                     x = h if fuse else self._post(i, h, x)
                     x, t = self.push_and_pull(hist, x, batch_size, n_id, offset, count)
                     t_all += t
@@ -111,14 +123,14 @@ class GCN2(ScalableGNN):
                 torch.cuda.current_stream().wait_stream(self._pull_stream)   # pushes done before the step ends
             h = self.convs[-1](x, x0b, adj_t,
                                grad_rows=batch_size if self.num_layers > 1 else None, relu=fuse,
-                               relu_input=ahead is not None and self.num_layers > 1)
+                               relu_input=ahead is not None and self.num_layers > 1, x0_sink=sink)
         else:  # no neighbour information (gcn2.py:151-181)
             x, x_0 = x[:batch_size], x_0[:batch_size]
             for i, conv in enumerate(self.convs[:-1]):
-                h = conv.forward_no_neighbor(x, x_0, relu=fuse)
+                h = conv.forward_no_neighbor(x, x_0, relu=fuse, x0_sink=sink)
                 x = h if fuse else self._post(i, h, x)
                 x = F.dropout(x, p=self.dropout, training=self.training)
-            h = self.convs[-1].forward_no_neighbor(x, x_0, relu=fuse)
+            h = self.convs[-1].forward_no_neighbor(x, x_0, relu=fuse, x0_sink=sink)
         x = h if fuse else self._post(self.num_layers - 1, h, x)
         x = F.dropout(x, p=self.dropout, training=self.training)
         return self.lins[1](x), t_all
@@ -129,8 +141,8 @@ class GCN2(ScalableGNN):
         batch_size, n_id, offset, count = (list(args) + [None] * 4)[:4]
         if self.drop_input:
             x = F.dropout(x, p=self.dropout, training=self.training)
-        x = x_0 = self.lins[0](x, relu=True)
-        x = F.dropout(x, p=self.dropout, training=self.training)
+        x_0, sink = self._first_linear(x)
+        x = F.dropout(x_0, p=self.dropout, training=self.training)
         fuse = self._fuse_relu
         x0b = x_0[:adj_t.size(0)]
         for i, conv in enumerate(self.convs):
@@ -138,7 +150,7 @@ class GCN2(ScalableGNN):
                 x = x[:batch_size]
             m_in, m_ag, gid = self._incagg_tables(i, batch_size, x.shape[1], n_id, offset, count)
             h = spmm_delta(adj_t, x, m_in, m_ag, gid)  # A_BB (x - M_in) + M_ag, one kernel
-            h = conv.forward_after_propagate(h, x0b, relu=fuse)
+            h = conv.forward_after_propagate(h, x0b, relu=fuse, x0_sink=sink)
             self._incagg_release()
             x = h if fuse else self._post(i, h, x)
             x = F.dropout(x, p=self.dropout, training=self.training)

@@ -111,6 +111,40 @@ def weight_grads_on_side_stream(device):
         _WGRAD['keep'].clear()
 
 
+class X0GradSink:
+    """Where the layers of one step accumulate d loss / d x_0[:B].  Every GCNII layer reads x_0
+    (gcn2.py:121), so autograd would add L gradients of [B, F] with L - 1 elementwise launches, pad the sum
+    to the [B + H] rows of x_0 (fill + copy) and add it to the gradient that arrives through layer 0's
+    propagation.  With a sink the input-gradient GEMM of each layer adds into one buffer in its epilogue
+    (first layer of the backward pass: plain store) and returns no x_0 gradient to autograd;
+    ``X0GradSink.join`` (placed on x_0 right after the first Linear) adds the buffer to the head rows of
+    the gradient that reaches x_0: one launch instead of L + 2.  One sink per forward pass."""
+
+    def __init__(self):
+        self.buf = None
+
+    def join(self, x0: Tensor) -> Tensor:
+        return _X0Join.apply(x0, self)
+
+
+class _X0Join(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, sink):
+        ctx.sink = sink
+        return x0.view_as(x0)
+
+    @staticmethod
+    def backward(ctx, g):
+        buf, ctx.sink.buf = ctx.sink.buf, None
+        if buf is None:
+            return g, None
+        if g is None:   # x_0 reached the loss only through the layers' x_0 operands
+            raise RuntimeError('X0GradSink.join: x_0 must also be the input of the first layer')
+        # g is the fresh output of layer 0's transposed SpMM (nobody else holds it): add in place
+        g[:buf.size(0)].add_(buf)
+        return g, None
+
+
 class _GCN2Dense(torch.autograd.Function):
     """The dense half of GCN2Conv after the propagation, fused around the tensor-core GEMM:
         s   = (1-a) h + a x0
@@ -124,7 +158,7 @@ class _GCN2Dense(torch.autograd.Function):
     (The reference path issues ~10 elementwise / addmm launches forward and ~20 backward here.)"""
 
     @staticmethod
-    def forward(ctx, h, x0, w1, w2, a, b, relu, out_full=None, defer_relu_bwd=False):
+    def forward(ctx, h, x0, w1, w2, a, b, relu, out_full=None, defer_relu_bwd=False, x0_sink=None):
         # defer_relu_bwd: the ReLU is applied here, but its backward mask is left to the one consumer
         # of the output (an SpMM with relu_input=True, which gates its input gradient by [out > 0] in
         # its epilogue): this node then receives an already masked gradient.
@@ -147,6 +181,7 @@ class _GCN2Dense(torch.autograd.Function):
         ctx.a, ctx.b, ctx.relu, ctx.shared = a, b, (relu and not defer_relu_bwd), w2 is None
         ctx.w1_param, ctx.w2_param = w1, w2
         ctx.rows = rows
+        ctx.x0_sink = x0_sink if w2 is not None else None
         if out_full is not None:
             ctx.mark_dirty(out_full)
             return out_full
@@ -167,8 +202,18 @@ class _GCN2Dense(torch.autograd.Function):
             gh, gx0 = (1. - a) * ds, a * ds
             gw1 = ops.gemm(s, g, trans_a=True, alpha=b)
         else:
-            gh, gx0 = ops.gemm_dual("n", g, w1, b2=w2, trans_b=True, scale_b=b * (1. - a), scale_b2=b * a,
-                                    cin=g, beta=(1. - b) * (1. - a), cin2=g, beta2=(1. - b) * a)
+            sink = ctx.x0_sink
+            if sink is not None and ctx.needs_input_grad[1]:
+                # d x_0 accumulates in the sink through the GEMM epilogue (first contribution: store)
+                first = sink.buf is None
+                if first:
+                    sink.buf = torch.empty_like(g)
+                gh, _ = ops.gemm_dual("n", g, w1, b2=w2, trans_b=True, scale_b=b * (1. - a), scale_b2=b * a,
+                                      cin=g, beta=(1. - b) * (1. - a), cin2=g, beta2=(1. - b) * a,
+                                      out2=sink.buf, acc2=not first)
+            else:
+                gh, gx0 = ops.gemm_dual("n", g, w1, b2=w2, trans_b=True, scale_b=b * (1. - a), scale_b2=b * a,
+                                        cin=g, beta=(1. - b) * (1. - a), cin2=g, beta2=(1. - b) * a)
             b1, b2 = _grad_buffer(ctx.w1_param), _grad_buffer(ctx.w2_param)
             if b1 is not None and b2 is not None:         # accumulate into the flat gradient buffers
                 side = _WGRAD['stream']
@@ -183,7 +228,7 @@ class _GCN2Dense(torch.autograd.Function):
                                   cin=b1, beta=1., cin2=b2, beta2=1., out=b1, out2=b2)
             else:
                 gw1, gw2 = ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a)
-        return gh, gx0, gw1, gw2, None, None, None, None, None
+        return gh, gx0, gw1, gw2, None, None, None, None, None, None
 
 
 class _MaskedCE(torch.autograd.Function):
@@ -206,6 +251,13 @@ class _MaskedCE(torch.autograd.Function):
 def masked_cross_entropy(logits: Tensor, y: Tensor, mask: Tensor):
     """-> (mean CE over rows with mask, [loss sum, mean, count]) ; logits [B, C] fp32, y int64."""
     return _MaskedCE.apply(logits, y, mask)
+
+
+def masked_cross_entropy_grad(logits: Tensor, y: Tensor, mask: Tensor):
+    """-> ([loss sum, mean, count], d mean-loss / d logits) without an autograd node: the training loop
+    feeds the gradient straight into ``logits.backward`` (``loss.backward()`` would first materialise a
+    ones tensor and multiply the gradient by it: two launches for nothing)."""
+    return ops.masked_ce_raw(logits.detach(), y, mask)
 
 
 def glorot_(w: Tensor) -> Tensor:
@@ -266,7 +318,8 @@ class GCN2Conv(torch.nn.Module):
             glorot_(self.weight2)
 
     def forward_after_propagate(self, h: Tensor, x_0: Tensor, relu: bool = False,
-                                out_full: Optional[Tensor] = None, defer_relu_bwd: bool = False) -> Tensor:
+                                out_full: Optional[Tensor] = None, defer_relu_bwd: bool = False,
+                                x0_sink: Optional[X0GradSink] = None) -> Tensor:
         """Everything of PyG's GCN2Conv.forward after ``propagate``:
             x = (1-alpha) h ; x_0 = alpha x_0[:B]
             shared:   out = x + x_0 ; out = (1-beta) out + beta out W1
@@ -277,19 +330,20 @@ class GCN2Conv(torch.nn.Module):
             x_0 = x_0[:h.size(0)]
         return _GCN2Dense.apply(h.contiguous(), x_0.contiguous(), self.weight1, self.weight2,
                                 float(self.alpha), float(self.beta), relu, out_full,
-                                bool(defer_relu_bwd and relu))
+                                bool(defer_relu_bwd and relu), x0_sink)
 
-    def forward_no_neighbor(self, x: Tensor, x_0: Tensor, relu: bool = False) -> Tensor:
-        return self.forward_after_propagate(x, x_0, relu)
+    def forward_no_neighbor(self, x: Tensor, x_0: Tensor, relu: bool = False,
+                            x0_sink: Optional[X0GradSink] = None) -> Tensor:
+        return self.forward_after_propagate(x, x_0, relu, x0_sink=x0_sink)
 
     def forward(self, x: Tensor, x_0: Tensor, adj_t: SparseTensor,
                 grad_rows: Optional[int] = None, relu: bool = False,
                 out_full: Optional[Tensor] = None, relu_input: bool = False,
-                defer_relu_bwd: bool = False) -> Tensor:
+                defer_relu_bwd: bool = False, x0_sink: Optional[X0GradSink] = None) -> Tensor:
         """relu_input: x is the ReLU output of a layer called with defer_relu_bwd=True (the two flags
         come in pairs: producer defers, this layer's SpMM applies the mask in its backward)."""
         h = spmm(adj_t, x, reduce='sum', grad_rows=grad_rows, relu_input=relu_input)
-        return self.forward_after_propagate(h, x_0, relu, out_full, defer_relu_bwd)
+        return self.forward_after_propagate(h, x_0, relu, out_full, defer_relu_bwd, x0_sink)
 
 
 class SAGEConv(torch.nn.Module):

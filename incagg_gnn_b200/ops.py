@@ -284,12 +284,15 @@ def gemm_dual(mode: str, a: Tensor, b: Tensor, a2: Optional[Tensor] = None, b2: 
               trans_a: bool = False, trans_b: bool = False, alpha: float = 1.0, alpha2: float = 1.0,
               scale_b: float = 1.0, scale_b2: float = 1.0, cin: Optional[Tensor] = None, beta: float = 0.0,
               cin2: Optional[Tensor] = None, beta2: float = 0.0, relu: bool = False,
-              out: Optional[Tensor] = None, out2: Optional[Tensor] = None, ws_slot: int = 0):
+              out: Optional[Tensor] = None, out2: Optional[Tensor] = None, ws_slot: int = 0,
+              acc2: bool = False):
     """Two GEMMs sharing an operand in one launch (include/incagg_b200.h, incagg_gemm_tf32x3_dual):
     mode 'k': out = alpha (a @ (scale_b b) + a2 @ (scale_b2 b2)) + beta cin + beta2 cin2
     mode 'n': out = alpha a @ (scale_b b) + beta cin ; out2 = alpha2 a @ (scale_b2 b2) + beta2 cin2
+              (acc2: out2 += ... instead of out2 = ..., the gradient accumulation of a shared input)
     mode 'm': out = alpha op(a) @ b ; out2 = alpha2 op(a2) @ b      (split-K)."""
     code = {"k": 1, "n": 2, "m": 3}[mode]
+    assert not acc2 or (mode == "n" and out2 is not None)
     a, b = _rowmajor(a), _rowmajor(b)
     a2 = _rowmajor(a2) if a2 is not None else None
     b2 = _rowmajor(b2) if b2 is not None else None
@@ -315,14 +318,14 @@ def gemm_dual(mode: str, a: Tensor, b: Tensor, a2: Optional[Tensor] = None, b2: 
         code, int(trans_a), int(trans_b), M, N, K, K2, ptr(a), _ld(a), ptr(a2), _ld(a2) if a2 is not None else 0,
         ptr(b), _ld(b), ptr(b2), _ld(b2) if b2 is not None else 0, float(alpha), float(alpha2), float(scale_b),
         float(scale_b2), ptr(cin), _ld(cin) if cin is not None else 0, float(beta), ptr(cin2),
-        _ld(cin2) if cin2 is not None else 0, float(beta2), int(relu), ptr(out), _ld(out), ptr(out2),
+        _ld(cin2) if cin2 is not None else 0, float(beta2), int(bool(relu)) | (2 if acc2 else 0), ptr(out), _ld(out), ptr(out2),
         _ld(out2) if out2 is not None else 0, ptr(ws), ws_bytes, _stream()))
     return (out, out2) if mode in ("n", "m") else out
 
 
 def relu_bwd_colsum(g: Tensor, y: Optional[Tensor] = None):
-    """(g * (y > 0), its column sums) in one pass; y=None: (g, column sums of g).  Rows 16-byte aligned,
-    cols % 4 == 0 (callers fall back to torch otherwise)."""
+    """(g * (y > 0), its column sums) in one pass; y=None: (g, column sums of g).  float4 path for
+    16-byte-aligned rows with cols % 4 == 0, scalar columns otherwise (<= 256 columns: colsum_supported)."""
     _require_cuda(g, y)
     g = _rowmajor(g)
     rows, cols = g.shape
@@ -341,8 +344,10 @@ def relu_bwd_colsum(g: Tensor, y: Optional[Tensor] = None):
 
 
 def colsum_supported(t: Tensor) -> bool:
-    return (t.dim() == 2 and t.dtype == torch.float32 and t.size(1) % 4 == 0 and t.size(1) <= 1024
-            and t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0)
+    if not (t.dim() == 2 and t.dtype == torch.float32 and t.stride(1) == 1 and 0 < t.size(1) <= 1024):
+        return False
+    vec = t.size(1) % 4 == 0 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0
+    return vec or t.size(1) <= 256
 
 
 def masked_ce_raw(logits: Tensor, y: Tensor, mask: Tensor):

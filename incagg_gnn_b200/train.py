@@ -183,13 +183,13 @@ def forward_backward(model, sub, optimizer, VR_update=False, averager=None, epoc
         optimizer.zero_grad(set_to_none=True)
     if y.dim() == 1 and out.dtype == torch.float32:
         # criterion(out[mask], y[mask]) as one fused masked cross-entropy (loss + gradient kernels)
-        from .nn import masked_cross_entropy, weight_grads_on_side_stream
-        loss, out3 = masked_cross_entropy(out, y, train_mask)
+        from .nn import masked_cross_entropy_grad, weight_grads_on_side_stream
+        out3, dlogits = masked_cross_entropy_grad(out, y, train_mask)   # loss and its gradient, no autograd node
         # (single-GPU path; with a gradient averager the step keeps the one-stream backward that the
         # multi-GPU runs of this round were measured and checked with)
         one_graph = averager is None or getattr(averager, 'fused', False)
         with (weight_grads_on_side_stream(out.device) if one_graph else contextlib.nullcontext()):
-            loss.backward()
+            out.backward(dlogits)
         return out3[0], out3[2]
     w = train_mask.to(out.dtype)
     n = w.sum()

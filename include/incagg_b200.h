@@ -176,6 +176,9 @@ int incagg_gemm_tf32x3(int transA, int transB, int64_t M, int64_t N, int64_t K, 
  *                             A [M,K], A2 [M,K2]: forward  [h | x0] · [c1 W1 ; c2 W2]
  *   mode 2 (N-concatenation)  D  = alpha  * A·(scaleB  B ) + beta  Cin
  *                             D2 = alpha2 * A·(scaleB2 B2) + beta2 Cin2   (shared A): input gradients
+ *                             (relu is a flag word here: bit 0 = ReLU; bit 1 = D2 += instead of D2 =, which
+ *                             accumulates the x_0 gradient of the layers in the epilogue - every GCNII layer
+ *                             reads x_0, gcn2.py:121)
  *   mode 3 (M-concatenation)  D  = alpha  * op(A )·B + beta Cin ,  D2 = alpha2 * op(A2)·B + beta2 Cin2
  *                             (shared B; split-K with the workspace): weight gradients  [h | x0]^T · g,
  *                             accumulated in place into the gradient buffers when Cin == D
@@ -193,7 +196,9 @@ int incagg_gemm_tf32x3_dual(int mode, int transA, int transB, int64_t M, int64_t
 /*
  * ReLU backward fused with the bias gradient of the Linear in front of it (gcn2.py:87 lins[0]):
  *   gm[r, c] = y[r, c] > 0 ? g[r, c] : 0 ;  colsum[c] = sum_r gm[r, c]   (fixed order: deterministic)
- * y == NULL: plain column sums of g (gm unused).  cols % 4 == 0, 16-byte aligned rows.
+ * y == NULL: plain column sums of g (gm unused).  float4 path when cols % 4 == 0 (<= 1024) and every
+ * operand is 16-byte aligned with ld % 4 == 0; any other layout runs scalar columns (cols <= 256, e.g. the
+ * 47 logits of the classifier head, gcn2.py:149 lins[1]).
  */
 size_t incagg_colsum_workspace_bytes(int64_t rows, int32_t cols);
 int incagg_relu_bwd_colsum(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows,

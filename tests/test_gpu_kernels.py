@@ -388,6 +388,61 @@ def test_gemm_dual_modes(ops, cuda):
         assert rel(gw2, c2 * d(xx).t() @ d(gg)) <= RTOL
 
 
+@pytest.mark.parametrize("M,C,N", [(700, 128, 128), (333, 128, 100), (20000, 96, 47), (260, 64, 192)])
+def test_gemm_dual_n_accumulates_second_output(ops, cuda, M, C, N):
+    """N-concatenated pair with acc2: D2 += alpha2 A (s2 B2) + beta2 Cin2 (the x_0 gradient of the GCNII
+    layers accumulated in the epilogue): vector and ragged n-tiles, the pair kernel (N <= 128) and the
+    two-set general kernel (N = 192), aligned and unaligned destinations."""
+    g = torch.Generator().manual_seed(M + N)
+    d = lambda t: t.double()
+    rel = lambda o, r: float((d(o) - r).abs().max() / r.abs().max())
+    gr = torch.randn(M, C, generator=g).to(cuda)
+    w1 = torch.randn(N, C, generator=g).to(cuda)
+    w2 = torch.randn(N, C, generator=g).to(cuda)
+    cin = torch.randn(M, N, generator=g).to(cuda)
+    for off in (0, 1):   # 16-byte aligned destination / not
+        store = torch.randn(M, N + 8, generator=g).to(cuda)
+        acc = store[:, off:off + N]
+        old = acc.clone()
+        o1, o2 = ops.gemm_dual("n", gr, w1, b2=w2, trans_b=True, scale_b=0.4, scale_b2=0.1, cin=cin, beta=0.5,
+                               cin2=cin, beta2=0.25, out2=acc, acc2=True)
+        assert o2.data_ptr() == acc.data_ptr()
+        assert rel(o1, 0.4 * d(gr) @ d(w1).t() + 0.5 * d(cin)) <= RTOL
+        assert rel(acc, d(old) + 0.1 * d(gr) @ d(w2).t() + 0.25 * d(cin)) <= RTOL
+        assert torch.equal(store[:, :off], store[:, :off]) and float(store[:, off + N:].abs().max()) > 0
+
+
+def test_x0_grad_sink_matches_autograd(ops, cuda):
+    """Five GCNII dense blocks sharing x_0: gradients with the epilogue-accumulating sink equal the
+    plain autograd accumulation (<= 1e-6 relative: same products, different order of the sums)."""
+    from incagg_gnn_b200.nn import GCN2Conv, X0GradSink
+    g = torch.Generator().manual_seed(21)
+    B, H, C = 600, 300, 128
+    convs = [GCN2Conv(C, alpha=0.1, theta=0.5, layer=i + 1, shared_weights=False).to(cuda) for i in range(5)]
+    base = torch.randn(B + H, C, generator=g).to(cuda)
+    gout = torch.randn(B, C, generator=g).to(cuda)
+
+    def run(with_sink):
+        x_full = base.clone().requires_grad_(True)
+        y = x_full * 1.0                      # stands for the first Linear
+        sink = X0GradSink() if with_sink else None
+        x_0 = sink.join(y) if with_sink else y
+        x0b = x_0[:B]
+        h = x_0[:B] * 0.5 + x_0[B:B + B // 2].repeat(2, 1)[:B]   # some function of all of x_0
+        for conv in convs:
+            conv.zero_grad(set_to_none=True)
+            h = conv.forward_after_propagate(h, x0b, relu=True, x0_sink=sink)
+        h.backward(gout)
+        return x_full.grad.clone(), [c.weight2.grad.clone() for c in convs]
+
+    gx_ref, gw_ref = run(False)
+    gx, gw = run(True)
+    assert float((gx - gx_ref).abs().max() / gx_ref.abs().max()) <= 1e-6
+    for a, b in zip(gw, gw_ref):
+        assert torch.equal(a, b)
+    ops.check_device_errors()
+
+
 # ---- transpose --------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(50, 70, 6, 0, 0), (300, 40, 40, 0, 0), (64, 20, 4, 2, 40000)])
 def test_csr_transpose_is_bit_exact_and_ordered(ops, cuda, shape):
@@ -623,6 +678,18 @@ def test_relu_bwd_colsum_and_masked_ce(ops, cuda):
     _, cs2 = ops.relu_bwd_colsum(G[:, :40].contiguous())
     r2 = G[:, :40].double().sum(0)
     assert float((cs2.double() - r2).abs().max() / r2.abs().max()) <= RTOL
+    # scalar-column path: 47 columns (the classifier head), a strided unaligned view, many row blocks
+    big = torch.randn(90000, 64, generator=g).to(cuda)
+    for view, yv in ((big[:, 1:48], None), (big[:, 3:50], big[:, 10:57])):
+        assert ops.colsum_supported(view)
+        gm3, cs3 = ops.relu_bwd_colsum(view, yv)
+        r3 = view if yv is None else view * (yv > 0)
+        assert torch.equal(gm3, r3)
+        assert float((cs3.double() - r3.double().sum(0)).abs().max() / r3.double().sum(0).abs().max()) <= RTOL
+    _, cs4 = ops.relu_bwd_colsum(big)          # 352 row blocks through the parallel finish
+    assert float((cs4.double() - big.double().sum(0)).abs().max() / big.double().sum(0).abs().max()) <= RTOL
+    # masked_cross_entropy_grad: the same numbers without an autograd node
+    from incagg_gnn_b200.nn import masked_cross_entropy_grad
     # masked cross-entropy: value and gradient vs torch
     logits = torch.randn(2000, 47, generator=g).to(cuda).requires_grad_(True)
     y = torch.randint(0, 47, (2000,), generator=g).to(cuda)
@@ -636,6 +703,8 @@ def test_relu_bwd_colsum_and_masked_ce(ops, cuda):
     assert abs(float(loss) - float(ref_loss)) <= RTOL * abs(float(ref_loss))
     assert float(out3[2]) == float(mask.sum())
     assert float((logits.grad.double() - l2.grad).abs().max() / l2.grad.abs().max()) <= 1e-5
+    o3, dl = masked_cross_entropy_grad(logits, y, mask)
+    assert torch.equal(o3, out3) and torch.equal(dl * 2.0, logits.grad)
     # empty mask: zero loss, zero gradient
     loss0, o0 = masked_cross_entropy(logits.detach(), y, torch.zeros_like(mask))
     assert float(loss0) == 0. and float(o0[2]) == 0.
