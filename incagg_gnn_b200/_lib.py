@@ -75,6 +75,9 @@ _PROTOS = {
     "incagg_relu_bwd_colsum": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, P, c_int64, P, P, c_size_t, P]),
     "incagg_masked_ce_workspace_bytes": (c_size_t, [c_int64]),
     "incagg_masked_ce": (c_int, [P, c_int64, P, P, c_int64, c_int32, P, c_int64, P, P, c_size_t, P]),
+    "incagg_mask_count": (c_int, [P, c_int64, P, P]),
+    "incagg_masked_ce_rows": (c_int, [P, c_int64, P, P, c_int64, c_int32, P, P, c_int64, P, c_size_t, P]),
+    "incagg_masked_ce_finish": (c_int, [P, c_int64, P, P, P, P]),
     "incagg_adam_step": (c_int, [P, P, P, P, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float,
                                  c_float, P, P, P]),
     "incagg_csr_transpose_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),

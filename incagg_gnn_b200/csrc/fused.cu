@@ -153,7 +153,8 @@ masked_ce_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __
 }
 
 __global__ void ce_finish_kernel(const float* __restrict__ partial, int nblocks, const float* __restrict__ count,
-                                 float* __restrict__ out /* [2]: loss sum, mean loss */) {
+                                 float* __restrict__ out /* [3]: loss sum, mean loss, count */,
+                                 double* __restrict__ running /* nullable [2]: += loss sum, += count */) {
   pdl_prologue();
   // one block, fixed order
   __shared__ double s[256];
@@ -164,8 +165,11 @@ __global__ void ce_finish_kernel(const float* __restrict__ partial, int nblocks,
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int k = 0; k < blockDim.x; ++k) t += s[k];
+    const float n = *count;
     out[0] = (float)t;
-    out[1] = (float)(t / (double)fmaxf(*count, 1.f));
+    out[1] = (float)(t / (double)fmaxf(n, 1.f));
+    out[2] = n;
+    if (running) { running[0] += (double)(float)t; running[1] += (double)n; }
   }
 }
 
@@ -239,7 +243,42 @@ extern "C" int incagg_masked_ce(const float* logits, int64_t ld, const int64_t* 
   float* partial = static_cast<float*>(workspace);
   launch(masked_ce_kernel, dim3(nblocks), dim3(CE_THREADS), (size_t)(0), st, logits, ld, y, mask, rows, C, count, dlogits, ldd, partial);
   IA_LAUNCH_CHECK();
-  launch(ce_finish_kernel, dim3(1), dim3(256), (size_t)(0), st, partial, nblocks, count, out3);
+  launch(ce_finish_kernel, dim3(1), dim3(256), (size_t)(0), st, partial, nblocks, count, out3, (double*)nullptr);
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}
+
+// The same three kernels as separate calls, so that a training step can keep only the middle one on its
+// critical path: the count depends on the mask alone (side stream, while the forward pass runs) and the
+// loss value is not needed by the backward pass (side stream, while it runs).
+extern "C" int incagg_mask_count(const uint8_t* mask, int64_t rows, float* count, incagg_stream_t stream) {
+  IA_CHECK_ARG(rows >= 0 && count != nullptr && (rows == 0 || mask != nullptr), "bad argument");
+  launch(mask_count_kernel, dim3(1), dim3(1024), (size_t)(0), as_stream(stream), mask, rows, count);
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}
+
+extern "C" int incagg_masked_ce_rows(const float* logits, int64_t ld, const int64_t* y, const uint8_t* mask,
+                                     int64_t rows, int32_t C, const float* count, float* dlogits, int64_t ldd,
+                                     void* workspace, size_t workspace_bytes, incagg_stream_t stream) {
+  IA_CHECK_ARG(rows >= 0 && C > 0 && count != nullptr, "bad argument");
+  IA_CHECK_ARG(workspace != nullptr && workspace_bytes >= incagg_masked_ce_workspace_bytes(rows),
+               "workspace too small");
+  if (rows == 0) return INCAGG_OK;
+  IA_CHECK_ARG(logits && y && mask && dlogits, "NULL argument");
+  const int nblocks = (int)((rows + CE_THREADS / 32 - 1) / (CE_THREADS / 32));
+  launch(masked_ce_kernel, dim3(nblocks), dim3(CE_THREADS), (size_t)(0), as_stream(stream), logits, ld, y, mask, rows,
+         C, count, dlogits, ldd, static_cast<float*>(workspace));
+  IA_LAUNCH_CHECK();
+  return INCAGG_OK;
+}
+
+extern "C" int incagg_masked_ce_finish(const void* workspace, int64_t rows, const float* count, float* out3,
+                                       double* acc, incagg_stream_t stream) {
+  IA_CHECK_ARG(rows >= 0 && count != nullptr && out3 != nullptr && (rows == 0 || workspace != nullptr), "bad argument");
+  const int nblocks = (int)((rows + CE_THREADS / 32 - 1) / (CE_THREADS / 32));
+  launch(ce_finish_kernel, dim3(1), dim3(256), (size_t)(0), as_stream(stream), static_cast<const float*>(workspace),
+         nblocks, count, out3, acc);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
 }

@@ -41,7 +41,7 @@ class _LinearTC(torch.autograd.Function):
         ctx.relu = relu
         ctx.save_for_backward(x, weight, y if relu else None)
         ctx.has_bias = bias is not None
-        ctx.weight_param = weight
+        ctx.weight_param, ctx.bias_param = weight, bias
         return y
 
     @staticmethod
@@ -50,6 +50,23 @@ class _LinearTC(torch.autograd.Function):
         g = g.contiguous()
         gx = gw = gb = None
         want_gb = ctx.has_bias and ctx.needs_input_grad[2]
+        side = _WGRAD['stream']
+        wbuf = _grad_buffer(ctx.weight_param) if ctx.needs_input_grad[1] else None
+        bbuf = _grad_buffer(ctx.bias_param) if want_gb else None
+        if (side is not None and not ctx.relu and ctx.needs_input_grad[0] and wbuf is not None
+                and (not want_gb or (bbuf is not None and ops.colsum_supported(g)))):
+            # Only the input gradient continues the backward chain: the weight and bias gradients (three
+            # launches + the accumulation into the flat gradient buffer) run beside it on the side stream.
+            side.wait_stream(torch.cuda.current_stream(g.device))
+            gx = ops.gemm(g, weight)
+            with torch.cuda.stream(side):
+                ops.gemm(g, x, trans_a=True, cin=wbuf, beta=1., out=wbuf, ws_slot=1)
+                if want_gb:
+                    _, cs = ops.relu_bwd_colsum(g, None)
+                    bbuf.add_(cs)
+                    _WGRAD['keep'].append(cs)
+            _WGRAD['keep'].append((g, x))
+            return gx, None, None, None
         if want_gb and ops.colsum_supported(g) and (not ctx.relu or ops.colsum_supported(y)):
             # ReLU backward and the bias gradient in one pass over g
             g, gb = ops.relu_bwd_colsum(g, y if ctx.relu else None)
@@ -143,6 +160,12 @@ class _X0Join(torch.autograd.Function):
         # g is the fresh output of layer 0's transposed SpMM (nobody else holds it): add in place
         g[:buf.size(0)].add_(buf)
         return g, None
+
+
+def side_stream_of_weight_grads():
+    """The side stream of the enclosing ``weight_grads_on_side_stream`` block (None outside one): work
+    that nothing in the rest of the backward pass reads may ride on it; the block joins it on exit."""
+    return _WGRAD['stream']
 
 
 class _GCN2Dense(torch.autograd.Function):

@@ -254,9 +254,10 @@ def _rowmajor(t: Tensor) -> Tensor:
 
 def gemm(a: Tensor, b: Tensor, trans_a: bool = False, trans_b: bool = False, alpha: float = 1.0,
          cin: Optional[Tensor] = None, beta: float = 0.0, bias: Optional[Tensor] = None,
-         relu: bool = False, out: Optional[Tensor] = None) -> Tensor:
+         relu: bool = False, out: Optional[Tensor] = None, ws_slot: int = 0) -> Tensor:
     """out[M,N] = alpha * op(a) @ op(b) + beta * cin + bias (+ReLU) with the tcgen05 3xTF32 kernel.
-    trans_a: `a` is stored [K, M]; trans_b: `b` is stored [N, K] (a Linear weight)."""
+    trans_a: `a` is stored [K, M]; trans_b: `b` is stored [N, K] (a Linear weight).  ws_slot: which
+    split-K scratch buffer to use (GEMMs issued on a side stream must not share the main stream's)."""
     _require_cuda(a, b, cin, bias, out)
     a, b = _rowmajor(a), _rowmajor(b)
     M, K = (a.size(1), a.size(0)) if trans_a else (a.size(0), a.size(1))
@@ -271,7 +272,7 @@ def gemm(a: Tensor, b: Tensor, trans_a: bool = False, trans_b: bool = False, alp
     ws = None
     if K >= 512 and M * N <= (1 << 20):  # long reduction, few output tiles: split-K partials
         ws_bytes = min(lib.incagg_gemm_workspace_bytes(M, N, K), 1 << 28)
-        ws = _gemm_workspace(a.device, ws_bytes)
+        ws = _gemm_workspace(a.device, ws_bytes, ws_slot)
         ws_bytes = ws.numel()
     LAUNCHES["calls"] += 1
     check(lib.incagg_gemm_tf32x3(int(trans_a), int(trans_b), M, N, K, ptr(a), _ld(a), ptr(b), _ld(b),
@@ -366,6 +367,47 @@ def masked_ce_raw(logits: Tensor, y: Tensor, mask: Tensor):
     check(lib.incagg_masked_ce(ptr(logits), _ld(logits), ptr(y), ptr(m8), rows, C, ptr(dl), _ld(dl), ptr(out3),
                                ptr(ws), nb, _stream()))
     return out3, dl
+
+
+def _mask_bytes(mask: Tensor) -> Tensor:
+    m8 = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+    return m8.contiguous()
+
+
+def mask_count(mask: Tensor) -> Tensor:
+    """Number of selected rows as a device float[1] (first third of masked_ce_raw)."""
+    _require_cuda(mask)
+    m8 = _mask_bytes(mask)
+    count = torch.empty(1, dtype=torch.float32, device=mask.device)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_mask_count(ptr(m8), m8.numel(), ptr(count), _stream()))
+    return count
+
+
+def masked_ce_rows(logits: Tensor, y: Tensor, mask: Tensor, count: Tensor):
+    """-> (dlogits, workspace holding the per-block loss partials) given the row count (mask_count)."""
+    _require_cuda(logits, y, mask, count)
+    logits = _rowmajor(logits)
+    assert y.dtype == torch.int64 and y.is_contiguous() and count.dtype == torch.float32
+    m8 = _mask_bytes(mask)
+    rows, C = logits.shape
+    dl = torch.empty_like(logits)
+    nb = lib.incagg_masked_ce_workspace_bytes(rows)
+    ws = torch.empty(nb, dtype=torch.uint8, device=logits.device)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_masked_ce_rows(ptr(logits), _ld(logits), ptr(y), ptr(m8), rows, C, ptr(count), ptr(dl), _ld(dl),
+                                    ptr(ws), nb, _stream()))
+    return dl, ws
+
+
+def masked_ce_finish(ws: Tensor, rows: int, count: Tensor, acc: Optional[Tensor] = None) -> Tensor:
+    """-> out3 = [loss sum, mean loss, count]; acc (float64[2], optional): acc += [loss sum, count]."""
+    _require_cuda(ws, count, acc)
+    assert acc is None or (acc.dtype == torch.float64 and acc.numel() >= 2 and acc.is_contiguous())
+    out3 = torch.empty(3, dtype=torch.float32, device=ws.device)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_masked_ce_finish(ptr(ws), int(rows), ptr(count), ptr(out3), ptr(acc), _stream()))
+    return out3
 
 
 def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, n_first: int, lr: float, beta1: float, beta2: float,

@@ -162,15 +162,24 @@ def _backward_prep(adj_t, batch_size, VR_update):
     return side
 
 
-def forward_backward(model, sub, optimizer, VR_update=False, averager=None, epoch=0, batch_idx=0):
+def forward_backward(model, sub, optimizer, VR_update=False, averager=None, epoch=0, batch_idx=0,
+                     loss_acc=None):
     """Forward + loss + backward of one mini_train iteration on an already collated batch.  Returns
-    (loss * n_train, n_train) as device scalars (no host synchronisation)."""
+    (loss * n_train, n_train) as device scalars (no host synchronisation); ``loss_acc`` (float64[2] on the
+    device, optional) additionally receives ``+= [loss * n_train, n_train]`` (main.py:82) from the loss
+    kernel itself."""
     batch, batch_size, n_id, offset, count = sub
     x, adj_t = batch.x, batch.adj_t
     y, train_mask = batch.y[:batch_size], batch.train_mask[:batch_size]
     # The transposed CSR and the plans that only the backward pass needs are built on a side stream
     # while the forward pass runs (a fork / join that CUDA-graph capture records as parallel branches).
     side = _backward_prep(adj_t, batch_size, VR_update)
+    fused_ce = y.dim() == 1 and x.is_cuda
+    n_train = None
+    if fused_ce and side is not None:
+        from . import ops
+        with torch.cuda.stream(side):   # the row count of the loss depends on the batch alone
+            n_train = ops.mask_count(train_mask)
     if VR_update:
         out = model.VR_call(x, adj_t, batch_size, n_id, offset, count, epoch=epoch, batch_idx=batch_idx)['out']
     else:
@@ -181,14 +190,28 @@ def forward_backward(model, sub, optimizer, VR_update=False, averager=None, epoc
         averager.zero()  # gradients are views into the averager's flat buffer
     else:
         optimizer.zero_grad(set_to_none=True)
-    if y.dim() == 1 and out.dtype == torch.float32:
-        # criterion(out[mask], y[mask]) as one fused masked cross-entropy (loss + gradient kernels)
-        from .nn import masked_cross_entropy_grad, weight_grads_on_side_stream
-        out3, dlogits = masked_cross_entropy_grad(out, y, train_mask)   # loss and its gradient, no autograd node
+    if fused_ce and out.dtype == torch.float32:
+        # criterion(out[mask], y[mask]) as one fused masked cross-entropy whose gradient feeds
+        # out.backward directly (no autograd node: loss.backward() would materialise a ones tensor and
+        # multiply the gradient by it).  Only the gradient kernel sits on the step's critical path: the
+        # row count was computed beside the forward pass, the loss value (and the running epoch loss)
+        # is finished beside the backward pass.
+        from . import ops
+        from .nn import weight_grads_on_side_stream, side_stream_of_weight_grads
+        if n_train is None:
+            n_train = ops.mask_count(train_mask)
+        dlogits, ce_ws = ops.masked_ce_rows(out.detach(), y, train_mask, n_train)
         # (single-GPU path; with a gradient averager the step keeps the one-stream backward that the
         # multi-GPU runs of this round were measured and checked with)
         one_graph = averager is None or getattr(averager, 'fused', False)
         with (weight_grads_on_side_stream(out.device) if one_graph else contextlib.nullcontext()):
+            wside = side_stream_of_weight_grads()
+            if wside is not None:
+                wside.wait_stream(torch.cuda.current_stream(out.device))
+                with torch.cuda.stream(wside):
+                    out3 = ops.masked_ce_finish(ce_ws, out.size(0), n_train, loss_acc)
+            else:
+                out3 = ops.masked_ce_finish(ce_ws, out.size(0), n_train, loss_acc)
             out.backward(dlogits)
         return out3[0], out3[2]
     w = train_mask.to(out.dtype)
@@ -197,6 +220,8 @@ def forward_backward(model, sub, optimizer, VR_update=False, averager=None, epoc
         out, y.to(out.dtype), reduction='none').mean(dim=-1)
     loss = (per_row * w).sum() / n.clamp(min=1.)
     loss.backward()
+    if loss_acc is not None:
+        loss_acc += torch.stack([(loss.detach() * n).double(), n.double()])
     return loss.detach() * n, n
 
 
@@ -274,8 +299,7 @@ class GraphedTrainer:
 
     def _body_a(self, ids):
         sub = self.loader._collate(list(ids))
-        ln, n = forward_backward(self.model, sub, self.optimizer, self.vr, self.averager)
-        self.acc += torch.stack([ln.double(), n.double()])
+        forward_backward(self.model, sub, self.optimizer, self.vr, self.averager, loss_acc=self.acc)
 
     def _body_b(self):
         apply_update(self.model, self.optimizer, self.grad_norm, self.averager)
@@ -287,8 +311,7 @@ class GraphedTrainer:
         return self.averager is not None and not getattr(self.averager, 'fused', False)
 
     def _step_on(self, sub):
-        ln, n = forward_backward(self.model, sub, self.optimizer, self.vr, self.averager)
-        self.acc += torch.stack([ln.double(), n.double()])
+        forward_backward(self.model, sub, self.optimizer, self.vr, self.averager, loss_acc=self.acc)
         if not self._two_graphs:
             apply_update(self.model, self.optimizer, self.grad_norm, self.averager)
 
@@ -378,9 +401,12 @@ class GraphedTrainer:
             gi = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gi):
                 sub = self.loader._collate(list(ids))
+                # the forward SpMM plan depends on the batch structure alone: built here, one step ahead,
+                # instead of between the first Linear and the first SpMM of the step
+                plan = sub.data.adj_t.plan() if sub.data.adj_t.col.is_cuda and sub.data.adj_t.nnz() else None
                 if self.host_prefetch:
                     self.model.prefetch_pulls(sub.batch_size, sub.n_id)
-            self.in_graphs[key] = (gi, sub)   # the outputs stay allocated: the step graph reads them
+            self.in_graphs[key] = (gi, sub, plan)   # the outputs stay allocated: the step graph reads them
             g, gb = torch.cuda.CUDAGraph(), None
             with torch.cuda.graph(g, pool=self.pool):
                 self._step_on(sub)

@@ -213,6 +213,21 @@ size_t incagg_masked_ce_workspace_bytes(int64_t rows);
 int incagg_masked_ce(const float* logits, int64_t ld, const int64_t* y, const uint8_t* mask, int64_t rows,
                      int32_t C, float* dlogits, int64_t ldd, float* out3, void* workspace,
                      size_t workspace_bytes, incagg_stream_t stream);
+/*
+ * The same computation as three calls, for a training step that keeps only the gradient on its critical
+ * path (main.py:80-82: the loss VALUE is bookkeeping, `total_loss += loss * n`):
+ *   incagg_mask_count        count[0] = n = number of non-zero mask bytes (depends on the batch alone)
+ *   incagg_masked_ce_rows    dlogits as above from a count computed earlier + per-block loss partials in
+ *                            the workspace (incagg_masked_ce_workspace_bytes)
+ *   incagg_masked_ce_finish  out3 = {loss sum, mean, n} from the partials; acc (nullable, double[2]):
+ *                            acc[0] += loss sum, acc[1] += n  (the running epoch loss, main.py:82)
+ */
+int incagg_mask_count(const uint8_t* mask, int64_t rows, float* count, incagg_stream_t stream);
+int incagg_masked_ce_rows(const float* logits, int64_t ld, const int64_t* y, const uint8_t* mask, int64_t rows,
+                          int32_t C, const float* count, float* dlogits, int64_t ldd, void* workspace,
+                          size_t workspace_bytes, incagg_stream_t stream);
+int incagg_masked_ce_finish(const void* workspace, int64_t rows, const float* count, float* out3, double* acc,
+                            incagg_stream_t stream);
 
 /*
  * One Adam step (torch.optim.Adam arithmetic, main.py:196-201) over flat fp32 buffers of n elements:

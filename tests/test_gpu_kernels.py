@@ -705,6 +705,13 @@ def test_relu_bwd_colsum_and_masked_ce(ops, cuda):
     assert float((logits.grad.double() - l2.grad).abs().max() / l2.grad.abs().max()) <= 1e-5
     o3, dl = masked_cross_entropy_grad(logits, y, mask)
     assert torch.equal(o3, out3) and torch.equal(dl * 2.0, logits.grad)
+    # the same computation as three calls (count | gradient + partials | loss value + running sums)
+    cnt = ops.mask_count(mask)
+    dl2, ws = ops.masked_ce_rows(logits.detach(), y, mask, cnt)
+    acc = torch.tensor([1.5, 2.0], dtype=torch.float64, device=cuda)
+    o3b = ops.masked_ce_finish(ws, logits.size(0), cnt, acc)
+    assert torch.equal(dl2, dl) and torch.equal(o3b, o3)
+    assert acc.tolist() == [1.5 + float(o3[0]), 2.0 + float(o3[2])]
     # empty mask: zero loss, zero gradient
     loss0, o0 = masked_cross_entropy(logits.detach(), y, torch.zeros_like(mask))
     assert float(loss0) == 0. and float(o0[2]) == 0.
