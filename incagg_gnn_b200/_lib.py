@@ -73,6 +73,8 @@ _PROTOS = {
                                         P, c_size_t, P]),
     "incagg_colsum_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "incagg_relu_bwd_colsum": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, P, c_int64, P, P, c_size_t, P]),
+    "incagg_relu_bwd_colsum_ex": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, P, c_int64, P, c_int64, c_int64, P,
+                                          c_int, P, c_size_t, P]),
     "incagg_masked_ce_workspace_bytes": (c_size_t, [c_int64]),
     "incagg_masked_ce": (c_int, [P, c_int64, P, P, c_int64, c_int32, P, c_int64, P, P, c_size_t, P]),
     "incagg_mask_count": (c_int, [P, c_int64, P, P]),

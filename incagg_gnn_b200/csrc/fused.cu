@@ -13,16 +13,19 @@
 namespace incagg {
 
 constexpr int CS_THREADS = 256;
-constexpr int CS_ROWS_PER_BLOCK = 256;
+constexpr int CS_ROWS_PER_BLOCK = 64;   // (256: 340 blocks for the layer-0 gradient = 2.3 per SM, a long unbalanced tail)
 
 // Each block owns CS_ROWS_PER_BLOCK rows; thread t owns column chunk (t % cvec) of row group
 // (t / cvec), walks its rows with a fixed stride and the block combines through shared memory in a
 // fixed order -> partial[block][cols].  V = 4: float4 along the row (cols % 4 == 0, 16-byte aligned
 // rows); V = 1: scalar columns (any layout, e.g. the 47 logits of the classifier head).
+// add (nullable): a second gradient that is added to the first add_rows rows of g before the mask (the
+// x_0 gradients collected by the layers' GEMM epilogues, nn.X0GradSink).
 template <int V>
 __global__ void __launch_bounds__(CS_THREADS)
 relu_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
                        int64_t rows, int cols, float* __restrict__ gm, int64_t ldo,
+                       const float* __restrict__ add, int64_t ldadd, int64_t add_rows,
                        float* __restrict__ partial) {
   pdl_prologue();
   extern __shared__ float sm[];  // [groups][cols]
@@ -36,12 +39,16 @@ relu_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int64_t r = r0 + grp; r < r1; r += groups) {
         float4 v = *reinterpret_cast<const float4*>(g + r * ldg + cv * 4);
+        if (add && r < add_rows) {
+          const float4 a = *reinterpret_cast<const float4*>(add + r * ldadd + cv * 4);
+          v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        }
         if (y) {
           const float4 m = *reinterpret_cast<const float4*>(y + r * ldy + cv * 4);
           v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
           v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
-          if (gm) *reinterpret_cast<float4*>(gm + r * ldo + cv * 4) = v;
         }
+        if (gm && (y || add)) *reinterpret_cast<float4*>(gm + r * ldo + cv * 4) = v;
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
       *reinterpret_cast<float4*>(sm + grp * cols + cv * 4) = acc;
@@ -49,10 +56,9 @@ relu_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __
       float acc = 0.f;
       for (int64_t r = r0 + grp; r < r1; r += groups) {
         float v = g[r * ldg + cv];
-        if (y) {
-          v = y[r * ldy + cv] > 0.f ? v : 0.f;
-          if (gm) gm[r * ldo + cv] = v;
-        }
+        if (add && r < add_rows) v += add[r * ldadd + cv];
+        if (y) v = y[r * ldy + cv] > 0.f ? v : 0.f;
+        if (gm && (y || add)) gm[r * ldo + cv] = v;
         acc += v;
       }
       sm[grp * cols + cv] = acc;
@@ -71,7 +77,8 @@ relu_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __
 // (One thread per column walking all the blocks took 17 us for the 340 blocks of the layer-0 gradient.)
 constexpr int CF_WARPS = 8;
 __global__ void __launch_bounds__(CF_WARPS * 32)
-colsum_finish_kernel(const float* __restrict__ partial, int nblocks, int cols, float* __restrict__ out) {
+colsum_finish_kernel(const float* __restrict__ partial, int nblocks, int cols, float* __restrict__ out,
+                     int accumulate) {
   pdl_prologue();
   __shared__ float part[CF_WARPS][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -93,7 +100,7 @@ colsum_finish_kernel(const float* __restrict__ partial, int nblocks, int cols, f
     float t = part[0][lane];
 #pragma unroll
     for (int i = 1; i < CF_WARPS; ++i) t += part[i][lane];
-    out[c] = t;
+    out[c] = accumulate ? out[c] + t : t;
   }
 }
 
@@ -182,39 +189,52 @@ extern "C" size_t incagg_colsum_workspace_bytes(int64_t rows, int32_t cols) {
   return sizeof(float) * (size_t)((rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK) * (size_t)cols;
 }
 
-extern "C" int incagg_relu_bwd_colsum(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows,
-                                      int32_t cols, float* gm, int64_t ldo, float* colsum, void* workspace,
-                                      size_t workspace_bytes, incagg_stream_t stream) {
+extern "C" int incagg_relu_bwd_colsum_ex(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows,
+                                         int32_t cols, float* gm, int64_t ldo, const float* add, int64_t ldadd,
+                                         int64_t add_rows, float* colsum, int accumulate, void* workspace,
+                                         size_t workspace_bytes, incagg_stream_t stream) {
   IA_CHECK_ARG(rows >= 0 && cols > 0, "bad size");
   IA_CHECK_ARG(colsum != nullptr, "colsum is NULL");
   cudaStream_t st = as_stream(stream);
   if (rows == 0) {
-    IA_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * (size_t)cols, st));
+    if (!accumulate) IA_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * (size_t)cols, st));
     return INCAGG_OK;
   }
   IA_CHECK_ARG(g != nullptr, "g is NULL");
+  IA_CHECK_ARG(add == nullptr || (add_rows >= 0 && add_rows <= rows && ldadd >= cols), "bad addend");
+  IA_CHECK_ARG((y == nullptr && add == nullptr) || gm != nullptr, "gm is NULL");
   IA_CHECK_ARG(workspace != nullptr && workspace_bytes >= incagg_colsum_workspace_bytes(rows, cols),
                "workspace too small");
   const int nblocks = (int)((rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK);
   float* partial = static_cast<float*>(workspace);
+  if (add == nullptr) add_rows = 0;
   // float4 path: cols % 4 == 0 and every operand 16-byte aligned with ld % 4 == 0; else scalar columns
   const bool vec = cols % 4 == 0 && cols <= 1024 && ldg % 4 == 0 && aligned16(g) &&
                    (y == nullptr || (ldy % 4 == 0 && aligned16(y))) &&
-                   (gm == nullptr || (ldo % 4 == 0 && aligned16(gm)));
+                   (gm == nullptr || (ldo % 4 == 0 && aligned16(gm))) &&
+                   (add == nullptr || (ldadd % 4 == 0 && aligned16(add)));
   if (vec) {
     const int groups = CS_THREADS / (cols / 4);
     launch(relu_bwd_colsum_kernel<4>, dim3(nblocks), dim3(CS_THREADS), (size_t)(sizeof(float) * (size_t)groups * cols), st,
-        g, ldg, y, ldy, rows, cols, gm, ldo, partial);
+        g, ldg, y, ldy, rows, cols, gm, ldo, add, ldadd, add_rows, partial);
   } else {
     IA_CHECK_ARG(cols <= CS_THREADS, "unaligned / ragged layouts support at most 256 columns");
     const int groups = CS_THREADS / cols;
     launch(relu_bwd_colsum_kernel<1>, dim3(nblocks), dim3(CS_THREADS), (size_t)(sizeof(float) * (size_t)groups * cols), st,
-        g, ldg, y, ldy, rows, cols, gm, ldo, partial);
+        g, ldg, y, ldy, rows, cols, gm, ldo, add, ldadd, add_rows, partial);
   }
   IA_LAUNCH_CHECK();
-  launch(colsum_finish_kernel, dim3((cols + 31) / 32), dim3(CF_WARPS * 32), (size_t)(0), st, partial, nblocks, cols, colsum);
+  launch(colsum_finish_kernel, dim3((cols + 31) / 32), dim3(CF_WARPS * 32), (size_t)(0), st, partial, nblocks, cols, colsum,
+         accumulate ? 1 : 0);
   IA_LAUNCH_CHECK();
   return INCAGG_OK;
+}
+
+extern "C" int incagg_relu_bwd_colsum(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows,
+                                      int32_t cols, float* gm, int64_t ldo, float* colsum, void* workspace,
+                                      size_t workspace_bytes, incagg_stream_t stream) {
+  return incagg_relu_bwd_colsum_ex(g, ldg, y, ldy, rows, cols, gm, ldo, nullptr, 0, 0, colsum, 0, workspace,
+                                   workspace_bytes, stream);
 }
 
 extern "C" size_t incagg_masked_ce_workspace_bytes(int64_t rows) {

@@ -49,6 +49,7 @@ struct GemmParams {
   float alpha, beta;
   int relu;
   int acc2;                                  // DUAL_N: D2 += (instead of =): gradient accumulation in the epilogue
+  int gate;                                  // single GEMM: Cin is a ReLU-backward gate, D = Cin > 0 ? alpha acc + bias : 0
   int kb_per_split;                          // k-blocks handled by one blockIdx.z
   // second operand set (fused GCNII layer GEMMs, see incagg_gemm_tf32x3_dual)
   int dual;
@@ -405,6 +406,8 @@ gemm_tf32x3_kernel(const GemmParams p) {
                        : Dptr + m * ldd;
   const int64_t ldd_eff = splitk ? p.ldp : ldd;
   const bool vecD = (ldd_eff % 4 == 0) && aligned16(splitk ? (const void*)p.partial : (const void*)Dptr);
+  const bool gate = p.gate != 0;             // (DUAL_NONE only: Cin is this CTA's gate)
+  if (gate) beta_e = 1.f;                    // the gate values are kept as they are
   const bool use_cin = !splitk && Cin && beta_e != 0.f;
   const bool vecC = use_cin && (ldcin % 4 == 0) && aligned16(Cin);
   const bool full_n = (n0 + BN <= p.N);
@@ -464,6 +467,11 @@ gemm_tf32x3_kernel(const GemmParams p) {
         float o[4];
         if (splitk) {
           o[0] = v[i]; o[1] = v[i + 1]; o[2] = v[i + 2]; o[3] = v[i + 3];
+        } else if (gate) {   // ReLU backward: the gradient passes where the forward output was positive
+          o[0] = ci.x > 0.f ? alpha * v[i] : 0.f;
+          o[1] = ci.y > 0.f ? alpha * v[i + 1] : 0.f;
+          o[2] = ci.z > 0.f ? alpha * v[i + 2] : 0.f;
+          o[3] = ci.w > 0.f ? alpha * v[i + 3] : 0.f;
         } else {
           o[0] = alpha * v[i] + ci.x;
           o[1] = alpha * v[i + 1] + ci.y;
@@ -706,7 +714,8 @@ gemm_splitk_reduce_kernel(const GemmParams p, int splits, int n_chunks) {
       for (int i = 1; i < RED_WARPS; ++i) t += part[i][lane];
       if (set == 0) {
         float x = p.alpha * t;
-        if (p.Cin && p.beta != 0.f) x += p.beta * p.Cin[m * p.ldcin + n];
+        if (p.gate) x = p.Cin[m * p.ldcin + n] > 0.f ? x : 0.f;
+        else if (p.Cin && p.beta != 0.f) x += p.beta * p.Cin[m * p.ldcin + n];
         if (p.bias) x += p.bias[n];
         if (p.relu) x = fmaxf(x, 0.f);
         p.D[m * p.ldd + n] = x;
@@ -775,8 +784,9 @@ static int run_gemm(GemmParams& p, void* workspace, size_t workspace_bytes, cuda
   static const int force_bn = getenv("INCAGG_GEMM_BN") ? atoi(getenv("INCAGG_GEMM_BN")) : 0;
   // 64-wide n-tiles only for narrow outputs: on the 16 K-row problems of this path, splitting 128
   // columns over two co-resident CTAs measured slower (the A tile is split into hi / lo twice)
-  const int bn = nc ? 256 : ((p.N <= 64 || force_bn == 64) ? 64 : 128);
   const int64_t mt = (p.M + G_BM - 1) / G_BM;
+  const bool many_tiles = p.dual == DUAL_NONE && mt >= (int64_t)tune_get(INCAGG_TUNE_GEMM_BN64_MIN_TILES, 1 << 30);
+  const int bn = nc ? 256 : ((p.N <= 64 || force_bn == 64 || many_tiles) ? 64 : 128);
   const int64_t nt = nc ? 1 : (p.N + bn - 1) / bn;
   p.tiles1 = (int)(p.dual == DUAL_N ? nt : mt);
   const int64_t gx = mt * (p.dual == DUAL_M ? 2 : 1), gy = nt * (p.dual == DUAL_N ? 2 : 1);
@@ -789,7 +799,8 @@ static int run_gemm(GemmParams& p, void* workspace, size_t workspace_bytes, cuda
   int splits = 1;
   if (num_kb >= 16 && tiles < sm_count() && p.dual != DUAL_K && p.dual != DUAL_N && workspace != nullptr) {
     // one wave: (tiles x splits) CTAs <= SM count (one CTA per SM is resident)
-    int64_t want = (int64_t)sm_count() / tiles;
+    const int64_t budget = p.dual == DUAL_M ? (int64_t)tune_get(INCAGG_TUNE_GEMM_DUAL_M_CTAS, sm_count()) : (int64_t)sm_count();
+    int64_t want = budget / tiles;
     if (want > num_kb / 4) want = num_kb / 4;
     if (want > 128) want = 128;
     const int64_t fit = (int64_t)(workspace_bytes / (sizeof(float) * (size_t)p.Mpad * (size_t)p.ldp));
@@ -839,7 +850,10 @@ extern "C" int incagg_gemm_tf32x3(int transA, int transB, int64_t M, int64_t N, 
   GemmParams p{};
   p.A = A; p.lda = lda; p.transA = transA; p.B = B; p.ldb = ldb; p.transB = transB;
   p.Cin = Cin; p.ldcin = ldcin; p.bias = bias; p.D = D; p.ldd = ldd; p.M = M; p.N = N; p.K = K;
-  p.alpha = alpha; p.beta = beta; p.relu = relu; p.scaleB = 1.f; p.scaleB2 = 1.f; p.dual = DUAL_NONE;
+  IA_CHECK_ARG((relu & ~5) == 0, "flags: bit 0 ReLU, bit 2 Cin is a ReLU-backward gate");
+  IA_CHECK_ARG(!(relu & 4) || (Cin != nullptr && bias == nullptr && !(relu & 1)), "gate needs Cin, no bias, no ReLU");
+  p.alpha = alpha; p.beta = beta; p.relu = relu & 1; p.gate = (relu >> 2) & 1; p.scaleB = 1.f; p.scaleB2 = 1.f;
+  p.dual = DUAL_NONE;
   return run_gemm(p, workspace, workspace_bytes, as_stream(stream));
 }
 

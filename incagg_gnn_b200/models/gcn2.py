@@ -65,13 +65,12 @@ class GCN2(ScalableGNN):
     def _first_linear(self, x: Tensor):
         """x_0 = ReLU(lins[0] x) (gcn2.py:87) and, in training, the sink that collects the x_0 gradients
         of the layers in their GEMM epilogues (nn.X0GradSink; unshared weights only)."""
-        x_0 = self.lins[0](x, relu=True)
         sink = None
-        if (torch.is_grad_enabled() and x_0.requires_grad and self.convs[0].weight2 is not None
+        if (torch.is_grad_enabled() and self.training and self.convs[0].weight2 is not None
+                and self.lins[0].weight.requires_grad
                 and os.environ.get('INCAGG_X0_SINK', '1') != '0'):   # (A/B switch)
             sink = X0GradSink()
-            x_0 = sink.join(x_0)
-        return x_0, sink
+        return self.lins[0](x, relu=True, x0_sink=sink), sink
 
     def _post(self, i: int, h: Tensor, x: Tensor) -> Tensor:
         if self.batch_norm:
@@ -123,17 +122,18 @@ class GCN2(ScalableGNN):
                 torch.cuda.current_stream().wait_stream(self._pull_stream)   # pushes done before the step ends
             h = self.convs[-1](x, x0b, adj_t,
                                grad_rows=batch_size if self.num_layers > 1 else None, relu=fuse,
-                               relu_input=ahead is not None and self.num_layers > 1, x0_sink=sink)
+                               relu_input=ahead is not None and self.num_layers > 1, x0_sink=sink,
+                               defer_relu_bwd=fuse)   # lins[1] gates its input gradient (relu_input)
         else:  # no neighbour information (gcn2.py:151-181)
             x, x_0 = x[:batch_size], x_0[:batch_size]
             for i, conv in enumerate(self.convs[:-1]):
                 h = conv.forward_no_neighbor(x, x_0, relu=fuse, x0_sink=sink)
                 x = h if fuse else self._post(i, h, x)
                 x = F.dropout(x, p=self.dropout, training=self.training)
-            h = self.convs[-1].forward_no_neighbor(x, x_0, relu=fuse, x0_sink=sink)
+            h = self.convs[-1].forward_no_neighbor(x, x_0, relu=fuse, x0_sink=sink, defer_relu_bwd=fuse)
         x = h if fuse else self._post(self.num_layers - 1, h, x)
         x = F.dropout(x, p=self.dropout, training=self.training)
-        return self.lins[1](x), t_all
+        return self.lins[1](x, relu_input=fuse), t_all
 
     # IncAgg step (gcn2.py:187-323)
     def VR_forward(self, x: Tensor, adj_t: SparseTensor, drift_norm: int, epoch: int, batch_idx: int,
@@ -149,12 +149,14 @@ class GCN2(ScalableGNN):
             if i == self.num_layers - 1:
                 x = x[:batch_size]
             m_in, m_ag, gid = self._incagg_tables(i, batch_size, x.shape[1], n_id, offset, count)
-            h = spmm_delta(adj_t, x, m_in, m_ag, gid)  # A_BB (x - M_in) + M_ag, one kernel
-            h = conv.forward_after_propagate(h, x0b, relu=fuse, x0_sink=sink)
+            # the ReLU of layer i rides in its GEMM epilogue; its backward mask rides in the epilogue of the
+            # next consumer (the transposed SpMM of layer i + 1, the classifier's input-gradient GEMM)
+            h = spmm_delta(adj_t, x, m_in, m_ag, gid, relu_input=fuse and i > 0)  # A_BB (x - M_in) + M_ag, one kernel
+            h = conv.forward_after_propagate(h, x0b, relu=fuse, x0_sink=sink, defer_relu_bwd=fuse)
             self._incagg_release()
             x = h if fuse else self._post(i, h, x)
             x = F.dropout(x, p=self.dropout, training=self.training)
-        return self.lins[1](x), 0, 0, 0
+        return self.lins[1](x, relu_input=fuse), 0, 0, 0
 
     # layer-wise sweep (gcn2.py:325-374); `agg` = precomputed A @ (layer input) in eval mode
     @torch.no_grad()

@@ -36,9 +36,14 @@ class _LinearTC(torch.autograd.Function):
     same kernel (input gradient g W, weight gradient g^T x with deterministic split-K)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu):
+    def forward(ctx, x, weight, bias, relu, relu_input=False, x0_sink=None):
+        # relu_input: x is the output of a ReLU whose backward mask was deferred to this node (its input
+        # gradient GEMM gates its epilogue by [x > 0]).  x0_sink: the gradients that the GCNII layers
+        # collected for this Linear's output (nn.X0GradSink) join the incoming gradient in the fused
+        # ReLU-backward / bias-gradient kernel.
         y = ops.gemm(x, weight, trans_b=True, bias=bias, relu=relu)
         ctx.relu = relu
+        ctx.relu_input, ctx.x0_sink = bool(relu_input), x0_sink
         ctx.save_for_backward(x, weight, y if relu else None)
         ctx.has_bias = bias is not None
         ctx.weight_param, ctx.bias_param = weight, bias
@@ -53,12 +58,16 @@ class _LinearTC(torch.autograd.Function):
         side = _WGRAD['stream']
         wbuf = _grad_buffer(ctx.weight_param) if ctx.needs_input_grad[1] else None
         bbuf = _grad_buffer(ctx.bias_param) if want_gb else None
-        if (side is not None and not ctx.relu and ctx.needs_input_grad[0] and wbuf is not None
+        gate = x if ctx.relu_input else None
+        add = None
+        if ctx.x0_sink is not None:
+            add, ctx.x0_sink.buf = ctx.x0_sink.buf, None
+        if (side is not None and not ctx.relu and add is None and ctx.needs_input_grad[0] and wbuf is not None
                 and (not want_gb or (bbuf is not None and ops.colsum_supported(g)))):
             # Only the input gradient continues the backward chain: the weight and bias gradients (three
             # launches + the accumulation into the flat gradient buffer) run beside it on the side stream.
             side.wait_stream(torch.cuda.current_stream(g.device))
-            gx = ops.gemm(g, weight)
+            gx = ops.gemm(g, weight, gate=gate)
             with torch.cuda.stream(side):
                 ops.gemm(g, x, trans_a=True, cin=wbuf, beta=1., out=wbuf, ws_slot=1)
                 if want_gb:
@@ -66,38 +75,48 @@ class _LinearTC(torch.autograd.Function):
                     bbuf.add_(cs)
                     _WGRAD['keep'].append(cs)
             _WGRAD['keep'].append((g, x))
-            return gx, None, None, None
-        if want_gb and ops.colsum_supported(g) and (not ctx.relu or ops.colsum_supported(y)):
-            # ReLU backward and the bias gradient in one pass over g
-            g, gb = ops.relu_bwd_colsum(g, y if ctx.relu else None)
+            return gx, None, None, None, None, None
+        if (want_gb and ops.colsum_supported(g) and (not ctx.relu or ops.colsum_supported(y))
+                and (add is None or ops.colsum_supported(add))):
+            # (sink +) ReLU backward and the bias gradient in one pass over g; the bias gradient lands in
+            # the flat gradient buffer directly when there is one
+            g, gb = ops.relu_bwd_colsum(g, y if ctx.relu else None, add=add, colsum_into=bbuf)
         else:
+            if add is not None:
+                g = g.clone()
+                g[:add.size(0)].add_(add)
             if ctx.relu:
                 g = torch.ops.aten.threshold_backward(g, y, 0.)  # ReLU backward, one kernel
             if want_gb:
                 gb = g.sum(0)
         if ctx.needs_input_grad[0]:
-            gx = ops.gemm(g, weight)                      # [M,N] x [N,K]
+            gx = ops.gemm(g, weight, gate=gate)           # [M,N] x [N,K]
         if ctx.needs_input_grad[1]:
             buf = _grad_buffer(ctx.weight_param)
             if buf is not None:                           # accumulate in the GEMM epilogue
                 ops.gemm(g, x, trans_a=True, cin=buf, beta=1., out=buf)
             else:
                 gw = ops.gemm(g, x, trans_a=True)         # g^T x : [N,M] x [M,K]
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None, None
 
 
-def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu: bool = False) -> Tensor:
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, relu: bool = False,
+           relu_input: bool = False, x0_sink=None) -> Tensor:
     if x.dim() != 2:
-        return linear(x.reshape(-1, x.size(-1)), weight, bias, relu).reshape(*x.shape[:-1], weight.size(0))
-    return _LinearTC.apply(x, weight, bias, relu)
+        assert x0_sink is None
+        return linear(x.reshape(-1, x.size(-1)), weight, bias, relu,
+                      relu_input).reshape(*x.shape[:-1], weight.size(0))
+    return _LinearTC.apply(x, weight, bias, relu, relu_input, x0_sink)
 
 
 class Linear(torch.nn.Linear):
     """torch.nn.Linear whose product runs on the hand-written tcgen05 GEMM (same parameters, same
     initialisation).  ``forward(x, relu=True)`` fuses the activation into the GEMM epilogue."""
 
-    def forward(self, x: Tensor, relu: bool = False) -> Tensor:
-        return linear(x, self.weight, self.bias, relu)
+    def forward(self, x: Tensor, relu: bool = False, relu_input: bool = False, x0_sink=None) -> Tensor:
+        """relu_input: x is a ReLU output whose backward mask this layer applies (the producer was called
+        with defer_relu_bwd=True).  x0_sink: see X0GradSink."""
+        return linear(x, self.weight, self.bias, relu, relu_input, x0_sink)
 
 
 # Weight gradients on a side stream -----------------------------------------------------------------
@@ -133,9 +152,11 @@ class X0GradSink:
     (gcn2.py:121), so autograd would add L gradients of [B, F] with L - 1 elementwise launches, pad the sum
     to the [B + H] rows of x_0 (fill + copy) and add it to the gradient that arrives through layer 0's
     propagation.  With a sink the input-gradient GEMM of each layer adds into one buffer in its epilogue
-    (first layer of the backward pass: plain store) and returns no x_0 gradient to autograd;
-    ``X0GradSink.join`` (placed on x_0 right after the first Linear) adds the buffer to the head rows of
-    the gradient that reaches x_0: one launch instead of L + 2.  One sink per forward pass."""
+    (first layer of the backward pass: plain store) and returns no x_0 gradient to autograd.  The buffer
+    joins the gradient that reaches x_0 through layer 0's propagation either inside the fused ReLU-backward
+    / bias-gradient kernel of the Linear that produced x_0 (``Linear.forward(..., x0_sink=sink)``: no
+    launch at all) or, for any other producer, in ``X0GradSink.join`` (one in-place add).  One sink per
+    forward pass."""
 
     def __init__(self):
         self.buf = None
@@ -356,8 +377,8 @@ class GCN2Conv(torch.nn.Module):
                                 bool(defer_relu_bwd and relu), x0_sink)
 
     def forward_no_neighbor(self, x: Tensor, x_0: Tensor, relu: bool = False,
-                            x0_sink: Optional[X0GradSink] = None) -> Tensor:
-        return self.forward_after_propagate(x, x_0, relu, x0_sink=x0_sink)
+                            x0_sink: Optional[X0GradSink] = None, defer_relu_bwd: bool = False) -> Tensor:
+        return self.forward_after_propagate(x, x_0, relu, None, defer_relu_bwd, x0_sink)
 
     def forward(self, x: Tensor, x_0: Tensor, adj_t: SparseTensor,
                 grad_rows: Optional[int] = None, relu: bool = False,

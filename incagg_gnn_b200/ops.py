@@ -10,6 +10,8 @@ Reference op names re-registered (csrc/relabel.cpp:40-42, csrc/async.cpp:44-48):
 """
 from typing import Optional, Tuple
 
+import os
+
 import torch
 from torch import Tensor
 
@@ -71,13 +73,17 @@ def _ld(t: Tensor) -> int:
 # --------------------------------------------------------------------------------------------
 # SpMM
 # --------------------------------------------------------------------------------------------
-TUNE = {"spmm_stream_variant": 0, "spmm_stream_min_f": 1}
+TUNE = {"spmm_stream_variant": 0, "spmm_stream_min_f": 1, "gemm_dual_m_ctas": 2, "gemm_bn64_min_tiles": 3}
 
 
 def tune(key: str, value: int) -> None:
     """Experiment knobs of the kernels (include/incagg_b200.h INCAGG_TUNE_*).  Plans built before a
     knob that changes the warp partition was set must be rebuilt (SparseTensor.drop_caches)."""
     check(lib.incagg_tune_set(TUNE[key], int(value)))
+
+
+for _kv in filter(None, os.environ.get("INCAGG_TUNE", "").split(",")):   # INCAGG_TUNE="key=value,..." (experiments)
+    tune(_kv.split("=")[0].strip(), int(_kv.split("=")[1]))
 
 
 # The SpMM kernels keep the partial sums of rows that are split over several CTAs / warps in one
@@ -254,10 +260,15 @@ def _rowmajor(t: Tensor) -> Tensor:
 
 def gemm(a: Tensor, b: Tensor, trans_a: bool = False, trans_b: bool = False, alpha: float = 1.0,
          cin: Optional[Tensor] = None, beta: float = 0.0, bias: Optional[Tensor] = None,
-         relu: bool = False, out: Optional[Tensor] = None, ws_slot: int = 0) -> Tensor:
+         relu: bool = False, out: Optional[Tensor] = None, ws_slot: int = 0,
+         gate: Optional[Tensor] = None) -> Tensor:
     """out[M,N] = alpha * op(a) @ op(b) + beta * cin + bias (+ReLU) with the tcgen05 3xTF32 kernel.
     trans_a: `a` is stored [K, M]; trans_b: `b` is stored [N, K] (a Linear weight).  ws_slot: which
-    split-K scratch buffer to use (GEMMs issued on a side stream must not share the main stream's)."""
+    split-K scratch buffer to use (GEMMs issued on a side stream must not share the main stream's).
+    gate ([M, N]): out is zeroed where gate <= 0 (ReLU backward in the epilogue; excludes cin / bias / relu)."""
+    if gate is not None:
+        assert cin is None and bias is None and not relu
+        cin = gate
     _require_cuda(a, b, cin, bias, out)
     a, b = _rowmajor(a), _rowmajor(b)
     M, K = (a.size(1), a.size(0)) if trans_a else (a.size(0), a.size(1))
@@ -277,7 +288,8 @@ def gemm(a: Tensor, b: Tensor, trans_a: bool = False, trans_b: bool = False, alp
     LAUNCHES["calls"] += 1
     check(lib.incagg_gemm_tf32x3(int(trans_a), int(trans_b), M, N, K, ptr(a), _ld(a), ptr(b), _ld(b),
                                  float(alpha), ptr(cin), _ld(cin) if cin is not None else 0, float(beta),
-                                 ptr(bias), int(relu), ptr(out), _ld(out), ptr(ws), ws_bytes, _stream()))
+                                 ptr(bias), int(bool(relu)) | (4 if gate is not None else 0), ptr(out), _ld(out),
+                                 ptr(ws), ws_bytes, _stream()))
     return out
 
 
@@ -324,24 +336,33 @@ def gemm_dual(mode: str, a: Tensor, b: Tensor, a2: Optional[Tensor] = None, b2: 
     return (out, out2) if mode in ("n", "m") else out
 
 
-def relu_bwd_colsum(g: Tensor, y: Optional[Tensor] = None):
-    """(g * (y > 0), its column sums) in one pass; y=None: (g, column sums of g).  float4 path for
-    16-byte-aligned rows with cols % 4 == 0, scalar columns otherwise (<= 256 columns: colsum_supported)."""
-    _require_cuda(g, y)
+def relu_bwd_colsum(g: Tensor, y: Optional[Tensor] = None, add: Optional[Tensor] = None,
+                    colsum_into: Optional[Tensor] = None):
+    """((g [+ add on its first rows]) * (y > 0), its column sums) in one pass; y=None: no mask.  float4 path
+    for 16-byte-aligned rows with cols % 4 == 0, scalar columns otherwise (<= 256 columns:
+    colsum_supported).  colsum_into: the column sums are ADDED to this buffer (a bias gradient view of the
+    flat gradient buffer) instead of being returned."""
+    _require_cuda(g, y, add, colsum_into)
     g = _rowmajor(g)
     rows, cols = g.shape
     gm = None
-    if y is not None:
-        y = _rowmajor(y)
+    if y is not None or add is not None:
+        y = _rowmajor(y) if y is not None else None
+        add = _rowmajor(add) if add is not None else None
         gm = torch.empty_like(g)
-    colsum = torch.empty(cols, dtype=torch.float32, device=g.device)
+    if colsum_into is not None:
+        assert colsum_into.dtype == torch.float32 and colsum_into.is_contiguous() and colsum_into.numel() == cols
+        colsum = colsum_into
+    else:
+        colsum = torch.empty(cols, dtype=torch.float32, device=g.device)
     nb = lib.incagg_colsum_workspace_bytes(rows, cols)
     ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=g.device)
     LAUNCHES["calls"] += 1
-    check(lib.incagg_relu_bwd_colsum(ptr(g), _ld(g), ptr(y), _ld(y) if y is not None else 0, rows, cols,
-                                     ptr(gm), _ld(gm) if gm is not None else 0, ptr(colsum), ptr(ws),
-                                     ws.numel(), _stream()))
-    return (gm if gm is not None else g), colsum
+    check(lib.incagg_relu_bwd_colsum_ex(ptr(g), _ld(g), ptr(y), _ld(y) if y is not None else 0, rows, cols,
+                                        ptr(gm), _ld(gm) if gm is not None else 0, ptr(add),
+                                        _ld(add) if add is not None else 0, add.size(0) if add is not None else 0,
+                                        ptr(colsum), int(colsum_into is not None), ptr(ws), ws.numel(), _stream()))
+    return (gm if gm is not None else g), (None if colsum_into is not None else colsum)
 
 
 def colsum_supported(t: Tensor) -> bool:

@@ -176,17 +176,29 @@ def forward_backward(model, sub, optimizer, VR_update=False, averager=None, epoc
     side = _backward_prep(adj_t, batch_size, VR_update)
     fused_ce = y.dim() == 1 and x.is_cuda
     n_train = None
-    if fused_ce and side is not None:
+    zeroed = False
+    if side is not None:
         from . import ops
-        with torch.cuda.stream(side):   # the row count of the loss depends on the batch alone
-            n_train = ops.mask_count(train_mask)
+        with torch.cuda.stream(side):
+            if fused_ce:   # the row count of the loss depends on the batch alone
+                n_train = ops.mask_count(train_mask)
+            # flat gradient buffers are cleared here, beside the forward pass (a fill on the main stream
+            # would sit between the last forward kernel and the loss)
+            if averager is not None:
+                averager.zero()  # gradients are views into the averager's flat buffer
+                zeroed = True
+            elif hasattr(optimizer, 'flat_g'):
+                optimizer.zero_grad(set_to_none=True)
+                zeroed = True
     if VR_update:
         out = model.VR_call(x, adj_t, batch_size, n_id, offset, count, epoch=epoch, batch_idx=batch_idx)['out']
     else:
         out = model(x, adj_t, batch_size, n_id, offset, count)['out']
     if side is not None:
         torch.cuda.current_stream().wait_stream(side)
-    if averager is not None:
+    if zeroed:
+        pass
+    elif averager is not None:
         averager.zero()  # gradients are views into the averager's flat buffer
     else:
         optimizer.zero_grad(set_to_none=True)

@@ -60,6 +60,8 @@ int64_t incagg_launch_count(void);
  * rebuilt. */
 #define INCAGG_TUNE_SPMM_STREAM_VARIANT 0 /* merge-path SpMM: -2 auto (delta form only, variant 2), -1 off, else gathers per buffer x warps/SM: 0 = 8 x 16, 1 = 4 x 32, 2 = 4 x 24, 3 = 2 x 40, 4 = 2 x 48, 5 = 16 x 8 */
 #define INCAGG_TUNE_SPMM_STREAM_MIN_F 1   /* smallest feature width routed to the merge-path kernel (65) */
+#define INCAGG_TUNE_GEMM_DUAL_M_CTAS 2    /* CTA budget of an M-concatenated split-K GEMM (weight gradients that run beside the backward chain); default: the SM count */
+#define INCAGG_TUNE_GEMM_BN64_MIN_TILES 3 /* 64-wide n-tiles (two CTAs per SM) for problems with at least this many m-tiles; default: never */
 #define INCAGG_TUNE_COUNT 8
 int incagg_tune_set(int key, int value);
 /* Device-side error word of the current device.  The reference raises on an index outside its table
@@ -160,7 +162,10 @@ int incagg_spmm_multi_arg(const int32_t* rowptr, const int32_t* col, const float
  * within ~1e-6 relative of an fp32 GEMM.
  *   transA = 0: A is [M,K] row-major (lda); 1: A is stored [K,M] row-major
  *   transB = 0: B is [K,N] row-major (ldb); 1: B is stored [N,K] row-major (a Linear weight)
- *   Cin / bias nullable.  workspace (nullable) enables deterministic split-K for long reductions
+ *   Cin / bias nullable.  relu is a flag word: bit 0 = ReLU; bit 2 (value 4) = Cin is a ReLU-backward gate
+ *   instead of an addend, D = Cin > 0 ? alpha op(A) op(B) : 0 (the input gradient of a Linear whose input
+ *   was a ReLU output, gcn2.py:149; no bias, beta ignored).
+ *   workspace (nullable) enables deterministic split-K for long reductions
  *   (weight gradients); incagg_gemm_workspace_bytes gives a sufficient size.
  */
 size_t incagg_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
@@ -204,6 +209,16 @@ size_t incagg_colsum_workspace_bytes(int64_t rows, int32_t cols);
 int incagg_relu_bwd_colsum(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows,
                            int32_t cols, float* gm, int64_t ldo, float* colsum, void* workspace,
                            size_t workspace_bytes, incagg_stream_t stream);
+/*
+ * Extended form: `add` (nullable, [add_rows, cols]) is added to the first add_rows rows of g before the mask
+ * (the x_0 gradients that the GCNII layers' GEMM epilogues collected, gcn2.py:121); accumulate != 0:
+ * colsum += instead of colsum = (the bias gradient lands in the flat gradient buffer directly).
+ * gm is required when y or add is given.
+ */
+int incagg_relu_bwd_colsum_ex(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t rows,
+                              int32_t cols, float* gm, int64_t ldo, const float* add, int64_t ldadd,
+                              int64_t add_rows, float* colsum, int accumulate, void* workspace,
+                              size_t workspace_bytes, incagg_stream_t stream);
 /*
  * Mean cross-entropy over the rows whose mask byte is non-zero (main.py:80
  * criterion(out[train_mask], y[train_mask])) and its gradient:

@@ -354,6 +354,15 @@ def test_gemm_epilogue_and_views(ops, cuda):
         o = ops.gemm(xa, w, trans_b=True)
         r = xa.double() @ w.double().t()
         assert float((o.double() - r).abs().max() / r.abs().max()) <= RTOL
+    # ReLU-backward gate in the epilogue: zero where gate <= 0 (full and ragged n-tiles, split-K)
+    for (m_, n_, k_) in ((333, 128, 47), (200, 100, 64), (96, 128, 4096)):
+        a_ = torch.randn(m_, k_, generator=g).to(cuda)
+        b_ = torch.randn(k_, n_, generator=g).to(cuda)
+        gate = torch.randn(m_, n_, generator=g).to(cuda)
+        o = ops.gemm(a_, b_, gate=gate)
+        r = (a_.double() @ b_.double()) * (gate > 0)
+        assert float((o.double() - r).abs().max() / r.abs().max()) <= RTOL
+        assert torch.equal(o == 0, ~(gate > 0) | (o == 0)) and float(o[gate <= 0].abs().max()) == 0.
     dst = torch.zeros(M, 256, device=cuda)
     ops.gemm(x, w, trans_b=True, out=dst[:, 128:])
     r = x.double() @ w.double().t()
@@ -686,6 +695,22 @@ def test_relu_bwd_colsum_and_masked_ce(ops, cuda):
         r3 = view if yv is None else view * (yv > 0)
         assert torch.equal(gm3, r3)
         assert float((cs3.double() - r3.double().sum(0)).abs().max() / r3.double().sum(0).abs().max()) <= RTOL
+    # addend on the first rows (the x_0 gradient sink) + accumulation into an existing buffer
+    addend = torch.randn(1000, 128, generator=g).to(cuda)
+    into = torch.randn(128, generator=g).to(cuda)
+    before = into.clone()
+    gm5, none5 = ops.relu_bwd_colsum(G, Y, add=addend, colsum_into=into)
+    r5 = G.clone()
+    r5[:1000] += addend
+    r5 = r5 * (Y > 0)
+    assert none5 is None and torch.equal(gm5, r5)
+    r5s = before.double() + r5.double().sum(0)
+    assert float((into.double() - r5s).abs().max() / r5s.abs().max()) <= RTOL
+    gm6, cs6 = ops.relu_bwd_colsum(G, None, add=addend)      # no mask: g + addend and its column sums
+    r6 = G.clone()
+    r6[:1000] += addend
+    assert torch.equal(gm6, r6)
+    assert float((cs6.double() - r6.double().sum(0)).abs().max() / r6.double().sum(0).abs().max()) <= RTOL
     _, cs4 = ops.relu_bwd_colsum(big)          # 352 row blocks through the parallel finish
     assert float((cs4.double() - big.double().sum(0)).abs().max() / big.double().sum(0).abs().max()) <= RTOL
     # masked_cross_entropy_grad: the same numbers without an autograd node
