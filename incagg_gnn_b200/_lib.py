@@ -71,6 +71,8 @@ _PROTOS = {
                                         c_int64, P, c_int64, P, c_int64, c_float, c_float, c_float, c_float,
                                         P, c_int64, c_float, P, c_int64, c_float, c_int, P, c_int64, P, c_int64,
                                         P, c_size_t, P]),
+    "incagg_gemm_tf32x3_group": (c_int, [c_int, c_int, c_int, c_int64, c_int64, c_int64, P, P, P, P, P, c_float, P, P,
+                                         P, c_size_t, P]),
     "incagg_colsum_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "incagg_relu_bwd_colsum": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, P, c_int64, P, P, c_size_t, P]),
     "incagg_relu_bwd_colsum_ex": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, P, c_int64, P, c_int64, c_int64, P,

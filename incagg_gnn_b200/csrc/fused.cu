@@ -75,7 +75,7 @@ relu_bwd_colsum_kernel(const float* __restrict__ g, int64_t ldg, const float* __
 // out[c] = sum_b partial[b][c]: a block of 8 warps owns 32 columns, warp w sums the blocks w, w + 8, ...
 // (independent coalesced loads), the eight sums are combined in warp order: a fixed association.
 // (One thread per column walking all the blocks took 17 us for the 340 blocks of the layer-0 gradient.)
-constexpr int CF_WARPS = 8;
+constexpr int CF_WARPS = 32;
 __global__ void __launch_bounds__(CF_WARPS * 32)
 colsum_finish_kernel(const float* __restrict__ partial, int nblocks, int cols, float* __restrict__ out,
                      int accumulate) {

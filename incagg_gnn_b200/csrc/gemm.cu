@@ -36,7 +36,16 @@ constexpr int G_BM = 128;
 constexpr int G_BK = 32;     // 32 tf32 = 128 bytes = one swizzle row
 constexpr int G_THREADS = 256;
 
-enum { DUAL_NONE = 0, DUAL_K = 1, DUAL_N = 2, DUAL_M = 3, DUAL_NC = 4 };  // NC: internal, see gemm_nc_kernel
+enum { DUAL_NONE = 0, DUAL_K = 1, DUAL_N = 2, DUAL_M = 3, DUAL_NC = 4, DUAL_GROUP = 5 };  // NC: internal, see gemm_nc_kernel
+// DUAL_GROUP: up to G_MAX_GROUP independent problems of one shape in one launch (incagg_gemm_tf32x3_group)
+constexpr int G_MAX_GROUP = 16;
+struct GemmGroup {
+  const float* A[G_MAX_GROUP];
+  const float* B[G_MAX_GROUP];
+  float* D[G_MAX_GROUP];
+  int64_t lda[G_MAX_GROUP], ldb[G_MAX_GROUP], ldd[G_MAX_GROUP];
+  float alpha[G_MAX_GROUP];
+};
 
 struct GemmParams {
   const float* A; int64_t lda; int transA;   // transA = 0: A is [M,K] row-major; 1: stored [K,M]
@@ -63,6 +72,8 @@ struct GemmParams {
   int tiles1;                                // DUAL_N / DUAL_M: tiles (y resp. x) of the first set
   int64_t Mpad;                              // rows of one split-K partial slab
   int64_t ldp;                               // row stride of a partial slab (N; 256 for DUAL_NC)
+  int group_n;                               // DUAL_GROUP: number of problems; m-tile index / tiles1 = problem
+  GemmGroup grp;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -292,7 +303,7 @@ template <int BN> struct GemmCfg { static constexpr int STAGES = (BN == 64) ? 2 
 
 template <int BN, bool TA, bool TBK>
 __global__ void __launch_bounds__(G_THREADS, GemmCfg<BN>::MIN_CTAS)
-gemm_tf32x3_kernel(const GemmParams p) {
+gemm_tf32x3_kernel(const __grid_constant__ GemmParams p) {
   pdl_trigger();  // the wait comes after the on-chip set-up (barriers, TMEM), before the first global access
   constexpr int G_STAGES = GemmCfg<BN>::STAGES;
   extern __shared__ __align__(1024) char smem_raw[];
@@ -318,6 +329,13 @@ gemm_tf32x3_kernel(const GemmParams p) {
     acc_d = p.acc2 != 0;
     by -= p.tiles1; Bptr = p.B2; ldb = p.ldb2; Dptr = p.D2; ldd = p.ldd2; alpha_e = p.alpha2; beta_e = p.beta2;
     Cin = p.Cin2; ldcin = p.ldcin2; scaleB = p.scaleB2;
+  }
+  if (p.dual == DUAL_GROUP) {   // problem `set` of the group; D accumulates in place when beta != 0
+    const int set = bx / p.tiles1;
+    bx -= set * p.tiles1;
+    Aptr = p.grp.A[set]; lda = p.grp.lda[set]; Bptr = p.grp.B[set]; ldb = p.grp.ldb[set];
+    Dptr = p.grp.D[set]; ldd = p.grp.ldd[set]; alpha_e = p.grp.alpha[set];
+    Cin = Dptr; ldcin = ldd;
   }
   if (p.dual == DUAL_M && bx >= p.tiles1) {
     bx -= p.tiles1; Aptr = p.A2; lda = p.lda2; Dptr = p.D2; ldd = p.ldd2; alpha_e = p.alpha2;
@@ -512,7 +530,7 @@ gemm_tf32x3_kernel(const GemmParams p) {
 // half the CTAs (the 16 K-row problems fit one wave).
 template <bool TA, bool TBK>
 __global__ void __launch_bounds__(G_THREADS, 1)
-gemm_nc_kernel(const GemmParams p) {
+gemm_nc_kernel(const __grid_constant__ GemmParams p) {
   pdl_trigger();  // the wait comes after the on-chip set-up (barriers, TMEM), before the first global access
   constexpr int STAGES = 2, BN = 256, HALF = 128;
   extern __shared__ __align__(1024) char smem_raw[];
@@ -681,11 +699,11 @@ gemm_nc_kernel(const GemmParams p) {
 // of the second output start at tiles1 * 128.
 constexpr int RED_WARPS = 8;
 __global__ void __launch_bounds__(RED_WARPS * 32)
-gemm_splitk_reduce_kernel(const GemmParams p, int splits, int n_chunks) {
+gemm_splitk_reduce_kernel(const __grid_constant__ GemmParams p, int splits, int n_chunks) {
   pdl_prologue();
   __shared__ float part[RED_WARPS][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t sets = (p.dual == DUAL_M || p.dual == DUAL_NC) ? 2 : 1;
+  const int64_t sets = (p.dual == DUAL_M || p.dual == DUAL_NC) ? 2 : (p.dual == DUAL_GROUP ? p.group_n : 1);
   const int64_t items = sets * p.M * n_chunks;             // one item = 32 columns of one output row
   const int64_t slab = p.Mpad * p.ldp;
   for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
@@ -694,7 +712,7 @@ gemm_splitk_reduce_kernel(const GemmParams p, int splits, int n_chunks) {
     const int64_t m = j / n_chunks;
     const int64_t n = (j - m * n_chunks) * 32 + lane;
     // DUAL_M: the second output's rows follow the first's; DUAL_NC: its columns start at 128
-    const int64_t prow = m + ((set && p.dual == DUAL_M) ? (int64_t)p.tiles1 * G_BM : 0);
+    const int64_t prow = m + ((p.dual == DUAL_M || p.dual == DUAL_GROUP) ? set * (int64_t)p.tiles1 * G_BM : 0);
     float acc = 0.f;
     if (n < p.N) {
       const float* src = p.partial + prow * p.ldp + n + ((set && p.dual == DUAL_NC) ? 128 : 0);
@@ -712,7 +730,12 @@ gemm_splitk_reduce_kernel(const GemmParams p, int splits, int n_chunks) {
       float t = part[0][lane];
 #pragma unroll
       for (int i = 1; i < RED_WARPS; ++i) t += part[i][lane];
-      if (set == 0) {
+      if (p.dual == DUAL_GROUP) {
+        float* d = p.grp.D[set] + m * p.grp.ldd[set] + n;
+        float x = p.grp.alpha[set] * t;
+        if (p.beta != 0.f) x += p.beta * *d;
+        *d = x;
+      } else if (set == 0) {
         float x = p.alpha * t;
         if (p.gate) x = p.Cin[m * p.ldcin + n] > 0.f ? x : 0.f;
         else if (p.Cin && p.beta != 0.f) x += p.beta * p.Cin[m * p.ldcin + n];
@@ -741,6 +764,7 @@ static int launch_gemm_t(const GemmParams& p, int splits, cudaStream_t st) {
   }
   unsigned gx = (unsigned)((p.M + G_BM - 1) / G_BM), gy = (unsigned)((p.N + BN - 1) / BN);
   if (p.dual == DUAL_M) gx *= 2;
+  if (p.dual == DUAL_GROUP) gx *= (unsigned)p.group_n;
   if (p.dual == DUAL_N) gy *= 2;
   dim3 grid(gx, gy, (unsigned)splits);
   launch(gemm_tf32x3_kernel<BN, TA, TBK>, dim3(grid), dim3(G_THREADS), (size_t)(SMEM), st, p);
@@ -789,7 +813,7 @@ static int run_gemm(GemmParams& p, void* workspace, size_t workspace_bytes, cuda
   const int bn = nc ? 256 : ((p.N <= 64 || force_bn == 64 || many_tiles) ? 64 : 128);
   const int64_t nt = nc ? 1 : (p.N + bn - 1) / bn;
   p.tiles1 = (int)(p.dual == DUAL_N ? nt : mt);
-  const int64_t gx = mt * (p.dual == DUAL_M ? 2 : 1), gy = nt * (p.dual == DUAL_N ? 2 : 1);
+  const int64_t gx = mt * (p.dual == DUAL_M ? 2 : (p.dual == DUAL_GROUP ? p.group_n : 1)), gy = nt * (p.dual == DUAL_N ? 2 : 1);
   p.Mpad = gx * G_BM;
   p.ldp = nc ? 256 : p.N;
   if (p.dual == DUAL_K) p.kb1 = (int)((p.K + G_BK - 1) / G_BK);
@@ -816,7 +840,7 @@ static int run_gemm(GemmParams& p, void* workspace, size_t workspace_bytes, cuda
   if (rc != INCAGG_OK) return rc;
   if (splits > 1) {
     const int n_chunks = (int)((p.N + 31) / 32);
-    const int64_t items = p.M * n_chunks * ((p.dual == DUAL_M || nc) ? 2 : 1);
+    const int64_t items = p.M * n_chunks * ((p.dual == DUAL_M || nc) ? 2 : (p.dual == DUAL_GROUP ? p.group_n : 1));
     const int blocks = (int)(items < (int64_t)sm_count() * 8 ? items : (int64_t)sm_count() * 8);
     launch(gemm_splitk_reduce_kernel, dim3(blocks), dim3(RED_WARPS * 32), (size_t)(0), st, p, splits, n_chunks);
     IA_LAUNCH_CHECK();
@@ -879,5 +903,30 @@ extern "C" int incagg_gemm_tf32x3_dual(int mode, int transA, int transB, int64_t
   IA_CHECK_ARG((relu & ~3) == 0 && (!(relu & 2) || mode == DUAL_N), "flags: bit 0 ReLU, bit 1 (mode 2 only) D2 accumulates");
   p.alpha = alpha; p.alpha2 = alpha2; p.scaleB = scaleB; p.scaleB2 = scaleB2; p.relu = relu & 1;
   p.acc2 = (relu >> 1) & 1; p.dual = mode;
+  return run_gemm(p, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int incagg_gemm_tf32x3_group(int count, int transA, int transB, int64_t M, int64_t N, int64_t K,
+                                        const float* const* A, const int64_t* lda, const float* const* B,
+                                        const int64_t* ldb, const float* alpha, float beta, float* const* D,
+                                        const int64_t* ldd, void* workspace, size_t workspace_bytes,
+                                        incagg_stream_t stream) {
+  IA_CHECK_ARG(count >= 1 && count <= G_MAX_GROUP, "1 <= count <= 16");
+  IA_CHECK_ARG(M > 0 && N > 0 && K > 0, "empty problem");
+  IA_CHECK_ARG(A && B && D && lda && ldb && ldd && alpha, "NULL argument");
+  IA_CHECK_ARG(((M + G_BM - 1) / G_BM) * count <= 0x3fffffff, "too many tiles");
+  GemmParams p{};
+  for (int g = 0; g < count; ++g) {
+    IA_CHECK_ARG(A[g] && B[g] && D[g], "NULL operand");
+    IA_CHECK_ARG(lda[g] >= (transA ? M : K) && ldb[g] >= (transB ? K : N) && ldd[g] >= N, "leading dimension too small");
+    p.grp.A[g] = A[g]; p.grp.B[g] = B[g]; p.grp.D[g] = D[g];
+    p.grp.lda[g] = lda[g]; p.grp.ldb[g] = ldb[g]; p.grp.ldd[g] = ldd[g]; p.grp.alpha[g] = alpha[g];
+  }
+  p.group_n = count;
+  // (set 0 stands in for the scalar fields; the kernels read the group table)
+  p.A = A[0]; p.lda = lda[0]; p.transA = transA; p.B = B[0]; p.ldb = ldb[0]; p.transB = transB;
+  p.D = D[0]; p.ldd = ldd[0]; p.Cin = beta != 0.f ? D[0] : nullptr; p.ldcin = ldd[0];
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha[0]; p.beta = beta; p.scaleB = 1.f; p.scaleB2 = 1.f;
+  p.dual = DUAL_GROUP;
   return run_gemm(p, workspace, workspace_bytes, as_stream(stream));
 }

@@ -68,8 +68,15 @@ class _LinearTC(torch.autograd.Function):
             # launches + the accumulation into the flat gradient buffer) run beside it on the side stream.
             side.wait_stream(torch.cuda.current_stream(g.device))
             gx = ops.gemm(g, weight, gate=gate)
+            if _WGRAD_GROUP:   # joins the grouped launch at the end of the backward pass
+                _WGRAD['pending'].append((g, x, wbuf, 1.))
+                if _WGRAD['ready'] is None:
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(g.device))
+                    _WGRAD['ready'] = ev
             with torch.cuda.stream(side):
-                ops.gemm(g, x, trans_a=True, cin=wbuf, beta=1., out=wbuf, ws_slot=1)
+                if not _WGRAD_GROUP:
+                    ops.gemm(g, x, trans_a=True, cin=wbuf, beta=1., out=wbuf, ws_slot=1)
                 if want_gb:
                     _, cs = ops.relu_bwd_colsum(g, None)
                     bbuf.add_(cs)
@@ -125,8 +132,33 @@ class Linear(torch.nn.Linear):
 # rest of the backward pass reads them, so they overlap the SpMM^T / input-gradient chain (a GEMM call is
 # bound by one CTA per SM moving its tiles, the SpMM by the L2 gather path: they share an SM well).
 # The operands are kept alive until the join at the end of the backward pass.
-_WGRAD = {'stream': None, 'keep': []}
+# The GCNII layers do not launch theirs one by one: they queue the problems (2 per layer, all of one
+# shape) and the block's exit issues them as ONE grouped split-K launch on the side stream, after the
+# last layer's input-gradient GEMM - a weight-gradient GEMM per layer holds every SM's shared memory for
+# ~25 us and the chain's own GEMM of that layer had to wait for it (35 instead of 22 us per layer).
+_WGRAD = {'stream': None, 'keep': [], 'pending': [], 'ready': None}
 _WGRAD_STREAMS = {}
+_WGRAD_GROUP = os.environ.get('INCAGG_WGRAD_GROUP', '1') != '0'   # (A/B switch)
+
+
+def _flush_weight_grads(side):
+    """Issue the queued GCNII weight-gradient problems: D += alpha * A^T B, 16 per launch."""
+    pend, _WGRAD['pending'] = _WGRAD['pending'], []
+    ready, _WGRAD['ready'] = _WGRAD['ready'], None
+    if not pend:
+        return
+    side.wait_event(ready)
+    with torch.cuda.stream(side):
+        shapes = {}
+        for item in pend:   # (A [K, M], B [K, N], D [M, N], alpha)
+            shapes.setdefault((tuple(item[0].shape), tuple(item[1].shape)), []).append(item)
+        # the largest bucket first: it is the one that must be out of the way before the tail begins
+        for items in sorted(shapes.values(), key=lambda it: -len(it) * it[0][0].numel()):
+            for i in range(0, len(items), 16):
+                chunk = items[i:i + 16]
+                ops.gemm_group([c[0] for c in chunk], [c[1] for c in chunk], [c[2] for c in chunk],
+                               [c[3] for c in chunk], trans_a=True, beta=1., ws_slot=1)
+    _WGRAD['keep'].append(pend)
 
 
 @contextlib.contextmanager
@@ -141,8 +173,10 @@ def weight_grads_on_side_stream(device):
     _WGRAD['stream'] = side
     try:
         yield
+        _flush_weight_grads(side)
     finally:
         _WGRAD['stream'] = None
+        _WGRAD['pending'], _WGRAD['ready'] = [], None
         torch.cuda.current_stream(device).wait_stream(side)
         _WGRAD['keep'].clear()
 
@@ -240,6 +274,13 @@ class _GCN2Dense(torch.autograd.Function):
             out = out[:ctx.rows]
             g = torch.ops.aten.threshold_backward(g, out, 0.)  # ReLU backward, one kernel
         gh = gx0 = gw1 = gw2 = None
+        g_ready = None
+        if _WGRAD['stream'] is not None and _WGRAD_GROUP and not ctx.shared:
+            # the grouped weight-gradient launch may start as soon as the LAST layer's g exists: it then
+            # runs beside that layer's input-gradient GEMM and transposed SpMM and is out of the way when
+            # the bandwidth-bound tail of the backward pass (first Linear) begins
+            g_ready = torch.cuda.Event()
+            g_ready.record(torch.cuda.current_stream(g.device))
         if ctx.shared:
             # out = (1-b) s + b s W1 ;  ds = (1-b) g + b g W1^T ; dh = (1-a) ds ; dx0 = a ds
             ds = ops.gemm(g, w1, trans_b=True, alpha=b, cin=g, beta=1. - b)
@@ -261,7 +302,12 @@ class _GCN2Dense(torch.autograd.Function):
             b1, b2 = _grad_buffer(ctx.w1_param), _grad_buffer(ctx.w2_param)
             if b1 is not None and b2 is not None:         # accumulate into the flat gradient buffers
                 side = _WGRAD['stream']
-                if side is not None:
+                if side is not None and _WGRAD_GROUP:
+                    # queued: one grouped launch for all layers when the backward pass has been issued
+                    _WGRAD['pending'].append((h, g, b1, b * (1. - a)))
+                    _WGRAD['pending'].append((x0, g, b2, b * a))
+                    _WGRAD['ready'] = g_ready
+                elif side is not None:
                     side.wait_stream(torch.cuda.current_stream(g.device))
                     with torch.cuda.stream(side):
                         ops.gemm_dual("m", h, g, a2=x0, trans_a=True, alpha=b * (1. - a), alpha2=b * a,

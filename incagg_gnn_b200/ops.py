@@ -336,6 +336,34 @@ def gemm_dual(mode: str, a: Tensor, b: Tensor, a2: Optional[Tensor] = None, b2: 
     return (out, out2) if mode in ("n", "m") else out
 
 
+def gemm_group(a_list, b_list, outs, alphas, trans_a: bool = False, trans_b: bool = False, beta: float = 0.0,
+               ws_slot: int = 0) -> None:
+    """outs[g] = alphas[g] * op(a_list[g]) @ op(b_list[g]) + beta * outs[g] for <= 16 problems of one shape,
+    ONE launch (include/incagg_b200.h, incagg_gemm_tf32x3_group); split-K for long reductions."""
+    import ctypes
+    n = len(a_list)
+    assert 1 <= n <= 16 and len(b_list) == n and len(outs) == n and len(alphas) == n
+    _require_cuda(*a_list, *b_list, *outs)
+    a_list = [_rowmajor(t) for t in a_list]
+    b_list = [_rowmajor(t) for t in b_list]
+    a, b = a_list[0], b_list[0]
+    M, K = (a.size(1), a.size(0)) if trans_a else (a.size(0), a.size(1))
+    N = b.size(0) if trans_b else b.size(1)
+    for t, u, o in zip(a_list, b_list, outs):
+        assert t.shape == a.shape and u.shape == b.shape and tuple(o.shape) == (M, N)
+        assert o.dtype == torch.float32 and o.stride(1) == 1
+    PtrArr, LdArr, FArr = ctypes.c_void_p * n, ctypes.c_int64 * n, ctypes.c_float * n
+    ws_bytes = min(lib.incagg_gemm_workspace_bytes(M * n, N, K), 1 << 28)
+    ws = _gemm_workspace(a.device, ws_bytes, ws_slot)
+    LAUNCHES["calls"] += 1
+    check(lib.incagg_gemm_tf32x3_group(
+        n, int(trans_a), int(trans_b), M, N, K,
+        PtrArr(*[t.data_ptr() for t in a_list]), LdArr(*[_ld(t) for t in a_list]),
+        PtrArr(*[t.data_ptr() for t in b_list]), LdArr(*[_ld(t) for t in b_list]),
+        FArr(*[float(x) for x in alphas]), float(beta),
+        PtrArr(*[t.data_ptr() for t in outs]), LdArr(*[_ld(t) for t in outs]), ptr(ws), ws.numel(), _stream()))
+
+
 def relu_bwd_colsum(g: Tensor, y: Optional[Tensor] = None, add: Optional[Tensor] = None,
                     colsum_into: Optional[Tensor] = None):
     """((g [+ add on its first rows]) * (y > 0), its column sums) in one pass; y=None: no mask.  float4 path

@@ -197,6 +197,19 @@ int incagg_gemm_tf32x3_dual(int mode, int transA, int transB, int64_t M, int64_t
                             float* D2, int64_t ldd2, void* workspace, size_t workspace_bytes,
                             incagg_stream_t stream);
 
+/*
+ * `count` (<= 16) independent GEMMs of ONE shape in one launch:  D[g] = alpha[g] * op(A[g]) op(B[g]) + beta * D[g]
+ * (A, lda, B, ldb, alpha, D, ldd: HOST arrays of `count` entries; the operands are device pointers).  The
+ * weight gradients of all GCNII layers of a step, [h_l | x_0]^T g_l (2 L problems of 128 x 128 x B,
+ * GCN2Conv's two weights per layer, gcn2.py:121), are one split-K launch beside the end of the backward
+ * pass instead of L launches that compete with its chain for the SMs.
+ */
+int incagg_gemm_tf32x3_group(int count, int transA, int transB, int64_t M, int64_t N, int64_t K,
+                             const float* const* A, const int64_t* lda, const float* const* B,
+                             const int64_t* ldb, const float* alpha, float beta, float* const* D,
+                             const int64_t* ldd, void* workspace, size_t workspace_bytes,
+                             incagg_stream_t stream);
+
 /* ---- small fused kernels of the training step ------------------------------ */
 /*
  * ReLU backward fused with the bias gradient of the Linear in front of it (gcn2.py:87 lins[0]):

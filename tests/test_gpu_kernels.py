@@ -397,6 +397,31 @@ def test_gemm_dual_modes(ops, cuda):
         assert rel(gw2, c2 * d(xx).t() @ d(gg)) <= RTOL
 
 
+@pytest.mark.parametrize("G,rows,M,N", [(10, 16384, 128, 128), (3, 300, 128, 100), (16, 5000, 64, 47), (1, 70000, 100, 128)])
+def test_gemm_group_accumulates_every_problem(ops, cuda, G, rows, M, N):
+    """incagg_gemm_tf32x3_group: G problems D[g] += alpha[g] A[g]^T B[g] in one launch (the weight gradients
+    of all GCNII layers), with and without split-K, ragged tiles, strided destinations."""
+    g = torch.Generator().manual_seed(G * 31 + rows)
+    d = lambda t: t.double()
+    As = [torch.randn(rows, M, generator=g).to(cuda) for _ in range(G)]
+    Bs = [torch.randn(rows, N, generator=g).to(cuda) for _ in range(G)]
+    flat = torch.randn(G, M, N + 4, generator=g).to(cuda)
+    outs = [flat[i, :, :N] for i in range(G)]
+    old = [o.clone() for o in outs]
+    alphas = [0.1 * (i + 1) for i in range(G)]
+    ops.gemm_group(As, Bs, outs, alphas, trans_a=True, beta=1.0)
+    for i in range(G):
+        ref = d(old[i]) + alphas[i] * d(As[i]).t() @ d(Bs[i])
+        assert float((d(outs[i]) - ref).abs().max() / ref.abs().max()) <= RTOL, i
+    keep = flat[:, :, N:].clone()
+    ops.gemm_group(As, Bs, outs, alphas, trans_a=True, beta=0.0)
+    for i in range(G):
+        ref = alphas[i] * d(As[i]).t() @ d(Bs[i])
+        assert float((d(outs[i]) - ref).abs().max() / ref.abs().max()) <= RTOL, i
+    assert torch.equal(flat[:, :, N:], keep)       # the columns beside the destinations are untouched
+    ops.check_device_errors()
+
+
 @pytest.mark.parametrize("M,C,N", [(700, 128, 128), (333, 128, 100), (20000, 96, 47), (260, 64, 192)])
 def test_gemm_dual_n_accumulates_second_output(ops, cuda, M, C, N):
     """N-concatenated pair with acc2: D2 += alpha2 A (s2 B2) + beta2 Cin2 (the x_0 gradient of the GCNII
