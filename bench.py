@@ -198,6 +198,12 @@ def timed_steps_graphed(run, mode, warmup, steps, dist):
     rp_host, ptr = loader._rowptr_host, loader.ptr
     groups = loader._batches_of_epoch()
     tr.warmup(groups[0])
+    # kernels of this library per step, counted on one eager step after the warm-up (a graph replay
+    # re-launches exactly the captured kernels, which the host-side counter cannot see)
+    from incagg_gnn_b200 import _lib
+    l0 = _lib.launch_count()
+    tr.warmup(groups[0], steps=1)
+    timed_steps_graphed.launches_per_step = _lib.launch_count() - l0
     t0 = time.perf_counter()
     if loader.fixed_batches:
         for ids in groups:
@@ -467,13 +473,8 @@ def main():
         sec, edges, _, _, wall = timed_steps(run, args.mode, args.warmup, args.steps, dist)
         launches = _lib.launch_count() - l0
     else:
-        # kernels of this library per step, counted on one eager step (a graph replay re-launches
-        # exactly the captured kernels, which the host-side counter cannot see)
-        l0 = _lib.launch_count()
-        timed_steps(run, args.mode, 0, 1, dist)
-        per_step = _lib.launch_count() - l0
         sec, edges, _, _, wall, n_graphs, t_cap = timed_steps_graphed(run, args.mode, args.warmup, args.steps, dist)
-        launches = per_step * args.steps
+        launches = timed_steps_graphed.launches_per_step * args.steps   # counted on one eager step, see there
         # (shuffled multi-partition groups never repeat: GraphedTrainer issues those steps eagerly)
         graphs = {"captured": n_graphs, "capture_s": round(t_cap, 2)} if n_graphs else None
     clocks = sampler.stop() if rank == 0 else None
