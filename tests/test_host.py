@@ -255,3 +255,35 @@ def test_bench_cpu_baseline_accepts_sharded_history_tables():
     full = bench.full_table(hist[0], data.num_nodes)
     assert full.shape == (data.num_nodes, H) and torch.equal(full[shard.lo:shard.hi], hist[0].emb)
     assert float(full[:shard.lo].abs().sum()) == 0.
+
+
+def test_x0_grad_sink_join_adds_the_collected_gradient():
+    """nn.X0GradSink.join (pure autograd, no kernel): the buffer the layers filled is added to the head
+    rows of the gradient that reaches x_0, once, and the sink is emptied."""
+    import torch
+    from incagg_gnn_b200.nn import X0GradSink
+    torch.manual_seed(0)
+    x = torch.randn(7, 4, requires_grad=True)
+    sink = X0GradSink()
+    y = sink.join(x * 2.0)
+    sink.buf = torch.ones(3, 4)          # what the layers' GEMM epilogues would have accumulated (B = 3)
+    (y * torch.arange(7.).view(7, 1)).sum().backward()
+    want = torch.arange(7.).view(7, 1).expand(7, 4).clone()
+    want[:3] += 1.0
+    assert torch.equal(x.grad, 2.0 * want)
+    assert sink.buf is None
+    # no contribution collected: the gradient passes through unchanged
+    x2 = torch.randn(5, 4, requires_grad=True)
+    X0GradSink().join(x2).sum().backward()
+    assert torch.equal(x2.grad, torch.ones(5, 4))
+
+
+def test_colsum_supported_layouts():
+    import torch
+    from incagg_gnn_b200 import ops
+    assert ops.colsum_supported(torch.zeros(10, 128))
+    assert ops.colsum_supported(torch.zeros(10, 47))            # scalar columns (<= 256)
+    assert ops.colsum_supported(torch.zeros(10, 64)[:, 1:48])   # unaligned strided view
+    assert not ops.colsum_supported(torch.zeros(10, 300)[:, :299])
+    assert not ops.colsum_supported(torch.zeros(10, 128).double())
+    assert not ops.colsum_supported(torch.zeros(128, 10).t())   # column-major
