@@ -9,7 +9,7 @@ from torch.nn import ModuleList, BatchNorm1d
 
 from ..nn import GCN2Conv, Linear, X0GradSink
 from ..sparse import SparseTensor, spmm_delta
-from .base import ScalableGNN
+from .base import ScalableGNN, _PULL_PRIORITY
 from ._masking import select_edges
 
 
@@ -85,14 +85,20 @@ class GCN2(ScalableGNN):
         batch_size, n_id, offset, count = (list(args) + [None] * 4)[:4]
         if self.drop_input:
             x = F.dropout(x, p=self.dropout, training=self.training)
+        fuse = self._fuse_relu  # no batch norm / residual: ReLU rides in the GEMM epilogue
+        # The halo pulls depend on nothing this step computes: issued before the first Linear, they run
+        # beside it (87 K x 100 -> 128, alone on the GPU for 50 us) instead of beside the first two layers,
+        # whose SpMM / GEMM they slowed by a fifth.
+        ahead = None
+        if use_aggregation and fuse:
+            ahead = self.pull_ahead(self.histories[:self.num_layers - 1], x, batch_size, n_id,
+                                    width=self.hidden_channels)
         x_0, sink = self._first_linear(x)
         x = F.dropout(x_0, p=self.dropout, training=self.training)
         t_all = 0
-        fuse = self._fuse_relu  # no batch norm / residual: ReLU rides in the GEMM epilogue
         x0b = x_0[:adj_t.size(0)]
         if use_aggregation:
             adj_t = select_edges(adj_t, batch_size, aggregate_combined)
-            ahead = self.pull_ahead(self.histories[:self.num_layers - 1], x, batch_size, n_id) if fuse else None
             for i, (conv, hist) in enumerate(zip(self.convs[:-1], self.histories)):
                 # rows >= B of x are constants (pulled history) after the first push_and_pull
                 if ahead is not None:
@@ -106,7 +112,7 @@ class GCN2(ScalableGNN):
                     # the table rows it writes: it rides on the pull stream, joined after the loop
                     main, side = torch.cuda.current_stream(), self._pull_stream
                     if side is None:
-                        side = self._pull_stream = torch.cuda.Stream(x.device)
+                        side = self._pull_stream = torch.cuda.Stream(x.device, priority=_PULL_PRIORITY)
                     side.wait_stream(main)
                     with torch.cuda.stream(side):
                         hist.push(x[:batch_size].detach(), n_id[:batch_size], offset, count)
